@@ -1,0 +1,142 @@
+"""CPU: the oracle (C + numpy restatements) against fixtures produced by the reference's own
+functions (oracle/gen_golden.py).  This is what pins the oracle before it is trusted as the
+checker of the CUDA kernels."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import np_ops
+from conftest import knn_rank_check
+
+
+@pytest.mark.parametrize("name", ["knn_q3", "knn_q64"])
+def test_knn_quantised_exact(golden, name):
+    """Grid-quantised inputs: every fp32 evaluation order agrees, ties are real -> strict equality with
+    the stable (lowest-index) ranking of the reference's pd matrix, and value-wise equality with topk."""
+    g = golden(name)
+    x, k, pd = g["x"], int(g["k"]), g["pd"]
+    idx, pdo = oracle.knn(x, k, return_pd=True)
+    stable = np.argsort(-pd, axis=2, kind="stable")[:, :, :k]
+    assert np.array_equal(idx, stable)
+    # same ranked VALUES as the reference's own topk output (tie-invariant statement)
+    assert np.array_equal(np.take_along_axis(pd, idx, 2), np.take_along_axis(pd, g["idx"], 2))
+    assert np.array_equal(pdo, np.take_along_axis(pd, idx, 2))
+    # self is the nearest neighbour
+    assert (np.take_along_axis(pd, idx[:, :, :1], 2)[..., 0] == pd.max(axis=2)).all()
+
+
+@pytest.mark.parametrize("name", ["knn_c3", "knn_c64", "knn_c128_k40"])
+def test_knn_continuous_certified(golden, name):
+    g = golden(name)
+    x, k = g["x"], int(g["k"])
+    idx = oracle.knn(x, k)
+    bad, unc = knn_rank_check(x, idx, k)
+    assert unc == 0, f"{unc} uncertified mismatches"
+    bad_ref, unc_ref = knn_rank_check(x, g["idx"], k)
+    assert unc_ref == 0
+    # the oracle is no further from fp64 truth than the reference's own sgemm is (plus slack)
+    assert bad <= bad_ref + max(4, idx.size // 20000), (bad, bad_ref)
+    # and it agrees with the reference everywhere except such near-ties
+    assert (idx != g["idx"]).sum() <= bad + bad_ref
+
+
+@pytest.mark.parametrize("name", ["ggf_3", "ggf_16"])
+def test_edge_gather(golden, name):
+    g = golden(name)
+    out = oracle.edge_gather(g["x"], g["idx"])                       # (B,N,k,2C)
+    assert np.array_equal(out.transpose(0, 3, 1, 2), g["out"])
+    assert bool(g["same_as_default"])
+
+
+def test_edge_gather_bwd(golden):
+    g = golden("ggf_bwd")
+    C = g["x"].shape[1]
+    gcl = np.ascontiguousarray(g["g"].transpose(0, 2, 3, 1))           # (B,2C,N,k) -> (B,N,k,2C)
+    gx = oracle.edge_gather_bwd(gcl, g["idx"], C)
+    np.testing.assert_allclose(gx, g["grad_x"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["fps", "fps_q_full"])
+def test_fps(golden, name):
+    g = golden(name)
+    cen, vals = oracle.fps(g["xyz"], int(g["npoint"]), g["centroids"][:, 0])
+    assert np.array_equal(cen, g["centroids"])
+    assert np.array_equal(vals, g["vals"])
+
+
+def test_regions(golden):
+    g = golden("regions")
+    assert np.array_equal(np_ops.assign_region_to_point(g["X"]), g["Y"])
+    np.testing.assert_allclose(np_ops.region_mean(3), g["lookup"], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("name,mode", [("deform_voxels_s1", "volume_based_voxels"),
+                                       ("deform_voxels_s7", "volume_based_voxels"),
+                                       ("deform_voxels_sparse", "volume_based_voxels"),
+                                       ("deform_radius", "volume_based_radius")])
+def test_deform_input(golden, name, mode):
+    g = golden(name)
+    X = g["X0"].copy()
+    np.random.seed(int(g["seed"]))
+    Xd, mask = np_ops.deform_input(X, np_ops.region_mean(3), mode)
+    assert np.array_equal(mask, g["mask"])
+    assert np.array_equal(Xd, g["X"])
+
+
+def test_chamfer(golden):
+    g = golden("chamfer")
+    loss, grad = oracle.reconstruction_loss(g["pred"], g["gold"], g["mask"])
+    assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    np.testing.assert_allclose(grad, g["grad"], rtol=1e-5, atol=1e-7)
+    gold_bnc = g["gold"].transpose(0, 2, 1)
+    m = g["mask"][:, 0, :]
+    _, _, a1 = oracle.chamfer_dir(g["pred"], gold_bnc, m)
+    _, _, a2 = oracle.chamfer_dir(gold_bnc, g["pred"], m)
+    assert (a1 != g["idx_pred_gold"]).mean() < 1e-3
+    assert (a2 != g["idx_gold_pred"]).mean() < 1e-3
+
+
+def test_chamfer_far_and_empty(golden):
+    g = golden("chamfer_far")
+    loss, grad = oracle.reconstruction_loss(g["pred"], g["gold"], g["mask"])
+    assert abs(loss - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    np.testing.assert_allclose(grad, g["grad"], rtol=1e-5, atol=1e-7)
+    loss, _ = oracle.reconstruction_loss(g["pred"], g["gold"], np.zeros_like(g["mask"]))
+    assert np.isnan(loss) and np.isnan(float(golden("chamfer_empty")["loss"]))
+
+
+def test_density_labels_arithmetic():
+    cnt = np.array([[0, 1, 2, 3, 29, 30, 31, 100]])
+    soft, row = np_ops.density_labels(cnt, 16, pergroup=2, shift=0)
+    assert row.tolist() == [[0, 1, 2, 3, 29, 30, 30, 30]]
+    assert soft[0, 1, 0] == 0.5 and soft[0, 1, 1] == 0.5 and soft[0, 2, 1] == 1.0
+    assert np.allclose(soft.sum(-1), 1.0)
+    soft, row = np_ops.density_labels(cnt, 16, pergroup=5, shift=10)
+    assert row.tolist() == [[0, 0, 0, 0, 19, 20, 21, 75]]
+
+
+def test_density_count_semantics():
+    """Restated pcl semantics: strict radius, K cap, neighbour index 0 dropped (mlsp.py:252-254)."""
+    rng = np.random.default_rng(0)
+    P = rng.uniform(-0.3, 0.3, (1, 300, 3)).astype(np.float32)
+    r = 0.13
+    cnt = oracle.density_count(P, r, K=100)[0]
+    d = ((P[0][:, None, :].astype(np.float64) - P[0][None]) ** 2).sum(-1)
+    full = (d < r * r).sum(1)
+    in0 = d[:, 0] < r * r
+    expect = np.minimum(full, 100) - in0
+    near = np.abs(d - r * r).min(1) < 1e-6          # fp32-vs-fp64 boundary cases excluded
+    assert np.array_equal(cnt[~near & (full <= 100)], expect[~near & (full <= 100)])
+    assert cnt[0] == min(full[0], 100) - 1          # point 0 always drops itself
+    cntK = oracle.density_count(P, 0.5, K=10)[0]
+    assert cntK.max() <= 10 and cntK.min() >= 9
+
+
+def test_normals_plane():
+    rng = np.random.default_rng(1)
+    P = np.zeros((1, 400, 3), np.float32)
+    P[0, :, :2] = rng.uniform(-1, 1, (400, 2))
+    P[0, :, 2] = 0.25
+    n = np_ops.pca_normals(P, 10)
+    assert np.allclose(np.abs(n[0, :, 2]), 1.0, atol=1e-9)
+    assert (n[0, :, 2] < 0).all()                   # flipped towards the origin: n.p <= 0
