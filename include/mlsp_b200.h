@@ -1,0 +1,145 @@
+/*
+ * mlsp_b200.h -- C ABI of libmlsp_b200.so: the B200 (sm_100a) implementation of the MLSP
+ * data-parallel hot path (DGCNN neighbourhood engine, masked-local-structure target builder,
+ * masked Chamfer loss).
+ *
+ * The reference (VITA-Group/MLSP) is pure Python/PyTorch and has no FFI; its boundary is the set
+ * of module-level Python functions named below.  Each entry point cites the
+ * reference function it replaces (file:line in the reference checkout).  The Python host side
+ * (mlsp_b200/ops.py) keeps the reference signatures and calls these through ctypes; see
+ * INTEGRATION.md for the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked "host";
+ *   - tensors are dense, row-major, in the layouts written next to each argument;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued, nothing synchronises;
+ *   - outputs and workspaces are caller-allocated (mlsp_workspace_bytes gives the size);
+ *   - return value: 0 on success, otherwise an MLSP_E* code; mlsp_last_error() (thread-local)
+ *     describes it.  There is no CPU fallback: without a CUDA device every call fails.
+ *   - indices are int64 at the boundary (the reference returns torch.long);
+ *   - inputs must be finite (the reference's NaN behaviour is not reproduced).
+ */
+#ifndef MLSP_B200_H
+#define MLSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MLSP_API __attribute__((visibility("default")))
+#else
+#define MLSP_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLSP_OK 0
+#define MLSP_EINVAL 1      /* bad shape / null pointer / k out of range            */
+#define MLSP_EUNSUPPORTED 2 /* shape outside what the kernels are built for        */
+#define MLSP_ECUDA 3       /* a CUDA runtime call or launch failed                  */
+#define MLSP_EWORKSPACE 4  /* workspace too small                                   */
+
+/* operation ids for mlsp_workspace_bytes */
+#define MLSP_OP_KNN 1
+#define MLSP_OP_EDGE_FWD 2
+#define MLSP_OP_EDGE_BWD 3
+#define MLSP_OP_CHAMFER 4
+
+/* flags for mlsp_knn_f32 */
+#define MLSP_KNN_AUTO 0        /* tensor-core filter + exact re-rank when C allows, else exact   */
+#define MLSP_KNN_EXACT_ONLY 1  /* force the fp32 CUDA-core kernel                                 */
+#define MLSP_KNN_TENSOR_ONLY 2 /* force the tcgen05 path (error if the shape does not allow it)  */
+
+MLSP_API int mlsp_version(void);
+MLSP_API const char *mlsp_last_error(void);
+MLSP_API size_t mlsp_workspace_bytes(int op, int B, int C, int N, int k);
+
+/* a1 -- knn(x, k): PointDA/model_utils.py:9-16 == PointSegDA/Models.py:8-15.
+ *   pd[i][j] = ((-|x_j|^2) - (-2 x_i.x_j)) - |x_i|^2 in fp32; the k largest per row, best first,
+ *   ties broken by lowest index.  x (B,C,N); idx (B,N,k) int64. 1 <= k <= min(N,64). */
+MLSP_API int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
+                 int flags, void *stream);
+
+/* a2 -- get_graph_feature(x, args, k, idx): PointDA/model_utils.py:18-42 == PointSegDA/Models.py:18-45.
+ *   out logical shape (B,2C,N,k) stored channels-last, i.e. memory order [B][N][k][2C]:
+ *   out[b][i][j][c] = x[b][c][idx[b][i][j]] - x[b][c][i] (c < C),  x[b][c-C][i] (c >= C). */
+MLSP_API int mlsp_edge_gather_fwd(const float *x, const int64_t *idx, int B, int C, int N, int k, float *out,
+                         void *ws, size_t ws_bytes, void *stream);
+
+/* backward of a2 w.r.t. x (the reference gets it from autograd: index_put_(accumulate=True)).
+ *   grad_out in the same channels-last storage [B][N][k][2C]; grad_x (B,C,N), overwritten. */
+MLSP_API int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, int B, int C, int N, int k,
+                         float *grad_x, void *ws, size_t ws_bytes, void *stream);
+
+/* a3 -- farthest_point_sample(args, xyz, npoint): utils/pc_utils.py:137-161.
+ *   xyz (B,3,N); start (B) int64 = the torch.randint draw of :150 (made by the host so the CPU RNG
+ *   stream stays the reference's); centroids (B,npoint) int64; vals (B,3,npoint). */
+MLSP_API int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
+             float *vals, void *stream);
+
+/* a4 -- assign_region_to_point (utils/pc_utils.py:33-73) + the per-region counts and the first-fit
+ *   region choice of deform_input (MLSP/mlsp.py:28-50, groups=1).
+ *   X (B,C,N), C >= 3; order = host pointer to the 27 region ids of np.random.permutation(27);
+ *   region (B,N) int64; counts (B,27) int32; chosen (B) int32 (-1: no region reaches min_pts);
+ *   nsel (B) int32 = points in the chosen region. */
+MLSP_API int mlsp_region_assign_select(const float *X, int B, int C, int N, const int32_t *order_host, int min_pts,
+                              int64_t *region, int32_t *counts, int32_t *chosen, int32_t *nsel,
+                              void *stream);
+
+/* a4/a8 -- the in-place deformation + mask of deform_input (MLSP/mlsp.py:44-48).
+ *   The r-th point (ascending index) of cloud b's chosen region receives noise[(offset[b]+r)*3 + c]
+ *   (the host's np.random.multivariate_normal draws); mask (B,C,N) is fully written:
+ *   1 on channels 0..2 of selected points, 0 elsewhere.  noise may be NULL (mask only). */
+MLSP_API int mlsp_region_mask_scatter(float *X, int B, int C, int N, const int64_t *region, const int32_t *chosen,
+                             const float *noise, const int32_t *offset, float *mask, void *stream);
+
+/* a5 -- collapse_to_point (utils/pc_utils.py:76-111), part 1: per point, the number of points with
+ *   pd = (|x_j|^2 - 2 x_i.x_j) + |x_i|^2 <= r2 (`pts_pass` before thresholding).  x (B,C>=3,N). */
+MLSP_API int mlsp_ball_count(const float *x, int B, int C, int N, float r2, int32_t *cnt, void *stream);
+
+/* a5 part 2: collapse the ball of `centre[b]` (host-chosen by np.random.choice, pc_utils.py:102):
+ *   in-ball points (ascending index) receive the noise rows, mask as in mlsp_region_mask_scatter.
+ *   centre[b] < 0 leaves the cloud untouched. */
+MLSP_API int mlsp_ball_mask_scatter(float *X, int B, int C, int N, float r2, const int32_t *centre, const float *noise,
+                           const int32_t *offset, float *mask, void *stream);
+
+/* a6 -- cal_density (MLSP/mlsp.py:240-272): per-point ball cardinality with the python-pcl radius-search
+ *   semantics (strict < r2, at most K nearest, neighbour index 0 dropped) and the soft class labels.
+ *   pts (B,N,3); labels (B,N,num_cls) float32; row (B,N) int64 = clip(count-shift, 0, (num_cls-1)*pergroup). */
+MLSP_API int mlsp_ball_count_labels(const float *pts, int B, int N, float r2, int K, int shift, int pergroup,
+                           int num_cls, float *labels, int64_t *row, void *stream);
+
+/* a7 -- kSearchNormalEstimation (PointDA/trainer.py:173-188, PointSegDA/trainer.py:73-88; python-pcl):
+ *   unit eigenvector of the smallest eigenvalue of the covariance of the k nearest neighbours (idx from
+ *   mlsp_knn_f32 on the same cloud, self included), oriented towards the origin (n.p <= 0).
+ *   pts (B,N,3); idx (B,N,k) int64; normals (B,N,3). */
+MLSP_API int mlsp_pca_normals(const float *pts, const int64_t *idx, int B, int N, int k, float *normals, void *stream);
+
+/* a9/a10 -- chamfer_distance(p1,p2,mask) MLSP/mlsp.py:115-153 and findneareat_index :196-220, one direction.
+ *   D[i][j] = (|p1_i - p2_j|_2)^2 + (mask_j == 0 ? 100 : 0); rowmin/argmin over j (lowest j on ties).
+ *   Points are addressed p[b*bstride + i*pstride + c*cstride] so both (B,N,3) and (B,3,N) tensors are
+ *   accepted without a copy; mask[b*mask_bstride + i] is the 0/1 row mask (the reference's mask[:,:,0]).
+ *   all_rows = 0: only rows with mask != 0 are evaluated (the others do not reach the loss; rowmin = 0,
+ *   argmin = -1 there); all_rows = 1: every row (findneareat_index).
+ *   partial (B) float: sum_i rowmin_i*mask_i / sum_i mask_i   (NaN for an empty mask, like the reference). */
+MLSP_API int mlsp_chamfer_dir_fwd(const float *p1, int64_t p1_bstride, int64_t p1_pstride, int64_t p1_cstride,
+                         const float *p2, int64_t p2_bstride, int64_t p2_pstride, int64_t p2_cstride,
+                         const float *mask, int64_t mask_bstride, int B, int N, int all_rows, float *rowmin,
+                         int64_t *argmin, float *partial, void *ws, size_t ws_bytes, void *stream);
+
+/* backward of one direction: for masked rows i with j* = argmin[i],
+ *   g = 2 (p1_i - p2_j*) * scale * grad_partial_sum / count_b ;  grad_p1[i] += g ; grad_p2[j*] -= g.
+ *   grad_p1 / grad_p2 are (B,N,3) contiguous float32 accumulators (either may be NULL);
+ *   scale_dev: device scalar (upstream gradient), scale_host multiplies it (e.g. 1/B). */
+MLSP_API int mlsp_chamfer_dir_bwd(const float *p1, int64_t p1_bstride, int64_t p1_pstride, int64_t p1_cstride,
+                         const float *p2, int64_t p2_bstride, int64_t p2_pstride, int64_t p2_cstride,
+                         const float *mask, int64_t mask_bstride, const int64_t *argmin, int B, int N,
+                         const float *scale_dev, float scale_host, float *grad_p1, float *grad_p2,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLSP_B200_H */

@@ -1,0 +1,228 @@
+// edge.cu -- a2: get_graph_feature(x, args, k, idx) forward and backward
+// (PointDA/model_utils.py:18-42 == PointSegDA/Models.py:18-45).
+//
+// The reference materialises transpose.contiguous -> gather -> repeat -> cat and returns a permuted view
+// whose memory order is [B][N][k][2C] (exactly NCHW channels_last).  Here: one tiled transpose of x to
+// point-major rows xt (B,N,C) (8-16 MB, stays in the 126 MB L2), then a single pass that reads each
+// neighbour row with 128-bit loads and streams the (i,j) rows of the output with 128-bit evict-first
+// stores.  HBM traffic is the algorithmic 4BCN + 8BNk + 8BCNk bytes; the kernel is bandwidth bound.
+// Backward: one pass over grad_out accumulates the centre terms in registers and scatters the
+// neighbour terms with vector float atomics into gxt (B,N,C) in L2, then a transpose back to (B,C,N).
+#include "common.cuh"
+
+namespace mlsp {
+
+size_t edge_workspace_bytes(int B, int C, int N, int k)
+{
+    (void)k;
+    return align_up(sizeof(float) * (size_t)B * C * N, 256);
+}
+
+// (B,R,S) -> (B,S,R), 32x32 tiles through shared memory
+__global__ void transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int R, int S)
+{
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const float *ib = in + (size_t)b * R * S;
+    float *ob = out + (size_t)b * R * S;
+    const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int r = r0 + rr, s = s0 + threadIdx.x;
+        tile[rr][threadIdx.x] = (r < R && s < S) ? ib[(size_t)r * S + s] : 0.0f;
+    }
+    __syncthreads();
+    for (int ss = threadIdx.y; ss < 32; ss += blockDim.y) {
+        const int s = s0 + ss, r = r0 + threadIdx.x;
+        if (r < R && s < S) ob[(size_t)s * R + r] = tile[threadIdx.x][ss];
+    }
+}
+
+static int launch_transpose(const float *in, float *out, int B, int R, int S, cudaStream_t st)
+{
+    dim3 grid((S + 31) / 32, (R + 31) / 32, B);
+    transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(in, out, R, S);
+    MLSP_LAUNCH_CHECK("transpose_kernel");
+    return MLSP_OK;
+}
+
+// ---- forward, C % 4 == 0: one warp per query point, 128-bit lanes over the 2C channels ------------
+// Q4 = C/4 float4 per point row.  Lane l handles float4 slots q = l, l+32, ... of the 2*Q4-wide output row.
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+edge_fwd_vec_kernel(const float4 *__restrict__ xt, const int64_t *__restrict__ idx, int N, int k, int Q4,
+                    float4 *__restrict__ out, long long total_points)
+{
+    const int lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // b*N + i
+    if (p >= total_points) return;
+    const long long b = p / N;
+    const float4 *xtb = xt + b * (long long)N * Q4;
+    const float4 *ctr_row = xt + p * Q4;
+    const int64_t *irow = idx + p * k;
+    float4 *orow = out + p * (long long)k * (2 * Q4);
+    const int W = 2 * Q4;  // float4 per output row
+
+    for (int q = lane; q < W; q += 32) {
+        const bool is_diff = q < Q4;
+        const int qc = is_diff ? q : q - Q4;
+        const float4 ctr = ctr_row[qc];
+        int j = 0;
+        for (; j + UNROLL <= k; j += UNROLL) {
+            float4 nb[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const long long n = is_diff ? irow[j + u] : 0;
+                nb[u] = is_diff ? xtb[n * Q4 + qc] : ctr;
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                float4 o = nb[u];
+                if (is_diff) {
+                    o.x = __fsub_rn(o.x, ctr.x);
+                    o.y = __fsub_rn(o.y, ctr.y);
+                    o.z = __fsub_rn(o.z, ctr.z);
+                    o.w = __fsub_rn(o.w, ctr.w);
+                }
+                st_stream_f4(orow + (long long)(j + u) * W + q, o);
+            }
+        }
+        for (; j < k; ++j) {
+            float4 o = ctr;
+            if (is_diff) {
+                const float4 nb = xtb[(long long)irow[j] * Q4 + qc];
+                o.x = __fsub_rn(nb.x, ctr.x);
+                o.y = __fsub_rn(nb.y, ctr.y);
+                o.z = __fsub_rn(nb.z, ctr.z);
+                o.w = __fsub_rn(nb.w, ctr.w);
+            }
+            st_stream_f4(orow + (long long)j * W + q, o);
+        }
+    }
+}
+
+// ---- forward, any C (used for C = 3): one thread per output element, fully coalesced stores ----------
+__global__ void __launch_bounds__(256)
+edge_fwd_scalar_kernel(const float *__restrict__ xt, const int64_t *__restrict__ idx, int N, int k, int C,
+                       float *__restrict__ out, long long total)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const int W = 2 * C;
+    const long long row = e / W;  // (b*N + i)*k + j
+    const int c = (int)(e - row * W);
+    const long long p = row / k;  // b*N + i
+    const long long b = p / N;
+    float v;
+    if (c < C) {
+        const long long n = idx[row];
+        v = __fsub_rn(xt[(b * N + n) * C + c], xt[p * C + c]);
+    } else {
+        v = xt[p * C + (c - C)];
+    }
+    __stcs(out + e, v);
+}
+
+// ---- backward --------------------------------------------------------------------------------------
+// gxt (B,N,C) zero-initialised.  One warp per query point.
+__global__ void __launch_bounds__(256)
+edge_bwd_vec_kernel(const float4 *__restrict__ g, const int64_t *__restrict__ idx, int N, int k, int Q4,
+                    float4 *__restrict__ gxt, long long total_points)
+{
+    const int lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= total_points) return;
+    const long long b = p / N;
+    float4 *gb = gxt + b * (long long)N * Q4;
+    const int64_t *irow = idx + p * k;
+    const float4 *grow = g + p * (long long)k * (2 * Q4);
+    const int W = 2 * Q4;
+    for (int q = lane; q < Q4; q += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < k; ++j) {
+            const float4 gd = __ldcs(grow + (long long)j * W + q);        // d out / d (nbr - ctr)
+            const float4 gc = __ldcs(grow + (long long)j * W + Q4 + q);   // d out / d ctr copy
+            acc.x += gc.x - gd.x;
+            acc.y += gc.y - gd.y;
+            acc.z += gc.z - gd.z;
+            acc.w += gc.w - gd.w;
+            atomicAdd(gb + (long long)irow[j] * Q4 + q, gd);
+        }
+        atomicAdd(gxt + p * Q4 + q, acc);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+edge_bwd_scalar_kernel(const float *__restrict__ g, const int64_t *__restrict__ idx, int N, int k, int C,
+                       float *__restrict__ gxt, long long total_rows)
+{
+    // one thread per (row, c): row = (b*N+i)*k + j
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_rows * C) return;
+    const long long row = t / C;
+    const int c = (int)(t - row * C);
+    const long long p = row / k;
+    const long long b = p / N;
+    const float gd = g[row * 2 * C + c];
+    const float gc = g[row * 2 * C + C + c];
+    atomicAdd(gxt + (b * N + idx[row]) * C + c, gd);
+    atomicAdd(gxt + p * C + c, gc - gd);
+}
+
+}  // namespace mlsp
+
+extern "C" int mlsp_edge_gather_fwd(const float *x, const int64_t *idx, int B, int C, int N, int k, float *out,
+                                    void *ws, size_t ws_bytes, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(x && idx && out && ws, MLSP_EINVAL, "edge_gather_fwd: null pointer");
+    MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "edge_gather_fwd: bad shape");
+    MLSP_REQUIRE(ws_bytes >= edge_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "edge_gather_fwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    float *xt = static_cast<float *>(ws);
+    int rc = launch_transpose(x, xt, B, C, N, st);  // (B,C,N) -> (B,N,C)
+    if (rc) return rc;
+    const long long points = (long long)B * N;
+    if (C % 4 == 0) {
+        const int warps = 8;
+        const long long blocks = (points + warps - 1) / warps;
+        MLSP_REQUIRE(blocks < (1ll << 31), MLSP_EUNSUPPORTED, "edge_gather_fwd: too many points");
+        edge_fwd_vec_kernel<4><<<(unsigned)blocks, warps * 32, 0, st>>>(
+            reinterpret_cast<const float4 *>(xt), idx, N, k, C / 4, reinterpret_cast<float4 *>(out), points);
+        MLSP_LAUNCH_CHECK("edge_fwd_vec_kernel");
+    } else {
+        const long long total = points * k * 2 * C;
+        const long long blocks = (total + 255) / 256;
+        MLSP_REQUIRE(blocks < (1ll << 31), MLSP_EUNSUPPORTED, "edge_gather_fwd: too many elements");
+        edge_fwd_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(xt, idx, N, k, C, out, total);
+        MLSP_LAUNCH_CHECK("edge_fwd_scalar_kernel");
+    }
+    return MLSP_OK;
+}
+
+extern "C" int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, int B, int C, int N, int k,
+                                    float *grad_x, void *ws, size_t ws_bytes, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(grad_out && idx && grad_x && ws, MLSP_EINVAL, "edge_gather_bwd: null pointer");
+    MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "edge_gather_bwd: bad shape");
+    MLSP_REQUIRE(ws_bytes >= edge_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "edge_gather_bwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    float *gxt = static_cast<float *>(ws);
+    MLSP_CUDA(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)B * C * N, st));
+    const long long points = (long long)B * N;
+    if (C % 4 == 0) {
+        const int warps = 8;
+        const long long blocks = (points + warps - 1) / warps;
+        MLSP_REQUIRE(blocks < (1ll << 31), MLSP_EUNSUPPORTED, "edge_gather_bwd: too many points");
+        edge_bwd_vec_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(
+            reinterpret_cast<const float4 *>(grad_out), idx, N, k, C / 4, reinterpret_cast<float4 *>(gxt), points);
+        MLSP_LAUNCH_CHECK("edge_bwd_vec_kernel");
+    } else {
+        const long long total = points * k * C;
+        const long long blocks = (total + 255) / 256;
+        MLSP_REQUIRE(blocks < (1ll << 31), MLSP_EUNSUPPORTED, "edge_gather_bwd: too many elements");
+        edge_bwd_scalar_kernel<<<(unsigned)blocks, 256, 0, st>>>(grad_out, idx, N, k, C, gxt, points * k);
+        MLSP_LAUNCH_CHECK("edge_bwd_scalar_kernel");
+    }
+    return launch_transpose(gxt, grad_x, B, N, C, st);  // (B,N,C) -> (B,C,N)
+}

@@ -1,0 +1,174 @@
+// knn.cu -- a1: knn(x, k)  (PointDA/model_utils.py:9-16 == PointSegDA/Models.py:8-15)
+//
+// Exact fp32 path on the CUDA cores.  Arithmetic is pinned to oracle/mlsp_oracle.c:orc_knn:
+//   xx_j = sum_c rn(x_cj^2)              (sequential adds, channel order)
+//   dot  = rn(x_0i x_0j), then fmaf chain over c = 1..C-1
+//   pd   = rn( rn(2 dot - xx_j) - xx_i ) == ((-xx_j) - (-2 dot)) - xx_i of the reference
+// and the ranking is (pd descending, index ascending).  Nothing of size (B,N,N) is materialised: a CTA
+// keeps 64 query rows in shared memory, streams candidate tiles through shared memory, and each warp
+// maintains the running top-k of its 8 rows in registers (topk.cuh), so the HBM traffic is the
+// algorithmic 4BCN + 8BNk bytes plus L2-resident re-reads of the cloud.
+#include "common.cuh"
+#include "topk.cuh"
+
+namespace mlsp {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_R = 8;                                  // query rows per warp
+constexpr int KNN_ROWS = (KNN_THREADS / 32) * KNN_R;      // 64 query rows per CTA
+constexpr int KNN_TJ = 128;                               // candidates per tile (4 per lane)
+constexpr int KNN_CK = 16;                                // channels per shared-memory chunk
+constexpr size_t KNN_WS_HEADER = 256;                     // stats live in the first bytes of the workspace
+
+size_t knn_workspace_bytes(int B, int C, int N, int k)
+{
+    (void)C;
+    (void)k;
+    return KNN_WS_HEADER + align_up(sizeof(float) * (size_t)B * N, 256);
+}
+
+__global__ void sq_norms_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xx)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= N) return;
+    const float *xb = x + (size_t)b * C * N;
+    float v = xb[j];
+    float s = __fmul_rn(v, v);
+    for (int c = 1; c < C; ++c) {
+        v = xb[(size_t)c * N + j];
+        s = __fadd_rn(s, __fmul_rn(v, v));
+    }
+    xx[(size_t)b * N + j] = s;
+}
+
+template <int KSLOTS>
+__global__ void __launch_bounds__(KNN_THREADS, 2)
+knn_exact_kernel(const float *__restrict__ x, const float *__restrict__ xx, int C, int N, int k,
+                 int64_t *__restrict__ idx)
+{
+    extern __shared__ __align__(16) float smem[];
+    float *rows_s = smem;                              // [C][KNN_ROWS]
+    float *cand_s = rows_s + (size_t)C * KNN_ROWS;     // [KNN_CK][KNN_TJ]
+    float *cn_s = cand_s + KNN_CK * KNN_TJ;            // [KNN_TJ] candidate norms
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int i0 = blockIdx.x * KNN_ROWS;
+    const float *xb = x + (size_t)b * C * N;
+    const float *xxb = xx + (size_t)b * N;
+
+    for (int e = tid; e < C * KNN_ROWS; e += KNN_THREADS) {
+        const int c = e / KNN_ROWS, r = e % KNN_ROWS;
+        const int i = i0 + r;
+        rows_s[e] = (i < N) ? xb[(size_t)c * N + i] : 0.0f;
+    }
+    float xxi[KNN_R];
+#pragma unroll
+    for (int rr = 0; rr < KNN_R; ++rr) {
+        const int i = i0 + warp * KNN_R + rr;
+        xxi[rr] = (i < N) ? xxb[i] : 0.0f;
+    }
+    TopK<KSLOTS> top[KNN_R];
+#pragma unroll
+    for (int rr = 0; rr < KNN_R; ++rr) top[rr].init(k);
+
+    for (int j0 = 0; j0 < N; j0 += KNN_TJ) {
+        float acc[KNN_R][4];
+        for (int c0 = 0; c0 < C; c0 += KNN_CK) {
+            __syncthreads();  // previous chunk (and, first time, rows_s) settled
+            for (int e = tid; e < KNN_CK * KNN_TJ; e += KNN_THREADS) {
+                const int cc = e / KNN_TJ, jj = e % KNN_TJ;
+                const int c = c0 + cc, j = j0 + jj;
+                cand_s[e] = (c < C && j < N) ? xb[(size_t)c * N + j] : 0.0f;
+            }
+            if (c0 == 0 && tid < KNN_TJ) cn_s[tid] = (j0 + tid < N) ? xxb[j0 + tid] : 0.0f;
+            __syncthreads();
+#pragma unroll
+            for (int cc = 0; cc < KNN_CK; ++cc) {
+                const int c = c0 + cc;
+                if (c < C) {
+                    const float4 ra = *reinterpret_cast<const float4 *>(&rows_s[c * KNN_ROWS + warp * KNN_R]);
+                    const float4 rb = *reinterpret_cast<const float4 *>(&rows_s[c * KNN_ROWS + warp * KNN_R + 4]);
+                    const float rv[KNN_R] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                    float cv[4];
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) cv[s] = cand_s[cc * KNN_TJ + s * 32 + lane];
+                    if (c == 0) {
+#pragma unroll
+                        for (int rr = 0; rr < KNN_R; ++rr)
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) acc[rr][s] = __fmul_rn(rv[rr], cv[s]);
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < KNN_R; ++rr)
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) acc[rr][s] = __fmaf_rn(rv[rr], cv[s], acc[rr][s]);
+                    }
+                }
+            }
+        }
+        float cn[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) cn[s] = cn_s[s * 32 + lane];
+#pragma unroll
+        for (int rr = 0; rr < KNN_R; ++rr) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int j = j0 + s * 32 + lane;
+                const float t = __fmaf_rn(2.0f, acc[rr][s], -cn[s]);
+                const float pd = __fsub_rn(t, xxi[rr]);
+                top[rr].offer(pd, j, j < N);
+            }
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < KNN_R; ++rr) {
+        const int i = i0 + warp * KNN_R + rr;
+        top[rr].finish(k);
+        if (i < N) {
+#pragma unroll
+            for (int s = 0; s < KSLOTS; ++s) {
+                const int e = s * 32 + lane;
+                if (e < k) idx[((size_t)b * N + i) * k + e] = (int64_t)top[rr].j[s];
+            }
+        }
+    }
+}
+
+static int launch_exact(const float *x, const float *xx, int B, int C, int N, int k, int64_t *idx,
+                        cudaStream_t st)
+{
+    const size_t smem = sizeof(float) * ((size_t)C * KNN_ROWS + KNN_CK * KNN_TJ + KNN_TJ);
+    MLSP_REQUIRE(smem <= 200 * 1024, MLSP_EUNSUPPORTED, "knn: C=%d too large for the exact kernel", C);
+    dim3 grid((N + KNN_ROWS - 1) / KNN_ROWS, B);
+    if (k <= 32) {
+        MLSP_CUDA(cudaFuncSetAttribute(knn_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_exact_kernel<1><<<grid, KNN_THREADS, smem, st>>>(x, xx, C, N, k, idx);
+    } else {
+        MLSP_CUDA(cudaFuncSetAttribute(knn_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn_exact_kernel<2><<<grid, KNN_THREADS, smem, st>>>(x, xx, C, N, k, idx);
+    }
+    MLSP_LAUNCH_CHECK("knn_exact_kernel");
+    return MLSP_OK;
+}
+
+}  // namespace mlsp
+
+extern "C" int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
+                            int flags, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(x && idx && ws, MLSP_EINVAL, "knn: null pointer");
+    MLSP_REQUIRE(B > 0 && C > 0 && N > 0, MLSP_EINVAL, "knn: bad shape B=%d C=%d N=%d", B, C, N);
+    MLSP_REQUIRE(k >= 1 && k <= N, MLSP_EINVAL, "knn: k=%d out of range for N=%d", k, N);
+    MLSP_REQUIRE(k <= 64, MLSP_EUNSUPPORTED, "knn: k=%d > 64 not supported", k);
+    MLSP_REQUIRE(B <= 65535, MLSP_EUNSUPPORTED, "knn: B=%d > 65535", B);
+    MLSP_REQUIRE(ws_bytes >= knn_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "knn: workspace too small");
+    MLSP_REQUIRE(flags != MLSP_KNN_TENSOR_ONLY, MLSP_EUNSUPPORTED, "knn: tensor path not available for this shape");
+    cudaStream_t st = as_stream(stream);
+    float *xx = reinterpret_cast<float *>(static_cast<char *>(ws) + KNN_WS_HEADER);
+    sq_norms_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, C, N, xx);
+    MLSP_LAUNCH_CHECK("sq_norms_kernel");
+    return launch_exact(x, xx, B, C, N, k, idx, st);
+}

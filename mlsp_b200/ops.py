@@ -1,0 +1,397 @@
+"""Host-side mirror of the reference's hot-path functions, backed by libmlsp_b200.so.
+
+Every public function keeps the name, argument order and return convention of the reference
+function it replaces (VITA-Group/MLSP; file:line cited per function), so `mlsp_b200.patch`
+can rebind them inside the reference modules and Models.py / mlsp.py / trainer.py run
+unchanged.  PyTorch is only the plumbing here (device memory, streams, autograd graph):
+all arithmetic happens in the sm_100a kernels behind the C ABI (include/mlsp_b200.h).
+There is no CPU path: non-CUDA tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MlspError
+
+NREGIONS = 3          # utils/pc_utils.py:10
+MIN_POINTS = 20       # utils/pc_utils.py:8
+RADIUS = 0.5          # utils/pc_utils.py:9
+DefRec_SCALER = 20.0  # MLSP/mlsp.py:7
+_MIN_PTS_VOXEL = 40   # MLSP/mlsp.py:27
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def _require_cuda_f32(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise MlspError(f"{name}: expected a CUDA tensor (mlsp_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise MlspError(f"{name}: expected float32, got {t.dtype}")
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _workspace(op: int, B: int, C: int, N: int, k: int, device) -> torch.Tensor:
+    return torch.empty(max(_lib.workspace_bytes(op, B, C, N, k), 16), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------------- a1
+def knn(x: torch.Tensor, k: int, flags: int = _lib.KNN_AUTO) -> torch.Tensor:
+    """knn(x, k): PointDA/model_utils.py:9-16 == PointSegDA/Models.py:8-15.
+    x (B,C,N) -> idx (B,N,k) int64, nearest first (self at rank 0), ties by lowest index."""
+    _require_cuda_f32(x, "knn")
+    if x.dim() != 3:
+        raise MlspError(f"knn: expected (B,C,N), got {tuple(x.shape)}")
+    x = x.detach().contiguous()
+    B, C, N = x.shape
+    if not (1 <= k <= N):
+        raise RuntimeError(f"selected index k out of range (k={k}, N={N})")  # torch.topk's message
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = _workspace(_lib.OP_KNN, B, C, N, k, x.device)
+        _lib.call("mlsp_knn_f32", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(), flags, _stream(x.device))
+    return idx
+
+
+# ----------------------------------------------------------------------------------------------- a2
+class _EdgeGather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        B, C, N = x.shape
+        k = idx.shape[2]
+        out = torch.empty((B, N, k, 2 * C), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = _workspace(_lib.OP_EDGE_FWD, B, C, N, k, x.device)
+            _lib.call("mlsp_edge_gather_fwd", _ptr(x), _ptr(idx), B, C, N, k, _ptr(out), _ptr(ws), ws.numel(),
+                      _stream(x.device))
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, C, N, k)
+        return out.permute(0, 3, 1, 2)   # (B,2C,N,k) with strides (N*k*2C, 1, k*2C, 2C), like the reference
+
+    @staticmethod
+    def backward(ctx, grad):
+        (idx,) = ctx.saved_tensors
+        B, C, N, k = ctx.dims
+        g = grad.permute(0, 2, 3, 1).contiguous()   # storage order [B][N][k][2C]; free if already channels_last
+        if g.dtype != torch.float32:
+            g = g.float()
+        gx = torch.empty((B, C, N), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            ws = _workspace(_lib.OP_EDGE_BWD, B, C, N, k, g.device)
+            _lib.call("mlsp_edge_gather_bwd", _ptr(g), _ptr(idx), B, C, N, k, _ptr(gx), _ptr(ws), ws.numel(),
+                      _stream(g.device))
+        return gx, None
+
+
+def get_graph_feature(x: torch.Tensor, args=None, k: int = 20, idx: torch.Tensor | None = None) -> torch.Tensor:
+    """get_graph_feature(x, args, k, idx): PointDA/model_utils.py:18-42 == PointSegDA/Models.py:18-45.
+    x (B,C,N) or (B,C,N,1) -> (B,2C,N,k) = [neighbour - centre ; centre], channels_last strides.
+    `args` only picked a device in the reference and is ignored; a caller-supplied idx is honoured."""
+    _require_cuda_f32(x, "get_graph_feature")
+    B, N = x.size(0), x.size(2)
+    x = x.reshape(B, -1, N).contiguous()
+    if idx is None:
+        idx = knn(x, k=k)
+    else:
+        if idx.shape != (B, N, k) or idx.dtype != torch.int64 or idx.device != x.device:
+            raise MlspError("get_graph_feature: idx must be int64 (B,N,k) on x's device")
+        idx = idx.contiguous()
+    return _EdgeGather.apply(x, idx)
+
+
+# ----------------------------------------------------------------------------------------------- a3
+def farthest_point_sample(args, xyz: torch.Tensor, npoint: int):
+    """farthest_point_sample(args, xyz, npoint): utils/pc_utils.py:137-161.
+    xyz (B,3,N) -> (centroids (B,npoint) int64, centroids_vals (B,3,npoint)).
+    Consumes exactly one torch.randint(0,N,(B,)) from the CPU generator, like :150."""
+    _require_cuda_f32(xyz, "farthest_point_sample")
+    B, C, N = xyz.shape
+    if C != 3:
+        raise MlspError("farthest_point_sample: expected (B,3,N)")   # the reference views the centroid as (B,3,1)
+    start = torch.randint(0, N, (B,), dtype=torch.long)
+    return fps_from_start(xyz, npoint, start)
+
+
+def fps_from_start(xyz: torch.Tensor, npoint: int, start: torch.Tensor):
+    """FPS with caller-provided start indices (CPU or CUDA int64 (B,))."""
+    _require_cuda_f32(xyz, "fps")
+    xyz = xyz.detach().contiguous()
+    B, _, N = xyz.shape
+    if start.device.type == "cpu" and (int(start.min()) < 0 or int(start.max()) >= N):
+        raise MlspError("fps: start index out of range")
+    start = start.to(device=xyz.device, dtype=torch.int64, non_blocking=True).contiguous()
+    cen = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
+    vals = torch.empty((B, 3, npoint), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.call("mlsp_fps", _ptr(xyz), B, N, int(npoint), _ptr(start), _ptr(cen), _ptr(vals), _stream(xyz.device))
+    return cen, vals
+
+
+# ----------------------------------------------------------------------------------------------- a4
+def region_mean(num_regions: int = NREGIONS) -> np.ndarray:
+    """region_mean(num_regions): utils/pc_utils.py:13-30 (host; voxel centres, id = 9qx+3qy+qz)."""
+    n = num_regions
+    d = 2 / n
+    axis = [1 - d * ((n - 1 - a) + 0.5) for a in range(n)]
+    return np.array([[x, y, z] for x in axis for y in axis for z in axis])
+
+
+def _region_pass(X: torch.Tensor, order: np.ndarray, min_pts: int):
+    B, C, N = X.shape
+    region = torch.empty((B, N), dtype=torch.int64, device=X.device)
+    counts = torch.empty((B, NREGIONS ** 3), dtype=torch.int32, device=X.device)
+    sel = torch.empty((2, B), dtype=torch.int32, device=X.device)   # [chosen ; nsel]
+    order32 = np.ascontiguousarray(order, dtype=np.int32)
+    with torch.cuda.device(X.device):
+        _lib.call("mlsp_region_assign_select", _ptr(X), B, C, N, ctypes.c_void_p(order32.ctypes.data), int(min_pts),
+                  _ptr(region), _ptr(counts), _ptr(sel[0]), _ptr(sel[1]), _stream(X.device))
+    return region, counts, sel
+
+
+def assign_region_to_point(X: torch.Tensor, device=None) -> torch.Tensor:
+    """assign_region_to_point(X, device): utils/pc_utils.py:33-73.  X (B,C,N) -> (B,N) int64."""
+    _require_cuda_f32(X, "assign_region_to_point")
+    region, _, _ = _region_pass(X.detach().contiguous(), np.arange(NREGIONS ** 3), 0)
+    return region
+
+
+_lookup_cache: dict = {}
+
+
+def _lookup_host(lookup) -> np.ndarray:
+    """`lookup[i].cpu().numpy()` of MLSP/mlsp.py:43 for all i, cached per tensor version (one D2H ever)."""
+    if isinstance(lookup, np.ndarray):
+        return lookup.astype(np.float32)
+    key = (lookup.data_ptr(), lookup._version, lookup.device)
+    hit = _lookup_cache.get(key)
+    if hit is None:
+        hit = lookup.detach().to("cpu", torch.float32).numpy()
+        _lookup_cache.clear()
+        _lookup_cache[key] = hit
+    return hit
+
+
+def _upload_noise(chunks, counts, device):
+    total = int(sum(counts))
+    offsets = np.zeros(len(counts), np.int32)
+    offsets[1:] = np.cumsum(counts[:-1], dtype=np.int64)
+    if total == 0:
+        return None, torch.from_numpy(offsets).to(device, non_blocking=True)
+    host = torch.from_numpy(np.concatenate(chunks, axis=0).astype(np.float32))
+    return host.to(device, non_blocking=True), torch.from_numpy(offsets).to(device, non_blocking=True)
+
+
+def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxels", device="cuda:0", groups: int = 1):
+    """deform_input(X, lookup, DefRec_dist, device, groups): MLSP/mlsp.py:10-51.
+    Mutates X (B,C,N) in place and returns (X, mask (B,C,N)).  The numpy RNG is consumed on the host in the
+    reference's order (one permutation(27); per cloud one choice / multivariate_normal), so seeded runs
+    reproduce the reference's masks and deformed points bit for bit; region assignment, histogram, choice,
+    ranking and scatter run on the GPU.  One device->host read of 2B ints (voxel mode)."""
+    _require_cuda_f32(X, "deform_input")
+    if groups != 1:
+        raise NotImplementedError("deform_input: only groups=1 (the value every reference caller uses)")
+    if not X.is_contiguous():
+        raise MlspError("deform_input: X must be contiguous (it is modified in place)")
+    B, C, N = X.shape
+    region_ids = np.random.permutation(NREGIONS ** 3)                      # mlsp.py:28
+    mask = torch.empty_like(X)
+    if DefRec_dist == "volume_based_radius":
+        return _deform_radius(X, mask)
+    region, _, sel = _region_pass(X, region_ids, _MIN_PTS_VOXEL)
+    sel_h = sel.cpu().numpy()                                              # the only sync of the voxel path
+    chosen, nsel = sel_h[0], sel_h[1]
+    noise = offsets = None
+    if DefRec_dist == "volume_based_voxels":
+        look = _lookup_host(lookup)
+        chunks = [np.random.multivariate_normal(look[chosen[b]], np.eye(3) * 0.001, int(nsel[b]))   # pc_utils.py:122
+                  for b in range(B) if chosen[b] >= 0]
+        noise, offsets = _upload_noise(chunks, np.where(chosen >= 0, nsel, 0), X.device)
+    with torch.cuda.device(X.device):
+        _lib.call("mlsp_region_mask_scatter", _ptr(X), B, C, N, _ptr(region), _ptr(sel[0]), _ptr(noise),
+                  _ptr(offsets), _ptr(mask), _stream(X.device))
+    return X, mask
+
+
+def ball_count(x: torch.Tensor, r2: float = RADIUS ** 2) -> torch.Tensor:
+    """Row sums of the in-ball matrix of collapse_to_point (utils/pc_utils.py:86-96). x (B,C,N) -> (B,N) int32."""
+    _require_cuda_f32(x, "ball_count")
+    x = x.detach().contiguous()
+    B, C, N = x.shape
+    cnt = torch.empty((B, N), dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.call("mlsp_ball_count", _ptr(x), B, C, N, ctypes.c_float(r2), _ptr(cnt), _stream(x.device))
+    return cnt
+
+
+def _deform_radius(X: torch.Tensor, mask: torch.Tensor):
+    B, C, N = X.shape
+    if C != 3:
+        raise MlspError("deform_input(volume_based_radius): expected (B,3,N)")
+    cnt = ball_count(X)
+    cnt_h = cnt.cpu().numpy()
+    X_h = X.cpu().numpy()
+    centres = np.full(B, -1, np.int32)
+    chunks, counts = [], np.zeros(B, np.int64)
+    for b in range(B):
+        cand = np.nonzero(cnt_h[b] >= MIN_POINTS)[0]                       # pc_utils.py:96-99
+        centre = np.random.choice(cand.squeeze())                          # pc_utils.py:102 (same quirks)
+        n = int(cnt_h[b, centre])
+        chunks.append(np.random.multivariate_normal(X_h[b, :, centre], np.eye(3) * 0.001, n))
+        centres[b], counts[b] = centre, n
+    noise, offsets = _upload_noise(chunks, counts, X.device)
+    centres_d = torch.from_numpy(centres).to(X.device, non_blocking=True)
+    with torch.cuda.device(X.device):
+        _lib.call("mlsp_ball_mask_scatter", _ptr(X), B, C, N, ctypes.c_float(RADIUS ** 2), _ptr(centres_d),
+                  _ptr(noise), _ptr(offsets), _ptr(mask), _stream(X.device))
+    return X, mask
+
+
+def collapse_to_point(x: torch.Tensor, device=None):
+    """collapse_to_point(x, device): utils/pc_utils.py:76-111 for one cloud x (3,N): returns (x, indices)."""
+    _require_cuda_f32(x, "collapse_to_point")
+    if not x.is_contiguous():
+        raise MlspError("collapse_to_point: x must be contiguous (it is modified in place)")
+    X = x.unsqueeze(0)
+    mask = torch.empty_like(X)
+    _deform_radius(X, mask)
+    return x, mask[0, 0].nonzero().squeeze()
+
+
+# ----------------------------------------------------------------------------------------------- a6
+def cal_density(batch_pts: torch.Tensor, radius: float, num_cls: int, pergroup: int = 2, shift: int = 0, K: int = 100):
+    """cal_density(batch_pts, radius, num_cls, pergroup, shift, K): MLSP/mlsp.py:240-272.
+    batch_pts (B,N,3) -> (soft labels (B,N,num_cls) float32, clipped counts (B,N) int64), both ON THE DEVICE
+    (the reference returns host numpy arrays; its callers wrap them in torch.tensor(...).to(device), which
+    accepts these unchanged: PointDA/trainer.py:533-536)."""
+    _require_cuda_f32(batch_pts, "cal_density")
+    pts = batch_pts.detach().contiguous()
+    B, N, three = pts.shape
+    if three != 3:
+        raise MlspError("cal_density: expected (B,N,3)")
+    r2 = float(np.float32(float(radius) * float(radius)))
+    labels = torch.empty((B, N, num_cls), dtype=torch.float32, device=pts.device)
+    row = torch.empty((B, N), dtype=torch.int64, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.call("mlsp_ball_count_labels", _ptr(pts), B, N, ctypes.c_float(r2), int(K), int(shift), int(pergroup),
+                  int(num_cls), _ptr(labels), _ptr(row), _stream(pts.device))
+    return labels, row
+
+
+# ----------------------------------------------------------------------------------------------- a7
+def estimate_normals(xyz: torch.Tensor, near: int = 20) -> torch.Tensor:
+    """Batched replacement of the per-cloud python-pcl loop PointDA/trainer.py:524-531 (kSearchNormalEstimation
+    :173-188).  xyz (B,N,3) -> unit normals (B,N,3), oriented towards the origin like pcl's default viewpoint."""
+    _require_cuda_f32(xyz, "estimate_normals")
+    pts = xyz.detach().contiguous()
+    B, N, _ = pts.shape
+    idx = knn(pts.transpose(1, 2).contiguous(), near)
+    normals = torch.empty((B, N, 3), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.call("mlsp_pca_normals", _ptr(pts), _ptr(idx), B, N, int(near), _ptr(normals), _stream(pts.device))
+    return normals
+
+
+# ----------------------------------------------------------------------------------------------- a9 / a10
+def _point_strides(p: torch.Tensor):
+    if p.dim() != 3 or p.size(2) != 3:
+        raise MlspError(f"chamfer: expected (B,N,3), got {tuple(p.shape)}")
+    return p.stride(0), p.stride(1), p.stride(2)
+
+
+def _mask_rows(mask: torch.Tensor):
+    """The reference's `mask_cord = mask[:, :, 0]` (mlsp.py:141) as (tensor, batch stride) with unit point stride."""
+    m = mask[:, :, 0]
+    if m.stride(1) != 1:
+        m = m.contiguous()
+    return m, m.stride(0)
+
+
+class _ChamferDir(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p1, p2, mask):
+        B, N, _ = p1.shape
+        m, mbs = _mask_rows(mask)
+        dev = p1.device
+        rowmin = torch.empty((B, N), dtype=torch.float32, device=dev)
+        argmin = torch.empty((B, N), dtype=torch.int64, device=dev)
+        partial = torch.empty((B,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _workspace(_lib.OP_CHAMFER, B, 3, N, 0, dev)
+            _lib.call("mlsp_chamfer_dir_fwd", _ptr(p1), *_point_strides(p1), _ptr(p2), *_point_strides(p2), _ptr(m), mbs,
+                      B, N, 0, _ptr(rowmin), _ptr(argmin), _ptr(partial), _ptr(ws), ws.numel(), _stream(dev))
+        ctx.save_for_backward(p1, p2, m, argmin)
+        return partial.sum()
+
+    @staticmethod
+    def backward(ctx, grad):
+        p1, p2, m, argmin = ctx.saved_tensors
+        B, N, _ = p1.shape
+        dev = p1.device
+        g1 = torch.zeros((B, N, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        g2 = torch.zeros((B, N, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        grad = grad.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _lib.call("mlsp_chamfer_dir_bwd", _ptr(p1), *_point_strides(p1), _ptr(p2), *_point_strides(p2), _ptr(m),
+                      m.stride(0), _ptr(argmin), B, N, _ptr(grad), ctypes.c_float(1.0), _ptr(g1), _ptr(g2), _stream(dev))
+        return g1, g2, None
+
+
+def chamfer_distance(p1: torch.Tensor, p2: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """chamfer_distance(p1, p2, mask): MLSP/mlsp.py:115-153.  p1, p2, mask (B,N,3) (any strides) -> 0-d tensor,
+    differentiable w.r.t. p1 and p2."""
+    _require_cuda_f32(p1, "chamfer_distance")
+    _require_cuda_f32(p2, "chamfer_distance")
+    _require_cuda_f32(mask, "chamfer_distance")
+    assert p1.size(0) == p2.size(0) and p1.size(2) == p2.size(2)           # mlsp.py:125
+    if p1.size(1) != p2.size(1):
+        raise MlspError("chamfer_distance: both clouds must have N points (the mask indexes both)")
+    return _ChamferDir.apply(p1, p2, mask)
+
+
+def reconstruction_loss(pred: torch.Tensor, gold: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """reconstruction_loss(pred, gold, mask): MLSP/mlsp.py:156-182.  pred (B,N,3), gold (B,3,N), mask (B,3,N)."""
+    batch_size = pred.size(0)
+    gold = gold.permute(0, 2, 1)
+    mask = mask.permute(0, 2, 1)
+    dist_gold = chamfer_distance(gold, pred, mask)
+    dist_pred = chamfer_distance(pred, gold, mask)
+    return (1 / batch_size) * (dist_gold + dist_pred)
+
+
+def findneareat_index(p1: torch.Tensor, p2: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """findneareat_index(p1, p2, mask): MLSP/mlsp.py:196-220 -> (B,N) int64 argmin of the penalised distances."""
+    _require_cuda_f32(p1, "findneareat_index")
+    _require_cuda_f32(p2, "findneareat_index")
+    assert p1.size(0) == p2.size(0) and p1.size(2) == p2.size(2)           # mlsp.py:197
+    B, N, _ = p1.shape
+    m, mbs = _mask_rows(mask)
+    dev = p1.device
+    rowmin = torch.empty((B, N), dtype=torch.float32, device=dev)
+    argmin = torch.empty((B, N), dtype=torch.int64, device=dev)
+    partial = torch.empty((B,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(_lib.OP_CHAMFER, B, 3, N, 0, dev)
+        _lib.call("mlsp_chamfer_dir_fwd", _ptr(p1), *_point_strides(p1), _ptr(p2), *_point_strides(p2), _ptr(m), mbs,
+                  B, N, 1, _ptr(rowmin), _ptr(argmin), _ptr(partial), _ptr(ws), ws.numel(), _stream(dev))
+    return argmin
+
+
+def findindexs(pred, gold, mask):
+    """findindexs(pred, gold, mask): MLSP/mlsp.py:184-193."""
+    gold = gold.permute(0, 2, 1)
+    mask = mask.permute(0, 2, 1)
+    return [findneareat_index(pred, gold, mask), findneareat_index(gold, pred, mask)]
+
+
+def calc_loss(args, logits, labels, mask):
+    """calc_loss(args, logits, labels, mask): MLSP/mlsp.py:222-229."""
+    return args.DefRec_weight * reconstruction_loss(logits["DefRec"], labels, mask) * DefRec_SCALER

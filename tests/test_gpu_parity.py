@@ -1,0 +1,326 @@
+"""GPU parity: every C-ABI entry point (through the reference-signature host layer mlsp_b200.ops)
+against the oracle on seeded inputs, against the reference-generated golden fixtures, and -- at
+BASELINE.json's full sizes -- through size-independent properties.
+
+Bars (BASELINE.json:north_star): kNN / FPS / ball-query indices and cardinality counts bit-exact
+(ties -> lowest index); distances, normals (up to sign) and Chamfer loss / gradients within 1e-5
+relative in fp32."""
+import numpy as np
+import pytest
+import torch
+
+import mlsp_b200 as M
+from mlsp_b200 import synth
+from conftest import knn_rank_check
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # north_star tolerance for fp32 outputs
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def npo():
+    from oracle import np_ops
+    return np_ops
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------ a1
+@pytest.mark.parametrize("name", ["knn_q3", "knn_q64"])
+def test_knn_golden_quantised(golden, dev, name):
+    g = golden(name)
+    k = int(g["k"])
+    idx = _np(M.knn(torch.from_numpy(g["x"]).to(dev), k))
+    stable = np.argsort(-g["pd"], axis=2, kind="stable")[:, :, :k]
+    assert np.array_equal(idx, stable)
+
+
+@pytest.mark.parametrize("name", ["knn_c3", "knn_c64", "knn_c128_k40"])
+def test_knn_golden_continuous(golden, dev, orc, name):
+    g = golden(name)
+    k = int(g["k"])
+    idx = _np(M.knn(torch.from_numpy(g["x"]).to(dev), k))
+    assert np.array_equal(idx, orc.knn(g["x"], k))                    # bit-exact with the pinned oracle
+    bad, unc = knn_rank_check(g["x"], idx, k)
+    assert unc == 0                                                   # vs fp64 truth: only certified near-ties
+    assert (idx != g["idx"]).sum() <= bad + knn_rank_check(g["x"], g["idx"], k)[0]
+
+
+@pytest.mark.parametrize("B,C,N,k,quant", [
+    (32, 3, 1024, 20, False), (32, 3, 1024, 20, True),     # config A
+    (16, 3, 2048, 20, False),                               # config S
+    (4, 3, 4096, 40, False),                                # config X shape, bounded batch
+    (3, 3, 1000, 20, False), (2, 3, 77, 20, True),          # ragged N
+    (2, 3, 20, 20, False), (1, 3, 33, 1, False),            # k == N, k == 1
+    (8, 64, 1024, 20, False), (4, 128, 1024, 20, False),    # DGCNN feature layers
+    (2, 64, 1024, 20, True), (2, 128, 4096, 40, False),
+    (2, 6, 500, 33, False), (1, 200, 300, 64, False),       # odd C, k > 32 slots
+])
+def test_knn_matches_oracle(dev, orc, B, C, N, k, quant):
+    if C == 3:
+        x = synth.clouds(B, N, 100 + N + k, quantised=quant)
+    else:
+        x = synth.features(B, C, N, 100 + N, quantised=True) if quant else synth.smooth_features(B, C, N, 100 + N)
+    idx = _np(M.knn(x.to(dev), k))
+    ref = orc.knn(x.numpy(), k)
+    assert idx.shape == (B, N, k) and idx.dtype == np.int64
+    assert np.array_equal(idx, ref)
+    assert (idx[:, :, 0] == np.arange(N)[None]).mean() > 0.99 or quant   # self first (duplicates aside)
+
+
+def test_knn_all_ties_lowest_index(dev):
+    x = torch.zeros(2, 3, 100)
+    idx = _np(M.knn(x.to(dev), 20))
+    assert np.array_equal(idx, np.broadcast_to(np.arange(20), (2, 100, 20)))
+
+
+def test_knn_errors(dev):
+    with pytest.raises(RuntimeError):
+        M.knn(torch.zeros(1, 3, 10, device=dev), 11)
+    with pytest.raises(M.MlspError):
+        M.knn(torch.zeros(1, 3, 100, device=dev), 65)
+
+
+# ------------------------------------------------------------------------------------------------ a2
+@pytest.mark.parametrize("name", ["ggf_3", "ggf_16"])
+def test_edge_gather_golden(golden, dev, name):
+    g = golden(name)
+    x = torch.from_numpy(g["x"]).to(dev)
+    idx = torch.from_numpy(g["idx"]).to(dev)
+    out = M.get_graph_feature(x, None, k=int(g["k"]), idx=idx)
+    B, C, N = x.shape
+    k = int(g["k"])
+    assert out.shape == (B, 2 * C, N, k)
+    assert out.stride() == (N * k * 2 * C, 1, k * 2 * C, 2 * C)       # the reference's channels_last view
+    assert np.array_equal(_np(out), g["out"])
+    out4 = M.get_graph_feature(x.view(B, C, N, 1), None, k=k)         # 4-D input, knn inside
+    assert out4.shape == out.shape
+
+
+@pytest.mark.parametrize("B,C,N,k", [(32, 3, 1024, 20), (8, 64, 1024, 20), (4, 128, 1024, 20), (2, 6, 333, 7),
+                                     (2, 20, 500, 40)])
+def test_edge_gather_matches_oracle(dev, orc, B, C, N, k):
+    x = synth.features(B, C, N, 7)
+    idx = torch.randint(0, N, (B, N, k), generator=torch.Generator().manual_seed(1))
+    out = M.get_graph_feature(x.to(dev), None, k=k, idx=idx.to(dev))
+    ref = orc.edge_gather(x.numpy(), idx.numpy())
+    assert np.array_equal(_np(out.permute(0, 2, 3, 1)), ref)
+
+
+def test_edge_gather_backward_golden(golden, dev):
+    g = golden("ggf_bwd")
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    out = M.get_graph_feature(x, None, k=g["idx"].shape[2], idx=torch.from_numpy(g["idx"]).to(dev))
+    out.backward(torch.from_numpy(g["g"]).to(dev))
+    np.testing.assert_allclose(_np(x.grad), g["grad_x"], rtol=RTOL, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,N,k", [(4, 3, 1024, 20), (4, 64, 1024, 20), (2, 128, 512, 20), (2, 5, 100, 9)])
+def test_edge_gather_backward_matches_oracle(dev, orc, B, C, N, k):
+    x = synth.features(B, C, N, 9).to(dev).requires_grad_(True)
+    idx = M.knn(x.detach(), k)
+    out = M.get_graph_feature(x, None, k=k, idx=idx)
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+    out.backward(g)
+    ref = orc.edge_gather_bwd(_np(g.permute(0, 2, 3, 1).contiguous()), _np(idx), C)
+    scale = np.abs(ref).max()
+    assert np.abs(_np(x.grad) - ref).max() <= 2e-6 * scale * np.sqrt(k)
+    # linearity of the backward: grad(2g) == 2 grad(g) exactly up to atomics order
+    x2 = x.detach().clone().requires_grad_(True)
+    M.get_graph_feature(x2, None, k=k, idx=idx).backward(2 * g)
+    np.testing.assert_allclose(_np(x2.grad), 2 * _np(x.grad), rtol=1e-4, atol=1e-4 * scale)
+
+
+# ------------------------------------------------------------------------------------------------ a3
+@pytest.mark.parametrize("name", ["fps", "fps_q_full"])
+def test_fps_golden(golden, dev, name):
+    g = golden(name)
+    torch.manual_seed(int(g["seed"]))                                  # the op draws torch.randint itself
+    cen, vals = M.farthest_point_sample(None, torch.from_numpy(g["xyz"]).to(dev), int(g["npoint"]))
+    assert np.array_equal(_np(cen), g["centroids"])
+    assert np.array_equal(_np(vals), g["vals"])
+
+
+@pytest.mark.parametrize("B,N,npoint", [(32, 1024, 1024), (32, 1024, 64), (16, 2048, 512), (4, 4096, 256),
+                                        (3, 1000, 100), (2, 100, 100), (2, 5000, 50), (1, 16384, 20)])
+def test_fps_matches_oracle(dev, orc, B, N, npoint):
+    x = synth.clouds(B, N, 5 + N)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(N))
+    cen, vals = M.fps_from_start(x.to(dev), npoint, start)
+    rc, rv = orc.fps(x.numpy(), npoint, start.numpy())
+    assert np.array_equal(_np(cen), rc)
+    assert np.array_equal(_np(vals), rv)
+    if npoint == N:                                                    # full sampling is a permutation
+        assert (np.sort(_np(cen), axis=1) == np.arange(N)[None]).all()
+
+
+# ------------------------------------------------------------------------------------------------ a4 / a5 / a8
+def test_regions_golden(golden, dev):
+    g = golden("regions")
+    Y = M.assign_region_to_point(torch.from_numpy(g["X"]).to(dev))
+    assert np.array_equal(_np(Y), g["Y"])
+    np.testing.assert_allclose(M.region_mean(3), g["lookup"], rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize("name,mode", [("deform_voxels_s1", "volume_based_voxels"),
+                                       ("deform_voxels_s7", "volume_based_voxels"),
+                                       ("deform_voxels_sparse", "volume_based_voxels"),
+                                       ("deform_radius", "volume_based_radius")])
+def test_deform_input_golden(golden, dev, name, mode):
+    g = golden(name)
+    X = torch.from_numpy(g["X0"]).to(dev)
+    lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=dev)
+    np.random.seed(int(g["seed"]))
+    Xd, mask = M.deform_input(X, lookup, mode, dev)
+    assert Xd is X                                                     # in place, like the reference
+    assert np.array_equal(_np(mask), g["mask"])
+    assert np.array_equal(_np(Xd), g["X"])
+
+
+@pytest.mark.parametrize("mode", ["volume_based_voxels", "volume_based_radius"])
+def test_deform_input_full_size(dev, npo, mode):
+    X0 = synth.surface_clouds(32, 1024, 77)
+    X = X0.clone().to(dev)
+    np.random.seed(5)
+    Xd, mask = M.deform_input(X, torch.tensor(M.region_mean(3), dtype=torch.float32), mode, dev)
+    Xo = X0.numpy().copy()
+    np.random.seed(5)
+    Xo, mo = npo.deform_input(Xo, npo.region_mean(3), mode)
+    assert np.array_equal(_np(mask), mo)
+    assert np.array_equal(_np(Xd), Xo)
+    m = _np(mask)
+    assert ((m == 0) | (m == 1)).all() and (m[:, 0] == m[:, 1]).all() and (m[:, 0] == m[:, 2]).all()
+    assert np.array_equal(_np(Xd)[m == 0], X0.numpy()[m == 0])          # untouched outside the mask
+
+
+def test_ball_count_matches_oracle(dev, orc):
+    x = synth.surface_clouds(8, 1024, 3)
+    assert np.array_equal(_np(M.ball_count(x.to(dev))), orc.ball_count(x.numpy()))
+    xq = synth.clouds(2, 700, 4, quantised=True)                       # boundary ties d == 0.25 possible
+    assert np.array_equal(_np(M.ball_count(xq.to(dev))), orc.ball_count(xq.numpy()))
+
+
+# ------------------------------------------------------------------------------------------------ a6
+@pytest.mark.parametrize("B,N,radius,num_cls,pergroup,shift,K", [
+    (32, 1024, 0.13, 16, 2, 0, 100), (16, 2048, 0.091, 16, 5, 10, 100), (2, 1500, 0.4, 16, 2, 0, 100),
+    (2, 300, 0.12, 8, 3, 1, 10)])
+def test_cal_density_matches_oracle(dev, npo, B, N, radius, num_cls, pergroup, shift, K):
+    pts = synth.surface_clouds(B, N, 21).permute(0, 2, 1).contiguous()
+    lab, row = M.cal_density(pts.to(dev), radius, num_cls, pergroup, shift, K)
+    ol, orow = npo.cal_density(pts.numpy(), radius, num_cls, pergroup, shift, K)
+    assert row.dtype == torch.int64 and lab.shape == (B, N, num_cls)
+    assert np.array_equal(_np(row), orow)                              # counts: bit-exact
+    assert np.array_equal(_np(lab), ol.astype(np.float32))
+    assert np.allclose(_np(lab).sum(-1), 1.0)
+
+
+# ------------------------------------------------------------------------------------------------ a7
+@pytest.mark.parametrize("B,N,near", [(32, 1024, 20), (16, 2048, 10)])
+def test_normals_match_oracle(dev, npo, B, N, near):
+    pts = synth.surface_clouds(B, N, 31).permute(0, 2, 1).contiguous()
+    n = _np(M.estimate_normals(pts.to(dev), near))
+    on, gap = npo.pca_normals(pts.numpy(), near, return_gap=True)
+    assert np.allclose(np.linalg.norm(n, axis=-1), 1.0, atol=1e-6)
+    assert ((n * pts.numpy()).sum(-1) <= 1e-6).all()                   # oriented towards the origin
+    cos = np.abs((n * on).sum(-1))
+    ok = gap > 1e-2                                                    # gate on the eigengap
+    assert ok.mean() > 0.98
+    assert (1.0 - cos[ok]).max() < RTOL
+    assert np.abs(np.abs(n) - np.abs(on))[ok].max() < 5e-5
+
+
+def test_normals_plane(dev):
+    g = torch.Generator().manual_seed(0)
+    P = torch.zeros(2, 500, 3)
+    P[:, :, :2] = torch.rand(2, 500, 2, generator=g) * 2 - 1
+    P[:, :, 2] = 0.5
+    n = _np(M.estimate_normals(P.to(dev), 12))
+    assert np.allclose(n[:, :, 2], -1.0, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ a9 / a10
+def _chamfer_case(golden, dev, name):
+    g = golden(name)
+    pred = torch.from_numpy(g["pred"]).to(dev).requires_grad_(True)
+    gold = torch.from_numpy(g["gold"]).to(dev)
+    mask = torch.from_numpy(g["mask"]).to(dev)
+    return g, pred, gold, mask
+
+
+@pytest.mark.parametrize("name", ["chamfer", "chamfer_far"])
+def test_chamfer_golden(golden, dev, name):
+    g, pred, gold, mask = _chamfer_case(golden, dev, name)
+    loss = M.reconstruction_loss(pred, gold, mask)
+    assert loss.dim() == 0
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= RTOL * abs(float(g["loss"]))
+    np.testing.assert_allclose(_np(pred.grad), g["grad"], rtol=RTOL, atol=1e-7)
+
+
+def test_chamfer_indices_golden(golden, dev, orc):
+    g, pred, gold, mask = _chamfer_case(golden, dev, "chamfer")
+    i1, i2 = M.findindexs(pred.detach(), gold, mask)
+    gold_bnc = g["gold"].transpose(0, 2, 1)
+    _, _, o1 = orc.chamfer_dir(g["pred"], gold_bnc, g["mask"][:, 0])
+    _, _, o2 = orc.chamfer_dir(gold_bnc, g["pred"], g["mask"][:, 0])
+    assert np.array_equal(_np(i1), o1) and np.array_equal(_np(i2), o2)   # bit-exact with the pinned oracle
+    assert (_np(i1) != g["idx_pred_gold"]).mean() < 1e-3                  # reference: only rounding near-ties
+    assert (_np(i2) != g["idx_gold_pred"]).mean() < 1e-3
+
+
+def test_chamfer_empty_mask_is_nan(golden, dev):
+    g, pred, gold, mask = _chamfer_case(golden, dev, "chamfer")
+    loss = M.reconstruction_loss(pred.detach(), gold, torch.zeros_like(mask))
+    assert torch.isnan(loss).item() and np.isnan(float(golden("chamfer_empty")["loss"]))
+
+
+@pytest.mark.parametrize("B,N", [(32, 1024), (16, 2048)])
+def test_chamfer_full_size(dev, orc, npo, B, N):
+    gold = synth.surface_clouds(B, N, 41)
+    X = gold.numpy().copy()
+    np.random.seed(1)
+    _, mask = npo.deform_input(X, npo.region_mean(3))
+    g = torch.Generator().manual_seed(2)
+    pred = (gold.permute(0, 2, 1) + 0.05 * torch.randn(B, N, 3, generator=g)).contiguous()
+    pd = pred.to(dev).requires_grad_(True)
+    loss = M.calc_loss(type("A", (), {"DefRec_weight": 0.5})(), {"DefRec": pd}, gold.to(dev), torch.from_numpy(mask).to(dev))
+    loss.backward()
+    lo, go = orc.reconstruction_loss(pred.numpy(), gold.numpy(), mask)
+    assert abs(loss.item() - 0.5 * 20.0 * lo) <= RTOL * abs(10.0 * lo)
+    np.testing.assert_allclose(_np(pd.grad), 10.0 * go, rtol=1e-4, atol=1e-6 * np.abs(go).max() * 10)
+    # gradient only on rows that take part: masked rows of pred and their matched columns
+    assert (np.abs(_np(pd.grad)).sum(-1) > 0).sum() <= 2 * int(mask[:, 0].sum())
+    # chamfer_distance is differentiable w.r.t. both arguments
+    a = pred.to(dev).requires_grad_(True)
+    b = gold.permute(0, 2, 1).contiguous().to(dev).requires_grad_(True)
+    M.chamfer_distance(a, b, torch.from_numpy(mask).to(dev).permute(0, 2, 1)).backward()
+    assert torch.isfinite(a.grad).all() and torch.isfinite(b.grad).all()
+    np.testing.assert_allclose(_np(a.grad.sum(1)), -_np(b.grad.sum(1)), rtol=1e-3, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ streams
+def test_ops_follow_current_stream(dev, orc):
+    x = synth.clouds(4, 512, 9)
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        xd = x.to(dev, non_blocking=True)
+        idx = M.knn(xd, 20)
+        out = M.get_graph_feature(xd, None, k=20, idx=idx)
+    s.synchronize()
+    assert np.array_equal(_np(idx), orc.knn(x.numpy(), 20))
+    assert np.array_equal(_np(out.permute(0, 2, 3, 1)), orc.edge_gather(x.numpy(), _np(idx)))
