@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- MLSP hot-path throughput on B200 (BASELINE.json metric: clouds/sec, B x 1024, k=20).
+
+A "step" is ONE pass of the whole hot path over one batch of synthetic clouds per GPU
+(workload "hotpath-A": 32 x 1024 points, k = 20, the PointDA-10 shape):
+
+  target builder : FPS (PCM split 512+512, utils/pc_utils.py:137) ; PCA normals near=20 ; ball cardinality
+                   r=0.13 + soft labels ; deform_input (voxel mask + in-place collapse + position targets)
+  neighbourhood  : knn + get_graph_feature forward AND backward for the five DGCNN layers
+                   (C = 3, 3, 64, 64, 128 ; PointDA/Models.py:111-127)
+  position loss  : reconstruction_loss (masked Chamfer, both directions) forward + backward
+
+All of it goes through the reference-signature API of mlsp_b200 (ctypes -> libmlsp_b200.so).  The torch
+conv / BN / head layers of DGCNN are out of scope and are not part of the step; the
+layer inputs and upstream gradients they would produce are synthetic tensors resident in HBM.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A|S]
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, batch sharded, weak scaling)
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference
+(oracle/ref_torch.py -- the Python reference itself cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MLSP clouds/sec (Bx1024,k=20)"
+UNIT = "clouds/s"
+LAYER_CHANNELS = (3, 3, 64, 64, 128)          # PointDA/Models.py:111,115,119,123,127
+RADIUS, NUM_CLS, NEAR = 0.13, 16, 20          # PointDA/trainer.py:81-83,98,103-111
+FPS_SPLIT = (512, 512)                        # PCM mix-up: num_pts_a + num_pts_b = N (MLSP/PCM.py:26-30)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------- inputs
+def make_inputs(B, N, k, seed, device, pin=False):
+    """Synthetic batch of the workload shape (CPU generator -> same data on every box)."""
+    from mlsp_b200 import synth
+    clouds = synth.surface_clouds(B, N, seed)
+    feats = [clouds, clouds]
+    for li, C in enumerate(LAYER_CHANNELS[2:]):
+        feats.append(synth.smooth_features(B, C, N, seed + 10 + li))
+    g = torch.Generator().manual_seed(seed + 99)
+    pred = (clouds.permute(0, 2, 1) + 0.05 * torch.randn(B, N, 3, generator=g)).contiguous()
+    host = {"clouds": clouds, "feats": feats, "pred": pred}
+    if device is None:
+        return host
+    if pin:
+        host["clouds"] = clouds.pin_memory()
+    dev = {"clouds": clouds.to(device), "feats": [f.to(device) for f in feats], "pred": pred.to(device)}
+    # upstream gradients of the edge tensors, in the channels_last storage the conv backward produces
+    dev["grads"] = [torch.randn(B, N, k, 2 * C, device=device).permute(0, 3, 1, 2) for C in LAYER_CHANNELS]
+    return host, dev
+
+
+class OpTimer:
+    """CUDA-event brackets per op on the current stream (the stream the kernels are launched on)."""
+
+    def __init__(self, enabled):
+        self.enabled = enabled
+        self.spans = {}
+
+    def __call__(self, name):
+        return _Span(self, name)
+
+    def totals_ms(self):
+        return {n: sum(a.elapsed_time(b) for a, b in ev) for n, ev in self.spans.items()}
+
+    def counts(self):
+        return {n: len(ev) for n, ev in self.spans.items()}
+
+
+class _Span:
+    def __init__(self, timer, name):
+        self.t, self.name = timer, name
+
+    def __enter__(self):
+        if self.t.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if self.t.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.t.spans.setdefault(self.name, []).append((self.a, b))
+
+
+# kernels launched per public-API call (counted from mlsp_b200/csrc: see DESIGN.md "launch inventory")
+LAUNCHES = {"fps": 1, "knn": 2, "edge_fwd": 2, "edge_bwd": 2, "normals": 2 + 1, "density": 1, "deform": 2,
+            "chamfer_fwd": 4, "chamfer_bwd": 2}
+
+
+def gpu_step(M, dev, lookup, k, timer, clouds=None):
+    """One hot-path step through the public API.  Returns (loss tensor, kernel launches)."""
+    clouds = dev["clouds"] if clouds is None else clouds
+    B, _, N = clouds.shape
+    launches = 0
+    # -- target builder (deform first: it holds the only host sync of the step)
+    with timer("deform_input"):
+        gold = clouds
+        X = clouds.clone()
+        X, mask = M.deform_input(X, lookup, "volume_based_voxels", clouds.device)
+    launches += LAUNCHES["deform"]
+    with timer("fps"):
+        for n in FPS_SPLIT:
+            M.farthest_point_sample(None, clouds, n)
+    launches += LAUNCHES["fps"] * len(FPS_SPLIT)
+    pts = clouds.permute(0, 2, 1).contiguous()
+    with timer("pca_normals"):
+        M.estimate_normals(pts, NEAR)
+    launches += LAUNCHES["normals"]
+    with timer("cal_density"):
+        M.cal_density(pts, RADIUS, NUM_CLS)
+    launches += LAUNCHES["density"]
+    # -- neighbourhood engine, five DGCNN layers, forward + backward
+    feats = [clouds, X] + dev["feats"][2:]
+    for li, (f, g) in enumerate(zip(feats, dev["grads"])):
+        C = f.shape[1]
+        f = f.detach().requires_grad_(True)
+        with timer(f"knn_C{C}"):
+            idx = M.knn(f, k)
+        with timer(f"edge_fwd_C{C}"):
+            out = M.get_graph_feature(f, None, k=k, idx=idx)
+        with timer(f"edge_bwd_C{C}"):
+            out.backward(g)
+        launches += LAUNCHES["knn"] + LAUNCHES["edge_fwd"] + LAUNCHES["edge_bwd"]
+    # -- position loss
+    pred = dev["pred"].detach().requires_grad_(True)
+    with timer("chamfer_fwd"):
+        loss = M.reconstruction_loss(pred, gold, mask)
+    with timer("chamfer_bwd"):
+        loss.backward()
+    launches += LAUNCHES["chamfer_fwd"] + LAUNCHES["chamfer_bwd"]
+    return loss, launches
+
+
+def algorithmic_bytes(op, B, N, k):
+    """algorithmic bytes per call (no credit for re-reads)."""
+    if op.startswith("edge_fwd_C") or op.startswith("edge_bwd_C"):
+        C = int(op.split("_C")[1])
+        return 4 * B * C * N + 8 * B * N * k + 8 * B * C * N * k
+    if op.startswith("knn_C"):
+        C = int(op.split("_C")[1])
+        return 4 * B * C * N + 8 * B * N * k
+    return None
+
+
+def algorithmic_flops(op, B, N, k):
+    if op.startswith("knn_C"):
+        C = int(op.split("_C")[1])
+        return 2 * B * N * N * C + 3 * B * N * N
+    return None
+
+
+# --------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_time(B_sample, N, k, seed, repeats=1):
+    """Seconds per hot-path step of the CPU port on B_sample clouds (all host threads)."""
+    from oracle import ref_torch, np_ops
+    torch.set_num_threads(os.cpu_count() or 1)
+    host = make_inputs(B_sample, N, k, seed, None)
+    g = torch.Generator().manual_seed(seed + 99)
+    grads = [torch.randn(B_sample, N, k, 2 * C, generator=g).permute(0, 3, 1, 2) for C in LAYER_CHANNELS]
+    lookup = torch.Tensor(np_ops.region_mean(3))
+    best = float("inf")
+    for _ in range(repeats):
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        t0 = time.perf_counter()
+        ref_torch.hot_path_step(host["clouds"], host["feats"], grads, host["pred"], lookup, k=k, radius=RADIUS,
+                                num_cls=NUM_CLS, near=NEAR, fps_split=FPS_SPLIT)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def run_reference_arm(args, B, N, k, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    probe = cpu_reference_time(2, N, k, 1234)                         # also warms the thread pool
+    budget = 150.0
+    Bs = int(max(1, min(B, (budget / max(args.steps + args.warmup, 1)) / (probe / 2))))
+    for _ in range(args.warmup):
+        cpu_reference_time(Bs, N, k, 1234)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_time(Bs, N, k, 1234)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    val = Bs / dt
+    sample = f"{Bs} of {B} clouds per step (same op list as hotpath-{args.workload}); oracle/ref_torch.py CPU port"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"hotpath-{args.workload}", "clouds_per_gpu": B, "points": N, "k": k,
+                   "layers_C": list(LAYER_CHANNELS), "device": "cpu"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="A", choices=["A", "S"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from mlsp_b200 import synth
+    B, N, k = synth.CONFIGS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, B, N, k, rank, world)
+        return
+
+    import mlsp_b200 as M
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    host, dev = make_inputs(B, N, k, 1234 + rank, device, pin=True)
+    lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=device)
+    np.random.seed(1234 + rank)
+    torch.manual_seed(1234 + rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    off = OpTimer(False)
+    for _ in range(args.warmup):
+        gpu_step(M, dev, lookup, k, off)
+    # ---- timed region 1: device-resident inputs, per-op CUDA-event spans inside it
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    timer = OpTimer(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    launches = 0
+    for _ in range(args.steps):
+        loss, n = gpu_step(M, dev, lookup, k, timer)
+        launches += n
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    # ---- timed region 2: end to end -- pinned host clouds in, loss out, every step
+    for _ in range(2):
+        gpu_step(M, dev, lookup, k, off, clouds=host["clouds"].to(device, non_blocking=True))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        c = host["clouds"].to(device, non_blocking=True)
+        loss, _ = gpu_step(M, dev, lookup, k, off, clouds=c)
+        loss_host = loss.item()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_ms = max_over_ranks(max(dev_ms, wall * 1e3) / args.steps)   # device time == wall here (host-sync'd step)
+    dev_only_ms = max_over_ranks(dev_ms / args.steps)
+    e2e_ms = max_over_ranks(e2e_s * 1e3 / args.steps)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    tot = timer.totals_ms()
+    cnt = timer.counts()
+    per_call_ms = {n: tot[n] / cnt[n] for n in tot}
+    per_step_ms = {n: tot[n] / args.steps for n in tot}
+    # dominant kernel = the hot-path op (with a SURVEY 8d work model) holding the largest share of the step
+    modelled = {n: v for n, v in per_step_ms.items() if algorithmic_bytes(n, B, N, k)}
+    dom = max(modelled, key=modelled.get)
+    roof = None
+    by = algorithmic_bytes(dom, B, N, k)
+    fl = algorithmic_flops(dom, B, N, k)
+    if dom.startswith("edge_") and by:
+        ach = by / (per_call_ms[dom] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "algorithmic_bytes": by, "ms_per_launch": per_call_ms[dom]}
+    elif dom.startswith("knn_") and fl:
+        C = int(dom.split("_C")[1])
+        if C >= 16:
+            ach = fl / (per_call_ms[dom] * 1e-3) / 1e12
+            peak = pk["bf16_tflops"] / 2                      # kind::tf32 denominator
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": pk["source"] + " bf16/2 (tf32)",
+                    "algorithmic_flops": fl, "ms_per_launch": per_call_ms[dom]}
+        else:
+            ach = by / (per_call_ms[dom] * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "algorithmic_bytes": by, "ms_per_launch": per_call_ms[dom]}
+    # secondary rooflines for every neighbourhood-engine op (explains the headline)
+    rooflines = {}
+    for n in per_call_ms:
+        b_ = algorithmic_bytes(n, B, N, k)
+        if b_:
+            rooflines[n] = {"ms": round(per_call_ms[n], 4), "GBps": round(b_ / (per_call_ms[n] * 1e-3) / 1e9, 1),
+                            "hbm_frac": round(b_ / (per_call_ms[n] * 1e-3) / 1e9 / pk["hbm_gbs"], 4)}
+            f_ = algorithmic_flops(n, B, N, k)
+            if f_:
+                rooflines[n]["TFLOPs"] = round(f_ / (per_call_ms[n] * 1e-3) / 1e12, 3)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        Bs = min(B, 16)
+        cpu_reference_time(2, N, k, 1234)                      # warm the thread pool
+        t = cpu_reference_time(Bs, N, k, 1234)
+        cpu = {"value": Bs / t, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 step on {Bs} of {B} clouds, {t:.1f} s; oracle/ref_torch.py (pure-torch port of the reference "
+                         "op composition; pcl pieces as dense-torch restatements)"}
+
+    value = B * world / (step_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"hotpath-{args.workload}", "clouds_per_gpu": B, "points": N, "k": k,
+                   "layers_C": list(LAYER_CHANNELS), "fps_split": list(FPS_SPLIT), "radius": RADIUS, "near": NEAR,
+                   "parallelism": f"batch-sharded x{world}, no data-path collective",
+                   "l2": "per-step working set ~2.9 GB (edge tensors + their gradients) >> 126 MB L2; no explicit flush",
+                   "timing": "K steps between barrier+synchronize; max(CUDA-event, wall) because deform_input syncs"},
+        "device_ms_per_step": dev_only_ms,
+        "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(host["clouds"].numel() * 4), "d2h_bytes_per_step": 4 + 8 * B,
+                "loss": loss_host},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "op_ms_per_step": {n: round(v, 4) for n, v in sorted(per_step_ms.items(), key=lambda kv: -kv[1])},
+        "op_rooflines": rooflines,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,8 +114,10 @@ MLSP_API int mlsp_ball_count_labels(const float *pts, int B, int N, float r2, in
 /* a7 -- kSearchNormalEstimation (PointDA/trainer.py:173-188, PointSegDA/trainer.py:73-88; python-pcl):
  *   unit eigenvector of the smallest eigenvalue of the covariance of the k nearest neighbours (idx from
  *   mlsp_knn_f32 on the same cloud, self included), oriented towards the origin (n.p <= 0).
- *   pts (B,N,3); idx (B,N,k) int64; normals (B,N,3). */
-MLSP_API int mlsp_pca_normals(const float *pts, const int64_t *idx, int B, int N, int k, float *normals, void *stream);
+ *   pts (B,N,3); idx (B,N,k) int64; normals (B,N,3); curvature (B,N) or NULL: pcl's 4th output column,
+ *   lambda_min / (lambda_0 + lambda_1 + lambda_2). */
+MLSP_API int mlsp_pca_normals(const float *pts, const int64_t *idx, int B, int N, int k, float *normals,
+                              float *curvature, void *stream);
 
 /* a9/a10 -- chamfer_distance(p1,p2,mask) MLSP/mlsp.py:115-153 and findneareat_index :196-220, one direction.
  *   D[i][j] = (|p1_i - p2_j|_2)^2 + (mask_j == 0 ? 100 : 0); rowmin/argmin over j (lowest j on ties).

@@ -273,7 +273,7 @@ __device__ __forceinline__ void jacobi_rotate(double &app, double &aqq, double &
 
 __global__ void __launch_bounds__(128)
 pca_normals_kernel(const float *__restrict__ pts, const int64_t *__restrict__ idx, int N, int k,
-                   float *__restrict__ normals, long long total)
+                   float *__restrict__ normals, float *__restrict__ curvature, long long total)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= total) return;
@@ -324,6 +324,10 @@ pca_normals_kernel(const float *__restrict__ pts, const int64_t *__restrict__ id
     normals[p * 3 + 0] = (float)nx;
     normals[p * 3 + 1] = (float)ny;
     normals[p * 3 + 2] = (float)nz;
+    if (curvature) {
+        const double tr = a00 + a11 + a22;
+        curvature[p] = tr > 0.0 ? (float)(fabs(lam) / tr) : 0.0f;
+    }
 }
 
 }  // namespace mlsp
@@ -399,13 +403,13 @@ extern "C" int mlsp_ball_count_labels(const float *pts, int B, int N, float r2, 
 }
 
 extern "C" int mlsp_pca_normals(const float *pts, const int64_t *idx, int B, int N, int k, float *normals,
-                                void *stream)
+                                float *curvature, void *stream)
 {
     using namespace mlsp;
     MLSP_REQUIRE(pts && idx && normals, MLSP_EINVAL, "pca_normals: null pointer");
     MLSP_REQUIRE(B > 0 && N > 0 && k >= 1, MLSP_EINVAL, "pca_normals: bad shape");
     const long long total = (long long)B * N;
-    pca_normals_kernel<<<(unsigned)((total + 127) / 128), 128, 0, as_stream(stream)>>>(pts, idx, N, k, normals, total);
+    pca_normals_kernel<<<(unsigned)((total + 127) / 128), 128, 0, as_stream(stream)>>>(pts, idx, N, k, normals, curvature, total);
     MLSP_LAUNCH_CHECK("pca_normals_kernel");
     return MLSP_OK;
 }

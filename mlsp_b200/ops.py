@@ -180,14 +180,47 @@ def _lookup_host(lookup) -> np.ndarray:
     return hit
 
 
-def _upload_noise(chunks, counts, device):
-    total = int(sum(counts))
-    offsets = np.zeros(len(counts), np.int32)
-    offsets[1:] = np.cumsum(counts[:-1], dtype=np.int64)
+_COV = np.eye(3) * 0.001                                                   # utils/pc_utils.py:122
+
+
+def _mvn_transform():
+    """The matrix np.random.multivariate_normal multiplies its standard normals with: sqrt(s)[:,None]*v from
+    svd(cov).  For cov = 0.001*I it is exactly diagonal, which makes the draw z*diag + mean -- one rounding per
+    element whatever BLAS does -- and lets one standard_normal call serve the whole batch (the legacy
+    generator's stream is continuous across calls).  tests/test_host_logic.py pins this against numpy itself."""
+    _, s, v = np.linalg.svd(_COV)
+    A = np.sqrt(s)[:, None] * v
+    if np.count_nonzero(A - np.diag(np.diag(A))) == 0:
+        return np.diag(A).copy()
+    return None
+
+
+_MVN_DIAG = _mvn_transform()
+
+
+def _draw_gaussians(means, counts):
+    """`draw_from_gaussian(mean_b, n_b)` (utils/pc_utils.py:114-122) for b = 0.., consuming the global numpy RNG
+    exactly like the per-cloud np.random.multivariate_normal calls of the reference.  -> (sum n_b, 3) float64."""
+    counts = np.asarray(counts, dtype=np.int64)
+    total = int(counts.sum())
     if total == 0:
-        return None, torch.from_numpy(offsets).to(device, non_blocking=True)
-    host = torch.from_numpy(np.concatenate(chunks, axis=0).astype(np.float32))
-    return host.to(device, non_blocking=True), torch.from_numpy(offsets).to(device, non_blocking=True)
+        return np.zeros((0, 3))
+    if _MVN_DIAG is None:                                                   # unexpected LAPACK behaviour: slow, same draws
+        return np.concatenate([np.random.multivariate_normal(m, _COV, int(n)) for m, n in zip(means, counts)], axis=0)
+    z = np.random.standard_normal((total, 3))
+    z *= _MVN_DIAG[None, :]
+    z += np.repeat(np.asarray(means, dtype=np.float64), counts, axis=0)
+    return z
+
+
+def _upload_noise(noise, counts, device):
+    counts = np.asarray(counts, dtype=np.int64)
+    offsets = np.zeros(len(counts), np.int32)
+    offsets[1:] = np.cumsum(counts[:-1])
+    off_d = torch.from_numpy(offsets).to(device, non_blocking=True)
+    if noise.shape[0] == 0:
+        return None, off_d
+    return torch.from_numpy(noise.astype(np.float32)).to(device, non_blocking=True), off_d
 
 
 def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxels", device="cuda:0", groups: int = 1):
@@ -212,9 +245,8 @@ def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxel
     noise = offsets = None
     if DefRec_dist == "volume_based_voxels":
         look = _lookup_host(lookup)
-        chunks = [np.random.multivariate_normal(look[chosen[b]], np.eye(3) * 0.001, int(nsel[b]))   # pc_utils.py:122
-                  for b in range(B) if chosen[b] >= 0]
-        noise, offsets = _upload_noise(chunks, np.where(chosen >= 0, nsel, 0), X.device)
+        counts = np.where(chosen >= 0, nsel, 0)
+        noise, offsets = _upload_noise(_draw_gaussians(look[np.maximum(chosen, 0)], counts), counts, X.device)
     with torch.cuda.device(X.device):
         _lib.call("mlsp_region_mask_scatter", _ptr(X), B, C, N, _ptr(region), _ptr(sel[0]), _ptr(noise),
                   _ptr(offsets), _ptr(mask), _stream(X.device))
@@ -241,13 +273,13 @@ def _deform_radius(X: torch.Tensor, mask: torch.Tensor):
     X_h = X.cpu().numpy()
     centres = np.full(B, -1, np.int32)
     chunks, counts = [], np.zeros(B, np.int64)
-    for b in range(B):
+    for b in range(B):                                                     # choice and draw interleave per cloud
         cand = np.nonzero(cnt_h[b] >= MIN_POINTS)[0]                       # pc_utils.py:96-99
         centre = np.random.choice(cand.squeeze())                          # pc_utils.py:102 (same quirks)
         n = int(cnt_h[b, centre])
-        chunks.append(np.random.multivariate_normal(X_h[b, :, centre], np.eye(3) * 0.001, n))
+        chunks.append(_draw_gaussians(X_h[b:b + 1, :, centre], [n]))
         centres[b], counts[b] = centre, n
-    noise, offsets = _upload_noise(chunks, counts, X.device)
+    noise, offsets = _upload_noise(np.concatenate(chunks, axis=0), counts, X.device)
     centres_d = torch.from_numpy(centres).to(X.device, non_blocking=True)
     with torch.cuda.device(X.device):
         _lib.call("mlsp_ball_mask_scatter", _ptr(X), B, C, N, ctypes.c_float(RADIUS ** 2), _ptr(centres_d),
@@ -287,17 +319,20 @@ def cal_density(batch_pts: torch.Tensor, radius: float, num_cls: int, pergroup: 
 
 
 # ----------------------------------------------------------------------------------------------- a7
-def estimate_normals(xyz: torch.Tensor, near: int = 20) -> torch.Tensor:
+def estimate_normals(xyz: torch.Tensor, near: int = 20, return_curvature: bool = False):
     """Batched replacement of the per-cloud python-pcl loop PointDA/trainer.py:524-531 (kSearchNormalEstimation
-    :173-188).  xyz (B,N,3) -> unit normals (B,N,3), oriented towards the origin like pcl's default viewpoint."""
+    :173-188).  xyz (B,N,3) -> unit normals (B,N,3), oriented towards the origin like pcl's default viewpoint;
+    optionally also pcl's 4th column, the surface curvature lambda_min / trace (B,N)."""
     _require_cuda_f32(xyz, "estimate_normals")
     pts = xyz.detach().contiguous()
     B, N, _ = pts.shape
     idx = knn(pts.transpose(1, 2).contiguous(), near)
     normals = torch.empty((B, N, 3), dtype=torch.float32, device=pts.device)
+    curv = torch.empty((B, N), dtype=torch.float32, device=pts.device) if return_curvature else None
     with torch.cuda.device(pts.device):
-        _lib.call("mlsp_pca_normals", _ptr(pts), _ptr(idx), B, N, int(near), _ptr(normals), _stream(pts.device))
-    return normals
+        _lib.call("mlsp_pca_normals", _ptr(pts), _ptr(idx), B, N, int(near), _ptr(normals), _ptr(curv),
+                  _stream(pts.device))
+    return (normals, curv) if return_curvature else normals
 
 
 # ----------------------------------------------------------------------------------------------- a9 / a10

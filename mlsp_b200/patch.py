@@ -1,0 +1,79 @@
+"""Drop-in boundary: rebind the reference's hot-path names to the B200 ops.
+
+The reference has no plugin or FFI layer; its boundary is Python name binding.  `patch()` walks the
+modules that define or captured the hot-path functions and replaces the attributes in place, so
+Models.py / mlsp.py / trainer.py keep calling `get_graph_feature(...)`, `mlsp.deform_input(...)`,
+`mlsp.calc_loss(...)`, `pc_utils.farthest_point_sample(...)` unchanged.
+
+    import mlsp_b200
+    mlsp_b200.patch.install_pcl_shim()        # before the reference imports `pcl`
+    import PointDA.Models, MLSP.mlsp, utils.pc_utils
+    mlsp_b200.patch.patch()                   # rebinds every captured name, returns what it touched
+"""
+from __future__ import annotations
+
+import sys
+
+from . import ops, pcl_shim
+
+# module name -> {attribute: replacement}.  Both `PointDA.model_utils` and the top-level `model_utils`
+# exist as distinct module objects in the reference (PointDA/Models.py:4 vs :10), and Models.py binds
+# get_graph_feature by `from ... import`, so each namespace is listed.
+_NEIGHBOURHOOD = {"knn": ops.knn, "get_graph_feature": ops.get_graph_feature}
+TARGETS = {
+    "PointDA.model_utils": _NEIGHBOURHOOD,
+    "model_utils": _NEIGHBOURHOOD,
+    "PointDA.Models": _NEIGHBOURHOOD,
+    "Models": _NEIGHBOURHOOD,
+    "PointSegDA.Models": _NEIGHBOURHOOD,
+    "utils.pc_utils": {
+        "farthest_point_sample": ops.farthest_point_sample,
+        "assign_region_to_point": ops.assign_region_to_point,
+        "collapse_to_point": ops.collapse_to_point,
+    },
+    "MLSP.mlsp": {
+        "deform_input": ops.deform_input,
+        "chamfer_distance": ops.chamfer_distance,
+        "reconstruction_loss": ops.reconstruction_loss,
+        "findneareat_index": ops.findneareat_index,
+        "findindexs": ops.findindexs,
+        "cal_density": ops.cal_density,
+    },
+}
+
+
+def install_pcl_shim(force: bool = False) -> bool:
+    return pcl_shim.install(force)
+
+
+def patch(modules=None, strict: bool = False):
+    """Rebind the hot-path names in every already-imported reference module (or in `modules`, a dict
+    name -> module object).  Only attributes the module already has are replaced.  Returns a list of
+    "module.attr" strings; with strict=True raises if nothing was patched."""
+    touched = []
+    originals = {}
+    for modname, table in TARGETS.items():
+        mod = (modules or {}).get(modname) or sys.modules.get(modname)
+        if mod is None:
+            continue
+        for attr, fn in table.items():
+            if hasattr(mod, attr) and getattr(mod, attr) is not fn:
+                originals[(modname, attr)] = getattr(mod, attr)
+                setattr(mod, attr, fn)
+                touched.append(f"{modname}.{attr}")
+    patch.originals.update(originals)
+    if strict and not touched:
+        raise RuntimeError("mlsp_b200.patch: no reference module is imported yet")
+    return touched
+
+
+patch.originals = {}
+
+
+def unpatch():
+    """Restore whatever patch() replaced."""
+    for (modname, attr), fn in list(patch.originals.items()):
+        mod = sys.modules.get(modname)
+        if mod is not None:
+            setattr(mod, attr, fn)
+    patch.originals.clear()

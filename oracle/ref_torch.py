@@ -1,0 +1,164 @@
+"""oracle/ref_torch.py -- TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Pure-torch CPU port of the reference's hot-path functions that keeps the reference's *op composition*
+(what it costs on a CPU is the same work: a (B,N,N) sgemm + topk, advanced-index gather + repeat + cat,
+the python FPS loop, the two (B,N,N,3) repeats of the Chamfer, 27 masked assignments ...).  It exists
+because the Python reference at /root/reference cannot travel to the GPU box: `bench.py --impl reference`
+and the `cpu_baseline` leg time THIS on the box's host cores.  Checked against the reference-generated
+goldens in tests/test_oracle_golden.py::test_ref_torch_*.
+
+The two python-pcl pieces (cardinality, normals) are timed through dense-torch restatements and labelled
+as such by bench.py (the reference's kd-tree code is not runnable anywhere we can reach).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def knn(x, k):
+    """PointDA/model_utils.py:9-16."""
+    inner = torch.matmul(x.transpose(2, 1), x).mul_(-2)
+    sq = (x ** 2).sum(dim=1, keepdim=True)
+    neg_d = -sq - inner - sq.transpose(2, 1)
+    return neg_d.topk(k=k, dim=-1)[1]
+
+
+def get_graph_feature(x, k=20, idx=None):
+    """PointDA/model_utils.py:18-42 (same materialisations: transpose copy, gather, repeat, cat, permute)."""
+    B, N = x.size(0), x.size(2)
+    x = x.view(B, -1, N)
+    if idx is None:
+        idx = knn(x, k)
+    flat = (idx + torch.arange(B).view(-1, 1, 1) * N).view(-1)
+    C = x.size(1)
+    pts = x.transpose(2, 1).contiguous()
+    nbr = pts.view(B * N, -1)[flat, :].view(B, N, k, C)
+    ctr = pts.view(B, N, 1, C).repeat(1, 1, k, 1)
+    return torch.cat((nbr - ctr, ctr), dim=3).permute(0, 3, 1, 2)
+
+
+def farthest_point_sample(xyz, npoint):
+    """utils/pc_utils.py:137-161 (python loop of npoint rounds)."""
+    B, C, N = xyz.shape
+    chosen = torch.zeros(B, npoint, dtype=torch.long)
+    vals = torch.zeros(B, C, npoint)
+    mind = torch.full((B, N), 1e10)
+    far = torch.randint(0, N, (B,), dtype=torch.long)
+    rows = torch.arange(B)
+    for s in range(npoint):
+        chosen[:, s] = far
+        c = xyz[rows, :, far].view(B, 3, 1)
+        vals[:, :, s] = c[:, :, 0]
+        d = ((xyz - c) ** 2).sum(1)
+        closer = d < mind
+        mind[closer] = d[closer]
+        far = mind.max(-1)[1]
+    return chosen, vals
+
+
+def assign_region_to_point(X):
+    """utils/pc_utils.py:33-73 (27 box tests with masked assignment)."""
+    n, d = 3, 2 / 3
+    Xc = torch.clamp(X, -0.99999999, 0.99999999)
+    B, _, N = X.shape
+    Y = torch.zeros((B, N), dtype=torch.long)
+    rid = 0
+    for ix in range(n):
+        for iy in range(n):
+            for iz in range(n):
+                tests = [(-1 + ix * d < Xc[:, 0, :]), (Xc[:, 0, :] < -1 + (ix + 1) * d),
+                         (-1 + iy * d < Xc[:, 1, :]), (Xc[:, 1, :] < -1 + (iy + 1) * d),
+                         (-1 + iz * d < Xc[:, 2, :]), (Xc[:, 2, :] < -1 + (iz + 1) * d)]
+                inside = torch.stack(tests, dim=1).min(dim=1)[0]
+                Y[inside] = rid
+                rid += 1
+    return Y
+
+
+def deform_input(X, lookup, min_pts=40):
+    """MLSP/mlsp.py:10-51, 'volume_based_voxels', groups=1 (per cloud, per region host loop)."""
+    regions = assign_region_to_point(X)
+    order = np.random.permutation(27)
+    mask = torch.zeros_like(X)
+    for b in range(X.shape[0]):
+        for i in order:
+            ind = regions[b, :] == i
+            if torch.sum(ind) >= min_pts:
+                mean = lookup[i].cpu().numpy()
+                mask[b, :3, ind] = 1
+                n = int(torch.sum(ind).cpu().numpy())
+                pts = np.random.multivariate_normal(mean, np.eye(3) * 0.001, n).T
+                X[b, :3, ind] = torch.tensor(pts, dtype=torch.float)
+                break
+    return X, mask
+
+
+def chamfer_distance(p1, p2, mask):
+    """MLSP/mlsp.py:115-153 (two (B,N,N,3) repeats, norm**2, +100 penalty, min)."""
+    a = p1.unsqueeze(1).repeat(1, p2.size(1), 1, 1).transpose(1, 2)
+    b = p2.unsqueeze(1).repeat(1, p1.size(1), 1, 1)
+    dist = torch.norm(a - b, 2, dim=3) ** 2
+    mc = mask[:, :, 0]
+    pen = mc.clone()
+    pen[pen == 0] = 100
+    pen[pen == 1] = 0
+    dist = dist + pen.view(dist.size(0), 1, dist.size(2))
+    dist = dist.min(dim=2)[0]
+    per_cloud = (dist * mc).sum(dim=1)
+    return (per_cloud / mc.sum(dim=1)).sum()
+
+
+def reconstruction_loss(pred, gold, mask):
+    """MLSP/mlsp.py:156-182."""
+    gold = gold.clone().permute(0, 2, 1)
+    mask = mask.permute(0, 2, 1)
+    return (1 / pred.size(0)) * (chamfer_distance(gold, pred, mask) + chamfer_distance(pred, gold, mask))
+
+
+def cal_density_dense(pts, radius, num_cls, pergroup=2, shift=0, K=100):
+    """Dense-torch RESTATEMENT of MLSP/mlsp.py:240-272 (the reference uses a python-pcl kd-tree per cloud)."""
+    d = torch.cdist(pts, pts) ** 2
+    cnt = (d < radius * radius).sum(-1).clamp(max=K) - (d[:, :, 0] < radius * radius).long()
+    row = (cnt - shift).clamp(0, (num_cls - 1) * pergroup)
+    lo = torch.div(row, pergroup, rounding_mode="floor")
+    hi = torch.div(row + pergroup - 1, pergroup, rounding_mode="floor")
+    eye = torch.eye(num_cls)
+    return (eye[lo] + eye[hi]) / 2, row
+
+
+def normals_dense(pts, near):
+    """Dense-torch RESTATEMENT of kSearchNormalEstimation PointDA/trainer.py:173-188 (python-pcl)."""
+    idx = knn(pts.transpose(1, 2).contiguous(), near)
+    B, N, _ = pts.shape
+    nb = pts[torch.arange(B).view(-1, 1, 1), idx]
+    d = nb - nb.mean(dim=2, keepdim=True)
+    cov = torch.einsum("bnki,bnkj->bnij", d, d) / near
+    _, v = torch.linalg.eigh(cov)
+    n = v[..., 0]
+    flip = (n * pts).sum(-1, keepdim=True) > 0
+    return torch.where(flip, -n, n)
+
+
+def hot_path_step(clouds, feats, grads, pred, lookup, k=20, radius=0.13, num_cls=16, near=20, fps_split=(512, 512)):
+    """One pass of the MLSP hot path over a batch, CPU torch, same op list as bench.py's GPU step.
+    clouds (B,3,N); feats: list of (B,C,N) layer inputs; grads: list of upstream grads (B,2C,N,k) or None."""
+    pts = clouds.permute(0, 2, 1).contiguous()
+    # target builder
+    for n in fps_split:
+        farthest_point_sample(clouds, n)
+    normals_dense(pts, near)
+    cal_density_dense(pts, radius, num_cls)
+    gold = clouds.clone()
+    X, mask = deform_input(clouds.clone(), lookup)
+    # neighbourhood engine, forward + backward of the edge gather
+    for f, g in zip(feats, grads):
+        f = f.clone().requires_grad_(True)
+        out = get_graph_feature(f, k=k)
+        if g is not None:
+            out.backward(g)
+    # position loss
+    p = pred.clone().requires_grad_(True)
+    loss = reconstruction_loss(p, gold, mask)
+    loss.backward()
+    return float(loss)

@@ -140,3 +140,45 @@ def test_normals_plane():
     n = np_ops.pca_normals(P, 10)
     assert np.allclose(np.abs(n[0, :, 2]), 1.0, atol=1e-9)
     assert (n[0, :, 2] < 0).all()                   # flipped towards the origin: n.p <= 0
+
+
+# ---- the pure-torch port that bench.py times on the CPU (oracle/ref_torch.py) ------------------------------
+def test_ref_torch_port_matches_goldens(golden):
+    import torch
+    from oracle import ref_torch as rt
+    g = golden("knn_q3")
+    idx = rt.knn(torch.from_numpy(g["x"]), int(g["k"])).numpy()
+    assert np.array_equal(np.take_along_axis(g["pd"], idx, 2), np.take_along_axis(g["pd"], g["idx"], 2))
+    g = golden("ggf_3")
+    out = rt.get_graph_feature(torch.from_numpy(g["x"]), k=int(g["k"]), idx=torch.from_numpy(g["idx"]))
+    assert np.array_equal(out.numpy(), g["out"])
+    g = golden("fps")
+    torch.manual_seed(int(g["seed"]))
+    cen, vals = rt.farthest_point_sample(torch.from_numpy(g["xyz"]), int(g["npoint"]))
+    assert np.array_equal(cen.numpy(), g["centroids"]) and np.array_equal(vals.numpy(), g["vals"])
+    g = golden("regions")
+    assert np.array_equal(rt.assign_region_to_point(torch.from_numpy(g["X"])).numpy(), g["Y"])
+    g = golden("deform_voxels_s1")
+    np.random.seed(int(g["seed"]))
+    X, mask = rt.deform_input(torch.from_numpy(g["X0"].copy()), torch.Tensor(np_ops.region_mean(3)))
+    assert np.array_equal(X.numpy(), g["X"]) and np.array_equal(mask.numpy(), g["mask"])
+    g = golden("chamfer")
+    pred = torch.from_numpy(g["pred"]).requires_grad_(True)
+    loss = rt.reconstruction_loss(pred, torch.from_numpy(g["gold"]), torch.from_numpy(g["mask"]))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    np.testing.assert_allclose(pred.grad.numpy(), g["grad"], rtol=1e-5, atol=1e-8)
+
+
+def test_ref_torch_restatements_match_oracle():
+    import torch
+    from oracle import ref_torch as rt
+    from mlsp_b200 import synth
+    pts = synth.surface_clouds(2, 400, 5).permute(0, 2, 1).contiguous()
+    lab, row = rt.cal_density_dense(pts, 0.13, 16)
+    ol, orow = np_ops.cal_density(pts.numpy(), 0.13, 16)
+    assert (row.numpy() != orow).mean() < 5e-3          # cdist rounding at the radius boundary only
+    n = rt.normals_dense(pts, 20).numpy()
+    on, gap = np_ops.pca_normals(pts.numpy(), 20, return_gap=True)
+    ok = gap > 1e-2
+    assert (1 - np.abs((n * on).sum(-1))[ok]).max() < 1e-3
