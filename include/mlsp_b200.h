@@ -62,6 +62,12 @@ MLSP_API size_t mlsp_workspace_bytes(int op, int B, int C, int N, int k);
 MLSP_API int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
                  int flags, void *stream);
 
+/* Test hook for the tcgen05 path of a1 (C in {64,128}, N >= 256): same result as mlsp_knn_f32, and when
+ * `dump` is non-NULL the approximate filter values |x_j|^2 - 2 dot~(x_i,x_j) are written to dump (B,N,N).
+ * After the call ws holds two int32 counters at offset 0: {rows sent to the exact fallback, rows certified}. */
+MLSP_API int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
+                                   float *dump, void *stream);
+
 /* a2 -- get_graph_feature(x, args, k, idx): PointDA/model_utils.py:18-42 == PointSegDA/Models.py:18-45.
  *   out logical shape (B,2C,N,k) stored channels-last, i.e. memory order [B][N][k][2C]:
  *   out[b][i][j][c] = x[b][c][idx[b][i][j]] - x[b][c][i] (c < C),  x[b][c-C][i] (c >= C). */

@@ -21,6 +21,7 @@ from .ops import (  # noqa: F401
     fps_from_start,
     get_graph_feature,
     knn,
+    knn_tensor_debug,
     reconstruction_loss,
     region_mean,
 )

@@ -20,6 +20,7 @@ _F = ctypes.c_float
 # name -> argtypes, in the order of include/mlsp_b200.h
 SIGNATURES = {
     "mlsp_knn_f32": [_P, _I, _I, _I, _I, _P, _P, _Z, _I, _P],
+    "mlsp_knn_tensor_debug": [_P, _I, _I, _I, _I, _P, _P, _Z, _P, _P],
     "mlsp_edge_gather_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P],
     "mlsp_edge_gather_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P],
     "mlsp_fps": [_P, _I, _I, _I, _P, _P, _P, _P],

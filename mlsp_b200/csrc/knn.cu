@@ -20,11 +20,15 @@ constexpr int KNN_TJ = 128;                               // candidates per tile
 constexpr int KNN_CK = 16;                                // channels per shared-memory chunk
 constexpr size_t KNN_WS_HEADER = 256;                     // stats live in the first bytes of the workspace
 
+bool knn_tensor_supported(int B, int C, int N, int k);
+size_t knn_tensor_workspace_bytes(int B, int C, int N);
+int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, cudaStream_t st);
+
 size_t knn_workspace_bytes(int B, int C, int N, int k)
 {
-    (void)C;
-    (void)k;
-    return KNN_WS_HEADER + align_up(sizeof(float) * (size_t)B * N, 256);
+    const size_t exact = KNN_WS_HEADER + align_up(sizeof(float) * (size_t)B * N, 256);
+    if (knn_tensor_supported(B, C, N, k)) return exact > knn_tensor_workspace_bytes(B, C, N) ? exact : knn_tensor_workspace_bytes(B, C, N);
+    return exact;
 }
 
 __global__ void sq_norms_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xx)
@@ -165,10 +169,26 @@ extern "C" int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t 
     MLSP_REQUIRE(k <= 64, MLSP_EUNSUPPORTED, "knn: k=%d > 64 not supported", k);
     MLSP_REQUIRE(B <= 65535, MLSP_EUNSUPPORTED, "knn: B=%d > 65535", B);
     MLSP_REQUIRE(ws_bytes >= knn_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "knn: workspace too small");
-    MLSP_REQUIRE(flags != MLSP_KNN_TENSOR_ONLY, MLSP_EUNSUPPORTED, "knn: tensor path not available for this shape");
     cudaStream_t st = as_stream(stream);
+    const bool tensor_ok = knn_tensor_supported(B, C, N, k);
+    MLSP_REQUIRE(flags != MLSP_KNN_TENSOR_ONLY || tensor_ok, MLSP_EUNSUPPORTED,
+                 "knn: tensor path not available for B=%d C=%d N=%d k=%d", B, C, N, k);
+    if (tensor_ok && flags != MLSP_KNN_EXACT_ONLY) return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, st);
+    MLSP_CUDA(cudaMemsetAsync(ws, 0, KNN_WS_HEADER, st));
     float *xx = reinterpret_cast<float *>(static_cast<char *>(ws) + KNN_WS_HEADER);
     sq_norms_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, C, N, xx);
     MLSP_LAUNCH_CHECK("sq_norms_kernel");
     return launch_exact(x, xx, B, C, N, k, idx, st);
+}
+
+// Test hook: the tensor path with a dump of the approximate filter values v = |x_j|^2 - 2 dot~ (B,N,N).
+extern "C" int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
+                                     float *dump, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(x && idx && ws, MLSP_EINVAL, "knn_tensor_debug: null pointer");
+    MLSP_REQUIRE(k >= 1 && k <= N, MLSP_EINVAL, "knn_tensor_debug: k out of range");
+    MLSP_REQUIRE(knn_tensor_supported(B, C, N, k), MLSP_EUNSUPPORTED, "knn_tensor_debug: shape not supported");
+    MLSP_REQUIRE(ws_bytes >= knn_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "knn_tensor_debug: workspace too small");
+    return knn_tensor_run(x, B, C, N, k, idx, ws, dump, as_stream(stream));
 }

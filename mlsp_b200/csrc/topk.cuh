@@ -12,6 +12,51 @@
 
 namespace mlsp {
 
+// 64-bit ranking key: ascending key order == (value descending, index ascending); dead entries last.
+__device__ __forceinline__ unsigned long long rank_key(float val, int idx, bool live)
+{
+    const float c = __fadd_rn(val, 0.0f);  // -0 -> +0 so equal values give equal keys
+    const uint32_t hi = live ? ~f32_orderable(c) : 0xffffffffu;
+    return ((unsigned long long)hi << 32) | (uint32_t)idx;
+}
+
+// Bitonic sort of 32*KSLOTS keys held as key[s] on lane l <-> element e = s*32 + l, ascending.
+template <int KSLOTS>
+__device__ __forceinline__ void warp_sort_u64(unsigned long long (&key)[KSLOTS])
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int size = 2; size <= 32 * KSLOTS; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int ds = stride / 32;  // partner slot distance; direction depends on the slot only
+#pragma unroll
+                for (int s = 0; s < KSLOTS; ++s) {
+                    if ((s & ds) == 0) {
+                        const bool up = ((s * 32) & size) == 0;
+                        const unsigned long long a = key[s], b = key[s | ds];
+                        const bool a_small = a < b;
+                        key[s] = (a_small == up) ? a : b;
+                        key[s | ds] = (a_small == up) ? b : a;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < KSLOTS; ++s) {
+                    const unsigned long long other = __shfl_xor_sync(MLSP_FULL, key[s], stride);
+                    const int e = s * 32 + lane;
+                    const bool up = (e & size) == 0;
+                    const bool lower = (lane & stride) == 0;
+                    const bool take_min = (lower == up);
+                    const bool other_smaller = other < key[s];
+                    key[s] = (take_min == other_smaller) ? other : key[s];
+                }
+            }
+        }
+    }
+}
+
 template <int KSLOTS>
 struct TopK {
     float v[KSLOTS];
@@ -70,38 +115,8 @@ struct TopK {
     {
         unsigned long long key[KSLOTS];
 #pragma unroll
-        for (int s = 0; s < KSLOTS; ++s) {
-            const float val = __fadd_rn(v[s], 0.0f);  // -0 -> +0 so equal values give equal keys
-            const uint32_t hi = slot_live(s, k) ? ~f32_orderable(val) : 0xffffffffu;
-            key[s] = ((unsigned long long)hi << 32) | (uint32_t)j[s];
-        }
-        const int lane = lane_id();
-#pragma unroll
-        for (int size = 2; size <= 32 * KSLOTS; size <<= 1) {
-#pragma unroll
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                if (stride >= 32) {
-                    // KSLOTS == 2, stride == 32: partner lives in the other slot of the same lane; the
-                    // whole 64-element block is ascending at this size.
-                    if (KSLOTS == 2) {
-                        const unsigned long long a = key[0], b = key[KSLOTS - 1];
-                        key[0] = a < b ? a : b;
-                        key[KSLOTS - 1] = a < b ? b : a;
-                    }
-                } else {
-#pragma unroll
-                    for (int s = 0; s < KSLOTS; ++s) {
-                        const unsigned long long other = __shfl_xor_sync(MLSP_FULL, key[s], stride);
-                        const int e = s * 32 + lane;
-                        const bool up = (e & size) == 0;
-                        const bool lower = (lane & stride) == 0;
-                        const bool take_min = (lower == up);
-                        const bool other_smaller = other < key[s];
-                        key[s] = (take_min == other_smaller) ? other : key[s];
-                    }
-                }
-            }
-        }
+        for (int s = 0; s < KSLOTS; ++s) key[s] = rank_key(v[s], j[s], slot_live(s, k));
+        warp_sort_u64<KSLOTS>(key);
 #pragma unroll
         for (int s = 0; s < KSLOTS; ++s) j[s] = (int)(uint32_t)(key[s] & 0xffffffffull);
     }

@@ -45,9 +45,11 @@ def _workspace(op: int, B: int, C: int, N: int, k: int, device) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------- a1
-def knn(x: torch.Tensor, k: int, flags: int = _lib.KNN_AUTO) -> torch.Tensor:
+def knn(x: torch.Tensor, k: int, flags: int = _lib.KNN_AUTO, return_stats: bool = False):
     """knn(x, k): PointDA/model_utils.py:9-16 == PointSegDA/Models.py:8-15.
-    x (B,C,N) -> idx (B,N,k) int64, nearest first (self at rank 0), ties by lowest index."""
+    x (B,C,N) -> idx (B,N,k) int64, nearest first (self at rank 0), ties by lowest index.
+    C in {64,128} with N >= 256 runs on the tcgen05 tensor-core path (filter + exact re-rank, same bits);
+    return_stats=True also returns {"fallback_rows", "certified_rows"} (forces a device sync; diagnostics)."""
     _require_cuda_f32(x, "knn")
     if x.dim() != 3:
         raise MlspError(f"knn: expected (B,C,N), got {tuple(x.shape)}")
@@ -59,7 +61,25 @@ def knn(x: torch.Tensor, k: int, flags: int = _lib.KNN_AUTO) -> torch.Tensor:
     with torch.cuda.device(x.device):
         ws = _workspace(_lib.OP_KNN, B, C, N, k, x.device)
         _lib.call("mlsp_knn_f32", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(), flags, _stream(x.device))
+    if return_stats:
+        c = ws[:8].view(torch.int32).cpu()
+        return idx, {"fallback_rows": int(c[0]), "certified_rows": int(c[1])}
     return idx
+
+
+def knn_tensor_debug(x: torch.Tensor, k: int):
+    """Test hook: tcgen05 path with a dump of the approximate filter values.  -> (idx, v (B,N,N), stats)."""
+    _require_cuda_f32(x, "knn_tensor_debug")
+    x = x.detach().contiguous()
+    B, C, N = x.shape
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+    dump = torch.full((B, N, N), float("nan"), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = _workspace(_lib.OP_KNN, B, C, N, k, x.device)
+        _lib.call("mlsp_knn_tensor_debug", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(), _ptr(dump),
+                  _stream(x.device))
+    c = ws[:8].view(torch.int32).cpu()
+    return idx, dump, {"fallback_rows": int(c[0]), "certified_rows": int(c[1])}
 
 
 # ----------------------------------------------------------------------------------------------- a2

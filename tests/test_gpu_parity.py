@@ -324,3 +324,45 @@ def test_ops_follow_current_stream(dev, orc):
     s.synchronize()
     assert np.array_equal(_np(idx), orc.knn(x.numpy(), 20))
     assert np.array_equal(_np(out.permute(0, 2, 3, 1)), orc.edge_gather(x.numpy(), _np(idx)))
+
+
+# ------------------------------------------------------------------------------------------------ a1, tcgen05 path
+@pytest.mark.parametrize("B,C,N,k", [(2, 64, 512, 20), (2, 128, 640, 20), (1, 64, 1000, 40)])
+def test_knn_tensor_filter_values(dev, B, C, N, k):
+    """The tensor-core filter values v = |x_j|^2 - 2 dot~ must sit within the certified error bound of the
+    exact values (this is what makes the candidate list a superset of the exact top-k)."""
+    x = synth.smooth_features(B, C, N, 55)
+    idx, v, stats = M.knn_tensor_debug(x.to(dev), k)
+    xd = x.double()
+    xx = (xd ** 2).sum(1)                                              # (B,N)
+    exact = xx[:, None, :] - 2 * torch.einsum("bci,bcj->bij", xd, xd)   # (B,N,N): |x_j|^2 - 2 x_i.x_j
+    err = (v.cpu().double() - exact).abs()
+    assert torch.isfinite(v).all()
+    bound = 2.0 ** -11 * xx.sqrt()[:, :, None] * xx.sqrt().amax(dim=1)[:, None, None]
+    assert (err <= bound).all(), float((err / bound).max())
+    assert float((err / bound).max()) < 0.5                            # 2x safety margin actually present
+    assert stats["certified_rows"] + stats["fallback_rows"] == B * N
+
+
+@pytest.mark.parametrize("B,C,N,k,quant", [(32, 64, 1024, 20, False), (32, 128, 1024, 20, False),
+                                           (16, 64, 2048, 20, False), (4, 128, 4096, 40, False),
+                                           (4, 64, 1024, 20, True), (3, 64, 1000, 20, False), (2, 128, 300, 33, False)])
+def test_knn_tensor_matches_oracle(dev, orc, B, C, N, k, quant):
+    x = synth.features(B, C, N, 77, quantised=True) if quant else synth.smooth_features(B, C, N, 77)
+    idx, stats = M.knn(x.to(dev), k, flags=M._lib.KNN_TENSOR_ONLY, return_stats=True)
+    ref = orc.knn(x.numpy(), k)
+    assert np.array_equal(_np(idx), ref)
+    assert stats["certified_rows"] + stats["fallback_rows"] == B * N
+    if not quant:
+        assert stats["fallback_rows"] <= 0.05 * B * N, stats            # the filter certifies nearly every row
+    exact = M.knn(x.to(dev), k, flags=M._lib.KNN_EXACT_ONLY)
+    assert torch.equal(exact, idx)
+
+
+def test_knn_tensor_ties_and_duplicates(dev, orc):
+    x = synth.smooth_features(2, 64, 512, 5)
+    x[:, :, 100:140] = x[:, :, 100:101]                                # 40 duplicate points: exact ties
+    x[1] = 0.0                                                         # a degenerate cloud: everything ties
+    idx, stats = M.knn(x.to(dev), 20, flags=M._lib.KNN_TENSOR_ONLY, return_stats=True)
+    assert np.array_equal(_np(idx), orc.knn(x.numpy(), 20))
+    assert stats["fallback_rows"] >= 512                               # the all-ties cloud cannot be certified
