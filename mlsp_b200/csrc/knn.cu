@@ -2,11 +2,12 @@
 //
 // Exact fp32 path on the CUDA cores.  Arithmetic is pinned to oracle/mlsp_oracle.c:orc_knn:
 //   xx_j = sum_c rn(x_cj^2)              (sequential adds, channel order)
-//   dot  = rn(x_0i x_0j), then fmaf chain over c = 1..C-1
+//   dot  = 8 interleaved fmaf chains (channel groups of 4, round robin) + fixed butterfly tree (dot_tree);
+//          a single sequential chain when C <= 4
 //   pd   = rn( rn(2 dot - xx_j) - xx_i ) == ((-xx_j) - (-2 dot)) - xx_i of the reference
 // and the ranking is (pd descending, index ascending).  Nothing of size (B,N,N) is materialised: a CTA
-// keeps 64 query rows in shared memory, streams candidate tiles through shared memory, and each warp
-// maintains the running top-k of its 8 rows in registers (topk.cuh), so the HBM traffic is the
+// keeps its query rows in shared memory, streams candidate tiles through shared memory, and each warp
+// maintains the running top-k of its rows in registers (topk.cuh), so the HBM traffic is the
 // algorithmic 4BCN + 8BNk bytes plus L2-resident re-reads of the cloud.
 #include "common.cuh"
 #include "topk.cuh"
@@ -14,10 +15,7 @@
 namespace mlsp {
 
 constexpr int KNN_THREADS = 256;
-constexpr int KNN_R = 8;                                  // query rows per warp
-constexpr int KNN_ROWS = (KNN_THREADS / 32) * KNN_R;      // 64 query rows per CTA
 constexpr int KNN_TJ = 128;                               // candidates per tile (4 per lane)
-constexpr int KNN_CK = 16;                                // channels per shared-memory chunk
 constexpr size_t KNN_WS_HEADER = 256;                     // stats live in the first bytes of the workspace
 
 bool knn_tensor_supported(int B, int C, int N, int k);
@@ -46,42 +44,52 @@ __global__ void sq_norms_kernel(const float *__restrict__ x, int C, int N, float
     xx[(size_t)b * N + j] = s;
 }
 
-template <int KSLOTS>
+// NPART = number of interleaved partial chains of the pinned dot product (oracle dot_tree):
+//   C <= 4 : one chain (NPART = 1, 8 rows per warp);  otherwise 8 chains + butterfly (NPART = 8, 2 rows per warp).
+template <int KSLOTS, int NPART, int R>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
 knn_exact_kernel(const float *__restrict__ x, const float *__restrict__ xx, int C, int N, int k,
                  int64_t *__restrict__ idx)
 {
+    constexpr int ROWS = (KNN_THREADS / 32) * R;
+    constexpr int CK = (NPART == 1) ? 4 : 32;          // channels per shared-memory chunk (32 = one round of the 8 chains)
     extern __shared__ __align__(16) float smem[];
-    float *rows_s = smem;                              // [C][KNN_ROWS]
-    float *cand_s = rows_s + (size_t)C * KNN_ROWS;     // [KNN_CK][KNN_TJ]
-    float *cn_s = cand_s + KNN_CK * KNN_TJ;            // [KNN_TJ] candidate norms
+    float *rows_s = smem;                              // [C][ROWS]
+    float *cand_s = rows_s + (size_t)C * ROWS;         // [CK][KNN_TJ]
+    float *cn_s = cand_s + CK * KNN_TJ;                // [KNN_TJ] candidate norms
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
-    const int i0 = blockIdx.x * KNN_ROWS;
+    const int i0 = blockIdx.x * ROWS;
     const float *xb = x + (size_t)b * C * N;
     const float *xxb = xx + (size_t)b * N;
 
-    for (int e = tid; e < C * KNN_ROWS; e += KNN_THREADS) {
-        const int c = e / KNN_ROWS, r = e % KNN_ROWS;
+    for (int e = tid; e < C * ROWS; e += KNN_THREADS) {
+        const int c = e / ROWS, r = e % ROWS;
         const int i = i0 + r;
         rows_s[e] = (i < N) ? xb[(size_t)c * N + i] : 0.0f;
     }
-    float xxi[KNN_R];
+    float xxi[R];
 #pragma unroll
-    for (int rr = 0; rr < KNN_R; ++rr) {
-        const int i = i0 + warp * KNN_R + rr;
+    for (int rr = 0; rr < R; ++rr) {
+        const int i = i0 + warp * R + rr;
         xxi[rr] = (i < N) ? xxb[i] : 0.0f;
     }
-    TopK<KSLOTS> top[KNN_R];
+    TopK<KSLOTS> top[R];
 #pragma unroll
-    for (int rr = 0; rr < KNN_R; ++rr) top[rr].init(k);
+    for (int rr = 0; rr < R; ++rr) top[rr].init(k);
 
     for (int j0 = 0; j0 < N; j0 += KNN_TJ) {
-        float acc[KNN_R][4];
-        for (int c0 = 0; c0 < C; c0 += KNN_CK) {
+        float acc[R][4][NPART];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+#pragma unroll
+                for (int t = 0; t < NPART; ++t) acc[rr][s][t] = 0.0f;
+        for (int c0 = 0; c0 < C; c0 += CK) {
             __syncthreads();  // previous chunk (and, first time, rows_s) settled
-            for (int e = tid; e < KNN_CK * KNN_TJ; e += KNN_THREADS) {
+            for (int e = tid; e < CK * KNN_TJ; e += KNN_THREADS) {
                 const int cc = e / KNN_TJ, jj = e % KNN_TJ;
                 const int c = c0 + cc, j = j0 + jj;
                 cand_s[e] = (c < C && j < N) ? xb[(size_t)c * N + j] : 0.0f;
@@ -89,26 +97,24 @@ knn_exact_kernel(const float *__restrict__ x, const float *__restrict__ xx, int 
             if (c0 == 0 && tid < KNN_TJ) cn_s[tid] = (j0 + tid < N) ? xxb[j0 + tid] : 0.0f;
             __syncthreads();
 #pragma unroll
-            for (int cc = 0; cc < KNN_CK; ++cc) {
+            for (int cc = 0; cc < CK; ++cc) {
                 const int c = c0 + cc;
                 if (c < C) {
-                    const float4 ra = *reinterpret_cast<const float4 *>(&rows_s[c * KNN_ROWS + warp * KNN_R]);
-                    const float4 rb = *reinterpret_cast<const float4 *>(&rows_s[c * KNN_ROWS + warp * KNN_R + 4]);
-                    const float rv[KNN_R] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+                    float rv[R];
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) rv[rr] = rows_s[c * ROWS + warp * R + rr];
                     float cv[4];
 #pragma unroll
                     for (int s = 0; s < 4; ++s) cv[s] = cand_s[cc * KNN_TJ + s * 32 + lane];
-                    if (c == 0) {
+                    constexpr int dummy = 0;
+                    const int t = (NPART == 1) ? dummy : (cc >> 2);      // (c/4) mod 8, static: c0 is a multiple of 32
 #pragma unroll
-                        for (int rr = 0; rr < KNN_R; ++rr)
+                    for (int rr = 0; rr < R; ++rr)
 #pragma unroll
-                            for (int s = 0; s < 4; ++s) acc[rr][s] = __fmul_rn(rv[rr], cv[s]);
-                    } else {
+                        for (int s = 0; s < 4; ++s)
 #pragma unroll
-                        for (int rr = 0; rr < KNN_R; ++rr)
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) acc[rr][s] = __fmaf_rn(rv[rr], cv[s], acc[rr][s]);
-                    }
+                            for (int tt = 0; tt < NPART; ++tt)
+                                if (tt == t) acc[rr][s][tt] = __fmaf_rn(rv[rr], cv[s], acc[rr][s][tt]);
                 }
             }
         }
@@ -116,19 +122,28 @@ knn_exact_kernel(const float *__restrict__ x, const float *__restrict__ xx, int 
 #pragma unroll
         for (int s = 0; s < 4; ++s) cn[s] = cn_s[s * 32 + lane];
 #pragma unroll
-        for (int rr = 0; rr < KNN_R; ++rr) {
+        for (int rr = 0; rr < R; ++rr) {
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int j = j0 + s * 32 + lane;
-                const float t = __fmaf_rn(2.0f, acc[rr][s], -cn[s]);
+                float dot;
+                if (NPART == 1) {
+                    dot = acc[rr][s][0];
+                } else {
+                    const float *p = acc[rr][s];
+                    const float q0 = __fadd_rn(p[0], p[4 % NPART]), q1 = __fadd_rn(p[1 % NPART], p[5 % NPART]);
+                    const float q2 = __fadd_rn(p[2 % NPART], p[6 % NPART]), q3 = __fadd_rn(p[3 % NPART], p[7 % NPART]);
+                    dot = __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3));
+                }
+                const float t = __fmaf_rn(2.0f, dot, -cn[s]);
                 const float pd = __fsub_rn(t, xxi[rr]);
                 top[rr].offer(pd, j, j < N);
             }
         }
     }
 #pragma unroll
-    for (int rr = 0; rr < KNN_R; ++rr) {
-        const int i = i0 + warp * KNN_R + rr;
+    for (int rr = 0; rr < R; ++rr) {
+        const int i = i0 + warp * R + rr;
         top[rr].finish(k);
         if (i < N) {
 #pragma unroll
@@ -140,21 +155,25 @@ knn_exact_kernel(const float *__restrict__ x, const float *__restrict__ xx, int 
     }
 }
 
+template <int KSLOTS, int NPART, int R>
+static int launch_exact_t(const float *x, const float *xx, int B, int C, int N, int k, int64_t *idx, cudaStream_t st)
+{
+    constexpr int ROWS = (KNN_THREADS / 32) * R;
+    constexpr int CK = (NPART == 1) ? 4 : 32;
+    const size_t smem = sizeof(float) * ((size_t)C * ROWS + CK * KNN_TJ + KNN_TJ);
+    MLSP_REQUIRE(smem <= 200 * 1024, MLSP_EUNSUPPORTED, "knn: C=%d too large for the exact kernel", C);
+    dim3 grid((N + ROWS - 1) / ROWS, B);
+    MLSP_CUDA(cudaFuncSetAttribute(knn_exact_kernel<KSLOTS, NPART, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_exact_kernel<KSLOTS, NPART, R><<<grid, KNN_THREADS, smem, st>>>(x, xx, C, N, k, idx);
+    MLSP_LAUNCH_CHECK("knn_exact_kernel");
+    return MLSP_OK;
+}
+
 static int launch_exact(const float *x, const float *xx, int B, int C, int N, int k, int64_t *idx,
                         cudaStream_t st)
 {
-    const size_t smem = sizeof(float) * ((size_t)C * KNN_ROWS + KNN_CK * KNN_TJ + KNN_TJ);
-    MLSP_REQUIRE(smem <= 200 * 1024, MLSP_EUNSUPPORTED, "knn: C=%d too large for the exact kernel", C);
-    dim3 grid((N + KNN_ROWS - 1) / KNN_ROWS, B);
-    if (k <= 32) {
-        MLSP_CUDA(cudaFuncSetAttribute(knn_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_exact_kernel<1><<<grid, KNN_THREADS, smem, st>>>(x, xx, C, N, k, idx);
-    } else {
-        MLSP_CUDA(cudaFuncSetAttribute(knn_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_exact_kernel<2><<<grid, KNN_THREADS, smem, st>>>(x, xx, C, N, k, idx);
-    }
-    MLSP_LAUNCH_CHECK("knn_exact_kernel");
-    return MLSP_OK;
+    if (C <= 4) return k <= 32 ? launch_exact_t<1, 1, 8>(x, xx, B, C, N, k, idx, st) : launch_exact_t<2, 1, 8>(x, xx, B, C, N, k, idx, st);
+    return k <= 32 ? launch_exact_t<1, 8, 2>(x, xx, B, C, N, k, idx, st) : launch_exact_t<2, 8, 2>(x, xx, B, C, N, k, idx, st);
 }
 
 }  // namespace mlsp

@@ -14,11 +14,11 @@
 //              registers; tau = k-th smallest class minimum is an upper bound of the k-th distance.
 //      pass 2: the same tiles again (the MMA is cheap); columns with v <= tau + 2 eps are appended to the
 //              row's candidate list in shared memory (about 1.5 k entries expected, capacity 2 NG).
-//      refine: one warp per row recomputes the candidates' distances with the exact fp32 chain of the
-//              specification and sorts them (value desc, index asc); the first k are the answer.
-//      eps bounds |v - exact| so every member of the exact top-k (ties included) is in the list; a row whose
-//      list overflows is not certified and goes to
-//   3. a fallback kernel (exact streaming top-k, one warp per listed row).
+//      eps bounds |v - exact| so every member of the exact top-k (ties included) is in the list.
+//   3. refine kernel (high occupancy, one warp per row): recomputes the candidates' distances with the exact
+//      fp32 chain of the specification and sorts them (value desc, index asc); the first k are the answer.
+//      A row whose list overflowed is not certified and goes to
+//   4. a fallback kernel (exact streaming top-k, one warp per listed row).
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA) -- profiles/.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -31,10 +31,14 @@ namespace mlsp {
 constexpr int KT_ROWS = 128;     // query rows per CTA   (UMMA M, TMEM lanes)
 constexpr int KT_COLS = 128;     // candidates per tile  (UMMA N, TMEM columns per accumulator buffer)
 constexpr int KT_KBLK = 64;      // bf16 per K block = one 128-byte swizzle span
-constexpr int KT_STAGES = 4;
-constexpr int KT_THREADS = 192;
+constexpr int KT_MAX_STAGES = 4;
+constexpr int KT_EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes one 64-column half of every tile
+constexpr int KT_THREADS = 64 + 32 * KT_EPI_WARPS;
 constexpr uint32_t KT_BLK_BYTES = KT_COLS * KT_KBLK * 2;  // 16 KiB per (128 x 64) bf16 block
-constexpr float KT_EPS_REL = 4.8828125e-4f;               // 2^-11: |v - exact| <= KT_EPS_REL |x_i| max|x_j|
+// |v - exact| <= KT_EPS_REL |x_i| max_j|x_j| :  dropped lo.lo and split residuals are <= 3*2^-16 |x_i||x_j| on the
+// dot product (Cauchy-Schwarz), i.e. 9.2e-5 on v; 2^-12 = 2.4e-4 leaves > 2.5x for the tensor core's fp32
+// accumulation and the specification's own roundings.  Measured worst case: 0.12 of this bound (tests).
+constexpr float KT_EPS_REL = 2.44140625e-4f;
 
 // ---------------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,7 +109,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&r)[32])
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * KT_EPI_WARPS) : "memory"); }
 
 // K-major, 128-byte swizzled operand block (rows 128 B apart, 8-row groups 1024 B apart), sm_100 version bit
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
@@ -163,24 +167,27 @@ __global__ void knn_prep_kernel(const float *__restrict__ x, int C, int N, float
 }
 
 // ------------------------------------------------------------------------------------------- helpers
-// exact specification distance of (i, j) from point-major rows: fmul then fmaf chain in channel order
+// exact specification distance of (i, j) from point-major rows (oracle dot_tree): 8 interleaved fmaf chains
+// over groups of 4 channels, fixed butterfly.  One lane does the whole candidate; requires C % 32 == 0.
 __device__ __forceinline__ float exact_pd(const float4 *__restrict__ xi, const float4 *__restrict__ xj, int C4,
                                           float xxi, float xxj)
 {
-    float4 a = xi[0], q = xj[0];
-    float acc = __fmul_rn(a.x, q.x);
-    acc = __fmaf_rn(a.y, q.y, acc);
-    acc = __fmaf_rn(a.z, q.z, acc);
-    acc = __fmaf_rn(a.w, q.w, acc);
-    for (int c = 1; c < C4; ++c) {
-        a = xi[c];
-        q = xj[c];
-        acc = __fmaf_rn(a.x, q.x, acc);
-        acc = __fmaf_rn(a.y, q.y, acc);
-        acc = __fmaf_rn(a.z, q.z, acc);
-        acc = __fmaf_rn(a.w, q.w, acc);
+    float p[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) p[t] = 0.0f;
+    for (int f0 = 0; f0 < C4; f0 += 8) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const float4 a = xi[f0 + t], q = xj[f0 + t];
+            p[t] = __fmaf_rn(a.x, q.x, p[t]);
+            p[t] = __fmaf_rn(a.y, q.y, p[t]);
+            p[t] = __fmaf_rn(a.z, q.z, p[t]);
+            p[t] = __fmaf_rn(a.w, q.w, p[t]);
+        }
     }
-    return __fsub_rn(__fmaf_rn(2.0f, acc, -xxj), xxi);
+    const float q0 = __fadd_rn(p[0], p[4]), q1 = __fadd_rn(p[1], p[5]), q2 = __fadd_rn(p[2], p[6]), q3 = __fadd_rn(p[3], p[7]);
+    const float dot = __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3));
+    return __fsub_rn(__fmaf_rn(2.0f, dot, -xxj), xxi);
 }
 
 // thread-local bitonic sort of NG registers, ascending
@@ -214,8 +221,11 @@ struct KtParams {
     int *fb_count;           // fallback row counter
     int *fb_rows;            // fallback rows (b*N + i)
     int *stats;              // [0] rows certified by the tensor path
+    uint16_t *cand;          // (B*N, CAP) candidate lists handed from the main kernel to the refine kernel
+    int *cand_cnt;           // (B*N) list lengths (> CAP: overflowed)
     float *dump;             // optional (B,N,N) approximate values (tests only)
     int N, C, k, T;          // T = candidate tiles per cloud
+    int stages;              // depth of the B-operand smem ring (2: two CTAs per SM at C = 64, 4 at C = 128)
 };
 
 // ------------------------------------------------------------------------------------------- main kernel
@@ -228,13 +238,16 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms need 1 KiB alignment
     const int KB = 3 * P.C / KT_KBLK;       // K blocks per tile (3 or 6)
     const int SEG = P.C / KT_KBLK;          // K blocks per hi / lo segment
+    const int STAGES = P.stages;
     uint8_t *sA = smem_raw;                                   // KB blocks, resident
-    uint8_t *sB = sA + (size_t)KB * KT_BLK_BYTES;             // KT_STAGES blocks, ring
-    uint16_t *lists = reinterpret_cast<uint16_t *>(sB + (size_t)KT_STAGES * KT_BLK_BYTES);   // [128][CAP]
+    uint8_t *sB = sA + (size_t)KB * KT_BLK_BYTES;             // STAGES blocks, ring
+    uint16_t *lists = reinterpret_cast<uint16_t *>(sB + (size_t)STAGES * KT_BLK_BYTES);      // [128][CAP]
+    float *xchg = reinterpret_cast<float *>(lists);            // [128][NG] class minima of the upper half (aliases lists)
     float *nrm_s = reinterpret_cast<float *>(lists + KT_ROWS * CAP);                            // [2][128]
-    int *cnt_s = reinterpret_cast<int *>(nrm_s + 2 * KT_COLS);                                 // [128]
+    float *thr_s = nrm_s + 2 * KT_COLS;                                                         // [128]
+    int *cnt_s = reinterpret_cast<int *>(thr_s + KT_ROWS);                                      // [128]
     uint64_t *bars = reinterpret_cast<uint64_t *>(cnt_s + KT_ROWS);
-    uint64_t *full = bars, *empty = bars + KT_STAGES, *a_full = bars + 2 * KT_STAGES;
+    uint64_t *full = bars, *empty = bars + KT_MAX_STAGES, *a_full = bars + 2 * KT_MAX_STAGES;
     uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
 
@@ -244,17 +257,18 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     const int rowbase = b * N;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < KT_STAGES; ++s) {
+        for (int s = 0; s < KT_MAX_STAGES; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
         mbar_init(a_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(tm_full + s, 1);
-            mbar_init(tm_empty + s, 4);
+            mbar_init(tm_empty + s, KT_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < KT_ROWS) cnt_s[threadIdx.x] = 0;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -272,17 +286,17 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 const int seg = kb / SEG, within = kb - seg * SEG;
                 tma_load_2d(sA + (size_t)kb * KT_BLK_BYTES, seg == 2 ? &map_lo : &map_hi, within * KT_KBLK, rowbase + i0, a_full);
             }
-            int it = 0;
+            int stage = 0;
+            uint32_t ph = 0;
             for (int g = 0; g < 2 * T; ++g) {
                 const int j0 = (g % T) * KT_COLS;
-                for (int kb = 0; kb < KB; ++kb, ++it) {   // B' = [hi | lo | hi]
-                    const int stage = it % KT_STAGES;
-                    const uint32_t ph = (it / KT_STAGES) & 1;
+                for (int kb = 0; kb < KB; ++kb) {   // B' = [hi | lo | hi]
                     mbar_wait(empty + stage, ph ^ 1);
                     mbar_expect_tx(full + stage, KT_BLK_BYTES);
                     const int seg = kb / SEG, within = kb - seg * SEG;
                     tma_load_2d(sB + (size_t)stage * KT_BLK_BYTES, seg == 1 ? &map_lo : &map_hi, within * KT_KBLK,
                                 rowbase + j0, full + stage);
+                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
             }
         }
@@ -291,15 +305,15 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         // ================================ MMA issuer ==================================
         if (lane == 0) {
             mbar_wait(a_full, 0);
-            int it = 0;
+            int stage = 0;
+            uint32_t ph = 0;
             for (int g = 0; g < 2 * T; ++g) {
                 const int buf = g & 1;
                 mbar_wait(tm_empty + buf, ((g >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)buf * KT_COLS;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
-                    const int stage = it % KT_STAGES;
-                    mbar_wait(full + stage, (it / KT_STAGES) & 1);
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(full + stage, ph);
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(smem_u32(sA + (size_t)kb * KT_BLK_BYTES));
                     const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * KT_BLK_BYTES));
@@ -307,17 +321,20 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                     for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)   // +32 bytes per K=16 step inside the swizzle span
                         tc_mma_bf16(d, da + 2 * k16, db + 2 * k16, KT_IDESC, (kb | k16) != 0);
                     tc_commit(empty + stage);                       // smem stage reusable when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
                 tc_commit(tm_full + buf);                           // accumulator of tile g complete
             }
         }
         __syncwarp();
     } else {
-        // ================================ epilogue: one thread per query row ===========
-        const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+        // ================================ epilogue: two threads per query row ===========
+        // warp w (2..9): TMEM lane quadrant q = w & 3 (hardware rule), column half h = (w - 2) >> 2.
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
         const int r = q * 32 + lane;             // row within the tile
         const int i = i0 + r;
-        const int et = threadIdx.x - 64;         // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 64;         // 0..255 among the epilogue threads
         const float xxi = (i < N) ? P.xx[(size_t)rowbase + i] : 0.0f;
         const float eps = KT_EPS_REL * sqrtf(xxi) * sqrtf(P.maxxx[b]);
         float gmin[NG];
@@ -325,28 +342,38 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         for (int e = 0; e < NG; ++e) gmin[e] = INFINITY;
         float thr = 0.0f;
         uint16_t *my_list = lists + r * CAP;
-        int cnt = 0;
         for (int g = 0; g < 2 * T; ++g) {
             const int buf = g & 1, t = g % T, j0 = t * KT_COLS;
             if (g == T) {
-                // ---- between the passes: tau = k-th smallest class minimum (thread-local sorting network)
-                reg_sort<NG>(gmin);
-                float tau = gmin[0];
+                // ---- between the passes: merge the two halves' class minima, tau = k-th smallest, broadcast thr
+                if (h == 1) {
 #pragma unroll
-                for (int e = 1; e < NG; ++e) tau = (e == P.k - 1) ? gmin[e] : tau;
-                thr = tau + 2.0f * eps;
+                    for (int e = 0; e < NG; ++e) xchg[e * KT_ROWS + r] = gmin[e];
+                }
+                epi_bar_sync();
+                if (h == 0) {
+#pragma unroll
+                    for (int e = 0; e < NG; ++e) gmin[e] = fminf(gmin[e], xchg[e * KT_ROWS + r]);
+                    reg_sort<NG>(gmin);
+                    float tau = gmin[0];
+#pragma unroll
+                    for (int e = 1; e < NG; ++e) tau = (e == P.k - 1) ? gmin[e] : tau;
+                    thr_s[r] = tau + 2.0f * eps;
+                }
+                epi_bar_sync();                  // xchg (aliasing the lists) is dead from here on
+                thr = thr_s[r];
             }
-            {
+            if (et < KT_COLS) {
                 const int j = j0 + et;
                 nrm_s[buf * KT_COLS + et] = (j < N) ? P.xx[(size_t)rowbase + j] : INFINITY;
             }
             epi_bar_sync();
             mbar_wait(tm_full + buf, (g >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * KT_COLS;
-            const float4 *nrm4 = reinterpret_cast<const float4 *>(nrm_s + buf * KT_COLS);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * KT_COLS + (uint32_t)h * 64;
+            const float4 *nrm4 = reinterpret_cast<const float4 *>(nrm_s + buf * KT_COLS + h * 64);
 #pragma unroll
-            for (int ch = 0; ch < KT_COLS / 32; ++ch) {
+            for (int ch = 0; ch < 2; ++ch) {
                 float acc[32];
                 tc_ld32(taddr + ch * 32, acc);
                 float v[32];
@@ -361,23 +388,23 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 if (g < T) {
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        const int e = (NG == 32) ? c : ((ch & 1) * 32 + c);   // column class j mod NG (static)
+                        const int e = (NG == 32) ? c : (ch * 32 + c);   // column class j mod NG (static)
                         gmin[e] = fminf(gmin[e], v[c]);
                     }
                     if (P.dump && i < N) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            const int j = j0 + ch * 32 + c;
+                            const int j = j0 + h * 64 + ch * 32 + c;
                             if (j < N) P.dump[((size_t)rowbase + i) * N + j] = v[c];
                         }
                     }
                 } else {
-                    const int jb = j0 + ch * 32;
+                    const int jb = j0 + h * 64 + ch * 32;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
-                        if (v[c] <= thr) {
-                            if (cnt < CAP) my_list[cnt] = (uint16_t)(jb + c);
-                            ++cnt;
+                        if (v[c] <= thr) {                         // rare (about 1.5 k / N of the columns)
+                            const int pos = atomicAdd(&cnt_s[r], 1);   // the row's list is shared by its two threads
+                            if (pos < CAP) my_list[pos] = (uint16_t)(jb + c);
                         }
                     }
                 }
@@ -386,7 +413,6 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + buf);
         }
-        cnt_s[r] = cnt;
     }
     tc_fence_before();
     __syncthreads();
@@ -395,41 +421,86 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
     }
 
-    // ================================ refine: exact fp32 re-rank, one warp per row ==========
-    const int C4 = P.C / 4;
-    int certified = 0;
-    for (int r = warp; r < KT_ROWS; r += KT_THREADS / 32) {
-        const int i = i0 + r;
-        if (i >= N) break;
-        const int cnt = cnt_s[r];
-        if (cnt > CAP || cnt < P.k) {               // not certified: exact fallback kernel takes the row
-            if (lane == 0) P.fb_rows[atomicAdd(P.fb_count, 1)] = rowbase + i;
-            continue;
-        }
-        const float4 *xi = reinterpret_cast<const float4 *>(P.xt + ((size_t)rowbase + i) * P.C);
-        const float xxi = P.xx[(size_t)rowbase + i];
-        unsigned long long key[CAP / 32];
-#pragma unroll
-        for (int s = 0; s < CAP / 32; ++s) {
-            const int e = s * 32 + lane;
-            float pd = -INFINITY;
-            int j = 0x7fffffff;
-            if (e < cnt) {
-                j = lists[r * CAP + e];
-                const float4 *xj = reinterpret_cast<const float4 *>(P.xt + ((size_t)rowbase + j) * P.C);
-                pd = exact_pd(xi, xj, C4, xxi, P.xx[(size_t)rowbase + j]);
-            }
-            key[s] = rank_key(pd, j, e < cnt);
-        }
-        warp_sort_u64<CAP / 32>(key);
-#pragma unroll
-        for (int s = 0; s < CAP / 32; ++s) {
-            const int e = s * 32 + lane;
-            if (e < P.k) P.idx[((size_t)rowbase + i) * P.k + e] = (int64_t)(uint32_t)(key[s] & 0xffffffffull);
-        }
-        ++certified;
+    // ---- hand the candidate lists to the refine kernel (coalesced copies, counts alongside)
+    {
+        const int rows_here = min(KT_ROWS, N - i0);
+        uint16_t *gl = P.cand + ((size_t)rowbase + i0) * CAP;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(lists);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(gl);
+        for (int e = threadIdx.x; e < rows_here * CAP / 2; e += KT_THREADS) dst[e] = src[e];
+        for (int r = threadIdx.x; r < rows_here; r += KT_THREADS) P.cand_cnt[(size_t)rowbase + i0 + r] = cnt_s[r];
     }
-    if (lane == 0 && certified) atomicAdd(P.stats, certified);
+}
+
+// ------------------------------------------------------------------------------------------- refine
+// Exact fp32 re-rank of the candidate lists.  One warp per query row; EIGHT lanes share one candidate: lane t
+// of a group reads the float4 pieces f = 8s + t of the candidate's point-major row (a warp-wide load touches
+// 4 candidates x 128 contiguous bytes) and runs partial chain t of the pinned dot product; three xor-shuffles
+// are the butterfly of oracle dot_tree, so all 8 lanes hold the exact specification value.  The warp then sorts
+// (value desc, index asc) and writes the first k.  Rows whose list overflowed go to the fallback list.
+template <int NG>
+__global__ void __launch_bounds__(256)
+knn_refine_kernel(KtParams P, long long total_rows)
+{
+    constexpr int CAP = 2 * NG;
+    constexpr int SLOTS = CAP / 32;
+    const int lane = threadIdx.x & 31;
+    const int grp = lane >> 3, t = lane & 7;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // b*N + i
+    if (row >= total_rows) return;
+    const long long base = (row / P.N) * P.N;
+    const int cnt = P.cand_cnt[row];
+    if (cnt > CAP || cnt < P.k) {
+        if (lane == 0) P.fb_rows[atomicAdd(P.fb_count, 1)] = (int)row;
+        return;
+    }
+    const int S = P.C / 32;                   // float4 pieces per lane: 2 (C = 64) or 4 (C = 128)
+    const float4 *xi = reinterpret_cast<const float4 *>(P.xt + (size_t)row * P.C);
+    float4 xr[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) xr[s] = (s < S) ? xi[8 * s + t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float xxi = P.xx[row];
+    const uint16_t *list = P.cand + (size_t)row * CAP;
+    unsigned long long key[SLOTS];
+#pragma unroll
+    for (int rnd = 0; rnd < SLOTS; ++rnd) {
+        key[rnd] = rank_key(-INFINITY, 0x7fffffff, false);
+        if (rnd * 32 < cnt) {
+#pragma unroll
+            for (int step = 0; step < 8; ++step) {
+                const int e0 = rnd * 32 + step * 4;
+                if (e0 < cnt) {                                     // warp-uniform
+                    const int e = e0 + grp;
+                    const bool live = e < cnt;
+                    const int j = live ? (int)list[e] : 0;
+                    const float4 *xj = reinterpret_cast<const float4 *>(P.xt + ((size_t)base + j) * P.C);
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) {
+                        if (s < S) {
+                            const float4 qv = xj[8 * s + t];
+                            acc = __fmaf_rn(xr[s].x, qv.x, acc);
+                            acc = __fmaf_rn(xr[s].y, qv.y, acc);
+                            acc = __fmaf_rn(xr[s].z, qv.z, acc);
+                            acc = __fmaf_rn(xr[s].w, qv.w, acc);
+                        }
+                    }
+                    acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 4));
+                    acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 2));
+                    acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 1));
+                    const float pd = __fsub_rn(__fmaf_rn(2.0f, acc, -P.xx[base + j]), xxi);
+                    if (step == t) key[rnd] = rank_key(pd, live ? j : 0x7fffffff, live);   // lane keeps e = 32 rnd + 4 t + grp
+                }
+            }
+        }
+    }
+    warp_sort_u64<SLOTS>(key);
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int e = s * 32 + lane;
+        if (e < P.k) P.idx[(size_t)row * P.k + e] = (int64_t)(uint32_t)(key[s] & 0xffffffffull);
+    }
+    if (lane == 0) atomicAdd(P.stats, 1);
 }
 
 // ------------------------------------------------------------------------------------------- fallback
@@ -500,7 +571,7 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t co
 }
 
 struct KtLayout {
-    size_t off_counters, off_max, off_xx, off_hi, off_lo, off_xt, off_rows, total;
+    size_t off_counters, off_max, off_xx, off_hi, off_lo, off_xt, off_rows, off_cand, off_cnt, total;
 };
 
 static KtLayout kt_layout(int B, int C, int N)
@@ -514,6 +585,8 @@ static KtLayout kt_layout(int B, int C, int N)
     L.off_lo = o;       o += align_up(2 * (size_t)B * N * C, 1024);
     L.off_xt = o;       o += align_up(sizeof(float) * (size_t)B * N * C, 256);
     L.off_rows = o;     o += align_up(sizeof(int) * (size_t)B * N, 256);
+    L.off_cand = o;     o += align_up(2 * (size_t)B * N * 128, 256);                 // CAP <= 128
+    L.off_cnt = o;      o += align_up(sizeof(int) * (size_t)B * N, 256);
     L.total = o;
     return L;
 }
@@ -551,11 +624,13 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
 
     KtParams P;
     P.xx = xx; P.maxxx = maxxx; P.xt = xt; P.idx = idx; P.fb_count = counters; P.fb_rows = rows;
-    P.stats = counters + 1; P.dump = dump; P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS;
+    P.stats = counters + 1; P.dump = dump;
+    P.cand = reinterpret_cast<uint16_t *>(w + L.off_cand); P.cand_cnt = reinterpret_cast<int *>(w + L.off_cnt); P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS;
     const int NG = (k <= 32) ? 32 : 64;
     const int KB = 3 * C / KT_KBLK;
-    const size_t smem = (size_t)(KB + KT_STAGES) * KT_BLK_BYTES + (size_t)KT_ROWS * 2 * NG * 2 + 2 * KT_COLS * 4 +
-                        KT_ROWS * 4 + 16 * 8 + 16 + 1024;
+    P.stages = (C == 64) ? 2 : 4;          // C = 64: 48 K (A') + 32 K (ring) + lists -> two CTAs per SM
+    const size_t smem = (size_t)(KB + P.stages) * KT_BLK_BYTES + (size_t)KT_ROWS * 2 * NG * 2 + 2 * KT_COLS * 4 +
+                        2 * KT_ROWS * 4 + 16 * 8 + 16 + 1024;
     dim3 grid((N + KT_ROWS - 1) / KT_ROWS, B);
     if (NG == 32) {
         MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -565,6 +640,15 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
         knn_tensor_kernel<64><<<grid, KT_THREADS, smem, st>>>(map_hi, map_lo, P);
     }
     MLSP_LAUNCH_CHECK("knn_tensor_kernel");
+    {
+        const long long rows_total = (long long)B * N;
+        const unsigned rblocks = (unsigned)((rows_total + 7) / 8);
+        if (NG == 32)
+            knn_refine_kernel<32><<<rblocks, 256, 0, st>>>(P, rows_total);
+        else
+            knn_refine_kernel<64><<<rblocks, 256, 0, st>>>(P, rows_total);
+        MLSP_LAUNCH_CHECK("knn_refine_kernel");
+    }
     const int fb_blocks = 2 * sm_count();
     if (k <= 32)
         knn_fallback_kernel<1><<<fb_blocks, 256, 0, st>>>(xt, xx, counters, rows, N, C, k, idx);

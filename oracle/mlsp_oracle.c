@@ -41,15 +41,34 @@ static void sq_norms(const float *x, int C, int N, float *xx)
     }
 }
 
-/* dot(x_i, x_j): first product rounded, then an fmaf chain in channel order.
- * Reference: `torch.matmul(x.transpose(2, 1), x)` PointDA/model_utils.py:10 (library sgemm,
- * order unspecified there; pinned here). */
+/* dot(x_i, x_j) for the 3-D ball test: first product rounded, then an fmaf chain in channel order.
+ * Reference: `torch.matmul(x.transpose(1, 0), x)` utils/pc_utils.py:87 (library sgemm, order
+ * unspecified there; pinned here). */
 static inline float dot_chain(const float *x, int C, int N, int i, int j)
 {
     float acc = x[i] * x[j];
     for (int c = 1; c < C; ++c)
         acc = fmaf(x[(size_t)c * N + i], x[(size_t)c * N + j], acc);
     return acc;
+}
+
+/* dot(x_i, x_j) for knn: the reference leaves the order to sgemm (`torch.matmul`,
+ * PointDA/model_utils.py:10); pinned here as EIGHT interleaved fmaf chains and a fixed tree:
+ *   p_t = fmaf chain from +0 over the channels c with (c/4) mod 8 == t, in increasing c   (t = 0..7)
+ *   dot = ((p0+p4) + (p2+p6)) + ((p1+p5) + (p3+p7))
+ * (groups of 4 consecutive channels go round-robin to 8 accumulators; this is the order in which
+ * 8 GPU lanes read one point-major row with coalesced 16-byte loads, and the butterfly they reduce
+ * with).  For C <= 4 it degenerates to one sequential chain. */
+static inline float dot_tree(const float *x, int C, int N, int i, int j)
+{
+    float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+        int t = (c >> 2) & 7;
+        p[t] = fmaf(x[(size_t)c * N + i], x[(size_t)c * N + j], p[t]);
+    }
+    float q0 = p[0] + p[4], q1 = p[1] + p[5], q2 = p[2] + p[6], q3 = p[3] + p[7];
+    float r0 = q0 + q2, r1 = q1 + q3;
+    return r0 + r1;
 }
 
 /* ---- a1: knn ------------------------------------------------------------------------
@@ -72,7 +91,7 @@ ORC_API int orc_knn(const float *x, int B, int C, int N, int k, int64_t *idx, fl
         for (int i = 0; i < N; ++i) {
             int cnt = 0;
             for (int j = 0; j < N; ++j) {
-                float d = dot_chain(xb, C, N, i, j);
+                float d = dot_tree(xb, C, N, i, j);
                 float t = fmaf(2.0f, d, -xx[j]);
                 float pd = t - xx[i];
                 /* candidates arrive in increasing j: a tie never displaces an earlier one */
