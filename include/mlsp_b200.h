@@ -48,8 +48,8 @@ extern "C" {
 #define MLSP_OP_CHAMFER 4
 
 /* flags for mlsp_knn_f32 */
-#define MLSP_KNN_AUTO 0        /* tensor-core filter + exact re-rank when C allows, else exact   */
-#define MLSP_KNN_EXACT_ONLY 1  /* force the fp32 CUDA-core kernel                                 */
+#define MLSP_KNN_AUTO 0        /* C=3: two-pass 3-D kernel; C in {64,128}: tcgen05 filter + exact re-rank; else streaming */
+#define MLSP_KNN_EXACT_ONLY 1  /* force the generic fp32 streaming-selection kernel (cross-check path)  */
 #define MLSP_KNN_TENSOR_ONLY 2 /* force the tcgen05 path (error if the shape does not allow it)  */
 
 MLSP_API int mlsp_version(void);

@@ -109,6 +109,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&r)[32])
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&r)[16])
+{
+    uint32_t u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * KT_EPI_WARPS) : "memory"); }
 
 // K-major, 128-byte swizzled operand block (rows 128 B apart, 8-row groups 1024 B apart), sm_100 version bit
@@ -213,6 +226,67 @@ __device__ __forceinline__ void reg_sort(float (&v)[NG])
     }
 }
 
+// ---- epilogue pieces ---------------------------------------------------------------------------------
+template <int NG>
+struct EpiState {
+    float gmin[NG];          // pass 1: minimum of v over the columns of class (j mod NG) seen by this thread
+    uint16_t *list;          // pass 2: the row's candidate list (shared by the row's two threads)
+    int *cnt;
+    __device__ __forceinline__ void init(uint16_t *l, int *c)
+    {
+#pragma unroll
+        for (int e = 0; e < NG; ++e) gmin[e] = INFINITY;
+        list = l;
+        cnt = c;
+    }
+};
+
+// one thread, one query row, 64 columns in pieces of 16 (tcgen05.ld 32x32b.x16): v = |x_j|^2 - 2 dot~
+// (16-wide pieces keep accumulators + class minima inside the 102-register budget of two CTAs per SM)
+template <int NG, int PASS>
+__device__ __forceinline__ void epi_tile(EpiState<NG> &st, uint32_t taddr, const float *nrm, float thr, int jbase)
+{
+    constexpr int CAP = 2 * NG;
+    const float4 *nrm4 = reinterpret_cast<const float4 *>(nrm);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        float acc[16];
+        tc_ld16(taddr + ch * 16, acc);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 nj = nrm4[ch * 4 + c4];
+            const float nv[4] = {nj.x, nj.y, nj.z, nj.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = 4 * c4 + u;
+                const float v = __fmaf_rn(-2.0f, acc[c], nv[u]);
+                if (PASS == 1) {
+                    const int e = (ch * 16 + c) % NG;           // column class j mod NG (static)
+                    st.gmin[e] = fminf(st.gmin[e], v);
+                } else if (v <= thr) {                          // rare (about 1.5 k / N of the columns)
+                    const int pos = atomicAdd(st.cnt, 1);       // the row's list is shared by its two threads
+                    if (pos < CAP) st.list[pos] = (uint16_t)(jbase + ch * 16 + c);
+                }
+            }
+        }
+    }
+}
+
+// test hook: write the approximate values of this thread's 64 columns
+// (tcgen05.ld is .sync.aligned: the whole warp must execute it, so row validity only predicates the stores)
+__device__ __noinline__ void dump_tile(float *row_out, bool row_valid, uint32_t taddr, const float *nrm, int jbase, int N)
+{
+    for (int ch = 0; ch < 2; ++ch) {
+        float acc[32];
+        tc_ld32(taddr + ch * 32, acc);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int j = jbase + ch * 32 + c;
+            if (row_valid && j < N) row_out[j] = __fmaf_rn(-2.0f, acc[c], nrm[ch * 32 + c]);
+        }
+    }
+}
+
 struct KtParams {
     const float *xx;         // (B,N) exact squared norms
     const float *maxxx;      // (B) max squared norm per cloud
@@ -230,7 +304,7 @@ struct KtParams {
 
 // ------------------------------------------------------------------------------------------- main kernel
 template <int NG>
-__global__ void __launch_bounds__(KT_THREADS, 1)
+__global__ void __launch_bounds__(KT_THREADS, (NG == 32) ? 2 : 1)   // NG = 32: two CTAs per SM (C = 64) need <= 102 registers
 knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, KtParams P)
 {
     constexpr int CAP = 2 * NG;
@@ -337,81 +411,62 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int et = threadIdx.x - 64;         // 0..255 among the epilogue threads
         const float xxi = (i < N) ? P.xx[(size_t)rowbase + i] : 0.0f;
         const float eps = KT_EPS_REL * sqrtf(xxi) * sqrtf(P.maxxx[b]);
-        float gmin[NG];
-#pragma unroll
-        for (int e = 0; e < NG; ++e) gmin[e] = INFINITY;
-        float thr = 0.0f;
-        uint16_t *my_list = lists + r * CAP;
-        for (int g = 0; g < 2 * T; ++g) {
-            const int buf = g & 1, t = g % T, j0 = t * KT_COLS;
-            if (g == T) {
-                // ---- between the passes: merge the two halves' class minima, tau = k-th smallest, broadcast thr
-                if (h == 1) {
-#pragma unroll
-                    for (int e = 0; e < NG; ++e) xchg[e * KT_ROWS + r] = gmin[e];
-                }
-                epi_bar_sync();
-                if (h == 0) {
-#pragma unroll
-                    for (int e = 0; e < NG; ++e) gmin[e] = fminf(gmin[e], xchg[e * KT_ROWS + r]);
-                    reg_sort<NG>(gmin);
-                    float tau = gmin[0];
-#pragma unroll
-                    for (int e = 1; e < NG; ++e) tau = (e == P.k - 1) ? gmin[e] : tau;
-                    thr_s[r] = tau + 2.0f * eps;
-                }
-                epi_bar_sync();                  // xchg (aliasing the lists) is dead from here on
-                thr = thr_s[r];
-            }
-            if (et < KT_COLS) {
-                const int j = j0 + et;
-                nrm_s[buf * KT_COLS + et] = (j < N) ? P.xx[(size_t)rowbase + j] : INFINITY;
-            }
-            epi_bar_sync();
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 64;
+        EpiState<NG> st;
+        st.init(lists + r * CAP, &cnt_s[r]);
+        const float *xxb = P.xx + rowbase;
+        // norms of tile 0; afterwards the norms of tile g+1 are fetched while tile g is processed
+        if (et < KT_COLS) nrm_s[et] = (et < N) ? xxb[et] : INFINITY;
+
+        // ---- pass 1: class minima
+        for (int g = 0; g < T; ++g) {
+            const int buf = g & 1;
+            float nxt = INFINITY;
+            const int jn = ((g + 1) % T) * KT_COLS + et;       // tile g+1 (pass 2 restarts at tile 0)
+            if (et < KT_COLS && jn < N) nxt = xxb[jn];
+            epi_bar_sync();                                     // norms of tile g visible
             mbar_wait(tm_full + buf, (g >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * KT_COLS + (uint32_t)h * 64;
-            const float4 *nrm4 = reinterpret_cast<const float4 *>(nrm_s + buf * KT_COLS + h * 64);
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                float acc[32];
-                tc_ld32(taddr + ch * 32, acc);
-                float v[32];
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 nj = nrm4[ch * 8 + c4];
-                    v[4 * c4 + 0] = __fmaf_rn(-2.0f, acc[4 * c4 + 0], nj.x);
-                    v[4 * c4 + 1] = __fmaf_rn(-2.0f, acc[4 * c4 + 1], nj.y);
-                    v[4 * c4 + 2] = __fmaf_rn(-2.0f, acc[4 * c4 + 2], nj.z);
-                    v[4 * c4 + 3] = __fmaf_rn(-2.0f, acc[4 * c4 + 3], nj.w);
-                }
-                if (g < T) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int e = (NG == 32) ? c : (ch * 32 + c);   // column class j mod NG (static)
-                        gmin[e] = fminf(gmin[e], v[c]);
-                    }
-                    if (P.dump && i < N) {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const int j = j0 + h * 64 + ch * 32 + c;
-                            if (j < N) P.dump[((size_t)rowbase + i) * N + j] = v[c];
-                        }
-                    }
-                } else {
-                    const int jb = j0 + h * 64 + ch * 32;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        if (v[c] <= thr) {                         // rare (about 1.5 k / N of the columns)
-                            const int pos = atomicAdd(&cnt_s[r], 1);   // the row's list is shared by its two threads
-                            if (pos < CAP) my_list[pos] = (uint16_t)(jb + c);
-                        }
-                    }
-                }
-            }
+            epi_tile<NG, 1>(st, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, 0.0f, 0);
+            if (P.dump) dump_tile(P.dump + ((size_t)rowbase + min(i, N - 1)) * N, i < N, tlane + (uint32_t)buf * KT_COLS,
+                                  nrm_s + buf * KT_COLS + h * 64, g * KT_COLS + h * 64, N);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + buf);
+            if (et < KT_COLS) nrm_s[(buf ^ 1) * KT_COLS + et] = nxt;
+        }
+        // ---- between the passes: merge the two halves' class minima, tau = k-th smallest, broadcast thr
+        if (h == 1) {
+#pragma unroll
+            for (int e = 0; e < NG; ++e) xchg[e * KT_ROWS + r] = st.gmin[e];
+        }
+        epi_bar_sync();
+        if (h == 0) {
+#pragma unroll
+            for (int e = 0; e < NG; ++e) st.gmin[e] = fminf(st.gmin[e], xchg[e * KT_ROWS + r]);
+            reg_sort<NG>(st.gmin);
+            float tau = st.gmin[0];
+#pragma unroll
+            for (int e = 1; e < NG; ++e) tau = (e == P.k - 1) ? st.gmin[e] : tau;
+            thr_s[r] = tau + 2.0f * eps;
+        }
+        epi_bar_sync();                          // xchg (aliasing the lists) is dead from here on
+        const float thr = thr_s[r];
+        // ---- pass 2: collect the candidates
+        for (int g = T; g < 2 * T; ++g) {
+            const int buf = g & 1;
+            float nxt = INFINITY;
+            const int jn = (g + 1 - T) * KT_COLS + et;
+            if (et < KT_COLS && g + 1 < 2 * T && jn < N) nxt = xxb[jn];
+            epi_bar_sync();
+            mbar_wait(tm_full + buf, (g >> 1) & 1);
+            tc_fence_after();
+            epi_tile<NG, 2>(st, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, thr,
+                            (g - T) * KT_COLS + h * 64);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tm_empty + buf);
+            if (et < KT_COLS) nrm_s[(buf ^ 1) * KT_COLS + et] = nxt;
         }
     }
     tc_fence_before();

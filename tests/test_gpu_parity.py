@@ -366,3 +366,17 @@ def test_knn_tensor_ties_and_duplicates(dev, orc):
     idx, stats = M.knn(x.to(dev), 20, flags=M._lib.KNN_TENSOR_ONLY, return_stats=True)
     assert np.array_equal(_np(idx), orc.knn(x.numpy(), 20))
     assert stats["fallback_rows"] >= 512                               # the all-ties cloud cannot be certified
+
+
+# ------------------------------------------------------------------------------------------------ a1, 3-D two-pass path
+@pytest.mark.parametrize("B,N,k", [(8, 1024, 20), (2, 4096, 40), (2, 700, 64), (3, 50, 20), (1, 8192, 20)])
+def test_knn3_equals_streaming_kernel(dev, B, N, k):
+    x = synth.clouds(B, N, 9, quantised=(N == 700)).to(dev)
+    assert torch.equal(M.knn(x, k), M.knn(x, k, flags=M._lib.KNN_EXACT_ONLY))
+
+
+def test_knn3_duplicates_overflow_path(dev, orc):
+    x = synth.clouds(2, 512, 3)
+    x[0, :, 100:300] = x[0, :, 100:101]              # 200 identical points: candidate lists overflow -> streaming path
+    idx = _np(M.knn(x.to(dev), 20))
+    assert np.array_equal(idx, orc.knn(x.numpy(), 20))
