@@ -99,7 +99,7 @@ class _Span:
     def __enter__(self):
         if self.t.enabled:
             self.a = torch.cuda.Event(enable_timing=True)
-            self.a.record()
+            self.a.record()                      # on the CURRENT stream: the one the op's kernels go to
 
     def __exit__(self, *exc):
         if self.t.enabled:
@@ -109,51 +109,79 @@ class _Span:
 
 
 # kernels launched per public-API call (counted from mlsp_b200/csrc: see DESIGN.md "launch inventory")
-LAUNCHES = {"fps": 1, "knn": 2, "edge_fwd": 2, "edge_bwd": 2, "normals": 2 + 1, "density": 1, "deform": 2,
-            "chamfer_fwd": 4, "chamfer_bwd": 2}
+LAUNCHES = {"fps": 1, "knn3": 1, "knn_tensor": 5, "edge_fwd_vec": 2, "edge_bwd_vec": 2, "edge_fwd_scalar": 1,
+            "edge_bwd_scalar": 1, "normals": 1 + 1, "density": 1, "deform": 2, "chamfer_fwd": 2, "chamfer_bwd": 1}
 
 
-def gpu_step(M, dev, lookup, k, timer, clouds=None):
-    """One hot-path step through the public API.  Returns (loss tensor, kernel launches)."""
+class Streams:
+    """Two streams per step: `model` carries the DGCNN neighbourhood layers and the loss, `target` the target
+    builder (deform_input with its host read-back, FPS, normals, cardinality).  Only layer 1 (it consumes the
+    deformed cloud) and the Chamfer loss (mask) wait for the target stream, so deform_input's device->host
+    read synchronises a nearly empty stream while the model stream keeps the GPU busy, and the latency-bound
+    FPS (one CTA per cloud) overlaps with the bandwidth-bound edge kernels."""
+
+    def __init__(self, device, serial=False, side_model=False):
+        self.model = torch.cuda.Stream(device=device) if side_model else torch.cuda.default_stream(device)
+        self.target = self.model if serial else torch.cuda.Stream(device=device)
+        self.serial = serial
+
+
+def _layer(M, timer, f, g, k):
+    C = f.shape[1]
+    f = f.detach().requires_grad_(True)
+    with timer(f"knn_C{C}"):
+        idx = M.knn(f, k)
+    with timer(f"edge_fwd_C{C}"):
+        out = M.get_graph_feature(f, None, k=k, idx=idx)
+    with timer(f"edge_bwd_C{C}"):
+        out.backward(g)
+    if C == 3:
+        return LAUNCHES["knn3"] + LAUNCHES["edge_fwd_scalar"] + LAUNCHES["edge_bwd_scalar"]
+    return LAUNCHES["knn_tensor"] + LAUNCHES["edge_fwd_vec"] + LAUNCHES["edge_bwd_vec"]
+
+
+def gpu_step(M, dev, lookup, k, timer, streams, clouds=None):
+    """One hot-path step through the public API.  Returns (loss tensor, kernel launches).
+    The caller's current stream is streams.model."""
+    sm, st = streams.model, streams.target
     clouds = dev["clouds"] if clouds is None else clouds
-    B, _, N = clouds.shape
     launches = 0
-    # -- target builder (deform first: it holds the only host sync of the step)
-    with timer("deform_input"):
-        gold = clouds
-        X = clouds.clone()
-        X, mask = M.deform_input(X, lookup, "volume_based_voxels", clouds.device)
-    launches += LAUNCHES["deform"]
-    with timer("fps"):
-        for n in FPS_SPLIT:
-            M.farthest_point_sample(None, clouds, n)
-    launches += LAUNCHES["fps"] * len(FPS_SPLIT)
-    pts = clouds.permute(0, 2, 1).contiguous()
-    with timer("pca_normals"):
-        M.estimate_normals(pts, NEAR)
-    launches += LAUNCHES["normals"]
-    with timer("cal_density"):
-        M.cal_density(pts, RADIUS, NUM_CLS)
-    launches += LAUNCHES["density"]
-    # -- neighbourhood engine, five DGCNN layers, forward + backward
-    feats = [clouds, X] + dev["feats"][2:]
-    for li, (f, g) in enumerate(zip(feats, dev["grads"])):
-        C = f.shape[1]
-        f = f.detach().requires_grad_(True)
-        with timer(f"knn_C{C}"):
-            idx = M.knn(f, k)
-        with timer(f"edge_fwd_C{C}"):
-            out = M.get_graph_feature(f, None, k=k, idx=idx)
-        with timer(f"edge_bwd_C{C}"):
-            out.backward(g)
-        launches += LAUNCHES["knn"] + LAUNCHES["edge_fwd"] + LAUNCHES["edge_bwd"]
-    # -- position loss
+    ready = torch.cuda.Event()
+    ready.record(sm)                                  # clouds resident (e2e: the H2D copy is on the model stream)
+    # -- neighbourhood engine, layers that do not depend on the deformed cloud: forward + backward
+    feats = [clouds, None] + dev["feats"][2:]
+    for li in (0, 2, 3, 4):
+        launches += _layer(M, timer, feats[li], dev["grads"][li], k)
+    # -- target builder on its own stream
+    with torch.cuda.stream(st):
+        st.wait_event(ready)
+        with timer("deform_input"):
+            gold = clouds
+            X = clouds.clone()
+            X, mask = M.deform_input(X, lookup, "volume_based_voxels", clouds.device)
+        deformed = torch.cuda.Event()
+        deformed.record(st)
+        with timer("fps"):
+            for n in FPS_SPLIT:
+                M.farthest_point_sample(None, clouds, n)
+        pts = clouds.permute(0, 2, 1).contiguous()
+        with timer("pca_normals"):
+            M.estimate_normals(pts, NEAR)
+        with timer("cal_density"):
+            M.cal_density(pts, RADIUS, NUM_CLS)
+        built = torch.cuda.Event()
+        built.record(st)
+    launches += LAUNCHES["deform"] + LAUNCHES["fps"] * len(FPS_SPLIT) + LAUNCHES["knn3"] + LAUNCHES["normals"] + LAUNCHES["density"]
+    # -- layer 1 (deformed cloud) and the position loss need the target stream's results
+    sm.wait_event(deformed)
+    launches += _layer(M, timer, X, dev["grads"][1], k)
     pred = dev["pred"].detach().requires_grad_(True)
     with timer("chamfer_fwd"):
         loss = M.reconstruction_loss(pred, gold, mask)
     with timer("chamfer_bwd"):
         loss.backward()
     launches += LAUNCHES["chamfer_fwd"] + LAUNCHES["chamfer_bwd"]
+    sm.wait_event(built)                              # join: the step ends when both streams are done
     return loss, launches
 
 
@@ -191,6 +219,27 @@ class ClockSampler:
         except OSError:
             pass
 
+    def _count(self):
+        try:
+            return sum(1 for _ in open(self.path))
+        except OSError:
+            return 0
+
+    def wait_first_sample(self, load, max_s=5.0):
+        """nvidia-smi takes about a second to print its first line; keep the GPU under the bench's own load meanwhile."""
+        t0 = time.perf_counter()
+        while self.proc is not None and self._count() == 0 and time.perf_counter() - t0 < max_s:
+            load()
+        self.skip = self._count()                      # samples before the timed region are not reported
+
+    def keep_load(self, load, min_samples=5, max_s=3.0):
+        """The timed region can be shorter than the 100 ms sampling period: continue the identical steps
+        (untimed) until enough samples under this load exist."""
+        t0 = time.perf_counter()
+        while self.proc is not None and self._count() - getattr(self, "skip", 0) < min_samples and time.perf_counter() - t0 < max_s:
+            load()
+        torch.cuda.synchronize()
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
@@ -201,7 +250,9 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for line in open(self.path):
+        for ln, line in enumerate(open(self.path)):
+            if ln < getattr(self, "skip", 0):
+                continue
             f = [s.strip() for s in line.split(",")]
             if len(f) < 9:
                 continue
@@ -275,6 +326,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="A", choices=["A", "S"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="headline on one stream (no target-builder overlap)")
+    ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -306,36 +359,56 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    streams = Streams(device, serial=args.serial, side_model=args.side_model_stream)
+    serial = Streams(device, serial=True, side_model=args.side_model_stream)
     off = OpTimer(False)
-    for _ in range(args.warmup):
-        gpu_step(M, dev, lookup, k, off)
-    # ---- timed region 1: device-resident inputs, per-op CUDA-event spans inside it
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    timer = OpTimer(True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    launches = 0
-    for _ in range(args.steps):
-        loss, n = gpu_step(M, dev, lookup, k, timer)
-        launches += n
-    e1.record()
-    barrier()
-    wall = time.perf_counter() - t0
-    dev_ms = e0.elapsed_time(e1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~1 s to start: begin before warm-up
+    torch.cuda.synchronize()
+    with torch.cuda.stream(streams.model):
+        for _ in range(args.warmup):
+            gpu_step(M, dev, lookup, k, off, streams)
+        if sampler:
+            sampler.wait_first_sample(lambda: gpu_step(M, dev, lookup, k, off, streams))
+        # ---- timed region 1 (the headline): device-resident inputs, K steps
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        launches = 0
+        for _ in range(args.steps):
+            loss, n = gpu_step(M, dev, lookup, k, off, streams)
+            launches += n
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        if sampler:                                              # keep the same load up until >= 5 samples exist
+            sampler.keep_load(lambda: gpu_step(M, dev, lookup, k, off, streams), min_samples=5, max_s=3.0)
     clocks = sampler.stop() if sampler else None
+    # ---- region 1b: the same K steps on ONE stream with per-op CUDA-event spans (op times, rooflines)
+    timer = OpTimer(True)
+    with torch.cuda.stream(serial.model):
+        gpu_step(M, dev, lookup, k, off, serial)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            gpu_step(M, dev, lookup, k, timer, serial)
+        s1.record()
+        barrier()
+        serial_ms = s0.elapsed_time(s1) / args.steps
     # ---- timed region 2: end to end -- pinned host clouds in, loss out, every step
-    for _ in range(2):
-        gpu_step(M, dev, lookup, k, off, clouds=host["clouds"].to(device, non_blocking=True))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        c = host["clouds"].to(device, non_blocking=True)
-        loss, _ = gpu_step(M, dev, lookup, k, off, clouds=c)
-        loss_host = loss.item()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    with torch.cuda.stream(streams.model):
+        for _ in range(2):
+            gpu_step(M, dev, lookup, k, off, streams, clouds=host["clouds"].to(device, non_blocking=True))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            c = host["clouds"].to(device, non_blocking=True)
+            loss, _ = gpu_step(M, dev, lookup, k, off, streams, clouds=c)
+            loss_host = loss.item()
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
     def max_over_ranks(v):
         if dist is None:
@@ -381,6 +454,13 @@ def main():
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                     "algorithmic_bytes": by, "ms_per_launch": per_call_ms[dom]}
+    # dram__bytes_read+write per launch of the op's main kernel, from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if roof is not None and os.path.exists(tpath):
+        tr = json.load(open(tpath)).get(f"{args.workload}:{dom}")
+        if tr:
+            roof["traffic"] = tr["dram_bytes"]
+            roof["traffic_source"] = tr["source"]
     # secondary rooflines for every neighbourhood-engine op (explains the headline)
     rooflines = {}
     for n in per_call_ms:
@@ -395,12 +475,17 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        Bs = min(B, 16)
         cpu_reference_time(2, N, k, 1234)                      # warm the thread pool
-        t = cpu_reference_time(Bs, N, k, 1234)
-        cpu = {"value": Bs / t, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 step on {Bs} of {B} clouds, {t:.1f} s; oracle/ref_torch.py (pure-torch port of the reference "
-                         "op composition; pcl pieces as dense-torch restatements)"}
+        t1 = cpu_reference_time(B, N, k, 1234)                 # one full-batch step to size the sample
+        reps = int(min(20, max(3, np.ceil(12.0 / t1))))        # about 12 s of CPU work
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cpu_reference_time(B, N, k, 1234)
+        t = (time.perf_counter() - t0) / reps
+        cpu = {"value": B / t, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{reps} steps on the full {B}-cloud batch, {t * reps:.1f} s in total (input generation included); "
+                         "oracle/ref_torch.py (pure-torch port of the reference op composition; pcl pieces as "
+                         "dense-torch restatements), torch.set_num_threads(all cores)"}
 
     value = B * world / (step_ms * 1e-3)
     line = {
@@ -410,9 +495,13 @@ def main():
         "config": {"workload": f"hotpath-{args.workload}", "clouds_per_gpu": B, "points": N, "k": k,
                    "layers_C": list(LAYER_CHANNELS), "fps_split": list(FPS_SPLIT), "radius": RADIUS, "near": NEAR,
                    "parallelism": f"batch-sharded x{world}, no data-path collective",
+                   "streams": "one (--serial)" if args.serial else
+                              "two: DGCNN layers + loss on one, target builder (deform_input/FPS/normals/cardinality) on the other",
                    "l2": "per-step working set ~2.9 GB (edge tensors + their gradients) >> 126 MB L2; no explicit flush",
-                   "timing": "K steps between barrier+synchronize; max(CUDA-event, wall) because deform_input syncs"},
+                   "timing": "K steps between barrier+synchronize; max(CUDA-event, wall) because deform_input syncs; "
+                             "op_ms_per_step / rooflines: CUDA-event spans in a second K-step region on ONE stream"},
         "device_ms_per_step": dev_only_ms,
+        "serial_ms_per_step": serial_ms,
         "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(host["clouds"].numel() * 4), "d2h_bytes_per_step": 4 + 8 * B,
                 "loss": loss_host},

@@ -147,6 +147,24 @@ MLSP_API int mlsp_chamfer_dir_bwd(const float *p1, int64_t p1_bstride, int64_t p
                          const float *scale_dev, float scale_host, float *grad_p1, float *grad_p2,
                          void *stream);
 
+/* a9 -- reconstruction_loss(pred, gold, mask) MLSP/mlsp.py:156-182 in one call: both Chamfer directions
+ *   (rows of gold against pred, rows of pred against gold), the per-cloud normalisation by the mask count and the
+ *   1/B batch mean.  pred/gold are addressed like the points above (any (B,N,3)/(B,3,N) strides), mask like above.
+ *   argmin (2,B,N) int64: matches of direction 0 (gold rows -> pred) then direction 1 (pred rows -> gold), -1 on
+ *   unmasked rows; loss: one device float.  Workspace: mlsp_workspace_bytes(MLSP_OP_CHAMFER, ...). */
+MLSP_API int mlsp_reconstruction_loss_fwd(const float *pred, int64_t pred_bstride, int64_t pred_pstride,
+                         int64_t pred_cstride, const float *gold, int64_t gold_bstride, int64_t gold_pstride,
+                         int64_t gold_cstride, const float *mask, int64_t mask_bstride, int B, int N,
+                         int64_t *argmin, float *loss, void *ws, size_t ws_bytes, void *stream);
+
+/* backward of the above w.r.t. pred: grad_pred (B,N,3) contiguous float32 is OVERWRITTEN with
+ *   grad_loss/B * sum over both directions of +-2 (pred - match) / count_b   (closed form on the saved argmin).
+ *   grad_loss: device scalar (upstream gradient) or NULL for 1. */
+MLSP_API int mlsp_reconstruction_loss_bwd(const float *pred, int64_t pred_bstride, int64_t pred_pstride,
+                         int64_t pred_cstride, const float *gold, int64_t gold_bstride, int64_t gold_pstride,
+                         int64_t gold_cstride, const float *mask, int64_t mask_bstride, const int64_t *argmin,
+                         int B, int N, const float *grad_loss, float *grad_pred, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

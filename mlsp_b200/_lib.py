@@ -32,6 +32,8 @@ SIGNATURES = {
     "mlsp_pca_normals": [_P, _P, _I, _I, _I, _P, _P, _P],
     "mlsp_chamfer_dir_fwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _Z, _P],
     "mlsp_chamfer_dir_bwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _P, _I, _I, _P, _F, _P, _P, _P],
+    "mlsp_reconstruction_loss_fwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _I, _I, _P, _P, _P, _Z, _P],
+    "mlsp_reconstruction_loss_bwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _P, _I, _I, _P, _P, _P],
 }
 
 OP_KNN, OP_EDGE_FWD, OP_EDGE_BWD, OP_CHAMFER = 1, 2, 3, 4

@@ -18,8 +18,8 @@ constexpr int CH_MAX_TILES = 64;
 
 size_t chamfer_workspace_bytes(int B, int N)
 {
-    (void)N;
-    return align_up(sizeof(float) * 2 * (size_t)B * CH_MAX_TILES, 256);
+    (void)N;   // (sum, count) partials per CTA; x2: both directions of mlsp_reconstruction_loss_fwd
+    return align_up(sizeof(float) * 4 * (size_t)B * CH_MAX_TILES, 256);
 }
 
 struct PtView {
@@ -32,10 +32,10 @@ struct PtView {
     }
 };
 
-__global__ void __launch_bounds__(CH_THREADS)
-chamfer_fwd_kernel(PtView p1, PtView p2, const float *__restrict__ mask, long long mask_bs, int N, int all_rows,
-                   int rows_per_cta, float *__restrict__ rowmin, int64_t *__restrict__ argmin,
-                   float *__restrict__ part_s, float *__restrict__ part_c)
+__device__ __forceinline__ void chamfer_fwd_body(const PtView &p1, const PtView &p2, const float *__restrict__ mask,
+                                                 long long mask_bs, int N, int all_rows, int rows_per_cta,
+                                                 float *__restrict__ rowmin, int64_t *__restrict__ argmin,
+                                                 float *__restrict__ part_s, float *__restrict__ part_c)
 {
     extern __shared__ float4 cols[];            // [N] (x,y,z,pen)
     int *list = reinterpret_cast<int *>(cols + N);  // [rows_per_cta] compacted row ids
@@ -60,7 +60,7 @@ chamfer_fwd_kernel(PtView p1, PtView p2, const float *__restrict__ mask, long lo
                 m = mb[i];
                 take = all_rows || (m != 0.0f);
                 if (!take) {
-                    rowmin[(size_t)b * N + i] = 0.0f;
+                    if (rowmin) rowmin[(size_t)b * N + i] = 0.0f;
                     argmin[(size_t)b * N + i] = -1;
                 }
             }
@@ -110,7 +110,7 @@ chamfer_fwd_kernel(PtView p1, PtView p2, const float *__restrict__ mask, long lo
             const int wi = (int)__reduce_min_sync(MLSP_FULL, (vb == wv) ? (uint32_t)bj : 0x7fffffffu);
             if (lane == 0) {
                 const float m = mb[i];
-                rowmin[(size_t)b * N + i] = __uint_as_float(wv);
+                if (rowmin) rowmin[(size_t)b * N + i] = __uint_as_float(wv);
                 argmin[(size_t)b * N + i] = wi;
                 sum += __uint_as_float(wv) * m;
                 cnt += m;
@@ -133,6 +133,48 @@ chamfer_fwd_kernel(PtView p1, PtView p2, const float *__restrict__ mask, long lo
     }
 }
 
+__global__ void __launch_bounds__(CH_THREADS)
+chamfer_fwd_kernel(PtView p1, PtView p2, const float *__restrict__ mask, long long mask_bs, int N, int all_rows,
+                   int rows_per_cta, float *__restrict__ rowmin, int64_t *__restrict__ argmin,
+                   float *__restrict__ part_s, float *__restrict__ part_c)
+{
+    chamfer_fwd_body(p1, p2, mask, mask_bs, N, all_rows, rows_per_cta, rowmin, argmin, part_s, part_c);
+}
+
+// both directions of reconstruction_loss in one launch: blockIdx.z = 0: rows of gold against pred, 1: the converse
+__global__ void __launch_bounds__(CH_THREADS)
+chamfer_pair_fwd_kernel(PtView pred, PtView gold, const float *__restrict__ mask, long long mask_bs, int B, int N,
+                        int rows_per_cta, int64_t *__restrict__ argmin, float *__restrict__ part_s,
+                        float *__restrict__ part_c)
+{
+    const int dir = blockIdx.z;
+    const size_t po = (size_t)dir * B * gridDim.x;
+    chamfer_fwd_body(dir == 0 ? gold : pred, dir == 0 ? pred : gold, mask, mask_bs, N, 0, rows_per_cta, nullptr,
+                     argmin + (size_t)dir * B * N, part_s + po, part_c + po);
+}
+
+// loss = (1/B) (sum_b s0_b/c_b + sum_b s1_b/c_b)   (mlsp.py:151-153, :175-180); one warp
+__global__ void chamfer_pair_finalize_kernel(const float *__restrict__ part_s, const float *__restrict__ part_c, int B,
+                                             int T, float *__restrict__ loss)
+{
+    float acc[2] = {0.f, 0.f};
+    for (int dir = 0; dir < 2; ++dir)
+        for (int b = threadIdx.x; b < B; b += 32) {
+            float s = 0.f, c = 0.f;
+            for (int t = 0; t < T; ++t) {
+                s += part_s[((size_t)dir * B + b) * T + t];
+                c += part_c[((size_t)dir * B + b) * T + t];
+            }
+            acc[dir] += s / c;                   // empty mask: 0/0 = NaN, like the reference
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc[0] += __shfl_xor_sync(MLSP_FULL, acc[0], o);
+        acc[1] += __shfl_xor_sync(MLSP_FULL, acc[1], o);
+    }
+    if (threadIdx.x == 0) *loss = (1.0f / (float)B) * (acc[0] + acc[1]);
+}
+
 // In all_rows mode unmasked rows contribute m=0 to both sums, so the count is still sum_i mask_i.
 __global__ void chamfer_finalize_kernel(const float *__restrict__ part_s, const float *__restrict__ part_c, int B,
                                         int T, float *__restrict__ partial)
@@ -147,10 +189,10 @@ __global__ void chamfer_finalize_kernel(const float *__restrict__ part_s, const 
     partial[b] = s / c;  // empty mask: 0/0 = NaN, like the reference
 }
 
-__global__ void __launch_bounds__(256)
-chamfer_bwd_kernel(PtView p1, PtView p2, const float *__restrict__ mask, long long mask_bs,
-                   const int64_t *__restrict__ argmin, int N, const float *__restrict__ scale_dev, float scale_host,
-                   float *__restrict__ g1, float *__restrict__ g2)
+__device__ __forceinline__ void chamfer_bwd_body(const PtView &p1, const PtView &p2, const float *__restrict__ mask,
+                                                 long long mask_bs, const int64_t *__restrict__ argmin, int N,
+                                                 const float *__restrict__ scale_dev, float scale_host,
+                                                 float *__restrict__ g1, float *__restrict__ g2)
 {
     __shared__ float wpart[8];
     __shared__ float total;
@@ -192,7 +234,73 @@ chamfer_bwd_kernel(PtView p1, PtView p2, const float *__restrict__ mask, long lo
     }
 }
 
+__global__ void __launch_bounds__(256)
+chamfer_bwd_kernel(PtView p1, PtView p2, const float *__restrict__ mask, long long mask_bs,
+                   const int64_t *__restrict__ argmin, int N, const float *__restrict__ scale_dev, float scale_host,
+                   float *__restrict__ g1, float *__restrict__ g2)
+{
+    chamfer_bwd_body(p1, p2, mask, mask_bs, argmin, N, scale_dev, scale_host, g1, g2);
+}
+
+// gradient of reconstruction_loss w.r.t. pred, both directions (blockIdx.y), accumulated into a zeroed buffer
+__global__ void __launch_bounds__(256)
+chamfer_pair_bwd_kernel(PtView pred, PtView gold, const float *__restrict__ mask, long long mask_bs,
+                        const int64_t *__restrict__ argmin, int B, int N, const float *__restrict__ scale_dev,
+                        float scale_host, float *__restrict__ grad_pred)
+{
+    if (blockIdx.y == 0)      // rows of gold matched into pred: pred is p2
+        chamfer_bwd_body(gold, pred, mask, mask_bs, argmin, N, scale_dev, scale_host, nullptr, grad_pred);
+    else                      // rows of pred matched into gold: pred is p1
+        chamfer_bwd_body(pred, gold, mask, mask_bs, argmin + (size_t)B * N, N, scale_dev, scale_host, grad_pred, nullptr);
+}
+
 }  // namespace mlsp
+
+extern "C" int mlsp_reconstruction_loss_fwd(const float *pred, int64_t pred_bstride, int64_t pred_pstride,
+                                            int64_t pred_cstride, const float *gold, int64_t gold_bstride,
+                                            int64_t gold_pstride, int64_t gold_cstride, const float *mask,
+                                            int64_t mask_bstride, int B, int N, int64_t *argmin, float *loss, void *ws,
+                                            size_t ws_bytes, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(pred && gold && mask && argmin && loss && ws, MLSP_EINVAL, "reconstruction_loss_fwd: null pointer");
+    MLSP_REQUIRE(B > 0 && N > 0, MLSP_EINVAL, "reconstruction_loss_fwd: bad shape");
+    MLSP_REQUIRE(ws_bytes >= chamfer_workspace_bytes(B, N), MLSP_EWORKSPACE, "reconstruction_loss_fwd: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    int T = (N + 511) / 512;
+    if (T > CH_MAX_TILES) T = CH_MAX_TILES;
+    const int rows_per_cta = (N + T - 1) / T;
+    const size_t smem = sizeof(float4) * (size_t)N + sizeof(int) * (size_t)rows_per_cta;
+    MLSP_REQUIRE(smem <= 200 * 1024, MLSP_EUNSUPPORTED, "reconstruction_loss_fwd: N=%d too large", N);
+    float *part_s = static_cast<float *>(ws);
+    float *part_c = part_s + 2 * (size_t)B * CH_MAX_TILES;
+    PtView vp{pred, pred_bstride, pred_pstride, pred_cstride}, vg{gold, gold_bstride, gold_pstride, gold_cstride};
+    MLSP_CUDA(cudaFuncSetAttribute(chamfer_pair_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chamfer_pair_fwd_kernel<<<dim3(T, B, 2), CH_THREADS, smem, st>>>(vp, vg, mask, mask_bstride, B, N, rows_per_cta,
+                                                                    argmin, part_s, part_c);
+    MLSP_LAUNCH_CHECK("chamfer_pair_fwd_kernel");
+    chamfer_pair_finalize_kernel<<<1, 32, 0, st>>>(part_s, part_c, B, T, loss);
+    MLSP_LAUNCH_CHECK("chamfer_pair_finalize_kernel");
+    return MLSP_OK;
+}
+
+extern "C" int mlsp_reconstruction_loss_bwd(const float *pred, int64_t pred_bstride, int64_t pred_pstride,
+                                            int64_t pred_cstride, const float *gold, int64_t gold_bstride,
+                                            int64_t gold_pstride, int64_t gold_cstride, const float *mask,
+                                            int64_t mask_bstride, const int64_t *argmin, int B, int N,
+                                            const float *grad_loss, float *grad_pred, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(pred && gold && mask && argmin && grad_pred, MLSP_EINVAL, "reconstruction_loss_bwd: null pointer");
+    MLSP_REQUIRE(B > 0 && N > 0, MLSP_EINVAL, "reconstruction_loss_bwd: bad shape");
+    cudaStream_t st = as_stream(stream);
+    MLSP_CUDA(cudaMemsetAsync(grad_pred, 0, sizeof(float) * 3 * (size_t)B * N, st));
+    PtView vp{pred, pred_bstride, pred_pstride, pred_cstride}, vg{gold, gold_bstride, gold_pstride, gold_cstride};
+    chamfer_pair_bwd_kernel<<<dim3(B, 2), 256, 0, st>>>(vp, vg, mask, mask_bstride, argmin, B, N, grad_loss,
+                                                       1.0f / (float)B, grad_pred);
+    MLSP_LAUNCH_CHECK("chamfer_pair_bwd_kernel");
+    return MLSP_OK;
+}
 
 extern "C" int mlsp_chamfer_dir_fwd(const float *p1, int64_t p1_bstride, int64_t p1_pstride, int64_t p1_cstride,
                                     const float *p2, int64_t p2_bstride, int64_t p2_pstride, int64_t p2_cstride,

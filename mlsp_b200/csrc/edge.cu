@@ -123,7 +123,11 @@ edge_fwd_scalar_kernel(const float *__restrict__ xt, const int64_t *__restrict__
 }
 
 // ---- backward --------------------------------------------------------------------------------------
-// gxt (B,N,C) zero-initialised.  One warp per query point.
+// gxt (B,N,C) zero-initialised.  One warp per query point.  The warp is split into G = 32/Q4 groups of Q4
+// lanes when a point row is narrower than the warp (C = 64: two groups), each group taking every G-th
+// neighbour, so all 32 lanes issue 128-bit loads; four neighbours per lane are in flight before their
+// vector atomics (red.global.add.v4.f32 into the L2-resident gxt) are issued.
+template <int UNROLL>
 __global__ void __launch_bounds__(256)
 edge_bwd_vec_kernel(const float4 *__restrict__ g, const int64_t *__restrict__ idx, int N, int k, int Q4,
                     float4 *__restrict__ gxt, long long total_points)
@@ -136,18 +140,47 @@ edge_bwd_vec_kernel(const float4 *__restrict__ g, const int64_t *__restrict__ id
     const int64_t *irow = idx + p * k;
     const float4 *grow = g + p * (long long)k * (2 * Q4);
     const int W = 2 * Q4;
-    for (int q = lane; q < Q4; q += 32) {
+    const int G = (Q4 < 32 && (32 % Q4) == 0) ? 32 / Q4 : 1;      // neighbour groups per warp
+    const int grp = (G > 1) ? lane / Q4 : 0;
+    const int q0 = (G > 1) ? lane - grp * Q4 : lane;
+    const int qstep = (G > 1) ? Q4 : 32;                          // G > 1: a single q per lane
+    for (int q = q0; q < Q4; q += qstep) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j = 0; j < k; ++j) {
-            const float4 gd = __ldcs(grow + (long long)j * W + q);        // d out / d (nbr - ctr)
-            const float4 gc = __ldcs(grow + (long long)j * W + Q4 + q);   // d out / d ctr copy
+        int j = grp;
+        for (; j + (UNROLL - 1) * G < k; j += UNROLL * G) {
+            float4 gd[UNROLL], gc[UNROLL];
+            long long n[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                gd[u] = __ldcs(grow + (long long)(j + u * G) * W + q);        // d out / d (nbr - ctr)
+                gc[u] = __ldcs(grow + (long long)(j + u * G) * W + Q4 + q);   // d out / d ctr copy
+                n[u] = irow[j + u * G];
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                acc.x += gc[u].x - gd[u].x;
+                acc.y += gc[u].y - gd[u].y;
+                acc.z += gc[u].z - gd[u].z;
+                acc.w += gc[u].w - gd[u].w;
+                atomicAdd(gb + n[u] * Q4 + q, gd[u]);
+            }
+        }
+        for (; j < k; j += G) {
+            const float4 gd = __ldcs(grow + (long long)j * W + q);
+            const float4 gc = __ldcs(grow + (long long)j * W + Q4 + q);
             acc.x += gc.x - gd.x;
             acc.y += gc.y - gd.y;
             acc.z += gc.z - gd.z;
             acc.w += gc.w - gd.w;
             atomicAdd(gb + (long long)irow[j] * Q4 + q, gd);
         }
-        atomicAdd(gxt + p * Q4 + q, acc);
+        for (int o = Q4; o < 32 && G > 1; o <<= 1) {             // fold the groups' centre terms
+            acc.x += __shfl_xor_sync(MLSP_FULL, acc.x, o);
+            acc.y += __shfl_xor_sync(MLSP_FULL, acc.y, o);
+            acc.z += __shfl_xor_sync(MLSP_FULL, acc.z, o);
+            acc.w += __shfl_xor_sync(MLSP_FULL, acc.w, o);
+        }
+        if (grp == 0) atomicAdd(gxt + p * Q4 + q, acc);
     }
 }
 
@@ -214,7 +247,7 @@ extern "C" int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, i
         const int warps = 8;
         const long long blocks = (points + warps - 1) / warps;
         MLSP_REQUIRE(blocks < (1ll << 31), MLSP_EUNSUPPORTED, "edge_gather_bwd: too many points");
-        edge_bwd_vec_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(
+        edge_bwd_vec_kernel<4><<<(unsigned)blocks, warps * 32, 0, st>>>(
             reinterpret_cast<const float4 *>(grad_out), idx, N, k, C / 4, reinterpret_cast<float4 *>(gxt), points);
         MLSP_LAUNCH_CHECK("edge_bwd_vec_kernel");
     } else {

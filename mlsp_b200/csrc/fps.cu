@@ -2,19 +2,143 @@
 //
 // The reference runs npoint dependent iterations of ~8 tiny ATen kernels.  Here one CTA owns one cloud
 // for the whole loop: point coordinates and running min-distances live in registers, the cloud is also
-// kept SoA in shared memory so the winner's coordinates are one broadcast read, and each round costs a
-// single __syncthreads: per-warp argmax with two redux.sync instructions (distances are >= +0, so the
-// float bit pattern orders as an unsigned integer), one shared-memory slot per warp (double buffered
-// by round parity), and every warp redundantly reduces the slots.
+// kept as float4 in shared memory so the winner's coordinates are one broadcast LDS.128, and each round
+// costs one redux.sync, one ballot and one __syncthreads (see fps_kernel).  The loop is a serial
+// dependency chain of npoint rounds; the kernel is latency-bound by construction (12 KB of input).
 // Arithmetic pinned to oracle/mlsp_oracle.c:orc_fps: d = (rn(dx^2) + rn(dy^2)) + rn(dz^2), distance =
 // min(distance, d) starting from 1e10, argmax with the lowest index on ties (torch.max semantics).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mlsp {
 
+// W warps per cloud, P points per lane.  Lane l of warp w owns the CONTIGUOUS points (w*32 + l)*P .. +P-1, so
+// "lowest (warp, lane, register)" is "lowest index": ties resolve without reducing indices --
+//   in-thread : compare tree over the P registers (strict > towards the higher index)
+//   in-warp   : one redux.sync.max.f32, one ballot; the first lane holding the maximum is the leader and
+//               publishes (value, index) for its warp
+//   in-CTA    : one __syncthreads per round; every thread reads the W slots and picks the first maximum.
+// Points beyond N carry distance -1 forever (d >= 0 never undercuts it, and it never wins a maximum).
+template <int P, int W>
+__global__ void __launch_bounds__(32 * W)
+fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start,
+           int64_t *__restrict__ centroids, float *__restrict__ vals)
+{
+    extern __shared__ float4 spt[];                       // [N] (x, y, z, 0), then the winners of all rounds
+    int *hist = reinterpret_cast<int *>(spt + N);         // [npoint]
+    __shared__ __align__(16 * W) uint2 slot[2][W];        // (value bits, index), double buffered by round parity
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *X = xyz + (size_t)b * 3 * N;
+    for (int p = tid; p < N; p += 32 * W) spt[p] = make_float4(X[p], X[N + p], X[2 * N + p], 0.0f);
+    __syncthreads();
+    const int p0 = tid * P;
+    float px[P], py[P], pz[P], dist[P];
+#pragma unroll
+    for (int r = 0; r < P; ++r) {
+        const bool ok = p0 + r < N;
+        const float4 q = spt[ok ? p0 + r : 0];
+        px[r] = q.x;
+        py[r] = q.y;
+        pz[r] = q.z;
+        dist[r] = ok ? 1e10f : -1.0f;
+    }
+    // shared-window addresses computed once (the compiler otherwise rebuilds them every round)
+    const uint32_t spt_a = (uint32_t)__cvta_generic_to_shared(spt);
+    const uint32_t slot_a = (uint32_t)__cvta_generic_to_shared(&slot[0][0]);
+    uint32_t my_slot = slot_a + warp * 8, all_slots = slot_a;
+    unsigned lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    int far = (int)start[b];
+
+    for (int s = 0; s + 1 < npoint; ++s) {
+        float cx, cy, cz, cw;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cx), "=f"(cy), "=f"(cz), "=f"(cw) : "r"(spt_a + far * 16));
+        if (tid == 0) hist[s] = far;
+        float bv[P];
+        int br[P];
+#pragma unroll
+        for (int r = 0; r < P; ++r) {
+            const float dx = __fsub_rn(px[r], cx), dy = __fsub_rn(py[r], cy), dz = __fsub_rn(pz[r], cz);
+            const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            dist[r] = (d < dist[r]) ? d : dist[r];
+            bv[r] = dist[r];
+            br[r] = r;
+        }
+#pragma unroll
+        for (int w = 1; w < P; w <<= 1)
+#pragma unroll
+            for (int r = 0; r + w < P; r += 2 * w) {
+                const bool hi = bv[r + w] > bv[r];       // strict: the lower index keeps ties
+                bv[r] = hi ? bv[r + w] : bv[r];
+                br[r] = hi ? br[r + w] : br[r];
+            }
+        const float wv = warp_max_f32(bv[0]);
+        const bool mine = bv[0] == wv;
+        const unsigned holders = __ballot_sync(MLSP_FULL, mine);
+        // the first lane holding the maximum publishes it (predicated store, no branch)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.u32 p, %0, 0;\n\t"
+            "@p st.shared.v2.u32 [%1], {%2, %3};\n\t}" ::"r"((unsigned)(mine && (holders & lt_mask) == 0u)),
+            "r"(my_slot), "r"(__float_as_uint(wv)), "r"((uint32_t)(p0 + br[0]))
+            : "memory");
+        __syncthreads();
+        uint32_t sv[W], si[W];
+        if (W == 1) {
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sv[0]), "=r"(si[0]) : "r"(all_slots));
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; w += 2)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(sv[w]), "=r"(si[w]), "=r"(sv[w + 1]), "=r"(si[w + 1])
+                             : "r"(all_slots + w * 8));
+        }
+#pragma unroll
+        for (int w = 1; w < W; w <<= 1)
+#pragma unroll
+            for (int r = 0; r + w < W; r += 2 * w) {
+                const bool hi = __uint_as_float(sv[r + w]) > __uint_as_float(sv[r]);   // lower warp keeps ties
+                sv[r] = hi ? sv[r + w] : sv[r];
+                si[r] = hi ? si[r + w] : si[r];
+            }
+        far = (int)si[0];
+        my_slot ^= W * 8;                                // other parity buffer (slot is aligned to its size)
+        all_slots ^= W * 8;
+    }
+    if (tid == 0 && npoint > 0) hist[npoint - 1] = far;
+    __syncthreads();
+    // ---- results, written once and coalesced: centroids (B,npoint) int64, centroids_vals (B,3,npoint)
+    int64_t *cen = centroids + (size_t)b * npoint;
+    float *vx = vals + (size_t)b * 3 * npoint;
+    for (int s = tid; s < npoint; s += 32 * W) {
+        const int f = hist[s];
+        const float4 c = spt[f];
+        cen[s] = f;
+        vx[s] = c.x;
+        vx[npoint + s] = c.y;
+        vx[2 * npoint + s] = c.z;
+    }
+}
+
+template <int P, int W>
+static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
+                      float *vals, cudaStream_t st)
+{
+    const size_t smem = sizeof(float4) * (size_t)N + sizeof(int) * (size_t)npoint;
+    MLSP_REQUIRE(smem <= 227 * 1024, MLSP_EUNSUPPORTED, "fps: N=%d, npoint=%d needs %zu bytes of shared memory", N, npoint, smem);
+    MLSP_CUDA(cudaFuncSetAttribute(fps_kernel<P, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_kernel<P, W><<<B, 32 * W, smem, st>>>(xyz, N, npoint, start, centroids, vals);
+    MLSP_LAUNCH_CHECK("fps_kernel");
+    return MLSP_OK;
+}
+
+// Large clouds (8192 < N <= 16384): SoA coordinates (12 N bytes of shared memory), strided ownership, two
+// redux.sync per level; results written per round.  Same arithmetic and tie rule.
 template <int PPT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start,
+fps_soa_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start,
            int64_t *__restrict__ centroids, float *__restrict__ vals)
 {
     extern __shared__ float smem[];
@@ -84,13 +208,13 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
 }
 
 template <int PPT, int THREADS>
-static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
+static int launch_fps_soa(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
                       float *vals, cudaStream_t st)
 {
     const size_t smem = sizeof(float) * 3 * (size_t)N;
-    MLSP_CUDA(cudaFuncSetAttribute(fps_kernel<PPT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fps_kernel<PPT, THREADS><<<B, THREADS, smem, st>>>(xyz, N, npoint, start, centroids, vals);
-    MLSP_LAUNCH_CHECK("fps_kernel");
+    MLSP_CUDA(cudaFuncSetAttribute(fps_soa_kernel<PPT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_soa_kernel<PPT, THREADS><<<B, THREADS, smem, st>>>(xyz, N, npoint, start, centroids, vals);
+    MLSP_LAUNCH_CHECK("fps_soa_kernel");
     return MLSP_OK;
 }
 
@@ -105,13 +229,23 @@ extern "C" int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_
     if (npoint == 0) return MLSP_OK;
     cudaStream_t st = as_stream(stream);
     // a valid point with the lowest index wins all-zero rounds; invalid start indices are the caller's bug
-    if (N <= 256) return launch_fps<1, 256>(xyz, B, N, npoint, start, centroids, vals, st);
-    if (N <= 512) return launch_fps<2, 256>(xyz, B, N, npoint, start, centroids, vals, st);
-    if (N <= 1024) return launch_fps<4, 256>(xyz, B, N, npoint, start, centroids, vals, st);
-    if (N <= 2048) return launch_fps<8, 256>(xyz, B, N, npoint, start, centroids, vals, st);
-    if (N <= 4096) return launch_fps<8, 512>(xyz, B, N, npoint, start, centroids, vals, st);
-    if (N <= 8192) return launch_fps<16, 512>(xyz, B, N, npoint, start, centroids, vals, st);
-    if (N <= 16384) return launch_fps<16, 1024>(xyz, B, N, npoint, start, centroids, vals, st);
+    const char *var = getenv("MLSP_FPS_VARIANT");          // tuning hook: "P,W"
+    if (var) {
+        int P = 0, W = 0;
+        if (sscanf(var, "%d,%d", &P, &W) == 2 && N <= 32 * P * W) {
+#define MLSP_FPS_TRY(PP, WW) if (P == PP && W == WW) return launch_fps<PP, WW>(xyz, B, N, npoint, start, centroids, vals, st);
+            MLSP_FPS_TRY(4, 8) MLSP_FPS_TRY(8, 4) MLSP_FPS_TRY(16, 2) MLSP_FPS_TRY(32, 1) MLSP_FPS_TRY(2, 16)
+            MLSP_FPS_TRY(8, 8) MLSP_FPS_TRY(16, 4) MLSP_FPS_TRY(4, 16)
+#undef MLSP_FPS_TRY
+        }
+    }
+    if (N <= 128) return launch_fps<4, 1>(xyz, B, N, npoint, start, centroids, vals, st);
+    if (N <= 512) return launch_fps<4, 4>(xyz, B, N, npoint, start, centroids, vals, st);
+    if (N <= 1024) return launch_fps<8, 4>(xyz, B, N, npoint, start, centroids, vals, st);
+    if (N <= 2048) return launch_fps<8, 8>(xyz, B, N, npoint, start, centroids, vals, st);
+    if (N <= 4096) return launch_fps<8, 16>(xyz, B, N, npoint, start, centroids, vals, st);
+    if (N <= 8192) return launch_fps<16, 16>(xyz, B, N, npoint, start, centroids, vals, st);
+    if (N <= 16384) return launch_fps_soa<16, 1024>(xyz, B, N, npoint, start, centroids, vals, st);
     set_error("fps: N=%d > 16384 not supported", N);
     return MLSP_EUNSUPPORTED;
 }

@@ -412,14 +412,53 @@ def chamfer_distance(p1: torch.Tensor, p2: torch.Tensor, mask: torch.Tensor) -> 
     return _ChamferDir.apply(p1, p2, mask)
 
 
+class _ReconstructionLoss(torch.autograd.Function):
+    """Both Chamfer directions, the per-cloud mean and the 1/B batch mean in one C call (two launches); the
+    backward is one memset + one launch on the saved argmins.  gold and mask are targets: no gradient."""
+
+    @staticmethod
+    def forward(ctx, pred, gold, mask):
+        B, N, _ = pred.shape
+        dev = pred.device
+        m, mbs = _mask_rows(mask)
+        argmin = torch.empty((2, B, N), dtype=torch.int64, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _workspace(_lib.OP_CHAMFER, B, 3, N, 0, dev)
+            _lib.call("mlsp_reconstruction_loss_fwd", _ptr(pred), *_point_strides(pred), _ptr(gold), *_point_strides(gold),
+                      _ptr(m), mbs, B, N, _ptr(argmin), _ptr(loss), _ptr(ws), ws.numel(), _stream(dev))
+        ctx.save_for_backward(pred, gold, m, argmin)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad):
+        pred, gold, m, argmin = ctx.saved_tensors
+        B, N, _ = pred.shape
+        dev = pred.device
+        gp = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+        grad = grad.to(torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            _lib.call("mlsp_reconstruction_loss_bwd", _ptr(pred), *_point_strides(pred), _ptr(gold), *_point_strides(gold),
+                      _ptr(m), m.stride(0), _ptr(argmin), B, N, _ptr(grad), _ptr(gp), _stream(dev))
+        return gp, None, None
+
+
 def reconstruction_loss(pred: torch.Tensor, gold: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
-    """reconstruction_loss(pred, gold, mask): MLSP/mlsp.py:156-182.  pred (B,N,3), gold (B,3,N), mask (B,3,N)."""
+    """reconstruction_loss(pred, gold, mask): MLSP/mlsp.py:156-182.  pred (B,N,3), gold (B,3,N), mask (B,3,N)
+    -> 0-d tensor, differentiable w.r.t. pred.  If gold itself requires a gradient (no reference caller does)
+    the two chamfer_distance directions are composed like the reference does."""
     batch_size = pred.size(0)
     gold = gold.permute(0, 2, 1)
     mask = mask.permute(0, 2, 1)
-    dist_gold = chamfer_distance(gold, pred, mask)
-    dist_pred = chamfer_distance(pred, gold, mask)
-    return (1 / batch_size) * (dist_gold + dist_pred)
+    if gold.requires_grad and torch.is_grad_enabled():
+        return (1 / batch_size) * (chamfer_distance(gold, pred, mask) + chamfer_distance(pred, gold, mask))
+    _require_cuda_f32(pred, "reconstruction_loss")
+    _require_cuda_f32(gold, "reconstruction_loss")
+    _require_cuda_f32(mask, "reconstruction_loss")
+    assert pred.size(0) == gold.size(0) and pred.size(2) == gold.size(2)   # mlsp.py:125
+    if pred.size(1) != gold.size(1):
+        raise MlspError("reconstruction_loss: both clouds must have N points (the mask indexes both)")
+    return _ReconstructionLoss.apply(pred, gold, mask)
 
 
 def findneareat_index(p1: torch.Tensor, p2: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:

@@ -313,6 +313,20 @@ def test_chamfer_full_size(dev, orc, npo, B, N):
     np.testing.assert_allclose(_np(a.grad.sum(1)), -_np(b.grad.sum(1)), rtol=1e-3, atol=1e-5)
 
 
+def test_reconstruction_loss_fused_equals_composed(golden, dev):
+    """The one-call loss (mlsp_reconstruction_loss_fwd/bwd) against the reference's own composition of two
+    chamfer_distance directions (mlsp_chamfer_dir_*), value and gradient, with an upstream scale."""
+    g, pred, gold, mask = _chamfer_case(golden, dev, "chamfer")
+    (3.0 * M.reconstruction_loss(pred, gold, mask)).backward()
+    fused, gfused = M.reconstruction_loss(pred.detach(), gold, mask).item(), pred.grad.clone()
+    p2 = pred.detach().clone().requires_grad_(True)
+    gp, mp = gold.permute(0, 2, 1), mask.permute(0, 2, 1)
+    comp = (1 / p2.size(0)) * (M.chamfer_distance(gp, p2, mp) + M.chamfer_distance(p2, gp, mp))
+    (3.0 * comp).backward()
+    assert abs(fused - comp.item()) <= 1e-6 * abs(comp.item())
+    np.testing.assert_allclose(_np(gfused), _np(p2.grad), rtol=1e-5, atol=1e-9)
+
+
 # ------------------------------------------------------------------------------------------------ streams
 def test_ops_follow_current_stream(dev, orc):
     x = synth.clouds(4, 512, 9)
