@@ -22,6 +22,7 @@
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA) -- profiles/.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "topk.cuh"
@@ -31,7 +32,7 @@ namespace mlsp {
 constexpr int KT_ROWS = 128;     // query rows per CTA   (UMMA M, TMEM lanes)
 constexpr int KT_COLS = 128;     // candidates per tile  (UMMA N, TMEM columns per accumulator buffer)
 constexpr int KT_KBLK = 64;      // bf16 per K block = one 128-byte swizzle span
-constexpr int KT_MAX_STAGES = 4;
+constexpr int KT_MAX_STAGES = 8;
 constexpr int KT_EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes one 64-column half of every tile
 constexpr int KT_THREADS = 64 + 32 * KT_EPI_WARPS;
 constexpr uint32_t KT_BLK_BYTES = KT_COLS * KT_KBLK * 2;  // 16 KiB per (128 x 64) bf16 block
@@ -122,6 +123,25 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&r)[16])
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
+// asynchronous 16-column load: the registers are valid only after tc_wait16 on the same array (the "+r"
+// operands make every later use of the values depend on the wait, so the compiler cannot hoist them above it)
+__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&u)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait16(uint32_t (&u)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
+                   "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * KT_EPI_WARPS) : "memory"); }
 
 // K-major, 128-byte swizzled operand block (rows 128 B apart, 8-row groups 1024 B apart), sm_100 version bit
@@ -132,50 +152,55 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
 // kind::f16: D = f32, A = B = bf16, both K-major, N = 128, M = 128
 constexpr uint32_t KT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((KT_COLS >> 3) << 17) | ((KT_ROWS >> 4) << 24);
 
-// ------------------------------------------------------------------------------------------- prep kernels
-// norms (exact, spec order) + per-cloud max norm (uint bit pattern max is valid for non-negative floats)
-__global__ void sq_norms_max_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xx,
-                                    unsigned int *__restrict__ maxbits)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    float s = 0.0f;
-    if (j < N) {
-        const float *xb = x + (size_t)b * C * N;
-        float v = xb[j];
-        s = __fmul_rn(v, v);
-        for (int c = 1; c < C; ++c) {
-            v = xb[(size_t)c * N + j];
-            s = __fadd_rn(s, __fmul_rn(v, v));
-        }
-        xx[(size_t)b * N + j] = s;
-    }
-    const unsigned int m = __reduce_max_sync(MLSP_FULL, __float_as_uint(s));
-    if ((threadIdx.x & 31) == 0) atomicMax(maxbits + b, m);
-}
+// ------------------------------------------------------------------------------------------- prep kernel
+// One pass over x (B,C,N): exact norms in the specification order (sequential adds over the channels),
+// per-cloud max norm (uint bit-pattern max is valid for non-negative floats), the point-major fp32 rows
+// xt (B,N,C) and the bf16 split hi/lo (B*N, C).  A CTA stages a [C][PREP_PTS] slab in shared memory
+// (coalesced 128-byte reads along n), then warps write whole point rows (coalesced along c).
+constexpr int PREP_PTS = 32;
+constexpr int PREP_THREADS = 256;
 
-// (B,C,N) fp32 -> xt (B,N,C) fp32, hi/lo (B*N, C) bf16 ; 32x32 tiles through shared memory
-__global__ void knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xt,
-                                __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo)
+__global__ void __launch_bounds__(PREP_THREADS)
+knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xx, unsigned int *__restrict__ maxbits,
+                float *__restrict__ xt, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo)
 {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    extern __shared__ float slab[];                       // [C][PREP_PTS + 1]
+    const int b = blockIdx.y, n0 = blockIdx.x * PREP_PTS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *xb = x + (size_t)b * C * N;
-    for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
-        const int c = c0 + cc, n = n0 + threadIdx.x;
-        tile[cc][threadIdx.x] = (c < C && n < N) ? xb[(size_t)c * N + n] : 0.0f;
+    for (int c = warp; c < C; c += PREP_THREADS / 32) {
+        const int n = n0 + lane;
+        slab[c * (PREP_PTS + 1) + lane] = (n < N) ? xb[(size_t)c * N + n] : 0.0f;
     }
     __syncthreads();
-    for (int nn = threadIdx.y; nn < 32; nn += blockDim.y) {
-        const int n = n0 + nn, c = c0 + threadIdx.x;
-        if (n < N && c < C) {
-            const float v = tile[threadIdx.x][nn];
-            const size_t o = ((size_t)b * N + n) * C + c;
-            xt[o] = v;
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            hi[o] = h;
-            lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    if (warp == 0) {                                       // norms: one point per lane, channels in order
+        float v = slab[lane];
+        float s = __fmul_rn(v, v);
+        for (int c = 1; c < C; ++c) {
+            v = slab[c * (PREP_PTS + 1) + lane];
+            s = __fadd_rn(s, __fmul_rn(v, v));
         }
+        const int n = n0 + lane;
+        if (n < N) xx[(size_t)b * N + n] = s; else s = 0.0f;
+        const unsigned int m = __reduce_max_sync(MLSP_FULL, __float_as_uint(s));
+        if (lane == 0) atomicMax(maxbits + b, m);
+    }
+    // rows: thread t handles channel pair (2t mod C ...) of point rows; consecutive threads -> consecutive channels
+    const int pairs = C / 2;                               // C is even (64 or 128)
+    for (int e = threadIdx.x; e < PREP_PTS * pairs; e += PREP_THREADS) {
+        const int pt = e / pairs, c = 2 * (e - pt * pairs);
+        const int n = n0 + pt;
+        if (n >= N) continue;
+        const float v0 = slab[c * (PREP_PTS + 1) + pt], v1 = slab[(c + 1) * (PREP_PTS + 1) + pt];
+        const size_t o = ((size_t)b * N + n) * C + c;
+        *reinterpret_cast<float2 *>(xt + o) = make_float2(v0, v1);
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        __nv_bfloat162 hv, lv;
+        hv.x = h0; hv.y = h1;
+        lv.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+        lv.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+        *reinterpret_cast<__nv_bfloat162 *>(hi + o) = hv;
+        *reinterpret_cast<__nv_bfloat162 *>(lo + o) = lv;
     }
 }
 
@@ -241,35 +266,60 @@ struct EpiState {
     }
 };
 
-// one thread, one query row, 64 columns in pieces of 16 (tcgen05.ld 32x32b.x16): v = |x_j|^2 - 2 dot~
-// (16-wide pieces keep accumulators + class minima inside the 102-register budget of two CTAs per SM)
+// one 16-column piece of one query row: v = |x_j|^2 - 2 dot~
+//   PASS 1: class minima (class = column within the thread's 64-column half, mod NG)
+//   PASS 2: columns with v <= thr are collected as a bit mask, then appended to the row's list (rare)
 template <int NG, int PASS>
-__device__ __forceinline__ void epi_tile(EpiState<NG> &st, uint32_t taddr, const float *nrm, float thr, int jbase)
+__device__ __forceinline__ void epi_piece(EpiState<NG> &st, const uint32_t (&u)[16], const float4 *nrm4, int ch,
+                                          float thr, int jbase)
 {
     constexpr int CAP = 2 * NG;
-    const float4 *nrm4 = reinterpret_cast<const float4 *>(nrm);
+    uint32_t hits = 0;
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        float acc[16];
-        tc_ld16(taddr + ch * 16, acc);
+    for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 nj = nrm4[ch * 4 + c4];
+        const float nv[4] = {nj.x, nj.y, nj.z, nj.w};
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 nj = nrm4[ch * 4 + c4];
-            const float nv[4] = {nj.x, nj.y, nj.z, nj.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = 4 * c4 + u;
-                const float v = __fmaf_rn(-2.0f, acc[c], nv[u]);
-                if (PASS == 1) {
-                    const int e = (ch * 16 + c) % NG;           // column class j mod NG (static)
-                    st.gmin[e] = fminf(st.gmin[e], v);
-                } else if (v <= thr) {                          // rare (about 1.5 k / N of the columns)
-                    const int pos = atomicAdd(st.cnt, 1);       // the row's list is shared by its two threads
-                    if (pos < CAP) st.list[pos] = (uint16_t)(jbase + ch * 16 + c);
-                }
+        for (int w = 0; w < 4; ++w) {
+            const int c = 4 * c4 + w;
+            const float v = __fmaf_rn(-2.0f, __uint_as_float(u[c]), nv[w]);
+            if (PASS == 1) {
+                const int e = (ch * 16 + c) % NG;
+                st.gmin[e] = fminf(st.gmin[e], v);
+            } else {
+                hits |= (v <= thr) ? (1u << c) : 0u;
             }
         }
     }
+    if (PASS == 2) {
+        while (hits) {                                              // about 1.2 k / N of the columns
+            const int c = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int pos = atomicAdd(st.cnt, 1);                   // the row's list is shared by its two threads
+            if (pos < CAP) st.list[pos] = (uint16_t)(jbase + ch * 16 + c);
+        }
+    }
+}
+
+// one thread, one query row, 64 columns in four pieces (tcgen05.ld 32x32b.x16), the load of piece p+1 in flight
+// while piece p is processed
+template <int NG, int PASS>
+__device__ __forceinline__ void epi_tile(EpiState<NG> &st, uint32_t taddr, const float *nrm, float thr, int jbase)
+{
+    const float4 *nrm4 = reinterpret_cast<const float4 *>(nrm);
+    uint32_t ua[16], ub[16];
+    tc_ld16_issue(taddr, ua);
+    tc_wait16(ua);
+    tc_ld16_issue(taddr + 16, ub);
+    epi_piece<NG, PASS>(st, ua, nrm4, 0, thr, jbase);
+    tc_wait16(ub);
+    tc_ld16_issue(taddr + 32, ua);
+    epi_piece<NG, PASS>(st, ub, nrm4, 1, thr, jbase);
+    tc_wait16(ua);
+    tc_ld16_issue(taddr + 48, ub);
+    epi_piece<NG, PASS>(st, ua, nrm4, 2, thr, jbase);
+    tc_wait16(ub);
+    epi_piece<NG, PASS>(st, ub, nrm4, 3, thr, jbase);
 }
 
 // test hook: write the approximate values of this thread's 64 columns
@@ -435,19 +485,19 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             if (lane == 0) mbar_arrive(tm_empty + buf);
             if (et < KT_COLS) nrm_s[(buf ^ 1) * KT_COLS + et] = nxt;
         }
-        // ---- between the passes: merge the two halves' class minima, tau = k-th smallest, broadcast thr
+        // ---- between the passes: the row has 2 NG class minima (NG per thread).  Each thread sorts its own;
+        // the k-th smallest of the union of two sorted lists A, B is max_{i<k} min(A[i], B[k-1-i]).
+        reg_sort<NG>(st.gmin);
         if (h == 1) {
 #pragma unroll
             for (int e = 0; e < NG; ++e) xchg[e * KT_ROWS + r] = st.gmin[e];
         }
         epi_bar_sync();
         if (h == 0) {
+            float tau = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < NG; ++e) st.gmin[e] = fminf(st.gmin[e], xchg[e * KT_ROWS + r]);
-            reg_sort<NG>(st.gmin);
-            float tau = st.gmin[0];
-#pragma unroll
-            for (int e = 1; e < NG; ++e) tau = (e == P.k - 1) ? st.gmin[e] : tau;
+            for (int e = 0; e < NG; ++e)
+                if (e < P.k) tau = fmaxf(tau, fminf(st.gmin[e], xchg[(P.k - 1 - e) * KT_ROWS + r]));
             thr_s[r] = tau + 2.0f * eps;
         }
         epi_bar_sync();                          // xchg (aliasing the lists) is dead from here on
@@ -488,72 +538,87 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------- refine
-// Exact fp32 re-rank of the candidate lists.  One warp per query row; EIGHT lanes share one candidate: lane t
-// of a group reads the float4 pieces f = 8s + t of the candidate's point-major row (a warp-wide load touches
-// 4 candidates x 128 contiguous bytes) and runs partial chain t of the pinned dot product; three xor-shuffles
-// are the butterfly of oracle dot_tree, so all 8 lanes hold the exact specification value.  The warp then sorts
-// (value desc, index asc) and writes the first k.  Rows whose list overflowed go to the fallback list.
-template <int NG>
-__global__ void __launch_bounds__(256)
+// Exact fp32 re-rank of the candidate lists.  One warp per query row, FOUR lanes per candidate, eight candidates
+// per pass: lane u of a group owns chains t = u and t = u + 4 of the pinned dot product (float4 pieces
+// f = u, u+4, u+8, ... of the point-major rows), so a warp-wide load touches 8 candidates x 64 contiguous bytes
+// and the query row's pieces live in registers.  p_u + p_{u+4} is a register add, two xor-shuffles finish the
+// tree of oracle dot_tree: ((p0+p4)+(p2+p6)) + ((p1+p5)+(p3+p7)), and all four lanes hold the exact value.
+// Lane 4g+u keeps the candidate its group computed in pass u; the warp then sorts (value desc, index asc) --
+// one key per lane when the list has <= 32 entries, the usual case -- and writes the first k.  Rows whose list
+// overflowed (or is shorter than k) go to the fallback list.
+constexpr int RF_WARPS = 8;
+
+template <int NG, int C>
+__global__ void __launch_bounds__(32 * RF_WARPS)
 knn_refine_kernel(KtParams P, long long total_rows)
 {
     constexpr int CAP = 2 * NG;
     constexpr int SLOTS = CAP / 32;
-    const int lane = threadIdx.x & 31;
-    const int grp = lane >> 3, t = lane & 7;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // b*N + i
+    constexpr int M = C / 16;                             // float4 pieces per lane: 4 (C = 64) or 8 (C = 128)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, u = lane & 3;
+    const long long row = (long long)blockIdx.x * RF_WARPS + warp;   // b*N + i
     if (row >= total_rows) return;
-    const long long base = (row / P.N) * P.N;
     const int cnt = P.cand_cnt[row];
     if (cnt > CAP || cnt < P.k) {
         if (lane == 0) P.fb_rows[atomicAdd(P.fb_count, 1)] = (int)row;
         return;
     }
-    const int S = P.C / 32;                   // float4 pieces per lane: 2 (C = 64) or 4 (C = 128)
-    const float4 *xi = reinterpret_cast<const float4 *>(P.xt + (size_t)row * P.C);
-    float4 xr[4];
+    const long long base = (row / P.N) * P.N;
+    const float4 *xig = reinterpret_cast<const float4 *>(P.xt + (size_t)row * C);
+    float4 xr[M];
 #pragma unroll
-    for (int s = 0; s < 4; ++s) xr[s] = (s < S) ? xi[8 * s + t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < M; ++m) xr[m] = xig[4 * m + u];
     const float xxi = P.xx[row];
     const uint16_t *list = P.cand + (size_t)row * CAP;
+
     unsigned long long key[SLOTS];
 #pragma unroll
-    for (int rnd = 0; rnd < SLOTS; ++rnd) {
-        key[rnd] = rank_key(-INFINITY, 0x7fffffff, false);
-        if (rnd * 32 < cnt) {
+    for (int s = 0; s < SLOTS; ++s) {
+        key[s] = rank_key(-INFINITY, 0x7fffffff, false);
 #pragma unroll
-            for (int step = 0; step < 8; ++step) {
-                const int e0 = rnd * 32 + step * 4;
-                if (e0 < cnt) {                                     // warp-uniform
-                    const int e = e0 + grp;
-                    const bool live = e < cnt;
-                    const int j = live ? (int)list[e] : 0;
-                    const float4 *xj = reinterpret_cast<const float4 *>(P.xt + ((size_t)base + j) * P.C);
-                    float acc = 0.0f;
+        for (int ps = 0; ps < 4; ++ps) {
+            const int e0 = s * 32 + ps * 8;
+            if (e0 < cnt) {                                // warp-uniform
+                const int e = e0 + g;
+                const bool live = e < cnt;
+                const int j = live ? (int)list[e] : 0;
+                const float4 *xj = reinterpret_cast<const float4 *>(P.xt + ((size_t)base + j) * C);
+                float4 q[M];
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        if (s < S) {
-                            const float4 qv = xj[8 * s + t];
-                            acc = __fmaf_rn(xr[s].x, qv.x, acc);
-                            acc = __fmaf_rn(xr[s].y, qv.y, acc);
-                            acc = __fmaf_rn(xr[s].z, qv.z, acc);
-                            acc = __fmaf_rn(xr[s].w, qv.w, acc);
-                        }
-                    }
-                    acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 4));
-                    acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 2));
-                    acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 1));
-                    const float pd = __fsub_rn(__fmaf_rn(2.0f, acc, -P.xx[base + j]), xxi);
-                    if (step == t) key[rnd] = rank_key(pd, live ? j : 0x7fffffff, live);   // lane keeps e = 32 rnd + 4 t + grp
+                for (int m = 0; m < M; ++m) q[m] = __ldg(xj + 4 * m + u);
+                const float xxj = P.xx[base + j];
+                float pa = 0.0f, pb = 0.0f;                // chains t = u and t = u + 4
+#pragma unroll
+                for (int m = 0; m < M; m += 2) {
+                    pa = __fmaf_rn(xr[m].x, q[m].x, pa);
+                    pa = __fmaf_rn(xr[m].y, q[m].y, pa);
+                    pa = __fmaf_rn(xr[m].z, q[m].z, pa);
+                    pa = __fmaf_rn(xr[m].w, q[m].w, pa);
+                    pb = __fmaf_rn(xr[m + 1].x, q[m + 1].x, pb);
+                    pb = __fmaf_rn(xr[m + 1].y, q[m + 1].y, pb);
+                    pb = __fmaf_rn(xr[m + 1].z, q[m + 1].z, pb);
+                    pb = __fmaf_rn(xr[m + 1].w, q[m + 1].w, pb);
                 }
+                float acc = __fadd_rn(pa, pb);                                        // q_u = p_u + p_{u+4}
+                acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 2));             // q0+q2 | q1+q3
+                acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 1));             // (q0+q2) + (q1+q3)
+                const float pd = __fsub_rn(__fmaf_rn(2.0f, acc, -xxj), xxi);
+                if (ps == u) key[s] = rank_key(pd, live ? j : 0x7fffffff, live);
             }
         }
     }
-    warp_sort_u64<SLOTS>(key);
+    if (SLOTS == 1 || cnt <= 32) {                         // warp-uniform: one key per lane
+        unsigned long long k1[1] = {key[0]};
+        warp_sort_u64<1>(k1);
+        if (lane < P.k) P.idx[(size_t)row * P.k + lane] = (int64_t)(uint32_t)(k1[0] & 0xffffffffull);
+    } else {
+        warp_sort_u64<SLOTS>(key);
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int e = s * 32 + lane;
-        if (e < P.k) P.idx[(size_t)row * P.k + e] = (int64_t)(uint32_t)(key[s] & 0xffffffffull);
+        for (int s = 0; s < SLOTS; ++s) {
+            const int e = s * 32 + lane;
+            if (e < P.k) P.idx[(size_t)row * P.k + e] = (int64_t)(uint32_t)(key[s] & 0xffffffffull);
+        }
     }
     if (lane == 0) atomicAdd(P.stats, 1);
 }
@@ -666,9 +731,8 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     int *rows = reinterpret_cast<int *>(w + L.off_rows);
 
     MLSP_CUDA(cudaMemsetAsync(w, 0, L.off_xx, st));    // counters + per-cloud max
-    sq_norms_max_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, C, N, xx, reinterpret_cast<unsigned int *>(maxxx));
-    MLSP_LAUNCH_CHECK("sq_norms_max_kernel");
-    knn_prep_kernel<<<dim3((N + 31) / 32, (C + 31) / 32, B), dim3(32, 8), 0, st>>>(x, C, N, xt, hi, lo);
+    knn_prep_kernel<<<dim3((N + PREP_PTS - 1) / PREP_PTS, B), PREP_THREADS, sizeof(float) * C * (PREP_PTS + 1), st>>>(
+        x, C, N, xx, reinterpret_cast<unsigned int *>(maxxx), xt, hi, lo);
     MLSP_LAUNCH_CHECK("knn_prep_kernel");
 
     CUtensorMap map_hi, map_lo;
@@ -684,8 +748,9 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     const int NG = (k <= 32) ? 32 : 64;
     const int KB = 3 * C / KT_KBLK;
     P.stages = (C == 64) ? 2 : 4;          // C = 64: 48 K (A') + 32 K (ring) + lists -> two CTAs per SM
+    if (const char *e = getenv("MLSP_KT_STAGES")) P.stages = atoi(e);   // tuning hook
     const size_t smem = (size_t)(KB + P.stages) * KT_BLK_BYTES + (size_t)KT_ROWS * 2 * NG * 2 + 2 * KT_COLS * 4 +
-                        2 * KT_ROWS * 4 + 16 * 8 + 16 + 1024;
+                        2 * KT_ROWS * 4 + 32 * 8 + 16 + 1024;
     dim3 grid((N + KT_ROWS - 1) / KT_ROWS, B);
     if (NG == 32) {
         MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -697,11 +762,15 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     MLSP_LAUNCH_CHECK("knn_tensor_kernel");
     {
         const long long rows_total = (long long)B * N;
-        const unsigned rblocks = (unsigned)((rows_total + 7) / 8);
-        if (NG == 32)
-            knn_refine_kernel<32><<<rblocks, 256, 0, st>>>(P, rows_total);
+        const unsigned rblocks = (unsigned)((rows_total + RF_WARPS - 1) / RF_WARPS);
+        if (NG == 32 && C == 64)
+            knn_refine_kernel<32, 64><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+        else if (NG == 32)
+            knn_refine_kernel<32, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+        else if (C == 64)
+            knn_refine_kernel<64, 64><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
         else
-            knn_refine_kernel<64><<<rblocks, 256, 0, st>>>(P, rows_total);
+            knn_refine_kernel<64, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
         MLSP_LAUNCH_CHECK("knn_refine_kernel");
     }
     const int fb_blocks = 2 * sm_count();
