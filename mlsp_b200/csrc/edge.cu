@@ -8,7 +8,11 @@
 // stores.  HBM traffic is the algorithmic 4BCN + 8BNk + 8BCNk bytes; the kernel is bandwidth bound.
 // Backward: one pass over grad_out accumulates the centre terms in registers and scatters the
 // neighbour terms with vector float atomics into gxt (B,N,C) in L2, then a transpose back to (B,C,N).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mlsp {
 
@@ -100,7 +104,41 @@ edge_fwd_vec_kernel(const float4 *__restrict__ xt, const int64_t *__restrict__ i
     }
 }
 
-// ---- forward, any C (used for C = 3): one thread per output element, fully coalesced stores ----------
+// ---- forward, C = 3 (the two 3-D DGCNN layers): one thread per 128-bit piece of the output ------------
+// The output row of (point p, neighbour j) is 6 floats (d0 d1 d2 c0 c1 c2), so three float4 cover two rows:
+//   piece 0 = row 2m (d0 d1 d2 c0), piece 1 = row 2m (c1 c2) + row 2m+1 (d0 d1), piece 2 = row 2m+1 (d2 c0 c1 c2).
+// Consecutive threads write consecutive float4 (fully coalesced streaming stores); x is read in its own
+// (B,3,N) layout (12 KB per cloud: L1 hits), so no transposed copy is needed.
+__global__ void __launch_bounds__(256)
+edge_fwd3_kernel(const float *__restrict__ x, const int64_t *__restrict__ idx, uint32_t N, uint32_t k,
+                 float4 *__restrict__ out, uint32_t total4)
+{
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    if (t >= total4) return;
+    const uint32_t m = t / 3u, s = t - 3u * m;
+    const uint32_t r0 = 2u * m, r1 = r0 + 1u;
+    const uint32_t ra = (s == 0u) ? r0 : r1;               // the row whose difference terms this piece holds
+    const uint32_t pa = ra / k, ba = pa / N, ia = pa - ba * N;
+    const float *xa = x + (size_t)ba * 3u * N;
+    const uint32_t n = (uint32_t)idx[ra];
+    float4 o;
+    if (s == 0u) {
+        const float c0 = __ldg(xa + ia), c1 = __ldg(xa + N + ia), c2 = __ldg(xa + 2u * N + ia);
+        o = make_float4(__fsub_rn(__ldg(xa + n), c0), __fsub_rn(__ldg(xa + N + n), c1),
+                        __fsub_rn(__ldg(xa + 2u * N + n), c2), c0);
+    } else if (s == 2u) {
+        const float c0 = __ldg(xa + ia), c1 = __ldg(xa + N + ia), c2 = __ldg(xa + 2u * N + ia);
+        o = make_float4(__fsub_rn(__ldg(xa + 2u * N + n), c2), c0, c1, c2);
+    } else {
+        const uint32_t p0 = r0 / k, b0 = p0 / N, i0 = p0 - b0 * N;
+        const float *x0 = x + (size_t)b0 * 3u * N;
+        o = make_float4(__ldg(x0 + N + i0), __ldg(x0 + 2u * N + i0), __fsub_rn(__ldg(xa + n), __ldg(xa + ia)),
+                        __fsub_rn(__ldg(xa + N + n), __ldg(xa + N + ia)));
+    }
+    st_stream_f4(out + t, o);
+}
+
+// ---- forward, any C (C % 4 != 0 and not the 3-D fast path): one thread per output element, fully coalesced stores ----------
 __global__ void __launch_bounds__(256)
 edge_fwd_scalar_kernel(const float *__restrict__ xt, const int64_t *__restrict__ idx, int N, int k, int C,
                        float *__restrict__ out, long long total)
@@ -184,6 +222,81 @@ edge_bwd_vec_kernel(const float4 *__restrict__ g, const int64_t *__restrict__ id
     }
 }
 
+// ---- backward, C = 3: one cluster of 8 CTAs per cloud, accumulators in (distributed) shared memory ----
+// Each CTA of the cluster takes N/8 query points and accumulates into its own copy of the cloud's gradient
+// acc[3][N] in shared memory (red.shared: the neighbour terms land anywhere in the cloud); one warp per
+// point reads its k*6 gradients as coalesced float2, reduces the three centre terms in registers.  After a
+// cluster barrier CTA r sums the eight copies of its slice through DSMEM and writes grad_x (B,3,N) directly:
+// no global atomics, no memset, no transposed buffer.
+constexpr int EB3_CL = 8;
+constexpr int EB3_THREADS = 1024;
+
+__global__ void __cluster_dims__(EB3_CL, 1, 1) __launch_bounds__(EB3_THREADS)
+edge_bwd3_kernel(const float *__restrict__ g, const int64_t *__restrict__ idx, int N, int k, float *__restrict__ gx)
+{
+    extern __shared__ float acc[];                          // [3][N]
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < 3 * N; e += EB3_THREADS) acc[e] = 0.0f;
+    __syncthreads();
+    const int chunk = (N + EB3_CL - 1) / EB3_CL;
+    const int i_lo = rank * chunk, i_hi = min(N, i_lo + chunk);
+    const int F = 3 * k;                                     // float2 pieces per point
+    for (int i = i_lo + warp; i < i_hi; i += EB3_THREADS / 32) {
+        const size_t row0 = ((size_t)b * N + i) * k;
+        const float2 *gr = reinterpret_cast<const float2 *>(g + row0 * 6);
+        const int64_t *ir = idx + row0;
+        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+        for (int f0 = 0; f0 < F; f0 += 128) {
+            float2 v[4];
+            int n[4], sel[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                    // all loads of the point in flight first
+                const int f = f0 + u * 32 + lane;
+                const bool ok = f < F;
+                const int j = f / 3;
+                sel[u] = ok ? f - 3 * j : 3;
+                v[u] = ok ? __ldcs(gr + f) : make_float2(0.0f, 0.0f);
+                n[u] = (sel[u] < 2) ? (int)ir[j] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (sel[u] == 0) {                           // (d0, d1)
+                    atomicAdd(acc + n[u], v[u].x);
+                    atomicAdd(acc + N + n[u], v[u].y);
+                    c0 -= v[u].x;
+                    c1 -= v[u].y;
+                } else if (sel[u] == 1) {                    // (d2, c0)
+                    atomicAdd(acc + 2 * N + n[u], v[u].x);
+                    c2 -= v[u].x;
+                    c0 += v[u].y;
+                } else if (sel[u] == 2) {                    // (c1, c2)
+                    c1 += v[u].x;
+                    c2 += v[u].y;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c0 += __shfl_xor_sync(MLSP_FULL, c0, o);
+            c1 += __shfl_xor_sync(MLSP_FULL, c1, o);
+            c2 += __shfl_xor_sync(MLSP_FULL, c2, o);
+        }
+        if (lane < 3) atomicAdd(acc + lane * N + i, lane == 0 ? c0 : (lane == 1 ? c1 : c2));
+    }
+    cl.sync();
+    const int span = i_hi - i_lo;
+    for (int e = tid; e < 3 * span; e += EB3_THREADS) {
+        const int c = e / span, n = i_lo + (e - c * span);
+        float s = 0.0f;
+#pragma unroll
+        for (int q = 0; q < EB3_CL; ++q) s += cl.map_shared_rank(acc, q)[c * N + n];
+        gx[((size_t)b * 3 + c) * N + n] = s;
+    }
+    cl.sync();                                               // peers may still be reading this CTA's copy
+}
+
 __global__ void __launch_bounds__(256)
 edge_bwd_scalar_kernel(const float *__restrict__ g, const int64_t *__restrict__ idx, int N, int k, int C,
                        float *__restrict__ gxt, long long total_rows)
@@ -211,10 +324,17 @@ extern "C" int mlsp_edge_gather_fwd(const float *x, const int64_t *idx, int B, i
     MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "edge_gather_fwd: bad shape");
     MLSP_REQUIRE(ws_bytes >= edge_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "edge_gather_fwd: workspace too small");
     cudaStream_t st = as_stream(stream);
+    const long long points = (long long)B * N;
+    if (C == 3 && (points * k) % 2 == 0 && points * k < (1ll << 31) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const uint32_t total4 = (uint32_t)(points * k * 6 / 4);
+        edge_fwd3_kernel<<<(total4 + 255u) / 256u, 256, 0, st>>>(x, idx, (uint32_t)N, (uint32_t)k,
+                                                                  reinterpret_cast<float4 *>(out), total4);
+        MLSP_LAUNCH_CHECK("edge_fwd3_kernel");
+        return MLSP_OK;
+    }
     float *xt = static_cast<float *>(ws);
     int rc = launch_transpose(x, xt, B, C, N, st);  // (B,C,N) -> (B,N,C)
     if (rc) return rc;
-    const long long points = (long long)B * N;
     if (C % 4 == 0) {
         const int warps = 8;
         const long long blocks = (points + warps - 1) / warps;
@@ -240,6 +360,13 @@ extern "C" int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, i
     MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "edge_gather_bwd: bad shape");
     MLSP_REQUIRE(ws_bytes >= edge_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "edge_gather_bwd: workspace too small");
     cudaStream_t st = as_stream(stream);
+    if (C == 3 && sizeof(float) * 3 * (size_t)N <= 200 * 1024 && B <= 65535) {
+        const size_t smem = sizeof(float) * 3 * (size_t)N;
+        MLSP_CUDA(cudaFuncSetAttribute(edge_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        edge_bwd3_kernel<<<dim3(EB3_CL, B), EB3_THREADS, smem, st>>>(grad_out, idx, N, k, grad_x);
+        MLSP_LAUNCH_CHECK("edge_bwd3_kernel");
+        return MLSP_OK;
+    }
     float *gxt = static_cast<float *>(ws);
     MLSP_CUDA(cudaMemsetAsync(gxt, 0, sizeof(float) * (size_t)B * C * N, st));
     const long long points = (long long)B * N;

@@ -4,11 +4,12 @@
 // rank pd descending / index ascending), different selection: with K = 3 the distance costs 5 instructions, so the
 // per-candidate insertion of topk.cuh (about 20 instructions, ~100 insertions per row) dominated.  Here a warp owns
 // R rows and makes two passes over the cloud (staged once per CTA in shared memory as (x,y,z,|x|^2) float4):
-//   pass 1: every lane keeps, per row, the best pd among ITS candidates (j = lane mod 32: a "class" maximum).
+//   pass 1: every lane keeps, per row, the best pd of each of ITS NC candidate classes (class = (j/32 mod NC, j mod 32)).
 //           The class maxima are 32*NC distinct candidates, so tau = their k-th largest value is a lower bound of
 //           the k-th best pd of the row.  (warp bitonic sort of orderable 32-bit keys, one shuffle per stage)
 //   pass 2: pd is recomputed and every candidate with pd >= tau (ties included -> superset of the exact top-k,
-//           about 1.5 k entries expected) is appended to the row's list in shared memory by ballot compaction.
+//           about 1.2 k entries expected) is recorded as one bit of a per-lane mask; the masks become the row's
+//           index list in shared memory once per 1024 candidates (prefix sum of popcounts).
 //   final : the list is sorted by (pd desc, index asc) with 64-bit keys; the first k are the answer.
 // A row whose list overflows (heavy duplicates / degenerate clouds) is re-done with the streaming selection.
 #include "common.cuh"
@@ -63,15 +64,17 @@ __device__ __forceinline__ void warp_sort_desc_u32(uint32_t (&key)[NC])
     }
 }
 
-// NC = classes per lane (1: k <= 32, 2: k <= 64);  list capacity CAPL = 64 * NC
+// NC = classes per lane (class of candidate j = (j / 32) mod NC, j mod 32): 32*NC classes.  More classes than k
+// tighten tau: the expected list length is sum_{i<k} M/(M-i) for M classes (23.7 for k = 20, M = 64; 47.7 for
+// k = 40, M = 128), so the final sort usually runs on HALF the capacity CAPL = 32*NC.
 template <int NC>
 __global__ void __launch_bounds__(K3_THREADS)
 knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx)
 {
-    constexpr int CAPL = 64 * NC;
+    constexpr int CAPL = 32 * NC;
     constexpr int SL = CAPL / 32;
     extern __shared__ float4 cloud[];                                  // [N]
-    uint2 *lists = reinterpret_cast<uint2 *>(cloud + N);               // [warps][R][CAPL] (pd bits, j)
+    uint16_t *lists = reinterpret_cast<uint16_t *>(cloud + N);         // [warps][R][CAPL] candidate indices
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
@@ -125,51 +128,84 @@ knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx
         tau[rr] = __uint_as_float(u);
     }
 
-    // ---- pass 2: collect every candidate with pd >= tau
-    uint2 *my = lists + (size_t)warp * K3_R * CAPL;
+    // ---- pass 2: every candidate with pd >= tau (ties included -> superset of the exact top-k).  Lane l tests
+    // candidates j = blk0 + 32 c + l and records hits as bit c of a per-row mask (one predicated OR per test, no
+    // votes); after each block of 1024 candidates the masks are turned into list entries: warp prefix sum of the
+    // popcounts, then every lane appends its own hits.  List order is irrelevant (the list is sorted below).
+    uint16_t *my = lists + (size_t)warp * K3_R * CAPL;
     int cnt[K3_R];
 #pragma unroll
     for (int rr = 0; rr < K3_R; ++rr) cnt[rr] = 0;
-    for (int j0 = 0; j0 < N; j0 += 32) {
-        const int j = j0 + lane;
-        const float4 q = cloud[min(j, N - 1)];
+    for (int blk0 = 0; blk0 < N; blk0 += 1024) {
+        uint32_t hm[K3_R];
+#pragma unroll
+        for (int rr = 0; rr < K3_R; ++rr) hm[rr] = 0u;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (blk0 + c * 32 < N) {                                    // warp-uniform
+                const int j = blk0 + c * 32 + lane;
+                const float4 q = cloud[min(j, N - 1)];
+#pragma unroll
+                for (int rr = 0; rr < K3_R; ++rr)
+                    if (j < N && pd3(xi[rr], q) >= tau[rr]) hm[rr] |= 1u << c;
+            }
+        }
 #pragma unroll
         for (int rr = 0; rr < K3_R; ++rr) {
-            const float pd = pd3(xi[rr], q);
-            const bool pass = (j < N) && (pd >= tau[rr]);
-            const unsigned m = __ballot_sync(MLSP_FULL, pass);
-            if (m) {
-                const int pos = cnt[rr] + __popc(m & ((1u << lane) - 1u));
-                if (pass && pos < CAPL) my[rr * CAPL + pos] = make_uint2(__float_as_uint(pd), (uint32_t)j);
-                cnt[rr] += __popc(m);
+            const int mine = __popc(hm[rr]);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(MLSP_FULL, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int pos = cnt[rr] + incl - mine;
+            cnt[rr] += __shfl_sync(MLSP_FULL, incl, 31);
+            uint32_t m = hm[rr];
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                if (pos < CAPL) my[rr * CAPL + pos] = (uint16_t)(blk0 + c * 32 + lane);
+                ++pos;
             }
         }
     }
     __syncwarp();
 
-    // ---- final: exact sort of the list (or streaming selection if it overflowed)
+    // ---- final: exact sort of the list by (pd desc, index asc), pd recomputed from the staged cloud
+    // (or the streaming selection if the list overflowed)
 #pragma unroll
     for (int rr = 0; rr < K3_R; ++rr) {
         const int i = i0 + rr;
         if (i >= N) break;
         int64_t *out = idx + ((size_t)b * N + i) * k;
-        if (cnt[rr] <= CAPL) {
+        const int n_l = cnt[rr];
+        if (n_l <= CAPL) {
             unsigned long long key[SL];
 #pragma unroll
             for (int s = 0; s < SL; ++s) {
                 const int e = s * 32 + lane;
-                const bool live = e < cnt[rr];
-                const uint2 v = live ? my[rr * CAPL + e] : make_uint2(0u, 0x7fffffffu);
-                key[s] = rank_key(__uint_as_float(v.x), (int)v.y, live);
+                const bool live = e < n_l;
+                const int j = live ? (int)my[rr * CAPL + e] : 0;
+                key[s] = rank_key(pd3(xi[rr], cloud[j]), live ? j : 0x7fffffff, live);
             }
-            warp_sort_u64<SL>(key);
+            if (n_l <= CAPL / 2) {                                       // warp-uniform, the usual case: the upper
+                unsigned long long half[SL / 2];                         // half of the slots is dead, sort the lower
+#pragma unroll
+                for (int s = 0; s < SL / 2; ++s) half[s] = key[s];
+                warp_sort_u64<SL / 2>(half);
+#pragma unroll
+                for (int s = 0; s < SL / 2; ++s) key[s] = half[s];
+            } else {
+                warp_sort_u64<SL>(key);
+            }
 #pragma unroll
             for (int s = 0; s < SL; ++s) {
                 const int e = s * 32 + lane;
                 if (e < k) out[e] = (int64_t)(uint32_t)(key[s] & 0xffffffffull);
             }
         } else {
-            TopK<NC> top;
+            TopK<(SL + 1) / 2> top;
             top.init(k);
             for (int j0 = 0; j0 < N; j0 += 32) {
                 const int j = j0 + lane;
@@ -178,7 +214,7 @@ knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx
             }
             top.finish(k);
 #pragma unroll
-            for (int s = 0; s < NC; ++s) {
+            for (int s = 0; s < (SL + 1) / 2; ++s) {
                 const int e = s * 32 + lane;
                 if (e < k) out[e] = (int64_t)top.j[s];
             }
@@ -190,15 +226,15 @@ bool knn3_supported(int C, int N, int k) { return C == 3 && k <= 64 && N >= 1 &&
 
 int knn3_run(const float *x, int B, int N, int k, int64_t *idx, cudaStream_t st)
 {
-    const int NC = (k <= 32) ? 1 : 2;
-    const size_t smem = sizeof(float4) * (size_t)N + sizeof(uint2) * (size_t)(K3_THREADS / 32) * K3_R * 64 * NC;
+    const int NC = (k <= 32) ? 2 : 4;                                  // 64 / 128 classes
+    const size_t smem = sizeof(float4) * (size_t)N + sizeof(uint16_t) * (size_t)(K3_THREADS / 32) * K3_R * 32 * NC;
     dim3 grid((N + K3_ROWS - 1) / K3_ROWS, B);
-    if (NC == 1) {
-        MLSP_CUDA(cudaFuncSetAttribute(knn3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn3_kernel<1><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx);
-    } else {
+    if (NC == 2) {
         MLSP_CUDA(cudaFuncSetAttribute(knn3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn3_kernel<2><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx);
+    } else {
+        MLSP_CUDA(cudaFuncSetAttribute(knn3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        knn3_kernel<4><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx);
     }
     MLSP_LAUNCH_CHECK("knn3_kernel");
     return MLSP_OK;

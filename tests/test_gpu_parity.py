@@ -65,6 +65,8 @@ def test_knn_golden_continuous(golden, dev, orc, name):
     (32, 3, 1024, 20, False), (32, 3, 1024, 20, True),     # config A
     (16, 3, 2048, 20, False),                               # config S
     (4, 3, 4096, 40, False),                                # config X shape, bounded batch
+    (2, 3, 8192, 64, False), (2, 3, 1500, 33, False),       # largest supported cloud / k, 128-class instance
+    (2, 3, 300, 32, True), (2, 3, 2500, 20, True),          # list-capacity edge (k = 32), three candidate blocks
     (3, 3, 1000, 20, False), (2, 3, 77, 20, True),          # ragged N
     (2, 3, 20, 20, False), (1, 3, 33, 1, False),            # k == N, k == 1
     (8, 64, 1024, 20, False), (4, 128, 1024, 20, False),    # DGCNN feature layers
@@ -113,7 +115,7 @@ def test_edge_gather_golden(golden, dev, name):
 
 
 @pytest.mark.parametrize("B,C,N,k", [(32, 3, 1024, 20), (8, 64, 1024, 20), (4, 128, 1024, 20), (2, 6, 333, 7),
-                                     (2, 20, 500, 40)])
+                                     (2, 20, 500, 40), (3, 3, 333, 7), (2, 3, 333, 8), (2, 3, 1000, 40), (16, 3, 2048, 20)])
 def test_edge_gather_matches_oracle(dev, orc, B, C, N, k):
     x = synth.features(B, C, N, 7)
     idx = torch.randint(0, N, (B, N, k), generator=torch.Generator().manual_seed(1))
@@ -130,7 +132,8 @@ def test_edge_gather_backward_golden(golden, dev):
     np.testing.assert_allclose(_np(x.grad), g["grad_x"], rtol=RTOL, atol=1e-5)
 
 
-@pytest.mark.parametrize("B,C,N,k", [(4, 3, 1024, 20), (4, 64, 1024, 20), (2, 128, 512, 20), (2, 5, 100, 9)])
+@pytest.mark.parametrize("B,C,N,k", [(4, 3, 1024, 20), (4, 64, 1024, 20), (2, 128, 512, 20), (2, 5, 100, 9),
+                                     (3, 3, 333, 7), (2, 3, 1000, 40), (2, 3, 5, 3), (4, 3, 2048, 20)])
 def test_edge_gather_backward_matches_oracle(dev, orc, B, C, N, k):
     x = synth.features(B, C, N, 9).to(dev).requires_grad_(True)
     idx = M.knn(x.detach(), k)
