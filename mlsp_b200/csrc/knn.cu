@@ -19,7 +19,7 @@ constexpr int KNN_TJ = 128;                               // candidates per tile
 constexpr size_t KNN_WS_HEADER = 256;                     // stats live in the first bytes of the workspace
 
 bool knn_tensor_supported(int B, int C, int N, int k);
-size_t knn_tensor_workspace_bytes(int B, int C, int N);
+size_t knn_tensor_workspace_bytes(int B, int C, int N, int k);
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, cudaStream_t st);
 bool knn3_supported(int C, int N, int k);
 int knn3_run(const float *x, int B, int N, int k, int64_t *idx, cudaStream_t st);
@@ -27,7 +27,7 @@ int knn3_run(const float *x, int B, int N, int k, int64_t *idx, cudaStream_t st)
 size_t knn_workspace_bytes(int B, int C, int N, int k)
 {
     const size_t exact = KNN_WS_HEADER + align_up(sizeof(float) * (size_t)B * N, 256);
-    if (knn_tensor_supported(B, C, N, k)) return exact > knn_tensor_workspace_bytes(B, C, N) ? exact : knn_tensor_workspace_bytes(B, C, N);
+    if (knn_tensor_supported(B, C, N, k)) return exact > knn_tensor_workspace_bytes(B, C, N, k) ? exact : knn_tensor_workspace_bytes(B, C, N, k);
     return exact;
 }
 

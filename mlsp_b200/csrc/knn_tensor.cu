@@ -4,19 +4,25 @@
 //
 // Filter (tensor cores) + refine (exact fp32) + certificate:
 //   1. prep: x (B,C,N) fp32 -> point-major fp32 rows xt (B,N,C) and an error-compensated bf16 split
-//      x = hi + lo (+ 2^-16 |x|).  With A' = [hi|hi|lo], B' = [hi|lo|hi] (K' = 3C) one UMMA chain gives
-//      dot~ = hi.hi + hi.lo + lo.hi, |dot~ - dot| <= ~1e-4 |x_i||x_j|.
+//      x = hi + lo (+ 2^-16 |x|).  The A operand [hi|lo] of the CTA's 128 query rows stays in shared memory; every
+//      candidate block B_hi is multiplied with A_hi and A_lo, every B_lo block with A_hi, all into one TMEM
+//      accumulator: dot~ = hi.hi + lo.hi + hi.lo, |dot~ - dot| <= ~1e-4 |x_i||x_j|, and each B byte is fetched once.
 //   2. main kernel, one CTA per 128 query rows, candidate tiles of 128 (UMMA 128x128x16, kind::f16):
-//        warp 0   : TMA producer (A' tile once, B' K-blocks through a 4-stage mbarrier ring)
+//        warp 0   : TMA producer (A tile once, B K-blocks through an mbarrier ring)
 //        warp 1   : TMEM allocator + single-thread MMA issuer, accumulators double-buffered in TMEM
-//        warps 2-5: epilogue, one thread per query row (tcgen05.ld 32x32b: TMEM lane == row)
+//        warps 2-9: epilogue, two threads per query row (tcgen05.ld 32x32b: TMEM lane == row)
 //      pass 1: v = |x_j|^2 - 2 dot~ ; per row the minimum of every column class (j mod NG) is tracked in
 //              registers; tau = k-th smallest class minimum is an upper bound of the k-th distance.
-//      pass 2: the same tiles again (the MMA is cheap); columns with v <= tau + 2 eps are appended to the
-//              row's candidate list in shared memory (about 1.5 k entries expected, capacity 2 NG).
-//      eps bounds |v - exact| so every member of the exact top-k (ties included) is in the list.
-//   3. refine kernel (high occupancy, one warp per row): recomputes the candidates' distances with the exact
-//      fp32 chain of the specification and sorts them (value desc, index asc); the first k are the answer.
+//      pass 2: the same tiles again (the MMA is cheap); columns with v <= tau + 2 eps are written as (v, j) pairs
+//              to the row's candidate list in global memory (L2): the two threads of a row fill it from both ends
+//              with private cursors -- predicated stores, no atomics, no votes (about 1.2 k entries expected,
+//              capacity 2 NG).  eps bounds |v - exact| so every member of the exact top-k (ties included) is listed.
+//   3. refine kernel (one warp per row): sorts the list by the approximate value.  Two neighbours of that order
+//      whose values differ by more than 2 eps are provably in the same order in exact fp32 arithmetic, so only
+//      runs of near-ties ("clusters") that start inside the first k positions need the exact value: for those the
+//      distance is recomputed with the pinned fp32 chain of the specification (four lanes per candidate, coalesced
+//      reads of the point-major rows) and the cluster is re-sorted by (value desc, index asc).  Typical rows need
+//      no or a few exact distances instead of one 4C-byte gather per candidate.
 //      A row whose list overflowed is not certified and goes to
 //   4. a fallback kernel (exact streaming top-k, one warp per listed row).
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA) -- profiles/.
@@ -251,30 +257,35 @@ __device__ __forceinline__ void reg_sort(float (&v)[NG])
     }
 }
 
+// per-pair error bound of the filter value: |v~_ij - exact_ij| <= KT_EPS_REL |x_i||x_j| + 2^-21 (|x_i|^2 + |x_j|^2)
+// (Cauchy-Schwarz on the dropped split terms and the accumulation, plus the specification's own roundings)
+__device__ __forceinline__ float pair_eps(float ni, float xxi, float xxj)
+{
+    return __fmaf_rn(KT_EPS_REL * ni, sqrtf(xxj), 4.76837158203125e-7f * (xxi + xxj));
+}
+
 // ---- epilogue pieces ---------------------------------------------------------------------------------
-template <int NG>
-struct EpiState {
-    float gmin[NG];          // pass 1: minimum of v over the columns of class (j mod NG) seen by this thread
-    uint16_t *list;          // pass 2: the row's candidate list (shared by the row's two threads)
-    int *cnt;
-    __device__ __forceinline__ void init(uint16_t *l, int *c)
-    {
-#pragma unroll
-        for (int e = 0; e < NG; ++e) gmin[e] = INFINITY;
-        list = l;
-        cnt = c;
-    }
+// pass-2 cursor of one thread: its end of the row's global candidate list
+struct Cursor {
+    uint2 *base;             // the thread's end of the row's list
+    int step;                // +1 (columns 0..63 of every tile: from the front) or -1 (columns 64..127: from the back)
+    int off;                 // step * (entries written so far)
+    bool ovf;
 };
 
 // one 16-column piece of one query row: v = |x_j|^2 - 2 dot~
 //   PASS 1: class minima (class = column within the thread's 64-column half, mod NG)
-//   PASS 2: columns with v <= thr are collected as a bit mask, then appended to the row's list (rare)
+//   PASS 2: every column with v <= thr is stored as (v, j) at the cursor -- predicated, branch-free
 template <int NG, int PASS>
-__device__ __forceinline__ void epi_piece(EpiState<NG> &st, const uint32_t (&u)[16], const float4 *nrm4, int ch,
-                                          float thr, int jbase)
+__device__ __forceinline__ void epi_piece(float (&gmin)[NG], Cursor &cur, const uint32_t (&u)[16], const float4 *nrm4,
+                                          int ch, float thr, uint32_t jcol)
 {
-    constexpr int CAP = 2 * NG;
-    uint32_t hits = 0;
+    if (PASS == 2) {
+        // a piece can add 16 entries: without room for them nothing is stored any more and the row is flagged
+        const bool room = abs(cur.off) <= 2 * NG - 16;
+        cur.ovf |= !room;
+        thr = room ? thr : -INFINITY;
+    }
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) {
         const float4 nj = nrm4[ch * 4 + c4];
@@ -285,18 +296,18 @@ __device__ __forceinline__ void epi_piece(EpiState<NG> &st, const uint32_t (&u)[
             const float v = __fmaf_rn(-2.0f, __uint_as_float(u[c]), nv[w]);
             if (PASS == 1) {
                 const int e = (ch * 16 + c) % NG;
-                st.gmin[e] = fminf(st.gmin[e], v);
+                gmin[e] = fminf(gmin[e], v);
             } else {
-                hits |= (v <= thr) ? (1u << c) : 0u;
+                // if (v <= thr) { list[off] = (v, j); off += step; }: one predicated store + one predicated add, no branch
+                uint2 *a = cur.base + cur.off;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.le.f32 p, %1, %2;\n\t"
+                    "@p st.global.v2.b32 [%3], {%4, %5};\n\t"
+                    "@p add.s32 %0, %0, %6;\n\t}"
+                    : "+r"(cur.off)
+                    : "f"(v), "f"(thr), "l"(a), "r"(__float_as_uint(v)), "r"(jcol + (uint32_t)c), "r"(cur.step));
             }
-        }
-    }
-    if (PASS == 2) {
-        while (hits) {                                              // about 1.2 k / N of the columns
-            const int c = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const int pos = atomicAdd(st.cnt, 1);                   // the row's list is shared by its two threads
-            if (pos < CAP) st.list[pos] = (uint16_t)(jbase + ch * 16 + c);
         }
     }
 }
@@ -304,22 +315,23 @@ __device__ __forceinline__ void epi_piece(EpiState<NG> &st, const uint32_t (&u)[
 // one thread, one query row, 64 columns in four pieces (tcgen05.ld 32x32b.x16), the load of piece p+1 in flight
 // while piece p is processed
 template <int NG, int PASS>
-__device__ __forceinline__ void epi_tile(EpiState<NG> &st, uint32_t taddr, const float *nrm, float thr, int jbase)
+__device__ __forceinline__ void epi_tile(float (&gmin)[NG], Cursor &cur, uint32_t taddr, const float *nrm, float thr,
+                                         uint32_t jbase)
 {
     const float4 *nrm4 = reinterpret_cast<const float4 *>(nrm);
     uint32_t ua[16], ub[16];
     tc_ld16_issue(taddr, ua);
     tc_wait16(ua);
     tc_ld16_issue(taddr + 16, ub);
-    epi_piece<NG, PASS>(st, ua, nrm4, 0, thr, jbase);
+    epi_piece<NG, PASS>(gmin, cur, ua, nrm4, 0, thr, jbase);
     tc_wait16(ub);
     tc_ld16_issue(taddr + 32, ua);
-    epi_piece<NG, PASS>(st, ub, nrm4, 1, thr, jbase);
+    epi_piece<NG, PASS>(gmin, cur, ub, nrm4, 1, thr, jbase + 16);
     tc_wait16(ua);
     tc_ld16_issue(taddr + 48, ub);
-    epi_piece<NG, PASS>(st, ua, nrm4, 2, thr, jbase);
+    epi_piece<NG, PASS>(gmin, cur, ua, nrm4, 2, thr, jbase + 32);
     tc_wait16(ub);
-    epi_piece<NG, PASS>(st, ub, nrm4, 3, thr, jbase);
+    epi_piece<NG, PASS>(gmin, cur, ub, nrm4, 3, thr, jbase + 48);
 }
 
 // test hook: write the approximate values of this thread's 64 columns
@@ -345,32 +357,40 @@ struct KtParams {
     int *fb_count;           // fallback row counter
     int *fb_rows;            // fallback rows (b*N + i)
     int *stats;              // [0] rows certified by the tensor path
-    uint16_t *cand;          // (B*N, CAP) candidate lists handed from the main kernel to the refine kernel
-    int *cand_cnt;           // (B*N) list lengths (> CAP: overflowed)
+    uint2 *cand;             // (B*N, CAP) candidate lists (v bits, j): main kernel -> refine kernel
+    int *cand_cnt;           // (B*N, 2) entries written from the front / from the back (> CAP: overflowed)
     float *dump;             // optional (B,N,N) approximate values (tests only)
     int N, C, k, T;          // T = candidate tiles per cloud
-    int stages;              // depth of the B-operand smem ring (2: two CTAs per SM at C = 64, 4 at C = 128)
+    int stages;              // depth of the B-operand smem ring
+    int mode;                // tuning hook (MLSP_KT_MODE): bit 0 skips the pass-1 math, bit 1 the pass-2 math
 };
 
 // ------------------------------------------------------------------------------------------- main kernel
+// shared memory: A (2*SEG blocks) | B ring (STAGES blocks) | xchg [min(k,NG)][128] | nrm [2][128] | thr [128] | barriers
+__host__ __device__ inline size_t kt_smem_bytes(int C, int k, int NG, int stages)
+{
+    const int kx = k < NG ? k : NG;
+    return (size_t)(2 * C / KT_KBLK + stages) * KT_BLK_BYTES + (size_t)kx * KT_ROWS * 4 + 2 * KT_COLS * 4 + KT_ROWS * 4 +
+           32 * 8 + 16 + 1024;
+}
+
 template <int NG>
-__global__ void __launch_bounds__(KT_THREADS, (NG == 32) ? 2 : 1)   // NG = 32: two CTAs per SM (C = 64) need <= 102 registers
+__global__ void __launch_bounds__(KT_THREADS, (NG == 32) ? 2 : 1)   // NG = 32: two CTAs per SM (one wave at 32 x 1024), <= 102 registers
 knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, KtParams P)
 {
     constexpr int CAP = 2 * NG;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms need 1 KiB alignment
-    const int KB = 3 * P.C / KT_KBLK;       // K blocks per tile (3 or 6)
-    const int SEG = P.C / KT_KBLK;          // K blocks per hi / lo segment
+    const int SEG = P.C / KT_KBLK;          // K blocks per hi / lo segment (1 or 2)
+    const int KB = 2 * SEG;                 // B blocks streamed per tile: hi blocks, then lo blocks
     const int STAGES = P.stages;
-    uint8_t *sA = smem_raw;                                   // KB blocks, resident
+    const int KX = min(P.k, NG);
+    uint8_t *sA = smem_raw;                                   // [hi blocks | lo blocks], resident
     uint8_t *sB = sA + (size_t)KB * KT_BLK_BYTES;             // STAGES blocks, ring
-    uint16_t *lists = reinterpret_cast<uint16_t *>(sB + (size_t)STAGES * KT_BLK_BYTES);      // [128][CAP]
-    float *xchg = reinterpret_cast<float *>(lists);            // [128][NG] class minima of the upper half (aliases lists)
-    float *nrm_s = reinterpret_cast<float *>(lists + KT_ROWS * CAP);                            // [2][128]
-    float *thr_s = nrm_s + 2 * KT_COLS;                                                         // [128]
-    int *cnt_s = reinterpret_cast<int *>(thr_s + KT_ROWS);                                      // [128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(cnt_s + KT_ROWS);
+    float *xchg = reinterpret_cast<float *>(sB + (size_t)STAGES * KT_BLK_BYTES);   // [KX][128] sorted class minima of the upper half
+    float *nrm_s = xchg + (size_t)KX * KT_ROWS;                                     // [2][128]
+    float *thr_s = nrm_s + 2 * KT_COLS;                                             // [128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(thr_s + KT_ROWS);
     uint64_t *full = bars, *empty = bars + KT_MAX_STAGES, *a_full = bars + 2 * KT_MAX_STAGES;
     uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
@@ -392,7 +412,6 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < KT_ROWS) cnt_s[threadIdx.x] = 0;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -406,19 +425,17 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         // ================================ TMA producer ================================
         if (lane == 0) {
             mbar_expect_tx(a_full, (uint32_t)KB * KT_BLK_BYTES);
-            for (int kb = 0; kb < KB; ++kb) {        // A' = [hi | hi | lo]
-                const int seg = kb / SEG, within = kb - seg * SEG;
-                tma_load_2d(sA + (size_t)kb * KT_BLK_BYTES, seg == 2 ? &map_lo : &map_hi, within * KT_KBLK, rowbase + i0, a_full);
-            }
+            for (int kb = 0; kb < KB; ++kb)          // A = [hi | lo]
+                tma_load_2d(sA + (size_t)kb * KT_BLK_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
+                            rowbase + i0, a_full);
             int stage = 0;
             uint32_t ph = 0;
             for (int g = 0; g < 2 * T; ++g) {
                 const int j0 = (g % T) * KT_COLS;
-                for (int kb = 0; kb < KB; ++kb) {   // B' = [hi | lo | hi]
+                for (int kb = 0; kb < KB; ++kb) {   // B blocks: hi ..., lo ...
                     mbar_wait(empty + stage, ph ^ 1);
                     mbar_expect_tx(full + stage, KT_BLK_BYTES);
-                    const int seg = kb / SEG, within = kb - seg * SEG;
-                    tma_load_2d(sB + (size_t)stage * KT_BLK_BYTES, seg == 1 ? &map_lo : &map_hi, within * KT_KBLK,
+                    tma_load_2d(sB + (size_t)stage * KT_BLK_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
                                 rowbase + j0, full + stage);
                     if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
@@ -439,11 +456,18 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(full + stage, ph);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(smem_u32(sA + (size_t)kb * KT_BLK_BYTES));
                     const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * KT_BLK_BYTES));
+                    const int ka = kb % SEG;                        // matching K block of A
+                    const uint64_t da_hi = umma_desc_sw128(smem_u32(sA + (size_t)ka * KT_BLK_BYTES));
 #pragma unroll
                     for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)   // +32 bytes per K=16 step inside the swizzle span
-                        tc_mma_bf16(d, da + 2 * k16, db + 2 * k16, KT_IDESC, (kb | k16) != 0);
+                        tc_mma_bf16(d, da_hi + 2 * k16, db + 2 * k16, KT_IDESC, (kb | k16) != 0);   // hi.hi | hi.lo
+                    if (kb < SEG) {                                 // a B_hi block also meets A_lo:  lo.hi
+                        const uint64_t da_lo = umma_desc_sw128(smem_u32(sA + (size_t)(SEG + ka) * KT_BLK_BYTES));
+#pragma unroll
+                        for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)
+                            tc_mma_bf16(d, da_lo + 2 * k16, db + 2 * k16, KT_IDESC, 1u);
+                    }
                     tc_commit(empty + stage);                       // smem stage reusable when these MMAs retire
                     if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
@@ -460,10 +484,19 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int i = i0 + r;
         const int et = threadIdx.x - 64;         // 0..255 among the epilogue threads
         const float xxi = (i < N) ? P.xx[(size_t)rowbase + i] : 0.0f;
-        const float eps = KT_EPS_REL * sqrtf(xxi) * sqrtf(P.maxxx[b]);
+        const float eps = pair_eps(sqrtf(xxi), xxi, P.maxxx[b]);   // bound for every candidate of the cloud
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 64;
-        EpiState<NG> st;
-        st.init(lists + r * CAP, &cnt_s[r]);
+        float gmin[NG];
+#pragma unroll
+        for (int e = 0; e < NG; ++e) gmin[e] = INFINITY;
+        Cursor cur;
+        {
+            uint2 *row_list = P.cand + ((size_t)rowbase + min(i, N - 1)) * CAP;
+            cur.step = h ? -1 : 1;
+            cur.base = h ? row_list + (CAP - 1) : row_list;
+            cur.off = 0;
+            cur.ovf = false;
+        }
         const float *xxb = P.xx + rowbase;
         // norms of tile 0; afterwards the norms of tile g+1 are fetched while tile g is processed
         if (et < KT_COLS) nrm_s[et] = (et < N) ? xxb[et] : INFINITY;
@@ -477,7 +510,7 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             epi_bar_sync();                                     // norms of tile g visible
             mbar_wait(tm_full + buf, (g >> 1) & 1);
             tc_fence_after();
-            epi_tile<NG, 1>(st, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, 0.0f, 0);
+            if (!(P.mode & 1)) epi_tile<NG, 1>(gmin, cur, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, 0.0f, 0u);
             if (P.dump) dump_tile(P.dump + ((size_t)rowbase + min(i, N - 1)) * N, i < N, tlane + (uint32_t)buf * KT_COLS,
                                   nrm_s + buf * KT_COLS + h * 64, g * KT_COLS + h * 64, N);
             tc_fence_before();
@@ -487,21 +520,22 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         }
         // ---- between the passes: the row has 2 NG class minima (NG per thread).  Each thread sorts its own;
         // the k-th smallest of the union of two sorted lists A, B is max_{i<k} min(A[i], B[k-1-i]).
-        reg_sort<NG>(st.gmin);
+        reg_sort<NG>(gmin);
         if (h == 1) {
 #pragma unroll
-            for (int e = 0; e < NG; ++e) xchg[e * KT_ROWS + r] = st.gmin[e];
+            for (int e = 0; e < NG; ++e)
+                if (e < KX) xchg[e * KT_ROWS + r] = gmin[e];
         }
         epi_bar_sync();
         if (h == 0) {
             float tau = -INFINITY;
 #pragma unroll
             for (int e = 0; e < NG; ++e)
-                if (e < P.k) tau = fmaxf(tau, fminf(st.gmin[e], xchg[(P.k - 1 - e) * KT_ROWS + r]));
+                if (e < P.k) tau = fmaxf(tau, fminf(gmin[e], xchg[(P.k - 1 - e) * KT_ROWS + r]));
             thr_s[r] = tau + 2.0f * eps;
         }
-        epi_bar_sync();                          // xchg (aliasing the lists) is dead from here on
-        const float thr = thr_s[r];
+        epi_bar_sync();
+        const float thr = (i < N) ? thr_s[r] : -INFINITY;    // rows beyond the cloud collect nothing
         // ---- pass 2: collect the candidates
         for (int g = T; g < 2 * T; ++g) {
             const int buf = g & 1;
@@ -511,12 +545,15 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             epi_bar_sync();
             mbar_wait(tm_full + buf, (g >> 1) & 1);
             tc_fence_after();
-            epi_tile<NG, 2>(st, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, thr,
-                            (g - T) * KT_COLS + h * 64);
+            if (!(P.mode & 2)) epi_tile<NG, 2>(gmin, cur, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, thr,
+                            (uint32_t)((g - T) * KT_COLS + h * 64));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + buf);
             if (et < KT_COLS) nrm_s[(buf ^ 1) * KT_COLS + et] = nxt;
+        }
+        if (i < N) {
+            P.cand_cnt[2 * ((size_t)rowbase + i) + h] = cur.ovf ? CAP + 1 : abs(cur.off);
         }
     }
     tc_fence_before();
@@ -525,28 +562,132 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
     }
-
-    // ---- hand the candidate lists to the refine kernel (coalesced copies, counts alongside)
-    {
-        const int rows_here = min(KT_ROWS, N - i0);
-        uint16_t *gl = P.cand + ((size_t)rowbase + i0) * CAP;
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(lists);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(gl);
-        for (int e = threadIdx.x; e < rows_here * CAP / 2; e += KT_THREADS) dst[e] = src[e];
-        for (int r = threadIdx.x; r < rows_here; r += KT_THREADS) P.cand_cnt[(size_t)rowbase + i0 + r] = cnt_s[r];
-    }
 }
 
 // ------------------------------------------------------------------------------------------- refine
-// Exact fp32 re-rank of the candidate lists.  One warp per query row, FOUR lanes per candidate, eight candidates
-// per pass: lane u of a group owns chains t = u and t = u + 4 of the pinned dot product (float4 pieces
-// f = u, u+4, u+8, ... of the point-major rows), so a warp-wide load touches 8 candidates x 64 contiguous bytes
-// and the query row's pieces live in registers.  p_u + p_{u+4} is a register add, two xor-shuffles finish the
-// tree of oracle dot_tree: ((p0+p4)+(p2+p6)) + ((p1+p5)+(p3+p7)), and all four lanes hold the exact value.
-// Lane 4g+u keeps the candidate its group computed in pass u; the warp then sorts (value desc, index asc) --
-// one key per lane when the list has <= 32 entries, the usual case -- and writes the first k.  Rows whose list
-// overflowed (or is shorter than k) go to the fallback list.
+// One warp per query row.  S slots of 32 lanes hold the row's candidates sorted by (v~ asc, j asc).
+//   link[e]    : v~[e] - v~[e-1] <= 2 eps  (the exact order of e-1 and e is not certified)
+//   cluster    : maximal run of linked positions; cs[e] = its first position
+//   amb[e]     : e belongs to a cluster of >= 2 members that starts inside the first k positions
+// Clusters are ordered among themselves by certificate, so only amb entries need the exact fp32 distance:
+// FOUR lanes per candidate, eight sorted positions per pass (passes without an amb entry are skipped): lane u
+// of a group owns chains t = u and t = u + 4 of the pinned dot product (float4 pieces f = u, u+4, u+8, ... of the
+// point-major rows), so a warp-wide load touches 8 candidates x 64 contiguous bytes; p_u + p_{u+4} is a register
+// add, two xor-shuffles finish the tree of oracle dot_tree: ((p0+p4)+(p2+p6)) + ((p1+p5)+(p3+p7)).  A second
+// sort on (cluster start, exact value desc, index asc) then gives the specification's order.
 constexpr int RF_WARPS = 8;
+
+template <int S, int C>
+__device__ __forceinline__ void refine_sorted(const KtParams &P, long long row, unsigned long long (&key)[S],
+                                              uint16_t *sj, float *se)
+{
+    constexpr int M = C / 16;                             // float4 pieces per lane: 4 (C = 64) or 8 (C = 128)
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> 2, u = lane & 3;
+    const int k = P.k;
+    const long long base = (row / P.N) * P.N;
+    const float xxi = P.xx[row];
+    const float ni = sqrtf(xxi);
+    warp_sort_u64<S>(key);
+    // ---- links, clusters
+    float v[S], ej[S];
+    bool link[S];
+    int cs[S];
+    int carry = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const bool live = key[s] != ~0ull;
+        const uint32_t ob = (uint32_t)(key[s] >> 32);                    // f32_orderable(v~)
+        v[s] = live ? __uint_as_float((ob & 0x80000000u) ? (ob ^ 0x80000000u) : ~ob) : INFINITY;
+        ej[s] = live ? pair_eps(ni, xxi, P.xx[base + ((uint32_t)key[s] & 0xffffu)]) : 0.0f;
+        float prev = __shfl_up_sync(MLSP_FULL, v[s], 1), eprev = __shfl_up_sync(MLSP_FULL, ej[s], 1);
+        if (s > 0) {
+            const float last = __shfl_sync(MLSP_FULL, v[s - 1], 31), elast = __shfl_sync(MLSP_FULL, ej[s - 1], 31);
+            if (lane == 0) { prev = last; eprev = elast; }
+        }
+        // order of (e-1, e) not certified: the gap does not exceed the two error bounds (inf - x, inf - inf: false)
+        link[s] = (s > 0 || lane > 0) && (v[s] - prev <= 1.0009765625f * (ej[s] + eprev));
+        int m = link[s] ? 0 : s * 32 + lane;                             // inclusive max-scan = cluster start
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(MLSP_FULL, m, o);
+            if (lane >= o) m = max(m, t);
+        }
+        cs[s] = max(m, carry);
+        carry = __shfl_sync(MLSP_FULL, cs[s], 31);
+    }
+    bool amb[S];
+    unsigned need[S];
+    int total = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        bool nxt = __shfl_down_sync(MLSP_FULL, link[s], 1);
+        if (s + 1 < S) {
+            const bool first = __shfl_sync(MLSP_FULL, link[s + 1], 0);
+            if (lane == 31) nxt = first;
+        } else if (lane == 31) {
+            nxt = false;
+        }
+        amb[s] = (link[s] || nxt) && cs[s] < k;
+        need[s] = __ballot_sync(MLSP_FULL, amb[s]);
+        total += __popc(need[s]);
+    }
+    if (total) {                                                         // warp-uniform
+        // compact the amb entries: rank -> candidate index in shared memory, eight per pass, results back by rank
+        int rank[S], off = 0;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            rank[s] = off + __popc(need[s] & ((1u << lane) - 1u));
+            if (amb[s]) sj[rank[s]] = (uint16_t)((uint32_t)key[s] & 0xffffu);
+            off += __popc(need[s]);
+        }
+        __syncwarp();
+        const float4 *xig = reinterpret_cast<const float4 *>(P.xt + (size_t)row * C);
+        float4 xr[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) xr[m] = xig[4 * m + u];
+        for (int t0 = 0; t0 < total; t0 += 8) {
+            const int t = min(t0 + g, total - 1);
+            const int j = (int)sj[t];
+            const float4 *xj = reinterpret_cast<const float4 *>(P.xt + ((size_t)base + j) * C);
+            float4 q[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) q[m] = __ldg(xj + 4 * m + u);
+            const float xxj = P.xx[base + j];
+            float pa = 0.0f, pb = 0.0f;                // chains t = u and t = u + 4
+#pragma unroll
+            for (int m = 0; m < M; m += 2) {
+                pa = __fmaf_rn(xr[m].x, q[m].x, pa);
+                pa = __fmaf_rn(xr[m].y, q[m].y, pa);
+                pa = __fmaf_rn(xr[m].z, q[m].z, pa);
+                pa = __fmaf_rn(xr[m].w, q[m].w, pa);
+                pb = __fmaf_rn(xr[m + 1].x, q[m + 1].x, pb);
+                pb = __fmaf_rn(xr[m + 1].y, q[m + 1].y, pb);
+                pb = __fmaf_rn(xr[m + 1].z, q[m + 1].z, pb);
+                pb = __fmaf_rn(xr[m + 1].w, q[m + 1].w, pb);
+            }
+            float acc = __fadd_rn(pa, pb);                                        // q_u = p_u + p_{u+4}
+            acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 2));             // q0+q2 | q1+q3
+            acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 1));             // (q0+q2) + (q1+q3)
+            if (u == 0 && t0 + g < total) se[t] = __fsub_rn(__fmaf_rn(2.0f, acc, -xxj), xxi);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            // (cluster start | exact value, best first | index); entries outside amb clusters keep their position
+            const uint32_t j = (uint32_t)key[s] & 0xffffu;
+            const uint32_t sub = amb[s] ? ~f32_orderable(__fadd_rn(se[rank[s]], 0.0f)) : 0u;
+            key[s] = (key[s] == ~0ull) ? ~0ull : ((unsigned long long)cs[s] << 48) | ((unsigned long long)sub << 16) | j;
+        }
+        warp_sort_u64<S>(key);
+        __syncwarp();
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const int e = s * 32 + lane;
+        if (e < k) P.idx[(size_t)row * k + e] = (int64_t)((uint32_t)key[s] & 0xffffu);
+    }
+}
 
 template <int NG, int C>
 __global__ void __launch_bounds__(32 * RF_WARPS)
@@ -554,71 +695,38 @@ knn_refine_kernel(KtParams P, long long total_rows)
 {
     constexpr int CAP = 2 * NG;
     constexpr int SLOTS = CAP / 32;
-    constexpr int M = C / 16;                             // float4 pieces per lane: 4 (C = 64) or 8 (C = 128)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, u = lane & 3;
     const long long row = (long long)blockIdx.x * RF_WARPS + warp;   // b*N + i
     if (row >= total_rows) return;
-    const int cnt = P.cand_cnt[row];
-    if (cnt > CAP || cnt < P.k) {
+    const int c0 = P.cand_cnt[2 * row], c1 = P.cand_cnt[2 * row + 1];
+    const int cnt = c0 + c1;
+    if (c0 > CAP || c1 > CAP || cnt > CAP || cnt < P.k) {
         if (lane == 0) P.fb_rows[atomicAdd(P.fb_count, 1)] = (int)row;
         return;
     }
-    const long long base = (row / P.N) * P.N;
-    const float4 *xig = reinterpret_cast<const float4 *>(P.xt + (size_t)row * C);
-    float4 xr[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) xr[m] = xig[4 * m + u];
-    const float xxi = P.xx[row];
-    const uint16_t *list = P.cand + (size_t)row * CAP;
-
+    __shared__ uint16_t sj_all[RF_WARPS][CAP];
+    __shared__ float se_all[RF_WARPS][CAP];
+    uint16_t *sj = sj_all[warp];
+    float *se = se_all[warp];
+    const uint2 *list = P.cand + (size_t)row * CAP;
     unsigned long long key[SLOTS];
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-        key[s] = rank_key(-INFINITY, 0x7fffffff, false);
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-            const int e0 = s * 32 + ps * 8;
-            if (e0 < cnt) {                                // warp-uniform
-                const int e = e0 + g;
-                const bool live = e < cnt;
-                const int j = live ? (int)list[e] : 0;
-                const float4 *xj = reinterpret_cast<const float4 *>(P.xt + ((size_t)base + j) * C);
-                float4 q[M];
-#pragma unroll
-                for (int m = 0; m < M; ++m) q[m] = __ldg(xj + 4 * m + u);
-                const float xxj = P.xx[base + j];
-                float pa = 0.0f, pb = 0.0f;                // chains t = u and t = u + 4
-#pragma unroll
-                for (int m = 0; m < M; m += 2) {
-                    pa = __fmaf_rn(xr[m].x, q[m].x, pa);
-                    pa = __fmaf_rn(xr[m].y, q[m].y, pa);
-                    pa = __fmaf_rn(xr[m].z, q[m].z, pa);
-                    pa = __fmaf_rn(xr[m].w, q[m].w, pa);
-                    pb = __fmaf_rn(xr[m + 1].x, q[m + 1].x, pb);
-                    pb = __fmaf_rn(xr[m + 1].y, q[m + 1].y, pb);
-                    pb = __fmaf_rn(xr[m + 1].z, q[m + 1].z, pb);
-                    pb = __fmaf_rn(xr[m + 1].w, q[m + 1].w, pb);
-                }
-                float acc = __fadd_rn(pa, pb);                                        // q_u = p_u + p_{u+4}
-                acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 2));             // q0+q2 | q1+q3
-                acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 1));             // (q0+q2) + (q1+q3)
-                const float pd = __fsub_rn(__fmaf_rn(2.0f, acc, -xxj), xxi);
-                if (ps == u) key[s] = rank_key(pd, live ? j : 0x7fffffff, live);
-            }
+        const int e = s * 32 + lane;
+        key[s] = ~0ull;
+        if (e < cnt) {
+            const uint2 ent = list[e < c0 ? e : CAP - 1 - (e - c0)];
+            key[s] = ((unsigned long long)f32_orderable(__fadd_rn(__uint_as_float(ent.x), 0.0f)) << 32) | ent.y;
         }
     }
-    if (SLOTS == 1 || cnt <= 32) {                         // warp-uniform: one key per lane
+    if (cnt <= 32) {                                       // warp-uniform, the usual case for k <= 20
         unsigned long long k1[1] = {key[0]};
-        warp_sort_u64<1>(k1);
-        if (lane < P.k) P.idx[(size_t)row * P.k + lane] = (int64_t)(uint32_t)(k1[0] & 0xffffffffull);
+        refine_sorted<1, C>(P, row, k1, sj, se);
+    } else if (SLOTS > 2 && cnt <= 64) {
+        unsigned long long k2[2] = {key[0], key[1]};
+        refine_sorted<2, C>(P, row, k2, sj, se);
     } else {
-        warp_sort_u64<SLOTS>(key);
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int e = s * 32 + lane;
-            if (e < P.k) P.idx[(size_t)row * P.k + e] = (int64_t)(uint32_t)(key[s] & 0xffffffffull);
-        }
+        refine_sorted<SLOTS, C>(P, row, key, sj, se);
     }
     if (lane == 0) atomicAdd(P.stats, 1);
 }
@@ -694,8 +802,9 @@ struct KtLayout {
     size_t off_counters, off_max, off_xx, off_hi, off_lo, off_xt, off_rows, off_cand, off_cnt, total;
 };
 
-static KtLayout kt_layout(int B, int C, int N)
+static KtLayout kt_layout(int B, int C, int N, int k)
 {
+    const int CAP = (k <= 32) ? 64 : 128;
     KtLayout L;
     size_t o = 0;
     L.off_counters = o; o += 256;                                            // [0] fb_count, [1] certified rows
@@ -705,8 +814,8 @@ static KtLayout kt_layout(int B, int C, int N)
     L.off_lo = o;       o += align_up(2 * (size_t)B * N * C, 1024);
     L.off_xt = o;       o += align_up(sizeof(float) * (size_t)B * N * C, 256);
     L.off_rows = o;     o += align_up(sizeof(int) * (size_t)B * N, 256);
-    L.off_cand = o;     o += align_up(2 * (size_t)B * N * 128, 256);                 // CAP <= 128
-    L.off_cnt = o;      o += align_up(sizeof(int) * (size_t)B * N, 256);
+    L.off_cand = o;     o += align_up(sizeof(uint2) * (size_t)B * N * CAP, 256);
+    L.off_cnt = o;      o += align_up(2 * sizeof(int) * (size_t)B * N, 256);
     L.total = o;
     return L;
 }
@@ -716,11 +825,11 @@ bool knn_tensor_supported(int B, int C, int N, int k)
     return (C == 64 || C == 128) && N >= 256 && N <= 65535 && k <= 64 && (long long)B * N < (1ll << 31) && B <= 65535;
 }
 
-size_t knn_tensor_workspace_bytes(int B, int C, int N) { return kt_layout(B, C, N).total; }
+size_t knn_tensor_workspace_bytes(int B, int C, int N, int k) { return kt_layout(B, C, N, k).total; }
 
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, cudaStream_t st)
 {
-    const KtLayout L = kt_layout(B, C, N);
+    const KtLayout L = kt_layout(B, C, N, k);
     char *w = static_cast<char *>(ws);
     int *counters = reinterpret_cast<int *>(w + L.off_counters);
     float *maxxx = reinterpret_cast<float *>(w + L.off_max);
@@ -744,13 +853,25 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     KtParams P;
     P.xx = xx; P.maxxx = maxxx; P.xt = xt; P.idx = idx; P.fb_count = counters; P.fb_rows = rows;
     P.stats = counters + 1; P.dump = dump;
-    P.cand = reinterpret_cast<uint16_t *>(w + L.off_cand); P.cand_cnt = reinterpret_cast<int *>(w + L.off_cnt); P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS;
+    P.cand = reinterpret_cast<uint2 *>(w + L.off_cand); P.cand_cnt = reinterpret_cast<int *>(w + L.off_cnt); P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS;
     const int NG = (k <= 32) ? 32 : 64;
-    const int KB = 3 * C / KT_KBLK;
-    P.stages = (C == 64) ? 2 : 4;          // C = 64: 48 K (A') + 32 K (ring) + lists -> two CTAs per SM
+    // ring depth: as deep as two CTAs per SM allow (NG = 32), else one CTA per SM with up to 8 stages
+    const size_t per_sm = 227 * 1024, reserved = 1024;
+    const size_t budget2 = per_sm / 2 - reserved;
+    int stages = 0;
+    if (NG == 32)
+        for (int s_ = 2; s_ <= KT_MAX_STAGES; ++s_)
+            if (kt_smem_bytes(C, k, NG, s_) <= budget2) stages = s_;
+    if (stages == 0)
+        for (int s_ = 2; s_ <= KT_MAX_STAGES; ++s_)
+            if (kt_smem_bytes(C, k, NG, s_) <= per_sm - reserved) stages = s_;
+    P.stages = stages;
     if (const char *e = getenv("MLSP_KT_STAGES")) P.stages = atoi(e);   // tuning hook
-    const size_t smem = (size_t)(KB + P.stages) * KT_BLK_BYTES + (size_t)KT_ROWS * 2 * NG * 2 + 2 * KT_COLS * 4 +
-                        2 * KT_ROWS * 4 + 32 * 8 + 16 + 1024;
+    P.mode = 0;
+    if (const char *e = getenv("MLSP_KT_MODE")) P.mode = atoi(e);
+    MLSP_REQUIRE(P.stages >= 2 && P.stages <= KT_MAX_STAGES && kt_smem_bytes(C, k, NG, P.stages) <= per_sm - reserved,
+                 MLSP_EUNSUPPORTED, "knn: no shared-memory configuration for C=%d k=%d", C, k);
+    const size_t smem = kt_smem_bytes(C, k, NG, P.stages);
     dim3 grid((N + KT_ROWS - 1) / KT_ROWS, B);
     if (NG == 32) {
         MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
