@@ -109,8 +109,8 @@ class _Span:
 
 
 # kernels launched per public-API call (counted from mlsp_b200/csrc: see DESIGN.md "launch inventory")
-LAUNCHES = {"fps": 1, "knn3": 1, "knn_tensor": 5, "edge_fwd_vec": 2, "edge_bwd_vec": 2, "edge_fwd_scalar": 1,
-            "edge_bwd_scalar": 1, "normals": 1 + 1, "density": 1, "deform": 2, "chamfer_fwd": 2, "chamfer_bwd": 1}
+LAUNCHES = {"fps": 1, "knn3": 1, "knn_tensor": 3, "edge_fwd_vec": 2, "edge_bwd_vec": 2, "edge_fwd3": 1,
+            "edge_bwd3": 1, "normals": 1 + 1, "density": 1, "deform": 2, "chamfer_fwd": 2, "chamfer_bwd": 1}
 
 
 class Streams:
@@ -127,17 +127,24 @@ class Streams:
 
 
 def _layer(M, timer, f, g, k):
+    """One DGCNN neighbourhood layer, forward + backward.  With the timer off this is the call the model makes:
+    get_graph_feature(x, args, k) with idx=None (knn inside; one fused C call).  With the timer on (the per-op
+    region) knn and the gather are separate calls so that each gets its own CUDA-event span."""
     C = f.shape[1]
     f = f.detach().requires_grad_(True)
-    with timer(f"knn_C{C}"):
-        idx = M.knn(f, k)
-    with timer(f"edge_fwd_C{C}"):
-        out = M.get_graph_feature(f, None, k=k, idx=idx)
+    if timer.enabled:
+        with timer(f"knn_C{C}"):
+            idx = M.knn(f, k)
+        with timer(f"edge_fwd_C{C}"):
+            out = M.get_graph_feature(f, None, k=k, idx=idx)
+    else:
+        out = M.get_graph_feature(f, None, k=k)
     with timer(f"edge_bwd_C{C}"):
         out.backward(g)
+    fused = 0 if timer.enabled else 1
     if C == 3:
-        return LAUNCHES["knn3"] + LAUNCHES["edge_fwd_scalar"] + LAUNCHES["edge_bwd_scalar"]
-    return LAUNCHES["knn_tensor"] + LAUNCHES["edge_fwd_vec"] + LAUNCHES["edge_bwd_vec"]
+        return LAUNCHES["knn3"] + LAUNCHES["edge_fwd3"] + LAUNCHES["edge_bwd3"]
+    return LAUNCHES["knn_tensor"] + LAUNCHES["edge_fwd_vec"] - fused + LAUNCHES["edge_bwd_vec"]
 
 
 def gpu_step(M, dev, lookup, k, timer, streams, clouds=None):

@@ -46,6 +46,7 @@ extern "C" {
 #define MLSP_OP_EDGE_FWD 2
 #define MLSP_OP_EDGE_BWD 3
 #define MLSP_OP_CHAMFER 4
+#define MLSP_OP_GRAPH_FEATURE 5
 
 /* flags for mlsp_knn_f32 */
 #define MLSP_KNN_AUTO 0        /* C=3: two-pass 3-D kernel; C in {64,128}: tcgen05 filter + exact re-rank; else streaming */
@@ -64,7 +65,7 @@ MLSP_API int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t *i
 
 /* Test hook for the tcgen05 path of a1 (C in {64,128}, N >= 256): same result as mlsp_knn_f32, and when
  * `dump` is non-NULL the approximate filter values |x_j|^2 - 2 dot~(x_i,x_j) are written to dump (B,N,N).
- * After the call ws holds two int32 counters at offset 0: {rows sent to the exact fallback, rows certified}. */
+ * After the call ws holds two int32 counters at offset 0: {rows re-done by the exact streaming selection, rows certified}. */
 MLSP_API int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
                                    float *dump, void *stream);
 
@@ -73,6 +74,13 @@ MLSP_API int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k, i
  *   out[b][i][j][c] = x[b][c][idx[b][i][j]] - x[b][c][i] (c < C),  x[b][c-C][i] (c >= C). */
 MLSP_API int mlsp_edge_gather_fwd(const float *x, const int64_t *idx, int B, int C, int N, int k, float *out,
                          void *ws, size_t ws_bytes, void *stream);
+
+/* a1 + a2 in one call -- get_graph_feature(x, args, k) with idx=None (the way DGCNN calls it: PointDA/Models.py:111-127,
+ *   PointSegDA/Models.py:172-182,219): idx (B,N,k) int64 is written (kept for the backward) and out as in
+ *   mlsp_edge_gather_fwd.  On the tcgen05 path the gather reads the point-major copy the kNN already made.
+ *   Workspace: mlsp_workspace_bytes(MLSP_OP_GRAPH_FEATURE, ...). */
+MLSP_API int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
+                           size_t ws_bytes, void *stream);
 
 /* backward of a2 w.r.t. x (the reference gets it from autograd: index_put_(accumulate=True)).
  *   grad_out in the same channels-last storage [B][N][k][2C]; grad_x (B,C,N), overwritten. */

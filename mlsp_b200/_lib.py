@@ -22,6 +22,7 @@ SIGNATURES = {
     "mlsp_knn_f32": [_P, _I, _I, _I, _I, _P, _P, _Z, _I, _P],
     "mlsp_knn_tensor_debug": [_P, _I, _I, _I, _I, _P, _P, _Z, _P, _P],
     "mlsp_edge_gather_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P],
+    "mlsp_graph_feature_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P],
     "mlsp_edge_gather_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P],
     "mlsp_fps": [_P, _I, _I, _I, _P, _P, _P, _P],
     "mlsp_region_assign_select": [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
@@ -36,7 +37,7 @@ SIGNATURES = {
     "mlsp_reconstruction_loss_bwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _P, _I, _I, _P, _P, _P],
 }
 
-OP_KNN, OP_EDGE_FWD, OP_EDGE_BWD, OP_CHAMFER = 1, 2, 3, 4
+OP_KNN, OP_EDGE_FWD, OP_EDGE_BWD, OP_CHAMFER, OP_GRAPH_FEATURE = 1, 2, 3, 4, 5
 KNN_AUTO, KNN_EXACT_ONLY, KNN_TENSOR_ONLY = 0, 1, 2
 
 

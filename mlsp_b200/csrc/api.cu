@@ -39,6 +39,7 @@ int sm_count()
 size_t knn_workspace_bytes(int B, int C, int N, int k);
 size_t edge_workspace_bytes(int B, int C, int N, int k);
 size_t chamfer_workspace_bytes(int B, int N);
+size_t graph_feature_workspace_bytes(int B, int C, int N, int k);
 
 }  // namespace mlsp
 
@@ -56,6 +57,7 @@ size_t mlsp_workspace_bytes(int op, int B, int C, int N, int k)
         case MLSP_OP_EDGE_FWD:
         case MLSP_OP_EDGE_BWD: return mlsp::edge_workspace_bytes(B, C, N, k);
         case MLSP_OP_CHAMFER: return mlsp::chamfer_workspace_bytes(B, N);
+        case MLSP_OP_GRAPH_FEATURE: return mlsp::graph_feature_workspace_bytes(B, C, N, k);
         default: return 0;
     }
 }

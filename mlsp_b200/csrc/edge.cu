@@ -22,6 +22,16 @@ size_t edge_workspace_bytes(int B, int C, int N, int k)
     return align_up(sizeof(float) * (size_t)B * C * N, 256);
 }
 
+size_t knn_workspace_bytes(int B, int C, int N, int k);
+bool knn_tensor_supported(int B, int C, int N, int k);
+const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k);
+
+size_t graph_feature_workspace_bytes(int B, int C, int N, int k)
+{
+    const size_t a = knn_workspace_bytes(B, C, N, k), b = edge_workspace_bytes(B, C, N, k);
+    return a > b ? a : b;
+}
+
 // (B,R,S) -> (B,S,R), 32x32 tiles through shared memory
 __global__ void transpose_kernel(const float *__restrict__ in, float *__restrict__ out, int R, int S)
 {
@@ -316,6 +326,20 @@ edge_bwd_scalar_kernel(const float *__restrict__ g, const int64_t *__restrict__ 
 
 }  // namespace mlsp
 
+namespace mlsp {
+static int launch_edge_fwd_vec(const float *xt, const int64_t *idx, int B, int C, int N, int k, float *out, cudaStream_t st)
+{
+    const long long points = (long long)B * N;
+    const int warps = 8;
+    const long long blocks = (points + warps - 1) / warps;
+    MLSP_REQUIRE(blocks < (1ll << 31), MLSP_EUNSUPPORTED, "edge_gather_fwd: too many points");
+    edge_fwd_vec_kernel<4><<<(unsigned)blocks, warps * 32, 0, st>>>(
+        reinterpret_cast<const float4 *>(xt), idx, N, k, C / 4, reinterpret_cast<float4 *>(out), points);
+    MLSP_LAUNCH_CHECK("edge_fwd_vec_kernel");
+    return MLSP_OK;
+}
+}  // namespace mlsp
+
 extern "C" int mlsp_edge_gather_fwd(const float *x, const int64_t *idx, int B, int C, int N, int k, float *out,
                                     void *ws, size_t ws_bytes, void *stream)
 {
@@ -336,12 +360,7 @@ extern "C" int mlsp_edge_gather_fwd(const float *x, const int64_t *idx, int B, i
     int rc = launch_transpose(x, xt, B, C, N, st);  // (B,C,N) -> (B,N,C)
     if (rc) return rc;
     if (C % 4 == 0) {
-        const int warps = 8;
-        const long long blocks = (points + warps - 1) / warps;
-        MLSP_REQUIRE(blocks < (1ll << 31), MLSP_EUNSUPPORTED, "edge_gather_fwd: too many points");
-        edge_fwd_vec_kernel<4><<<(unsigned)blocks, warps * 32, 0, st>>>(
-            reinterpret_cast<const float4 *>(xt), idx, N, k, C / 4, reinterpret_cast<float4 *>(out), points);
-        MLSP_LAUNCH_CHECK("edge_fwd_vec_kernel");
+        return launch_edge_fwd_vec(xt, idx, B, C, N, k, out, st);
     } else {
         const long long total = points * k * 2 * C;
         const long long blocks = (total + 255) / 256;
@@ -385,4 +404,20 @@ extern "C" int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, i
         MLSP_LAUNCH_CHECK("edge_bwd_scalar_kernel");
     }
     return launch_transpose(gxt, grad_x, B, N, C, st);  // (B,N,C) -> (B,C,N)
+}
+
+// get_graph_feature(x, args, k) with idx=None in one call: knn + edge gather.  On the tcgen05 path the point-major
+// copy of x that the kNN prep kernel leaves in the workspace is gathered from directly (no second transpose).
+extern "C" int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
+                                      size_t ws_bytes, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(x && idx && out && ws, MLSP_EINVAL, "graph_feature_fwd: null pointer");
+    MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "graph_feature_fwd: bad shape");
+    MLSP_REQUIRE(ws_bytes >= graph_feature_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "graph_feature_fwd: workspace too small");
+    int rc = mlsp_knn_f32(x, B, C, N, k, idx, ws, ws_bytes, MLSP_KNN_AUTO, stream);
+    if (rc) return rc;
+    if (knn_tensor_supported(B, C, N, k) && C % 4 == 0)
+        return launch_edge_fwd_vec(knn_tensor_xt(ws, B, C, N, k), idx, B, C, N, k, out, as_stream(stream));
+    return mlsp_edge_gather_fwd(x, idx, B, C, N, k, out, ws, ws_bytes, stream);   // stream order: the kNN is done with ws
 }

@@ -69,8 +69,9 @@ __device__ __forceinline__ void warp_sort_desc_u32(uint32_t (&key)[NC])
 // k = 40, M = 128), so the final sort usually runs on HALF the capacity CAPL = 32*NC.
 template <int NC>
 __global__ void __launch_bounds__(K3_THREADS)
-knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx)
+knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx, int *__restrict__ stats)
 {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) stats[threadIdx.x] = 0;   // {fallback rows, certified rows}: tensor path only
     constexpr int CAPL = 32 * NC;
     constexpr int SL = CAPL / 32;
     extern __shared__ float4 cloud[];                                  // [N]
@@ -224,17 +225,17 @@ knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx
 
 bool knn3_supported(int C, int N, int k) { return C == 3 && k <= 64 && N >= 1 && N <= 8192; }
 
-int knn3_run(const float *x, int B, int N, int k, int64_t *idx, cudaStream_t st)
+int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, cudaStream_t st)
 {
     const int NC = (k <= 32) ? 2 : 4;                                  // 64 / 128 classes
     const size_t smem = sizeof(float4) * (size_t)N + sizeof(uint16_t) * (size_t)(K3_THREADS / 32) * K3_R * 32 * NC;
     dim3 grid((N + K3_ROWS - 1) / K3_ROWS, B);
     if (NC == 2) {
         MLSP_CUDA(cudaFuncSetAttribute(knn3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn3_kernel<2><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx);
+        knn3_kernel<2><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx, stats);
     } else {
         MLSP_CUDA(cudaFuncSetAttribute(knn3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn3_kernel<4><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx);
+        knn3_kernel<4><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx, stats);
     }
     MLSP_LAUNCH_CHECK("knn3_kernel");
     return MLSP_OK;

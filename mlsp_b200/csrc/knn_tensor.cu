@@ -24,7 +24,7 @@
 //      reads of the point-major rows) and the cluster is re-sorted by (value desc, index asc).  Typical rows need
 //      no or a few exact distances instead of one 4C-byte gather per candidate.
 //      A row whose list overflowed is not certified and goes to
-//   4. a fallback kernel (exact streaming top-k, one warp per listed row).
+//      the exact streaming top-k (topk.cuh) in the same warp.
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA) -- profiles/.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -159,17 +159,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
 constexpr uint32_t KT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((KT_COLS >> 3) << 17) | ((KT_ROWS >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------- prep kernel
-// One pass over x (B,C,N): exact norms in the specification order (sequential adds over the channels),
-// per-cloud max norm (uint bit-pattern max is valid for non-negative floats), the point-major fp32 rows
-// xt (B,N,C) and the bf16 split hi/lo (B*N, C).  A CTA stages a [C][PREP_PTS] slab in shared memory
+// One pass over x (B,C,N): exact norms in the specification order (sequential adds over the channels), the
+// point-major fp32 rows xt (B,N,C) and the bf16 split hi/lo (B*N, C); also zeroes the two diagnostic counters.  A CTA stages a [C][PREP_PTS] slab in shared memory
 // (coalesced 128-byte reads along n), then warps write whole point rows (coalesced along c).
 constexpr int PREP_PTS = 32;
 constexpr int PREP_THREADS = 256;
 
 __global__ void __launch_bounds__(PREP_THREADS)
-knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xx, unsigned int *__restrict__ maxbits,
+knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xx, int *__restrict__ counters,
                 float *__restrict__ xt, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo)
 {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) counters[threadIdx.x] = 0;
     extern __shared__ float slab[];                       // [C][PREP_PTS + 1]
     const int b = blockIdx.y, n0 = blockIdx.x * PREP_PTS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,9 +187,7 @@ knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ x
             s = __fadd_rn(s, __fmul_rn(v, v));
         }
         const int n = n0 + lane;
-        if (n < N) xx[(size_t)b * N + n] = s; else s = 0.0f;
-        const unsigned int m = __reduce_max_sync(MLSP_FULL, __float_as_uint(s));
-        if (lane == 0) atomicMax(maxbits + b, m);
+        if (n < N) xx[(size_t)b * N + n] = s;
     }
     // rows: thread t handles channel pair (2t mod C ...) of point rows; consecutive threads -> consecutive channels
     const int pairs = C / 2;                               // C is even (64 or 128)
@@ -351,12 +349,10 @@ __device__ __noinline__ void dump_tile(float *row_out, bool row_valid, uint32_t 
 
 struct KtParams {
     const float *xx;         // (B,N) exact squared norms
-    const float *maxxx;      // (B) max squared norm per cloud
     const float *xt;         // (B,N,C) fp32 point-major
     int64_t *idx;            // (B,N,k)
-    int *fb_count;           // fallback row counter
-    int *fb_rows;            // fallback rows (b*N + i)
-    int *stats;              // [0] rows certified by the tensor path
+    int *fb_count;           // rows whose list overflowed (re-done with the exact streaming selection)
+    int *stats;              // rows certified by the tensor path
     uint2 *cand;             // (B*N, CAP) candidate lists (v bits, j): main kernel -> refine kernel
     int *cand_cnt;           // (B*N, 2) entries written from the front / from the back (> CAP: overflowed)
     float *dump;             // optional (B,N,N) approximate values (tests only)
@@ -366,11 +362,11 @@ struct KtParams {
 };
 
 // ------------------------------------------------------------------------------------------- main kernel
-// shared memory: A (2*SEG blocks) | B ring (STAGES blocks) | xchg [min(k,NG)][128] | nrm [2][128] | thr [128] | barriers
+// shared memory: A (2*SEG blocks) | B ring (STAGES blocks) | xchg [min(k,NG)][128] | nrm [2][128] | thr [128] | max [4] | barriers
 __host__ __device__ inline size_t kt_smem_bytes(int C, int k, int NG, int stages)
 {
     const int kx = k < NG ? k : NG;
-    return (size_t)(2 * C / KT_KBLK + stages) * KT_BLK_BYTES + (size_t)kx * KT_ROWS * 4 + 2 * KT_COLS * 4 + KT_ROWS * 4 +
+    return (size_t)(2 * C / KT_KBLK + stages) * KT_BLK_BYTES + (size_t)kx * KT_ROWS * 4 + 2 * KT_COLS * 4 + KT_ROWS * 4 + 16 +
            32 * 8 + 16 + 1024;
 }
 
@@ -390,7 +386,8 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     float *xchg = reinterpret_cast<float *>(sB + (size_t)STAGES * KT_BLK_BYTES);   // [KX][128] sorted class minima of the upper half
     float *nrm_s = xchg + (size_t)KX * KT_ROWS;                                     // [2][128]
     float *thr_s = nrm_s + 2 * KT_COLS;                                             // [128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(thr_s + KT_ROWS);
+    uint32_t *max_s = reinterpret_cast<uint32_t *>(thr_s + KT_ROWS);                // [4] per-warp maxima of the cloud's norms
+    uint64_t *bars = reinterpret_cast<uint64_t *>(max_s + 4);
     uint64_t *full = bars, *empty = bars + KT_MAX_STAGES, *a_full = bars + 2 * KT_MAX_STAGES;
     uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
@@ -484,7 +481,6 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int i = i0 + r;
         const int et = threadIdx.x - 64;         // 0..255 among the epilogue threads
         const float xxi = (i < N) ? P.xx[(size_t)rowbase + i] : 0.0f;
-        const float eps = pair_eps(sqrtf(xxi), xxi, P.maxxx[b]);   // bound for every candidate of the cloud
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 64;
         float gmin[NG];
 #pragma unroll
@@ -498,15 +494,24 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             cur.ovf = false;
         }
         const float *xxb = P.xx + rowbase;
-        // norms of tile 0; afterwards the norms of tile g+1 are fetched while tile g is processed
-        if (et < KT_COLS) nrm_s[et] = (et < N) ? xxb[et] : INFINITY;
+        // norms of tile 0; afterwards the norms of tile g+1 are fetched while tile g is processed.  The same threads
+        // see every norm of the cloud once during pass 1: their maximum gives the error bound of the row.
+        float nmax = 0.0f;
+        if (et < KT_COLS) {
+            const float n0 = (et < N) ? xxb[et] : INFINITY;
+            nrm_s[et] = n0;
+            if (et < N) nmax = n0;
+        }
 
         // ---- pass 1: class minima
         for (int g = 0; g < T; ++g) {
             const int buf = g & 1;
             float nxt = INFINITY;
             const int jn = ((g + 1) % T) * KT_COLS + et;       // tile g+1 (pass 2 restarts at tile 0)
-            if (et < KT_COLS && jn < N) nxt = xxb[jn];
+            if (et < KT_COLS && jn < N) {
+                nxt = xxb[jn];
+                nmax = fmaxf(nmax, nxt);
+            }
             epi_bar_sync();                                     // norms of tile g visible
             mbar_wait(tm_full + buf, (g >> 1) & 1);
             tc_fence_after();
@@ -526,8 +531,14 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             for (int e = 0; e < NG; ++e)
                 if (e < KX) xchg[e * KT_ROWS + r] = gmin[e];
         }
+        if (et < KT_COLS) {                                     // warps 2..5 hold the norms
+            const uint32_t m = __reduce_max_sync(MLSP_FULL, __float_as_uint(nmax));   // non-negative floats order as uints
+            if (lane == 0) max_s[warp - 2] = m;
+        }
         epi_bar_sync();
         if (h == 0) {
+            const float maxxx = __uint_as_float(max(max(max_s[0], max_s[1]), max(max_s[2], max_s[3])));
+            const float eps = pair_eps(sqrtf(xxi), xxi, maxxx);   // bound for every candidate of the cloud
             float tau = -INFINITY;
 #pragma unroll
             for (int e = 0; e < NG; ++e)
@@ -689,6 +700,33 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, long long row, 
     }
 }
 
+// exact streaming top-k of one row by one warp, for the (rare) rows whose candidate list overflowed
+// (duplicate-heavy or degenerate clouds): point-major rows, the pinned dot order, selection of topk.cuh
+template <int KSLOTS>
+__device__ __noinline__ void knn_row_exact(const float *__restrict__ xt, const float *__restrict__ xx, long long row,
+                                           int N, int C, int k, int64_t *__restrict__ idx)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t base = (size_t)(row / N) * N;
+    const int C4 = C / 4;
+    const float4 *xi = reinterpret_cast<const float4 *>(xt + (size_t)row * C);
+    const float xxi = xx[row];
+    TopK<KSLOTS> top;
+    top.init(k);
+    for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        float pd = -INFINITY;
+        if (j < N) pd = exact_pd(xi, reinterpret_cast<const float4 *>(xt + (base + j) * C), C4, xxi, xx[base + j]);
+        top.offer(pd, j, j < N);
+    }
+    top.finish(k);
+#pragma unroll
+    for (int s = 0; s < KSLOTS; ++s) {
+        const int r = s * 32 + lane;
+        if (r < k) idx[(size_t)row * k + r] = (int64_t)top.j[s];
+    }
+}
+
 template <int NG, int C>
 __global__ void __launch_bounds__(32 * RF_WARPS)
 knn_refine_kernel(KtParams P, long long total_rows)
@@ -701,7 +739,8 @@ knn_refine_kernel(KtParams P, long long total_rows)
     const int c0 = P.cand_cnt[2 * row], c1 = P.cand_cnt[2 * row + 1];
     const int cnt = c0 + c1;
     if (c0 > CAP || c1 > CAP || cnt > CAP || cnt < P.k) {
-        if (lane == 0) P.fb_rows[atomicAdd(P.fb_count, 1)] = (int)row;
+        knn_row_exact<NG / 32>(P.xt, P.xx, row, P.N, C, P.k, P.idx);   // warp-uniform
+        if (lane == 0) atomicAdd(P.fb_count, 1);
         return;
     }
     __shared__ uint16_t sj_all[RF_WARPS][CAP];
@@ -729,40 +768,6 @@ knn_refine_kernel(KtParams P, long long total_rows)
         refine_sorted<SLOTS, C>(P, row, key, sj, se);
     }
     if (lane == 0) atomicAdd(P.stats, 1);
-}
-
-// ------------------------------------------------------------------------------------------- fallback
-// exact streaming top-k for the (rare) uncertified rows: one warp per listed row, point-major rows
-template <int KSLOTS>
-__global__ void __launch_bounds__(256)
-knn_fallback_kernel(const float *__restrict__ xt, const float *__restrict__ xx, const int *__restrict__ fb_count,
-                    const int *__restrict__ fb_rows, int N, int C, int k, int64_t *__restrict__ idx)
-{
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    const int count = *fb_count;
-    const int C4 = C / 4;
-    for (int e = gw; e < count; e += nw) {
-        const int row = fb_rows[e];
-        const int b = row / N;
-        const size_t base = (size_t)b * N;
-        const float4 *xi = reinterpret_cast<const float4 *>(xt + (size_t)row * C);
-        const float xxi = xx[row];
-        TopK<KSLOTS> top;
-        top.init(k);
-        for (int j0 = 0; j0 < N; j0 += 32) {
-            const int j = j0 + lane;
-            float pd = -INFINITY;
-            if (j < N) pd = exact_pd(xi, reinterpret_cast<const float4 *>(xt + (base + j) * C), C4, xxi, xx[base + j]);
-            top.offer(pd, j, j < N);
-        }
-        top.finish(k);
-#pragma unroll
-        for (int s = 0; s < KSLOTS; ++s) {
-            const int r = s * 32 + lane;
-            if (r < k) idx[(size_t)row * k + r] = (int64_t)top.j[s];
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -799,7 +804,7 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t co
 }
 
 struct KtLayout {
-    size_t off_counters, off_max, off_xx, off_hi, off_lo, off_xt, off_rows, off_cand, off_cnt, total;
+    size_t off_counters, off_xx, off_hi, off_lo, off_xt, off_cand, off_cnt, total;
 };
 
 static KtLayout kt_layout(int B, int C, int N, int k)
@@ -808,12 +813,10 @@ static KtLayout kt_layout(int B, int C, int N, int k)
     KtLayout L;
     size_t o = 0;
     L.off_counters = o; o += 256;                                            // [0] fb_count, [1] certified rows
-    L.off_max = o;      o += align_up(sizeof(float) * (size_t)B, 256);
     L.off_xx = o;       o += align_up(sizeof(float) * (size_t)B * N, 256);
     L.off_hi = o;       o += align_up(2 * (size_t)B * N * C, 1024);
     L.off_lo = o;       o += align_up(2 * (size_t)B * N * C, 1024);
     L.off_xt = o;       o += align_up(sizeof(float) * (size_t)B * N * C, 256);
-    L.off_rows = o;     o += align_up(sizeof(int) * (size_t)B * N, 256);
     L.off_cand = o;     o += align_up(sizeof(uint2) * (size_t)B * N * CAP, 256);
     L.off_cnt = o;      o += align_up(2 * sizeof(int) * (size_t)B * N, 256);
     L.total = o;
@@ -827,21 +830,24 @@ bool knn_tensor_supported(int B, int C, int N, int k)
 
 size_t knn_tensor_workspace_bytes(int B, int C, int N, int k) { return kt_layout(B, C, N, k).total; }
 
+// the point-major copy xt (B,N,C) the tensor path leaves in its workspace (reused by the fused edge gather)
+const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k)
+{
+    return reinterpret_cast<const float *>(static_cast<const char *>(ws) + kt_layout(B, C, N, k).off_xt);
+}
+
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, cudaStream_t st)
 {
     const KtLayout L = kt_layout(B, C, N, k);
     char *w = static_cast<char *>(ws);
     int *counters = reinterpret_cast<int *>(w + L.off_counters);
-    float *maxxx = reinterpret_cast<float *>(w + L.off_max);
     float *xx = reinterpret_cast<float *>(w + L.off_xx);
     __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(w + L.off_hi);
     __nv_bfloat16 *lo = reinterpret_cast<__nv_bfloat16 *>(w + L.off_lo);
     float *xt = reinterpret_cast<float *>(w + L.off_xt);
-    int *rows = reinterpret_cast<int *>(w + L.off_rows);
 
-    MLSP_CUDA(cudaMemsetAsync(w, 0, L.off_xx, st));    // counters + per-cloud max
     knn_prep_kernel<<<dim3((N + PREP_PTS - 1) / PREP_PTS, B), PREP_THREADS, sizeof(float) * C * (PREP_PTS + 1), st>>>(
-        x, C, N, xx, reinterpret_cast<unsigned int *>(maxxx), xt, hi, lo);
+        x, C, N, xx, counters, xt, hi, lo);
     MLSP_LAUNCH_CHECK("knn_prep_kernel");
 
     CUtensorMap map_hi, map_lo;
@@ -851,7 +857,7 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     if (rc) return rc;
 
     KtParams P;
-    P.xx = xx; P.maxxx = maxxx; P.xt = xt; P.idx = idx; P.fb_count = counters; P.fb_rows = rows;
+    P.xx = xx; P.xt = xt; P.idx = idx; P.fb_count = counters;
     P.stats = counters + 1; P.dump = dump;
     P.cand = reinterpret_cast<uint2 *>(w + L.off_cand); P.cand_cnt = reinterpret_cast<int *>(w + L.off_cnt); P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS;
     const int NG = (k <= 32) ? 32 : 64;
@@ -894,12 +900,6 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
             knn_refine_kernel<64, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
         MLSP_LAUNCH_CHECK("knn_refine_kernel");
     }
-    const int fb_blocks = 2 * sm_count();
-    if (k <= 32)
-        knn_fallback_kernel<1><<<fb_blocks, 256, 0, st>>>(xt, xx, counters, rows, N, C, k, idx);
-    else
-        knn_fallback_kernel<2><<<fb_blocks, 256, 0, st>>>(xt, xx, counters, rows, N, C, k, idx);
-    MLSP_LAUNCH_CHECK("knn_fallback_kernel");
     return MLSP_OK;
 }
 

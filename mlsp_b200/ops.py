@@ -99,17 +99,44 @@ class _EdgeGather(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
-        (idx,) = ctx.saved_tensors
-        B, C, N, k = ctx.dims
-        g = grad.permute(0, 2, 3, 1).contiguous()   # storage order [B][N][k][2C]; free if already channels_last
-        if g.dtype != torch.float32:
-            g = g.float()
-        gx = torch.empty((B, C, N), dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
-            ws = _workspace(_lib.OP_EDGE_BWD, B, C, N, k, g.device)
-            _lib.call("mlsp_edge_gather_bwd", _ptr(g), _ptr(idx), B, C, N, k, _ptr(gx), _ptr(ws), ws.numel(),
-                      _stream(g.device))
-        return gx, None
+        return _edge_backward(ctx, grad), None
+
+
+def _edge_backward(ctx, grad):
+    (idx,) = ctx.saved_tensors
+    B, C, N, k = ctx.dims
+    g = grad.permute(0, 2, 3, 1).contiguous()   # storage order [B][N][k][2C]; free if already channels_last
+    if g.dtype != torch.float32:
+        g = g.float()
+    gx = torch.empty((B, C, N), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        ws = _workspace(_lib.OP_EDGE_BWD, B, C, N, k, g.device)
+        _lib.call("mlsp_edge_gather_bwd", _ptr(g), _ptr(idx), B, C, N, k, _ptr(gx), _ptr(ws), ws.numel(),
+                  _stream(g.device))
+    return gx
+
+
+class _GraphFeature(torch.autograd.Function):
+    """knn + edge gather in one C call (the idx=None form every DGCNN layer uses); same backward as _EdgeGather."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        B, C, N = x.shape
+        if not (1 <= k <= N):
+            raise RuntimeError(f"selected index k out of range (k={k}, N={N})")  # torch.topk's message
+        out = torch.empty((B, N, k, 2 * C), dtype=torch.float32, device=x.device)
+        idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = _workspace(_lib.OP_GRAPH_FEATURE, B, C, N, k, x.device)
+            _lib.call("mlsp_graph_feature_fwd", _ptr(x), B, C, N, k, _ptr(idx), _ptr(out), _ptr(ws), ws.numel(),
+                      _stream(x.device))
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, C, N, k)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return _edge_backward(ctx, grad), None
 
 
 def get_graph_feature(x: torch.Tensor, args=None, k: int = 20, idx: torch.Tensor | None = None) -> torch.Tensor:
@@ -120,12 +147,10 @@ def get_graph_feature(x: torch.Tensor, args=None, k: int = 20, idx: torch.Tensor
     B, N = x.size(0), x.size(2)
     x = x.reshape(B, -1, N).contiguous()
     if idx is None:
-        idx = knn(x, k=k)
-    else:
-        if idx.shape != (B, N, k) or idx.dtype != torch.int64 or idx.device != x.device:
-            raise MlspError("get_graph_feature: idx must be int64 (B,N,k) on x's device")
-        idx = idx.contiguous()
-    return _EdgeGather.apply(x, idx)
+        return _GraphFeature.apply(x, int(k))
+    if idx.shape != (B, N, k) or idx.dtype != torch.int64 or idx.device != x.device:
+        raise MlspError("get_graph_feature: idx must be int64 (B,N,k) on x's device")
+    return _EdgeGather.apply(x, idx.contiguous())
 
 
 # ----------------------------------------------------------------------------------------------- a3

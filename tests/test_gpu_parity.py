@@ -124,6 +124,25 @@ def test_edge_gather_matches_oracle(dev, orc, B, C, N, k):
     assert np.array_equal(_np(out.permute(0, 2, 3, 1)), ref)
 
 
+@pytest.mark.parametrize("B,C,N,k", [(4, 3, 1024, 20), (4, 64, 1024, 20), (2, 128, 1024, 20), (2, 128, 2048, 40),
+                                     (2, 6, 333, 7), (2, 64, 200, 20)])
+def test_graph_feature_fused_call(dev, orc, B, C, N, k):
+    """get_graph_feature(x, args, k) with idx=None -- the form DGCNN uses -- goes through mlsp_graph_feature_fwd
+    (knn + gather in one C call, sharing the point-major copy on the tensor path): same bits as the two-step path
+    and as the oracle, and the same backward."""
+    x = (synth.clouds(B, N, 5) if C == 3 else synth.smooth_features(B, C, N, 5)).to(dev).requires_grad_(True)
+    out = M.get_graph_feature(x, None, k=k)
+    idx = orc.knn(_np(x), k)
+    assert out.shape == (B, 2 * C, N, k) and out.stride() == (N * k * 2 * C, 1, k * 2 * C, 2 * C)
+    assert np.array_equal(_np(out.permute(0, 2, 3, 1)), orc.edge_gather(_np(x), idx))
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+    out.backward(g)
+    x2 = x.detach().clone().requires_grad_(True)
+    M.get_graph_feature(x2, None, k=k, idx=torch.from_numpy(idx).to(dev)).backward(g)
+    scale = float(x2.grad.abs().max())
+    assert float((x.grad - x2.grad).abs().max()) <= 1e-5 * scale
+
+
 def test_edge_gather_backward_golden(golden, dev):
     g = golden("ggf_bwd")
     x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
