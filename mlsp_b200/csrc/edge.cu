@@ -8,18 +8,15 @@
 // stores.  HBM traffic is the algorithmic 4BCN + 8BNk + 8BCNk bytes; the kernel is bandwidth bound.
 // Backward: one pass over grad_out accumulates the centre terms in registers and scatters the
 // neighbour terms with vector float atomics into gxt (B,N,C) in L2, then a transpose back to (B,C,N).
-#include <cooperative_groups.h>
-
+// C = 3 (the two 3-D layers) has its own forward (no transposed copy at all) and backward (padded scratch).
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace mlsp {
 
 size_t edge_workspace_bytes(int B, int C, int N, int k)
 {
     (void)k;
-    return align_up(sizeof(float) * (size_t)B * C * N, 256);
+    return align_up(sizeof(float) * (size_t)B * (C < 4 ? 4 : C) * N, 256);   // C = 3 backward: padded (B,N,4) scratch
 }
 
 size_t knn_workspace_bytes(int B, int C, int N, int k);
@@ -232,79 +229,53 @@ edge_bwd_vec_kernel(const float4 *__restrict__ g, const int64_t *__restrict__ id
     }
 }
 
-// ---- backward, C = 3: one cluster of 8 CTAs per cloud, accumulators in (distributed) shared memory ----
-// Each CTA of the cluster takes N/8 query points and accumulates into its own copy of the cloud's gradient
-// acc[3][N] in shared memory (red.shared: the neighbour terms land anywhere in the cloud); one warp per
-// point reads its k*6 gradients as coalesced float2, reduces the three centre terms in registers.  After a
-// cluster barrier CTA r sums the eight copies of its slice through DSMEM and writes grad_x (B,3,N) directly:
-// no global atomics, no memset, no transposed buffer.
-constexpr int EB3_CL = 8;
-constexpr int EB3_THREADS = 1024;
-
-__global__ void __cluster_dims__(EB3_CL, 1, 1) __launch_bounds__(EB3_THREADS)
-edge_bwd3_kernel(const float *__restrict__ g, const int64_t *__restrict__ idx, int N, int k, float *__restrict__ gx)
+// ---- backward, C = 3: one warp per query point, one lane per neighbour --------------------------------
+// Lane j reads the 6 gradients of output row (i, j) as three float2 (the warp covers the point's k*24
+// contiguous bytes) and adds (d0, d1, d2, 0) to the neighbour's slot of a padded point-major scratch
+// gx4 (B,N,4) with ONE 128-bit reduction (red.global.add.v4.f32, L2 resident); the centre terms sum_j (c - d)
+// are reduced over the warp and added with one more.  A second tiny kernel turns gx4 into grad_x (B,3,N).
+// (Shared-memory accumulation is not an option: fp32 atomicAdd on shared memory is a CAS loop on sm_100.)
+__global__ void __launch_bounds__(256)
+edge_bwd3_kernel(const float *__restrict__ g, const int64_t *__restrict__ idx, int N, int k, float4 *__restrict__ gx4,
+                 long long total_points)
 {
-    extern __shared__ float acc[];                          // [3][N]
-    cg::cluster_group cl = cg::this_cluster();
-    const int rank = (int)cl.block_rank();
-    const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < 3 * N; e += EB3_THREADS) acc[e] = 0.0f;
-    __syncthreads();
-    const int chunk = (N + EB3_CL - 1) / EB3_CL;
-    const int i_lo = rank * chunk, i_hi = min(N, i_lo + chunk);
-    const int F = 3 * k;                                     // float2 pieces per point
-    for (int i = i_lo + warp; i < i_hi; i += EB3_THREADS / 32) {
-        const size_t row0 = ((size_t)b * N + i) * k;
-        const float2 *gr = reinterpret_cast<const float2 *>(g + row0 * 6);
-        const int64_t *ir = idx + row0;
-        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
-        for (int f0 = 0; f0 < F; f0 += 128) {
-            float2 v[4];
-            int n[4], sel[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {                    // all loads of the point in flight first
-                const int f = f0 + u * 32 + lane;
-                const bool ok = f < F;
-                const int j = f / 3;
-                sel[u] = ok ? f - 3 * j : 3;
-                v[u] = ok ? __ldcs(gr + f) : make_float2(0.0f, 0.0f);
-                n[u] = (sel[u] < 2) ? (int)ir[j] : 0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (sel[u] == 0) {                           // (d0, d1)
-                    atomicAdd(acc + n[u], v[u].x);
-                    atomicAdd(acc + N + n[u], v[u].y);
-                    c0 -= v[u].x;
-                    c1 -= v[u].y;
-                } else if (sel[u] == 1) {                    // (d2, c0)
-                    atomicAdd(acc + 2 * N + n[u], v[u].x);
-                    c2 -= v[u].x;
-                    c0 += v[u].y;
-                } else if (sel[u] == 2) {                    // (c1, c2)
-                    c1 += v[u].x;
-                    c2 += v[u].y;
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            c0 += __shfl_xor_sync(MLSP_FULL, c0, o);
-            c1 += __shfl_xor_sync(MLSP_FULL, c1, o);
-            c2 += __shfl_xor_sync(MLSP_FULL, c2, o);
-        }
-        if (lane < 3) atomicAdd(acc + lane * N + i, lane == 0 ? c0 : (lane == 1 ? c1 : c2));
+    const int lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // b*N + i
+    if (p >= total_points) return;
+    const long long b = p / N;
+    float4 *gb = gx4 + b * N;
+    const float2 *gr = reinterpret_cast<const float2 *>(g + p * k * 6);
+    const int64_t *ir = idx + p * k;
+    float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+    for (int j = lane; j < k; j += 32) {
+        const float2 a = __ldcs(gr + 3 * j), m = __ldcs(gr + 3 * j + 1), c = __ldcs(gr + 3 * j + 2);   // d0 d1 | d2 c0 | c1 c2
+        const long long n = ir[j];
+        atomicAdd(gb + n, make_float4(a.x, a.y, m.x, 0.0f));
+        c0 += m.y - a.x;
+        c1 += c.x - a.y;
+        c2 += c.y - m.x;
     }
-    cl.sync();
-    const int span = i_hi - i_lo;
-    for (int e = tid; e < 3 * span; e += EB3_THREADS) {
-        const int c = e / span, n = i_lo + (e - c * span);
-        float s = 0.0f;
 #pragma unroll
-        for (int q = 0; q < EB3_CL; ++q) s += cl.map_shared_rank(acc, q)[c * N + n];
-        gx[((size_t)b * 3 + c) * N + n] = s;
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(MLSP_FULL, c0, o);
+        c1 += __shfl_xor_sync(MLSP_FULL, c1, o);
+        c2 += __shfl_xor_sync(MLSP_FULL, c2, o);
     }
-    cl.sync();                                               // peers may still be reading this CTA's copy
+    if (lane == 0) atomicAdd(gx4 + p, make_float4(c0, c1, c2, 0.0f));
+}
+
+// gx4 (B,N,4) -> grad_x (B,3,N)
+__global__ void __launch_bounds__(256)
+edge_bwd3_finish_kernel(const float4 *__restrict__ gx4, int N, float *__restrict__ gx, long long total_points)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total_points) return;
+    const long long b = p / N, n = p - b * N;
+    const float4 v = gx4[p];
+    float *o = gx + b * 3 * N + n;
+    o[0] = v.x;
+    o[N] = v.y;
+    o[2 * (long long)N] = v.z;
 }
 
 __global__ void __launch_bounds__(256)
@@ -379,11 +350,14 @@ extern "C" int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, i
     MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "edge_gather_bwd: bad shape");
     MLSP_REQUIRE(ws_bytes >= edge_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "edge_gather_bwd: workspace too small");
     cudaStream_t st = as_stream(stream);
-    if (C == 3 && sizeof(float) * 3 * (size_t)N <= 200 * 1024 && B <= 65535) {
-        const size_t smem = sizeof(float) * 3 * (size_t)N;
-        MLSP_CUDA(cudaFuncSetAttribute(edge_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        edge_bwd3_kernel<<<dim3(EB3_CL, B), EB3_THREADS, smem, st>>>(grad_out, idx, N, k, grad_x);
+    if (C == 3 && (long long)B * N < (1ll << 31) - 256) {
+        const long long points = (long long)B * N;
+        float4 *gx4 = static_cast<float4 *>(ws);
+        MLSP_CUDA(cudaMemsetAsync(gx4, 0, sizeof(float4) * (size_t)points, st));
+        edge_bwd3_kernel<<<(unsigned)((points + 7) / 8), 256, 0, st>>>(grad_out, idx, N, k, gx4, points);
         MLSP_LAUNCH_CHECK("edge_bwd3_kernel");
+        edge_bwd3_finish_kernel<<<(unsigned)((points + 255) / 256), 256, 0, st>>>(gx4, N, grad_x, points);
+        MLSP_LAUNCH_CHECK("edge_bwd3_finish_kernel");
         return MLSP_OK;
     }
     float *gxt = static_cast<float *>(ws);

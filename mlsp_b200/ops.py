@@ -104,7 +104,12 @@ class _EdgeGather(torch.autograd.Function):
 
 def _edge_backward(ctx, grad):
     (idx,) = ctx.saved_tensors
-    B, C, N, k = ctx.dims
+    return edge_gather_backward(grad, idx, ctx.dims[1])
+
+
+def edge_gather_backward(grad: torch.Tensor, idx: torch.Tensor, C: int) -> torch.Tensor:
+    """Backward of get_graph_feature w.r.t. x (what autograd calls): grad (B,2C,N,k) -> (B,C,N)."""
+    B, N, k = idx.shape
     g = grad.permute(0, 2, 3, 1).contiguous()   # storage order [B][N][k][2C]; free if already channels_last
     if g.dtype != torch.float32:
         g = g.float()
@@ -258,14 +263,47 @@ def _draw_gaussians(means, counts):
     return z
 
 
+class _PinnedRing:
+    """Four pinned staging buffers per device, reused round-robin; an event per slot guards reuse, so the upload
+    of step s can still be in flight while the host prepares step s+1."""
+
+    def __init__(self):
+        self.slots = {}
+        self.turn = 0
+
+    def stage(self, nbytes: int, device):
+        key = (torch.device(device).index or 0, self.turn & 3)
+        self.turn += 1
+        buf, ev = self.slots.get(key, (None, None))
+        if ev is not None:
+            ev.synchronize()
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+        ev = torch.cuda.Event()
+        self.slots[key] = (buf, ev)
+        return buf, ev
+
+
+_ring = _PinnedRing()
+
+
 def _upload_noise(noise, counts, device):
+    """One pinned-memory upload of [offsets (B int32) | noise (total,3) float32] -> (noise view or None, offsets view)."""
     counts = np.asarray(counts, dtype=np.int64)
-    offsets = np.zeros(len(counts), np.int32)
-    offsets[1:] = np.cumsum(counts[:-1])
-    off_d = torch.from_numpy(offsets).to(device, non_blocking=True)
-    if noise.shape[0] == 0:
-        return None, off_d
-    return torch.from_numpy(noise.astype(np.float32)).to(device, non_blocking=True), off_d
+    B, total = len(counts), int(noise.shape[0])
+    nwords = B + 3 * total
+    buf, ev = _ring.stage(4 * nwords, device)
+    host = buf.numpy()[: 4 * nwords].view(np.float32)
+    off = host[:B].view(np.int32)
+    off[0] = 0
+    np.cumsum(counts[:-1], out=off[1:])
+    if total:
+        host[B:] = noise.reshape(-1)                       # float64 -> float32, like X[b,:3,ind] = torch.tensor(...) does
+    dev = torch.empty(nwords, dtype=torch.float32, device=device)
+    dev.copy_(buf[: 4 * nwords].view(torch.float32), non_blocking=True)
+    ev.record(torch.cuda.current_stream(device))
+    off_d = dev[:B].view(torch.int32)
+    return (dev[B:] if total else None), off_d
 
 
 def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxels", device="cuda:0", groups: int = 1):
@@ -364,14 +402,20 @@ def cal_density(batch_pts: torch.Tensor, radius: float, num_cls: int, pergroup: 
 
 
 # ----------------------------------------------------------------------------------------------- a7
-def estimate_normals(xyz: torch.Tensor, near: int = 20, return_curvature: bool = False):
+def estimate_normals(xyz: torch.Tensor, near: int = 20, return_curvature: bool = False, idx: torch.Tensor | None = None):
     """Batched replacement of the per-cloud python-pcl loop PointDA/trainer.py:524-531 (kSearchNormalEstimation
     :173-188).  xyz (B,N,3) -> unit normals (B,N,3), oriented towards the origin like pcl's default viewpoint;
-    optionally also pcl's 4th column, the surface curvature lambda_min / trace (B,N)."""
+    optionally also pcl's 4th column, the surface curvature lambda_min / trace (B,N).  `idx` (B,N,near) int64:
+    neighbourhoods already computed on the same cloud (knn(xyz^T, near)), reused instead of a second kNN pass."""
     _require_cuda_f32(xyz, "estimate_normals")
     pts = xyz.detach().contiguous()
     B, N, _ = pts.shape
-    idx = knn(pts.transpose(1, 2).contiguous(), near)
+    if idx is None:
+        idx = knn(pts.transpose(1, 2).contiguous(), near)
+    elif idx.shape != (B, N, near) or idx.dtype != torch.int64 or idx.device != pts.device:
+        raise MlspError("estimate_normals: idx must be int64 (B,N,near) on xyz's device")
+    else:
+        idx = idx.contiguous()
     normals = torch.empty((B, N, 3), dtype=torch.float32, device=pts.device)
     curv = torch.empty((B, N), dtype=torch.float32, device=pts.device) if return_curvature else None
     with torch.cuda.device(pts.device):
@@ -437,35 +481,46 @@ def chamfer_distance(p1: torch.Tensor, p2: torch.Tensor, mask: torch.Tensor) -> 
     return _ChamferDir.apply(p1, p2, mask)
 
 
+def reconstruction_loss_forward(pred, gold, mask):
+    """Forward half of reconstruction_loss on (B,N,3)-viewed tensors -> (loss, mask rows, argmin (2,B,N))."""
+    B, N, _ = pred.shape
+    dev = pred.device
+    m, mbs = _mask_rows(mask)
+    argmin = torch.empty((2, B, N), dtype=torch.int64, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(_lib.OP_CHAMFER, B, 3, N, 0, dev)
+        _lib.call("mlsp_reconstruction_loss_fwd", _ptr(pred), *_point_strides(pred), _ptr(gold), *_point_strides(gold),
+                  _ptr(m), mbs, B, N, _ptr(argmin), _ptr(loss), _ptr(ws), ws.numel(), _stream(dev))
+    return loss, m, argmin
+
+
+def reconstruction_loss_backward(pred, gold, m, argmin, grad):
+    """Backward half (what autograd calls): closed form on the saved argmins -> grad_pred (B,N,3)."""
+    B, N, _ = pred.shape
+    dev = pred.device
+    gp = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    grad = grad.to(torch.float32).contiguous()
+    with torch.cuda.device(dev):
+        _lib.call("mlsp_reconstruction_loss_bwd", _ptr(pred), *_point_strides(pred), _ptr(gold), *_point_strides(gold),
+                  _ptr(m), m.stride(0), _ptr(argmin), B, N, _ptr(grad), _ptr(gp), _stream(dev))
+    return gp
+
+
 class _ReconstructionLoss(torch.autograd.Function):
     """Both Chamfer directions, the per-cloud mean and the 1/B batch mean in one C call (two launches); the
-    backward is one memset + one launch on the saved argmins.  gold and mask are targets: no gradient."""
+    backward is one launch on the saved argmins.  gold and mask are targets: no gradient."""
 
     @staticmethod
     def forward(ctx, pred, gold, mask):
-        B, N, _ = pred.shape
-        dev = pred.device
-        m, mbs = _mask_rows(mask)
-        argmin = torch.empty((2, B, N), dtype=torch.int64, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            ws = _workspace(_lib.OP_CHAMFER, B, 3, N, 0, dev)
-            _lib.call("mlsp_reconstruction_loss_fwd", _ptr(pred), *_point_strides(pred), _ptr(gold), *_point_strides(gold),
-                      _ptr(m), mbs, B, N, _ptr(argmin), _ptr(loss), _ptr(ws), ws.numel(), _stream(dev))
+        loss, m, argmin = reconstruction_loss_forward(pred, gold, mask)
         ctx.save_for_backward(pred, gold, m, argmin)
         return loss
 
     @staticmethod
     def backward(ctx, grad):
         pred, gold, m, argmin = ctx.saved_tensors
-        B, N, _ = pred.shape
-        dev = pred.device
-        gp = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
-        grad = grad.to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
-            _lib.call("mlsp_reconstruction_loss_bwd", _ptr(pred), *_point_strides(pred), _ptr(gold), *_point_strides(gold),
-                      _ptr(m), m.stride(0), _ptr(argmin), B, N, _ptr(grad), _ptr(gp), _stream(dev))
-        return gp, None, None
+        return reconstruction_loss_backward(pred, gold, m, argmin, grad), None, None
 
 
 def reconstruction_loss(pred: torch.Tensor, gold: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
