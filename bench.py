@@ -492,6 +492,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     host, dev = make_inputs(B, N, k, 1234 + rank, device, pin=True)
     lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=device)
