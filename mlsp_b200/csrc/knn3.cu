@@ -21,13 +21,15 @@ constexpr int K3_THREADS = 256;
 constexpr int K3_R = 4;                                   // rows per warp
 constexpr int K3_ROWS = (K3_THREADS / 32) * K3_R;         // 32 rows per CTA
 
-__device__ __forceinline__ float pd3(float4 a, float4 q)
+// t = rn(2 dot - |x_j|^2): the candidate-dependent part of pd
+__device__ __forceinline__ float t3(float4 a, float4 q)
 {
     float d = __fmaf_rn(a.x, q.x, 0.0f);
     d = __fmaf_rn(a.y, q.y, d);
     d = __fmaf_rn(a.z, q.z, d);
-    return __fsub_rn(__fmaf_rn(2.0f, d, -q.w), a.w);
+    return __fmaf_rn(2.0f, d, -q.w);
 }
+__device__ __forceinline__ float pd3(float4 a, float4 q) { return __fsub_rn(t3(a, q), a.w); }
 
 // descending bitonic sort of 32*NC 32-bit keys across the warp (key[s] on lane l <-> element s*32+l)
 template <int NC>
@@ -106,10 +108,15 @@ knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx
             if (j < N) {
                 const float4 q = cloud[j];
 #pragma unroll
-                for (int rr = 0; rr < K3_R; ++rr) cmax[rr][c] = fmaxf(cmax[rr][c], pd3(xi[rr], q));
+                for (int rr = 0; rr < K3_R; ++rr) cmax[rr][c] = fmaxf(cmax[rr][c], t3(xi[rr], q));
             }
         }
     }
+    // the maxima were taken on t = rn(2 dot - |x_j|^2); rn(. - |x_i|^2) is monotone, so max_j pd = rn(max_j t - |x_i|^2)
+#pragma unroll
+    for (int rr = 0; rr < K3_R; ++rr)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cmax[rr][c] = __fsub_rn(cmax[rr][c], xi[rr].w);
     // ---- tau = k-th largest class maximum (orderable keys; -inf classes sort last)
     float tau[K3_R];
 #pragma unroll

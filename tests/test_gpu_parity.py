@@ -214,6 +214,17 @@ def test_deform_input_golden(golden, dev, name, mode):
     assert np.array_equal(_np(Xd), g["X"])
 
 
+def test_normals_reuse_neighbourhoods(dev):
+    """estimate_normals(xyz, near, idx=knn(xyz^T, near)) -- the neighbourhood-reuse form -- equals the one-call form."""
+    x = synth.surface_clouds(3, 700, 21).to(dev)
+    pts = x.permute(0, 2, 1).contiguous()
+    a = M.estimate_normals(pts, 12)
+    b, curv = M.estimate_normals(pts, 12, return_curvature=True, idx=M.knn(x, 12))
+    assert torch.equal(a, b) and curv.shape == (3, 700)
+    with pytest.raises(M.MlspError):
+        M.estimate_normals(pts, 12, idx=M.knn(x, 11))
+
+
 @pytest.mark.parametrize("mode", ["volume_based_voxels", "volume_based_radius"])
 def test_deform_input_full_size(dev, npo, mode):
     X0 = synth.surface_clouds(32, 1024, 77)
