@@ -560,6 +560,28 @@ def main():
         barrier()
         e2e_s = time.perf_counter() - t0
 
+    # ---- region 3: the target builder alone (BASELINE.json configs[1]: "MLSP target generation ... 32x1024 on 1
+    # B200"): deform_input + FPS 512+512 + PCA normals + cardinality per step, for both masking modes of
+    # deform_input (the reference's default voxel regions, and the ball-query collapse 'volume_based_radius')
+    target_gen = {}
+    with torch.cuda.stream(streams.model):
+        pts_c = dev["clouds"].permute(0, 2, 1).contiguous()
+        for mode in ("volume_based_voxels", "volume_based_radius"):
+            def tg():
+                M.deform_input(dev["clouds"].clone(), lookup, mode, device)
+                for n_ in FPS_SPLIT:
+                    M.farthest_point_sample(None, dev["clouds"], n_)
+                M.estimate_normals(pts_c, NEAR)
+                M.cal_density(pts_c, RADIUS, NUM_CLS)
+            for _ in range(3):
+                tg()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                tg()
+            barrier()
+            target_gen[mode] = (time.perf_counter() - t0) / args.steps * 1e3
+
     def max_over_ranks(v):
         if dist is None:
             return v
@@ -570,6 +592,7 @@ def main():
     step_ms = max_over_ranks(max(dev_ms, wall * 1e3) / args.steps)   # device time == wall here (host-sync'd step)
     dev_only_ms = max_over_ranks(dev_ms / args.steps)
     e2e_ms = max_over_ranks(e2e_s * 1e3 / args.steps)
+    target_gen = {m_: max_over_ranks(v) for m_, v in target_gen.items()}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -666,6 +689,8 @@ def main():
                 "h2d_bytes_per_step": int(host["clouds"].numel() * 4), "d2h_bytes_per_step": 4 + 8 * B,
                 "loss": loss_host},
         "gpu_launches": launches,
+        "target_gen": {m_: {"ms_per_step": round(v, 4), "clouds_per_s": round(B * world / (v * 1e-3), 1)}
+                       for m_, v in target_gen.items()},
         "roofline": roof,
         "op_ms_per_step": {n: round(v, 4) for n, v in sorted(per_step_ms.items(), key=lambda kv: -kv[1])},
         "op_rooflines": rooflines,

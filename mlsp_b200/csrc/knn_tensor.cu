@@ -654,28 +654,33 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, long long row, 
         }
         __syncwarp();
         const float4 *xig = reinterpret_cast<const float4 *>(P.xt + (size_t)row * C);
-        float4 xr[M];
-#pragma unroll
-        for (int m = 0; m < M; ++m) xr[m] = xig[4 * m + u];
         for (int t0 = 0; t0 < total; t0 += 8) {
             const int t = min(t0 + g, total - 1);
             const int j = (int)sj[t];
             const float4 *xj = reinterpret_cast<const float4 *>(P.xt + ((size_t)base + j) * C);
-            float4 q[M];
-#pragma unroll
-            for (int m = 0; m < M; ++m) q[m] = __ldg(xj + 4 * m + u);
             const float xxj = P.xx[base + j];
             float pa = 0.0f, pb = 0.0f;                // chains t = u and t = u + 4
+            // four float4 pieces of both rows at a time (C = 128: two rounds) keeps the kernel at 64 registers;
+            // each chain still sees its channels in ascending order
 #pragma unroll
-            for (int m = 0; m < M; m += 2) {
-                pa = __fmaf_rn(xr[m].x, q[m].x, pa);
-                pa = __fmaf_rn(xr[m].y, q[m].y, pa);
-                pa = __fmaf_rn(xr[m].z, q[m].z, pa);
-                pa = __fmaf_rn(xr[m].w, q[m].w, pa);
-                pb = __fmaf_rn(xr[m + 1].x, q[m + 1].x, pb);
-                pb = __fmaf_rn(xr[m + 1].y, q[m + 1].y, pb);
-                pb = __fmaf_rn(xr[m + 1].z, q[m + 1].z, pb);
-                pb = __fmaf_rn(xr[m + 1].w, q[m + 1].w, pb);
+            for (int m0 = 0; m0 < M; m0 += 4) {
+                float4 xr[4], q[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    xr[m] = __ldg(xig + 4 * (m0 + m) + u);
+                    q[m] = __ldg(xj + 4 * (m0 + m) + u);
+                }
+#pragma unroll
+                for (int m = 0; m < 4; m += 2) {
+                    pa = __fmaf_rn(xr[m].x, q[m].x, pa);
+                    pa = __fmaf_rn(xr[m].y, q[m].y, pa);
+                    pa = __fmaf_rn(xr[m].z, q[m].z, pa);
+                    pa = __fmaf_rn(xr[m].w, q[m].w, pa);
+                    pb = __fmaf_rn(xr[m + 1].x, q[m + 1].x, pb);
+                    pb = __fmaf_rn(xr[m + 1].y, q[m + 1].y, pb);
+                    pb = __fmaf_rn(xr[m + 1].z, q[m + 1].z, pb);
+                    pb = __fmaf_rn(xr[m + 1].w, q[m + 1].w, pb);
+                }
             }
             float acc = __fadd_rn(pa, pb);                                        // q_u = p_u + p_{u+4}
             acc = __fadd_rn(acc, __shfl_xor_sync(MLSP_FULL, acc, 2));             // q0+q2 | q1+q3
@@ -728,7 +733,7 @@ __device__ __noinline__ void knn_row_exact(const float *__restrict__ xt, const f
 }
 
 template <int NG, int C>
-__global__ void __launch_bounds__(32 * RF_WARPS)
+__global__ void __launch_bounds__(32 * RF_WARPS, 4)   // <= 64 registers: four CTAs per SM
 knn_refine_kernel(KtParams P, long long total_rows)
 {
     constexpr int CAP = 2 * NG;
