@@ -1,6 +1,6 @@
 """oracle/ref_torch.py -- TEST INFRASTRUCTURE (see oracle/__init__.py).
 
-Pure-torch CPU port of the reference's hot-path functions that keeps the reference's *op composition*
+Pure-torch port of the reference's hot-path functions that keeps the reference's *op composition*
 (what it costs on a CPU is the same work: a (B,N,N) sgemm + topk, advanced-index gather + repeat + cat,
 the python FPS loop, the two (B,N,N,3) repeats of the Chamfer, 27 masked assignments ...).  It exists
 because the Python reference at /root/reference cannot travel to the GPU box: `bench.py --impl reference`
@@ -9,6 +9,10 @@ goldens in tests/test_oracle_golden.py::test_ref_torch_*.
 
 The two python-pcl pieces (cardinality, normals) are timed through dense-torch restatements and labelled
 as such by bench.py (the reference's kd-tree code is not runnable anywhere we can reach).
+
+Device-agnostic like the reference itself (tensors are created on the input's device): bench.py also times
+this composition on the GPU it benchmarks (`torch_gpu_reference`: what a user of the reference gets from
+torch's CUDA kernels on the same B200), next to the CPU baseline.
 """
 from __future__ import annotations
 
@@ -30,7 +34,7 @@ def get_graph_feature(x, k=20, idx=None):
     x = x.view(B, -1, N)
     if idx is None:
         idx = knn(x, k)
-    flat = (idx + torch.arange(B).view(-1, 1, 1) * N).view(-1)
+    flat = (idx + torch.arange(B, device=x.device).view(-1, 1, 1) * N).view(-1)
     C = x.size(1)
     pts = x.transpose(2, 1).contiguous()
     nbr = pts.view(B * N, -1)[flat, :].view(B, N, k, C)
@@ -41,11 +45,12 @@ def get_graph_feature(x, k=20, idx=None):
 def farthest_point_sample(xyz, npoint):
     """utils/pc_utils.py:137-161 (python loop of npoint rounds)."""
     B, C, N = xyz.shape
-    chosen = torch.zeros(B, npoint, dtype=torch.long)
-    vals = torch.zeros(B, C, npoint)
-    mind = torch.full((B, N), 1e10)
-    far = torch.randint(0, N, (B,), dtype=torch.long)
-    rows = torch.arange(B)
+    dev = xyz.device
+    chosen = torch.zeros(B, npoint, dtype=torch.long, device=dev)
+    vals = torch.zeros(B, C, npoint, device=dev)
+    mind = torch.full((B, N), 1e10, device=dev)
+    far = torch.randint(0, N, (B,), dtype=torch.long).to(dev)      # CPU generator, like utils/pc_utils.py:150
+    rows = torch.arange(B, device=dev)
     for s in range(npoint):
         chosen[:, s] = far
         c = xyz[rows, :, far].view(B, 3, 1)
@@ -62,7 +67,7 @@ def assign_region_to_point(X):
     n, d = 3, 2 / 3
     Xc = torch.clamp(X, -0.99999999, 0.99999999)
     B, _, N = X.shape
-    Y = torch.zeros((B, N), dtype=torch.long)
+    Y = torch.zeros((B, N), dtype=torch.long, device=X.device)
     rid = 0
     for ix in range(n):
         for iy in range(n):
@@ -89,7 +94,7 @@ def deform_input(X, lookup, min_pts=40):
                 mask[b, :3, ind] = 1
                 n = int(torch.sum(ind).cpu().numpy())
                 pts = np.random.multivariate_normal(mean, np.eye(3) * 0.001, n).T
-                X[b, :3, ind] = torch.tensor(pts, dtype=torch.float)
+                X[b, :3, ind] = torch.tensor(pts, dtype=torch.float).to(X.device)
                 break
     return X, mask
 
@@ -123,7 +128,7 @@ def cal_density_dense(pts, radius, num_cls, pergroup=2, shift=0, K=100):
     row = (cnt - shift).clamp(0, (num_cls - 1) * pergroup)
     lo = torch.div(row, pergroup, rounding_mode="floor")
     hi = torch.div(row + pergroup - 1, pergroup, rounding_mode="floor")
-    eye = torch.eye(num_cls)
+    eye = torch.eye(num_cls, device=pts.device)
     return (eye[lo] + eye[hi]) / 2, row
 
 
@@ -131,24 +136,26 @@ def normals_dense(pts, near):
     """Dense-torch RESTATEMENT of kSearchNormalEstimation PointDA/trainer.py:173-188 (python-pcl)."""
     idx = knn(pts.transpose(1, 2).contiguous(), near)
     B, N, _ = pts.shape
-    nb = pts[torch.arange(B).view(-1, 1, 1), idx]
+    nb = pts[torch.arange(B, device=pts.device).view(-1, 1, 1), idx]
     d = nb - nb.mean(dim=2, keepdim=True)
     cov = torch.einsum("bnki,bnkj->bnij", d, d) / near
-    _, v = torch.linalg.eigh(cov)
-    n = v[..., 0]
+    # chunks of 8192 matrices: cusolver's batched syev (torch 2.11 on CUDA) rejects larger batches
+    v = torch.cat([torch.linalg.eigh(c)[1] for c in cov.reshape(-1, 3, 3).split(8192)], dim=0)
+    n = v[..., 0].reshape(B, N, 3)
     flip = (n * pts).sum(-1, keepdim=True) > 0
     return torch.where(flip, -n, n)
 
 
-def hot_path_step(clouds, feats, grads, pred, lookup, k=20, radius=0.13, num_cls=16, near=20, fps_split=(512, 512)):
-    """One pass of the MLSP hot path over a batch, CPU torch, same op list as bench.py's GPU step.
+def hot_path_step(clouds, feats, grads, pred, lookup, k=20, radius=0.13, num_cls=16, near=20, fps_split=(512, 512),
+                  pergroup=2, shift=0):
+    """One pass of the MLSP hot path over a batch in plain torch (on the tensors' device), same op list as bench.py's step.
     clouds (B,3,N); feats: list of (B,C,N) layer inputs; grads: list of upstream grads (B,2C,N,k) or None."""
     pts = clouds.permute(0, 2, 1).contiguous()
     # target builder
     for n in fps_split:
         farthest_point_sample(clouds, n)
     normals_dense(pts, near)
-    cal_density_dense(pts, radius, num_cls)
+    cal_density_dense(pts, radius, num_cls, pergroup, shift)
     gold = clouds.clone()
     X, mask = deform_input(clouds.clone(), lookup)
     # neighbourhood engine, forward + backward of the edge gather
