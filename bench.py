@@ -234,13 +234,21 @@ class GraphedStep:
             for li in [0] + list(range(2, len(feats))):
                 self.launches += _layer(M, off, feats[li], dev["grads"][li], k)
         self.gT = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.clouds.device)
         with torch.cuda.graph(self.gT):
+            # the FPS calls are independent of each other and of the normals / cardinality (PCM samples two point sets,
+            # MLSP/PCM.py:29-30): each is one CTA per cloud for ~100-250 us, so the graph forks them onto a second branch
+            cap = torch.cuda.current_stream()
             self.start_dev.copy_(self.start_host, non_blocking=True)
-            for i, n in enumerate(FPS_SPLIT):
+            side.wait_stream(cap)
+            with torch.cuda.stream(side):
+                M.fps_from_start(self.clouds, FPS_SPLIT[0], self.start_dev[0])
+            for i, n in list(enumerate(FPS_SPLIT))[1:]:
                 M.fps_from_start(self.clouds, n, self.start_dev[i])
             pts = self.clouds.permute(0, 2, 1).contiguous()
             M.estimate_normals(pts, NEAR)
             M.cal_density(pts, RADIUS, NUM_CLS, PERGROUP, SHIFT)
+            cap.wait_stream(side)
         self.launches += LAUNCHES["fps"] * len(FPS_SPLIT) + LAUNCHES["knn3"] + LAUNCHES["normals"] + LAUNCHES["density"]
         self.gB = torch.cuda.CUDAGraph()
         self.X.copy_(self.clouds)

@@ -1,0 +1,53 @@
+"""CPU checks of bench.py's bookkeeping: the SURVEY.md section 8(d) work formulas, the per-workload step
+definitions, the peak table, and the reference arm's JSON line (rank > 0 prints nothing)."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bench():
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_algorithmic_work_matches_survey(bench):
+    B, N, k = 32, 1024, 20                                             # config A, SURVEY.md section 8(d)
+    assert bench.algorithmic_bytes("edge_fwd_C64", B, N, k) == pytest.approx(349.2e6, rel=1e-3)
+    assert bench.algorithmic_bytes("edge_bwd_C128", B, N, k) == pytest.approx(693.1e6, rel=1e-3)
+    assert bench.algorithmic_bytes("edge_fwd_C3", B, N, k) == pytest.approx(21.4e6, rel=5e-3)
+    assert bench.algorithmic_flops("knn_C64", B, N, k) == pytest.approx(4.40e9, rel=2e-3)
+    assert bench.algorithmic_flops("knn_C128", B, N, k) == pytest.approx(8.69e9, rel=2e-3)
+    assert bench.algorithmic_bytes("knn_C64", B, N, k) == pytest.approx(13.6e6, rel=5e-3)
+    assert bench.algorithmic_bytes("chamfer_fwd", B, N, k) is None     # no work model: never the roofline kernel
+
+
+def test_workloads(bench):
+    a, s = bench.WORKLOADS["A"], bench.WORKLOADS["S"]
+    assert a["layers"] == (3, 3, 64, 64, 128) and a["near"] == 20 and sum(a["fps_split"]) == 1024   # PointDA-10
+    assert s["layers"] == (3, 3, 64, 64) and s["near"] == 10 and sum(s["fps_split"]) == 2048        # PointSegDA
+    bench.set_workload("S")
+    assert bench.LAYER_CHANNELS == s["layers"] and bench.SHIFT == 10 and bench.PERGROUP == 5
+    bench.set_workload("A")
+    assert bench.LAYER_CHANNELS == a["layers"] and bench.RADIUS == 0.13
+
+
+def test_peaks_table(bench):
+    p = bench.peaks()
+    assert 5000 < p["hbm_gbs"] < 8100 and 1000 < p["bf16_tflops"] < 2300 and p["source"] in ("measured", "fallback")
+
+
+def test_reference_arm_line():
+    """`bench.py --impl reference` prints one JSON line with the contract's keys on rank 0 and nothing on other ranks."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
