@@ -64,7 +64,8 @@ MLSP_API int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t *i
                  int flags, void *stream);
 
 /* Test hook for the tcgen05 path of a1 (C in {64,128}, N >= 256): same result as mlsp_knn_f32, and when
- * `dump` is non-NULL the approximate filter values |x_j|^2 - 2 dot~(x_i,x_j) are written to dump (B,N,N).
+ * `dump` is non-NULL the approximate filter values |x_j|^2 - 2 dot~(x_i,x_j) are written to dump (2,B,N,N):
+ * [0] = pass 1 (bf16 heads only, sets the threshold), [1] = pass 2 (three-term split, the listed values).
  * After the call ws holds two int32 counters at offset 0: {rows re-done by the exact streaming selection, rows certified}. */
 MLSP_API int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
                                    float *dump, void *stream);
@@ -124,6 +125,13 @@ MLSP_API int mlsp_ball_mask_scatter(float *X, int B, int C, int N, float r2, con
  *   pts (B,N,3); labels (B,N,num_cls) float32; row (B,N) int64 = clip(count-shift, 0, (num_cls-1)*pergroup). */
 MLSP_API int mlsp_ball_count_labels(const float *pts, int B, int N, float r2, int K, int shift, int pergroup,
                            int num_cls, float *labels, int64_t *row, void *stream);
+
+/* a6, list form -- pcl KdTreeFLANN.radius_search_for_cloud(cloud, radius, K) as called at MLSP/mlsp.py:250 (python-pcl;
+ *   the `pcl` shim of mlsp_b200/pcl_shim.py binds it): per point the neighbours with squared distance < r2, nearest first
+ *   (ties by lowest index), at most K (<= 128) of them; unused slots are 0 in both outputs, so `(ind != 0).sum(1)` is the
+ *   reference's count.  pts (B,N,3); ind (B,N,K) int32; sqdist (B,N,K) float32. */
+MLSP_API int mlsp_radius_search(const float *pts, int B, int N, float r2, int K, int32_t *ind, float *sqdist,
+                                void *stream);
 
 /* a7 -- kSearchNormalEstimation (PointDA/trainer.py:173-188, PointSegDA/trainer.py:73-88; python-pcl):
  *   unit eigenvector of the smallest eigenvalue of the covariance of the k nearest neighbours (idx from

@@ -22,6 +22,7 @@ from .ops import (  # noqa: F401
     get_graph_feature,
     knn,
     knn_tensor_debug,
+    radius_search,
     reconstruction_loss,
     region_mean,
 )

@@ -9,6 +9,8 @@
 // Backward: one pass over grad_out accumulates the centre terms in registers and scatters the
 // neighbour terms with vector float atomics into gxt (B,N,C) in L2, then a transpose back to (B,C,N).
 // C = 3 (the two 3-D layers) has its own forward (no transposed copy at all) and backward (padded scratch).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mlsp {
@@ -21,7 +23,11 @@ size_t edge_workspace_bytes(int B, int C, int N, int k)
 
 size_t knn_workspace_bytes(int B, int C, int N, int k);
 bool knn_tensor_supported(int B, int C, int N, int k);
+bool knn3_supported(int C, int N, int k);
+int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, float *edge_out, cudaStream_t st);
 const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k);
+int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
+                   cudaStream_t st);
 
 size_t graph_feature_workspace_bytes(int B, int C, int N, int k)
 {
@@ -388,10 +394,22 @@ extern "C" int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k
     using namespace mlsp;
     MLSP_REQUIRE(x && idx && out && ws, MLSP_EINVAL, "graph_feature_fwd: null pointer");
     MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "graph_feature_fwd: bad shape");
+    MLSP_REQUIRE(k <= N, MLSP_EINVAL, "graph_feature_fwd: k=%d out of range for N=%d", k, N);
     MLSP_REQUIRE(ws_bytes >= graph_feature_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "graph_feature_fwd: workspace too small");
+    if (knn_tensor_supported(B, C, N, k) && k <= 64) {
+        // tcgen05 path: the refine kernel that ranks a row also writes its edge features (no separate gather launch,
+        // idx is not read back).  MLSP_GGF_FUSED=0 (tuning hook) keeps the two-kernel form.
+        const bool fused = !(getenv("MLSP_GGF_FUSED") && atoi(getenv("MLSP_GGF_FUSED")) == 0);
+        int rc = knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, fused ? out : nullptr, as_stream(stream));
+        if (rc || fused) return rc;
+        return launch_edge_fwd_vec(knn_tensor_xt(ws, B, C, N, k), idx, B, C, N, k, out, as_stream(stream));
+    }
+    if (knn3_supported(C, N, k) && B <= 65535 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+        // 3-D clouds: the two-pass kernel that ranks a row also writes its k x 6 edge features from the staged cloud
+        const bool fused = !(getenv("MLSP_GGF_FUSED") && atoi(getenv("MLSP_GGF_FUSED")) == 0);
+        if (fused) return knn3_run(x, B, N, k, idx, static_cast<int *>(ws), out, as_stream(stream));
+    }
     int rc = mlsp_knn_f32(x, B, C, N, k, idx, ws, ws_bytes, MLSP_KNN_AUTO, stream);
     if (rc) return rc;
-    if (knn_tensor_supported(B, C, N, k) && C % 4 == 0)
-        return launch_edge_fwd_vec(knn_tensor_xt(ws, B, C, N, k), idx, B, C, N, k, out, as_stream(stream));
     return mlsp_edge_gather_fwd(x, idx, B, C, N, k, out, ws, ws_bytes, stream);   // stream order: the kNN is done with ws
 }

@@ -20,9 +20,10 @@ constexpr size_t KNN_WS_HEADER = 256;                     // stats live in the f
 
 bool knn_tensor_supported(int B, int C, int N, int k);
 size_t knn_tensor_workspace_bytes(int B, int C, int N, int k);
-int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, cudaStream_t st);
+int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
+                   cudaStream_t st);
 bool knn3_supported(int C, int N, int k);
-int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, cudaStream_t st);
+int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, float *edge_out, cudaStream_t st);
 
 size_t knn_workspace_bytes(int B, int C, int N, int k)
 {
@@ -194,8 +195,8 @@ extern "C" int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t 
     const bool tensor_ok = knn_tensor_supported(B, C, N, k);
     MLSP_REQUIRE(flags != MLSP_KNN_TENSOR_ONLY || tensor_ok, MLSP_EUNSUPPORTED,
                  "knn: tensor path not available for B=%d C=%d N=%d k=%d", B, C, N, k);
-    if (tensor_ok && flags != MLSP_KNN_EXACT_ONLY) return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, st);
-    if (flags != MLSP_KNN_EXACT_ONLY && knn3_supported(C, N, k)) return knn3_run(x, B, N, k, idx, static_cast<int *>(ws), st);
+    if (tensor_ok && flags != MLSP_KNN_EXACT_ONLY) return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, nullptr, st);
+    if (flags != MLSP_KNN_EXACT_ONLY && knn3_supported(C, N, k)) return knn3_run(x, B, N, k, idx, static_cast<int *>(ws), nullptr, st);
     MLSP_CUDA(cudaMemsetAsync(ws, 0, KNN_WS_HEADER, st));
     float *xx = reinterpret_cast<float *>(static_cast<char *>(ws) + KNN_WS_HEADER);
     sq_norms_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, C, N, xx);
@@ -212,5 +213,5 @@ extern "C" int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k,
     MLSP_REQUIRE(k >= 1 && k <= N, MLSP_EINVAL, "knn_tensor_debug: k out of range");
     MLSP_REQUIRE(knn_tensor_supported(B, C, N, k), MLSP_EUNSUPPORTED, "knn_tensor_debug: shape not supported");
     MLSP_REQUIRE(ws_bytes >= knn_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "knn_tensor_debug: workspace too small");
-    return knn_tensor_run(x, B, C, N, k, idx, ws, dump, as_stream(stream));
+    return knn_tensor_run(x, B, C, N, k, idx, ws, dump, nullptr, as_stream(stream));
 }

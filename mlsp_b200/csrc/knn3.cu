@@ -66,12 +66,39 @@ __device__ __forceinline__ void warp_sort_desc_u32(uint32_t (&key)[NC])
     }
 }
 
+// a2 fused (get_graph_feature with idx=None on a 3-D cloud): the warp that ranked row i writes the row's k x 6 edge
+// features [x_j - x_i | x_i] as 3k float2 (d0 d1 | d2 c0 | c1 c2 per neighbour), consecutive lanes -> consecutive
+// float2, neighbours read from the staged cloud.  nbr[s] on lane l = the neighbour of rank s*32 + l.
+template <int SL>
+__device__ __forceinline__ void edge_row3(float2 *__restrict__ orow, float4 ctr, const float4 *cloud, const uint32_t (&nbr)[SL],
+                                          int k, int N)
+{
+    const int lane = lane_id();
+    for (int t0 = 0; t0 < 3 * k; t0 += 32) {
+        const int t = t0 + lane;
+        const int e = min(t / 3, k - 1), part = t - 3 * (t / 3);
+        uint32_t n = 0;
+#pragma unroll
+        for (int s = 0; s < SL; ++s) {
+            const uint32_t v = __shfl_sync(MLSP_FULL, nbr[s], e & 31);
+            if ((e >> 5) == s) n = v;
+        }
+        const float4 q = cloud[min(n, (uint32_t)(N - 1))];
+        float2 o;
+        if (part == 0) o = make_float2(__fsub_rn(q.x, ctr.x), __fsub_rn(q.y, ctr.y));
+        else if (part == 1) o = make_float2(__fsub_rn(q.z, ctr.z), ctr.x);
+        else o = make_float2(ctr.y, ctr.z);
+        if (t < 3 * k) __stcs(orow + t, o);
+    }
+}
+
 // NC = classes per lane (class of candidate j = (j / 32) mod NC, j mod 32): 32*NC classes.  More classes than k
 // tighten tau: the expected list length is sum_{i<k} M/(M-i) for M classes (23.7 for k = 20, M = 64; 47.7 for
 // k = 40, M = 128), so the final sort usually runs on HALF the capacity CAPL = 32*NC.
 template <int NC>
 __global__ void __launch_bounds__(K3_THREADS)
-knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx, int *__restrict__ stats)
+knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx, int *__restrict__ stats,
+            float2 *__restrict__ edge_out)
 {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) stats[threadIdx.x] = 0;   // {fallback rows, certified rows}: tensor path only
     constexpr int CAPL = 32 * NC;
@@ -212,6 +239,12 @@ knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx
                 const int e = s * 32 + lane;
                 if (e < k) out[e] = (int64_t)(uint32_t)(key[s] & 0xffffffffull);
             }
+            if (edge_out) {
+                uint32_t nbr[(SL + 1) / 2];                               // k <= 16 NC: the ranked neighbours sit in the lower slots
+#pragma unroll
+                for (int s = 0; s < (SL + 1) / 2; ++s) nbr[s] = (uint32_t)(key[s] & 0xffffffffull);
+                edge_row3<(SL + 1) / 2>(edge_out + ((size_t)b * N + i) * k * 3, xi[rr], cloud, nbr, k, N);
+            }
         } else {
             TopK<(SL + 1) / 2> top;
             top.init(k);
@@ -226,23 +259,30 @@ knn3_kernel(const float *__restrict__ x, int N, int k, int64_t *__restrict__ idx
                 const int e = s * 32 + lane;
                 if (e < k) out[e] = (int64_t)top.j[s];
             }
+            if (edge_out) {
+                uint32_t nbr[(SL + 1) / 2];
+#pragma unroll
+                for (int s = 0; s < (SL + 1) / 2; ++s) nbr[s] = (uint32_t)top.j[s];
+                edge_row3<(SL + 1) / 2>(edge_out + ((size_t)b * N + i) * k * 3, xi[rr], cloud, nbr, k, N);
+            }
         }
     }
 }
 
 bool knn3_supported(int C, int N, int k) { return C == 3 && k <= 64 && N >= 1 && N <= 8192; }
 
-int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, cudaStream_t st)
+int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, float *edge_out, cudaStream_t st)
 {
+    float2 *eo = reinterpret_cast<float2 *>(edge_out);                  // (B,N,k,6) floats: rows are 8-byte aligned
     const int NC = (k <= 32) ? 2 : 4;                                  // 64 / 128 classes
     const size_t smem = sizeof(float4) * (size_t)N + sizeof(uint16_t) * (size_t)(K3_THREADS / 32) * K3_R * 32 * NC;
     dim3 grid((N + K3_ROWS - 1) / K3_ROWS, B);
     if (NC == 2) {
         MLSP_CUDA(cudaFuncSetAttribute(knn3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn3_kernel<2><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx, stats);
+        knn3_kernel<2><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx, stats, eo);
     } else {
         MLSP_CUDA(cudaFuncSetAttribute(knn3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn3_kernel<4><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx, stats);
+        knn3_kernel<4><<<grid, K3_THREADS, smem, st>>>(x, N, k, idx, stats, eo);
     }
     MLSP_LAUNCH_CHECK("knn3_kernel");
     return MLSP_OK;

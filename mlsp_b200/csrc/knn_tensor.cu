@@ -46,6 +46,10 @@ constexpr uint32_t KT_BLK_BYTES = KT_COLS * KT_KBLK * 2;  // 16 KiB per (128 x 6
 // dot product (Cauchy-Schwarz), i.e. 9.2e-5 on v; 2^-12 = 2.4e-4 leaves > 2.5x for the tensor core's fp32
 // accumulation and the specification's own roundings.  Measured worst case: 0.12 of this bound (tests).
 constexpr float KT_EPS_REL = 2.44140625e-4f;
+// Pass 1 multiplies the bf16 heads only (dot~1 = hi.hi): x = hi + r with |r_c| <= 2^-9 |x_c|, so
+// |hi_i.hi_j - x_i.x_j| <= (2^-8 + 2^-17 + 2^-18) |x_i||x_j| and the pass-1 value v1 = |x_j|^2 - 2 dot~1 is within
+// KT_EPS1_REL |x_i||x_j| (= 2^-7 + 2^-14) of the three-term value; tau1 + eps1 still upper-bounds the k-th distance.
+constexpr float KT_EPS1_REL = 0.00787353515625f;
 
 // ---------------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -355,10 +359,11 @@ struct KtParams {
     int *stats;              // rows certified by the tensor path
     uint2 *cand;             // (B*N, CAP) candidate lists (v bits, j): main kernel -> refine kernel
     int *cand_cnt;           // (B*N, 2) entries written from the front / from the back (> CAP: overflowed)
-    float *dump;             // optional (B,N,N) approximate values (tests only)
+    float *dump;             // optional (2,B,N,N) filter values of pass 1 and pass 2 (tests only)
+    float4 *edge_out;        // optional (B,N,k,2C): the refine kernel also writes the row's edge features (a2 fused)
     int N, C, k, T;          // T = candidate tiles per cloud
     int stages;              // depth of the B-operand smem ring
-    int mode;                // tuning hook (MLSP_KT_MODE): bit 0 skips the pass-1 math, bit 1 the pass-2 math
+    int mode;                // tuning hook (MLSP_KT_MODE): bit 0 skips the pass-1 math, bit 1 the pass-2 math, bit 2: three-term pass 1
 };
 
 // ------------------------------------------------------------------------------------------- main kernel
@@ -429,7 +434,8 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             uint32_t ph = 0;
             for (int g = 0; g < 2 * T; ++g) {
                 const int j0 = (g % T) * KT_COLS;
-                for (int kb = 0; kb < KB; ++kb) {   // B blocks: hi ..., lo ...
+                const int nkb = (g < T && !(P.mode & 4)) ? SEG : KB;  // pass 1 multiplies hi.hi only: no lo blocks
+                for (int kb = 0; kb < nkb; ++kb) {   // B blocks: hi ..., lo ...
                     mbar_wait(empty + stage, ph ^ 1);
                     mbar_expect_tx(full + stage, KT_BLK_BYTES);
                     tma_load_2d(sB + (size_t)stage * KT_BLK_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
@@ -450,7 +456,9 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 mbar_wait(tm_empty + buf, ((g >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)buf * KT_COLS;
-                for (int kb = 0; kb < KB; ++kb) {
+                const bool first = g < T && !(P.mode & 4);          // pass 1: dot~ = hi.hi (a looser, cheaper bound)
+                const int nkb = first ? SEG : KB;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(full + stage, ph);
                     tc_fence_after();
                     const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * KT_BLK_BYTES));
@@ -459,7 +467,7 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 #pragma unroll
                     for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)   // +32 bytes per K=16 step inside the swizzle span
                         tc_mma_bf16(d, da_hi + 2 * k16, db + 2 * k16, KT_IDESC, (kb | k16) != 0);   // hi.hi | hi.lo
-                    if (kb < SEG) {                                 // a B_hi block also meets A_lo:  lo.hi
+                    if (kb < SEG && !first) {                       // pass 2: a B_hi block also meets A_lo:  lo.hi
                         const uint64_t da_lo = umma_desc_sw128(smem_u32(sA + (size_t)(SEG + ka) * KT_BLK_BYTES));
 #pragma unroll
                         for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)
@@ -539,11 +547,13 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         if (h == 0) {
             const float maxxx = __uint_as_float(max(max(max_s[0], max_s[1]), max(max_s[2], max_s[3])));
             const float eps = pair_eps(sqrtf(xxi), xxi, maxxx);   // bound for every candidate of the cloud
+            // pass 1 saw dot~ = hi.hi only: |v1 - v| <= KT_EPS1_REL |x_i| max_j |x_j|
+            const float eps1 = (P.mode & 4) ? 0.0f : KT_EPS1_REL * sqrtf(xxi) * sqrtf(maxxx);
             float tau = -INFINITY;
 #pragma unroll
             for (int e = 0; e < NG; ++e)
                 if (e < P.k) tau = fmaxf(tau, fminf(gmin[e], xchg[(P.k - 1 - e) * KT_ROWS + r]));
-            thr_s[r] = tau + 2.0f * eps;
+            thr_s[r] = tau + eps1 + 2.0f * eps;
         }
         epi_bar_sync();
         const float thr = (i < N) ? thr_s[r] : -INFINITY;    // rows beyond the cloud collect nothing
@@ -558,6 +568,8 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             tc_fence_after();
             if (!(P.mode & 2)) epi_tile<NG, 2>(gmin, cur, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, thr,
                             (uint32_t)((g - T) * KT_COLS + h * 64));
+            if (P.dump) dump_tile(P.dump + ((size_t)gridDim.y * N + rowbase + min(i, N - 1)) * N, i < N, tlane + (uint32_t)buf * KT_COLS,
+                                  nrm_s + buf * KT_COLS + h * 64, (g - T) * KT_COLS + h * 64, N);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + buf);
@@ -588,18 +600,30 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 // sort on (cluster start, exact value desc, index asc) then gives the specification's order.
 constexpr int RF_WARPS = 8;
 
-template <int S, int C>
-__device__ __forceinline__ void refine_sorted(const KtParams &P, long long row, unsigned long long (&key)[S],
-                                              uint16_t *sj, float *se)
+// Keys arrive as (orderable v~ << 32 | j << 16 | list slot): the slot names where the candidate's norm |x_j|^2 --
+// fetched before the sort, so that its L2 latency hides behind the sorting network -- waits in shared memory.
+template <int S, int C, int KS>
+__device__ __forceinline__ void refine_sorted(const KtParams &P, uint32_t row, uint32_t base, unsigned long long (&key)[S],
+                                              const float (&xpre)[S], uint16_t *sj, float *se, uint32_t (&nbr)[KS])
 {
     constexpr int M = C / 16;                             // float4 pieces per lane: 4 (C = 64) or 8 (C = 128)
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, u = lane & 3;
     const int k = P.k;
-    const long long base = (row / P.N) * P.N;
     const float xxi = P.xx[row];
     const float ni = sqrtf(xxi);
     warp_sort_u64<S>(key);
+#pragma unroll
+    for (int s = 0; s < S; ++s) se[s * 32 + lane] = xpre[s];             // norms by list slot
+    __syncwarp();
+    float xs[S];                                                         // |x_j|^2 of the candidate now at (s, lane)
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint32_t low = (uint32_t)key[s];
+        const bool live = key[s] != ~0ull;
+        xs[s] = live ? se[low & 0xffffu] : 0.0f;
+        if (live) key[s] = (key[s] & 0xffffffff00000000ull) | (low >> 16);   // -> (orderable v~ << 32 | j)
+    }
     // ---- links, clusters
     float v[S], ej[S];
     bool link[S];
@@ -610,7 +634,7 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, long long row, 
         const bool live = key[s] != ~0ull;
         const uint32_t ob = (uint32_t)(key[s] >> 32);                    // f32_orderable(v~)
         v[s] = live ? __uint_as_float((ob & 0x80000000u) ? (ob ^ 0x80000000u) : ~ob) : INFINITY;
-        ej[s] = live ? pair_eps(ni, xxi, P.xx[base + ((uint32_t)key[s] & 0xffffu)]) : 0.0f;
+        ej[s] = live ? pair_eps(ni, xxi, xs[s]) : 0.0f;
         float prev = __shfl_up_sync(MLSP_FULL, v[s], 1), eprev = __shfl_up_sync(MLSP_FULL, ej[s], 1);
         if (s > 0) {
             const float last = __shfl_sync(MLSP_FULL, v[s - 1], 31), elast = __shfl_sync(MLSP_FULL, ej[s - 1], 31);
@@ -702,6 +726,71 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, long long row, 
     for (int s = 0; s < S; ++s) {
         const int e = s * 32 + lane;
         if (e < k) P.idx[(size_t)row * k + e] = (int64_t)((uint32_t)key[s] & 0xffffu);
+        if (s < KS) nbr[s] = (uint32_t)key[s] & 0xffffu;                  // rank e = s*32 + lane, for the fused gather
+    }
+}
+
+// a2 fused into the refine kernel (get_graph_feature with idx=None): the warp that ranked row i writes the row's
+// k x 2C edge features [x_j - x_i | x_i] straight away -- the latency-bound ranking of some warps overlaps the
+// write stream of others, and idx is not read back.  Same lane layout as edge_fwd_vec_kernel (edge.cu): lanes span
+// the 2C channels in float4, four neighbour rows in flight, evict-first 128-bit stores.  nbr[s] on lane l = the
+// neighbour of rank s*32 + l.
+template <int C, int KS>
+__device__ __forceinline__ void gather_row(const KtParams &P, uint32_t row, uint32_t base, const uint32_t (&nbr)[KS])
+{
+    constexpr int Q4 = C / 4, W = 2 * Q4;
+    const int lane = threadIdx.x & 31, k = P.k;
+    const float4 *xt4 = reinterpret_cast<const float4 *>(P.xt);
+    const float4 *xtb = xt4 + (size_t)base * Q4;
+    const float4 *ctr_row = xt4 + (size_t)row * Q4;
+    float4 *orow = P.edge_out + (size_t)row * k * W;
+#pragma unroll
+    for (int q0 = 0; q0 < W; q0 += 32) {
+        const int q = q0 + lane;
+        const bool is_diff = q < Q4;
+        const int qc = is_diff ? q : q - Q4;
+        const float4 ctr = __ldg(ctr_row + qc);
+        // neighbour rows of ranks j..j+3 (all lanes take part in the shuffles; j, k are warp-uniform)
+        auto load4 = [&](float4 (&nb)[4], int j) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                nb[u] = ctr;
+                if (q0 < Q4) {                                           // compile time: this pass holds difference lanes
+                    const int e = min(j + u, k - 1);
+                    uint32_t n = 0;
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        const uint32_t t = __shfl_sync(MLSP_FULL, nbr[s], e & 31);
+                        if ((e >> 5) == s) n = t;
+                    }
+                    if (is_diff) nb[u] = __ldg(xtb + (size_t)n * Q4 + qc);
+                }
+            }
+        };
+        auto store4 = [&](const float4 (&nb)[4], int j) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j + u < k) {
+                    float4 o = nb[u];
+                    if (is_diff) {
+                        o.x = __fsub_rn(o.x, ctr.x);
+                        o.y = __fsub_rn(o.y, ctr.y);
+                        o.z = __fsub_rn(o.z, ctr.z);
+                        o.w = __fsub_rn(o.w, ctr.w);
+                    }
+                    st_stream_f4(orow + (size_t)(j + u) * W + q, o);
+                }
+            }
+        };
+        // two groups of four rows in flight: the loads of one group are issued before the other group is stored
+        float4 ga[4], gb[4];
+        load4(ga, 0);
+        for (int j = 0; j < k; j += 8) {
+            if (j + 4 < k) load4(gb, j + 4);
+            store4(ga, j);
+            if (j + 8 < k) load4(ga, j + 8);
+            if (j + 4 < k) store4(gb, j + 4);
+        }
     }
 }
 
@@ -739,40 +828,80 @@ knn_refine_kernel(KtParams P, long long total_rows)
     constexpr int CAP = 2 * NG;
     constexpr int SLOTS = CAP / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long row = (long long)blockIdx.x * RF_WARPS + warp;   // b*N + i
-    if (row >= total_rows) return;
-    const int c0 = P.cand_cnt[2 * row], c1 = P.cand_cnt[2 * row + 1];
+    const long long row64 = (long long)blockIdx.x * RF_WARPS + warp;   // b*N + i
+    if (row64 >= total_rows) return;
+    const uint32_t row = (uint32_t)row64;                              // B*N < 2^31 (knn_tensor_supported)
+    const uint32_t base = row / (uint32_t)P.N * (uint32_t)P.N;         // first row of the cloud
+    // The two ends of the row's list are fetched SPECULATIVELY together with the two counters (one L2 round trip
+    // instead of two dependent ones): slot (h, lane) of the front end is valid iff h*32+lane < c0, of the back end iff
+    // h*32+lane < c1.  Counts above CAP/2 at one end (rare) re-read that end below.
+    constexpr int HS = CAP / 64;
+    const uint2 *list = P.cand + (size_t)row * CAP;
+    const int2 cc = *reinterpret_cast<const int2 *>(P.cand_cnt + 2 * (size_t)row);
+    uint2 fa[HS], fb[HS];
+#pragma unroll
+    for (int h = 0; h < HS; ++h) {
+        fa[h] = list[h * 32 + lane];
+        fb[h] = list[CAP - 1 - (h * 32 + lane)];
+    }
+    const int c0 = cc.x, c1 = cc.y;
     const int cnt = c0 + c1;
+    constexpr int KS = NG / 32;                            // slots holding the k <= NG ranked neighbours
+    uint32_t nbr[KS];
     if (c0 > CAP || c1 > CAP || cnt > CAP || cnt < P.k) {
-        knn_row_exact<NG / 32>(P.xt, P.xx, row, P.N, C, P.k, P.idx);   // warp-uniform
+        knn_row_exact<NG / 32>(P.xt, P.xx, row64, P.N, C, P.k, P.idx);   // warp-uniform
         if (lane == 0) atomicAdd(P.fb_count, 1);
+        if (P.edge_out) {
+            __syncwarp();                                  // the row's idx, written by this warp, is visible to it
+#pragma unroll
+            for (int s = 0; s < KS; ++s) nbr[s] = (s * 32 + lane < P.k) ? (uint32_t)P.idx[(size_t)row * P.k + s * 32 + lane] : 0u;
+            gather_row<C, KS>(P, row, base, nbr);
+        }
         return;
     }
     __shared__ uint16_t sj_all[RF_WARPS][CAP];
     __shared__ float se_all[RF_WARPS][CAP];
     uint16_t *sj = sj_all[warp];
     float *se = se_all[warp];
-    const uint2 *list = P.cand + (size_t)row * CAP;
+    __shared__ uint2 sc_all[RF_WARPS][CAP];
+    uint2 *sc = sc_all[warp];
+    if (c0 <= 32 * HS && c1 <= 32 * HS) {                  // warp-uniform: compact the two ends into list order
+#pragma unroll
+        for (int h = 0; h < HS; ++h) {
+            const int e = h * 32 + lane;
+            if (e < c0) sc[e] = fa[h];
+            if (e < c1) sc[c0 + e] = fb[h];
+        }
+    } else {
+        for (int e = lane; e < cnt; e += 32) sc[e] = list[e < c0 ? e : CAP - 1 - (e - c0)];
+    }
+    __syncwarp();
     unsigned long long key[SLOTS];
+    float xpre[SLOTS];
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
         const int e = s * 32 + lane;
         key[s] = ~0ull;
+        xpre[s] = 0.0f;
         if (e < cnt) {
-            const uint2 ent = list[e < c0 ? e : CAP - 1 - (e - c0)];
-            key[s] = ((unsigned long long)f32_orderable(__fadd_rn(__uint_as_float(ent.x), 0.0f)) << 32) | ent.y;
+            const uint2 ent = sc[e];
+            key[s] = ((unsigned long long)f32_orderable(__fadd_rn(__uint_as_float(ent.x), 0.0f)) << 32) | (ent.y << 16) | (uint32_t)e;
+            xpre[s] = P.xx[base + ent.y];                  // consumed after the sort
         }
     }
     if (cnt <= 32) {                                       // warp-uniform, the usual case for k <= 20
         unsigned long long k1[1] = {key[0]};
-        refine_sorted<1, C>(P, row, k1, sj, se);
+        const float x1[1] = {xpre[0]};
+        refine_sorted<1, C, KS>(P, row, base, k1, x1, sj, se, nbr);
     } else if (SLOTS > 2 && cnt <= 64) {
         unsigned long long k2[2] = {key[0], key[1]};
-        refine_sorted<2, C>(P, row, k2, sj, se);
+        const float x2[2] = {xpre[0], xpre[1]};
+        refine_sorted<2, C, KS>(P, row, base, k2, x2, sj, se, nbr);
     } else {
-        refine_sorted<SLOTS, C>(P, row, key, sj, se);
+        refine_sorted<SLOTS, C, KS>(P, row, base, key, xpre, sj, se, nbr);
     }
     if (lane == 0) atomicAdd(P.stats, 1);
+    if (P.edge_out) gather_row<C, KS>(P, row, base, nbr);
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -841,7 +970,8 @@ const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k)
     return reinterpret_cast<const float *>(static_cast<const char *>(ws) + kt_layout(B, C, N, k).off_xt);
 }
 
-int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, cudaStream_t st)
+int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
+                   cudaStream_t st)
 {
     const KtLayout L = kt_layout(B, C, N, k);
     char *w = static_cast<char *>(ws);
@@ -863,7 +993,7 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
 
     KtParams P;
     P.xx = xx; P.xt = xt; P.idx = idx; P.fb_count = counters;
-    P.stats = counters + 1; P.dump = dump;
+    P.stats = counters + 1; P.dump = dump; P.edge_out = reinterpret_cast<float4 *>(edge_out);
     P.cand = reinterpret_cast<uint2 *>(w + L.off_cand); P.cand_cnt = reinterpret_cast<int *>(w + L.off_cnt); P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS;
     const int NG = (k <= 32) ? 32 : 64;
     // ring depth: as deep as two CTAs per SM allow (NG = 32), else one CTA per SM with up to 8 stages

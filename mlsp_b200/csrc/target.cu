@@ -7,6 +7,7 @@
 // Arithmetic pinned to oracle/mlsp_oracle.c and oracle/np_ops.py.  All of these move a few hundred KB
 // at the PointDA shape, so each is a single launch with the cloud staged once in shared memory.
 #include "common.cuh"
+#include "topk.cuh"
 
 namespace mlsp {
 
@@ -248,6 +249,49 @@ ball_count_labels_kernel(const float *__restrict__ pts, int N, float r2, int K, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// a6, list form: python-pcl KdTreeFLANN.radius_search_for_cloud(cloud, r, K) (MLSP/mlsp.py:250), restated
+// like the count above: for every point the neighbours with d < r2, nearest first (ties by lowest index),
+// at most K of them, rows zero-padded.  One warp per query row: the in-ball points enter the streaming
+// selection of topk.cuh (value -d, so "largest" = nearest), which keeps the K nearest; distances of the
+// kept entries are recomputed with the same pinned expression.
+template <int KSLOTS>
+__global__ void __launch_bounds__(BALL_THREADS)
+radius_search_kernel(const float *__restrict__ pts, int N, float r2, int K, int32_t *__restrict__ ind,
+                     float *__restrict__ sqd)
+{
+    extern __shared__ float4 cloud[];
+    const int b = blockIdx.y;
+    const float *P = pts + (size_t)b * N * 3;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) cloud[n] = make_float4(P[3 * n], P[3 * n + 1], P[3 * n + 2], 0.f);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = blockIdx.x * BALL_ROWS + warp * BALL_ROWS_PER_WARP;
+    for (int r = 0; r < BALL_ROWS_PER_WARP; ++r) {
+        const int i = i0 + r;
+        if (i >= N) break;                                   // warp-uniform
+        const float4 pi = cloud[i];
+        TopK<KSLOTS> top;
+        top.init(K);
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int j = j0 + lane;
+            const float d = (j < N) ? direct_d2(pi, cloud[j]) : INFINITY;
+            top.offer(-d, j, d < r2);
+        }
+        top.finish(K);
+#pragma unroll
+        for (int s = 0; s < KSLOTS; ++s) {
+            const int e = s * 32 + lane;
+            if (e >= K) continue;
+            const int j = top.j[s];
+            const bool hit = j >= 0 && j < N;                // unfilled slots keep their huge placeholder index
+            const size_t o = ((size_t)b * N + i) * K + e;
+            ind[o] = hit ? j : 0;
+            sqd[o] = hit ? direct_d2(pi, cloud[j]) : 0.0f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // a7: PCA normals.  One thread per point, fp64 covariance about the neighbourhood mean and a cyclic
 // Jacobi eigen-solve of the symmetric 3x3 (robust for the near-degenerate planar patches of CAD scans).
 __device__ __forceinline__ void jacobi_rotate(double &app, double &aqq, double &apq, double &arp, double &arq,
@@ -399,6 +443,29 @@ extern "C" int mlsp_ball_count_labels(const float *pts, int B, int N, float r2, 
     ball_count_labels_kernel<<<dim3((N + BALL_ROWS - 1) / BALL_ROWS, B), BALL_THREADS, smem, as_stream(stream)>>>(
         pts, N, r2, K, shift, pergroup, num_cls, labels, row);
     MLSP_LAUNCH_CHECK("ball_count_labels_kernel");
+    return MLSP_OK;
+}
+
+extern "C" int mlsp_radius_search(const float *pts, int B, int N, float r2, int K, int32_t *ind, float *sqdist,
+                                  void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(pts && ind && sqdist, MLSP_EINVAL, "radius_search: null pointer");
+    MLSP_REQUIRE(B > 0 && N > 0 && K > 0, MLSP_EINVAL, "radius_search: bad arguments");
+    MLSP_REQUIRE(K <= 128, MLSP_EUNSUPPORTED, "radius_search: K=%d > 128", K);
+    const size_t smem = sizeof(float4) * (size_t)N;
+    MLSP_REQUIRE(smem <= 200 * 1024, MLSP_EUNSUPPORTED, "radius_search: N=%d too large", N);
+    const dim3 grid((N + BALL_ROWS - 1) / BALL_ROWS, B);
+#define MLSP_RS_LAUNCH(S)                                                                                             \
+    do {                                                                                                              \
+        MLSP_CUDA(cudaFuncSetAttribute(radius_search_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        radius_search_kernel<S><<<grid, BALL_THREADS, smem, as_stream(stream)>>>(pts, N, r2, K, ind, sqdist);          \
+    } while (0)
+    if (K <= 32) MLSP_RS_LAUNCH(1);
+    else if (K <= 64) MLSP_RS_LAUNCH(2);
+    else MLSP_RS_LAUNCH(4);
+#undef MLSP_RS_LAUNCH
+    MLSP_LAUNCH_CHECK("radius_search_kernel");
     return MLSP_OK;
 }
 

@@ -68,12 +68,13 @@ def knn(x: torch.Tensor, k: int, flags: int = _lib.KNN_AUTO, return_stats: bool 
 
 
 def knn_tensor_debug(x: torch.Tensor, k: int):
-    """Test hook: tcgen05 path with a dump of the approximate filter values.  -> (idx, v (B,N,N), stats)."""
+    """Test hook: tcgen05 path with a dump of the approximate filter values.
+    -> (idx, v (2,B,N,N): [0] pass 1 (bf16 heads only), [1] pass 2 (three-term split, the listed values), stats)."""
     _require_cuda_f32(x, "knn_tensor_debug")
     x = x.detach().contiguous()
     B, C, N = x.shape
     idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
-    dump = torch.full((B, N, N), float("nan"), dtype=torch.float32, device=x.device)
+    dump = torch.full((2, B, N, N), float("nan"), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         ws = _workspace(_lib.OP_KNN, B, C, N, k, x.device)
         _lib.call("mlsp_knn_tensor_debug", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(), _ptr(dump),
@@ -313,8 +314,6 @@ def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxel
     reproduce the reference's masks and deformed points bit for bit; region assignment, histogram, choice,
     ranking and scatter run on the GPU.  One device->host read of 2B ints (voxel mode)."""
     _require_cuda_f32(X, "deform_input")
-    if groups != 1:
-        raise NotImplementedError("deform_input: only groups=1 (the value every reference caller uses)")
     if not X.is_contiguous():
         raise MlspError("deform_input: X must be contiguous (it is modified in place)")
     B, C, N = X.shape
@@ -322,6 +321,8 @@ def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxel
     mask = torch.empty_like(X)
     if DefRec_dist == "volume_based_radius":
         return _deform_radius(X, mask)
+    if groups > 1:
+        return _deform_voxel_groups(X, mask, lookup, region_ids, DefRec_dist, int(groups))
     region, _, sel = _region_pass(X, region_ids, _MIN_PTS_VOXEL)
     sel_h = sel.cpu().numpy()                                              # the only sync of the voxel path
     chosen, nsel = sel_h[0], sel_h[1]
@@ -333,6 +334,41 @@ def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxel
     with torch.cuda.device(X.device):
         _lib.call("mlsp_region_mask_scatter", _ptr(X), B, C, N, _ptr(region), _ptr(sel[0]), _ptr(noise),
                   _ptr(offsets), _ptr(mask), _stream(X.device))
+    return X, mask
+
+
+def _deform_voxel_groups(X, mask, lookup, region_ids, DefRec_dist, groups):
+    """groups > 1 (MLSP/mlsp.py:37-50: the walk over region_ids continues until `groups` regions with >= 40 points
+    were deformed; no shipped caller passes it).  The histogram comes back to the host (27 ints per cloud), the draws
+    follow the reference's order (cloud-major, then region), and the scatter kernel runs once per group slot."""
+    B, C, N = X.shape
+    region, counts, _ = _region_pass(X, region_ids, _MIN_PTS_VOXEL)
+    counts_h = counts.cpu().numpy()
+    chosen = np.full((B, groups), -1, np.int32)
+    nsel = np.zeros((B, groups), np.int64)
+    for b in range(B):
+        g = 0
+        for i in region_ids:
+            if counts_h[b, i] >= _MIN_PTS_VOXEL:
+                chosen[b, g], nsel[b, g] = i, counts_h[b, i]
+                g += 1
+                if g >= groups:
+                    break
+    noise = offsets = None
+    if DefRec_dist == "volume_based_voxels":
+        look = _lookup_host(lookup)
+        noise, offsets = _upload_noise(_draw_gaussians(look[np.maximum(chosen, 0).reshape(-1)], nsel.reshape(-1)),
+                                       nsel.reshape(-1), X.device)
+        offsets = offsets.view(B, groups).t().contiguous()                   # (groups, B)
+    chosen_d = torch.from_numpy(np.ascontiguousarray(chosen.T)).to(X.device)  # (groups, B)
+    part = torch.empty_like(mask)
+    with torch.cuda.device(X.device):
+        for g in range(groups):
+            out = mask if g == 0 else part
+            _lib.call("mlsp_region_mask_scatter", _ptr(X), B, C, N, _ptr(region), _ptr(chosen_d[g]), _ptr(noise),
+                      _ptr(offsets[g]) if offsets is not None else None, _ptr(out), _stream(X.device))
+            if g:
+                torch.maximum(mask, part, out=mask)
     return X, mask
 
 
@@ -399,6 +435,25 @@ def cal_density(batch_pts: torch.Tensor, radius: float, num_cls: int, pergroup: 
         _lib.call("mlsp_ball_count_labels", _ptr(pts), B, N, ctypes.c_float(r2), int(K), int(shift), int(pergroup),
                   int(num_cls), _ptr(labels), _ptr(row), _stream(pts.device))
     return labels, row
+
+
+def radius_search(batch_pts: torch.Tensor, radius: float, K: int = 100):
+    """python-pcl's `KdTreeFLANN.radius_search_for_cloud(cloud, radius, K)` (the call of MLSP/mlsp.py:250), batched:
+    batch_pts (B,N,3) -> (ind (B,N,K) int32, sqdist (B,N,K) float32): per point the neighbours with squared distance
+    < radius^2, nearest first (ties by lowest index), at most K; unused slots are 0, so `(ind != 0).sum(-1)` is the
+    count cal_density derives (mlsp.py:252-253)."""
+    _require_cuda_f32(batch_pts, "radius_search")
+    pts = batch_pts.detach().contiguous()
+    B, N, three = pts.shape
+    if three != 3:
+        raise MlspError("radius_search: expected (B,N,3)")
+    r2 = float(np.float32(float(radius) * float(radius)))
+    ind = torch.empty((B, N, int(K)), dtype=torch.int32, device=pts.device)
+    sqd = torch.empty((B, N, int(K)), dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.call("mlsp_radius_search", _ptr(pts), B, N, ctypes.c_float(r2), int(K), _ptr(ind), _ptr(sqd),
+                  _stream(pts.device))
+    return ind, sqd
 
 
 # ----------------------------------------------------------------------------------------------- a7

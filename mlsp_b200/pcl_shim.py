@@ -11,7 +11,8 @@ PointSegDA/trainer.py) and uses exactly this surface:
 `install()` registers this module as `pcl` when the real one is absent, so the reference imports and its
 per-cloud `kSearchNormalEstimation` loop (PointDA/trainer.py:173-188, :524-531) run on the GPU op
 `mlsp_pca_normals`.  The batched fast path is `mlsp_b200.estimate_normals`.  `cal_density` is rebound as a whole
-by `mlsp_b200.patch()`, so `radius_search_for_cloud` is deliberately not provided.
+by `mlsp_b200.patch()` (one fused launch for the batch); an un-patched `cal_density` still works through
+`radius_search_for_cloud` (GPU op `mlsp_radius_search`, one cloud per call like the reference's loop).
 """
 from __future__ import annotations
 
@@ -38,8 +39,18 @@ class _KdTree:
         self.cloud = cloud
 
     def radius_search_for_cloud(self, cloud, radius, K=100):
-        raise NotImplementedError("pcl shim: radius search is only reached from MLSP.mlsp.cal_density, which "
-                                  "mlsp_b200.patch() replaces with the fused GPU cardinality op")
+        """-> [ind (N,K) int32, sqdist (N,K) float32], rows zero-padded (python-pcl's return convention, consumed by
+        MLSP/mlsp.py:250-253).  The tree's own cloud is searched around every point of `cloud`; the reference only
+        ever passes a copy of the same points, which is what the GPU op supports."""
+        import torch
+        from . import ops
+        q = cloud._pts if isinstance(cloud, PointCloud) else np.asarray(cloud, dtype=np.float32)
+        if q.shape != self.cloud._pts.shape or not np.array_equal(q, self.cloud._pts):
+            raise NotImplementedError("pcl shim: radius_search_for_cloud is provided for the reference's usage "
+                                      "(query cloud == indexed cloud, MLSP/mlsp.py:243-250)")
+        pts = torch.from_numpy(self.cloud._pts).cuda().unsqueeze(0)
+        ind, sqd = ops.radius_search(pts, float(radius), int(K))
+        return [ind[0].cpu().numpy(), sqd[0].cpu().numpy()]
 
 
 class _NormalEstimation:

@@ -76,12 +76,13 @@ def lib() -> ctypes.CDLL:
         L.orc_ball_count.argtypes = [c_f, I, I, ctypes.c_float, c_i]
         L.orc_ball_row.argtypes = [c_f, I, ctypes.c_float, I, c_b]
         L.orc_density_count.argtypes = [c_f, I, I, ctypes.c_float, I, c_i]
+        L.orc_radius_search.argtypes = [c_f, I, I, ctypes.c_float, I, c_i, c_f]
         L.orc_chamfer_dir.argtypes = [c_f, c_f, c_f, I, I, c_f, c_l]
         L.orc_chamfer_dir.restype = ctypes.c_double
         L.orc_reconstruction_loss.argtypes = [c_f, c_f, c_f, I, I, c_d]
         L.orc_reconstruction_loss.restype = ctypes.c_double
         for fn in ("orc_knn", "orc_knn_row_f64", "orc_edge_gather", "orc_edge_gather_bwd", "orc_fps",
-                   "orc_ball_count", "orc_ball_row", "orc_density_count"):
+                   "orc_ball_count", "orc_ball_row", "orc_density_count", "orc_radius_search"):
             getattr(L, fn).restype = I
         _lib = L
     return _lib
@@ -238,6 +239,23 @@ def density_count(pts, radius, K=100, threads=None):
 
     _over_batches(B, threads, run)
     return cnt
+
+
+def radius_search(pts, radius, K=100, threads=None):
+    """pts (B,N,3) -> (ind (B,N,K) int32, sqdist (B,N,K) float32), rows zero-padded: the restated
+    pcl radius_search_for_cloud whose `(ind != 0).sum(-1)` is density_count."""
+    pts = _f32(pts)
+    B, N, _ = pts.shape
+    r2 = np.float32(float(radius) * float(radius))
+    ind = np.empty((B, N, int(K)), np.int32)
+    sqd = np.empty((B, N, int(K)), np.float32)
+
+    def run(b0, b1):
+        _check(lib().orc_radius_search(_f(pts[b0:b1]), b1 - b0, N, r2, int(K), _i(ind[b0:b1]), _f(sqd[b0:b1])),
+               "radius_search")
+
+    _over_batches(B, threads, run)
+    return ind, sqd
 
 
 # --------------------------------------------------------------------------- a9 / a10

@@ -114,6 +114,13 @@ def main():
         assert Xd is X
         np.savez_compressed(os.path.join(OUT, f"deform_voxels_s{seed}.npz"), X0=X0.numpy(), X=Xd.numpy(),
                             mask=mask.numpy(), seed=seed)
+    # groups=3: the walk over the permuted regions deforms three regions per cloud (mlsp.py:49)
+    X0 = synth.surface_clouds(3, 1024, 58)
+    X = X0.clone()
+    np.random.seed(5)
+    Xd, mask = mlsp.deform_input(X, lookup, "volume_based_voxels", "cpu", groups=3)
+    np.savez_compressed(os.path.join(OUT, "deform_voxels_g3.npz"), X0=X0.numpy(), X=Xd.numpy(),
+                        mask=mask.numpy(), seed=5, groups=3)
     # sparse cloud: no region reaches 40 points -> untouched, empty mask
     X0 = synth.clouds(2, 64, 59)
     X = X0.clone()

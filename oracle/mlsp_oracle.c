@@ -280,6 +280,39 @@ ORC_API int orc_density_count(const float *pts, int B, int N, float r2, int K, i
     return 0;
 }
 
+/* ---- a6, list form: pcl KdTreeFLANN.radius_search_for_cloud(cloud, r, K) (MLSP/mlsp.py:250) ----------
+ * Same restatement as orc_density_count (PARITY UNPINNED): per point the neighbours with d < r2, sorted by
+ * (d ascending, index ascending), the first K kept, rows zero-padded.  Plain insertion into a sorted list.
+ * pts (B,N,3); ind (B,N,K) int32; sqd (B,N,K) float. */
+ORC_API int orc_radius_search(const float *pts, int B, int N, float r2, int K, int32_t *ind, float *sqd)
+{
+    for (int b = 0; b < B; ++b) {
+        const float *P = pts + (size_t)b * N * 3;
+        for (int i = 0; i < N; ++i) {
+            int32_t *I = ind + ((size_t)b * N + i) * K;
+            float *D = sqd + ((size_t)b * N + i) * K;
+            int n = 0;
+            for (int j = 0; j < N; ++j) {
+                float dx = P[3 * i] - P[3 * j], dy = P[3 * i + 1] - P[3 * j + 1],
+                      dz = P[3 * i + 2] - P[3 * j + 2];
+                float qx = dx * dx, qy = dy * dy, qz = dz * dz;
+                float d = qx + qy; d = d + qz;
+                if (!(d < r2)) continue;
+                /* position: after every kept entry with distance <= d (equal distances keep index order) */
+                int pos = n;
+                while (pos > 0 && D[pos - 1] > d) --pos;
+                if (pos >= K) continue;
+                int last = n < K ? n : K - 1;
+                for (int t = last; t > pos; --t) { D[t] = D[t - 1]; I[t] = I[t - 1]; }
+                D[pos] = d; I[pos] = j;
+                if (n < K) ++n;
+            }
+            for (int t = n; t < K; ++t) { D[t] = 0.0f; I[t] = 0; }
+        }
+    }
+    return 0;
+}
+
 /* ---- a9/a10: masked Chamfer ------------------------------------------------------------------
  * Reference: chamfer_distance MLSP/mlsp.py:115-153, findneareat_index :196-220.
  *   D[i][j] = (||p1_i - p2_j||_2)^2  (sqrt then square, :138) + (mask_j==0 ? 100 : 0)

@@ -69,7 +69,7 @@ def choose_region(counts, region_ids, min_pts=MIN_PTS_VOXEL):
     return chosen
 
 
-def deform_input(X, lookup, DefRec_dist="volume_based_voxels"):
+def deform_input(X, lookup, DefRec_dist="volume_based_voxels", groups=1):
     """MLSP/mlsp.py:10-51 on numpy arrays, consuming the global numpy RNG in the reference's order.
     X (B,3,N) float32 is modified in place; returns (X, mask (B,3,N) float32)."""
     X = np.asarray(X)
@@ -90,18 +90,21 @@ def deform_input(X, lookup, DefRec_dist="volume_based_voxels"):
             mask[b][:3, ind] = 1
         return X, mask
     counts = region_hist(regions)
-    chosen = choose_region(counts, region_ids)
     lookup = np.asarray(lookup, dtype=np.float32)
     for b in range(B):
-        i = chosen[b]
-        if i < 0:
-            continue
-        ind = regions[b] == i
-        n = int(ind.sum())
-        mask[b][:3, ind] = 1
-        if DefRec_dist == "volume_based_voxels":
-            pts = np.random.multivariate_normal(lookup[i], np.eye(3) * 0.001, n).T
-            X[b][:3, ind] = pts.astype(np.float32)
+        iters = 0
+        for i in region_ids:                                     # mlsp.py:37-50
+            if counts[b, i] < MIN_PTS_VOXEL:
+                continue
+            iters += 1
+            ind = regions[b] == i
+            n = int(ind.sum())
+            mask[b][:3, ind] = 1
+            if DefRec_dist == "volume_based_voxels":
+                pts = np.random.multivariate_normal(lookup[i], np.eye(3) * 0.001, n).T
+                X[b][:3, ind] = pts.astype(np.float32)
+            if iters >= groups:
+                break
     return X, mask
 
 

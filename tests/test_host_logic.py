@@ -107,7 +107,10 @@ def test_pcl_shim_surface():
         ne = cloud.make_NormalEstimation()
         ne.set_SearchMethod(cloud.make_kdtree())
         ne.set_KSearch(3)
-        with pytest.raises(NotImplementedError):
+        other = pcl.PointCloud(np.ones((5, 3), np.float32))
+        with pytest.raises(NotImplementedError):                       # only the reference's usage: query == indexed cloud
+            cloud.make_kdtree_flann().radius_search_for_cloud(other, 0.1, 100)
+        with pytest.raises(RuntimeError):                              # no CPU fallback: the search itself needs the GPU op
             cloud.make_kdtree_flann().radius_search_for_cloud(cloud, 0.1, 100)
         with pytest.raises(ValueError):
             cloud.from_array(np.zeros((5, 2), np.float32))

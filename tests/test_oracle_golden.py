@@ -73,12 +73,13 @@ def test_regions(golden):
 @pytest.mark.parametrize("name,mode", [("deform_voxels_s1", "volume_based_voxels"),
                                        ("deform_voxels_s7", "volume_based_voxels"),
                                        ("deform_voxels_sparse", "volume_based_voxels"),
+                                       ("deform_voxels_g3", "volume_based_voxels"),
                                        ("deform_radius", "volume_based_radius")])
 def test_deform_input(golden, name, mode):
     g = golden(name)
     X = g["X0"].copy()
     np.random.seed(int(g["seed"]))
-    Xd, mask = np_ops.deform_input(X, np_ops.region_mean(3), mode)
+    Xd, mask = np_ops.deform_input(X, np_ops.region_mean(3), mode, groups=int(g["groups"]) if "groups" in g else 1)
     assert np.array_equal(mask, g["mask"])
     assert np.array_equal(Xd, g["X"])
 
@@ -130,6 +131,25 @@ def test_density_count_semantics():
     assert cnt[0] == min(full[0], 100) - 1          # point 0 always drops itself
     cntK = oracle.density_count(P, 0.5, K=10)[0]
     assert cntK.max() <= 10 and cntK.min() >= 9
+
+
+def test_radius_search_is_the_list_form_of_density_count():
+    """orc_radius_search (the list pcl's radius_search_for_cloud returns) against brute force, and its
+    `(ind != 0).sum(1)` -- the expression of MLSP/mlsp.py:252-253 -- against orc_density_count."""
+    rng = np.random.default_rng(1)
+    P = rng.uniform(-0.4, 0.4, (2, 400, 3)).astype(np.float32)
+    diff = (P[:, :, None, :] - P[:, None, :, :]) ** 2                 # float32, the oracle's own expression
+    d = (diff[..., 0] + diff[..., 1]) + diff[..., 2]
+    for r, K in ((0.13, 100), (0.3, 20), (0.6, 128)):
+        ind, sqd = oracle.radius_search(P, r, K)
+        assert np.array_equal((ind != 0).sum(-1), oracle.density_count(P, r, K))
+        r2 = np.float32(r * r)
+        for b in range(2):
+            for i in (0, 7, 399):
+                js = np.nonzero(d[b, i] < r2)[0]
+                js = js[np.lexsort((js, d[b, i, js]))][:K]
+                assert np.array_equal(ind[b, i, :len(js)], js) and not ind[b, i, len(js):].any()
+                assert np.array_equal(sqd[b, i, :len(js)], d[b, i, js]) and not sqd[b, i, len(js):].any()
 
 
 def test_normals_plane():
