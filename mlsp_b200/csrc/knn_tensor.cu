@@ -625,23 +625,31 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, uint32_t row, u
         if (live) key[s] = (key[s] & 0xffffffff00000000ull) | (low >> 16);   // -> (orderable v~ << 32 | j)
     }
     // ---- links, clusters
-    float v[S], ej[S];
+    // A position e that starts a new cluster must certify EVERY later position m >= e against EVERY earlier one
+    // t < e: exact_m - exact_t >= (v_e - v_{e-1}) - eps_m - eps_t.  The per-pair bounds differ with the norms, so the
+    // test uses the largest bound of the whole list (one redux per slot): gap > 2 max eps.
+    float v[S];
     bool link[S];
     int cs[S];
     int carry = 0;
+    float emax = 0.0f;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const bool live = key[s] != ~0ull;
         const uint32_t ob = (uint32_t)(key[s] >> 32);                    // f32_orderable(v~)
         v[s] = live ? __uint_as_float((ob & 0x80000000u) ? (ob ^ 0x80000000u) : ~ob) : INFINITY;
-        ej[s] = live ? pair_eps(ni, xxi, xs[s]) : 0.0f;
-        float prev = __shfl_up_sync(MLSP_FULL, v[s], 1), eprev = __shfl_up_sync(MLSP_FULL, ej[s], 1);
+        emax = fmaxf(emax, warp_max_f32(live ? pair_eps(ni, xxi, xs[s]) : 0.0f));
+    }
+    const float gap_max = 1.0009765625f * (emax + emax);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        float prev = __shfl_up_sync(MLSP_FULL, v[s], 1);
         if (s > 0) {
-            const float last = __shfl_sync(MLSP_FULL, v[s - 1], 31), elast = __shfl_sync(MLSP_FULL, ej[s - 1], 31);
-            if (lane == 0) { prev = last; eprev = elast; }
+            const float last = __shfl_sync(MLSP_FULL, v[s - 1], 31);
+            if (lane == 0) prev = last;
         }
-        // order of (e-1, e) not certified: the gap does not exceed the two error bounds (inf - x, inf - inf: false)
-        link[s] = (s > 0 || lane > 0) && (v[s] - prev <= 1.0009765625f * (ej[s] + eprev));
+        // order across position e not certified: the gap does not exceed the error bounds (inf - x, inf - inf: false)
+        link[s] = (s > 0 || lane > 0) && (v[s] - prev <= gap_max);
         int m = link[s] ? 0 : s * 32 + lane;                             // inclusive max-scan = cluster start
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -738,59 +746,49 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, uint32_t row, u
 template <int C, int KS>
 __device__ __forceinline__ void gather_row(const KtParams &P, uint32_t row, uint32_t base, const uint32_t (&nbr)[KS])
 {
-    constexpr int Q4 = C / 4, W = 2 * Q4;
+    constexpr int Q4 = C / 4, W = 2 * Q4;                 // float4 per point row / per output row
+    static_assert(C == 64 || C == 128, "gather_row: C");
     const int lane = threadIdx.x & 31, k = P.k;
-    const float4 *xt4 = reinterpret_cast<const float4 *>(P.xt);
-    const float4 *xtb = xt4 + (size_t)base * Q4;
-    const float4 *ctr_row = xt4 + (size_t)row * Q4;
-    float4 *orow = P.edge_out + (size_t)row * k * W;
-#pragma unroll
-    for (int q0 = 0; q0 < W; q0 += 32) {
-        const int q = q0 + lane;
-        const bool is_diff = q < Q4;
-        const int qc = is_diff ? q : q - Q4;
-        const float4 ctr = __ldg(ctr_row + qc);
-        // neighbour rows of ranks j..j+3 (all lanes take part in the shuffles; j, k are warp-uniform)
-        auto load4 = [&](float4 (&nb)[4], int j) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                nb[u] = ctr;
-                if (q0 < Q4) {                                           // compile time: this pass holds difference lanes
-                    const int e = min(j + u, k - 1);
-                    uint32_t n = 0;
-#pragma unroll
-                    for (int s = 0; s < KS; ++s) {
-                        const uint32_t t = __shfl_sync(MLSP_FULL, nbr[s], e & 31);
-                        if ((e >> 5) == s) n = t;
-                    }
-                    if (is_diff) nb[u] = __ldg(xtb + (size_t)n * Q4 + qc);
-                }
-            }
-        };
-        auto store4 = [&](const float4 (&nb)[4], int j) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (j + u < k) {
-                    float4 o = nb[u];
-                    if (is_diff) {
-                        o.x = __fsub_rn(o.x, ctr.x);
-                        o.y = __fsub_rn(o.y, ctr.y);
-                        o.z = __fsub_rn(o.z, ctr.z);
-                        o.w = __fsub_rn(o.w, ctr.w);
-                    }
-                    st_stream_f4(orow + (size_t)(j + u) * W + q, o);
-                }
-            }
-        };
-        // two groups of four rows in flight: the loads of one group are issued before the other group is stored
-        float4 ga[4], gb[4];
-        load4(ga, 0);
-        for (int j = 0; j < k; j += 8) {
-            if (j + 4 < k) load4(gb, j + 4);
-            store4(ga, j);
-            if (j + 8 < k) load4(ga, j + 8);
-            if (j + 4 < k) store4(gb, j + 4);
+    const float4 *xtb = reinterpret_cast<const float4 *>(P.xt) + (size_t)base * Q4;
+    const float4 *ctr_row = reinterpret_cast<const float4 *>(P.xt) + (size_t)row * Q4;
+    float4 *o = P.edge_out + (size_t)row * k * W + lane;
+    // C = 64: one output row is 32 float4 -- lanes 0..15 hold the difference half, 16..31 the centre half.
+    // C = 128: 64 float4 -- every lane holds one difference slot (q = lane) and one centre slot (q = 32 + lane).
+    const bool is_diff = (C == 128) || lane < Q4;
+    const uint32_t qc = (C == 128) ? lane : (lane & (Q4 - 1));
+    const float4 ctr = __ldg(ctr_row + qc);
+    // out = nb - sub with (nb, sub) = (x_j, x_i) on difference lanes and (x_i, 0) on centre lanes: x - 0 == x exactly
+    const float4 sub = is_diff ? ctr : make_float4(0.f, 0.f, 0.f, 0.f);
+    // row (within the cloud) a lane reads for the neighbour of rank e (warp-uniform e, a register shuffle): x_j on
+    // difference lanes, x_i again on centre lanes (an L1 hit) -- one unconditional load, no per-lane copies of ctr
+    const uint32_t self = row - base;
+    auto rank = [&](int e) -> uint32_t {
+        uint32_t n = __shfl_sync(MLSP_FULL, nbr[0], e & 31);
+        if (KS > 1) {
+            const uint32_t n1 = __shfl_sync(MLSP_FULL, nbr[KS - 1], e & 31);
+            if (e >> 5) n = n1;
         }
+        return is_diff ? n : self;
+    };
+    int j = 0;
+    for (; j + 4 <= k; j += 4, o += 4 * W) {               // four neighbour rows in flight, no predicates
+        float4 nb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            nb[u] = __ldg(xtb + (rank(j + u) * Q4 + qc));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            st_stream_f4(o + u * W, make_float4(__fsub_rn(nb[u].x, sub.x), __fsub_rn(nb[u].y, sub.y),
+                                                __fsub_rn(nb[u].z, sub.z), __fsub_rn(nb[u].w, sub.w)));
+            if (C == 128) st_stream_f4(o + u * W + 32, ctr);
+        }
+    }
+    for (; j < k; ++j, o += W) {
+        const float4 nb = __ldg(xtb + (rank(j) * Q4 + qc));
+        st_stream_f4(o, make_float4(__fsub_rn(nb.x, sub.x), __fsub_rn(nb.y, sub.y), __fsub_rn(nb.z, sub.z),
+                                    __fsub_rn(nb.w, sub.w)));
+        if (C == 128) st_stream_f4(o + 32, ctr);
     }
 }
 

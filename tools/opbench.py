@@ -68,6 +68,9 @@ timeit("knn3", lambda: M.knn(clouds, k))
 timeit("knn64", lambda: M.knn(f64, k))
 timeit("knn128", lambda: M.knn(f128, k))
 timeit("knn64_exact", lambda: M.knn(f64, k, flags=1), reps=10)
+timeit("ggf3", lambda: M.get_graph_feature(clouds, None, k=k), flush_l2=True)       # knn + gather in one call (the DGCNN call)
+timeit("ggf64", lambda: M.get_graph_feature(f64, None, k=k), flush_l2=True)
+timeit("ggf128", lambda: M.get_graph_feature(f128, None, k=k), flush_l2=True)
 for C, f, idx in ((3, clouds, idx3), (64, f64, idx64), (128, f128, idx128)):
     g = torch.randn(B, N, k, 2 * C, device=dev).permute(0, 3, 1, 2)
     fr = f.detach().requires_grad_(True)
