@@ -502,6 +502,162 @@ def run_reference_arm(args, B, N, k, rank, world):
     }), flush=True)
 
 
+# --------------------------------------------------------------------------------------------------- workload X
+def run_workload_x(args):
+    """BASELINE.json configs[4]: 256 x 4096 points, k = 40, feature-space kNN on 64- and 128-dim DGCNN features
+    (SURVEY.md 8d set X: leaky_relu(randn)).  A step = knn(x64, 40) + knn(x128, 40) over the rank's 256 clouds through
+    the public API; the dominant kernel is the tcgen05 filter, graded on algorithmic flops 2BN^2C against bf16/2."""
+    from mlsp_b200 import synth
+    B, N, k = synth.CONFIGS["X"]
+    Cs = (64, 128)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "MLSP clouds/sec (Bx4096,k=40) feature-space kNN"
+    cfg = {"workload": "knn-X", "clouds_per_gpu": B, "points": N, "k": k, "feature_dims": list(Cs),
+           "parallelism": f"batch-sharded x{world}, no data-path collective",
+           "l2": "inputs 268 + 537 MB and the 1 GB candidate lists per call >> 126 MB L2; no explicit flush"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import ref_torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        Bs = 2                                                # the reference materialises (B,N,N): 2 clouds = 134 MB per call
+        xs = [synth.features(Bs, C, N, 5 + C) for C in Cs]
+        for _ in range(max(args.warmup, 1)):
+            for x in xs:
+                ref_torch.knn(x, k)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            for x in xs:
+                ref_torch.knn(x, k)
+        dt = (time.perf_counter() - t0) / max(args.steps, 1)
+        val = Bs / dt
+        sample = f"{Bs} of {B} clouds per step; oracle/ref_torch.py knn (matmul + topk, the reference's op composition)"
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": dict(cfg, device="cpu"),
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+
+    import mlsp_b200 as M
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host = [synth.features(B, C, N, 1234 + rank + C).pin_memory() for C in Cs]
+    dev = [h.to(device) for h in host]
+    steps = min(args.steps, 10)                               # a step is ~13 ms of GPU work on 1.3 G pairs
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    def step(xs):
+        return [M.knn(x, k) for x in xs]
+
+    for _ in range(max(args.warmup, 3)):
+        step(dev)
+    if sampler:
+        sampler.wait_first_sample(lambda: step(dev))
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(Cs) * steps + 2)]
+    ev[0].record()
+    for s_ in range(steps):
+        for i, x in enumerate(dev):                           # per-call spans on the launching (current) stream
+            a = ev[1 + 2 * (s_ * len(Cs) + i)]
+            b = ev[2 + 2 * (s_ * len(Cs) + i)]
+            a.record()
+            M.knn(x, k)
+            b.record()
+    ev[-1].record()
+    barrier()
+    dev_ms = ev[0].elapsed_time(ev[-1]) / steps
+    call_ms = [float(np.mean([ev[1 + 2 * (s_ * len(Cs) + i)].elapsed_time(ev[2 + 2 * (s_ * len(Cs) + i)]) for s_ in range(steps)]))
+               for i in range(len(Cs))]
+    if sampler:
+        sampler.keep_load(lambda: step(dev), min_samples=5, max_s=3.0)
+    clocks = sampler.stop() if sampler else None
+    # end to end: pinned host features in, the neighbour indices' checksum out, every step
+    gbuf = [torch.empty_like(d) for d in dev]
+    for _ in range(2):
+        for g, h in zip(gbuf, host):
+            g.copy_(h, non_blocking=True)
+        step(gbuf)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for g, h in zip(gbuf, host):
+            g.copy_(h, non_blocking=True)
+        chk = sum(int(i_.sum().item()) for i_ in step(gbuf))
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_ms, e2e_ms = max_over_ranks(dev_ms), max_over_ranks(e2e_s * 1e3)
+    call_ms = [max_over_ranks(v) for v in call_ms]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    fl = [2.0 * B * N * N * C + 3.0 * B * N * N for C in Cs]
+    i_dom = int(np.argmax(call_ms))
+    ach = fl[i_dom] / (call_ms[i_dom] * 1e-3) / 1e12
+    peak = pk["bf16_tflops_sustained"] / 2
+    roof = {"kernel": "knn_tensor_kernel", "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": None, "peak_source": pk["source"] + " sustained bf16/2 (fp32-faithful contraction; SURVEY.md 8d)",
+            "algorithmic_flops_per_launch": fl[i_dom], "ms_per_launch": call_ms[i_dom], "launches_per_step": 1,
+            "ops": [f"knn_C{Cs[i_dom]}"],
+            "note": "op-level span of knn(x, 40) at C=%d: knn_prep + knn_tensor (tcgen05, 4 MMA products per pair: bf16 heads in "
+                    "pass 1, three-term split in pass 2) + knn_refine; achieved = algorithmic 2BN^2C flops / the whole span" % Cs[i_dom]}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        xs = [synth.features(2, C, N, 5 + C) for C in Cs]
+        for x in xs:
+            ref_torch.knn(x, k)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            for x in xs:
+                ref_torch.knn(x, k)
+        t = (time.perf_counter() - t0) / reps
+        cpu = {"value": 2 / t, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{reps} steps on 2 of {B} clouds ({t * reps:.1f} s; the reference materialises (B,N,N): 17 GB at the "
+                         "full batch); oracle/ref_torch.py knn, all host threads"}
+    line = {"metric": metric, "value": B * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(sum(h.numel() * 4 for h in host)), "d2h_bytes_per_step": 8 * len(Cs), "checksum": chk},
+            "gpu_launches": 3 * len(Cs) * steps,
+            "op_ms_per_step": {f"knn_C{C}": round(v, 4) for C, v in zip(Cs, call_ms)},
+            "op_rooflines": {f"knn_C{C}": {"ms": round(v, 4), "TFLOPs": round(f / (v * 1e-3) / 1e12, 2)}
+                             for C, v, f in zip(Cs, call_ms, fl)},
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -509,7 +665,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="A", choices=["A", "S"])
+    ap.add_argument("--workload", default="A", choices=["A", "S", "X"],
+                    help="A: PointDA-10 hot path (default, the BASELINE metric); S: PointSegDA hot path; "
+                         "X: the scaling-sweep shape 256x4096, k=40 -- feature-space kNN on 64/128-dim features (configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="headline on one stream (no target-builder overlap)")
     ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")
@@ -520,6 +678,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     from mlsp_b200 import synth
+    if args.workload == "X":
+        return run_workload_x(args)
     set_workload(args.workload)
     B, N, k = synth.CONFIGS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

@@ -51,3 +51,23 @@ def test_reference_arm_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_workload_x_reference_arm_line():
+    """configs[4] (256 x 4096, k = 40, feature-space kNN): the reference arm of `--workload X` prints the contract's line
+    on a bounded sample of the workload."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "X", "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "clouds/s" and line["value"] > 0
+    assert line["config"]["points"] == 4096 and line["config"]["k"] == 40 and line["config"]["feature_dims"] == [64, 128]
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "ggf_fwd_C64" not in line.get("op_ms_per_step", {})
+
+
+def test_fused_call_accounting(bench):
+    """The DGCNN layers make the fused get_graph_feature(idx=None) call: its work model is the edge tensor's bytes."""
+    B, N, k = 32, 1024, 20
+    assert bench.algorithmic_bytes("ggf_fwd_C64", B, N, k) == bench.algorithmic_bytes("edge_fwd_C64", B, N, k)
+    assert bench.LAUNCHES["ggf_tensor"] == 3 and bench.LAUNCHES["ggf3"] == 1

@@ -169,6 +169,51 @@ def test_graph_feature_fused_3d_path(dev, orc, B, N, k):
     assert np.array_equal(_np(out.permute(0, 2, 3, 1)), orc.edge_gather(x.numpy(), idx_ref))
 
 
+def test_dgcnn_slice_forward_backward(dev):
+    """A DGCNN-shaped slice (PointDA/Models.py:111-129: get_graph_feature -> 1x1 conv -> BN -> LeakyReLU -> max over k,
+    three layers C = 3, 64, 64 -> 128) trained one step through the fused drop-in call, against the same torch layers
+    fed by the reference's op composition (oracle/ref_torch.get_graph_feature) on the same neighbour indices: outputs,
+    input gradient and every parameter gradient agree to fp32 tolerance -- the autograd plumbing of the drop-in."""
+    from oracle import ref_torch
+    torch.manual_seed(0)
+    B, N, k = 4, 1024, 20
+    x0 = synth.surface_clouds(B, N, 31).to(dev)
+
+    def make():
+        torch.manual_seed(1)
+        chans = [(6, 64), (128, 64), (128, 128)]
+        return torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Conv2d(i, o, 1, bias=False), torch.nn.BatchNorm2d(o),
+                                                        torch.nn.LeakyReLU(0.2)) for i, o in chans]).to(dev)
+
+    def run(layers, ggf):
+        x = x0.clone().requires_grad_(True)
+        h, feats = x, []
+        for layer in layers:
+            h = layer(ggf(h)).max(dim=-1)[0]
+            feats.append(h)
+        out = torch.cat(feats, dim=1)
+        (out ** 2).mean().backward()
+        return out.detach(), x.grad, [p.grad for p in layers.parameters()]
+
+    idx_log = []
+
+    def ours(h):
+        return M.get_graph_feature(h, None, k=k)
+
+    def theirs(h):
+        idx = M.knn(h.detach(), k)                                     # same neighbourhoods; the gather is torch's
+        idx_log.append(idx)
+        return ref_torch.get_graph_feature(h, k=k, idx=idx)
+
+    oa, ga, pa = run(make(), ours)
+    ob, gb, pb = run(make(), theirs)
+    assert len(idx_log) == 3
+    assert torch.allclose(oa, ob, rtol=1e-4, atol=1e-5)
+    assert float((ga - gb).abs().max()) <= 1e-4 * float(gb.abs().max())
+    for a, b in zip(pa, pb):
+        assert float((a - b).abs().max()) <= 1e-4 * max(float(b.abs().max()), 1e-12)
+
+
 def test_edge_gather_backward_golden(golden, dev):
     g = golden("ggf_bwd")
     x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
