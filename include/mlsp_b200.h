@@ -83,6 +83,13 @@ MLSP_API int mlsp_edge_gather_fwd(const float *x, const int64_t *idx, int B, int
 MLSP_API int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
                            size_t ws_bytes, void *stream);
 
+/* Measurement hook for the call above on the tcgen05 path (C in {64,128}): `stages` selects which of its kernels are
+ *   launched -- bit 0: knn_prep, bit 1: knn_tensor (filter), bit 2: knn_refine (ranking + fused edge gather).  Every
+ *   kernel only reads what the earlier ones left in ws, so after one full call with the same arguments and the same ws
+ *   a single stage can be re-run alone (bench.py times each kernel this way with CUDA events). */
+MLSP_API int mlsp_graph_feature_fwd_stage(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
+                                 size_t ws_bytes, int stages, void *stream);
+
 /* backward of a2 w.r.t. x (the reference gets it from autograd: index_put_(accumulate=True)).
  *   grad_out in the same channels-last storage [B][N][k][2C]; grad_x (B,C,N), overwritten. */
 MLSP_API int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, int B, int C, int N, int k,

@@ -23,6 +23,7 @@ SIGNATURES = {
     "mlsp_knn_tensor_debug": [_P, _I, _I, _I, _I, _P, _P, _Z, _P, _P],
     "mlsp_edge_gather_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P],
     "mlsp_graph_feature_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P],
+    "mlsp_graph_feature_fwd_stage": [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _I, _P],
     "mlsp_edge_gather_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P],
     "mlsp_fps": [_P, _I, _I, _I, _P, _P, _P, _P],
     "mlsp_region_assign_select": [_P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],

@@ -413,3 +413,19 @@ extern "C" int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k
     if (rc) return rc;
     return mlsp_edge_gather_fwd(x, idx, B, C, N, k, out, ws, ws_bytes, stream);   // stream order: the kNN is done with ws
 }
+
+// Measurement hook: mlsp_graph_feature_fwd restricted to some of the kernels of the tcgen05 path (stages: bit 0 = prep,
+// bit 1 = tensor-core filter, bit 2 = ranking + fused edge gather).  Each kernel only reads what the earlier ones left
+// in `ws`, so after one full call on the same arguments any single stage can be re-run -- and timed -- alone.
+// Shapes that do not take the tcgen05 path run the whole op.
+namespace mlsp {
+extern thread_local int g_kt_stages;
+}
+extern "C" int mlsp_graph_feature_fwd_stage(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
+                                            size_t ws_bytes, int stages, void *stream)
+{
+    mlsp::g_kt_stages = stages & 7;
+    const int rc = mlsp_graph_feature_fwd(x, B, C, N, k, idx, out, ws, ws_bytes, stream);
+    mlsp::g_kt_stages = 7;
+    return rc;
+}

@@ -968,6 +968,9 @@ const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k)
     return reinterpret_cast<const float *>(static_cast<const char *>(ws) + kt_layout(B, C, N, k).off_xt);
 }
 
+// measurement hook (mlsp_graph_feature_fwd_stage): which of the three kernels a call launches; 7 = all
+thread_local int g_kt_stages = 7;
+
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
                    cudaStream_t st)
 {
@@ -979,9 +982,11 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     __nv_bfloat16 *lo = reinterpret_cast<__nv_bfloat16 *>(w + L.off_lo);
     float *xt = reinterpret_cast<float *>(w + L.off_xt);
 
-    knn_prep_kernel<<<dim3((N + PREP_PTS - 1) / PREP_PTS, B), PREP_THREADS, sizeof(float) * C * (PREP_PTS + 1), st>>>(
-        x, C, N, xx, counters, xt, hi, lo);
-    MLSP_LAUNCH_CHECK("knn_prep_kernel");
+    if (g_kt_stages & 1) {
+        knn_prep_kernel<<<dim3((N + PREP_PTS - 1) / PREP_PTS, B), PREP_THREADS, sizeof(float) * C * (PREP_PTS + 1), st>>>(
+            x, C, N, xx, counters, xt, hi, lo);
+        MLSP_LAUNCH_CHECK("knn_prep_kernel");
+    }
 
     CUtensorMap map_hi, map_lo;
     int rc = make_map(&map_hi, hi, (uint64_t)B * N, (uint64_t)C);
@@ -1012,7 +1017,8 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
                  MLSP_EUNSUPPORTED, "knn: no shared-memory configuration for C=%d k=%d", C, k);
     const size_t smem = kt_smem_bytes(C, k, NG, P.stages);
     dim3 grid((N + KT_ROWS - 1) / KT_ROWS, B);
-    if (NG == 32) {
+    if (!(g_kt_stages & 2)) {
+    } else if (NG == 32) {
         MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         knn_tensor_kernel<32><<<grid, KT_THREADS, smem, st>>>(map_hi, map_lo, P);
     } else {
@@ -1020,7 +1026,7 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
         knn_tensor_kernel<64><<<grid, KT_THREADS, smem, st>>>(map_hi, map_lo, P);
     }
     MLSP_LAUNCH_CHECK("knn_tensor_kernel");
-    {
+    if (g_kt_stages & 4) {
         const long long rows_total = (long long)B * N;
         const unsigned rblocks = (unsigned)((rows_total + RF_WARPS - 1) / RF_WARPS);
         if (NG == 32 && C == 64)

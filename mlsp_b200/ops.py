@@ -145,6 +145,28 @@ class _GraphFeature(torch.autograd.Function):
         return _edge_backward(ctx, grad), None
 
 
+class GraphFeatureStages:
+    """Measurement handle: get_graph_feature(x, None, k) forward on the tcgen05 path with the workspace kept alive, so
+    that each of its three kernels can be re-launched alone (`run(stages)`: bit 0 prep, bit 1 filter, bit 2 ranking +
+    fused edge gather).  Construction runs the whole op once.  bench.py times the kernels with it; not a model-facing API."""
+
+    def __init__(self, x: torch.Tensor, k: int):
+        _require_cuda_f32(x, "GraphFeatureStages")
+        self.x = x.detach().contiguous()
+        B, C, N = self.x.shape
+        self.dims = (B, C, N, int(k))
+        self.out = torch.empty((B, N, k, 2 * C), dtype=torch.float32, device=x.device)
+        self.idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
+        self.ws = _workspace(_lib.OP_GRAPH_FEATURE, B, C, N, k, x.device)
+        self.run(7)
+
+    def run(self, stages: int) -> None:
+        B, C, N, k = self.dims
+        with torch.cuda.device(self.x.device):
+            _lib.call("mlsp_graph_feature_fwd_stage", _ptr(self.x), B, C, N, k, _ptr(self.idx), _ptr(self.out), _ptr(self.ws),
+                      self.ws.numel(), int(stages), _stream(self.x.device))
+
+
 def get_graph_feature(x: torch.Tensor, args=None, k: int = 20, idx: torch.Tensor | None = None) -> torch.Tensor:
     """get_graph_feature(x, args, k, idx): PointDA/model_utils.py:18-42 == PointSegDA/Models.py:18-45.
     x (B,C,N) or (B,C,N,1) -> (B,2C,N,k) = [neighbour - centre ; centre], channels_last strides.

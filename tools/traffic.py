@@ -38,9 +38,10 @@ for name, tot, us in rows:
     elif "knn_refine_kernel" in name:
         C = 128 if ", 128>" in name else 64
         if us > (80 if C == 128 else 50):               # with the fused edge gather (ggf*); the ranking alone is 30-40 us
-            groups[f"A:ggf_fwd_C{C}"].append(tot)
+            groups[f"A:k_rank_gather_C{C}"].append(tot)
     elif "knn_tensor_kernel" in name:
-        groups[f"A:knn_C{64 if us < 48 else 128}"].append(tot)
+        groups[f"A:knn_C{64 if us < 43 else 128}"].append(tot)
+        groups[f"A:k_filter_C{64 if us < 43 else 128}"].append(tot)
     elif "knn3_kernel" in name:
         groups["A:knn_C3"].append(tot)
     elif "edge_fwd3" in name:
@@ -52,7 +53,7 @@ for key, v in sorted(groups.items()):
     out[key] = {"dram_bytes": sum(v) / len(v), "launches": len(v),
                 "source": f"profiles/ncu_{tag}.md (ncu --set full --clock-control none over tools/opbench.py; main kernel of the op, "
                           "dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
-    if (key.startswith("A:edge_") or key.startswith("A:ggf_")) and not key.endswith("C3"):
+    if (key.startswith("A:edge_") or key.startswith("A:k_rank_gather_")) and not key.endswith("C3"):
         out[key]["algorithmic_bytes"] = alg(int(key.split("_C")[1]))
 json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
 print(json.dumps(out, indent=1))
