@@ -11,7 +11,8 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless marked "host";
- *   - tensors are dense, row-major, in the layouts written next to each argument;
+ *   - tensors are dense, row-major, in the layouts written next to each argument; edge tensors, their gradients
+ *     and workspaces are 16-byte aligned (128-bit accesses);
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued, nothing synchronises;
  *   - outputs and workspaces are caller-allocated (mlsp_workspace_bytes gives the size);
  *   - return value: 0 on success, otherwise an MLSP_E* code; mlsp_last_error() (thread-local)

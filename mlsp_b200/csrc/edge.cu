@@ -324,6 +324,8 @@ extern "C" int mlsp_edge_gather_fwd(const float *x, const int64_t *idx, int B, i
     MLSP_REQUIRE(x && idx && out && ws, MLSP_EINVAL, "edge_gather_fwd: null pointer");
     MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "edge_gather_fwd: bad shape");
     MLSP_REQUIRE(ws_bytes >= edge_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "edge_gather_fwd: workspace too small");
+    MLSP_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0 || C % 4 != 0, MLSP_EINVAL,
+                 "edge_gather_fwd: out and ws must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     const long long points = (long long)B * N;
     if (C == 3 && (points * k) % 2 == 0 && points * k < (1ll << 31) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
@@ -355,6 +357,8 @@ extern "C" int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, i
     MLSP_REQUIRE(grad_out && idx && grad_x && ws, MLSP_EINVAL, "edge_gather_bwd: null pointer");
     MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "edge_gather_bwd: bad shape");
     MLSP_REQUIRE(ws_bytes >= edge_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "edge_gather_bwd: workspace too small");
+    MLSP_REQUIRE(((reinterpret_cast<uintptr_t>(grad_out) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0 || C % 4 != 0, MLSP_EINVAL,
+                 "edge_gather_bwd: grad_out and ws must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     if (C == 3 && (long long)B * N < (1ll << 31) - 256) {
         const long long points = (long long)B * N;
@@ -395,6 +399,8 @@ extern "C" int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k
     MLSP_REQUIRE(x && idx && out && ws, MLSP_EINVAL, "graph_feature_fwd: null pointer");
     MLSP_REQUIRE(B > 0 && C > 0 && N > 0 && k > 0, MLSP_EINVAL, "graph_feature_fwd: bad shape");
     MLSP_REQUIRE(k <= N, MLSP_EINVAL, "graph_feature_fwd: k=%d out of range for N=%d", k, N);
+    MLSP_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0 || C % 4 != 0, MLSP_EINVAL,
+                 "graph_feature_fwd: out and ws must be 16-byte aligned");
     MLSP_REQUIRE(ws_bytes >= graph_feature_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "graph_feature_fwd: workspace too small");
     if (knn_tensor_supported(B, C, N, k) && k <= 64) {
         // tcgen05 path: the refine kernel that ranks a row also writes its edge features (no separate gather launch,
