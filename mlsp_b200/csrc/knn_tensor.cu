@@ -88,11 +88,40 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and complete_tx is signalled
+// on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same arrive, delivered to the mbarrier at this offset in every CTA of `mask` (a stage shared by a CTA pair is
+// free only when both CTAs' MMAs have read it)
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -363,6 +392,7 @@ struct KtParams {
     float4 *edge_out;        // optional (B,N,k,2C): the refine kernel also writes the row's edge features (a2 fused)
     int N, C, k, T;          // T = candidate tiles per cloud
     int stages;              // depth of the B-operand smem ring
+    int pair;                // launched in clusters of two CTAs sharing the candidate blocks by TMA multicast
     int mode;                // tuning hook (MLSP_KT_MODE): bit 0 skips the pass-1 math, bit 1 the pass-2 math, bit 2: three-term pass 1
 };
 
@@ -377,8 +407,14 @@ __host__ __device__ inline size_t kt_smem_bytes(int C, int k, int NG, int stages
 
 template <int NG>
 __global__ void __launch_bounds__(KT_THREADS, (NG == 32) ? 2 : 1)   // NG = 32: two CTAs per SM (one wave at 32 x 1024), <= 102 registers
-knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, KtParams P)
+knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                  const __grid_constant__ CUtensorMap half_hi, const __grid_constant__ CUtensorMap half_lo, KtParams P)
 {
+    // P.pair: the kernel was launched in clusters of two CTAs = two adjacent row blocks of one cloud.  Both stream the
+    // same candidate blocks, so each CTA fetches HALF of every block (64 of its 128 rows) and TMA multicasts it into
+    // both shared memories: the L2 -> SM operand traffic, which bounds the MMA pipeline, halves.
+    const bool pair = P.pair != 0;
+    const uint32_t crank = pair ? cluster_ctarank() : 0u;
     constexpr int CAP = 2 * NG;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms need 1 KiB alignment
@@ -405,7 +441,7 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < KT_MAX_STAGES; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, 1);
+            mbar_init(empty + s, pair ? 2 : 1);                   // pair: one commit-arrive from each CTA's MMA issuer
         }
         mbar_init(a_full, 1);
         for (int s = 0; s < 2; ++s) {
@@ -421,6 +457,7 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (pair) cluster_sync_all();                                   // the peer's barriers exist before anything signals them
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
@@ -438,8 +475,13 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 for (int kb = 0; kb < nkb; ++kb) {   // B blocks: hi ..., lo ...
                     mbar_wait(empty + stage, ph ^ 1);
                     mbar_expect_tx(full + stage, KT_BLK_BYTES);
-                    tma_load_2d(sB + (size_t)stage * KT_BLK_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
-                                rowbase + j0, full + stage);
+                    if (pair)                                       // my half of the block, into both CTAs
+                        tma_load_2d_mc(sB + (size_t)stage * KT_BLK_BYTES + (size_t)crank * (KT_BLK_BYTES / 2),
+                                       kb < SEG ? &half_hi : &half_lo, (kb % SEG) * KT_KBLK,
+                                       rowbase + j0 + (int)crank * (KT_COLS / 2), full + stage, (uint16_t)3);
+                    else
+                        tma_load_2d(sB + (size_t)stage * KT_BLK_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
+                                    rowbase + j0, full + stage);
                     if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
             }
@@ -473,7 +515,8 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                         for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)
                             tc_mma_bf16(d, da_lo + 2 * k16, db + 2 * k16, KT_IDESC, 1u);
                     }
-                    tc_commit(empty + stage);                       // smem stage reusable when these MMAs retire
+                    if (pair) tc_commit_mc(empty + stage, (uint16_t)3);   // stage reusable when BOTH CTAs' MMAs retired
+                    else tc_commit(empty + stage);                  // smem stage reusable when these MMAs retire
                     if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
                 tc_commit(tm_full + buf);                           // accumulator of tile g complete
@@ -516,10 +559,8 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             const int buf = g & 1;
             float nxt = INFINITY;
             const int jn = ((g + 1) % T) * KT_COLS + et;       // tile g+1 (pass 2 restarts at tile 0)
-            if (et < KT_COLS && jn < N) {
-                nxt = xxb[jn];
-                nmax = fmaxf(nmax, nxt);
-            }
+            if (et < KT_COLS && jn < N) nxt = xxb[jn];           // consumed at the bottom of the iteration: the L2 latency
+                                                                // hides behind the tile (a use here would stall all 8 warps at the barrier)
             epi_bar_sync();                                     // norms of tile g visible
             mbar_wait(tm_full + buf, (g >> 1) & 1);
             tc_fence_after();
@@ -529,7 +570,10 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + buf);
-            if (et < KT_COLS) nrm_s[(buf ^ 1) * KT_COLS + et] = nxt;
+            if (et < KT_COLS) {
+                nrm_s[(buf ^ 1) * KT_COLS + et] = nxt;
+                if (jn < N) nmax = fmaxf(nmax, nxt);
+            }
         }
         // ---- between the passes: the row has 2 NG class minima (NG per thread).  Each thread sorts its own;
         // the k-th smallest of the union of two sorted lists A, B is max_{i<k} min(A[i], B[k-1-i]).
@@ -582,6 +626,7 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (pair) cluster_sync_all();            // no CTA leaves while its peer can still signal its barriers / write its smem
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
     }
@@ -920,13 +965,13 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols)
+static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
 {
     EncodeTiledFn fn = encode_fn();
     MLSP_REQUIRE(fn, MLSP_ECUDA, "knn: cuTensorMapEncodeTiled not available");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KT_KBLK, (cuuint32_t)KT_COLS};
+    cuuint32_t box[2] = {(cuuint32_t)KT_KBLK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -988,10 +1033,14 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
         MLSP_LAUNCH_CHECK("knn_prep_kernel");
     }
 
-    CUtensorMap map_hi, map_lo;
-    int rc = make_map(&map_hi, hi, (uint64_t)B * N, (uint64_t)C);
+    CUtensorMap map_hi, map_lo, half_hi, half_lo;       // boxes of 128 rows (A tiles, unpaired B blocks) and of 64 rows (paired)
+    int rc = make_map(&map_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_COLS);
     if (rc) return rc;
-    rc = make_map(&map_lo, lo, (uint64_t)B * N, (uint64_t)C);
+    rc = make_map(&map_lo, lo, (uint64_t)B * N, (uint64_t)C, KT_COLS);
+    if (rc) return rc;
+    rc = make_map(&half_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_COLS / 2);
+    if (rc) return rc;
+    rc = make_map(&half_lo, lo, (uint64_t)B * N, (uint64_t)C, KT_COLS / 2);
     if (rc) return rc;
 
     KtParams P;
@@ -1017,13 +1066,31 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
                  MLSP_EUNSUPPORTED, "knn: no shared-memory configuration for C=%d k=%d", C, k);
     const size_t smem = kt_smem_bytes(C, k, NG, P.stages);
     dim3 grid((N + KT_ROWS - 1) / KT_ROWS, B);
-    if (!(g_kt_stages & 2)) {
-    } else if (NG == 32) {
-        MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_tensor_kernel<32><<<grid, KT_THREADS, smem, st>>>(map_hi, map_lo, P);
-    } else {
-        MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_tensor_kernel<64><<<grid, KT_THREADS, smem, st>>>(map_hi, map_lo, P);
+    // MLSP_KT_CLUSTER=1 (tuning hook): clusters of two adjacent row blocks of a cloud share every candidate block by TMA
+    // multicast (needs an even number of row blocks per cloud).  Off by default: halving the L2 -> SM operand traffic
+    // changed nothing (profiles/kt_ablate_r1h.log), i.e. the MMA pipeline is not fed-bound.
+    P.pair = 0;
+    if (const char *e = getenv("MLSP_KT_CLUSTER")) P.pair = (atoi(e) != 0 && grid.x % 2 == 0) ? 1 : 0;
+    if (g_kt_stages & 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(KT_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = P.pair ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (NG == 32) {
+            MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<32>, map_hi, map_lo, half_hi, half_lo, P));
+        } else {
+            MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<64>, map_hi, map_lo, half_hi, half_lo, P));
+        }
     }
     MLSP_LAUNCH_CHECK("knn_tensor_kernel");
     if (g_kt_stages & 4) {

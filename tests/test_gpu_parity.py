@@ -525,6 +525,17 @@ def test_knn_tensor_matches_oracle(dev, orc, B, C, N, k, quant):
     assert torch.equal(exact, idx)
 
 
+def test_knn_tensor_cluster_multicast_variant(dev, orc, monkeypatch):
+    """MLSP_KT_CLUSTER=1: the filter launched in clusters of two CTAs that share every candidate block by TMA
+    multicast (each CTA fetches half of it) gives the same indices."""
+    monkeypatch.setenv("MLSP_KT_CLUSTER", "1")
+    for B, C, N, k in [(3, 64, 1024, 20), (2, 128, 768, 40)]:
+        x = synth.smooth_features(B, C, N, 78)
+        idx, stats = M.knn(x.to(dev), k, flags=M._lib.KNN_TENSOR_ONLY, return_stats=True)
+        assert np.array_equal(_np(idx), orc.knn(x.numpy(), k))
+        assert stats["fallback_rows"] <= 0.05 * B * N
+
+
 def test_knn_tensor_ties_and_duplicates(dev, orc):
     x = synth.smooth_features(2, 64, 512, 5)
     x[:, :, 100:140] = x[:, :, 100:101]                                # 40 duplicate points: exact ties
