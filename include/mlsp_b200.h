@@ -48,6 +48,7 @@ extern "C" {
 #define MLSP_OP_EDGE_BWD 3
 #define MLSP_OP_CHAMFER 4
 #define MLSP_OP_GRAPH_FEATURE 5
+#define MLSP_OP_EDGECONV_BWD 6 /* C = output channels O */
 
 /* flags for mlsp_knn_f32 */
 #define MLSP_KNN_AUTO 0        /* C=3: two-pass 3-D kernel; C in {64,128}: tcgen05 filter + exact re-rank; else streaming */
@@ -188,6 +189,42 @@ MLSP_API int mlsp_reconstruction_loss_bwd(const float *pred, int64_t pred_bstrid
                          int64_t pred_cstride, const float *gold, int64_t gold_bstride, int64_t gold_pstride,
                          int64_t gold_cstride, const float *mask, int64_t mask_bstride, const int64_t *argmin,
                          int B, int N, const float *grad_loss, float *grad_pred, void *stream);
+
+/* ---- EdgeConv without the edge tensor ------------------------------------------------------
+ * Replaces the layer  get_graph_feature -> conv_2d (1x1 Conv2d [+ BatchNorm2d] + LeakyReLU) -> max over k
+ * (PointDA/Models.py:114-128 with PointDA/model_utils.py:45-63; PointSegDA/Models.py:171-184, stacked convs without
+ * BatchNorm / activation).  The 1x1 convolution is linear in [x_j - x_i | x_i]:
+ *     h[b,o,i,j] = Y[b,idx[b,i,j],o] + Z[b,i,o],  Y = Wa x, Z = (Wb - Wa) x + bias,  W = [Wa | Wb]
+ * so the caller makes ONE point-wise GEMM yz (B,N,2O) = [Y | Z] (a library call) and these entry points do the rest.
+ * BatchNorm is a*h + c per channel with a = gamma*invstd, LeakyReLU is increasing:
+ *     out[b,o,i] = lrelu(a_o * ext_j h[b,o,i,j] + c_o),  ext = max where a_o >= 0, min where a_o < 0.
+ * All tensors point-major, 16-byte aligned; O % 4 == 0, O <= 1024, k <= 255. */
+
+/* per point: hsel (B,N,O) = the extreme of h over the k neighbours (max where sgn_src[o] >= 0, else min; sgn_src NULL:
+ *   max), slot (B,N,O) uint8 = the neighbour rank that attains it (first on ties).  With stats != NULL (training-mode
+ *   BatchNorm) also rowsum (B,N,O) = sum_j h and stats (2,O) double = [sum h ; sum h^2] over all B*N*k edges
+ *   (zeroed by the call, accumulated with fp64 atomics). */
+MLSP_API int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, int O, int k, const float *sgn_src,
+                             float *hsel, uint8_t *slot, float *rowsum, double *stats, void *stream);
+
+/* BatchNorm2d in training mode (torch.nn.functional.batch_norm: biased variance): stats of `count` = B*N*k edges ->
+ *   coef (4,O) = [a = gamma*invstd ; c = beta - a*mean ; mean ; invstd], var_out (O) = biased variance (may be NULL).
+ *   gamma / beta NULL = 1 / 0 (affine=False). */
+MLSP_API int mlsp_edgeconv_bn_coeffs(const double *stats, const float *gamma, const float *beta, int O, double count, float eps,
+                            float *coef, float *var_out, void *stream);
+
+/* out (B,O,N) = lrelu_slope(a_o * hsel[b,i,o] + c_o), coef rows 0 and 1 = a, c  (slope 1: no activation, 0: ReLU) */
+MLSP_API int mlsp_edgeconv_apply_fwd(const float *hsel, const float *coef, int B, int N, int O, float slope, float *out,
+                            void *stream);
+
+/* backward: g (B,O,N) = d loss / d out  ->  dyz (B,N,2O) = [dY | dZ] (overwritten).
+ *   bn_train != 0: exact gradient through the batch statistics (needs rowsum and coef rows 2,3 = mean, invstd);
+ *   dgamma_dbeta (2,O), may be NULL when bn_train == 0: [sum dy*(hsel-mean)*invstd ; sum dy], dy = g*lrelu'(.) -- the
+ *   gradients of gamma and beta, or of (a, c) when the caller sets mean = 0, invstd = 1 (fixed affine / bias).
+ *   ws: mlsp_workspace_bytes(MLSP_OP_EDGECONV_BWD, B, O, N, k). */
+MLSP_API int mlsp_edgeconv_bwd(const float *g, const float *yz, const int64_t *idx, const float *hsel, const uint8_t *slot,
+                      const float *rowsum, const float *coef, int B, int N, int O, int k, float slope, int bn_train,
+                      float *dyz, float *dgamma_dbeta, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,7 @@ size_t knn_workspace_bytes(int B, int C, int N, int k);
 size_t edge_workspace_bytes(int B, int C, int N, int k);
 size_t chamfer_workspace_bytes(int B, int N);
 size_t graph_feature_workspace_bytes(int B, int C, int N, int k);
+size_t edgeconv_workspace_bytes(int B, int O, int N);
 
 }  // namespace mlsp
 
@@ -58,6 +59,7 @@ size_t mlsp_workspace_bytes(int op, int B, int C, int N, int k)
         case MLSP_OP_EDGE_BWD: return mlsp::edge_workspace_bytes(B, C, N, k);
         case MLSP_OP_CHAMFER: return mlsp::chamfer_workspace_bytes(B, N);
         case MLSP_OP_GRAPH_FEATURE: return mlsp::graph_feature_workspace_bytes(B, C, N, k);
+        case MLSP_OP_EDGECONV_BWD: return mlsp::edgeconv_workspace_bytes(B, C, N);
         default: return 0;
     }
 }

@@ -1,0 +1,223 @@
+"""EdgeConv without the edge tensor -- an opt-in, Models.py-level swap.
+
+The reference builds every DGCNN layer as
+
+    x = get_graph_feature(x, args, k)        # (B,2C,N,k), 0.34-0.67 GB per layer at 32x1024
+    x = conv_2d(x)                           # 1x1 Conv2d [+ BatchNorm2d] + LeakyReLU      PointDA/model_utils.py:45-63
+    x = x.max(dim=-1, keepdim=False)[0]      # PointDA/Models.py:114-128; PointSegDA/Models.py:171-184 (stacked plain convs)
+
+`edge_conv` computes the same (B,O,N) result and the same gradients without materialising anything of size
+B*N*k: the convolution is linear in [x_j - x_i | x_i], so  h_ij = Y[idx_ij] + Z[i]  with two point-wise products
+(one library GEMM on (B*N,C) x (C,2O)); BatchNorm in training mode needs only sum h and sum h^2 over the edges;
+BatchNorm + LeakyReLU are monotone per channel, so the max over k commutes with them (min where gamma < 0).
+Kernels: mlsp_b200/csrc/edgeconv.cu behind mlsp_edgeconv_* (include/mlsp_b200.h).  No CPU path.
+
+Results agree with the reference composition to fp32 rounding (a different, equally valid association of the same
+sums: tests/test_gpu_parity.py::test_edge_conv_*, tolerance 1e-5 relative as north_star states for floating point).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch import nn
+
+from . import _lib
+from ._lib import MlspError
+from .ops import _ptr, _require_cuda_f32, _stream, knn
+
+
+class _EdgeConvReduce(torch.autograd.Function):
+    """(yz, idx, p0, p1) -> out (B,O,N).
+    mode "bn_train": p0 = gamma, p1 = beta (None = 1 / 0); batch statistics over the B*N*k edges.
+    mode "affine"  : p0 = a, p1 = c per channel (eval-mode BatchNorm folded, or a = 1 / c = 0).
+    Also returns (mean, biased var) of the batch in bn_train mode (non-differentiable; for the running statistics)."""
+
+    @staticmethod
+    def forward(ctx, yz, idx, p0, p1, mode, eps, slope):
+        B, N, O2 = yz.shape
+        O = O2 // 2
+        k = idx.shape[2]
+        dev = yz.device
+        yz = yz.contiguous()
+        hsel = torch.empty((B, N, O), dtype=torch.float32, device=dev)
+        slot = torch.empty((B, N, O), dtype=torch.uint8, device=dev)
+        coef = torch.empty((4, O), dtype=torch.float32, device=dev)
+        out = torch.empty((B, O, N), dtype=torch.float32, device=dev)
+        train = mode == "bn_train"
+        rowsum = var = None
+        p0c = p0.detach().float().contiguous() if p0 is not None else None
+        p1c = p1.detach().float().contiguous() if p1 is not None else None
+        with torch.cuda.device(dev):
+            s = _stream(dev)
+            if train:
+                rowsum = torch.empty((B, N, O), dtype=torch.float32, device=dev)
+                stats = torch.empty((2, O), dtype=torch.float64, device=dev)
+                var = torch.empty((O,), dtype=torch.float32, device=dev)
+                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(p0c), _ptr(hsel), _ptr(slot),
+                          _ptr(rowsum), _ptr(stats), s)
+                _lib.call("mlsp_edgeconv_bn_coeffs", _ptr(stats), _ptr(p0c), _ptr(p1c), O, float(B * N * k), float(eps),
+                          _ptr(coef), _ptr(var), s)
+            else:
+                coef[0] = p0c if p0c is not None else 1.0
+                coef[1] = p1c if p1c is not None else 0.0
+                coef[2] = 0.0          # with mean = 0, invstd = 1 the backward sums are the gradients of (a, c)
+                coef[3] = 1.0
+                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(p0c), _ptr(hsel), _ptr(slot),
+                          ctypes.c_void_p(0), ctypes.c_void_p(0), s)
+            _lib.call("mlsp_edgeconv_apply_fwd", _ptr(hsel), _ptr(coef), B, N, O, float(slope), _ptr(out), s)
+        ctx.save_for_backward(yz, idx, hsel, slot, coef, rowsum if train else hsel)
+        ctx.cfg = (B, N, O, k, float(slope), train, p0 is not None, p1 is not None)
+        if train:
+            mean = coef[2].clone()
+            ctx.mark_non_differentiable(mean, var)
+            return out, mean, var
+        return out, None, None
+
+    @staticmethod
+    def backward(ctx, g, _gm, _gv):
+        yz, idx, hsel, slot, coef, rowsum = ctx.saved_tensors
+        B, N, O, k, slope, train, has0, has1 = ctx.cfg
+        dev = yz.device
+        g = g.contiguous().float()
+        dyz = torch.empty((B, N, 2 * O), dtype=torch.float32, device=dev)
+        need_p = train or has0 or has1
+        dp = torch.empty((2, O), dtype=torch.float32, device=dev) if need_p else None
+        with torch.cuda.device(dev):
+            nbytes = max(_lib.workspace_bytes(_lib.OP_EDGECONV_BWD, B, O, N, k), 16)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.call("mlsp_edgeconv_bwd", _ptr(g), _ptr(yz), _ptr(idx), _ptr(hsel), _ptr(slot),
+                      _ptr(rowsum) if train else ctypes.c_void_p(0), _ptr(coef), B, N, O, k, slope, 1 if train else 0,
+                      _ptr(dyz), _ptr(dp), _ptr(ws), ws.numel(), _stream(dev))
+        return dyz, None, (dp[0] if has0 else None), (dp[1] if has1 else None), None, None, None
+
+
+def _split_weight(weight: torch.Tensor, C: int) -> torch.Tensor:
+    """W (O,2C[,1,1]) = [Wa | Wb] over [x_j - x_i | x_i]  ->  (2O, C) = [Wa ; Wb - Wa]  (rows of Y, then rows of Z)."""
+    W = weight.reshape(weight.shape[0], -1)
+    if W.shape[1] != 2 * C:
+        raise MlspError(f"edge_conv: weight has {W.shape[1]} input channels, expected 2*C = {2 * C}")
+    Wa, Wb = W[:, :C], W[:, C:]
+    return torch.cat((Wa, Wb - Wa), dim=0)
+
+
+def edge_conv(x: torch.Tensor, weight: torch.Tensor, k: int = 20, *, bias: torch.Tensor | None = None,
+              bn: nn.BatchNorm2d | None = None, negative_slope: float | None = 0.2, idx: torch.Tensor | None = None):
+    """max_j act(bn(conv1x1(get_graph_feature(x, args, k))))  ->  (B,O,N), without the (B,2C,N,k) tensor.
+
+    x (B,C,N) or (B,C,N,1) float32 CUDA; weight (O,2C) or (O,2C,1,1); bias (O) or None; bn: the layer's
+    nn.BatchNorm2d (training mode: batch statistics over all edges and running-statistics update exactly like
+    torch.nn.functional.batch_norm; eval mode: running statistics) or None; negative_slope: LeakyReLU slope
+    (PointDA uses 0.2), 0.0 = ReLU, None = no activation (PointSegDA's shared layers).  idx (B,N,k) int64 overrides the
+    kNN graph (default: knn(x, k), PointDA/model_utils.py:9-16, same bits as the reference's ranking).
+    Differentiable w.r.t. x, weight, bias and the BatchNorm affine parameters."""
+    _require_cuda_f32(x, "edge_conv")
+    B, N = x.size(0), x.size(2)
+    x = x.reshape(B, -1, N)
+    C = x.size(1)
+    O = weight.shape[0]
+    if O % 4 != 0 or O > 1024:
+        raise MlspError(f"edge_conv: output channels must be a multiple of 4 and <= 1024, got {O}")
+    if idx is None:
+        idx = knn(x, int(k))
+    elif idx.shape != (B, N, k) or idx.dtype != torch.int64 or idx.device != x.device:
+        raise MlspError("edge_conv: idx must be int64 (B,N,k) on x's device")
+    slope = 1.0 if negative_slope is None else float(negative_slope)
+    if slope < 0.0:
+        raise MlspError("edge_conv: the activation must be non-decreasing (negative_slope >= 0)")
+    Wcat = _split_weight(weight, C)                                   # (2O, C), autograd tracks the split
+    yz = torch.matmul(x.transpose(1, 2), Wcat.t())                    # (B,N,2O): the one library GEMM of the layer
+    if bias is not None:
+        yz = yz + torch.cat((torch.zeros_like(bias), bias)).view(1, 1, 2 * O)
+    idx = idx.contiguous()
+    if bn is None:
+        out, _, _ = _EdgeConvReduce.apply(yz, idx, None, None, "affine", 0.0, slope)
+        return out
+    if bn.training or not bn.track_running_stats or bn.running_mean is None:
+        out, mean, var = _EdgeConvReduce.apply(yz, idx, bn.weight, bn.bias, "bn_train", bn.eps, slope)
+        if bn.training and bn.track_running_stats and bn.running_mean is not None:
+            with torch.no_grad():                                    # torch/nn/modules/batchnorm.py: same update rule
+                bn.num_batches_tracked += 1
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                cnt = B * N * idx.shape[2]
+                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
+                bn.running_var.mul_(1 - m).add_(var * (cnt / max(cnt - 1, 1)), alpha=m)
+        return out
+    invstd = torch.rsqrt(bn.running_var + bn.eps)
+    a = invstd * bn.weight if bn.weight is not None else invstd
+    c = -bn.running_mean * a
+    if bn.bias is not None:
+        c = c + bn.bias
+    out, _, _ = _EdgeConvReduce.apply(yz, idx, a, c, "affine", 0.0, slope)
+    return out
+
+
+class FusedEdgeConv(nn.Module):
+    """One DGCNN layer (graph feature -> 1x1 convs [-> BatchNorm2d] -> activation -> max over k) that SHARES the
+    parameters of the reference modules it is built from, so a trained / freshly initialised reference model can be
+    switched over in place and its optimiser keeps working.
+
+        FusedEdgeConv.from_reference(model.conv2, k=20)                    # PointDA conv_2d (Conv2d, BatchNorm2d, LeakyReLU)
+        FusedEdgeConv.from_reference([sl.conv1, sl.conv2], k=20)           # PointSegDA: plain Conv2d stack, no activation
+    """
+
+    def __init__(self, convs, bn=None, negative_slope=None, k: int = 20):
+        super().__init__()
+        self.convs = nn.ModuleList(convs)
+        self.bn = bn
+        self.negative_slope = negative_slope
+        self.k = k
+        for c in self.convs:
+            if not isinstance(c, nn.Conv2d) or c.kernel_size != (1, 1) or c.groups != 1:
+                raise MlspError("FusedEdgeConv: only 1x1 ungrouped Conv2d layers can be fused")
+
+    @classmethod
+    def from_reference(cls, module, k: int = 20):
+        mods = list(module) if isinstance(module, (list, tuple)) else [module]
+        flat = []
+        for m in mods:
+            inner = getattr(m, "conv", m)                   # conv_2d wraps an nn.Sequential called .conv
+            flat.extend(list(inner) if isinstance(inner, nn.Sequential) else [inner])
+        convs, bn, slope = [], None, None
+        for m in flat:
+            if isinstance(m, nn.Conv2d):
+                if bn is not None or slope is not None:
+                    raise MlspError("FusedEdgeConv: a convolution after BatchNorm / activation cannot be folded")
+                convs.append(m)
+            elif isinstance(m, nn.BatchNorm2d):
+                bn = m
+            elif isinstance(m, nn.LeakyReLU):
+                slope = m.negative_slope
+            elif isinstance(m, nn.ReLU):
+                slope = 0.0
+            else:
+                raise MlspError(f"FusedEdgeConv: cannot fuse {type(m).__name__}")
+        return cls(convs, bn, slope, k)
+
+    def effective_weight_bias(self):
+        """The stack of linear 1x1 convolutions as one (O, 2C) matrix and bias (autograd reaches every layer's parameters)."""
+        W = self.convs[0].weight.flatten(1)
+        b = self.convs[0].bias
+        for c in self.convs[1:]:
+            Wn = c.weight.flatten(1)
+            b = (Wn @ b if b is not None else None)
+            if c.bias is not None:
+                b = c.bias if b is None else b + c.bias
+            W = Wn @ W
+        return W, b
+
+    def forward(self, x, idx=None):
+        W, b = self.effective_weight_bias()
+        return edge_conv(x, W, self.k, bias=b, bn=self.bn, negative_slope=self.negative_slope, idx=idx)
+
+
+def dgcnn_backbone(model, x: torch.Tensor, k: int = 20) -> torch.Tensor:
+    """The four EdgeConv layers of the reference's PointDA DGCNN (PointDA/Models.py:114-130: conv1..conv4 on the
+    transformed cloud) through `edge_conv`; returns x_cat (B, 64+64+128+256, N) like `torch.cat((x1,x2,x3,x4), 1)`.
+    `model` is the reference's DGCNN instance (its conv_2d modules are used in place)."""
+    outs = []
+    for name in ("conv1", "conv2", "conv3", "conv4"):
+        layer = FusedEdgeConv.from_reference(getattr(model, name), k=k)
+        x = layer(x)
+        outs.append(x)
+    return torch.cat(outs, dim=1)

@@ -557,3 +557,232 @@ def test_knn3_duplicates_overflow_path(dev, orc):
     x[0, :, 100:300] = x[0, :, 100:101]              # 200 identical points: candidate lists overflow -> streaming path
     idx = _np(M.knn(x.to(dev), 20))
     assert np.array_equal(idx, orc.knn(x.numpy(), 20))
+
+
+# ------------------------------------------------------------------------------------------------ 8f rank 1: EdgeConv
+def _rel_max(got, want):
+    return float(np.abs(got - want).max()) / max(float(np.abs(want).max()), 1e-30)
+
+
+def _bn_from(g, O, dev, training=True):
+    bn = torch.nn.BatchNorm2d(O, eps=float(g["eps"]), momentum=float(g["momentum"])).to(dev)
+    with torch.no_grad():
+        bn.weight.copy_(torch.from_numpy(g["gamma"]))
+        bn.bias.copy_(torch.from_numpy(g["beta"]))
+        bn.running_mean.copy_(torch.from_numpy(g["running_mean0"]))
+        bn.running_var.copy_(torch.from_numpy(g["running_var0"]))
+    bn.train(training)
+    return bn
+
+
+@pytest.mark.parametrize("name", ["edgeconv_da_16_32", "edgeconv_da_3_64"])
+def test_edge_conv_golden_pointda_layer(golden, dev, name):
+    """edge_conv == the reference's conv_2d(get_graph_feature(x)).max(-1) (PointDA/Models.py:114-116, fixture made by the
+    reference's own modules): output, gradients of x / conv weight / BatchNorm weight and bias, running statistics
+    after the training step, and the eval-mode output."""
+    from mlsp_b200 import edgeconv
+    g = golden(name)
+    O = g["weight"].shape[0]
+    k = int(g["k"])
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    W = torch.from_numpy(g["weight"]).to(dev).requires_grad_(True)
+    idx = torch.from_numpy(g["idx"]).to(dev)
+    bn = _bn_from(g, O, dev)
+    out = edgeconv.edge_conv(x, W, k, bn=bn, negative_slope=float(g["slope"]), idx=idx)
+    assert out.shape == g["out"].shape and out.is_contiguous()
+    out.backward(torch.from_numpy(g["g"]).to(dev))
+    assert _rel_max(_np(out), g["out"]) <= RTOL
+    assert _rel_max(_np(x.grad), g["grad_x"]) <= RTOL
+    assert _rel_max(_np(W.grad), g["grad_weight"]) <= RTOL
+    assert _rel_max(_np(bn.weight.grad), g["grad_gamma"]) <= RTOL
+    assert _rel_max(_np(bn.bias.grad), g["grad_beta"]) <= RTOL
+    assert np.allclose(_np(bn.running_mean), g["running_mean1"], atol=2e-6)
+    assert np.allclose(_np(bn.running_var), g["running_var1"], rtol=1e-5, atol=2e-6)
+    assert int(bn.num_batches_tracked) == 1
+    bn.eval()
+    with torch.no_grad():
+        ev = edgeconv.edge_conv(x.detach(), W.detach(), k, bn=bn, negative_slope=float(g["slope"]), idx=idx)
+    assert _rel_max(_np(ev), g["out_eval"]) <= RTOL
+    # idx=None: the layer ranks the neighbours itself with knn() (a1)
+    with torch.no_grad():
+        ev2 = edgeconv.edge_conv(x.detach(), W.detach(), k, bn=bn, negative_slope=float(g["slope"]))
+        ev3 = edgeconv.edge_conv(x.detach(), W.detach(), k, bn=bn, negative_slope=float(g["slope"]), idx=M.knn(x.detach(), k))
+    assert torch.equal(ev2, ev3)
+
+
+def test_edge_conv_golden_pointsegda_stack(golden, dev):
+    """FusedEdgeConv over PointSegDA's conv1 -> conv2 (plain Conv2d with bias, no BatchNorm, no activation,
+    PointSegDA/Models.py:159-160,171-174): the fused module shares the two Conv2d modules, so their .grad fields are
+    what the reference's autograd produced."""
+    from mlsp_b200 import edgeconv
+    g = golden("edgeconv_seg_3_64_64")
+    k = int(g["k"])
+    H, O = g["w1"].shape[0], g["w2"].shape[0]
+    c1 = torch.nn.Conv2d(g["w1"].shape[1], H, 1, bias=True).to(dev)
+    c2 = torch.nn.Conv2d(H, O, 1, bias=True).to(dev)
+    with torch.no_grad():
+        c1.weight.copy_(torch.from_numpy(g["w1"]).view_as(c1.weight))
+        c1.bias.copy_(torch.from_numpy(g["b1"]))
+        c2.weight.copy_(torch.from_numpy(g["w2"]).view_as(c2.weight))
+        c2.bias.copy_(torch.from_numpy(g["b2"]))
+    layer = edgeconv.FusedEdgeConv.from_reference([c1, c2], k=k)
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    out = layer(x, idx=torch.from_numpy(g["idx"]).to(dev))
+    out.backward(torch.from_numpy(g["g"]).to(dev))
+    assert _rel_max(_np(out), g["out"]) <= RTOL
+    assert _rel_max(_np(x.grad), g["grad_x"]) <= RTOL
+    assert _rel_max(_np(c1.weight.grad).reshape(H, -1), g["grad_w1"]) <= RTOL
+    assert _rel_max(_np(c1.bias.grad), g["grad_b1"]) <= RTOL
+    assert _rel_max(_np(c2.weight.grad).reshape(O, -1), g["grad_w2"]) <= RTOL
+    assert _rel_max(_np(c2.bias.grad), g["grad_b2"]) <= RTOL
+
+
+def _edgeconv_case(B, C, O, N, k, seed, quantised):
+    """Inputs on which every fp32 association of the layer's sums is exact (quantised=True: x on a 2^-8 grid, W on a
+    2^-5 grid, so the reference's W.[x_j-x_i | x_i] and the fused Wa x_j + (Wb-Wa) x_i are the same numbers and ties
+    between neighbours are real ties, broken by the first neighbour on both sides), or continuous ones."""
+    gen = torch.Generator().manual_seed(seed)
+    x = synth.features(B, C, N, seed) if C != 3 else synth.clouds(B, N, seed)
+    W = torch.randn(O, 2 * C, generator=gen) * (0.3 if C != 3 else 1.0)
+    if quantised:
+        x = torch.clamp(torch.round(x * 256.0) / 256.0, -4.0, 4.0)
+        W = torch.clamp(torch.round(W * 32.0) / 32.0, -1.0, 1.0)
+    gamma = torch.randn(O, generator=gen)
+    beta = 0.5 * torch.randn(O, generator=gen)
+    bias = torch.round(torch.randn(O, generator=gen) * 16.0) / 16.0
+    gout = torch.randn(B, O, N, generator=gen)
+    return x, W, gamma, beta, bias, gout
+
+
+@pytest.mark.parametrize("B,C,O,N,k,mode", [
+    (4, 64, 64, 1024, 20, "bn_train"), (2, 64, 128, 512, 20, "bn_train"), (2, 3, 64, 700, 20, "bn_train"),
+    (2, 64, 256, 333, 9, "bn_train"), (2, 32, 24, 200, 5, "bn_train"), (2, 64, 64, 512, 20, "bn_eval"),
+    (2, 64, 64, 512, 20, "bias_linear"), (2, 16, 32, 300, 7, "relu"), (1, 8, 1024, 64, 3, "bn_train")])
+def test_edge_conv_matches_oracle_exact_inputs(dev, B, C, O, N, k, mode):
+    """edge_conv against the reference composition (oracle/edgeconv_ref.layer, CPU) on exactly-summable inputs: the
+    selected neighbour of every (point, channel) is the same on both sides (first extreme wins), so outputs and ALL
+    gradients agree to fp32 rounding -- training-mode BatchNorm with both signs of gamma (max and min over k), eval-mode
+    BatchNorm, bias without activation (PointSegDA), ReLU; O up to 1024, ragged N, small k."""
+    from mlsp_b200 import edgeconv
+    from oracle import edgeconv_ref
+    x0, W0, gamma0, beta0, bias0, gout = _edgeconv_case(B, C, O, N, k, 100 + O + N, True)
+    idx = M.knn(x0.to(dev), k)
+    bn_r = bn_g = None
+    slope = 0.2
+    use_bias = False
+    if mode in ("bn_train", "bn_eval"):
+        bn_g = torch.nn.BatchNorm2d(O).to(dev)
+        with torch.no_grad():
+            bn_g.weight.copy_(gamma0)
+            bn_g.bias.copy_(beta0)
+            bn_g.running_mean.copy_(0.1 * beta0)
+            bn_g.running_var.copy_(0.5 + gamma0.abs())
+        bn_g.train(mode == "bn_train")
+    elif mode == "bias_linear":
+        slope, use_bias = None, True
+    elif mode == "relu":
+        slope, use_bias = 0.0, True
+    # ---- ours
+    x = x0.to(dev).requires_grad_(True)
+    W = W0.to(dev).requires_grad_(True)
+    bias = bias0.to(dev).requires_grad_(True) if use_bias else None
+    rm0 = bn_g.running_mean.clone() if bn_g is not None else None
+    rv0 = bn_g.running_var.clone() if bn_g is not None else None
+    out = edgeconv.edge_conv(x, W, k, bias=bias, bn=bn_g, negative_slope=slope, idx=idx)
+    out.backward(gout.to(dev))
+    # ---- reference composition on the CPU
+    xr = x0.clone().requires_grad_(True)
+    Wr = W0.clone().requires_grad_(True)
+    br = bias0.clone().requires_grad_(True) if use_bias else None
+    gr = gamma0.clone().requires_grad_(True)
+    btr = beta0.clone().requires_grad_(True)
+    running = (rm0.cpu().clone(), rv0.cpu().clone()) if bn_g is not None else None
+    ref = edgeconv_ref.layer(xr, idx.cpu(), [Wr], [br], gr, btr, bn=bn_g is not None, eps=1e-5, slope=slope,
+                             running=running, momentum=0.1, training=(mode == "bn_train"))
+    ref.backward(gout)
+    assert _rel_max(_np(out), ref.detach().numpy()) <= RTOL
+    assert _rel_max(_np(x.grad), xr.grad.numpy()) <= RTOL
+    assert _rel_max(_np(W.grad), Wr.grad.numpy()) <= RTOL
+    if use_bias:
+        assert _rel_max(_np(bias.grad), br.grad.numpy()) <= RTOL
+    if bn_g is not None:
+        assert _rel_max(_np(bn_g.weight.grad), gr.grad.numpy()) <= RTOL
+        assert _rel_max(_np(bn_g.bias.grad), btr.grad.numpy()) <= RTOL
+        assert np.allclose(_np(bn_g.running_mean), running[0].numpy(), atol=1e-5)
+        assert np.allclose(_np(bn_g.running_var), running[1].numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_edge_conv_continuous_full_size(dev):
+    """Config A layer shapes on continuous activations (C=64 -> O=64 and C=128 -> O=256, 8 x 1024, k=20, training-mode
+    BatchNorm): the output agrees to 1e-5; for the gradients a neighbour whose pre-activation is within rounding of the
+    maximum may be selected on one side and not the other (the reference itself is not reproducible at that level
+    between devices), which moves O(1e-5) of the entries -- so >= 99.5 % of them must agree to 1e-5 and the rest must be
+    small in norm."""
+    from mlsp_b200 import edgeconv
+    from oracle import edgeconv_ref
+    for C, O in ((64, 64), (128, 256)):
+        B, N, k = 8, 1024, 20
+        x0, W0, gamma0, beta0, _, gout = _edgeconv_case(B, C, O, N, k, 7 + C, False)
+        idx = M.knn(x0.to(dev), k)
+        bn = torch.nn.BatchNorm2d(O).to(dev)
+        with torch.no_grad():
+            bn.weight.copy_(gamma0)
+            bn.bias.copy_(beta0)
+        x = x0.to(dev).requires_grad_(True)
+        W = W0.to(dev).requires_grad_(True)
+        out = edgeconv.edge_conv(x, W, k, bn=bn, negative_slope=0.2, idx=idx)
+        out.backward(gout.to(dev))
+        xr, Wr = x0.clone().requires_grad_(True), W0.clone().requires_grad_(True)
+        gr, btr = gamma0.clone().requires_grad_(True), beta0.clone().requires_grad_(True)
+        ref = edgeconv_ref.layer(xr, idx.cpu(), [Wr], None, gr, btr, bn=True, slope=0.2)
+        ref.backward(gout)
+        assert _rel_max(_np(out), ref.detach().numpy()) <= RTOL
+        for got, want in ((x.grad, xr.grad), (W.grad, Wr.grad), (bn.weight.grad, gr.grad), (bn.bias.grad, btr.grad)):
+            a, b = _np(got), want.numpy()
+            scale = np.abs(b).max()
+            ok = np.abs(a - b) <= RTOL * scale
+            assert ok.mean() >= 0.995, (C, O, float(ok.mean()))
+            assert np.linalg.norm(a - b) <= 2e-2 * np.linalg.norm(b), (C, O)
+
+
+def test_edge_conv_dgcnn_backbone_and_errors(dev):
+    """dgcnn_backbone over reference-shaped conv_2d modules (Sequential(Conv2d, BatchNorm2d, LeakyReLU) in `.conv`,
+    PointDA/model_utils.py:45-63) == the same modules fed by the drop-in get_graph_feature, layer by layer; the fused
+    path leaves parameter gradients in the shared modules; unsupported shapes raise."""
+    import types
+    from mlsp_b200 import edgeconv
+    torch.manual_seed(3)
+    B, N, k = 2, 512, 20
+
+    def make():
+        torch.manual_seed(5)
+        m = types.SimpleNamespace()
+        for name, (i, o) in zip(("conv1", "conv2", "conv3", "conv4"), ((6, 64), (128, 64), (128, 128), (256, 256))):
+            seq = torch.nn.Sequential(torch.nn.Conv2d(i, o, 1, bias=False), torch.nn.BatchNorm2d(o), torch.nn.LeakyReLU(0.2)).to(dev)
+            setattr(m, name, types.SimpleNamespace(conv=seq))
+        return m
+
+    x0 = synth.surface_clouds(B, N, 17).to(dev)
+    ma, mb = make(), make()
+    xa = x0.clone().requires_grad_(True)
+    cat_a = edgeconv.dgcnn_backbone(ma, xa, k=k)
+    xb = x0.clone().requires_grad_(True)
+    h, feats = xb, []
+    for name in ("conv1", "conv2", "conv3", "conv4"):
+        h = getattr(mb, name).conv(M.get_graph_feature(h, None, k=k)).max(dim=-1)[0]
+        feats.append(h)
+    cat_b = torch.cat(feats, dim=1)
+    assert cat_a.shape == (B, 512, N)
+    # deeper layers see neighbourhoods chosen from activations that differ by rounding, so compare layer 1 strictly and
+    # the whole stack in norm
+    assert float((cat_a[:, :64] - cat_b[:, :64]).abs().max()) <= 1e-4 * float(cat_b[:, :64].abs().max())
+    assert float((cat_a - cat_b).norm()) <= 1e-2 * float(cat_b.norm())
+    (cat_a ** 2).mean().backward()
+    assert xa.grad is not None and all(p.grad is not None for n in ("conv1", "conv4") for p in getattr(ma, n).conv.parameters())
+    assert int(ma.conv1.conv[1].num_batches_tracked) == 1
+    with pytest.raises(M.MlspError):
+        edgeconv.edge_conv(x0, torch.zeros(6, 6, device=dev), k)                 # O % 4 != 0
+    with pytest.raises(M.MlspError):
+        edgeconv.edge_conv(x0, torch.zeros(8, 8, device=dev), k)                 # weight is not (O, 2C)
+    with pytest.raises(M.MlspError):
+        edgeconv.edge_conv(x0, torch.zeros(8, 6, device=dev), k, negative_slope=-0.1)

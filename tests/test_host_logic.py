@@ -168,3 +168,37 @@ def test_two_rank_sharding_over_gloo():
     assert t0 == t1 == 2.0                                          # max over ranks
     assert c0 == c1 == [17, 16] and sum(c0) == 33
     assert s0 != s1                                                 # different shards
+
+
+def test_edgeconv_weight_algebra():
+    """Host algebra of mlsp_b200.edgeconv (CPU part only): the [Wa ; Wb-Wa] split reproduces W.[x_j-x_i | x_i], and a
+    stack of plain 1x1 convolutions with biases folds into one (W, b) -- the facts edge_conv's single GEMM rests on."""
+    from mlsp_b200 import edgeconv
+    torch.manual_seed(0)
+    C, O = 5, 8
+    W = torch.randn(O, 2 * C, 1, 1, dtype=torch.float64)
+    xi, xj = torch.randn(C, dtype=torch.float64), torch.randn(C, dtype=torch.float64)
+    Wcat = edgeconv._split_weight(W, C)
+    want = W.flatten(1) @ torch.cat((xj - xi, xi))
+    got = Wcat[:O] @ xj + Wcat[O:] @ xi
+    assert torch.allclose(got, want, atol=1e-12)
+    with pytest.raises(M.MlspError):
+        edgeconv._split_weight(W, C + 1)
+    c1 = torch.nn.Conv2d(2 * C, 6, 1, bias=True).double()
+    c2 = torch.nn.Conv2d(6, O, 1, bias=False).double()
+    c3 = torch.nn.Conv2d(O, O, 1, bias=True).double()
+    layer = edgeconv.FusedEdgeConv.from_reference([c1, c2, c3], k=4)
+    Weff, beff = layer.effective_weight_bias()
+    e = torch.randn(2, 2 * C, 7, 3, dtype=torch.float64)
+    want = c3(c2(c1(e)))
+    got = torch.einsum("oc,bcnk->bonk", Weff, e) + beff.view(1, -1, 1, 1)
+    assert torch.allclose(got, want, atol=1e-12)
+    assert layer.bn is None and layer.negative_slope is None
+    seq = torch.nn.Sequential(torch.nn.Conv2d(6, 8, 1, bias=False), torch.nn.BatchNorm2d(8), torch.nn.LeakyReLU(0.2))
+    wrapped = types.SimpleNamespace(conv=seq)                       # shape of the reference's conv_2d module
+    layer = edgeconv.FusedEdgeConv.from_reference(wrapped, k=20)
+    assert layer.bn is seq[1] and layer.negative_slope == 0.2 and layer.convs[0] is seq[0]
+    with pytest.raises(M.MlspError):
+        edgeconv.FusedEdgeConv.from_reference([seq, torch.nn.Conv2d(8, 8, 1)])
+    with pytest.raises(M.MlspError):
+        edgeconv.edge_conv(torch.zeros(1, 3, 8), torch.zeros(4, 6))   # no CPU path

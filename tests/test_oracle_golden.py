@@ -202,3 +202,52 @@ def test_ref_torch_restatements_match_oracle():
     on, gap = np_ops.pca_normals(pts.numpy(), 20, return_gap=True)
     ok = gap > 1e-2
     assert (1 - np.abs((n * on).sum(-1))[ok]).max() < 1e-3
+
+
+# ---- the EdgeConv layer (reference composition restated in oracle/edgeconv_ref.py)
+def _t(a):
+    import torch
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("name", ["edgeconv_da_16_32", "edgeconv_da_3_64"])
+def test_edgeconv_oracle_pointda_layer(golden, name):
+    """oracle.edgeconv_ref.layer == the reference's conv_2d(get_graph_feature(x)).max(-1) (PointDA/Models.py:114-116):
+    forward, every gradient, the running statistics after one training step, and the eval-mode forward."""
+    import torch
+    from oracle import edgeconv_ref
+    torch.set_num_threads(1)
+    g = golden(name)
+    x = _t(g["x"]).requires_grad_(True)
+    W = _t(g["weight"]).requires_grad_(True)
+    gamma = _t(g["gamma"]).requires_grad_(True)
+    beta = _t(g["beta"]).requires_grad_(True)
+    rm, rv = _t(g["running_mean0"]).clone(), _t(g["running_var0"]).clone()
+    idx = _t(g["idx"])
+    out = edgeconv_ref.layer(x, idx, [W], None, gamma, beta, bn=True, eps=float(g["eps"]), slope=float(g["slope"]),
+                             running=(rm, rv), momentum=float(g["momentum"]), training=True)
+    out.backward(_t(g["g"]))
+    assert np.allclose(out.detach().numpy(), g["out"], rtol=0, atol=1e-6 * np.abs(g["out"]).max())
+    for got, want in ((x.grad, "grad_x"), (W.grad, "grad_weight"), (gamma.grad, "grad_gamma"), (beta.grad, "grad_beta")):
+        assert np.allclose(got.numpy(), g[want], rtol=0, atol=2e-6 * np.abs(g[want]).max()), want
+    assert np.allclose(rm.numpy(), g["running_mean1"], atol=1e-6) and np.allclose(rv.numpy(), g["running_var1"], atol=1e-6)
+    with torch.no_grad():
+        ev = edgeconv_ref.layer(x, idx, [W], None, gamma, beta, bn=True, eps=float(g["eps"]), slope=float(g["slope"]),
+                                running=(rm, rv), training=False)
+    assert np.allclose(ev.numpy(), g["out_eval"], rtol=0, atol=1e-6 * np.abs(g["out_eval"]).max())
+
+
+def test_edgeconv_oracle_pointsegda_layer(golden):
+    """== conv2(conv1(get_graph_feature(x))).max(-1) of PointSegDA/Models.py:171-174 (plain Conv2d stack with bias)."""
+    import torch
+    from oracle import edgeconv_ref
+    torch.set_num_threads(1)
+    g = golden("edgeconv_seg_3_64_64")
+    x = _t(g["x"]).requires_grad_(True)
+    ps = {n: _t(g[n]).requires_grad_(True) for n in ("w1", "b1", "w2", "b2")}
+    out = edgeconv_ref.layer(x, _t(g["idx"]), [ps["w1"], ps["w2"]], [ps["b1"], ps["b2"]])
+    out.backward(_t(g["g"]))
+    assert np.allclose(out.detach().numpy(), g["out"], rtol=0, atol=1e-6 * np.abs(g["out"]).max())
+    assert np.allclose(x.grad.numpy(), g["grad_x"], rtol=0, atol=2e-6 * np.abs(g["grad_x"]).max())
+    for n in ps:
+        assert np.allclose(ps[n].grad.numpy(), g["grad_" + n], rtol=0, atol=2e-6 * np.abs(g["grad_" + n]).max()), n
