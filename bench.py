@@ -14,7 +14,7 @@ All of it goes through the reference-signature API of mlsp_b200 (ctypes -> libml
 conv / BN / head layers of DGCNN are out of scope and are not part of the step; the
 layer inputs and upstream gradients they would produce are synthetic tensors resident in HBM.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A|S]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload A|S|X|E]
   torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, batch sharded, weak scaling)
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference
@@ -667,6 +667,275 @@ def run_workload_x(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------- workload E
+EC_LAYERS = ((3, 64), (64, 64), (64, 128), (128, 256))        # PointDA/Models.py:91-94 conv1..conv4 (in = 2C)
+
+
+def _ec_make_layers(device):
+    """conv_2d-shaped modules of the reference's DGCNN backbone (PointDA/model_utils.py:45-63), seeded init."""
+    torch.manual_seed(0)
+    return [torch.nn.Sequential(torch.nn.Conv2d(2 * C, O, 1, bias=False), torch.nn.BatchNorm2d(O), torch.nn.LeakyReLU(0.2)).to(device)
+            for C, O in EC_LAYERS]
+
+
+def _ec_reference_step(layers, clouds, k, ggf, knn):
+    """The reference's backbone step, op for op (PointDA/Models.py:114-130): graph feature -> conv_2d -> max over k, four
+    times, concatenated; loss = mean square; backward to the cloud and every parameter."""
+    x = clouds.detach().requires_grad_(True)
+    h, feats = x, []
+    for seq in layers:
+        h = seq(ggf(h, k, knn(h.detach(), k))).max(dim=-1, keepdim=False)[0]
+        feats.append(h)
+    loss = torch.cat(feats, dim=1).square().mean()
+    for seq in layers:
+        for p_ in seq.parameters():
+            p_.grad = None
+    loss.backward()
+    return loss
+
+
+def run_workload_e(args):
+    """SURVEY.md 8f rank 1 (`--workload E`): the four EdgeConv layers of the PointDA DGCNN backbone (C -> O = 3->64, 64->64,
+    64->128, 128->256; training-mode BatchNorm, LeakyReLU 0.2, max over k = 20) forward + backward on 32 x 1024 clouds,
+    chained like the model chains them, through mlsp_b200.edgeconv (no (B,2C,N,k) tensor).  The reference arm and the CPU
+    baseline run the reference's own composition (get_graph_feature -> Conv2d -> BatchNorm2d -> LeakyReLU -> max)."""
+    from mlsp_b200 import synth
+    B, N, k = synth.CONFIGS["A"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "MLSP clouds/sec (Bx1024,k=20) DGCNN EdgeConv backbone fwd+bwd"
+    cfg = {"workload": "edgeconv-E", "clouds_per_gpu": B, "points": N, "k": k, "layers_C_O": [list(l) for l in EC_LAYERS],
+           "batchnorm": "training mode (batch statistics over B*N*k edges, running statistics updated)",
+           "parallelism": f"batch-sharded x{world}, no data-path collective (BatchNorm statistics per rank, like the "
+                          "reference's DataParallel replicas)"}
+
+    def cpu_time(Bs, reps):
+        from oracle import ref_torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        layers = _ec_make_layers("cpu")
+        clouds = synth.surface_clouds(Bs, N, 1234)
+        _ec_reference_step(layers, clouds, k, ref_torch.get_graph_feature, ref_torch.knn)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            _ec_reference_step(layers, clouds, k, ref_torch.get_graph_feature, ref_torch.knn)
+        return (time.perf_counter() - t0) / reps
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        Bs = 4
+        for _ in range(max(args.warmup - 1, 0)):
+            cpu_time(Bs, 1)
+        dt = cpu_time(Bs, max(args.steps, 1))
+        val = Bs / dt
+        sample = (f"{Bs} of {B} clouds per step; the reference's layer composition (oracle/ref_torch.py get_graph_feature + "
+                  "torch Conv2d/BatchNorm2d/LeakyReLU/max, autograd backward) on the host cores")
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": dict(cfg, device="cpu"),
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+
+    import mlsp_b200 as M
+    from mlsp_b200 import _lib, edgeconv
+    from mlsp_b200.ops import _ptr, _stream
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host = synth.surface_clouds(B, N, 1234 + rank).pin_memory()
+    clouds = host.to(device)
+    layers = _ec_make_layers(device)
+    fused = [edgeconv.FusedEdgeConv.from_reference(seq, k=k) for seq in layers]
+    params = [p_ for seq in layers for p_ in seq.parameters()]
+
+    def step_eager():
+        x = clouds.detach().requires_grad_(True)
+        h, feats = x, []
+        for f in fused:
+            h = f(h)
+            feats.append(h)
+        loss = torch.cat(feats, dim=1).square().mean()
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            for p_ in params:
+                p_.grad = None
+            step_eager()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for p_ in params:
+        p_.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss_static = step_eager()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        graph.replay()
+    if sampler:
+        sampler.wait_first_sample(graph.replay)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1) / args.steps
+    if sampler:
+        sampler.keep_load(graph.replay, min_samples=5, max_s=3.0)
+    clocks = sampler.stop() if sampler else None
+    # end to end: pinned host clouds in, the loss out, every step
+    for _ in range(2):
+        clouds.copy_(host, non_blocking=True)
+        graph.replay()
+        loss_static.item()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        clouds.copy_(host, non_blocking=True)
+        graph.replay()
+        lv = loss_static.item()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / args.steps * 1e3
+
+    # per-kernel spans through the C ABI on buffers of each layer's shape (CUDA events on the launching stream)
+    def span(fn, reps=20):
+        for _ in range(3):
+            fn()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b_) / reps
+
+    per = {}
+    P = B * N
+    h = clouds
+    s_ = _stream(device)
+    for (C, O), f in zip(EC_LAYERS, fused):
+        with torch.no_grad():
+            idx = M.knn(h, k)
+            W, _b = f.effective_weight_bias()
+            yz = torch.matmul(h.transpose(1, 2), edgeconv._split_weight(W, C).t()).contiguous()
+            hsel = torch.empty((B, N, O), device=device)
+            slot = torch.empty((B, N, O), dtype=torch.uint8, device=device)
+            rowsum = torch.empty((B, N, O), device=device)
+            stats = torch.empty((2, O), dtype=torch.float64, device=device)
+            coef = torch.empty((4, O), device=device)
+            gam = f.bn.weight.detach()
+            g = torch.randn(B, O, N, device=device)
+            dyz = torch.empty((B, N, 2 * O), device=device)
+            dp = torch.empty((2, O), device=device)
+            ws = torch.empty(_lib.workspace_bytes(_lib.OP_EDGECONV_BWD, B, O, N, k), dtype=torch.uint8, device=device)
+
+            def red():
+                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(gam), _ptr(hsel), _ptr(slot),
+                          _ptr(rowsum), _ptr(stats), s_)
+
+            def bwd():
+                _lib.call("mlsp_edgeconv_bwd", _ptr(g), _ptr(yz), _ptr(idx), _ptr(hsel), _ptr(slot), _ptr(rowsum), _ptr(coef),
+                          B, N, O, k, 0.2, 1, _ptr(dyz), _ptr(dp), _ptr(ws), ws.numel(), s_)
+
+            red()
+            _lib.call("mlsp_edgeconv_bn_coeffs", _ptr(stats), _ptr(gam), _ptr(f.bn.bias.detach()), O, float(P * k), 1e-5,
+                      _ptr(coef), None, s_)
+            per[f"reduce_fwd_O{O}_C{C}"] = (span(red), P * (17 * O + 8 * k), 4.0 * P * k * O)
+            per[f"bwd_O{O}_C{C}"] = (span(bwd), P * (29 * O + 8 * k), 4.0 * P * k * O)
+            per[f"knn_C{C}"] = (span(lambda: M.knn(h, k)), None, None)
+            h = f(h)
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_ms, e2e_ms = max_over_ranks(dev_ms), max_over_ranks(e2e_ms)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    fam = {}
+    for name, (ms, by, l2) in per.items():
+        if by is None:
+            continue
+        d = fam.setdefault(name.split("_O")[0], [0.0, 0.0, 0.0, 0])
+        d[0] += ms
+        d[1] += by
+        d[2] += l2
+        d[3] += 1
+    dom = max(fam, key=lambda n: fam[n][0])
+    ms, by, l2, n = fam[dom]
+    ach = by / (ms * 1e-3) / 1e9
+    kern = {"reduce_fwd": "edgeconv_reduce_kernel", "bwd": "edgeconv_bwd_scatter_kernel"}[dom]
+    roof = {"kernel": kern, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            "traffic": None, "peak_source": pk["source"], "algorithmic_bytes_per_launch": by / n, "ms_per_launch": ms / n,
+            "launches_per_step": n, "ops": [x for x in per if x.startswith(dom)],
+            "l2_gather_bytes_per_launch": l2 / n, "l2_gather_GBps": l2 / (ms * 1e-3) / 1e9,
+            "note": "call-level span of mlsp_edgeconv_%s over the four layer shapes; algorithmic HBM bytes are the compact "
+                    "(B,N,O) tensors and idx -- the k row gathers (forward) / 128-bit reductions (backward) of 4*B*N*k*O bytes "
+                    "go to L2, which is what bounds the kernel (l2_gather_GBps)" % ("reduce_fwd" if dom == "reduce_fwd" else "bwd")}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        t = cpu_time(4, 2)
+        cpu = {"value": 4 / t, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"2 steps on 4 of {B} clouds ({2 * t:.1f} s); the reference's layer composition on the host cores"}
+    # context: the same reference composition on this GPU (torch kernels, cuDNN off like the reference's trainers),
+    # and the drop-in composition (our fused get_graph_feature feeding torch's Conv2d/BatchNorm2d/max)
+    from oracle import ref_torch
+    ctx = {}
+    with torch.backends.cudnn.flags(enabled=False):
+        ref_layers = _ec_make_layers(device)
+        for name, ggf, knn_ in (("torch_gpu_reference_ms", ref_torch.get_graph_feature, ref_torch.knn),
+                                ("dropin_graph_feature_plus_torch_layers_ms",
+                                 lambda x_, k_, idx_: M.get_graph_feature(x_, None, k=k_, idx=idx_), M.knn)):
+            for _ in range(2):
+                _ec_reference_step(ref_layers, clouds, k, ggf, knn_)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                _ec_reference_step(ref_layers, clouds, k, ggf, knn_)
+            torch.cuda.synchronize()
+            ctx[name] = round((time.perf_counter() - t0) / 3 * 1e3, 3)
+    launches_per_step = sum((1 if C == 3 else 3) + 3 + 4 for C, _ in EC_LAYERS)
+    line = {"metric": metric, "value": B * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(cfg, graphs="one CUDA graph of the chained forward + backward, captured through the public API",
+                           l2="per-step working set (activations, yz, gradients, workspaces) ~0.6 GB >> 126 MB L2; no explicit flush"),
+            "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(host.numel() * 4), "d2h_bytes_per_step": 4, "loss": lv},
+            "gpu_launches": launches_per_step * args.steps,
+            "op_ms_per_call": {n_: round(v[0], 4) for n_, v in per.items()},
+            "roofline": roof, "cpu_baseline": cpu, "context": ctx, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -674,9 +943,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="A", choices=["A", "S", "X"],
+    ap.add_argument("--workload", default="A", choices=["A", "S", "X", "E"],
                     help="A: PointDA-10 hot path (default, the BASELINE metric); S: PointSegDA hot path; "
-                         "X: the scaling-sweep shape 256x4096, k=40 -- feature-space kNN on 64/128-dim features (configs[4])")
+                         "X: the scaling-sweep shape 256x4096, k=40 -- feature-space kNN on 64/128-dim features (configs[4]); "
+                         "E: the DGCNN EdgeConv backbone without the edge tensor (SURVEY 8f rank 1), forward + backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="headline on one stream (no target-builder overlap)")
     ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")
@@ -689,6 +959,8 @@ def main():
     from mlsp_b200 import synth
     if args.workload == "X":
         return run_workload_x(args)
+    if args.workload == "E":
+        return run_workload_e(args)
     set_workload(args.workload)
     B, N, k = synth.CONFIGS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

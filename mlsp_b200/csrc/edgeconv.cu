@@ -54,8 +54,8 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         uchar4 sl = make_uchar4(0, 0, 0, 0);
         float4 rs = make_float4(0.f, 0.f, 0.f, 0.f), rq = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int j = 0; j < k; ++j) {
+#pragma unroll 5
+        for (int j = 0; j < k; ++j) {                         // k = 20: four batches of five independent (idx, row) loads
             const long long nb = ip[j];
             const float4 y = __ldg(yb + nb * 2 * G);
             const float4 h = make_float4(y.x + z.x, y.y + z.y, y.z + z.z, y.w + z.w);
@@ -141,8 +141,8 @@ edgeconv_apply_kernel(const float *__restrict__ hsel, const float *__restrict__ 
 
 // ------------------------------------------------------------------------------------------------ backward
 // dy[b,i,o] = g[b,o,i] * lrelu'(a*hsel + c); with SUMS also dsum[o] += dy, dsum[O+o] += dy * (hsel - mean) * invstd.
-// A block owns 32 channels x EC_PTS points so that it ends with 64 atomics.
-static constexpr int EC_PTS = 256;
+// A block owns 32 channels x EC_PTS points and ends with 64 fp64 atomics.
+static constexpr int EC_PTS = 64;
 template <bool SUMS>
 __global__ void __launch_bounds__(256)
 edgeconv_bwd_prepare_kernel(const float *__restrict__ g, const float *__restrict__ hsel, const float *__restrict__ coef, int N,
@@ -306,8 +306,12 @@ int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, 
     cudaStream_t s = as_stream(stream);
     const int G = O / 4, threads = ec_block(G);
     const long long items = (long long)B * N * G;
-    long long want = (items + threads - 1) / threads;
-    const int grid = (int)(want < 4LL * sm_count() ? want : 4LL * sm_count());
+    // persistent grid: exactly the resident blocks (one wave), so that the grid-stride loop is balanced
+    int per_sm = 0;
+    if (stats) MLSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edgeconv_reduce_kernel<true>, threads, 0));
+    else MLSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edgeconv_reduce_kernel<false>, threads, 0));
+    const long long want = (items + threads - 1) / threads, resident = (long long)(per_sm > 0 ? per_sm : 1) * sm_count();
+    const int grid = (int)(want < resident ? want : resident);
     if (stats) {
         MLSP_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * O * sizeof(double), s));
         edgeconv_reduce_kernel<true><<<grid, threads, 0, s>>>(reinterpret_cast<const float4 *>(yz), idx, N, G, k, items, sgn_src,

@@ -71,3 +71,16 @@ def test_fused_call_accounting(bench):
     B, N, k = 32, 1024, 20
     assert bench.algorithmic_bytes("ggf_fwd_C64", B, N, k) == bench.algorithmic_bytes("edge_fwd_C64", B, N, k)
     assert bench.LAUNCHES["ggf_tensor"] == 3 and bench.LAUNCHES["ggf3"] == 1
+
+
+def test_workload_e_reference_arm_line(bench):
+    """SURVEY 8f rank 1 (`--workload E`, the EdgeConv backbone): the reference arm runs the reference's layer composition on
+    a bounded sample and prints the contract's line; the layer list is the PointDA DGCNN's conv1..conv4."""
+    assert bench.EC_LAYERS == ((3, 64), (64, 64), (64, 128), (128, 256))          # PointDA/Models.py:91-94
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "E", "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "clouds/s" and line["value"] > 0
+    assert line["config"]["workload"] == "edgeconv-E" and line["config"]["points"] == 1024 and line["config"]["k"] == 20
+    assert line["cpu_baseline"]["kind"] == "port" and line["gpu_launches"] == 0
