@@ -217,12 +217,13 @@ MLSP_API int mlsp_edgeconv_bn_coeffs(const double *stats, const float *gamma, co
 MLSP_API int mlsp_edgeconv_apply_fwd(const float *hsel, const float *coef, int B, int N, int O, float slope, float *out,
                             void *stream);
 
-/* backward: g (B,O,N) = d loss / d out  ->  dyz (B,N,2O) = [dY | dZ] (overwritten).
+/* backward: g (B,O,N) = d loss / d out, rows dense, batches g_bstride floats apart (O*N when contiguous; a channel slice
+ *   of a concatenated gradient, as torch.cat's backward hands it over, is used in place)  ->  dyz (B,N,2O) = [dY | dZ].
  *   bn_train != 0: exact gradient through the batch statistics (needs rowsum and coef rows 2,3 = mean, invstd);
  *   dgamma_dbeta (2,O), may be NULL when bn_train == 0: [sum dy*(hsel-mean)*invstd ; sum dy], dy = g*lrelu'(.) -- the
  *   gradients of gamma and beta, or of (a, c) when the caller sets mean = 0, invstd = 1 (fixed affine / bias).
  *   ws: mlsp_workspace_bytes(MLSP_OP_EDGECONV_BWD, B, O, N, k). */
-MLSP_API int mlsp_edgeconv_bwd(const float *g, const float *yz, const int64_t *idx, const float *hsel, const uint8_t *slot,
+MLSP_API int mlsp_edgeconv_bwd(const float *g, int64_t g_bstride, const float *yz, const int64_t *idx, const float *hsel, const uint8_t *slot,
                       const float *rowsum, const float *coef, int B, int N, int O, int k, float slope, int bn_train,
                       float *dyz, float *dgamma_dbeta, void *ws, size_t ws_bytes, void *stream);
 

@@ -30,8 +30,8 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ?
 // ------------------------------------------------------------------------------------------------ forward
 // grid-stride over (point, float4-of-channels) items with a stride that is a multiple of G = O/4, so a thread keeps
 // its channels and the statistics stay in registers until the end.
-template <bool STATS>
-__global__ void __launch_bounds__(EC_THREADS)
+template <bool STATS, bool SIGNED>
+__global__ void __launch_bounds__(EC_THREADS, 4)
 edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict__ idx, int N, int G, int k, long long items,
                        const float *__restrict__ sgn_src, float4 *__restrict__ hsel, uchar4 *__restrict__ slot,
                        float4 *__restrict__ rowsum, double *__restrict__ stats)
@@ -40,7 +40,7 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
     const int c4 = threadIdx.x % G;                           // blockDim.x % G == 0
     const long long stride = (long long)gridDim.x * blockDim.x;
     float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (sgn_src) {
+    if (SIGNED) {
         const float4 s = reinterpret_cast<const float4 *>(sgn_src)[c4];
         sg = make_float4(s.x < 0.f ? -1.f : 1.f, s.y < 0.f ? -1.f : 1.f, s.z < 0.f ? -1.f : 1.f, s.w < 0.f ? -1.f : 1.f);
     }
@@ -59,7 +59,7 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
             const long long nb = ip[j];
             const float4 y = __ldg(yb + nb * 2 * G);
             const float4 h = make_float4(y.x + z.x, y.y + z.y, y.z + z.z, y.w + z.w);
-            const float4 t = make_float4(h.x * sg.x, h.y * sg.y, h.z * sg.z, h.w * sg.w);
+            const float4 t = SIGNED ? make_float4(h.x * sg.x, h.y * sg.y, h.z * sg.z, h.w * sg.w) : h;
             if (t.x > m.x) { m.x = t.x; sl.x = (unsigned char)j; }      // strict: the first extreme wins
             if (t.y > m.y) { m.y = t.y; sl.y = (unsigned char)j; }
             if (t.z > m.z) { m.z = t.z; sl.z = (unsigned char)j; }
@@ -69,7 +69,7 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
                 rq.x = fmaf(h.x, h.x, rq.x); rq.y = fmaf(h.y, h.y, rq.y); rq.z = fmaf(h.z, h.z, rq.z); rq.w = fmaf(h.w, h.w, rq.w);
             }
         }
-        hsel[p * G + c4] = make_float4(m.x * sg.x, m.y * sg.y, m.z * sg.z, m.w * sg.w);
+        hsel[p * G + c4] = SIGNED ? make_float4(m.x * sg.x, m.y * sg.y, m.z * sg.z, m.w * sg.w) : m;
         slot[p * G + c4] = sl;
         if (STATS) {
             rowsum[p * G + c4] = rs;
@@ -141,40 +141,42 @@ edgeconv_apply_kernel(const float *__restrict__ hsel, const float *__restrict__ 
 
 // ------------------------------------------------------------------------------------------------ backward
 // dy[b,i,o] = g[b,o,i] * lrelu'(a*hsel + c); with SUMS also dsum[o] += dy, dsum[O+o] += dy * (hsel - mean) * invstd.
-// A block owns 32 channels x EC_PTS points and ends with 64 fp64 atomics.
-static constexpr int EC_PTS = 64;
+// A block owns a 32-channel x 32-point tile (both global loads of a thread are issued before the barrier) and ends
+// with 64 fp64 atomics.
+static constexpr int EC_PTS = 32;
 template <bool SUMS>
 __global__ void __launch_bounds__(256)
-edgeconv_bwd_prepare_kernel(const float *__restrict__ g, const float *__restrict__ hsel, const float *__restrict__ coef, int N,
-                            int O, float slope, float *__restrict__ dy, double *__restrict__ dsum)
+edgeconv_bwd_prepare_kernel(const float *__restrict__ g, long long g_bstride, const float *__restrict__ hsel,
+                            const float *__restrict__ coef, int N, int O, float slope, float *__restrict__ dy,
+                            double *__restrict__ dsum)
 {
     __shared__ float tile[32][33];
     __shared__ double red[2][8][32];
-    const int b = blockIdx.z, o0 = blockIdx.y * 32;
+    const int b = blockIdx.z, o0 = blockIdx.y * 32, i0 = blockIdx.x * EC_PTS;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int o = o0 + tx;
     const float a = o < O ? coef[o] : 0.f, c = o < O ? coef[O + o] : 0.f;
     const float mean = o < O ? coef[2 * O + o] : 0.f, invstd = o < O ? coef[3 * O + o] : 0.f;
+    float hs[4], gv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 8 * r;                       // point-major side, coalesced along o
+        hs[r] = (i < N && o < O) ? hsel[((long long)b * N + i) * O + o] : 0.f;
+        const int oo = o0 + ty + 8 * r, ig = i0 + tx;        // g tile, coalesced along i
+        gv[r] = (oo < O && ig < N) ? g[b * g_bstride + (long long)oo * N + ig] : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) tile[ty + 8 * r][tx] = gv[r];
+    __syncthreads();
     double sb = 0.0, sgm = 0.0;
-    for (int i0 = blockIdx.x * EC_PTS; i0 < min(N, (int)(blockIdx.x + 1) * EC_PTS); i0 += 32) {
 #pragma unroll
-        for (int r = ty; r < 32; r += 8) {                   // g tile, coalesced along i
-            const int oo = o0 + r, i = i0 + tx;
-            tile[r][tx] = (oo < O && i < N) ? g[((long long)b * O + oo) * N + i] : 0.f;
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 8 * r;
+        if (i < N && o < O) {
+            const float d = tile[tx][ty + 8 * r] * (fmaf(a, hs[r], c) > 0.0f ? 1.0f : slope);
+            dy[((long long)b * N + i) * O + o] = d;
+            if (SUMS) { sb += d; sgm += (double)d * (double)((hs[r] - mean) * invstd); }
         }
-        __syncthreads();
-#pragma unroll
-        for (int r = ty; r < 32; r += 8) {                   // point-major side, coalesced along o
-            const int i = i0 + r;
-            if (i < N && o < O) {
-                const long long e = ((long long)b * N + i) * O + o;
-                const float hs = hsel[e];
-                const float d = tile[tx][r] * (fmaf(a, hs, c) > 0.0f ? 1.0f : slope);
-                dy[e] = d;
-                if (SUMS) { sb += d; sgm += (double)d * (double)((hs - mean) * invstd); }
-            }
-        }
-        __syncthreads();
     }
     if (SUMS) {
         red[0][ty][tx] = sb;
@@ -307,21 +309,17 @@ int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, 
     const int G = O / 4, threads = ec_block(G);
     const long long items = (long long)B * N * G;
     // persistent grid: exactly the resident blocks (one wave), so that the grid-stride loop is balanced
+    using Kern = void (*)(const float4 *, const int64_t *, int, int, int, long long, const float *, float4 *, uchar4 *, float4 *,
+                          double *);
+    const Kern kern = stats ? (sgn_src ? (Kern)edgeconv_reduce_kernel<true, true> : (Kern)edgeconv_reduce_kernel<true, false>)
+                            : (sgn_src ? (Kern)edgeconv_reduce_kernel<false, true> : (Kern)edgeconv_reduce_kernel<false, false>);
     int per_sm = 0;
-    if (stats) MLSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edgeconv_reduce_kernel<true>, threads, 0));
-    else MLSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edgeconv_reduce_kernel<false>, threads, 0));
+    MLSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
     const long long want = (items + threads - 1) / threads, resident = (long long)(per_sm > 0 ? per_sm : 1) * sm_count();
     const int grid = (int)(want < resident ? want : resident);
-    if (stats) {
-        MLSP_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * O * sizeof(double), s));
-        edgeconv_reduce_kernel<true><<<grid, threads, 0, s>>>(reinterpret_cast<const float4 *>(yz), idx, N, G, k, items, sgn_src,
-                                                              reinterpret_cast<float4 *>(hsel), reinterpret_cast<uchar4 *>(slot),
-                                                              reinterpret_cast<float4 *>(rowsum), stats);
-    } else {
-        edgeconv_reduce_kernel<false><<<grid, threads, 0, s>>>(reinterpret_cast<const float4 *>(yz), idx, N, G, k, items, sgn_src,
-                                                               reinterpret_cast<float4 *>(hsel), reinterpret_cast<uchar4 *>(slot),
-                                                               nullptr, nullptr);
-    }
+    if (stats) MLSP_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * O * sizeof(double), s));
+    kern<<<grid, threads, 0, s>>>(reinterpret_cast<const float4 *>(yz), idx, N, G, k, items, sgn_src, reinterpret_cast<float4 *>(hsel),
+                                  reinterpret_cast<uchar4 *>(slot), reinterpret_cast<float4 *>(rowsum), stats);
     MLSP_LAUNCH_CHECK("edgeconv_reduce_kernel");
     return MLSP_OK;
 }
@@ -346,11 +344,12 @@ int mlsp_edgeconv_apply_fwd(const float *hsel, const float *coef, int B, int N, 
     return MLSP_OK;
 }
 
-int mlsp_edgeconv_bwd(const float *g, const float *yz, const int64_t *idx, const float *hsel, const uint8_t *slot,
+int mlsp_edgeconv_bwd(const float *g, int64_t g_bstride, const float *yz, const int64_t *idx, const float *hsel, const uint8_t *slot,
                       const float *rowsum, const float *coef, int B, int N, int O, int k, float slope, int bn_train,
                       float *dyz, float *dgamma_dbeta, void *ws, size_t ws_bytes, void *stream)
 {
     MLSP_REQUIRE(g && yz && idx && hsel && slot && coef && dyz && ws, MLSP_EINVAL, "edgeconv_bwd: null pointer");
+    MLSP_REQUIRE(g_bstride >= (int64_t)O * N, MLSP_EINVAL, "edgeconv_bwd: g batch stride %lld < O*N", (long long)g_bstride);
     MLSP_REQUIRE(B > 0 && N > 0 && O > 0 && k >= 1 && k <= N && B <= 65535, MLSP_EINVAL, "edgeconv_bwd: bad shape B=%d N=%d O=%d k=%d", B, N, O, k);
     MLSP_REQUIRE(O % 4 == 0 && O <= 4 * EC_THREADS && k <= 255, MLSP_EUNSUPPORTED, "edgeconv_bwd: O=%d k=%d unsupported", O, k);
     MLSP_REQUIRE(!bn_train || (rowsum && dgamma_dbeta), MLSP_EINVAL, "edgeconv_bwd: training-mode BatchNorm needs rowsum and dgamma_dbeta");
@@ -372,9 +371,9 @@ int mlsp_edgeconv_bwd(const float *g, const float *yz, const int64_t *idx, const
     MLSP_CUDA(cudaMemsetAsync(ws, 0, zero_bytes, s));
     dim3 pgrid((N + EC_PTS - 1) / EC_PTS, (O + 31) / 32, B);
     if (dgamma_dbeta)
-        edgeconv_bwd_prepare_kernel<true><<<pgrid, 256, 0, s>>>(g, hsel, coef, N, O, slope, dy, dsum);
+        edgeconv_bwd_prepare_kernel<true><<<pgrid, 256, 0, s>>>(g, (long long)g_bstride, hsel, coef, N, O, slope, dy, dsum);
     else
-        edgeconv_bwd_prepare_kernel<false><<<pgrid, 256, 0, s>>>(g, hsel, coef, N, O, slope, dy, dsum);
+        edgeconv_bwd_prepare_kernel<false><<<pgrid, 256, 0, s>>>(g, (long long)g_bstride, hsel, coef, N, O, slope, dy, dsum);
     MLSP_LAUNCH_CHECK("edgeconv_bwd_prepare_kernel");
     const int G = O / 4;
     const long long items = (long long)pts * G;

@@ -28,9 +28,10 @@ from .ops import _ptr, _require_cuda_f32, _stream, knn
 
 
 class _EdgeConvReduce(torch.autograd.Function):
-    """(yz, idx, p0, p1) -> out (B,O,N).
-    mode "bn_train": p0 = gamma, p1 = beta (None = 1 / 0); batch statistics over the B*N*k edges.
-    mode "affine"  : p0 = a, p1 = c per channel (eval-mode BatchNorm folded, or a = 1 / c = 0).
+    """(yz, idx, p0, p1) -> out (B,O,N) = lrelu(a * max_j h_j + c), h_j = Y[idx_j] + Z.
+    mode "bn_train": p0 = gamma >= 0, p1 = beta (None = 1 / 0); batch statistics over the B*N*k edges.
+    mode "affine"  : p0 = a >= 0, p1 = c per channel (eval-mode BatchNorm folded, or a = 1 / c = 0).
+    The caller (edge_conv) folds the sign of gamma / a into the rows of the weight, so the extreme is always a max.
     Also returns (mean, biased var) of the batch in bn_train mode (non-differentiable; for the running statistics)."""
 
     @staticmethod
@@ -54,7 +55,7 @@ class _EdgeConvReduce(torch.autograd.Function):
                 rowsum = torch.empty((B, N, O), dtype=torch.float32, device=dev)
                 stats = torch.empty((2, O), dtype=torch.float64, device=dev)
                 var = torch.empty((O,), dtype=torch.float32, device=dev)
-                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(p0c), _ptr(hsel), _ptr(slot),
+                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, ctypes.c_void_p(0), _ptr(hsel), _ptr(slot),
                           _ptr(rowsum), _ptr(stats), s)
                 _lib.call("mlsp_edgeconv_bn_coeffs", _ptr(stats), _ptr(p0c), _ptr(p1c), O, float(B * N * k), float(eps),
                           _ptr(coef), _ptr(var), s)
@@ -63,7 +64,7 @@ class _EdgeConvReduce(torch.autograd.Function):
                 coef[1] = p1c if p1c is not None else 0.0
                 coef[2] = 0.0          # with mean = 0, invstd = 1 the backward sums are the gradients of (a, c)
                 coef[3] = 1.0
-                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(p0c), _ptr(hsel), _ptr(slot),
+                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, ctypes.c_void_p(0), _ptr(hsel), _ptr(slot),
                           ctypes.c_void_p(0), ctypes.c_void_p(0), s)
             _lib.call("mlsp_edgeconv_apply_fwd", _ptr(hsel), _ptr(coef), B, N, O, float(slope), _ptr(out), s)
         ctx.save_for_backward(yz, idx, hsel, slot, coef, rowsum if train else hsel)
@@ -79,14 +80,16 @@ class _EdgeConvReduce(torch.autograd.Function):
         yz, idx, hsel, slot, coef, rowsum = ctx.saved_tensors
         B, N, O, k, slope, train, has0, has1 = ctx.cfg
         dev = yz.device
-        g = g.contiguous().float()
+        g = g.float()
+        if g.stride(2) != 1 or g.stride(1) != N or g.stride(0) < O * N:   # a channel slice of a cat gradient is used in place
+            g = g.contiguous()
         dyz = torch.empty((B, N, 2 * O), dtype=torch.float32, device=dev)
         need_p = train or has0 or has1
         dp = torch.empty((2, O), dtype=torch.float32, device=dev) if need_p else None
         with torch.cuda.device(dev):
             nbytes = max(_lib.workspace_bytes(_lib.OP_EDGECONV_BWD, B, O, N, k), 16)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            _lib.call("mlsp_edgeconv_bwd", _ptr(g), _ptr(yz), _ptr(idx), _ptr(hsel), _ptr(slot),
+            _lib.call("mlsp_edgeconv_bwd", _ptr(g), int(g.stride(0)), _ptr(yz), _ptr(idx), _ptr(hsel), _ptr(slot),
                       _ptr(rowsum) if train else ctypes.c_void_p(0), _ptr(coef), B, N, O, k, slope, 1 if train else 0,
                       _ptr(dyz), _ptr(dp), _ptr(ws), ws.numel(), _stream(dev))
         return dyz, None, (dp[0] if has0 else None), (dp[1] if has1 else None), None, None, None
@@ -125,30 +128,46 @@ def edge_conv(x: torch.Tensor, weight: torch.Tensor, k: int = 20, *, bias: torch
     slope = 1.0 if negative_slope is None else float(negative_slope)
     if slope < 0.0:
         raise MlspError("edge_conv: the activation must be non-decreasing (negative_slope >= 0)")
-    Wcat = _split_weight(weight, C)                                   # (2O, C), autograd tracks the split
-    yz = torch.matmul(x.transpose(1, 2), Wcat.t())                    # (B,N,2O): the one library GEMM of the layer
-    if bias is not None:
-        yz = yz + torch.cat((torch.zeros_like(bias), bias)).view(1, 1, 2 * O)
     idx = idx.contiguous()
+    train = bn is not None and (bn.training or not bn.track_running_stats or bn.running_mean is None)
+    # per-channel affine map after the convolution: training-mode BatchNorm -> (gamma, beta) with batch statistics,
+    # eval-mode BatchNorm -> a = gamma / sqrt(running_var + eps), c = beta - a * running_mean, no BatchNorm -> (1, 0).
     if bn is None:
-        out, _, _ = _EdgeConvReduce.apply(yz, idx, None, None, "affine", 0.0, slope)
+        p0 = p1 = None
+    elif train:
+        p0, p1 = bn.weight, bn.bias
+    else:
+        invstd = torch.rsqrt(bn.running_var + bn.eps)
+        p0 = invstd * bn.weight if bn.weight is not None else invstd
+        p1 = -bn.running_mean * p0
+        if bn.bias is not None:
+            p1 = p1 + bn.bias
+    # a negative scale turns the max over k into a min: fold its sign into the rows of W (and the bias), so that the
+    # kernels always take a max and see a non-negative scale:  p0 * h = |p0| * (sign(p0) * h)
+    sgn = None
+    if p0 is not None:
+        sgn = torch.where(p0.detach() < 0, -1.0, 1.0).to(torch.float32)
+        p0 = p0 * sgn
+    Wcat = _split_weight(weight, C)                                   # (2O, C), autograd tracks the split
+    if sgn is not None:
+        Wcat = Wcat * sgn.repeat(2).view(2 * O, 1)
+    # the one library GEMM of the layer, batched so that its weight gradient is B partial products summed afterwards
+    # (a single (C x B*N) x (B*N x 2O) product is a long reduction that cuBLAS runs on a handful of CTAs)
+    yz = torch.bmm(x.transpose(1, 2), Wcat.t().unsqueeze(0).expand(B, C, 2 * O))          # (B,N,2O) = [Y | Z]
+    if bias is not None:
+        zb = bias if sgn is None else bias * sgn
+        yz = yz + torch.cat((torch.zeros_like(zb), zb)).view(1, 1, 2 * O)
+    if not train:
+        out, _, _ = _EdgeConvReduce.apply(yz, idx, p0, p1, "affine", 0.0, slope)
         return out
-    if bn.training or not bn.track_running_stats or bn.running_mean is None:
-        out, mean, var = _EdgeConvReduce.apply(yz, idx, bn.weight, bn.bias, "bn_train", bn.eps, slope)
-        if bn.training and bn.track_running_stats and bn.running_mean is not None:
-            with torch.no_grad():                                    # torch/nn/modules/batchnorm.py: same update rule
-                bn.num_batches_tracked += 1
-                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                cnt = B * N * idx.shape[2]
-                bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                bn.running_var.mul_(1 - m).add_(var * (cnt / max(cnt - 1, 1)), alpha=m)
-        return out
-    invstd = torch.rsqrt(bn.running_var + bn.eps)
-    a = invstd * bn.weight if bn.weight is not None else invstd
-    c = -bn.running_mean * a
-    if bn.bias is not None:
-        c = c + bn.bias
-    out, _, _ = _EdgeConvReduce.apply(yz, idx, a, c, "affine", 0.0, slope)
+    out, mean, var = _EdgeConvReduce.apply(yz, idx, p0, p1, "bn_train", bn.eps, slope)
+    if bn.training and bn.track_running_stats and bn.running_mean is not None:
+        with torch.no_grad():                                        # torch/nn/modules/batchnorm.py: same update rule
+            bn.num_batches_tracked += 1
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            cnt = B * N * idx.shape[2]
+            bn.running_mean.mul_(1 - m).add_(mean * sgn if sgn is not None else mean, alpha=m)
+            bn.running_var.mul_(1 - m).add_(var * (cnt / max(cnt - 1, 1)), alpha=m)
     return out
 
 
