@@ -30,7 +30,9 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ?
 // ------------------------------------------------------------------------------------------------ forward
 // grid-stride over (point, float4-of-channels) items with a stride that is a multiple of G = O/4, so a thread keeps
 // its channels and the statistics stay in registers until the end.
-template <bool STATS, bool SIGNED>
+// COOP (G a power of two): the min(G,32) lanes that share a point load its neighbour indices once, coalesced, and hand
+// them round with shuffles -- the k row gathers then depend on no load and are issued five at a time.
+template <bool STATS, bool SIGNED, bool COOP>
 __global__ void __launch_bounds__(EC_THREADS, 4)
 edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict__ idx, int N, int G, int k, long long items,
                        const float *__restrict__ sgn_src, float4 *__restrict__ hsel, uchar4 *__restrict__ slot,
@@ -39,6 +41,8 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
     __shared__ double red[EC_THREADS * 2];
     const int c4 = threadIdx.x % G;                           // blockDim.x % G == 0
     const long long stride = (long long)gridDim.x * blockDim.x;
+    const int gw = G < 32 ? G : 32;                           // lanes of this warp that work on the same point
+    const int lig = lane_id() & (gw - 1), gbase = lane_id() & ~(gw - 1);
     float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
     if (SIGNED) {
         const float4 s = reinterpret_cast<const float4 *>(sgn_src)[c4];
@@ -54,10 +58,8 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         uchar4 sl = make_uchar4(0, 0, 0, 0);
         float4 rs = make_float4(0.f, 0.f, 0.f, 0.f), rq = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 5
-        for (int j = 0; j < k; ++j) {                         // k = 20: four batches of five independent (idx, row) loads
-            const long long nb = ip[j];
-            const float4 y = __ldg(yb + nb * 2 * G);
+        auto visit = [&](int j, int nb) {
+            const float4 y = __ldg(yb + (long long)nb * 2 * G);
             const float4 h = make_float4(y.x + z.x, y.y + z.y, y.z + z.z, y.w + z.w);
             const float4 t = SIGNED ? make_float4(h.x * sg.x, h.y * sg.y, h.z * sg.z, h.w * sg.w) : h;
             if (t.x > m.x) { m.x = t.x; sl.x = (unsigned char)j; }      // strict: the first extreme wins
@@ -68,6 +70,18 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
                 rs.x += h.x; rs.y += h.y; rs.z += h.z; rs.w += h.w;
                 rq.x = fmaf(h.x, h.x, rq.x); rq.y = fmaf(h.y, h.y, rq.y); rq.z = fmaf(h.z, h.z, rq.z); rq.w = fmaf(h.w, h.w, rq.w);
             }
+        };
+        if (COOP) {
+            const unsigned mask = __activemask();             // whole groups are active or not (items % G == 0)
+            for (int j0 = 0; j0 < k; j0 += gw) {
+                const int cnt = min(gw, k - j0);
+                const int mine = lig < cnt ? (int)ip[j0 + lig] : 0;
+#pragma unroll 5
+                for (int jj = 0; jj < cnt; ++jj) visit(j0 + jj, __shfl_sync(mask, mine, gbase + jj));
+            }
+        } else {
+#pragma unroll 5
+            for (int j = 0; j < k; ++j) visit(j, (int)ip[j]);
         }
         hsel[p * G + c4] = SIGNED ? make_float4(m.x * sg.x, m.y * sg.y, m.z * sg.z, m.w * sg.w) : m;
         slot[p * G + c4] = sl;
@@ -311,8 +325,14 @@ int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, 
     // persistent grid: exactly the resident blocks (one wave), so that the grid-stride loop is balanced
     using Kern = void (*)(const float4 *, const int64_t *, int, int, int, long long, const float *, float4 *, uchar4 *, float4 *,
                           double *);
-    const Kern kern = stats ? (sgn_src ? (Kern)edgeconv_reduce_kernel<true, true> : (Kern)edgeconv_reduce_kernel<true, false>)
-                            : (sgn_src ? (Kern)edgeconv_reduce_kernel<false, true> : (Kern)edgeconv_reduce_kernel<false, false>);
+    const bool coop = (G & (G - 1)) == 0;
+    Kern kern;
+    if (coop)
+        kern = stats ? (sgn_src ? (Kern)edgeconv_reduce_kernel<true, true, true> : (Kern)edgeconv_reduce_kernel<true, false, true>)
+                     : (sgn_src ? (Kern)edgeconv_reduce_kernel<false, true, true> : (Kern)edgeconv_reduce_kernel<false, false, true>);
+    else
+        kern = stats ? (sgn_src ? (Kern)edgeconv_reduce_kernel<true, true, false> : (Kern)edgeconv_reduce_kernel<true, false, false>)
+                     : (sgn_src ? (Kern)edgeconv_reduce_kernel<false, true, false> : (Kern)edgeconv_reduce_kernel<false, false, false>);
     int per_sm = 0;
     MLSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
     const long long want = (items + threads - 1) / threads, resident = (long long)(per_sm > 0 ? per_sm : 1) * sm_count();

@@ -95,6 +95,28 @@ class _EdgeConvReduce(torch.autograd.Function):
         return dyz, None, (dp[0] if has0 else None), (dp[1] if has1 else None), None, None, None
 
 
+class _PointwiseYZ(torch.autograd.Function):
+    """yz (B,N,2O) = x^T Wcat^T -- the layer's one library GEMM, with a backward that keeps every operand in the layout
+    it already has: grad_x comes out as (B,C,N) directly, and the weight gradient is B partial products summed afterwards
+    (as a single (2O x B*N) x (B*N x C) product it is a long reduction that cuBLAS runs on a handful of CTAs)."""
+
+    @staticmethod
+    def forward(ctx, x, Wcat):
+        ctx.save_for_backward(x, Wcat)
+        B = x.shape[0]
+        return torch.bmm(x.transpose(1, 2), Wcat.t().unsqueeze(0).expand(B, -1, -1))
+
+    @staticmethod
+    def backward(ctx, dyz):
+        x, Wcat = ctx.saved_tensors
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.matmul(Wcat.t(), dyz.transpose(1, 2))                      # (C,2O) x (B,2O,N) -> (B,C,N)
+        if ctx.needs_input_grad[1]:
+            gw = torch.bmm(dyz.transpose(1, 2), x.transpose(1, 2)).sum(dim=0)     # (B,2O,C) partials -> (2O,C)
+        return gx, gw
+
+
 def _split_weight(weight: torch.Tensor, C: int) -> torch.Tensor:
     """W (O,2C[,1,1]) = [Wa | Wb] over [x_j - x_i | x_i]  ->  (2O, C) = [Wa ; Wb - Wa]  (rows of Y, then rows of Z)."""
     W = weight.reshape(weight.shape[0], -1)
@@ -151,9 +173,7 @@ def edge_conv(x: torch.Tensor, weight: torch.Tensor, k: int = 20, *, bias: torch
     Wcat = _split_weight(weight, C)                                   # (2O, C), autograd tracks the split
     if sgn is not None:
         Wcat = Wcat * sgn.repeat(2).view(2 * O, 1)
-    # the one library GEMM of the layer, batched so that its weight gradient is B partial products summed afterwards
-    # (a single (C x B*N) x (B*N x 2O) product is a long reduction that cuBLAS runs on a handful of CTAs)
-    yz = torch.bmm(x.transpose(1, 2), Wcat.t().unsqueeze(0).expand(B, C, 2 * O))          # (B,N,2O) = [Y | Z]
+    yz = _PointwiseYZ.apply(x, Wcat)                                  # (B,N,2O) = [Y | Z]: the one library GEMM of the layer
     if bias is not None:
         zb = bias if sgn is None else bias * sgn
         yz = yz + torch.cat((torch.zeros_like(zb), zb)).view(1, 1, 2 * O)

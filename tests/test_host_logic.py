@@ -202,3 +202,14 @@ def test_edgeconv_weight_algebra():
         edgeconv.FusedEdgeConv.from_reference([seq, torch.nn.Conv2d(8, 8, 1)])
     with pytest.raises(M.MlspError):
         edgeconv.edge_conv(torch.zeros(1, 3, 8), torch.zeros(4, 6))   # no CPU path
+    # the layer's GEMM with its hand-written backward (grad_x straight in (B,C,N), weight gradient from B partial products)
+    x = torch.randn(3, C, 7, dtype=torch.float64, requires_grad=True)
+    Wc = torch.randn(2 * O, C, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(3, 7, 2 * O, dtype=torch.float64)
+    edgeconv._PointwiseYZ.apply(x, Wc).backward(gy)
+    gx, gw = x.grad.clone(), Wc.grad.clone()
+    x.grad = Wc.grad = None
+    ref = torch.matmul(x.transpose(1, 2), Wc.t())
+    ref.backward(gy)
+    assert torch.allclose(edgeconv._PointwiseYZ.apply(x, Wc), ref, atol=1e-12)
+    assert torch.allclose(gx, x.grad, atol=1e-12) and torch.allclose(gw, Wc.grad, atol=1e-12) and gx.is_contiguous()
