@@ -864,7 +864,7 @@ def run_workload_e(args):
 
             red()
             _lib.call("mlsp_edgeconv_bn_coeffs", _ptr(stats), _ptr(gam), _ptr(f.bn.bias.detach()), O, float(P * k), 1e-5,
-                      _ptr(coef), None, s_)
+                      _ptr(coef), None, None, None, 0.0, s_)
             per[f"reduce_fwd_O{O}_C{C}"] = (span(red), P * (17 * O + 8 * k), 4.0 * P * k * O)
             per[f"bwd_O{O}_C{C}"] = (span(bwd), P * (29 * O + 8 * k), 4.0 * P * k * O)
             per[f"knn_C{C}"] = (span(lambda: M.knn(h, k)), None, None)

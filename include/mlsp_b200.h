@@ -208,10 +208,13 @@ MLSP_API int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B
                              float *hsel, uint8_t *slot, float *rowsum, double *stats, void *stream);
 
 /* BatchNorm2d in training mode (torch.nn.functional.batch_norm: biased variance): stats of `count` = B*N*k edges ->
- *   coef (4,O) = [a = gamma*invstd ; c = beta - a*mean ; mean ; invstd], var_out (O) = biased variance (may be NULL).
- *   gamma / beta NULL = 1 / 0 (affine=False). */
+ *   coef (4,O) = [a = gamma*invstd ; c = beta - a*mean ; mean ; invstd].  gamma / beta NULL = 1 / 0 (affine=False).
+ *   running_mean / running_var (O, both or neither): updated in place like torch.nn.BatchNorm2d does,
+ *   r = (1-momentum)*r + momentum*batch value, the variance unbiased by count/(count-1); `sign` (O, +-1, may be NULL)
+ *   multiplies the mean first -- for callers that folded the sign of gamma into the rows of the weight. */
 MLSP_API int mlsp_edgeconv_bn_coeffs(const double *stats, const float *gamma, const float *beta, int O, double count, float eps,
-                            float *coef, float *var_out, void *stream);
+                            float *coef, float *running_mean, float *running_var, const float *sign, float momentum,
+                            void *stream);
 
 /* out (B,O,N) = lrelu_slope(a_o * hsel[b,i,o] + c_o), coef rows 0 and 1 = a, c  (slope 1: no activation, 0: ReLU) */
 MLSP_API int mlsp_edgeconv_apply_fwd(const float *hsel, const float *coef, int B, int N, int O, float slope, float *out,

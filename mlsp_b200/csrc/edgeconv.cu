@@ -110,11 +110,14 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
     }
 }
 
-// stats (2,O) double: sum h, sum h^2 over `count` edges -> coef (4,O): a = gamma*invstd, c = beta - a*mean, mean, invstd;
-// var_out (O): the biased batch variance (the caller updates running_var with the unbiased one)
+// stats (2,O) double: sum h, sum h^2 over `count` edges -> coef (4,O): a = gamma*invstd, c = beta - a*mean, mean, invstd.
+// With running_mean / running_var the kernel also makes BatchNorm's running-statistics update (torch semantics:
+// r = (1-m) r + m * batch value, the variance unbiased by count/(count-1)); `sign` (O, +-1 or NULL) maps the mean back
+// when the caller has folded the sign of gamma into the weight rows (h' = sign*h has mean' = sign*mean, same variance).
 __global__ void edgeconv_coeffs_kernel(const double *__restrict__ stats, const float *__restrict__ gamma,
                                        const float *__restrict__ beta, int O, double count, float eps, float *__restrict__ coef,
-                                       float *__restrict__ var_out)
+                                       float *__restrict__ running_mean, float *__restrict__ running_var,
+                                       const float *__restrict__ sign, float momentum)
 {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= O) return;
@@ -127,7 +130,12 @@ __global__ void edgeconv_coeffs_kernel(const double *__restrict__ stats, const f
     coef[O + o] = (float)(bt - g * invstd * mean);
     coef[2 * O + o] = (float)mean;
     coef[3 * O + o] = (float)invstd;
-    if (var_out) var_out[o] = (float)var;
+    if (running_mean) {
+        const float m = momentum, sg = sign ? sign[o] : 1.0f;
+        const float unbiased = (float)(var * (count / (count > 1.0 ? count - 1.0 : 1.0)));
+        running_mean[o] = (1.0f - m) * running_mean[o] + m * (sg * (float)mean);
+        running_var[o] = (1.0f - m) * running_var[o] + m * unbiased;
+    }
 }
 
 // out[b,o,i] = lrelu(a_o * hsel[b,i,o] + c_o): 32 points x 32 channels per block through a padded shared tile
@@ -345,11 +353,14 @@ int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, 
 }
 
 int mlsp_edgeconv_bn_coeffs(const double *stats, const float *gamma, const float *beta, int O, double count, float eps,
-                            float *coef, float *var_out, void *stream)
+                            float *coef, float *running_mean, float *running_var, const float *sign, float momentum,
+                            void *stream)
 {
     MLSP_REQUIRE(stats && coef, MLSP_EINVAL, "edgeconv_bn_coeffs: null pointer");
     MLSP_REQUIRE(O > 0 && count > 0, MLSP_EINVAL, "edgeconv_bn_coeffs: bad shape O=%d count=%g", O, count);
-    edgeconv_coeffs_kernel<<<(O + 127) / 128, 128, 0, as_stream(stream)>>>(stats, gamma, beta, O, count, eps, coef, var_out);
+    MLSP_REQUIRE((running_mean == nullptr) == (running_var == nullptr), MLSP_EINVAL, "edgeconv_bn_coeffs: running_mean and running_var go together");
+    edgeconv_coeffs_kernel<<<(O + 127) / 128, 128, 0, as_stream(stream)>>>(stats, gamma, beta, O, count, eps, coef, running_mean,
+                                                                           running_var, sign, momentum);
     MLSP_LAUNCH_CHECK("edgeconv_coeffs_kernel");
     return MLSP_OK;
 }

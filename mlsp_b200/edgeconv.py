@@ -32,10 +32,10 @@ class _EdgeConvReduce(torch.autograd.Function):
     mode "bn_train": p0 = gamma >= 0, p1 = beta (None = 1 / 0); batch statistics over the B*N*k edges.
     mode "affine"  : p0 = a >= 0, p1 = c per channel (eval-mode BatchNorm folded, or a = 1 / c = 0).
     The caller (edge_conv) folds the sign of gamma / a into the rows of the weight, so the extreme is always a max.
-    Also returns (mean, biased var) of the batch in bn_train mode (non-differentiable; for the running statistics)."""
+    running = (running_mean, running_var, sign or None, momentum): updated in place by the coefficient kernel."""
 
     @staticmethod
-    def forward(ctx, yz, idx, p0, p1, mode, eps, slope):
+    def forward(ctx, yz, idx, p0, p1, mode, eps, slope, running=None):
         B, N, O2 = yz.shape
         O = O2 // 2
         k = idx.shape[2]
@@ -46,7 +46,7 @@ class _EdgeConvReduce(torch.autograd.Function):
         coef = torch.empty((4, O), dtype=torch.float32, device=dev)
         out = torch.empty((B, O, N), dtype=torch.float32, device=dev)
         train = mode == "bn_train"
-        rowsum = var = None
+        rowsum = None
         p0c = p0.detach().float().contiguous() if p0 is not None else None
         p1c = p1.detach().float().contiguous() if p1 is not None else None
         with torch.cuda.device(dev):
@@ -54,11 +54,11 @@ class _EdgeConvReduce(torch.autograd.Function):
             if train:
                 rowsum = torch.empty((B, N, O), dtype=torch.float32, device=dev)
                 stats = torch.empty((2, O), dtype=torch.float64, device=dev)
-                var = torch.empty((O,), dtype=torch.float32, device=dev)
+                rmean, rvar, rsign, mom = running if running is not None else (None, None, None, 0.0)
                 _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, ctypes.c_void_p(0), _ptr(hsel), _ptr(slot),
                           _ptr(rowsum), _ptr(stats), s)
                 _lib.call("mlsp_edgeconv_bn_coeffs", _ptr(stats), _ptr(p0c), _ptr(p1c), O, float(B * N * k), float(eps),
-                          _ptr(coef), _ptr(var), s)
+                          _ptr(coef), _ptr(rmean), _ptr(rvar), _ptr(rsign), float(mom), s)
             else:
                 coef[0] = p0c if p0c is not None else 1.0
                 coef[1] = p1c if p1c is not None else 0.0
@@ -69,14 +69,10 @@ class _EdgeConvReduce(torch.autograd.Function):
             _lib.call("mlsp_edgeconv_apply_fwd", _ptr(hsel), _ptr(coef), B, N, O, float(slope), _ptr(out), s)
         ctx.save_for_backward(yz, idx, hsel, slot, coef, rowsum if train else hsel)
         ctx.cfg = (B, N, O, k, float(slope), train, p0 is not None, p1 is not None)
-        if train:
-            mean = coef[2].clone()
-            ctx.mark_non_differentiable(mean, var)
-            return out, mean, var
-        return out, None, None
+        return out
 
     @staticmethod
-    def backward(ctx, g, _gm, _gv):
+    def backward(ctx, g):
         yz, idx, hsel, slot, coef, rowsum = ctx.saved_tensors
         B, N, O, k, slope, train, has0, has1 = ctx.cfg
         dev = yz.device
@@ -92,7 +88,7 @@ class _EdgeConvReduce(torch.autograd.Function):
             _lib.call("mlsp_edgeconv_bwd", _ptr(g), int(g.stride(0)), _ptr(yz), _ptr(idx), _ptr(hsel), _ptr(slot),
                       _ptr(rowsum) if train else ctypes.c_void_p(0), _ptr(coef), B, N, O, k, slope, 1 if train else 0,
                       _ptr(dyz), _ptr(dp), _ptr(ws), ws.numel(), _stream(dev))
-        return dyz, None, (dp[0] if has0 else None), (dp[1] if has1 else None), None, None, None
+        return dyz, None, (dp[0] if has0 else None), (dp[1] if has1 else None), None, None, None, None
 
 
 class _PointwiseYZ(torch.autograd.Function):
@@ -178,17 +174,17 @@ def edge_conv(x: torch.Tensor, weight: torch.Tensor, k: int = 20, *, bias: torch
         zb = bias if sgn is None else bias * sgn
         yz = yz + torch.cat((torch.zeros_like(zb), zb)).view(1, 1, 2 * O)
     if not train:
-        out, _, _ = _EdgeConvReduce.apply(yz, idx, p0, p1, "affine", 0.0, slope)
-        return out
-    out, mean, var = _EdgeConvReduce.apply(yz, idx, p0, p1, "bn_train", bn.eps, slope)
+        return _EdgeConvReduce.apply(yz, idx, p0, p1, "affine", 0.0, slope)
+    running = None
     if bn.training and bn.track_running_stats and bn.running_mean is not None:
         with torch.no_grad():                                        # torch/nn/modules/batchnorm.py: same update rule
             bn.num_batches_tracked += 1
-            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-            cnt = B * N * idx.shape[2]
-            bn.running_mean.mul_(1 - m).add_(mean * sgn if sgn is not None else mean, alpha=m)
-            bn.running_var.mul_(1 - m).add_(var * (cnt / max(cnt - 1, 1)), alpha=m)
-    return out
+        m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        if (bn.running_mean.dtype != torch.float32 or not bn.running_mean.is_contiguous()
+                or not bn.running_var.is_contiguous()):
+            raise MlspError("edge_conv: BatchNorm running statistics must be contiguous float32")
+        running = (bn.running_mean, bn.running_var, sgn, m)          # updated in place by the coefficient kernel
+    return _EdgeConvReduce.apply(yz, idx, p0, p1, "bn_train", bn.eps, slope, running)
 
 
 class FusedEdgeConv(nn.Module):
