@@ -855,7 +855,7 @@ def run_workload_e(args):
             ws = torch.empty(_lib.workspace_bytes(_lib.OP_EDGECONV_BWD, B, O, N, k), dtype=torch.uint8, device=device)
 
             def red():
-                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, None, _ptr(hsel), _ptr(slot),
+                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(hsel), _ptr(slot),
                           _ptr(rowsum), _ptr(stats), s_)
 
             def bwd():

@@ -197,15 +197,16 @@ MLSP_API int mlsp_reconstruction_loss_bwd(const float *pred, int64_t pred_bstrid
  *     h[b,o,i,j] = Y[b,idx[b,i,j],o] + Z[b,i,o],  Y = Wa x, Z = (Wb - Wa) x + bias,  W = [Wa | Wb]
  * so the caller makes ONE point-wise GEMM yz (B,N,2O) = [Y | Z] (a library call) and these entry points do the rest.
  * BatchNorm is a*h + c per channel with a = gamma*invstd, LeakyReLU is increasing:
- *     out[b,o,i] = lrelu(a_o * ext_j h[b,o,i,j] + c_o),  ext = max where a_o >= 0, min where a_o < 0.
+ *     out[b,o,i] = lrelu(a_o * max_j h[b,o,i,j] + c_o)  for a_o >= 0 (negative scales: see mlsp_edgeconv_reduce_fwd).
  * All tensors point-major, 16-byte aligned; O % 4 == 0, O <= 1024, k <= 255. */
 
-/* per point: hsel (B,N,O) = the extreme of h over the k neighbours (max where sgn_src[o] >= 0, else min; sgn_src NULL:
- *   max), slot (B,N,O) uint8 = the neighbour rank that attains it (first on ties).  With stats != NULL (training-mode
+/* per point: hsel (B,N,O) = max_j h over the k neighbours, slot (B,N,O) uint8 = the neighbour rank that attains it
+ *   (first on ties).  A channel whose scale a_o is negative needs the minimum instead: the caller folds the sign into
+ *   that channel's rows of the weight (h' = -h, a' = -a; mlsp_b200/edgeconv.py does).  With stats != NULL (training-mode
  *   BatchNorm) also rowsum (B,N,O) = sum_j h and stats (2,O) double = [sum h ; sum h^2] over all B*N*k edges
  *   (zeroed by the call, accumulated with fp64 atomics). */
-MLSP_API int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, int O, int k, const float *sgn_src,
-                             float *hsel, uint8_t *slot, float *rowsum, double *stats, void *stream);
+MLSP_API int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, int O, int k, float *hsel, uint8_t *slot,
+                             float *rowsum, double *stats, void *stream);
 
 /* BatchNorm2d in training mode (torch.nn.functional.batch_norm: biased variance): stats of `count` = B*N*k edges ->
  *   coef (4,O) = [a = gamma*invstd ; c = beta - a*mean ; mean ; invstd].  gamma / beta NULL = 1 / 0 (affine=False).

@@ -8,7 +8,8 @@
 //     h[b,o,i,j] = Y[b,idx[b,i,j],o] + Z[b,i,o],   Y = Wa x,  Z = (Wb - Wa) x  (+ bias)
 // and the two point-wise products are one plain GEMM on (B*N, C) x (C, 2O) (library call on the host side).
 // BatchNorm (training statistics over all B*N*k edges) is a per-channel affine map a*h + c with the sign of gamma,
-// LeakyReLU is increasing, so   max_j lrelu(a h_j + c) = lrelu(a * (a >= 0 ? max_j h_j : min_j h_j) + c).
+// LeakyReLU is increasing, so   max_j lrelu(a h_j + c) = lrelu(a * max_j h_j + c)  for a >= 0; a caller with a negative
+// scale folds its sign into the rows of W (h' = -h, a' = -a), so these kernels always take a max.
 // What remains for this file is HBM/L2-bound index work:
 //   edgeconv_reduce_kernel : per point, gather k rows of Y (L2 resident), track the extreme value and its slot, the
 //                            row sum and -- for the batch statistics -- sum h and sum h^2 per channel (fp64 partials)
@@ -32,22 +33,17 @@ __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.0f ?
 // its channels and the statistics stay in registers until the end.
 // COOP (G a power of two): the min(G,32) lanes that share a point load its neighbour indices once, coalesced, and hand
 // them round with shuffles -- the k row gathers then depend on no load and are issued five at a time.
-template <bool STATS, bool SIGNED, bool COOP>
+template <bool STATS, bool COOP>
 __global__ void __launch_bounds__(EC_THREADS, 4)
 edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict__ idx, int N, int G, int k, long long items,
-                       const float *__restrict__ sgn_src, float4 *__restrict__ hsel, uchar4 *__restrict__ slot,
-                       float4 *__restrict__ rowsum, double *__restrict__ stats)
+                       float4 *__restrict__ hsel, uchar4 *__restrict__ slot, float4 *__restrict__ rowsum,
+                       double *__restrict__ stats)
 {
     __shared__ double red[EC_THREADS * 2];
     const int c4 = threadIdx.x % G;                           // blockDim.x % G == 0
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int gw = G < 32 ? G : 32;                           // lanes of this warp that work on the same point
     const int lig = lane_id() & (gw - 1), gbase = lane_id() & ~(gw - 1);
-    float4 sg = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (SIGNED) {
-        const float4 s = reinterpret_cast<const float4 *>(sgn_src)[c4];
-        sg = make_float4(s.x < 0.f ? -1.f : 1.f, s.y < 0.f ? -1.f : 1.f, s.z < 0.f ? -1.f : 1.f, s.w < 0.f ? -1.f : 1.f);
-    }
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
         const long long p = it / G;                           // global point b*N + i
@@ -61,11 +57,10 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
         auto visit = [&](int j, int nb) {
             const float4 y = __ldg(yb + (long long)nb * 2 * G);
             const float4 h = make_float4(y.x + z.x, y.y + z.y, y.z + z.z, y.w + z.w);
-            const float4 t = SIGNED ? make_float4(h.x * sg.x, h.y * sg.y, h.z * sg.z, h.w * sg.w) : h;
-            if (t.x > m.x) { m.x = t.x; sl.x = (unsigned char)j; }      // strict: the first extreme wins
-            if (t.y > m.y) { m.y = t.y; sl.y = (unsigned char)j; }
-            if (t.z > m.z) { m.z = t.z; sl.z = (unsigned char)j; }
-            if (t.w > m.w) { m.w = t.w; sl.w = (unsigned char)j; }
+            if (h.x > m.x) { m.x = h.x; sl.x = (unsigned char)j; }      // strict: the first maximum wins
+            if (h.y > m.y) { m.y = h.y; sl.y = (unsigned char)j; }
+            if (h.z > m.z) { m.z = h.z; sl.z = (unsigned char)j; }
+            if (h.w > m.w) { m.w = h.w; sl.w = (unsigned char)j; }
             if (STATS) {
                 rs.x += h.x; rs.y += h.y; rs.z += h.z; rs.w += h.w;
                 rq.x = fmaf(h.x, h.x, rq.x); rq.y = fmaf(h.y, h.y, rq.y); rq.z = fmaf(h.z, h.z, rq.z); rq.w = fmaf(h.w, h.w, rq.w);
@@ -83,7 +78,7 @@ edgeconv_reduce_kernel(const float4 *__restrict__ yz, const int64_t *__restrict_
 #pragma unroll 5
             for (int j = 0; j < k; ++j) visit(j, (int)ip[j]);
         }
-        hsel[p * G + c4] = SIGNED ? make_float4(m.x * sg.x, m.y * sg.y, m.z * sg.z, m.w * sg.w) : m;
+        hsel[p * G + c4] = m;
         slot[p * G + c4] = sl;
         if (STATS) {
             rowsum[p * G + c4] = rs;
@@ -319,8 +314,8 @@ using namespace mlsp;
 
 extern "C" {
 
-int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, int O, int k, const float *sgn_src,
-                             float *hsel, uint8_t *slot, float *rowsum, double *stats, void *stream)
+int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, int O, int k, float *hsel, uint8_t *slot,
+                             float *rowsum, double *stats, void *stream)
 {
     MLSP_REQUIRE(yz && idx && hsel && slot, MLSP_EINVAL, "edgeconv_reduce_fwd: null pointer");
     MLSP_REQUIRE(B > 0 && N > 0 && O > 0 && k >= 1 && k <= N, MLSP_EINVAL, "edgeconv_reduce_fwd: bad shape B=%d N=%d O=%d k=%d", B, N, O, k);
@@ -331,22 +326,16 @@ int mlsp_edgeconv_reduce_fwd(const float *yz, const int64_t *idx, int B, int N, 
     const int G = O / 4, threads = ec_block(G);
     const long long items = (long long)B * N * G;
     // persistent grid: exactly the resident blocks (one wave), so that the grid-stride loop is balanced
-    using Kern = void (*)(const float4 *, const int64_t *, int, int, int, long long, const float *, float4 *, uchar4 *, float4 *,
-                          double *);
+    using Kern = void (*)(const float4 *, const int64_t *, int, int, int, long long, float4 *, uchar4 *, float4 *, double *);
     const bool coop = (G & (G - 1)) == 0;
-    Kern kern;
-    if (coop)
-        kern = stats ? (sgn_src ? (Kern)edgeconv_reduce_kernel<true, true, true> : (Kern)edgeconv_reduce_kernel<true, false, true>)
-                     : (sgn_src ? (Kern)edgeconv_reduce_kernel<false, true, true> : (Kern)edgeconv_reduce_kernel<false, false, true>);
-    else
-        kern = stats ? (sgn_src ? (Kern)edgeconv_reduce_kernel<true, true, false> : (Kern)edgeconv_reduce_kernel<true, false, false>)
-                     : (sgn_src ? (Kern)edgeconv_reduce_kernel<false, true, false> : (Kern)edgeconv_reduce_kernel<false, false, false>);
+    const Kern kern = coop ? (stats ? (Kern)edgeconv_reduce_kernel<true, true> : (Kern)edgeconv_reduce_kernel<false, true>)
+                           : (stats ? (Kern)edgeconv_reduce_kernel<true, false> : (Kern)edgeconv_reduce_kernel<false, false>);
     int per_sm = 0;
     MLSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
     const long long want = (items + threads - 1) / threads, resident = (long long)(per_sm > 0 ? per_sm : 1) * sm_count();
     const int grid = (int)(want < resident ? want : resident);
     if (stats) MLSP_CUDA(cudaMemsetAsync(stats, 0, (size_t)2 * O * sizeof(double), s));
-    kern<<<grid, threads, 0, s>>>(reinterpret_cast<const float4 *>(yz), idx, N, G, k, items, sgn_src, reinterpret_cast<float4 *>(hsel),
+    kern<<<grid, threads, 0, s>>>(reinterpret_cast<const float4 *>(yz), idx, N, G, k, items, reinterpret_cast<float4 *>(hsel),
                                   reinterpret_cast<uchar4 *>(slot), reinterpret_cast<float4 *>(rowsum), stats);
     MLSP_LAUNCH_CHECK("edgeconv_reduce_kernel");
     return MLSP_OK;

@@ -55,7 +55,7 @@ class _EdgeConvReduce(torch.autograd.Function):
                 rowsum = torch.empty((B, N, O), dtype=torch.float32, device=dev)
                 stats = torch.empty((2, O), dtype=torch.float64, device=dev)
                 rmean, rvar, rsign, mom = running if running is not None else (None, None, None, 0.0)
-                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, ctypes.c_void_p(0), _ptr(hsel), _ptr(slot),
+                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(hsel), _ptr(slot),
                           _ptr(rowsum), _ptr(stats), s)
                 _lib.call("mlsp_edgeconv_bn_coeffs", _ptr(stats), _ptr(p0c), _ptr(p1c), O, float(B * N * k), float(eps),
                           _ptr(coef), _ptr(rmean), _ptr(rvar), _ptr(rsign), float(mom), s)
@@ -64,7 +64,7 @@ class _EdgeConvReduce(torch.autograd.Function):
                 coef[1] = p1c if p1c is not None else 0.0
                 coef[2] = 0.0          # with mean = 0, invstd = 1 the backward sums are the gradients of (a, c)
                 coef[3] = 1.0
-                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, ctypes.c_void_p(0), _ptr(hsel), _ptr(slot),
+                _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(hsel), _ptr(slot),
                           ctypes.c_void_p(0), ctypes.c_void_p(0), s)
             _lib.call("mlsp_edgeconv_apply_fwd", _ptr(hsel), _ptr(coef), B, N, O, float(slope), _ptr(out), s)
         ctx.save_for_backward(yz, idx, hsel, slot, coef, rowsum if train else hsel)

@@ -84,3 +84,7 @@ def test_workload_e_reference_arm_line(bench):
     assert line["impl"] == "reference" and line["unit"] == "clouds/s" and line["value"] > 0
     assert line["config"]["workload"] == "edgeconv-E" and line["config"]["points"] == 1024 and line["config"]["k"] == 20
     assert line["cpu_baseline"]["kind"] == "port" and line["gpu_launches"] == 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")          # other ranks exit 0 without work
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "E", "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
