@@ -136,9 +136,14 @@ class Streams:
     read synchronises a nearly empty stream while the model stream keeps the GPU busy, and the latency-bound
     FPS (one CTA per cloud) overlaps with the bandwidth-bound edge kernels."""
 
-    def __init__(self, device, serial=False, side_model=False):
-        self.model = torch.cuda.Stream(device=device) if side_model else torch.cuda.default_stream(device)
-        self.target = self.model if serial else torch.cuda.Stream(device=device)
+    def __init__(self, device, serial=False, side_model=False, prio=False):
+        # prio: the model stream (the step's critical path) gets the high stream priority, the target builder the low
+        # one, so that the block scheduler hands free SM slots to the DGCNN layers' kernels first
+        if prio:
+            self.model = torch.cuda.Stream(device=device, priority=-1)
+        else:
+            self.model = torch.cuda.Stream(device=device) if side_model else torch.cuda.default_stream(device)
+        self.target = self.model if serial else torch.cuda.Stream(device=device, priority=0)
         self.serial = serial
 
 
@@ -957,6 +962,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="headline on one stream (no target-builder overlap)")
     ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")
+    ap.add_argument("--prio", action="store_true",
+                    help="experiment: model stream at high stream priority, target-builder stream at low priority")
     ap.add_argument("--no-graphs", action="store_true", help="eager model path (no CUDA-graph capture)")
     ap.add_argument("--step-only", action="store_true",
                     help="run only the warm-up and the K timed steps (for `ncu` launch lists: kernel shares of the step itself)")
@@ -998,7 +1005,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    streams = Streams(device, serial=args.serial, side_model=args.side_model_stream)
+    streams = Streams(device, serial=args.serial, side_model=args.side_model_stream, prio=args.prio)
     serial = Streams(device, serial=True, side_model=args.side_model_stream)
     off = OpTimer(False)
     sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~1 s to start: begin before warm-up
