@@ -676,9 +676,22 @@ def run_workload_x(args):
 EC_LAYERS = ((3, 64), (64, 64), (64, 128), (128, 256))        # PointDA/Models.py:91-94 conv1..conv4 (in = 2C)
 
 
-def _ec_make_layers(device):
-    """conv_2d-shaped modules of the reference's DGCNN backbone (PointDA/model_utils.py:45-63), seeded init."""
+SEG_LAYERS = ((3, (64, 64)), (64, (64, 64)), (64, (64,)))     # PointSegDA/Models.py:159-163 conv1+conv2, conv3+conv4, conv5
+
+
+def _ec_make_layers(device, seg=False):
+    """The layer modules of the reference's backbones, seeded init: PointDA conv_2d = Conv2d + BatchNorm2d + LeakyReLU
+    (PointDA/model_utils.py:45-63); PointSegDA shared_layers = stacks of plain nn.Conv2d with bias (Models.py:159-163)."""
     torch.manual_seed(0)
+    if seg:
+        out = []
+        for C, widths in SEG_LAYERS:
+            mods, i = [], 2 * C
+            for w in widths:
+                mods.append(torch.nn.Conv2d(i, w, 1, bias=True))
+                i = w
+            out.append(torch.nn.Sequential(*mods).to(device))
+        return out
     return [torch.nn.Sequential(torch.nn.Conv2d(2 * C, O, 1, bias=False), torch.nn.BatchNorm2d(O), torch.nn.LeakyReLU(0.2)).to(device)
             for C, O in EC_LAYERS]
 
@@ -705,20 +718,27 @@ def run_workload_e(args):
     chained like the model chains them, through mlsp_b200.edgeconv (no (B,2C,N,k) tensor).  The reference arm and the CPU
     baseline run the reference's own composition (get_graph_feature -> Conv2d -> BatchNorm2d -> LeakyReLU -> max)."""
     from mlsp_b200 import synth
-    B, N, k = synth.CONFIGS["A"]
+    seg = bool(getattr(args, "seg", False))
+    B, N, k = synth.CONFIGS["S" if seg else "A"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    metric = "MLSP clouds/sec (Bx1024,k=20) DGCNN EdgeConv backbone fwd+bwd"
-    cfg = {"workload": "edgeconv-E", "clouds_per_gpu": B, "points": N, "k": k, "layers_C_O": [list(l) for l in EC_LAYERS],
-           "batchnorm": "training mode (batch statistics over B*N*k edges, running statistics updated)",
-           "parallelism": f"batch-sharded x{world}, no data-path collective (BatchNorm statistics per rank, like the "
-                          "reference's DataParallel replicas)"}
+    if seg:       # --seg: the three shared layers of PointSegDA's DGCNN (plain Conv2d stacks with bias, no BatchNorm, no activation)
+        metric = "MLSP clouds/sec (Bx2048,k=20) PointSegDA EdgeConv shared layers fwd+bwd"
+        cfg = {"workload": "edgeconv-E-seg", "clouds_per_gpu": B, "points": N, "k": k,
+               "layers_C_widths": [[C, list(w)] for C, w in SEG_LAYERS], "batchnorm": "none (PointSegDA/Models.py:159-163)",
+               "parallelism": f"batch-sharded x{world}, no data-path collective"}
+    else:
+        metric = "MLSP clouds/sec (Bx1024,k=20) DGCNN EdgeConv backbone fwd+bwd"
+        cfg = {"workload": "edgeconv-E", "clouds_per_gpu": B, "points": N, "k": k, "layers_C_O": [list(l) for l in EC_LAYERS],
+               "batchnorm": "training mode (batch statistics over B*N*k edges, running statistics updated)",
+               "parallelism": f"batch-sharded x{world}, no data-path collective (BatchNorm statistics per rank, like the "
+                              "reference's DataParallel replicas)"}
 
     def cpu_time(Bs, reps):
         from oracle import ref_torch
         torch.set_num_threads(os.cpu_count() or 1)
-        layers = _ec_make_layers("cpu")
+        layers = _ec_make_layers("cpu", seg)
         clouds = synth.surface_clouds(Bs, N, 1234)
         _ec_reference_step(layers, clouds, k, ref_torch.get_graph_feature, ref_torch.knn)
         t0 = time.perf_counter()
@@ -764,7 +784,7 @@ def run_workload_e(args):
 
     host = synth.surface_clouds(B, N, 1234 + rank).pin_memory()
     clouds = host.to(device)
-    layers = _ec_make_layers(device)
+    layers = _ec_make_layers(device, seg)
     fused = [edgeconv.FusedEdgeConv.from_reference(seq, k=k) for seq in layers]
     params = [p_ for seq in layers for p_ in seq.parameters()]
 
@@ -843,7 +863,9 @@ def run_workload_e(args):
     P = B * N
     h = clouds
     s_ = _stream(device)
-    for (C, O), f in zip(EC_LAYERS, fused):
+    dims = [(f.convs[0].in_channels // 2, f.convs[-1].out_channels) for f in fused]
+    for (C, O), f in zip(dims, fused):
+        train = f.bn is not None
         with torch.no_grad():
             idx = M.knn(h, k)
             W, _b = f.effective_weight_bias()
@@ -853,7 +875,7 @@ def run_workload_e(args):
             rowsum = torch.empty((B, N, O), device=device)
             stats = torch.empty((2, O), dtype=torch.float64, device=device)
             coef = torch.empty((4, O), device=device)
-            gam = f.bn.weight.detach().abs()              # edge_conv folds the sign of gamma into the weight rows
+            gam = f.bn.weight.detach().abs() if train else None   # edge_conv folds the sign of gamma into the weight rows
             g = torch.randn(B, O, N, device=device)
             dyz = torch.empty((B, N, 2 * O), device=device)
             dp = torch.empty((2, O), device=device)
@@ -861,15 +883,19 @@ def run_workload_e(args):
 
             def red():
                 _lib.call("mlsp_edgeconv_reduce_fwd", _ptr(yz), _ptr(idx), B, N, O, k, _ptr(hsel), _ptr(slot),
-                          _ptr(rowsum), _ptr(stats), s_)
+                          _ptr(rowsum) if train else None, _ptr(stats) if train else None, s_)
 
             def bwd():
-                _lib.call("mlsp_edgeconv_bwd", _ptr(g), O * N, _ptr(yz), _ptr(idx), _ptr(hsel), _ptr(slot), _ptr(rowsum), _ptr(coef),
-                          B, N, O, k, 0.2, 1, _ptr(dyz), _ptr(dp), _ptr(ws), ws.numel(), s_)
+                _lib.call("mlsp_edgeconv_bwd", _ptr(g), O * N, _ptr(yz), _ptr(idx), _ptr(hsel), _ptr(slot),
+                          _ptr(rowsum) if train else None, _ptr(coef), B, N, O, k, 0.2 if train else 1.0, 1 if train else 0,
+                          _ptr(dyz), _ptr(dp), _ptr(ws), ws.numel(), s_)
 
             red()
-            _lib.call("mlsp_edgeconv_bn_coeffs", _ptr(stats), _ptr(gam), _ptr(f.bn.bias.detach()), O, float(P * k), 1e-5,
-                      _ptr(coef), None, None, None, 0.0, s_)
+            if train:
+                _lib.call("mlsp_edgeconv_bn_coeffs", _ptr(stats), _ptr(gam), _ptr(f.bn.bias.detach()), O, float(P * k), 1e-5,
+                          _ptr(coef), None, None, None, 0.0, s_)
+            else:
+                coef.copy_(torch.tensor([[1.0], [0.0], [0.0], [1.0]], device=device).expand(4, O))
             per[f"reduce_fwd_O{O}_C{C}"] = (span(red), P * (17 * O + 8 * k), 4.0 * P * k * O)
             per[f"bwd_O{O}_C{C}"] = (span(bwd), P * (29 * O + 8 * k), 4.0 * P * k * O)
             per[f"knn_C{C}"] = (span(lambda: M.knn(h, k)), None, None)
@@ -905,7 +931,7 @@ def run_workload_e(args):
             "traffic": None, "peak_source": pk["source"], "algorithmic_bytes_per_launch": by / n, "ms_per_launch": ms / n,
             "launches_per_step": n, "ops": [x for x in per if x.startswith(dom)],
             "l2_gather_bytes_per_launch": l2 / n, "l2_gather_GBps": l2 / (ms * 1e-3) / 1e9,
-            "note": "call-level span of mlsp_edgeconv_%s over the four layer shapes; algorithmic HBM bytes are the compact "
+            "note": "call-level span of mlsp_edgeconv_%s over the layer shapes; algorithmic HBM bytes are the compact "
                     "(B,N,O) tensors and idx -- the k row gathers (forward) / 128-bit reductions (backward) of 4*B*N*k*O bytes "
                     "go to L2, which is what bounds the kernel (l2_gather_GBps)" % ("reduce_fwd" if dom == "reduce_fwd" else "bwd")}
     cpu = None
@@ -920,7 +946,7 @@ def run_workload_e(args):
     from oracle import ref_torch
     ctx = {}
     with torch.backends.cudnn.flags(enabled=False):
-        ref_layers = _ec_make_layers(device)
+        ref_layers = _ec_make_layers(device, seg)
         for name, ggf, knn_ in (("torch_gpu_reference_ms", ref_torch.get_graph_feature, ref_torch.knn),
                                 ("dropin_graph_feature_plus_torch_layers_ms",
                                  lambda x_, k_, idx_: M.get_graph_feature(x_, None, k=k_, idx=idx_), M.knn)):
@@ -932,7 +958,7 @@ def run_workload_e(args):
                 _ec_reference_step(ref_layers, clouds, k, ggf, knn_)
             torch.cuda.synchronize()
             ctx[name] = round((time.perf_counter() - t0) / 3 * 1e3, 3)
-    launches_per_step = sum((1 if C == 3 else 3) + 3 + 4 for C, _ in EC_LAYERS)
+    launches_per_step = sum((1 if C == 3 else 3) + (3 if f.bn is not None else 2) + 4 for (C, _), f in zip(dims, fused))
     line = {"metric": metric, "value": B * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -959,6 +985,8 @@ def main():
                     help="A: PointDA-10 hot path (default, the BASELINE metric); S: PointSegDA hot path; "
                          "X: the scaling-sweep shape 256x4096, k=40 -- feature-space kNN on 64/128-dim features (configs[4]); "
                          "E: the DGCNN EdgeConv backbone without the edge tensor (SURVEY 8f rank 1), forward + backward")
+    ap.add_argument("--seg", action="store_true",
+                    help="with --workload E: the PointSegDA shape (16 x 2048) and its shared layers (plain Conv2d stacks, no BatchNorm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="headline on one stream (no target-builder overlap)")
     ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")

@@ -77,6 +77,9 @@ def test_workload_e_reference_arm_line(bench):
     """SURVEY 8f rank 1 (`--workload E`, the EdgeConv backbone): the reference arm runs the reference's layer composition on
     a bounded sample and prints the contract's line; the layer list is the PointDA DGCNN's conv1..conv4."""
     assert bench.EC_LAYERS == ((3, 64), (64, 64), (64, 128), (128, 256))          # PointDA/Models.py:91-94
+    assert bench.SEG_LAYERS == ((3, (64, 64)), (64, (64, 64)), (64, (64,)))        # PointSegDA/Models.py:159-163
+    seg = bench._ec_make_layers("cpu", seg=True)
+    assert [len(m) for m in seg] == [2, 2, 1] and seg[1][0].in_channels == 128 and seg[0][0].bias is not None
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "E", "--impl", "reference", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-500:]
