@@ -200,9 +200,12 @@ constexpr int PREP_THREADS = 256;
 
 __global__ void __launch_bounds__(PREP_THREADS)
 knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xx, int *__restrict__ counters,
-                float *__restrict__ xt, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo)
+                float *__restrict__ xt, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
+                int *__restrict__ cloud_mode)
 {
+    __shared__ float mode_acc[2];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) counters[threadIdx.x] = 0;
+    if (threadIdx.x < 2) mode_acc[threadIdx.x] = 0.0f;
     extern __shared__ float slab[];                       // [C][PREP_PTS + 1]
     const int b = blockIdx.y, n0 = blockIdx.x * PREP_PTS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -221,6 +224,29 @@ knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ x
         }
         const int n = n0 + lane;
         if (n < N) xx[(size_t)b * N + n] = s;
+    }
+    // Which pass 1 for this cloud?  The bf16-head product is within KT_EPS1_REL |x_i||x_j| of the distance: fine for
+    // activations whose spread is comparable to their norm (BatchNorm + LeakyReLU outputs: E|x|^2 ~ 1.3-3 x the variance),
+    // hopeless for a tight cluster far from the origin (BatchNorm-free layers with a bias: the bound exceeds the k-th
+    // distance, every list overflows and the rows fall back to the exact streaming selection, 50x slower).  The first
+    // CTA of a cloud estimates E|x|^2 and the total variance from its 32 staged points and flags the cloud for the
+    // three-term pass 1 (error KT_EPS_REL, 32x tighter, 13 % more filter time) when E|x|^2 > 4 Var.  Either choice is
+    // certified; the flag only picks the cheaper one that works.
+    if (blockIdx.x == 0) {
+        const int np = min(PREP_PTS, N - n0);
+        if ((int)threadIdx.x < C) {
+            float sm = 0.0f, sq = 0.0f;
+            for (int pt = 0; pt < np; ++pt) {
+                const float v = slab[threadIdx.x * (PREP_PTS + 1) + pt];
+                sm += v;
+                sq = fmaf(v, v, sq);
+            }
+            const float m2 = sq / (float)np, mu = sm / (float)np;
+            atomicAdd(&mode_acc[0], m2);                      // E|x|^2 summed over channels
+            atomicAdd(&mode_acc[1], fmaxf(m2 - mu * mu, 0.0f));   // total variance
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) cloud_mode[b] = (mode_acc[0] > 4.0f * mode_acc[1]) ? 1 : 0;
     }
     // rows: thread t handles channel pair (2t mod C ...) of point rows; consecutive threads -> consecutive channels
     const int pairs = C / 2;                               // C is even (64 or 128)
@@ -393,7 +419,9 @@ struct KtParams {
     int N, C, k, T;          // T = candidate tiles per cloud
     int stages;              // depth of the B-operand smem ring
     int pair;                // launched in clusters of two CTAs sharing the candidate blocks by TMA multicast
+    const int *cloud_mode;   // (B) written by the prep kernel: 1 = this cloud's pass 1 uses the three-term product (below)
     int mode;                // tuning hook (MLSP_KT_MODE): bit 0 skips the pass-1 math, bit 1 the pass-2 math, bit 2: three-term pass 1
+                             // for every cloud, bit 3: bf16-head pass 1 for every cloud (ignore cloud_mode)
 };
 
 // ------------------------------------------------------------------------------------------- main kernel
@@ -437,6 +465,9 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     const int b = blockIdx.y, i0 = blockIdx.x * KT_ROWS;
     const int N = P.N, T = P.T;
     const int rowbase = b * N;
+    // pass 1 on the three-term product (as tight as pass 2) instead of the bf16 heads: forced by the tuning hook, or
+    // chosen per cloud by the prep kernel for activations far from the origin (uniform over the CTA and its pair)
+    const bool three = (P.mode & 4) || (!(P.mode & 8) && P.cloud_mode[b] != 0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < KT_MAX_STAGES; ++s) {
@@ -471,7 +502,7 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             uint32_t ph = 0;
             for (int g = 0; g < 2 * T; ++g) {
                 const int j0 = (g % T) * KT_COLS;
-                const int nkb = (g < T && !(P.mode & 4)) ? SEG : KB;  // pass 1 multiplies hi.hi only: no lo blocks
+                const int nkb = (g < T && !three) ? SEG : KB;          // pass 1 multiplies hi.hi only: no lo blocks
                 for (int kb = 0; kb < nkb; ++kb) {   // B blocks: hi ..., lo ...
                     mbar_wait(empty + stage, ph ^ 1);
                     mbar_expect_tx(full + stage, KT_BLK_BYTES);
@@ -498,7 +529,7 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
                 mbar_wait(tm_empty + buf, ((g >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)buf * KT_COLS;
-                const bool first = g < T && !(P.mode & 4);          // pass 1: dot~ = hi.hi (a looser, cheaper bound)
+                const bool first = g < T && !three;                 // pass 1: dot~ = hi.hi (a looser, cheaper bound)
                 const int nkb = first ? SEG : KB;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(full + stage, ph);
@@ -592,7 +623,7 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             const float maxxx = __uint_as_float(max(max(max_s[0], max_s[1]), max(max_s[2], max_s[3])));
             const float eps = pair_eps(sqrtf(xxi), xxi, maxxx);   // bound for every candidate of the cloud
             // pass 1 saw dot~ = hi.hi only: |v1 - v| <= KT_EPS1_REL |x_i| max_j |x_j|
-            const float eps1 = (P.mode & 4) ? 0.0f : KT_EPS1_REL * sqrtf(xxi) * sqrtf(maxxx);
+            const float eps1 = three ? 0.0f : KT_EPS1_REL * sqrtf(xxi) * sqrtf(maxxx);
             float tau = -INFINITY;
 #pragma unroll
             for (int e = 0; e < NG; ++e)
@@ -981,7 +1012,7 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t co
 }
 
 struct KtLayout {
-    size_t off_counters, off_xx, off_hi, off_lo, off_xt, off_cand, off_cnt, total;
+    size_t off_counters, off_mode, off_xx, off_hi, off_lo, off_xt, off_cand, off_cnt, total;
 };
 
 static KtLayout kt_layout(int B, int C, int N, int k)
@@ -990,6 +1021,7 @@ static KtLayout kt_layout(int B, int C, int N, int k)
     KtLayout L;
     size_t o = 0;
     L.off_counters = o; o += 256;                                            // [0] fb_count, [1] certified rows
+    L.off_mode = o;     o += align_up(sizeof(int) * (size_t)B, 256);         // per-cloud pass-1 choice
     L.off_xx = o;       o += align_up(sizeof(float) * (size_t)B * N, 256);
     L.off_hi = o;       o += align_up(2 * (size_t)B * N * C, 1024);
     L.off_lo = o;       o += align_up(2 * (size_t)B * N * C, 1024);
@@ -1022,6 +1054,7 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     const KtLayout L = kt_layout(B, C, N, k);
     char *w = static_cast<char *>(ws);
     int *counters = reinterpret_cast<int *>(w + L.off_counters);
+    int *cloud_mode = reinterpret_cast<int *>(w + L.off_mode);
     float *xx = reinterpret_cast<float *>(w + L.off_xx);
     __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(w + L.off_hi);
     __nv_bfloat16 *lo = reinterpret_cast<__nv_bfloat16 *>(w + L.off_lo);
@@ -1029,7 +1062,7 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
 
     if (g_kt_stages & 1) {
         knn_prep_kernel<<<dim3((N + PREP_PTS - 1) / PREP_PTS, B), PREP_THREADS, sizeof(float) * C * (PREP_PTS + 1), st>>>(
-            x, C, N, xx, counters, xt, hi, lo);
+            x, C, N, xx, counters, xt, hi, lo, cloud_mode);
         MLSP_LAUNCH_CHECK("knn_prep_kernel");
     }
 
@@ -1044,7 +1077,7 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     if (rc) return rc;
 
     KtParams P;
-    P.xx = xx; P.xt = xt; P.idx = idx; P.fb_count = counters;
+    P.xx = xx; P.xt = xt; P.idx = idx; P.fb_count = counters; P.cloud_mode = cloud_mode;
     P.stats = counters + 1; P.dump = dump; P.edge_out = reinterpret_cast<float4 *>(edge_out);
     P.cand = reinterpret_cast<uint2 *>(w + L.off_cand); P.cand_cnt = reinterpret_cast<int *>(w + L.off_cnt); P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS;
     const int NG = (k <= 32) ? 32 : 64;

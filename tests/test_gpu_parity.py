@@ -787,3 +787,26 @@ def test_edge_conv_dgcnn_backbone_and_errors(dev):
         edgeconv.edge_conv(x0, torch.zeros(8, 8, device=dev), k)                 # weight is not (O, 2C)
     with pytest.raises(M.MlspError):
         edgeconv.edge_conv(x0, torch.zeros(8, 6, device=dev), k, negative_slope=-0.1)
+
+
+def test_knn_tensor_activations_far_from_the_origin(dev, orc, monkeypatch):
+    """A tight cluster far from the origin (what BatchNorm-free layers with a bias produce, PointSegDA/Models.py:159-184:
+    E|x|^2 ~ 10-30 x the variance): the bf16-head pass 1 of the tcgen05 filter bounds the k-th distance too loosely there
+    (every candidate list would overflow and the rows would fall back to the exact streaming selection), so the prep
+    kernel flags such clouds for the three-term pass 1.  Same bits as the oracle either way; with the flag almost every
+    row stays on the tensor path."""
+    from mlsp_b200 import _lib
+    B, C, N, k = 3, 64, 1024, 20
+    x = 0.25 * synth.smooth_features(B, C, N, 77) + 1.0
+    x[1] = synth.smooth_features(1, C, N, 78)[0]              # an ordinary cloud in the same batch keeps the fast pass
+    ref = orc.knn(x.numpy(), k)
+    idx, st = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
+    assert np.array_equal(_np(idx), ref)
+    assert st["fallback_rows"] <= 0.02 * B * N, st
+    monkeypatch.setenv("MLSP_KT_MODE", "8")                    # bf16 heads for every cloud: still exact, via the fallback
+    idx8, st8 = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
+    assert np.array_equal(_np(idx8), ref)
+    assert st8["fallback_rows"] >= st["fallback_rows"]
+    monkeypatch.setenv("MLSP_KT_MODE", "4")                    # three-term pass 1 for every cloud
+    idx4, st4 = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
+    assert np.array_equal(_np(idx4), ref) and st4["fallback_rows"] <= st["fallback_rows"]
