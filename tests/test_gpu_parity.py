@@ -797,8 +797,8 @@ def test_knn_tensor_activations_far_from_the_origin(dev, orc, monkeypatch):
     row stays on the tensor path."""
     from mlsp_b200 import _lib
     B, C, N, k = 3, 64, 1024, 20
-    x = 0.25 * synth.smooth_features(B, C, N, 77) + 1.0
-    x[1] = synth.smooth_features(1, C, N, 78)[0]              # an ordinary cloud in the same batch keeps the fast pass
+    x = synth.smooth_features(B, C, N, 77) + 0.7               # E|x|^2 / Var ~ 25; about half the rows would overflow
+    x[1] = synth.smooth_features(1, C, N, 78)[0]              # an ordinary cloud (ratio 1.5) in the same batch keeps the fast pass
     ref = orc.knn(x.numpy(), k)
     idx, st = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
     assert np.array_equal(_np(idx), ref)
@@ -806,7 +806,7 @@ def test_knn_tensor_activations_far_from_the_origin(dev, orc, monkeypatch):
     monkeypatch.setenv("MLSP_KT_MODE", "8")                    # bf16 heads for every cloud: still exact, via the fallback
     idx8, st8 = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
     assert np.array_equal(_np(idx8), ref)
-    assert st8["fallback_rows"] >= st["fallback_rows"]
+    assert st8["fallback_rows"] >= 0.1 * 2 * N, st8           # what the flag avoids
     monkeypatch.setenv("MLSP_KT_MODE", "4")                    # three-term pass 1 for every cloud
     idx4, st4 = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
     assert np.array_equal(_np(idx4), ref) and st4["fallback_rows"] <= st["fallback_rows"]
