@@ -122,6 +122,31 @@ def _split_weight(weight: torch.Tensor, C: int) -> torch.Tensor:
     return torch.cat((Wa, Wb - Wa), dim=0)
 
 
+class BNParams:
+    """BatchNorm2d as torch.nn.functional.batch_norm sees it: the tensors plus `batch_stats` (normalise with the statistics
+    of this batch), `update_running` (write the running statistics back with `momentum`) and `eps`."""
+    __slots__ = ("weight", "bias", "running_mean", "running_var", "batch_stats", "update_running", "momentum", "eps")
+
+    def __init__(self, weight, bias, running_mean, running_var, batch_stats, update_running, momentum, eps):
+        self.weight, self.bias, self.running_mean, self.running_var = weight, bias, running_mean, running_var
+        self.batch_stats, self.update_running, self.momentum, self.eps = batch_stats, update_running, momentum, eps
+
+    @classmethod
+    def from_module(cls, bn: nn.BatchNorm2d):
+        """What nn.BatchNorm2d.forward hands to F.batch_norm (torch/nn/modules/batchnorm.py), side effect included:
+        num_batches_tracked is incremented when the running statistics are going to be updated."""
+        has_running = bn.track_running_stats and bn.running_mean is not None
+        batch_stats = bn.training or not has_running
+        update = bn.training and has_running
+        momentum = 0.0
+        if update:
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+            momentum = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+        return cls(bn.weight, bn.bias, bn.running_mean if has_running else None, bn.running_var if has_running else None,
+                   batch_stats, update, momentum, bn.eps)
+
+
 def edge_conv(x: torch.Tensor, weight: torch.Tensor, k: int = 20, *, bias: torch.Tensor | None = None,
               bn: nn.BatchNorm2d | None = None, negative_slope: float | None = 0.2, idx: torch.Tensor | None = None):
     """max_j act(bn(conv1x1(get_graph_feature(x, args, k))))  ->  (B,O,N), without the (B,2C,N,k) tensor.
@@ -132,6 +157,12 @@ def edge_conv(x: torch.Tensor, weight: torch.Tensor, k: int = 20, *, bias: torch
     (PointDA uses 0.2), 0.0 = ReLU, None = no activation (PointSegDA's shared layers).  idx (B,N,k) int64 overrides the
     kNN graph (default: knn(x, k), PointDA/model_utils.py:9-16, same bits as the reference's ranking).
     Differentiable w.r.t. x, weight, bias and the BatchNorm affine parameters."""
+    return edge_conv_functional(x, weight, k, bias, BNParams.from_module(bn) if bn is not None else None, negative_slope, idx)
+
+
+def edge_conv_functional(x, weight, k, bias, bnp: BNParams | None, negative_slope, idx=None):
+    """edge_conv with BatchNorm given as tensors (BNParams) instead of a module -- the form mlsp_b200.lazy needs when it
+    meets F.batch_norm on a deferred graph feature."""
     _require_cuda_f32(x, "edge_conv")
     B, N = x.size(0), x.size(2)
     x = x.reshape(B, -1, N)
@@ -147,19 +178,19 @@ def edge_conv(x: torch.Tensor, weight: torch.Tensor, k: int = 20, *, bias: torch
     if slope < 0.0:
         raise MlspError("edge_conv: the activation must be non-decreasing (negative_slope >= 0)")
     idx = idx.contiguous()
-    train = bn is not None and (bn.training or not bn.track_running_stats or bn.running_mean is None)
-    # per-channel affine map after the convolution: training-mode BatchNorm -> (gamma, beta) with batch statistics,
-    # eval-mode BatchNorm -> a = gamma / sqrt(running_var + eps), c = beta - a * running_mean, no BatchNorm -> (1, 0).
-    if bn is None:
+    train = bnp is not None and bnp.batch_stats
+    # per-channel affine map after the convolution: batch-statistics BatchNorm -> (gamma, beta), running-statistics
+    # BatchNorm -> a = gamma / sqrt(running_var + eps), c = beta - a * running_mean, no BatchNorm -> (1, 0).
+    if bnp is None:
         p0 = p1 = None
     elif train:
-        p0, p1 = bn.weight, bn.bias
+        p0, p1 = bnp.weight, bnp.bias
     else:
-        invstd = torch.rsqrt(bn.running_var + bn.eps)
-        p0 = invstd * bn.weight if bn.weight is not None else invstd
-        p1 = -bn.running_mean * p0
-        if bn.bias is not None:
-            p1 = p1 + bn.bias
+        invstd = torch.rsqrt(bnp.running_var + bnp.eps)
+        p0 = invstd * bnp.weight if bnp.weight is not None else invstd
+        p1 = -bnp.running_mean * p0
+        if bnp.bias is not None:
+            p1 = p1 + bnp.bias
     # a negative scale turns the max over k into a min: fold its sign into the rows of W (and the bias), so that the
     # kernels always take a max and see a non-negative scale:  p0 * h = |p0| * (sign(p0) * h)
     sgn = None
@@ -176,15 +207,24 @@ def edge_conv(x: torch.Tensor, weight: torch.Tensor, k: int = 20, *, bias: torch
     if not train:
         return _EdgeConvReduce.apply(yz, idx, p0, p1, "affine", 0.0, slope)
     running = None
-    if bn.training and bn.track_running_stats and bn.running_mean is not None:
-        with torch.no_grad():                                        # torch/nn/modules/batchnorm.py: same update rule
-            bn.num_batches_tracked += 1
-        m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-        if (bn.running_mean.dtype != torch.float32 or not bn.running_mean.is_contiguous()
-                or not bn.running_var.is_contiguous()):
+    if bnp.update_running:
+        rm, rv = bnp.running_mean, bnp.running_var
+        if rm.dtype != torch.float32 or not rm.is_contiguous() or not rv.is_contiguous():
             raise MlspError("edge_conv: BatchNorm running statistics must be contiguous float32")
-        running = (bn.running_mean, bn.running_var, sgn, m)          # updated in place by the coefficient kernel
-    return _EdgeConvReduce.apply(yz, idx, p0, p1, "bn_train", bn.eps, slope, running)
+        running = (rm, rv, sgn, float(bnp.momentum))                 # updated in place by the coefficient kernel
+    return _EdgeConvReduce.apply(yz, idx, p0, p1, "bn_train", bnp.eps, slope, running)
+
+
+def fold_convs(layers):
+    """A stack of linear 1x1 convolutions [(W (O,I[,1,1]), b or None), ...] applied in order -> one (W, b)."""
+    W, b = layers[0][0].flatten(1), layers[0][1]
+    for Wn, bn_ in layers[1:]:
+        Wn = Wn.flatten(1)
+        b = Wn @ b if b is not None else None
+        if bn_ is not None:
+            b = bn_ if b is None else b + bn_
+        W = Wn @ W
+    return W, b
 
 
 class FusedEdgeConv(nn.Module):
@@ -231,15 +271,7 @@ class FusedEdgeConv(nn.Module):
 
     def effective_weight_bias(self):
         """The stack of linear 1x1 convolutions as one (O, 2C) matrix and bias (autograd reaches every layer's parameters)."""
-        W = self.convs[0].weight.flatten(1)
-        b = self.convs[0].bias
-        for c in self.convs[1:]:
-            Wn = c.weight.flatten(1)
-            b = (Wn @ b if b is not None else None)
-            if c.bias is not None:
-                b = c.bias if b is None else b + c.bias
-            W = Wn @ W
-        return W, b
+        return fold_convs([(c.weight, c.bias) for c in self.convs])
 
     def forward(self, x, idx=None):
         W, b = self.effective_weight_bias()

@@ -9,12 +9,16 @@ Models.py / mlsp.py / trainer.py keep calling `get_graph_feature(...)`, `mlsp.de
     mlsp_b200.patch.install_pcl_shim()        # before the reference imports `pcl`
     import PointDA.Models, MLSP.mlsp, utils.pc_utils
     mlsp_b200.patch.patch()                   # rebinds every captured name, returns what it touched
+
+`patch(fuse_edgeconv=True)` binds `get_graph_feature` to mlsp_b200.lazy.get_graph_feature instead: the graph feature is
+deferred, and a following `conv_2d(...)` / Conv2d stack + `.max(dim=-1)` runs as one EdgeConv layer without the
+(B,2C,N,k) tensor -- still with the reference's model code unchanged.
 """
 from __future__ import annotations
 
 import sys
 
-from . import ops, pcl_shim
+from . import lazy, ops, pcl_shim
 
 # module name -> {attribute: replacement}.  Both `PointDA.model_utils` and the top-level `model_utils`
 # exist as distinct module objects in the reference (PointDA/Models.py:4 vs :10), and Models.py binds
@@ -46,13 +50,16 @@ def install_pcl_shim(force: bool = False) -> bool:
     return pcl_shim.install(force)
 
 
-def patch(modules=None, strict: bool = False):
+def patch(modules=None, strict: bool = False, fuse_edgeconv: bool = False):
     """Rebind the hot-path names in every already-imported reference module (or in `modules`, a dict
     name -> module object).  Only attributes the module already has are replaced.  Returns a list of
-    "module.attr" strings; with strict=True raises if nothing was patched."""
+    "module.attr" strings; with strict=True raises if nothing was patched.  fuse_edgeconv=True: get_graph_feature
+    returns the deferred feature of mlsp_b200.lazy (EdgeConv layers run without the edge tensor)."""
     touched = []
     originals = {}
     for modname, table in TARGETS.items():
+        if fuse_edgeconv and "get_graph_feature" in table:
+            table = dict(table, get_graph_feature=lazy.get_graph_feature)
         mod = (modules or {}).get(modname) or sys.modules.get(modname)
         if mod is None:
             continue

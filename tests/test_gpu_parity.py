@@ -810,3 +810,47 @@ def test_knn_tensor_activations_far_from_the_origin(dev, orc, monkeypatch):
     monkeypatch.setenv("MLSP_KT_MODE", "4")                    # three-term pass 1 for every cloud
     idx4, st4 = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
     assert np.array_equal(_np(idx4), ref) and st4["fallback_rows"] <= st["fallback_rows"]
+
+
+def test_lazy_graph_feature_fuses_reference_shaped_layers(dev):
+    """mlsp_b200.lazy on the GPU: `conv_2d(get_graph_feature(x)).max(dim=-1)[0]` written exactly like the reference writes
+    it (PointDA/Models.py:114-116; PointSegDA/Models.py:171-174) runs as one edge_conv -- same output and gradients as the
+    drop-in get_graph_feature feeding the same torch modules -- and a transform-net-shaped block (two conv_2d before the
+    max, PointDA/model_utils.py:111-114) materialises the feature and matches as well."""
+    import copy
+    from mlsp_b200 import lazy
+    torch.manual_seed(2)
+    B, N, k = 2, 512, 20
+    x0 = synth.surface_clouds(B, N, 23).to(dev)
+    conv_2d = lambda i, o: torch.nn.Sequential(torch.nn.Conv2d(i, o, 1, bias=False), torch.nn.BatchNorm2d(o),   # noqa: E731
+                                               torch.nn.LeakyReLU(0.2, inplace=True)).to(dev)
+    l1, l2, t1, t2 = conv_2d(6, 64), conv_2d(128, 64), conv_2d(6, 64), conv_2d(64, 128)
+    s1, s2 = torch.nn.Conv2d(128, 64, 1).to(dev), torch.nn.Conv2d(64, 32, 1).to(dev)
+    mods = torch.nn.ModuleList([l1, l2, t1, t2, s1, s2])
+    twin = copy.deepcopy(mods)
+
+    def run(ms, ggf):
+        a1, a2, b1, b2, c1, c2 = ms
+        x = x0.clone().requires_grad_(True)
+        h1 = a1(ggf(x, None, k=k)).max(dim=-1, keepdim=False)[0]                       # PointDA layer
+        h2 = a2(ggf(h1, None, k=k)).max(dim=-1, keepdim=False)[0]
+        h3 = c2(c1(ggf(h2, None, k=k))).max(dim=-1, keepdim=False)[0]                  # PointSegDA stack
+        tr = b2(b1(ggf(x, None, k=k))).max(dim=-1, keepdim=False)[0]                   # transform-net shape: not foldable
+        loss = h1.square().mean() + h2.square().mean() + h3.square().mean() + tr.square().mean()
+        loss.backward()
+        return [h1, h2, h3, tr], x.grad, [p.grad for p in ms.parameters()]
+
+    lazy.counters.clear()
+    outs, gx, gp = run(mods, lazy.get_graph_feature)
+    assert lazy.counters == {"fused": 3, "materialised": 1}, dict(lazy.counters)
+    with torch.backends.cudnn.flags(enabled=False):                                   # fp32 convolutions (cuDNN would use TF32)
+        outs_r, gx_r, gp_r = run(twin, M.get_graph_feature)
+    assert float((outs[0] - outs_r[0]).abs().max()) <= 1e-5 * float(outs_r[0].abs().max())      # same neighbourhoods: strict
+    assert float((outs[3] - outs_r[3]).abs().max()) <= 1e-5 * float(outs_r[3].abs().max())
+    for a, b in zip(outs[1:3], outs_r[1:3]):          # deeper layers rank neighbours on activations that differ by rounding
+        assert float((a - b).norm()) <= 1e-3 * float(b.norm())
+    assert float((gx - gx_r).norm()) <= 1e-2 * float(gx_r.norm())
+    for a, b in zip(gp, gp_r):
+        assert float((a - b).norm()) <= 1e-2 * max(float(b.norm()), 1e-12)
+    for (n1, b1), (_, b2) in zip(mods.named_buffers(), twin.named_buffers()):
+        assert torch.allclose(b1.float(), b2.float(), rtol=1e-3, atol=1e-5), n1

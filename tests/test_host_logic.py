@@ -213,3 +213,114 @@ def test_edgeconv_weight_algebra():
     ref.backward(gy)
     assert torch.allclose(edgeconv._PointwiseYZ.apply(x, Wc), ref, atol=1e-12)
     assert torch.allclose(gx, x.grad, atol=1e-12) and torch.allclose(gw, Wc.grad, atol=1e-12) and gx.is_contiguous()
+
+
+# ---- mlsp_b200.lazy: the deferred graph feature (EdgeConv fusion behind the reference's unchanged model code)
+@pytest.fixture
+def lazy_on_cpu(monkeypatch):
+    """The interception logic of mlsp_b200.lazy with its two CUDA computations swapped for the oracle (the reference's
+    own op composition on the CPU): what is fused, what is materialised, and which arguments reach either."""
+    from mlsp_b200 import lazy
+    from oracle import edgeconv_ref, ref_torch
+
+    def fused(x, W, k, b, bnp, slope, idx):
+        idx = ref_torch.knn(x, k) if idx is None else idx
+        if bnp is None:
+            return edgeconv_ref.layer(x, idx, [W], [b], slope=slope)
+        running = (bnp.running_mean, bnp.running_var) if bnp.update_running else None
+        if not bnp.batch_stats:
+            running = (bnp.running_mean, bnp.running_var)
+        return edgeconv_ref.layer(x, idx, [W], [b], bnp.weight, bnp.bias, bn=True, eps=bnp.eps, slope=slope, running=running,
+                                  momentum=bnp.momentum, training=bnp.batch_stats)
+
+    monkeypatch.setattr(lazy.ops, "_require_cuda_f32", lambda *a, **k: None)
+    monkeypatch.setattr(lazy, "_materialise_backend", lambda x, k, idx: ref_torch.get_graph_feature(x, k, idx))
+    monkeypatch.setattr(lazy, "_fused_backend", fused)
+    lazy.counters.clear()
+    return lazy
+
+
+def test_lazy_graph_feature_interception(lazy_on_cpu):
+    import copy
+    from oracle import ref_torch
+    lazy = lazy_on_cpu
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 64)
+    t = lazy.get_graph_feature(x, None, k=8)
+    assert isinstance(t, lazy.LazyGraphFeature) and t.shape == (2, 6, 64, 8) and t.dim() == 4 and t.size(0) == 2
+    assert t.get_device() == -1 and t.dtype == torch.float32 and not lazy.counters            # nothing has run
+    # PointDA conv_2d + max over k -> one fused layer; BatchNorm's side effects happen exactly once
+    seq = torch.nn.Sequential(torch.nn.Conv2d(6, 16, 1, bias=False), torch.nn.BatchNorm2d(16), torch.nn.LeakyReLU(0.2, inplace=True))
+    twin = copy.deepcopy(seq)
+    y = seq(t)
+    assert isinstance(y, lazy.LazyGraphFeature) and y.shape == (2, 16, 64, 8) and not lazy.counters
+    out = y.max(dim=-1, keepdim=False)[0]
+    want = twin(ref_torch.get_graph_feature(x, 8)).max(dim=-1, keepdim=False)[0]
+    assert torch.allclose(out, want, atol=1e-6) and lazy.counters == {"fused": 1}
+    assert int(seq[1].num_batches_tracked) == 1 and torch.allclose(seq[1].running_var, twin[1].running_var, atol=1e-6)
+    seq.eval(), twin.eval()
+    out = seq(lazy.get_graph_feature(x, None, k=8)).max(dim=-1)[0]                               # running statistics
+    assert torch.allclose(out, twin(ref_torch.get_graph_feature(x, 8)).max(dim=-1)[0], atol=1e-6)
+    assert int(seq[1].num_batches_tracked) == 1 and lazy.counters == {"fused": 2}
+    # PointSegDA: plain Conv2d stack with bias, no activation
+    c1, c2 = torch.nn.Conv2d(6, 12, 1), torch.nn.Conv2d(12, 8, 1)
+    out = c2(c1(lazy.get_graph_feature(x, None, k=8))).max(dim=-1, keepdim=False)[0]
+    assert torch.allclose(out, c2(c1(ref_torch.get_graph_feature(x, 8))).max(dim=-1)[0], atol=1e-5) and lazy.counters["fused"] == 3
+    # a second convolution after the activation (the input-transform nets) cannot be folded: materialise and carry on
+    seq.train(), twin.train()
+    tail = torch.nn.Sequential(torch.nn.Conv2d(16, 8, 1), torch.nn.ReLU())
+    z = tail(seq(lazy.get_graph_feature(x, None, k=8)))
+    assert type(z) is torch.Tensor and lazy.counters["materialised"] == 1
+    assert torch.allclose(z, tail(twin(ref_torch.get_graph_feature(x, 8))), atol=1e-6)
+    assert torch.allclose(seq[1].running_mean, twin[1].running_mean, atol=1e-6)
+    # arbitrary use of the feature: it is the reference's tensor
+    feat = ref_torch.get_graph_feature(x, 8)
+    assert torch.equal(lazy.get_graph_feature(x, None, k=8) * 2.0, feat * 2.0)
+    assert torch.equal(lazy.get_graph_feature(x, None, k=8)[1, :, 3], feat[1, :, 3])
+    assert torch.cat((lazy.get_graph_feature(x, None, k=8), feat), 1).shape == (2, 12, 64, 8)
+    assert torch.equal(lazy.get_graph_feature(x, None, k=8).max(dim=2)[0], feat.max(dim=2)[0])  # not the max over k
+    wide = torch.nn.Conv2d(6, 8, (1, 3), padding=(0, 1))                                         # not a 1x1 convolution
+    assert torch.allclose(wide(lazy.get_graph_feature(x, None, k=8)), wide(feat), atol=1e-6)
+    with pytest.raises(RuntimeError):
+        lazy.get_graph_feature(x, None, k=65)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/MLSP"), reason="reference checkout not mounted")
+def test_lazy_fusion_runs_the_real_reference_models(lazy_on_cpu):
+    """In the build container: the reference's OWN DGCNN (PointDA/Models.py:82-162) and DGCNN_DefRec
+    (PointSegDA/Models.py:197-242) with get_graph_feature rebound by patch(fuse_edgeconv=True) -- model code untouched --
+    give the same logits and BatchNorm statistics as unpatched, with every EdgeConv layer fused (4 and 3) and only the
+    input-transform net's feature materialised."""
+    import copy
+    import warnings
+    from oracle import gen_golden_edgeconv
+    lazy = lazy_on_cpu
+    gen_golden_edgeconv.load_reference()
+    import PointDA.Models as PM
+    import PointSegDA.Models as SM
+    warnings.filterwarnings("ignore")
+    args = types.SimpleNamespace(num_class=10, cuda=False, gpus=[-1], model="dgcnn", dropout=0.5, encoder_type="",
+                                 density_num_class=16, pergroup=2)
+    torch.manual_seed(0)
+    cases = [(PM.DGCNN(args), dict(activate_DefRec=True, activate_normal=True), 4),
+             (SM.DGCNN_DefRec(types.SimpleNamespace(cuda=False, gpus=[-1], dropout=0.5, density_num_class=16, pergroup=5),
+                              in_size=3, num_classes=8), dict(make_seg=True, activate_DefRec=True), 3)]
+    x = M.synth.surface_clouds(2, 128, 5)
+    for model, kw, n_fused in cases:
+        twin = copy.deepcopy(model)
+        torch.manual_seed(1)
+        want = twin(x.clone(), **kw)                                   # the reference, untouched
+        lazy.counters.clear()
+        touched = patch.patch(fuse_edgeconv=True)
+        try:
+            assert any(t.endswith("get_graph_feature") for t in touched)
+            torch.manual_seed(1)
+            got = model(x.clone(), **kw)
+        finally:
+            patch.unpatch()
+        assert lazy.counters == {"fused": n_fused, "materialised": 1}, dict(lazy.counters)
+        assert set(got) == set(want)
+        for name in want:
+            assert torch.allclose(got[name], want[name], rtol=1e-4, atol=1e-5), name
+        for (n1, b1), (_, b2) in zip(model.named_buffers(), twin.named_buffers()):
+            assert torch.allclose(b1.float(), b2.float(), rtol=1e-4, atol=1e-6), n1
