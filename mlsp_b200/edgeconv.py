@@ -92,25 +92,43 @@ class _EdgeConvReduce(torch.autograd.Function):
 
 
 class _PointwiseYZ(torch.autograd.Function):
-    """yz (B,N,2O) = x^T Wcat^T -- the layer's one library GEMM, with a backward that keeps every operand in the layout
-    it already has: grad_x comes out as (B,C,N) directly, and the weight gradient is B partial products summed afterwards
-    (as a single (2O x B*N) x (B*N x C) product it is a long reduction that cuBLAS runs on a handful of CTAs)."""
+    """yz (B,N,2O) = [Y | Z],  Y = s*Wa x,  Z = s*(Wb - Wa) x + s*bias  -- the layer's one library GEMM together with the
+    weight split W = [Wa | Wb] -> [Wa ; Wb - Wa] and the sign fold (s = +-1 per output channel, see edge_conv_functional).
+    One autograd node instead of a dozen: the backward keeps every operand in the layout it already has (grad_x comes out
+    as (B,C,N) directly), makes the weight gradient from B partial products summed afterwards (as a single
+    (2O x B*N) x (B*N x C) product it is a long reduction that cuBLAS runs on a handful of CTAs), and un-splits it."""
 
     @staticmethod
-    def forward(ctx, x, Wcat):
-        ctx.save_for_backward(x, Wcat)
-        B = x.shape[0]
-        return torch.bmm(x.transpose(1, 2), Wcat.t().unsqueeze(0).expand(B, -1, -1))
+    def forward(ctx, x, weight, bias, sgn):
+        B, C, _ = x.shape
+        Wcat = _split_weight(weight, C)                                        # (2O, C)
+        if sgn is not None:
+            Wcat = Wcat * sgn.repeat(2).unsqueeze(1)
+        yz = torch.bmm(x.transpose(1, 2), Wcat.t().unsqueeze(0).expand(B, -1, -1))
+        if bias is not None:
+            zb = bias if sgn is None else bias * sgn
+            yz[..., Wcat.shape[0] // 2:] += zb
+        ctx.save_for_backward(x, Wcat, sgn)
+        ctx.wshape = weight.shape
+        return yz
 
     @staticmethod
     def backward(ctx, dyz):
-        x, Wcat = ctx.saved_tensors
-        gx = gw = None
+        x, Wcat, sgn = ctx.saved_tensors
+        O = Wcat.shape[0] // 2
+        gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.matmul(Wcat.t(), dyz.transpose(1, 2))                      # (C,2O) x (B,2O,N) -> (B,C,N)
         if ctx.needs_input_grad[1]:
-            gw = torch.bmm(dyz.transpose(1, 2), x.transpose(1, 2)).sum(dim=0)     # (B,2O,C) partials -> (2O,C)
-        return gx, gw
+            g = torch.bmm(dyz.transpose(1, 2), x.transpose(1, 2)).sum(dim=0)      # (B,2O,C) partials -> (2O,C)
+            if sgn is not None:
+                g = g * sgn.repeat(2).unsqueeze(1)
+            gw = torch.cat((g[:O] - g[O:], g[O:]), dim=1).reshape(ctx.wshape)     # d/dWa = gY - gZ, d/dWb = gZ
+        if ctx.needs_input_grad[2]:
+            gb = dyz[..., O:].sum(dim=(0, 1))
+            if sgn is not None:
+                gb = gb * sgn
+        return gx, gw, gb, None
 
 
 def _split_weight(weight: torch.Tensor, C: int) -> torch.Tensor:
@@ -197,13 +215,9 @@ def edge_conv_functional(x, weight, k, bias, bnp: BNParams | None, negative_slop
     if p0 is not None:
         sgn = torch.where(p0.detach() < 0, -1.0, 1.0).to(torch.float32)
         p0 = p0 * sgn
-    Wcat = _split_weight(weight, C)                                   # (2O, C), autograd tracks the split
-    if sgn is not None:
-        Wcat = Wcat * sgn.repeat(2).view(2 * O, 1)
-    yz = _PointwiseYZ.apply(x, Wcat)                                  # (B,N,2O) = [Y | Z]: the one library GEMM of the layer
-    if bias is not None:
-        zb = bias if sgn is None else bias * sgn
-        yz = yz + torch.cat((torch.zeros_like(zb), zb)).view(1, 1, 2 * O)
+    if weight.reshape(O, -1).shape[1] != 2 * C:
+        raise MlspError(f"edge_conv: weight has {weight.reshape(O, -1).shape[1]} input channels, expected 2*C = {2 * C}")
+    yz = _PointwiseYZ.apply(x, weight, bias, sgn)                     # (B,N,2O) = [Y | Z]: the one library GEMM of the layer
     if not train:
         return _EdgeConvReduce.apply(yz, idx, p0, p1, "affine", 0.0, slope)
     running = None
