@@ -250,15 +250,23 @@ class FusedEdgeConv(nn.Module):
         FusedEdgeConv.from_reference([sl.conv1, sl.conv2], k=20)           # PointSegDA: plain Conv2d stack, no activation
     """
 
-    def __init__(self, convs, bn=None, negative_slope=None, k: int = 20):
+    def __init__(self, convs, bn=None, negative_slope=None, k: int = 20, register: bool = True):
+        """register=False (what from_reference uses): the Conv2d / BatchNorm2d modules stay owned by the model they come
+        from -- they are not submodules of this layer, so the model's state_dict keys, parameter list, .train() / .to()
+        are exactly what they were (reference checkpoints load with strict=True; the optimiser sees each parameter once)."""
         super().__init__()
-        self.convs = nn.ModuleList(convs)
-        self.bn = bn
-        self.negative_slope = negative_slope
-        self.k = k
-        for c in self.convs:
+        convs = list(convs)
+        for c in convs:
             if not isinstance(c, nn.Conv2d) or c.kernel_size != (1, 1) or c.groups != 1:
                 raise MlspError("FusedEdgeConv: only 1x1 ungrouped Conv2d layers can be fused")
+        if register:
+            self.convs = nn.ModuleList(convs)
+            self.bn = bn
+        else:
+            object.__setattr__(self, "convs", tuple(convs))
+            object.__setattr__(self, "bn", bn)
+        self.negative_slope = negative_slope
+        self.k = k
 
     @classmethod
     def from_reference(cls, module, k: int = 20):
@@ -281,7 +289,7 @@ class FusedEdgeConv(nn.Module):
                 slope = 0.0
             else:
                 raise MlspError(f"FusedEdgeConv: cannot fuse {type(m).__name__}")
-        return cls(convs, bn, slope, k)
+        return cls(convs, bn, slope, k, register=False)
 
     def effective_weight_bias(self):
         """The stack of linear 1x1 convolutions as one (O, 2C) matrix and bias (autograd reaches every layer's parameters)."""

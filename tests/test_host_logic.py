@@ -198,6 +198,15 @@ def test_edgeconv_weight_algebra():
     wrapped = types.SimpleNamespace(conv=seq)                       # shape of the reference's conv_2d module
     layer = edgeconv.FusedEdgeConv.from_reference(wrapped, k=20)
     assert layer.bn is seq[1] and layer.negative_slope == 0.2 and layer.convs[0] is seq[0]
+    # the reference modules stay owned by their model: attaching the fused layer to it adds no state_dict key and no
+    # parameter, so reference checkpoints still load with strict=True and the optimiser sees each parameter once
+    host = torch.nn.Module()
+    host.conv1 = seq
+    keys, nparam = set(host.state_dict()), len(list(host.parameters()))
+    host.edge1 = layer
+    assert set(host.state_dict()) == keys and len(list(host.parameters())) == nparam and list(layer.parameters()) == []
+    own = edgeconv.FusedEdgeConv([torch.nn.Conv2d(6, 8, 1)], torch.nn.BatchNorm2d(8), 0.2)       # stand-alone: registered
+    assert len(list(own.parameters())) == 4 and "bn.running_mean" in own.state_dict()
     with pytest.raises(M.MlspError):
         edgeconv.FusedEdgeConv.from_reference([seq, torch.nn.Conv2d(8, 8, 1)])
     with pytest.raises(M.MlspError):
