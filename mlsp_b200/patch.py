@@ -68,7 +68,8 @@ def patch(modules=None, strict: bool = False, fuse_edgeconv: bool = False):
                 originals[(modname, attr)] = getattr(mod, attr)
                 setattr(mod, attr, fn)
                 touched.append(f"{modname}.{attr}")
-    patch.originals.update(originals)
+    for key, fn in originals.items():                 # a second patch() (e.g. fuse_edgeconv=True after a plain one) must not
+        patch.originals.setdefault(key, fn)           # forget the reference's own function
     if strict and not touched:
         raise RuntimeError("mlsp_b200.patch: no reference module is imported yet")
     return touched

@@ -57,6 +57,13 @@ def test_patch_rebinds_every_namespace():
     assert fake["MLSP.mlsp"].cal_density is ops.cal_density
     assert fake["MLSP.mlsp"].untouched is ref_fn
     assert patch.patch(modules=fake) == []                     # idempotent
+    # fuse_edgeconv=True on top: only get_graph_feature moves (to the deferred feature), and unpatch still knows the
+    # reference's own function
+    from mlsp_b200 import lazy
+    touched = patch.patch(modules=fake, fuse_edgeconv=True)
+    assert sorted(touched) == sorted(f"{m}.get_graph_feature" for m in patch.TARGETS if "get_graph_feature" in patch.TARGETS[m])
+    assert fake["PointDA.Models"].get_graph_feature is lazy.get_graph_feature and fake["model_utils"].knn is ops.knn
+    assert patch.patch.originals[("PointDA.Models", "get_graph_feature")] is ref_fn
     patch.patch.originals.clear()
 
 
