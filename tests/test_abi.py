@@ -61,6 +61,25 @@ def test_argument_errors_without_gpu(lib):
     assert rc == 2
 
 
+def test_edgeconv_argument_errors_without_gpu(lib):
+    """The EdgeConv entry points validate shapes / pointers / workspace before any CUDA call (codes of mlsp_b200.h)."""
+    buf = ctypes.create_string_buffer(256)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.mlsp_edgeconv_reduce_fwd(None, p, 1, 16, 8, 4, p, p, None, None, None) == 1 and b"null" in lib.mlsp_last_error()
+    assert lib.mlsp_edgeconv_reduce_fwd(p, p, 1, 16, 6, 4, p, p, None, None, None) == 2          # O % 4 != 0
+    assert lib.mlsp_edgeconv_reduce_fwd(p, p, 1, 1024, 8, 300, p, p, None, None, None) == 2      # k > 255: slots are bytes
+    assert lib.mlsp_edgeconv_reduce_fwd(p, p, 1, 16, 8, 40, p, p, None, None, None) == 1         # k > N
+    assert lib.mlsp_edgeconv_reduce_fwd(p, p, 1, 16, 8, 4, p, p, p, None, None) == 1             # rowsum without stats
+    assert lib.mlsp_edgeconv_bn_coeffs(p, None, None, 8, 64.0, 1e-5, p, p, None, None, 0.1, None) == 1   # running_mean without running_var
+    assert lib.mlsp_edgeconv_apply_fwd(p, p, 0, 16, 8, 0.2, p, None) == 1
+    args = (p, 16 * 8, p, p, p, p, None, p, 1, 16, 8, 4, 0.2)
+    assert lib.mlsp_edgeconv_bwd(*args, 1, p, p, p, 1 << 20, None) == 1 and b"rowsum" in lib.mlsp_last_error()   # bn_train needs rowsum
+    assert lib.mlsp_edgeconv_bwd(*args, 0, p, None, p, 16, None) == 4                             # workspace too small
+    assert lib.mlsp_edgeconv_bwd(p, 8, p, p, p, p, None, p, 1, 16, 8, 4, 0.2, 0, p, None, p, 1 << 20, None) == 1   # g batch stride < O*N
+    from mlsp_b200 import _lib
+    assert _lib.workspace_bytes(_lib.OP_EDGECONV_BWD, 32, 64, 1024, 20) >= 3 * 32 * 1024 * 64 * 4
+
+
 def test_ops_refuse_cpu_tensors():
     import torch
     import mlsp_b200 as M
