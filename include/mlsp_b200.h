@@ -18,7 +18,10 @@
  *   - return value: 0 on success, otherwise an MLSP_E* code; mlsp_last_error() (thread-local)
  *     describes it.  There is no CPU fallback: without a CUDA device every call fails.
  *   - indices are int64 at the boundary (the reference returns torch.long);
- *   - inputs must be finite (the reference's NaN behaviour is not reproduced).
+ *   - inputs must be finite for the index-producing ops (the reference's NaN ranking is not reproduced); the Chamfer
+ *     entry points propagate non-finite points to a NaN loss like torch.min does and never address outside the cloud;
+ *   - caller-supplied neighbour indices (idx arguments) must lie in [0, N): they are used as raw offsets, the host
+ *     layer (mlsp_b200/ops.py) range-checks them when MLSP_B200_CHECK_IDX=1 is set in the environment.
  */
 #ifndef MLSP_B200_H
 #define MLSP_B200_H
@@ -105,28 +108,34 @@ MLSP_API int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_t 
 
 /* a4 -- assign_region_to_point (utils/pc_utils.py:33-73) + the per-region counts and the first-fit
  *   region choice of deform_input (MLSP/mlsp.py:28-50, groups=1).
- *   X (B,C,N), C >= 3; order = host pointer to the 27 region ids of np.random.permutation(27);
+ *   X (B,C,N), C >= 3, addressed X[b*xs_b + c*xs_c + n*xs_n] (strides in floats; all three 0 = dense): the reference's
+ *   trainers pass the permuted view data.permute(0,2,1) of a (B,N,3) batch (PointDA/trainer.py:380-387), taken as is;
+ *   order = host pointer to the 27 region ids of np.random.permutation(27);
  *   region (B,N) int64; counts (B,27) int32; chosen (B) int32 (-1: no region reaches min_pts);
  *   nsel (B) int32 = points in the chosen region. */
-MLSP_API int mlsp_region_assign_select(const float *X, int B, int C, int N, const int32_t *order_host, int min_pts,
+MLSP_API int mlsp_region_assign_select(const float *X, int64_t xs_b, int64_t xs_c, int64_t xs_n, int B, int C, int N,
+                              const int32_t *order_host, int min_pts,
                               int64_t *region, int32_t *counts, int32_t *chosen, int32_t *nsel,
                               void *stream);
 
 /* a4/a8 -- the in-place deformation + mask of deform_input (MLSP/mlsp.py:44-48).
  *   The r-th point (ascending index) of cloud b's chosen region receives noise[(offset[b]+r)*3 + c]
- *   (the host's np.random.multivariate_normal draws); mask (B,C,N) is fully written:
+ *   (the host's np.random.multivariate_normal draws); X strided as above; mask (B,C,N) dense is fully written:
  *   1 on channels 0..2 of selected points, 0 elsewhere.  noise may be NULL (mask only). */
-MLSP_API int mlsp_region_mask_scatter(float *X, int B, int C, int N, const int64_t *region, const int32_t *chosen,
+MLSP_API int mlsp_region_mask_scatter(float *X, int64_t xs_b, int64_t xs_c, int64_t xs_n, int B, int C, int N,
+                             const int64_t *region, const int32_t *chosen,
                              const float *noise, const int32_t *offset, float *mask, void *stream);
 
 /* a5 -- collapse_to_point (utils/pc_utils.py:76-111), part 1: per point, the number of points with
- *   pd = (|x_j|^2 - 2 x_i.x_j) + |x_i|^2 <= r2 (`pts_pass` before thresholding).  x (B,C>=3,N). */
-MLSP_API int mlsp_ball_count(const float *x, int B, int C, int N, float r2, int32_t *cnt, void *stream);
+ *   pd = (|x_j|^2 - 2 x_i.x_j) + |x_i|^2 <= r2 (`pts_pass` before thresholding).  x (B,C>=3,N), strided like X above. */
+MLSP_API int mlsp_ball_count(const float *x, int64_t xs_b, int64_t xs_c, int64_t xs_n, int B, int C, int N, float r2,
+                    int32_t *cnt, void *stream);
 
 /* a5 part 2: collapse the ball of `centre[b]` (host-chosen by np.random.choice, pc_utils.py:102):
  *   in-ball points (ascending index) receive the noise rows, mask as in mlsp_region_mask_scatter.
  *   centre[b] < 0 leaves the cloud untouched. */
-MLSP_API int mlsp_ball_mask_scatter(float *X, int B, int C, int N, float r2, const int32_t *centre, const float *noise,
+MLSP_API int mlsp_ball_mask_scatter(float *X, int64_t xs_b, int64_t xs_c, int64_t xs_n, int B, int C, int N, float r2,
+                           const int32_t *centre, const float *noise,
                            const int32_t *offset, float *mask, void *stream);
 
 /* a6 -- cal_density (MLSP/mlsp.py:240-272): per-point ball cardinality with the python-pcl radius-search

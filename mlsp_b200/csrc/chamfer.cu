@@ -100,14 +100,21 @@ __device__ __forceinline__ void chamfer_fwd_body(const PtView &p1, const PtView 
                 const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
                 const float n = __fsqrt_rn(s);
                 const float D = __fadd_rn(__fmul_rn(n, n), q.w);
-                if (D < best) {
+                // torch.min propagates NaN (a diverged step): the first NaN of a lane sticks, like the first minimum
+                if (D < best || (D != D && best == best)) {
                     best = D;
                     bj = j;
                 }
             }
             const uint32_t vb = __float_as_uint(best);  // D >= 0: bit pattern orders like the value
-            const uint32_t wv = __reduce_min_sync(MLSP_FULL, vb);
-            const int wi = (int)__reduce_min_sync(MLSP_FULL, (vb == wv) ? (uint32_t)bj : 0x7fffffffu);
+            uint32_t wv = __reduce_min_sync(MLSP_FULL, vb);
+            int wi = (int)__reduce_min_sync(MLSP_FULL, (vb == wv) ? (uint32_t)bj : 0x7fffffffu);
+            const unsigned nan_lanes = __ballot_sync(MLSP_FULL, best != best);
+            if (nan_lanes) {                            // non-finite input: NaN row minimum at the first NaN column
+                wv = 0x7fc00000u;
+                wi = (int)__reduce_min_sync(MLSP_FULL, (best != best) ? (uint32_t)bj : 0x7fffffffu);
+            }
+            if (wi >= N) wi = 0;                        // every D was +inf: torch.min returns index 0
             if (lane == 0) {
                 const float m = mb[i];
                 if (rowmin) rowmin[(size_t)b * N + i] = __uint_as_float(wv);
@@ -215,7 +222,7 @@ __device__ __forceinline__ void chamfer_bwd_body(const PtView &p1, const PtView 
         const float m = mb[i];
         if (m == 0.0f) continue;
         const long long j = argmin[(size_t)b * N + i];
-        if (j < 0) continue;
+        if (j < 0 || j >= N) continue;                 // unmasked row / corrupted index: never address outside the cloud
         const float3 a = p1.get(b, i), q = p2.get(b, (int)j);
         const float w = 2.0f * up * m;
         const float gx = (a.x - q.x) * w, gy = (a.y - q.y) * w, gz = (a.z - q.z) * w;

@@ -19,6 +19,12 @@ struct RegionOrder {
     int32_t id[27];
 };
 
+// X (B,C,N) addressed X[b*sb + c*sc + n*sn]: the reference's trainers hand deform_input the permuted view
+// `data.permute(0,2,1)` of a (B,N,3) batch (PointDA/trainer.py:380-387), i.e. strides (3N, 1, 3); it is deformed in place.
+struct CloudView {
+    long long sb, sc, sn;
+};
+
 __device__ __forceinline__ int voxel_axis(float v)
 {
     const float t1 = -0.3333333432674408f, t2 = 0.3333333432674408f;
@@ -30,7 +36,7 @@ __device__ __forceinline__ int voxel_axis(float v)
 }
 
 __global__ void __launch_bounds__(256)
-region_assign_select_kernel(const float *__restrict__ X, int C, int N, RegionOrder order, int min_pts,
+region_assign_select_kernel(const float *__restrict__ X, CloudView V, int N, RegionOrder order, int min_pts,
                             int64_t *__restrict__ region, int32_t *__restrict__ counts,
                             int32_t *__restrict__ chosen, int32_t *__restrict__ nsel)
 {
@@ -38,9 +44,10 @@ region_assign_select_kernel(const float *__restrict__ X, int C, int N, RegionOrd
     const int b = blockIdx.x;
     if (threadIdx.x < 27) hist[threadIdx.x] = 0;
     __syncthreads();
-    const float *Xb = X + (size_t)b * C * N;
+    const float *Xb = X + b * V.sb;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const int qx = voxel_axis(Xb[n]), qy = voxel_axis(Xb[N + n]), qz = voxel_axis(Xb[2 * N + n]);
+        const float *pn = Xb + n * V.sn;
+        const int qx = voxel_axis(pn[0]), qy = voxel_axis(pn[V.sc]), qz = voxel_axis(pn[2 * V.sc]);
         const int r = (qx >= 0 && qy >= 0 && qz >= 0) ? 9 * qx + 3 * qy + qz : 0;
         region[(size_t)b * N + n] = r;
         atomicAdd(&hist[r], 1);
@@ -67,7 +74,7 @@ region_assign_select_kernel(const float *__restrict__ X, int C, int N, RegionOrd
 // order (the order of a boolean-mask assignment in torch), mask is written for every element.
 // One CTA per cloud; block-wide exclusive scan over chunks of blockDim points.
 template <typename FlagFn>
-__device__ __forceinline__ void scatter_flagged(float *Xb, float *Mb, int C, int N, const float *noise,
+__device__ __forceinline__ void scatter_flagged(float *Xb, CloudView V, float *Mb, int C, int N, const float *noise,
                                                 FlagFn flag)
 {
     __shared__ int warp_tot[32];
@@ -87,9 +94,10 @@ __device__ __forceinline__ void scatter_flagged(float *Xb, float *Mb, int C, int
         if (n < N) {
             for (int c = 0; c < C; ++c) Mb[(size_t)c * N + n] = (f && c < 3) ? 1.0f : 0.0f;
             if (f && noise) {
-                Xb[n] = noise[(size_t)rank * 3 + 0];
-                Xb[N + n] = noise[(size_t)rank * 3 + 1];
-                Xb[2 * N + n] = noise[(size_t)rank * 3 + 2];
+                float *pn = Xb + n * V.sn;
+                pn[0] = noise[(size_t)rank * 3 + 0];
+                pn[V.sc] = noise[(size_t)rank * 3 + 1];
+                pn[2 * V.sc] = noise[(size_t)rank * 3 + 2];
             }
         }
         __syncthreads();
@@ -103,7 +111,7 @@ __device__ __forceinline__ void scatter_flagged(float *Xb, float *Mb, int C, int
 }
 
 __global__ void __launch_bounds__(256)
-region_mask_scatter_kernel(float *__restrict__ X, int C, int N, const int64_t *__restrict__ region,
+region_mask_scatter_kernel(float *__restrict__ X, CloudView V, int C, int N, const int64_t *__restrict__ region,
                            const int32_t *__restrict__ chosen, const float *__restrict__ noise,
                            const int32_t *__restrict__ offset, float *__restrict__ mask)
 {
@@ -111,7 +119,7 @@ region_mask_scatter_kernel(float *__restrict__ X, int C, int N, const int64_t *_
     const int sel = chosen[b];
     const int64_t *rb = region + (size_t)b * N;
     const float *nz = noise ? noise + (size_t)offset[b] * 3 : nullptr;
-    scatter_flagged(X + (size_t)b * C * N, mask + (size_t)b * C * N, C, N, nz,
+    scatter_flagged(X + b * V.sb, V, mask + (size_t)b * C * N, C, N, nz,
                     [&](int n) { return sel >= 0 && rb[n] == (int64_t)sel; });
 }
 
@@ -131,21 +139,22 @@ constexpr int BALL_ROWS_PER_WARP = 4;
 constexpr int BALL_THREADS = 256;
 constexpr int BALL_ROWS = (BALL_THREADS / 32) * BALL_ROWS_PER_WARP;
 
-// stage cloud b as float4 (x,y,z,xx) into shared memory, N points, from channel-major (C,N) storage
-__device__ __forceinline__ void stage_cloud_soa(const float *Xb, int N, float4 *s)
+// stage cloud b as float4 (x,y,z,xx) into shared memory, N points, from (C,N) storage with strides (sc, sn)
+__device__ __forceinline__ void stage_cloud_soa(const float *Xb, CloudView V, int N, float4 *s)
 {
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        const float x = Xb[n], y = Xb[N + n], z = Xb[2 * N + n];
+        const float *pn = Xb + n * V.sn;
+        const float x = pn[0], y = pn[V.sc], z = pn[2 * V.sc];
         s[n] = make_float4(x, y, z, sq3(x, y, z));
     }
 }
 
 __global__ void __launch_bounds__(BALL_THREADS)
-ball_count_kernel(const float *__restrict__ X, int C, int N, float r2, int32_t *__restrict__ cnt)
+ball_count_kernel(const float *__restrict__ X, CloudView V, int N, float r2, int32_t *__restrict__ cnt)
 {
     extern __shared__ float4 cloud[];
     const int b = blockIdx.y;
-    stage_cloud_soa(X + (size_t)b * C * N, N, cloud);
+    stage_cloud_soa(X + b * V.sb, V, N, cloud);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = blockIdx.x * BALL_ROWS + warp * BALL_ROWS_PER_WARP;
@@ -169,23 +178,25 @@ ball_count_kernel(const float *__restrict__ X, int C, int N, float r2, int32_t *
 }
 
 __global__ void __launch_bounds__(256)
-ball_mask_scatter_kernel(float *__restrict__ X, int C, int N, float r2, const int32_t *__restrict__ centre,
+ball_mask_scatter_kernel(float *__restrict__ X, CloudView V, int C, int N, float r2, const int32_t *__restrict__ centre,
                          const float *__restrict__ noise, const int32_t *__restrict__ offset,
                          float *__restrict__ mask)
 {
     const int b = blockIdx.x;
-    float *Xb = X + (size_t)b * C * N;
+    float *Xb = X + b * V.sb;
     const int ci = centre[b];
     float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ci >= 0 && ci < N) {
-        const float x = Xb[ci], y = Xb[N + ci], z = Xb[2 * N + ci];
+        const float *pn = Xb + ci * V.sn;
+        const float x = pn[0], y = pn[V.sc], z = pn[2 * V.sc];
         pc = make_float4(x, y, z, sq3(x, y, z));
     }
     __syncthreads();  // every thread has read the centre before any thread overwrites it
     const float *nz = noise ? noise + (size_t)offset[b] * 3 : nullptr;
-    scatter_flagged(Xb, mask + (size_t)b * C * N, C, N, nz, [&](int n) {
+    scatter_flagged(Xb, V, mask + (size_t)b * C * N, C, N, nz, [&](int n) {
         if (ci < 0 || ci >= N) return false;
-        const float x = Xb[n], y = Xb[N + n], z = Xb[2 * N + n];
+        const float *pn = Xb + n * V.sn;
+        const float x = pn[0], y = pn[V.sc], z = pn[2 * V.sc];
         return ball_pd(pc, make_float4(x, y, z, sq3(x, y, z))) <= r2;
     });
 }
@@ -377,7 +388,16 @@ pca_normals_kernel(const float *__restrict__ pts, const int64_t *__restrict__ id
 }  // namespace mlsp
 
 // =====================================================================================================
-extern "C" int mlsp_region_assign_select(const float *X, int B, int C, int N, const int32_t *order_host,
+// strides (in floats) of a (B,C,N) view; all zero = dense
+static inline mlsp::CloudView cloud_view(int64_t sb, int64_t sc, int64_t sn, int C, int N)
+{
+    mlsp::CloudView V;
+    if (sb == 0 && sc == 0 && sn == 0) { V.sb = (long long)C * N; V.sc = N; V.sn = 1; }
+    else { V.sb = sb; V.sc = sc; V.sn = sn; }
+    return V;
+}
+
+extern "C" int mlsp_region_assign_select(const float *X, int64_t xs_b, int64_t xs_c, int64_t xs_n, int B, int C, int N, const int32_t *order_host,
                                          int min_pts, int64_t *region, int32_t *counts, int32_t *chosen,
                                          int32_t *nsel, void *stream)
 {
@@ -389,24 +409,24 @@ extern "C" int mlsp_region_assign_select(const float *X, int B, int C, int N, co
         MLSP_REQUIRE(order_host[t] >= 0 && order_host[t] < 27, MLSP_EINVAL, "region_assign_select: bad region id");
         ord.id[t] = order_host[t];
     }
-    region_assign_select_kernel<<<B, 256, 0, as_stream(stream)>>>(X, C, N, ord, min_pts, region, counts, chosen, nsel);
+    region_assign_select_kernel<<<B, 256, 0, as_stream(stream)>>>(X, cloud_view(xs_b, xs_c, xs_n, C, N), N, ord, min_pts, region, counts, chosen, nsel);
     MLSP_LAUNCH_CHECK("region_assign_select_kernel");
     return MLSP_OK;
 }
 
-extern "C" int mlsp_region_mask_scatter(float *X, int B, int C, int N, const int64_t *region, const int32_t *chosen,
+extern "C" int mlsp_region_mask_scatter(float *X, int64_t xs_b, int64_t xs_c, int64_t xs_n, int B, int C, int N, const int64_t *region, const int32_t *chosen,
                                         const float *noise, const int32_t *offset, float *mask, void *stream)
 {
     using namespace mlsp;
     MLSP_REQUIRE(X && region && chosen && mask, MLSP_EINVAL, "region_mask_scatter: null pointer");
     MLSP_REQUIRE(!noise || offset, MLSP_EINVAL, "region_mask_scatter: noise without offsets");
     MLSP_REQUIRE(B > 0 && C >= 3 && N > 0, MLSP_EINVAL, "region_mask_scatter: bad shape");
-    region_mask_scatter_kernel<<<B, 256, 0, as_stream(stream)>>>(X, C, N, region, chosen, noise, offset, mask);
+    region_mask_scatter_kernel<<<B, 256, 0, as_stream(stream)>>>(X, cloud_view(xs_b, xs_c, xs_n, C, N), C, N, region, chosen, noise, offset, mask);
     MLSP_LAUNCH_CHECK("region_mask_scatter_kernel");
     return MLSP_OK;
 }
 
-extern "C" int mlsp_ball_count(const float *x, int B, int C, int N, float r2, int32_t *cnt, void *stream)
+extern "C" int mlsp_ball_count(const float *x, int64_t xs_b, int64_t xs_c, int64_t xs_n, int B, int C, int N, float r2, int32_t *cnt, void *stream)
 {
     using namespace mlsp;
     MLSP_REQUIRE(x && cnt, MLSP_EINVAL, "ball_count: null pointer");
@@ -414,19 +434,19 @@ extern "C" int mlsp_ball_count(const float *x, int B, int C, int N, float r2, in
     const size_t smem = sizeof(float4) * (size_t)N;
     MLSP_REQUIRE(smem <= 200 * 1024, MLSP_EUNSUPPORTED, "ball_count: N=%d too large", N);
     MLSP_CUDA(cudaFuncSetAttribute(ball_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ball_count_kernel<<<dim3((N + BALL_ROWS - 1) / BALL_ROWS, B), BALL_THREADS, smem, as_stream(stream)>>>(x, C, N, r2, cnt);
+    ball_count_kernel<<<dim3((N + BALL_ROWS - 1) / BALL_ROWS, B), BALL_THREADS, smem, as_stream(stream)>>>(x, cloud_view(xs_b, xs_c, xs_n, C, N), N, r2, cnt);
     MLSP_LAUNCH_CHECK("ball_count_kernel");
     return MLSP_OK;
 }
 
-extern "C" int mlsp_ball_mask_scatter(float *X, int B, int C, int N, float r2, const int32_t *centre,
+extern "C" int mlsp_ball_mask_scatter(float *X, int64_t xs_b, int64_t xs_c, int64_t xs_n, int B, int C, int N, float r2, const int32_t *centre,
                                       const float *noise, const int32_t *offset, float *mask, void *stream)
 {
     using namespace mlsp;
     MLSP_REQUIRE(X && centre && mask, MLSP_EINVAL, "ball_mask_scatter: null pointer");
     MLSP_REQUIRE(!noise || offset, MLSP_EINVAL, "ball_mask_scatter: noise without offsets");
     MLSP_REQUIRE(B > 0 && C >= 3 && N > 0, MLSP_EINVAL, "ball_mask_scatter: bad shape");
-    ball_mask_scatter_kernel<<<B, 256, 0, as_stream(stream)>>>(X, C, N, r2, centre, noise, offset, mask);
+    ball_mask_scatter_kernel<<<B, 256, 0, as_stream(stream)>>>(X, cloud_view(xs_b, xs_c, xs_n, C, N), C, N, r2, centre, noise, offset, mask);
     MLSP_LAUNCH_CHECK("ball_mask_scatter_kernel");
     return MLSP_OK;
 }

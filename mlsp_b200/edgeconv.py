@@ -192,6 +192,9 @@ def edge_conv_functional(x, weight, k, bias, bnp: BNParams | None, negative_slop
         idx = knn(x, int(k))
     elif idx.shape != (B, N, k) or idx.dtype != torch.int64 or idx.device != x.device:
         raise MlspError("edge_conv: idx must be int64 (B,N,k) on x's device")
+    else:
+        from .ops import _check_idx
+        _check_idx(idx, N, "edge_conv")
     slope = 1.0 if negative_slope is None else float(negative_slope)
     if slope < 0.0:
         raise MlspError("edge_conv: the activation must be non-decreasing (negative_slope >= 0)")

@@ -160,7 +160,8 @@ class LazyGraphFeature(torch.Tensor):
         if not c.convs or dim is None or isinstance(dim, torch.Tensor) or keepdim or dim not in (-1, 3):
             return None
         O = c.convs[-1][0].shape[0]
-        if O % 4 != 0 or O > 1024:
+        # the same support predicate as edge_conv_functional / the C ABI: anything else materialises the reference's tensor
+        if O % 4 != 0 or O > 1024 or self.shape[3] > 64:
             return None
         return MaxResult(self.fused_max(), None)      # the reference takes [0]; the arg-max over k is not produced
 

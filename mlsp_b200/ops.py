@@ -10,6 +10,7 @@ There is no CPU path: non-CUDA tensors raise.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -38,6 +39,17 @@ def _stream(device) -> ctypes.c_void_p:
 
 def _ptr(t) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+_CHECK_IDX = os.environ.get("MLSP_B200_CHECK_IDX", "0") not in ("", "0")
+
+
+def _check_idx(idx: torch.Tensor, N: int, name: str) -> None:
+    """Caller-supplied neighbour indices are raw offsets for the gather / scatter kernels (include/mlsp_b200.h).  The
+    reference's advanced indexing raises on out-of-range values; this debug check (MLSP_B200_CHECK_IDX=1, one device
+    sync per call) does the same."""
+    if _CHECK_IDX and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= N):
+        raise IndexError(f"{name}: neighbour index out of range [0, {N})")
 
 
 def _workspace(op: int, B: int, C: int, N: int, k: int, device) -> torch.Tensor:
@@ -178,6 +190,7 @@ def get_graph_feature(x: torch.Tensor, args=None, k: int = 20, idx: torch.Tensor
         return _GraphFeature.apply(x, int(k))
     if idx.shape != (B, N, k) or idx.dtype != torch.int64 or idx.device != x.device:
         raise MlspError("get_graph_feature: idx must be int64 (B,N,k) on x's device")
+    _check_idx(idx, N, "get_graph_feature")
     return _EdgeGather.apply(x, idx.contiguous())
 
 
@@ -199,7 +212,7 @@ def fps_from_start(xyz: torch.Tensor, npoint: int, start: torch.Tensor):
     _require_cuda_f32(xyz, "fps")
     xyz = xyz.detach().contiguous()
     B, _, N = xyz.shape
-    if start.device.type == "cpu" and (int(start.min()) < 0 or int(start.max()) >= N):
+    if (start.device.type == "cpu" or _CHECK_IDX) and (int(start.min()) < 0 or int(start.max()) >= N):
         raise MlspError("fps: start index out of range")
     start = start.to(device=xyz.device, dtype=torch.int64, non_blocking=True).contiguous()
     cen = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
@@ -218,6 +231,11 @@ def region_mean(num_regions: int = NREGIONS) -> np.ndarray:
     return np.array([[x, y, z] for x in axis for y in axis for z in axis])
 
 
+def _strides(X: torch.Tensor):
+    """(batch, channel, point) strides of a (B,C,N) view, in elements, for the strided entry points."""
+    return X.stride(0), X.stride(1), X.stride(2)
+
+
 def _region_pass(X: torch.Tensor, order: np.ndarray, min_pts: int):
     B, C, N = X.shape
     region = torch.empty((B, N), dtype=torch.int64, device=X.device)
@@ -225,7 +243,7 @@ def _region_pass(X: torch.Tensor, order: np.ndarray, min_pts: int):
     sel = torch.empty((2, B), dtype=torch.int32, device=X.device)   # [chosen ; nsel]
     order32 = np.ascontiguousarray(order, dtype=np.int32)
     with torch.cuda.device(X.device):
-        _lib.call("mlsp_region_assign_select", _ptr(X), B, C, N, ctypes.c_void_p(order32.ctypes.data), int(min_pts),
+        _lib.call("mlsp_region_assign_select", _ptr(X), *_strides(X), B, C, N, ctypes.c_void_p(order32.ctypes.data), int(min_pts),
                   _ptr(region), _ptr(counts), _ptr(sel[0]), _ptr(sel[1]), _stream(X.device))
     return region, counts, sel
 
@@ -233,7 +251,7 @@ def _region_pass(X: torch.Tensor, order: np.ndarray, min_pts: int):
 def assign_region_to_point(X: torch.Tensor, device=None) -> torch.Tensor:
     """assign_region_to_point(X, device): utils/pc_utils.py:33-73.  X (B,C,N) -> (B,N) int64."""
     _require_cuda_f32(X, "assign_region_to_point")
-    region, _, _ = _region_pass(X.detach().contiguous(), np.arange(NREGIONS ** 3), 0)
+    region, _, _ = _region_pass(X.detach(), np.arange(NREGIONS ** 3), 0)
     return region
 
 
@@ -331,16 +349,17 @@ def _upload_noise(noise, counts, device):
 
 def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxels", device="cuda:0", groups: int = 1):
     """deform_input(X, lookup, DefRec_dist, device, groups): MLSP/mlsp.py:10-51.
-    Mutates X (B,C,N) in place and returns (X, mask (B,C,N)).  The numpy RNG is consumed on the host in the
+    Mutates X (B,C,N) in place -- any strides: the trainers pass the permuted view `data.permute(0,2,1)` of a
+    (B,N,3) batch (PointDA/trainer.py:380-387) -- and returns (X, mask (B,C,N)).  The numpy RNG is consumed on the host in the
     reference's order (one permutation(27); per cloud one choice / multivariate_normal), so seeded runs
     reproduce the reference's masks and deformed points bit for bit; region assignment, histogram, choice,
     ranking and scatter run on the GPU.  One device->host read of 2B ints (voxel mode)."""
     _require_cuda_f32(X, "deform_input")
-    if not X.is_contiguous():
-        raise MlspError("deform_input: X must be contiguous (it is modified in place)")
+    if X.dim() != 3:
+        raise MlspError(f"deform_input: expected (B,C,N), got {tuple(X.shape)}")
     B, C, N = X.shape
     region_ids = np.random.permutation(NREGIONS ** 3)                      # mlsp.py:28
-    mask = torch.empty_like(X)
+    mask = torch.empty((B, C, N), dtype=torch.float32, device=X.device)    # dense whatever X's strides are
     if DefRec_dist == "volume_based_radius":
         return _deform_radius(X, mask)
     if groups > 1:
@@ -354,7 +373,7 @@ def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxel
         counts = np.where(chosen >= 0, nsel, 0)
         noise, offsets = _upload_noise(_draw_gaussians(look[np.maximum(chosen, 0)], counts), counts, X.device)
     with torch.cuda.device(X.device):
-        _lib.call("mlsp_region_mask_scatter", _ptr(X), B, C, N, _ptr(region), _ptr(sel[0]), _ptr(noise),
+        _lib.call("mlsp_region_mask_scatter", _ptr(X), *_strides(X), B, C, N, _ptr(region), _ptr(sel[0]), _ptr(noise),
                   _ptr(offsets), _ptr(mask), _stream(X.device))
     return X, mask
 
@@ -387,7 +406,7 @@ def _deform_voxel_groups(X, mask, lookup, region_ids, DefRec_dist, groups):
     with torch.cuda.device(X.device):
         for g in range(groups):
             out = mask if g == 0 else part
-            _lib.call("mlsp_region_mask_scatter", _ptr(X), B, C, N, _ptr(region), _ptr(chosen_d[g]), _ptr(noise),
+            _lib.call("mlsp_region_mask_scatter", _ptr(X), *_strides(X), B, C, N, _ptr(region), _ptr(chosen_d[g]), _ptr(noise),
                       _ptr(offsets[g]) if offsets is not None else None, _ptr(out), _stream(X.device))
             if g:
                 torch.maximum(mask, part, out=mask)
@@ -397,11 +416,11 @@ def _deform_voxel_groups(X, mask, lookup, region_ids, DefRec_dist, groups):
 def ball_count(x: torch.Tensor, r2: float = RADIUS ** 2) -> torch.Tensor:
     """Row sums of the in-ball matrix of collapse_to_point (utils/pc_utils.py:86-96). x (B,C,N) -> (B,N) int32."""
     _require_cuda_f32(x, "ball_count")
-    x = x.detach().contiguous()
+    x = x.detach()
     B, C, N = x.shape
     cnt = torch.empty((B, N), dtype=torch.int32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.call("mlsp_ball_count", _ptr(x), B, C, N, ctypes.c_float(r2), _ptr(cnt), _stream(x.device))
+        _lib.call("mlsp_ball_count", _ptr(x), *_strides(x), B, C, N, ctypes.c_float(r2), _ptr(cnt), _stream(x.device))
     return cnt
 
 
@@ -423,7 +442,7 @@ def _deform_radius(X: torch.Tensor, mask: torch.Tensor):
     noise, offsets = _upload_noise(np.concatenate(chunks, axis=0), counts, X.device)
     centres_d = torch.from_numpy(centres).to(X.device, non_blocking=True)
     with torch.cuda.device(X.device):
-        _lib.call("mlsp_ball_mask_scatter", _ptr(X), B, C, N, ctypes.c_float(RADIUS ** 2), _ptr(centres_d),
+        _lib.call("mlsp_ball_mask_scatter", _ptr(X), *_strides(X), B, C, N, ctypes.c_float(RADIUS ** 2), _ptr(centres_d),
                   _ptr(noise), _ptr(offsets), _ptr(mask), _stream(X.device))
     return X, mask
 
@@ -431,10 +450,8 @@ def _deform_radius(X: torch.Tensor, mask: torch.Tensor):
 def collapse_to_point(x: torch.Tensor, device=None):
     """collapse_to_point(x, device): utils/pc_utils.py:76-111 for one cloud x (3,N): returns (x, indices)."""
     _require_cuda_f32(x, "collapse_to_point")
-    if not x.is_contiguous():
-        raise MlspError("collapse_to_point: x must be contiguous (it is modified in place)")
-    X = x.unsqueeze(0)
-    mask = torch.empty_like(X)
+    X = x.unsqueeze(0)                                                     # a view: x itself is modified, whatever its strides
+    mask = torch.empty(X.shape, dtype=torch.float32, device=X.device)
     _deform_radius(X, mask)
     return x, mask[0, 0].nonzero().squeeze()
 
@@ -492,6 +509,7 @@ def estimate_normals(xyz: torch.Tensor, near: int = 20, return_curvature: bool =
     elif idx.shape != (B, N, near) or idx.dtype != torch.int64 or idx.device != pts.device:
         raise MlspError("estimate_normals: idx must be int64 (B,N,near) on xyz's device")
     else:
+        _check_idx(idx, N, "estimate_normals")
         idx = idx.contiguous()
     normals = torch.empty((B, N, 3), dtype=torch.float32, device=pts.device)
     curv = torch.empty((B, N), dtype=torch.float32, device=pts.device) if return_curvature else None

@@ -313,6 +313,59 @@ def test_deform_input_full_size(dev, npo, mode):
     assert np.array_equal(_np(Xd)[m == 0], X0.numpy()[m == 0])          # untouched outside the mask
 
 
+def test_chamfer_non_finite_inputs_give_nan_not_a_fault(dev):
+    """A diverged step hands the loss NaN / Inf predictions: the reference returns a NaN loss; the kernels must do the
+    same and must not index outside the cloud in the backward."""
+    B, N = 3, 512
+    gold = synth.surface_clouds(B, N, 5).to(dev)
+    mask = torch.zeros(B, 3, N, device=dev)
+    mask[:, :, 100:160] = 1
+    for bad in (float("nan"), float("inf")):
+        pred = gold.permute(0, 2, 1).contiguous().clone()
+        pred[1, 120] = bad                                               # a masked row of one cloud
+        pred.requires_grad_(True)
+        loss = M.reconstruction_loss(pred, gold, mask)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert not torch.isfinite(loss)                                   # NaN (nan input) or inf (inf input), like torch
+        g = pred.grad
+        assert torch.isfinite(g[0]).all() and torch.isfinite(g[2]).all()   # other clouds unaffected
+        idx = M.findneareat_index(pred.detach(), gold.permute(0, 2, 1), mask.permute(0, 2, 1))
+        assert int(idx.min()) >= 0 and int(idx.max()) < N
+    allbad = torch.full((1, 64, 3), float("inf"), device=dev)
+    idx = M.findneareat_index(allbad, torch.zeros(1, 64, 3, device=dev), torch.ones(1, 64, 3, device=dev))
+    assert int(idx.min()) >= 0 and int(idx.max()) < 64
+
+
+@pytest.mark.parametrize("mode", ["volume_based_voxels", "volume_based_radius"])
+def test_deform_input_on_the_trainers_permuted_view(dev, npo, mode):
+    """The reference trainers call deform_input on `data.to(device).permute(0,2,1)` (PointDA/trainer.py:380-387,
+    PointSegDA/trainer.py:326-332): a (B,3,N) view with strides (3N,1,3).  It must be deformed in place, as is."""
+    X0 = synth.surface_clouds(6, 1024, 31)                              # (B,3,N) dense
+    data = X0.permute(0, 2, 1).contiguous().to(dev)                     # the loader's (B,N,3) batch
+    X = data.permute(0, 2, 1)                                           # what the trainer passes
+    assert not X.is_contiguous()
+    np.random.seed(9)
+    Xd, mask = M.deform_input(X, torch.tensor(M.region_mean(3), dtype=torch.float32), mode, dev)
+    assert Xd is X and mask.shape == X.shape
+    Xo = X0.numpy().copy()
+    np.random.seed(9)
+    Xo, mo = npo.deform_input(Xo, npo.region_mean(3), mode)
+    assert np.array_equal(_np(mask), mo)
+    assert np.array_equal(_np(Xd), Xo)
+    assert np.array_equal(_np(data), Xo.transpose(0, 2, 1))             # the underlying (B,N,3) batch was modified
+    # the loss consumes the strided tensors as they are (MLSP/mlsp.py:170-176)
+    pred = (X.permute(0, 2, 1) + 0.01).contiguous().requires_grad_(True)
+    loss = M.reconstruction_loss(pred, torch.from_numpy(X0.numpy()).to(dev), mask)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(pred.grad).all()
+    if mode == "volume_based_radius":
+        xb = data.permute(0, 2, 1)[0]                                   # one strided (3,N) cloud, as mlsp.py:34 passes it
+        np.random.seed(3)
+        out, ind = M.collapse_to_point(xb, dev)
+        assert out is xb and ind.numel() >= 20
+
+
 def test_ball_count_matches_oracle(dev, orc):
     x = synth.surface_clouds(8, 1024, 3)
     assert np.array_equal(_np(M.ball_count(x.to(dev))), orc.ball_count(x.numpy()))
