@@ -75,6 +75,14 @@ MLSP_API int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t *i
 MLSP_API int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
                                    float *dump, void *stream);
 
+/* Profiling hook for the tcgen05 path of a1: same result as mlsp_knn_f32; tstamp (B * ceil(N/128), 16) int64 receives, per
+ * CTA of the filter kernel, %globaltimer (ns) marks of its phases ([0] entry, [1] prologue done, [2] first accumulator
+ * ready, [3] pass 1 done, [4] class maxima sorted, [5] exchanged, [6] threshold ready, [7] pass 2 done, [8] lists complete,
+ * [9] lists copied out) and the SM id in [15].  cluster: CTAs per cluster sharing the candidate blocks by TMA multicast (1, 2, 4;
+ * 0 = the library's default).  tools/kt_timeline.py prints the phase breakdown. */
+MLSP_API int mlsp_knn_tensor_timeline(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
+                                      long long *tstamp, int cluster, void *stream);
+
 /* a2 -- get_graph_feature(x, args, k, idx): PointDA/model_utils.py:18-42 == PointSegDA/Models.py:18-45.
  *   out logical shape (B,2C,N,k) stored channels-last, i.e. memory order [B][N][k][2C]:
  *   out[b][i][j][c] = x[b][c][idx[b][i][j]] - x[b][c][i] (c < C),  x[b][c-C][i] (c >= C). */

@@ -21,6 +21,7 @@ _F = ctypes.c_float
 SIGNATURES = {
     "mlsp_knn_f32": [_P, _I, _I, _I, _I, _P, _P, _Z, _I, _P],
     "mlsp_knn_tensor_debug": [_P, _I, _I, _I, _I, _P, _P, _Z, _P, _P],
+    "mlsp_knn_tensor_timeline": [_P, _I, _I, _I, _I, _P, _P, _Z, _P, _I, _P],
     "mlsp_edge_gather_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P],
     "mlsp_graph_feature_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P],
     "mlsp_graph_feature_fwd_stage": [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _I, _P],

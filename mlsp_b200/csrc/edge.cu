@@ -27,7 +27,7 @@ bool knn3_supported(int C, int N, int k);
 int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, float *edge_out, cudaStream_t st);
 const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k);
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
-                   cudaStream_t st);
+                   int stages_mask, cudaStream_t st, long long *tstamp = nullptr, int cluster = 0);
 
 size_t graph_feature_workspace_bytes(int B, int C, int N, int k)
 {
@@ -392,8 +392,9 @@ extern "C" int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, i
 
 // get_graph_feature(x, args, k) with idx=None in one call: knn + edge gather.  On the tcgen05 path the point-major
 // copy of x that the kNN prep kernel leaves in the workspace is gathered from directly (no second transpose).
-extern "C" int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
-                                      size_t ws_bytes, void *stream)
+// stages: which kernels of the tcgen05 path run (7 = the whole op; see mlsp_graph_feature_fwd_stage)
+static int graph_feature_fwd_impl(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
+                                  size_t ws_bytes, int stages, void *stream)
 {
     using namespace mlsp;
     MLSP_REQUIRE(x && idx && out && ws, MLSP_EINVAL, "graph_feature_fwd: null pointer");
@@ -402,36 +403,30 @@ extern "C" int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k
     MLSP_REQUIRE(((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0 || C % 4 != 0, MLSP_EINVAL,
                  "graph_feature_fwd: out and ws must be 16-byte aligned");
     MLSP_REQUIRE(ws_bytes >= graph_feature_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "graph_feature_fwd: workspace too small");
-    if (knn_tensor_supported(B, C, N, k) && k <= 64) {
+    if (knn_tensor_supported(B, C, N, k))
         // tcgen05 path: the refine kernel that ranks a row also writes its edge features (no separate gather launch,
-        // idx is not read back).  MLSP_GGF_FUSED=0 (tuning hook) keeps the two-kernel form.
-        const bool fused = !(getenv("MLSP_GGF_FUSED") && atoi(getenv("MLSP_GGF_FUSED")) == 0);
-        int rc = knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, fused ? out : nullptr, as_stream(stream));
-        if (rc || fused) return rc;
-        return launch_edge_fwd_vec(knn_tensor_xt(ws, B, C, N, k), idx, B, C, N, k, out, as_stream(stream));
-    }
-    if (knn3_supported(C, N, k) && B <= 65535 && (reinterpret_cast<uintptr_t>(out) & 7) == 0) {
+        // idx is not read back)
+        return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, out, stages, as_stream(stream));
+    if (knn3_supported(C, N, k) && B <= 65535 && (reinterpret_cast<uintptr_t>(out) & 7) == 0)
         // 3-D clouds: the two-pass kernel that ranks a row also writes its k x 6 edge features from the staged cloud
-        const bool fused = !(getenv("MLSP_GGF_FUSED") && atoi(getenv("MLSP_GGF_FUSED")) == 0);
-        if (fused) return knn3_run(x, B, N, k, idx, static_cast<int *>(ws), out, as_stream(stream));
-    }
+        return knn3_run(x, B, N, k, idx, static_cast<int *>(ws), out, as_stream(stream));
     int rc = mlsp_knn_f32(x, B, C, N, k, idx, ws, ws_bytes, MLSP_KNN_AUTO, stream);
     if (rc) return rc;
     return mlsp_edge_gather_fwd(x, idx, B, C, N, k, out, ws, ws_bytes, stream);   // stream order: the kNN is done with ws
+}
+
+extern "C" int mlsp_graph_feature_fwd(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
+                                      size_t ws_bytes, void *stream)
+{
+    return graph_feature_fwd_impl(x, B, C, N, k, idx, out, ws, ws_bytes, 7, stream);
 }
 
 // Measurement hook: mlsp_graph_feature_fwd restricted to some of the kernels of the tcgen05 path (stages: bit 0 = prep,
 // bit 1 = tensor-core filter, bit 2 = ranking + fused edge gather).  Each kernel only reads what the earlier ones left
 // in `ws`, so after one full call on the same arguments any single stage can be re-run -- and timed -- alone.
 // Shapes that do not take the tcgen05 path run the whole op.
-namespace mlsp {
-extern thread_local int g_kt_stages;
-}
 extern "C" int mlsp_graph_feature_fwd_stage(const float *x, int B, int C, int N, int k, int64_t *idx, float *out, void *ws,
                                             size_t ws_bytes, int stages, void *stream)
 {
-    mlsp::g_kt_stages = stages & 7;
-    const int rc = mlsp_graph_feature_fwd(x, B, C, N, k, idx, out, ws, ws_bytes, stream);
-    mlsp::g_kt_stages = 7;
-    return rc;
+    return graph_feature_fwd_impl(x, B, C, N, k, idx, out, ws, ws_bytes, stages & 7, stream);
 }

@@ -20,8 +20,8 @@ constexpr size_t KNN_WS_HEADER = 256;                     // stats live in the f
 
 bool knn_tensor_supported(int B, int C, int N, int k);
 size_t knn_tensor_workspace_bytes(int B, int C, int N, int k);
-int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
-                   cudaStream_t st);
+int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out, int stages_mask,
+                   cudaStream_t st, long long *tstamp = nullptr, int cluster = 0);
 bool knn3_supported(int C, int N, int k);
 int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, float *edge_out, cudaStream_t st);
 
@@ -195,7 +195,7 @@ extern "C" int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t 
     const bool tensor_ok = knn_tensor_supported(B, C, N, k);
     MLSP_REQUIRE(flags != MLSP_KNN_TENSOR_ONLY || tensor_ok, MLSP_EUNSUPPORTED,
                  "knn: tensor path not available for B=%d C=%d N=%d k=%d", B, C, N, k);
-    if (tensor_ok && flags != MLSP_KNN_EXACT_ONLY) return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, nullptr, st);
+    if (tensor_ok && flags != MLSP_KNN_EXACT_ONLY) return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, nullptr, 7, st);
     if (flags != MLSP_KNN_EXACT_ONLY && knn3_supported(C, N, k)) return knn3_run(x, B, N, k, idx, static_cast<int *>(ws), nullptr, st);
     MLSP_CUDA(cudaMemsetAsync(ws, 0, KNN_WS_HEADER, st));
     float *xx = reinterpret_cast<float *>(static_cast<char *>(ws) + KNN_WS_HEADER);
@@ -205,6 +205,20 @@ extern "C" int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t 
 }
 
 // Test hook: the tensor path with a dump of the approximate filter values v = |x_j|^2 - 2 dot~ (B,N,N).
+// Profiling hook: the tensor path with phase marks of the filter kernel; tstamp (CTAs, 16) int64, CTA = b * ceil(N/128) + row block:
+// %globaltimer (ns) at [0] kernel entry, [1] prologue done, [2] first accumulator ready, [3] pass 1 done, [4] class maxima
+// sorted, [5] exchanged, [6] threshold ready, [7] pass 2 done, [8] lists complete, [9] lists copied out; [15] = SM id.
+extern "C" int mlsp_knn_tensor_timeline(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
+                                        long long *tstamp, int cluster, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(x && idx && ws && tstamp, MLSP_EINVAL, "knn_tensor_timeline: null pointer");
+    MLSP_REQUIRE(k >= 1 && k <= N, MLSP_EINVAL, "knn_tensor_timeline: k out of range");
+    MLSP_REQUIRE(knn_tensor_supported(B, C, N, k), MLSP_EUNSUPPORTED, "knn_tensor_timeline: shape not supported");
+    MLSP_REQUIRE(ws_bytes >= knn_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "knn_tensor_timeline: workspace too small");
+    return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, nullptr, 7, as_stream(stream), tstamp, cluster);
+}
+
 extern "C" int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, size_t ws_bytes,
                                      float *dump, void *stream)
 {
@@ -213,5 +227,5 @@ extern "C" int mlsp_knn_tensor_debug(const float *x, int B, int C, int N, int k,
     MLSP_REQUIRE(k >= 1 && k <= N, MLSP_EINVAL, "knn_tensor_debug: k out of range");
     MLSP_REQUIRE(knn_tensor_supported(B, C, N, k), MLSP_EUNSUPPORTED, "knn_tensor_debug: shape not supported");
     MLSP_REQUIRE(ws_bytes >= knn_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "knn_tensor_debug: workspace too small");
-    return knn_tensor_run(x, B, C, N, k, idx, ws, dump, nullptr, as_stream(stream));
+    return knn_tensor_run(x, B, C, N, k, idx, ws, dump, nullptr, 7, as_stream(stream));
 }

@@ -3,28 +3,28 @@
 // selection epilogue, and results that are STILL bit-exact with the fp32 specification of knn.cu.
 //
 // Filter (tensor cores) + refine (exact fp32) + certificate:
-//   1. prep: x (B,C,N) fp32 -> point-major fp32 rows xt (B,N,C) and an error-compensated bf16 split
-//      x = hi + lo (+ 2^-16 |x|).  The A operand [hi|lo] of the CTA's 128 query rows stays in shared memory; every
-//      candidate block B_hi is multiplied with A_hi and A_lo, every B_lo block with A_hi, all into one TMEM
-//      accumulator: dot~ = hi.hi + lo.hi + hi.lo, |dot~ - dot| <= ~1e-4 |x_i||x_j|, and each B byte is fetched once.
-//   2. main kernel, one CTA per 128 query rows, candidate tiles of 128 (UMMA 128x128x16, kind::f16):
-//        warp 0   : TMA producer (A tile once, B K-blocks through an mbarrier ring)
-//        warp 1   : TMEM allocator + single-thread MMA issuer, accumulators double-buffered in TMEM
-//        warps 2-9: epilogue, two threads per query row (tcgen05.ld 32x32b: TMEM lane == row)
-//      pass 1: v = |x_j|^2 - 2 dot~ ; per row the minimum of every column class (j mod NG) is tracked in
-//              registers; tau = k-th smallest class minimum is an upper bound of the k-th distance.
-//      pass 2: the same tiles again (the MMA is cheap); columns with v <= tau + 2 eps are written as (v, j) pairs
-//              to the row's candidate list in global memory (L2): the two threads of a row fill it from both ends
-//              with private cursors -- predicated stores, no atomics, no votes (about 1.2 k entries expected,
-//              capacity 2 NG).  eps bounds |v - exact| so every member of the exact top-k (ties included) is listed.
-//   3. refine kernel (one warp per row): sorts the list by the approximate value.  Two neighbours of that order
-//      whose values differ by more than 2 eps are provably in the same order in exact fp32 arithmetic, so only
+//   1. prep: x (B,C,N) fp32 -> point-major fp32 rows xt (B,N,C); the cloud is re-centred (y = x - c, c = mean of a strided
+//      sample of its points: distances are translation invariant, the filter's error bounds scale with |y_i||y_j|) and split
+//      into bf16 pieces y = hi + lo (+ 2^-18 |y|).  Per point also the column term t_j = |x_j|^2 - 2 c.y_j - |c|^2 (the
+//      specification's own norm, so its rounding cancels), stored as three bf16 pieces of -t_j/2.
+//   2. filter kernel, one CTA per 128 query rows (one CTA per SM), candidate tiles of 128 (UMMA 128x128x16, kind::f16):
+//        warp 0    : TMA producer (A = [hi|lo] of the rows once; per candidate block 16 KiB + the 2 KiB norm tile)
+//        warp 1    : TMEM allocator (all 512 columns = four accumulator buffers) + single-thread MMA issuer
+//        warps 2-17: epilogue, FOUR threads per query row (tcgen05.ld 32x32b.x32: TMEM lane == row, 32 columns each)
+//      Every tile starts with one extra K=16 MMA  ones(128x16) . norms(128x16)^T  that initialises the accumulator
+//      with -t_j/2, so the accumulator IS the ranking value: acc = y_i.y_j - t_j/2 = -(|x_j|^2 - 2 x_i.x_j)/2 + row const.
+//      pass 1 (hi.hi only): per thread the maximum of every column class in registers -- one FMNMX3 per TWO elements;
+//              tau = k-th largest class maximum of the row (thread-local sort + 4-way merge) bounds the k-th distance.
+//      pass 2 (hi.hi + lo.hi + hi.lo): columns with acc >= tau - slack are appended to the row's candidate list in
+//              SHARED memory (32-bit addresses): setp + lop3 + predicated st.shared + predicated add per element, the
+//              column index packed into the 5 low mantissa bits, the tile recovered from per-tile cursor snapshots.
+//              The lists are copied to global memory (L2) once at the end.
+//   3. refine kernel (one warp per row): decodes the list, sorts it by the approximate value.  Two neighbours of that
+//      order whose values differ by more than 2 eps are provably in the same order in exact fp32 arithmetic, so only
 //      runs of near-ties ("clusters") that start inside the first k positions need the exact value: for those the
 //      distance is recomputed with the pinned fp32 chain of the specification (four lanes per candidate, coalesced
-//      reads of the point-major rows) and the cluster is re-sorted by (value desc, index asc).  Typical rows need
-//      no or a few exact distances instead of one 4C-byte gather per candidate.
-//      A row whose list overflowed is not certified and goes to
-//      the exact streaming top-k (topk.cuh) in the same warp.
+//      reads of the point-major rows) and the cluster is re-sorted by (value desc, index asc).
+//      A row whose list overflowed is not certified and goes to the exact streaming top-k (topk.cuh) in the same warp.
 // SASS evidence: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA) -- profiles/.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -39,17 +39,28 @@ constexpr int KT_ROWS = 128;     // query rows per CTA   (UMMA M, TMEM lanes)
 constexpr int KT_COLS = 128;     // candidates per tile  (UMMA N, TMEM columns per accumulator buffer)
 constexpr int KT_KBLK = 64;      // bf16 per K block = one 128-byte swizzle span
 constexpr int KT_MAX_STAGES = 8;
-constexpr int KT_EPI_WARPS = 8;  // two per TMEM lane quadrant: each takes one 64-column half of every tile
-constexpr int KT_THREADS = 64 + 32 * KT_EPI_WARPS;
+constexpr int KT_TPR = 4;        // epilogue threads per query row: each owns a 32-column quarter of every tile
+constexpr int KT_EPI_WARPS = 4 * KT_TPR;
+constexpr int KT_EPI_THREADS = 32 * KT_EPI_WARPS;
+constexpr int KT_THREADS = 64 + KT_EPI_THREADS;
+constexpr int KT_NBUF = 4;       // accumulator buffers: 4 x 128 columns = the whole TMEM of the SM
 constexpr uint32_t KT_BLK_BYTES = KT_COLS * KT_KBLK * 2;  // 16 KiB per (128 x 64) bf16 block
-// |v - exact| <= KT_EPS_REL |x_i| max_j|x_j| :  dropped lo.lo and split residuals are <= 3*2^-16 |x_i||x_j| on the
-// dot product (Cauchy-Schwarz), i.e. 9.2e-5 on v; 2^-12 = 2.4e-4 leaves > 2.5x for the tensor core's fp32
-// accumulation and the specification's own roundings.  Measured worst case: 0.12 of this bound (tests).
+constexpr uint32_t KT_NB_BYTES = KT_COLS * 16;            // 2 KiB: one K-group (8 bf16) of the norm operand per candidate
+constexpr uint32_t KT_STAGE_BYTES = KT_BLK_BYTES + KT_NB_BYTES;
+constexpr int KT_MAX_TILES = 64; // snapshots in shared memory: N <= 8192
+// Error model of the filter value v~ = -2 acc against the specification value:
+//   |v~_ij - (row const_i) - (-spec_ij)| <= eps_ij = KT_EPS_REL |y_i||y_j| + KT_EPS_YY (|y_i|^2+|y_j|^2) + KT_RND(C) (|x_i|^2+|x_j|^2)
+// KT_EPS_REL: dropped lo.lo and split residuals 3*2^-16 on the dot product (Cauchy-Schwarz) = 9.2e-5 on v, the 5 mantissa
+//   bits given to the column index 2^-16, the tensor core's fp32 accumulation; 2^-12 = 2.4e-4 leaves > 2x.
+// KT_EPS_YY: rounding / packing of the column term (magnitude |y_j|^2/2 in the accumulator).
+// KT_RND(C) = (C/8 + 8) 2^-24: the specification's own roundings (8 fma chains of C/8 terms, the butterfly, two
+//   subtractions), which act on the UNCENTRED norms.
 constexpr float KT_EPS_REL = 2.44140625e-4f;
-// Pass 1 multiplies the bf16 heads only (dot~1 = hi.hi): x = hi + r with |r_c| <= 2^-9 |x_c|, so
-// |hi_i.hi_j - x_i.x_j| <= (2^-8 + 2^-17 + 2^-18) |x_i||x_j| and the pass-1 value v1 = |x_j|^2 - 2 dot~1 is within
-// KT_EPS1_REL |x_i||x_j| (= 2^-7 + 2^-14) of the three-term value; tau1 + eps1 still upper-bounds the k-th distance.
+constexpr float KT_EPS_YY = 3.0517578125e-5f;             // 2^-15
+// Pass 1 multiplies the bf16 heads only (dot~1 = hi.hi): y = hi + r with |r_c| <= 2^-9 |y_c|, so the pass-1 value is
+// within KT_EPS1_REL |y_i||y_j| (= 2^-7 + 2^-14) of the pass-2 value; tau1 + eps1 still upper-bounds the k-th distance.
 constexpr float KT_EPS1_REL = 0.00787353515625f;
+__host__ __device__ __forceinline__ float kt_rnd(int C) { return (float)(C / 8 + 8) * 5.9604644775390625e-8f; }
 
 // ---------------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -98,6 +109,17 @@ __device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// shared -> global bulk copy by the TMA engine (one thread), and the wait that makes the source reusable
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
     uint32_t r;
@@ -108,20 +130,29 @@ __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// the same arrive, delivered to the mbarrier at this offset in every CTA of `mask` (a stage shared by a CTA pair is
-// free only when both CTAs' MMAs have read it)
+// the same arrive, delivered to the mbarrier at this offset in every CTA of `mask` (a stage shared by a cluster is free
+// only when every CTA's MMAs have read it)
 __device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                      smem_u32(bar)),
                  "h"(mask)
                  : "memory");
+}
+// One lane of a converged warp (warp-uniform predicate: code under it keeps its operands in uniform registers -- under a
+// plain `lane == 0` test the compiler wraps every tcgen05.mma / TMA instruction in an R2UR waterfall loop of ~20
+// instructions, which made the single issuing thread the bottleneck of the whole kernel)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
@@ -134,9 +165,10 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&r)[32])
+// asynchronous 32-column load: the registers are valid only after tc_wait32 on the same array (the "+r" operands
+// make every later use of the values depend on the wait, so the compiler cannot hoist them above it)
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&u)[32])
 {
-    uint32_t u[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -145,108 +177,114 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&r)[32])
           "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
           "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&r)[16])
-{
-    uint32_t u[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
-}
-// asynchronous 16-column load: the registers are valid only after tc_wait16 on the same array (the "+r"
-// operands make every later use of the values depend on the wait, so the compiler cannot hoist them above it)
-__device__ __forceinline__ void tc_ld16_issue(uint32_t taddr, uint32_t (&u)[16])
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait16(uint32_t (&u)[16])
+__device__ __forceinline__ void tc_wait32(uint32_t (&u)[32])
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]),
-                   "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15])
+                   "+r"(u[8]), "+r"(u[9]), "+r"(u[10]), "+r"(u[11]), "+r"(u[12]), "+r"(u[13]), "+r"(u[14]), "+r"(u[15]),
+                   "+r"(u[16]), "+r"(u[17]), "+r"(u[18]), "+r"(u[19]), "+r"(u[20]), "+r"(u[21]), "+r"(u[22]), "+r"(u[23]),
+                   "+r"(u[24]), "+r"(u[25]), "+r"(u[26]), "+r"(u[27]), "+r"(u[28]), "+r"(u[29]), "+r"(u[30]), "+r"(u[31])
                  :
                  : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * KT_EPI_WARPS) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(KT_EPI_THREADS) : "memory"); }
+// MMA warp + epilogue warps (everything but the TMA producer, which is already streaming)
+__device__ __forceinline__ void setup_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(KT_EPI_THREADS + 32) : "memory"); }
 
 // K-major, 128-byte swizzled operand block (rows 128 B apart, 8-row groups 1024 B apart), sm_100 version bit
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
 {
     return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major operand without swizzle: 8-row x 16-byte core matrices, `sbo` bytes between 8-row groups, `lbo` bytes between
+// the two K groups of one K = 16 instruction
+__device__ __forceinline__ uint64_t umma_desc_plain(uint32_t saddr, uint32_t lbo, uint32_t sbo)
+{
+    return (uint64_t)((saddr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
 // kind::f16: D = f32, A = B = bf16, both K-major, N = 128, M = 128
 constexpr uint32_t KT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((KT_COLS >> 3) << 17) | ((KT_ROWS >> 4) << 24);
 
+// ------------------------------------------------------------------------------------------- centre kernel
+// c (B,C) = mean of KT_CEN_SAMPLES points of every cloud, taken at a fixed stride over the cloud (a representative
+// sample whatever the point order).  Any c works for correctness -- distances are translation invariant -- a c inside
+// the cloud makes |y| = |x - c| comparable to the cloud's spread, which is what the filter's error bounds scale with.
+constexpr int KT_CEN_SAMPLES = 64;
+
+__global__ void __launch_bounds__(256)
+knn_centre_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ cen)
+{
+    __shared__ float part[256];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int parts = 256 / C;                             // 2 (C = 128) or 4 (C = 64)
+    const int c = t % C, pr = t / C;
+    const int stride = N / KT_CEN_SAMPLES;                 // N >= 256
+    const float *row = x + ((size_t)b * C + c) * N;
+    float s = 0.0f;
+    for (int q = pr; q < KT_CEN_SAMPLES; q += parts) s = __fadd_rn(s, row[(size_t)q * stride]);
+    part[t] = s;
+    __syncthreads();
+    if (pr == 0) {
+        for (int q = 1; q < parts; ++q) s = __fadd_rn(s, part[q * C + c]);
+        cen[(size_t)b * C + c] = __fmul_rn(s, 1.0f / KT_CEN_SAMPLES);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- prep kernel
-// One pass over x (B,C,N): exact norms in the specification order (sequential adds over the channels), the
-// point-major fp32 rows xt (B,N,C) and the bf16 split hi/lo (B*N, C); also zeroes the two diagnostic counters.  A CTA stages a [C][PREP_PTS] slab in shared memory
-// (coalesced 128-byte reads along n), then warps write whole point rows (coalesced along c).
+// One pass over x (B,C,N).  Per cloud the centre c comes from knn_centre_kernel.  Per point: the exact norm xx in the specification order (sequential adds over the channels), the
+// centred norm yy = |y|^2 (error bounds), the row shift ss = 2 c.y + |c|^2 and the column term t = xx - ss (fp64, one
+// rounding) whose half, negated, goes into the norm operand nb as three bf16 pieces; the point-major fp32 rows xt
+// (B,N,C) of the UNCENTRED cloud (exact re-rank, edge gather) and the bf16 split hi/lo (B*N, C) of y.
+// A CTA stages a [C][PREP_PTS] slab in shared memory (coalesced 128-byte reads along n), then warps write whole point
+// rows (coalesced along c).  Also zeroes the two diagnostic counters.
 constexpr int PREP_PTS = 32;
 constexpr int PREP_THREADS = 256;
 
 __global__ void __launch_bounds__(PREP_THREADS)
-knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ xx, int *__restrict__ counters,
-                float *__restrict__ xt, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo,
-                int *__restrict__ cloud_mode)
+knn_prep_kernel(const float *__restrict__ x, const float *__restrict__ cen, int C, int N, float *__restrict__ xx, float *__restrict__ yy,
+                float *__restrict__ ss, int *__restrict__ counters, float *__restrict__ xt,
+                __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, uint4 *__restrict__ nb)
 {
-    __shared__ float mode_acc[2];
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) counters[threadIdx.x] = 0;
-    if (threadIdx.x < 2) mode_acc[threadIdx.x] = 0.0f;
-    extern __shared__ float slab[];                       // [C][PREP_PTS + 1]
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
+    extern __shared__ float slab[];                       // [C][PREP_PTS + 1] | cvec [C]
+    float *cvec = slab + C * (PREP_PTS + 1);
     const int b = blockIdx.y, n0 = blockIdx.x * PREP_PTS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *xb = x + (size_t)b * C * N;
+    if ((int)threadIdx.x < C) cvec[threadIdx.x] = cen[(size_t)b * C + threadIdx.x];
     for (int c = warp; c < C; c += PREP_THREADS / 32) {
         const int n = n0 + lane;
         slab[c * (PREP_PTS + 1) + lane] = (n < N) ? xb[(size_t)c * N + n] : 0.0f;
     }
     __syncthreads();
-    if (warp == 0) {                                       // norms: one point per lane, channels in order
-        float v = slab[lane];
-        float s = __fmul_rn(v, v);
-        for (int c = 1; c < C; ++c) {
-            v = slab[c * (PREP_PTS + 1) + lane];
-            s = __fadd_rn(s, __fmul_rn(v, v));
+    if (warp == 0) {                                       // one point per lane, channels in order
+        float s = 0.0f, q = 0.0f;
+        double cy = 0.0, cc = 0.0;
+        for (int c = 0; c < C; ++c) {
+            const float v = slab[c * (PREP_PTS + 1) + lane], cv = cvec[c];
+            const float y = __fsub_rn(v, cv);
+            s = (c == 0) ? __fmul_rn(v, v) : __fadd_rn(s, __fmul_rn(v, v));
+            q = __fmaf_rn(y, y, q);
+            cy += (double)cv * (double)y;
+            cc += (double)cv * (double)cv;
         }
         const int n = n0 + lane;
-        if (n < N) xx[(size_t)b * N + n] = s;
-    }
-    // Which pass 1 for this cloud?  The bf16-head product is within KT_EPS1_REL |x_i||x_j| of the distance: fine for
-    // activations whose spread is comparable to their norm (BatchNorm + LeakyReLU outputs: E|x|^2 ~ 1.3-3 x the variance),
-    // hopeless for a tight cluster far from the origin (BatchNorm-free layers with a bias: the bound exceeds the k-th
-    // distance, every list overflows and the rows fall back to the exact streaming selection, 50x slower).  The first
-    // CTA of a cloud estimates E|x|^2 and the total variance from its 32 staged points and flags the cloud for the
-    // three-term pass 1 (error KT_EPS_REL, 32x tighter, 13 % more filter time) when E|x|^2 > 4 Var.  Either choice is
-    // certified; the flag only picks the cheaper one that works.
-    if (blockIdx.x == 0) {
-        const int np = min(PREP_PTS, N - n0);
-        if ((int)threadIdx.x < C) {
-            float sm = 0.0f, sq = 0.0f;
-            for (int pt = 0; pt < np; ++pt) {
-                const float v = slab[threadIdx.x * (PREP_PTS + 1) + pt];
-                sm += v;
-                sq = fmaf(v, v, sq);
-            }
-            const float m2 = sq / (float)np, mu = sm / (float)np;
-            atomicAdd(&mode_acc[0], m2);                      // E|x|^2 summed over channels
-            atomicAdd(&mode_acc[1], fmaxf(m2 - mu * mu, 0.0f));   // total variance
+        if (n < N) {
+            const double shift = 2.0 * cy + cc;
+            const float t = (float)((double)s - shift);
+            const float hneg = -0.5f * t;
+            const __nv_bfloat16 h1 = __float2bfloat16_rn(hneg);
+            const float r1 = hneg - __bfloat162float(h1);
+            const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 h3 = __float2bfloat16_rn(r1 - __bfloat162float(h2));
+            const size_t o = (size_t)b * N + n;
+            xx[o] = s;
+            yy[o] = q;
+            ss[o] = (float)shift;
+            nb[o] = make_uint4((uint32_t)__bfloat16_as_ushort(h1) | ((uint32_t)__bfloat16_as_ushort(h2) << 16),
+                               (uint32_t)__bfloat16_as_ushort(h3), 0u, 0u);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) cloud_mode[b] = (mode_acc[0] > 4.0f * mode_acc[1]) ? 1 : 0;
     }
     // rows: thread t handles channel pair (2t mod C ...) of point rows; consecutive threads -> consecutive channels
     const int pairs = C / 2;                               // C is even (64 or 128)
@@ -257,11 +295,12 @@ knn_prep_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ x
         const float v0 = slab[c * (PREP_PTS + 1) + pt], v1 = slab[(c + 1) * (PREP_PTS + 1) + pt];
         const size_t o = ((size_t)b * N + n) * C + c;
         *reinterpret_cast<float2 *>(xt + o) = make_float2(v0, v1);
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        const float y0 = __fsub_rn(v0, cvec[c]), y1 = __fsub_rn(v1, cvec[c + 1]);
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
         __nv_bfloat162 hv, lv;
         hv.x = h0; hv.y = h1;
-        lv.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-        lv.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+        lv.x = __float2bfloat16_rn(y0 - __bfloat162float(h0));
+        lv.y = __float2bfloat16_rn(y1 - __bfloat162float(h1));
         *reinterpret_cast<__nv_bfloat162 *>(hi + o) = hv;
         *reinterpret_cast<__nv_bfloat162 *>(lo + o) = lv;
     }
@@ -291,9 +330,9 @@ __device__ __forceinline__ float exact_pd(const float4 *__restrict__ xi, const f
     return __fsub_rn(__fmaf_rn(2.0f, dot, -xxj), xxi);
 }
 
-// thread-local bitonic sort of NG registers, ascending
+// thread-local bitonic sort of NG registers, DESCENDING
 template <int NG>
-__device__ __forceinline__ void reg_sort(float (&v)[NG])
+__device__ __forceinline__ void reg_sort_desc(float (&v)[NG])
 {
 #pragma unroll
     for (int size = 2; size <= NG; size <<= 1) {
@@ -303,363 +342,457 @@ __device__ __forceinline__ void reg_sort(float (&v)[NG])
             for (int e = 0; e < NG; ++e) {
                 const int p = e ^ stride;
                 if (p > e) {
-                    const bool up = (e & size) == 0;
+                    const bool down = (e & size) == 0;
                     const float a = v[e], b = v[p];
                     const float mn = fminf(a, b), mx = fmaxf(a, b);
-                    v[e] = up ? mn : mx;
-                    v[p] = up ? mx : mn;
+                    v[e] = down ? mx : mn;
+                    v[p] = down ? mn : mx;
                 }
             }
         }
     }
 }
 
-// per-pair error bound of the filter value: |v~_ij - exact_ij| <= KT_EPS_REL |x_i||x_j| + 2^-21 (|x_i|^2 + |x_j|^2)
-// (Cauchy-Schwarz on the dropped split terms and the accumulation, plus the specification's own roundings)
-__device__ __forceinline__ float pair_eps(float ni, float xxi, float xxj)
+// in-register bitonic merge: v is bitonic (descending then ascending) on entry, sorted descending on exit
+template <int L>
+__device__ __forceinline__ void bitonic_merge_desc(float (&v)[L])
 {
-    return __fmaf_rn(KT_EPS_REL * ni, sqrtf(xxj), 4.76837158203125e-7f * (xxi + xxj));
-}
-
-// ---- epilogue pieces ---------------------------------------------------------------------------------
-// pass-2 cursor of one thread: its end of the row's global candidate list
-struct Cursor {
-    uint2 *base;             // the thread's end of the row's list
-    int step;                // +1 (columns 0..63 of every tile: from the front) or -1 (columns 64..127: from the back)
-    int off;                 // step * (entries written so far)
-    bool ovf;
-};
-
-// one 16-column piece of one query row: v = |x_j|^2 - 2 dot~
-//   PASS 1: class minima (class = column within the thread's 64-column half, mod NG)
-//   PASS 2: every column with v <= thr is stored as (v, j) at the cursor -- predicated, branch-free
-template <int NG, int PASS>
-__device__ __forceinline__ void epi_piece(float (&gmin)[NG], Cursor &cur, const uint32_t (&u)[16], const float4 *nrm4,
-                                          int ch, float thr, uint32_t jcol)
-{
-    if (PASS == 2) {
-        // a piece can add 16 entries: without room for them nothing is stored any more and the row is flagged
-        const bool room = abs(cur.off) <= 2 * NG - 16;
-        cur.ovf |= !room;
-        thr = room ? thr : -INFINITY;
-    }
 #pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-        const float4 nj = nrm4[ch * 4 + c4];
-        const float nv[4] = {nj.x, nj.y, nj.z, nj.w};
+    for (int stride = L / 2; stride > 0; stride >>= 1) {
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const int c = 4 * c4 + w;
-            const float v = __fmaf_rn(-2.0f, __uint_as_float(u[c]), nv[w]);
-            if (PASS == 1) {
-                const int e = (ch * 16 + c) % NG;
-                gmin[e] = fminf(gmin[e], v);
-            } else {
-                // if (v <= thr) { list[off] = (v, j); off += step; }: one predicated store + one predicated add, no branch
-                uint2 *a = cur.base + cur.off;
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "setp.le.f32 p, %1, %2;\n\t"
-                    "@p st.global.v2.b32 [%3], {%4, %5};\n\t"
-                    "@p add.s32 %0, %0, %6;\n\t}"
-                    : "+r"(cur.off)
-                    : "f"(v), "f"(thr), "l"(a), "r"(__float_as_uint(v)), "r"(jcol + (uint32_t)c), "r"(cur.step));
+        for (int e = 0; e < L; ++e) {
+            if ((e & stride) == 0) {
+                const float a = v[e], b = v[e + stride];
+                v[e] = fmaxf(a, b);
+                v[e + stride] = fminf(a, b);
             }
         }
     }
 }
 
-// one thread, one query row, 64 columns in four pieces (tcgen05.ld 32x32b.x16), the load of piece p+1 in flight
-// while piece p is processed
-template <int NG, int PASS>
-__device__ __forceinline__ void epi_tile(float (&gmin)[NG], Cursor &cur, uint32_t taddr, const float *nrm, float thr,
-                                         uint32_t jbase)
+// per-pair error bound of the filter value against the specification value (constants above)
+__device__ __forceinline__ float pair_eps(float yyi, float yyj, float xxi, float xxj, int C)
 {
-    const float4 *nrm4 = reinterpret_cast<const float4 *>(nrm);
-    uint32_t ua[16], ub[16];
-    tc_ld16_issue(taddr, ua);
-    tc_wait16(ua);
-    tc_ld16_issue(taddr + 16, ub);
-    epi_piece<NG, PASS>(gmin, cur, ua, nrm4, 0, thr, jbase);
-    tc_wait16(ub);
-    tc_ld16_issue(taddr + 32, ua);
-    epi_piece<NG, PASS>(gmin, cur, ub, nrm4, 1, thr, jbase + 16);
-    tc_wait16(ua);
-    tc_ld16_issue(taddr + 48, ub);
-    epi_piece<NG, PASS>(gmin, cur, ua, nrm4, 2, thr, jbase + 32);
-    tc_wait16(ub);
-    epi_piece<NG, PASS>(gmin, cur, ub, nrm4, 3, thr, jbase + 48);
+    return __fmaf_rn(KT_EPS_REL * sqrtf(yyi), sqrtf(yyj), __fmaf_rn(KT_EPS_YY, yyi + yyj, kt_rnd(C) * (xxi + xxj)));
 }
 
-// test hook: write the approximate values of this thread's 64 columns
-// (tcgen05.ld is .sync.aligned: the whole warp must execute it, so row validity only predicates the stores)
-__device__ __noinline__ void dump_tile(float *row_out, bool row_valid, uint32_t taddr, const float *nrm, int jbase, int N)
+// pass 2, one element: if (acc >= t) { *cur = (acc & ~31) | column; cur += step; } -- setp, lop3 (column as the immediate),
+// one predicated st.shared and one predicated add on a 32-bit shared-memory address; no branch, no vote, no atomics
+template <int COL>
+__device__ __forceinline__ void collect_tile(uint32_t &cur, const uint32_t (&u)[32], float t, int step, uint32_t keep)
 {
-    for (int ch = 0; ch < 2; ++ch) {
-        float acc[32];
-        tc_ld32(taddr + ch * 32, acc);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const int j = jbase + ch * 32 + c;
-            if (row_valid && j < N) row_out[j] = __fmaf_rn(-2.0f, acc[c], nrm[ch * 32 + c]);
-        }
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 w;\n\t"
+        "setp.ge.f32 p, %1, %2;\n\t"
+        "lop3.b32 w, %3, %6, %4, 0xEA;\n\t"
+        "@p st.shared.b32 [%0], w;\n\t"
+        "@p add.s32 %0, %0, %5;\n\t}"
+        : "+r"(cur)
+        : "f"(__uint_as_float(u[COL])), "f"(t), "r"(u[COL]), "n"(COL), "r"(step), "r"(keep)
+        : "memory");
+    if constexpr (COL + 1 < 32) collect_tile<COL + 1>(cur, u, t, step, keep);
 }
 
 struct KtParams {
-    const float *xx;         // (B,N) exact squared norms
+    const float *xx;         // (B,N) exact squared norms (specification order)
+    const float *yy;         // (B,N) squared norms of the centred points
+    const float *ss;         // (B,N) row shift 2 c.y_i + |c|^2 (only the test dump needs it)
     const float *xt;         // (B,N,C) fp32 point-major
     int64_t *idx;            // (B,N,k)
     int *fb_count;           // rows whose list overflowed (re-done with the exact streaming selection)
     int *stats;              // rows certified by the tensor path
-    uint2 *cand;             // (B*N, CAP) candidate lists (v bits, j): main kernel -> refine kernel
-    int *cand_cnt;           // (B*N, 2) entries written from the front / from the back (> CAP: overflowed)
+    uint32_t *cand;          // (B*N, capw) packed candidate words: filter value with the column (mod 32) in its 5 low bits
+    uint8_t *cand_cnt;       // (B*N, 4) entries written by each column quarter; 255: overflowed
+    uint8_t *snap;           // (B*N, 4, TP) cursor of each quarter after every candidate tile (padding 255)
     float *dump;             // optional (2,B,N,N) filter values of pass 1 and pass 2 (tests only)
+    long long *tstamp;       // optional (CTAs, 16) clock64 / globaltimer marks of the filter kernel's phases (tools/kt_timeline.py)
     float4 *edge_out;        // optional (B,N,k,2C): the refine kernel also writes the row's edge features (a2 fused)
     int N, C, k, T;          // T = candidate tiles per cloud
+    int TP;                  // T rounded up to a multiple of 8
     int stages;              // depth of the B-operand smem ring
-    int pair;                // launched in clusters of two CTAs sharing the candidate blocks by TMA multicast
-    const int *cloud_mode;   // (B) written by the prep kernel: 1 = this cloud's pass 1 uses the three-term product (below)
-    int mode;                // tuning hook (MLSP_KT_MODE): bit 0 skips the pass-1 math, bit 1 the pass-2 math, bit 2: three-term pass 1
-                             // for every cloud, bit 3: bf16-head pass 1 for every cloud (ignore cloud_mode)
+    int capw;                // list words per row: 128 (k <= 32) or 192
+    int cs;                  // CTAs per cluster (1, 2 or 4 adjacent row blocks of a cloud) sharing every candidate block by TMA multicast
 };
 
-// ------------------------------------------------------------------------------------------- main kernel
-// shared memory: A (2*SEG blocks) | B ring (STAGES blocks) | xchg [min(k,NG)][128] | nrm [2][128] | thr [128] | max [4] | barriers
-__host__ __device__ inline size_t kt_smem_bytes(int C, int k, int NG, int stages)
+// ------------------------------------------------------------------------------------------- filter kernel
+// shared memory: A (2*SEG blocks) | ring (STAGES x (16 KiB block + 2 KiB norm tile)) | ones (4 KiB) |
+//                lists [128][capw] (aliased: sorted class maxima [4][KX][128]) | snapshots [T][512] | thr [128] | red [32] | barriers
+__host__ __device__ inline size_t kt_smem_bytes(int C, int k, int T, int stages)
 {
-    const int kx = k < NG ? k : NG;
-    return (size_t)(2 * C / KT_KBLK + stages) * KT_BLK_BYTES + (size_t)kx * KT_ROWS * 4 + 2 * KT_COLS * 4 + KT_ROWS * 4 + 16 +
-           32 * 8 + 16 + 1024;
+    const int capw = k <= 32 ? 128 : 192;
+    return (size_t)(2 * C / KT_KBLK) * KT_BLK_BYTES + (size_t)stages * KT_STAGE_BYTES + 4096 + (size_t)KT_ROWS * capw * 4 +
+           (size_t)T * KT_EPI_THREADS + KT_ROWS * 4 + 32 * 4 + 32 * 8 + 16 + 1024;
 }
 
-template <int NG>
-__global__ void __launch_bounds__(KT_THREADS, (NG == 32) ? 2 : 1)   // NG = 32: two CTAs per SM (one wave at 32 x 1024), <= 102 registers
-knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                  const __grid_constant__ CUtensorMap half_hi, const __grid_constant__ CUtensorMap half_lo, KtParams P)
+__device__ __forceinline__ void kt_mark(const KtParams &P, int slot)
 {
-    // P.pair: the kernel was launched in clusters of two CTAs = two adjacent row blocks of one cloud.  Both stream the
-    // same candidate blocks, so each CTA fetches HALF of every block (64 of its 128 rows) and TMA multicasts it into
-    // both shared memories: the L2 -> SM operand traffic, which bounds the MMA pipeline, halves.
-    const bool pair = P.pair != 0;
-    const uint32_t crank = pair ? cluster_ctarank() : 0u;
-    constexpr int CAP = 2 * NG;
+    if (P.tstamp) {
+        long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        P.tstamp[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = g;
+    }
+}
+
+template <int NGT>                                        // column classes per thread: 16 (k <= 32) or 32 (k <= 64)
+__global__ void __launch_bounds__(KT_THREADS, 1)
+knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                  const __grid_constant__ CUtensorMap part_hi, const __grid_constant__ CUtensorMap part_lo,
+                  const __grid_constant__ CUtensorMap map_nb, KtParams P)
+{
+    // P.cs > 1: the kernel was launched in clusters of P.cs CTAs = adjacent row blocks of one cloud.  They stream the same
+    // candidate blocks, so each CTA fetches 1/cs of every block (and of the norm tile) and TMA multicasts it into all of
+    // their shared memories: the per-SM TMA issue and the L2 -> SM operand traffic, which bound the MMA pipeline at these
+    // arithmetic intensities (2 x 128 MACs per operand byte), shrink by cs.
+    const int CS = P.cs;
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms need 1 KiB alignment
     const int SEG = P.C / KT_KBLK;          // K blocks per hi / lo segment (1 or 2)
-    const int KB = 2 * SEG;                 // B blocks streamed per tile: hi blocks, then lo blocks
+    const int KB = 2 * SEG;                 // B blocks streamed per pass-2 tile: hi blocks, then lo blocks
     const int STAGES = P.stages;
-    const int KX = min(P.k, NG);
+    const int CAPW = P.capw, HC = CAPW / 2;
+    const int KX = min(P.k, NGT);
     uint8_t *sA = smem_raw;                                   // [hi blocks | lo blocks], resident
-    uint8_t *sB = sA + (size_t)KB * KT_BLK_BYTES;             // STAGES blocks, ring
-    float *xchg = reinterpret_cast<float *>(sB + (size_t)STAGES * KT_BLK_BYTES);   // [KX][128] sorted class minima of the upper half
-    float *nrm_s = xchg + (size_t)KX * KT_ROWS;                                     // [2][128]
-    float *thr_s = nrm_s + 2 * KT_COLS;                                             // [128]
-    uint32_t *max_s = reinterpret_cast<uint32_t *>(thr_s + KT_ROWS);                // [4] per-warp maxima of the cloud's norms
-    uint64_t *bars = reinterpret_cast<uint64_t *>(max_s + 4);
+    uint8_t *sB = sA + (size_t)KB * KT_BLK_BYTES;             // ring: STAGES x (block | norm tile)
+    uint8_t *sOnes = sB + (size_t)STAGES * KT_STAGE_BYTES;    // [K group 0: rows of (1,1,1,0,...) | K group 1: zeros]
+    uint32_t *lists = reinterpret_cast<uint32_t *>(sOnes + 4096);
+    float *xchg = reinterpret_cast<float *>(lists);           // between the passes only
+    uint8_t *snap_s = reinterpret_cast<uint8_t *>(lists + (size_t)KT_ROWS * CAPW);
+    float *thr_s = reinterpret_cast<float *>(snap_s + (((size_t)P.T * KT_EPI_THREADS + 15) & ~(size_t)15));
+    float *red_s = thr_s + KT_ROWS;                           // [16] per-warp max |x|^2, [16] per-warp max |y|^2
+    uint64_t *bars = reinterpret_cast<uint64_t *>(red_s + 32);
     uint64_t *full = bars, *empty = bars + KT_MAX_STAGES, *a_full = bars + 2 * KT_MAX_STAGES;
-    uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
+    uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + KT_NBUF;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + KT_NBUF);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, i0 = blockIdx.x * KT_ROWS;
     const int N = P.N, T = P.T;
     const int rowbase = b * N;
-    // pass 1 on the three-term product (as tight as pass 2) instead of the bf16 heads: forced by the tuning hook, or
-    // chosen per cloud by the prep kernel for activations far from the origin (uniform over the CTA and its pair)
-    const bool three = (P.mode & 4) || (!(P.mode & 8) && P.cloud_mode[b] != 0);
+    if (threadIdx.x == 64) {
+        kt_mark(P, 0);
+        if (P.tstamp) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.tstamp[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 15] = smid;
+        }
+    }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < KT_MAX_STAGES; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, pair ? 2 : 1);                   // pair: one commit-arrive from each CTA's MMA issuer
+            mbar_init(empty + s, (uint32_t)CS);                   // one commit-arrive from every CTA of the cluster
         }
         mbar_init(a_full, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < KT_NBUF; ++s) {
             mbar_init(tm_full + s, 1);
             mbar_init(tm_empty + s, KT_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tma_prefetch_desc(&map_hi);
+        tma_prefetch_desc(&map_lo);
+        tma_prefetch_desc(CS > 1 ? &part_hi : &map_nb);
     }
+    if (CS > 1) cluster_sync_all();                                 // the peers' barriers exist before anything signals them
+    else __syncthreads();
+    // From here the TMA producer streams; the MMA warp allocates TMEM and the epilogue warps build the constant operand
+    // and reduce the cloud's norms meanwhile; those 17 warps meet at setup_bar_sync.
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        tc_fence_before();
+        setup_bar_sync();
+        tc_fence_after();
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (pair) cluster_sync_all();                                   // the peer's barriers exist before anything signals them
-    const uint32_t tmem_base = *tmem_slot;
+    float xxi = 0.0f, yyi = 0.0f;                                   // epilogue threads: the norms of their row
+    if (warp >= 2) {
+        const int et = threadIdx.x - 64;
+        const int ii = i0 + ((warp & 3) * 32 + lane);
+        if (ii < N) {
+            xxi = P.xx[(size_t)rowbase + ii];
+            yyi = P.yy[(size_t)rowbase + ii];
+        }
+        if (et < 256) {                                       // the constant A operand of the norm MMA
+            const uint4 one = make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u);   // bf16 (1, 1, 1, 0, 0, 0, 0, 0)
+            reinterpret_cast<uint4 *>(sOnes)[et] = (et < KT_ROWS) ? one : make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core's reads
+        }
+        // maxima of the cloud's norms: the row-level error bounds of the threshold
+        float mx = 0.0f, my = 0.0f;
+        for (int j = et; j < N; j += KT_EPI_THREADS) {
+            mx = fmaxf(mx, P.xx[(size_t)rowbase + j]);
+            my = fmaxf(my, P.yy[(size_t)rowbase + j]);
+        }
+        mx = warp_max_f32(mx);
+        my = warp_max_f32(my);
+        if (lane == 0) {
+            red_s[warp - 2] = mx;
+            red_s[16 + warp - 2] = my;
+        }
+        tc_fence_before();
+        setup_bar_sync();
+        tc_fence_after();
+    }
+    const uint32_t tmem_base = (warp >= 1) ? *tmem_slot : 0u;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        // the whole warp runs the loop (waits included); one elected lane issues
+        if (elect_one()) {
             mbar_expect_tx(a_full, (uint32_t)KB * KT_BLK_BYTES);
             for (int kb = 0; kb < KB; ++kb)          // A = [hi | lo]
                 tma_load_2d(sA + (size_t)kb * KT_BLK_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
                             rowbase + i0, a_full);
-            int stage = 0;
-            uint32_t ph = 0;
-            for (int g = 0; g < 2 * T; ++g) {
-                const int j0 = (g % T) * KT_COLS;
-                const int nkb = (g < T && !three) ? SEG : KB;          // pass 1 multiplies hi.hi only: no lo blocks
-                for (int kb = 0; kb < nkb; ++kb) {   // B blocks: hi ..., lo ...
-                    mbar_wait(empty + stage, ph ^ 1);
-                    mbar_expect_tx(full + stage, KT_BLK_BYTES);
-                    if (pair)                                       // my half of the block, into both CTAs
-                        tma_load_2d_mc(sB + (size_t)stage * KT_BLK_BYTES + (size_t)crank * (KT_BLK_BYTES / 2),
-                                       kb < SEG ? &half_hi : &half_lo, (kb % SEG) * KT_KBLK,
-                                       rowbase + j0 + (int)crank * (KT_COLS / 2), full + stage, (uint16_t)3);
-                    else
-                        tma_load_2d(sB + (size_t)stage * KT_BLK_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
-                                    rowbase + j0, full + stage);
-                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
+        }
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int g = 0; g < 2 * T; ++g) {
+            const int j0 = (g % T) * KT_COLS;
+            const int nkb = (g < T) ? SEG : KB;                 // pass 1 multiplies hi.hi only: no lo blocks
+            for (int kb = 0; kb < nkb; ++kb) {                  // B blocks: hi ..., lo ...
+                uint8_t *st = sB + (size_t)stage * KT_STAGE_BYTES;
+                mbar_wait(empty + stage, ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full + stage, KT_BLK_BYTES + (kb == 0 ? KT_NB_BYTES : 0u));
+                    if (CS > 1) {                               // my 1/cs of the block's rows, into every CTA of the cluster
+                        const int rows = KT_COLS / CS;
+                        tma_load_2d_mc(st + (size_t)crank * rows * 128, kb < SEG ? &part_hi : &part_lo, (kb % SEG) * KT_KBLK,
+                                       rowbase + j0 + (int)crank * rows, full + stage, cmask);
+                        if (kb == 0)
+                            tma_load_2d_mc(st + KT_BLK_BYTES + (size_t)crank * rows * 16, &map_nb, 0, rowbase + j0 + (int)crank * rows,
+                                           full + stage, cmask);
+                    } else {
+                        tma_load_2d(st, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK, rowbase + j0, full + stage);
+                        if (kb == 0) tma_load_2d(st + KT_BLK_BYTES, &map_nb, 0, rowbase + j0, full + stage);   // the tile's norm operand
+                    }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
-            mbar_wait(a_full, 0);
-            int stage = 0;
-            uint32_t ph = 0;
-            for (int g = 0; g < 2 * T; ++g) {
-                const int buf = g & 1;
-                mbar_wait(tm_empty + buf, ((g >> 1) & 1) ^ 1);
+        // the whole warp runs the loop; one elected lane issues the tcgen05 instructions
+        mbar_wait(a_full, 0);
+        const uint32_t ones_addr = smem_u32(sOnes);
+        const uint64_t da_ones = umma_desc_plain(ones_addr, 2048u, 128u);
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int g = 0; g < 2 * T; ++g) {
+            const int buf = g & (KT_NBUF - 1);
+            mbar_wait(tm_empty + buf, ((g / KT_NBUF) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)buf * KT_COLS;
+            const bool first = g < T;                           // pass 1: dot~ = hi.hi (a looser, cheaper bound)
+            const int nkb = first ? SEG : KB;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full + stage, ph);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)buf * KT_COLS;
-                const bool first = g < T && !three;                 // pass 1: dot~ = hi.hi (a looser, cheaper bound)
-                const int nkb = first ? SEG : KB;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(full + stage, ph);
-                    tc_fence_after();
-                    const uint64_t db = umma_desc_sw128(smem_u32(sB + (size_t)stage * KT_BLK_BYTES));
-                    const int ka = kb % SEG;                        // matching K block of A
-                    const uint64_t da_hi = umma_desc_sw128(smem_u32(sA + (size_t)ka * KT_BLK_BYTES));
+                const uint32_t st_addr = smem_u32(sB + (size_t)stage * KT_STAGE_BYTES);
+                const uint64_t db = umma_desc_sw128(st_addr);
+                const int ka = kb % SEG;                        // matching K block of A
+                const uint64_t da_hi = umma_desc_sw128(smem_u32(sA + (size_t)ka * KT_BLK_BYTES));
+                const uint64_t da_lo = umma_desc_sw128(smem_u32(sA + (size_t)(SEG + ka) * KT_BLK_BYTES));
+                if (elect_one()) {
+                    if (kb == 0) {
+                        // acc = ones . norms^T = -t_j / 2 in every row: K group 0 of B is the tile the TMA just wrote,
+                        // K group 1 is the zero half of the ones block (its A counterpart is zero as well)
+                        const uint32_t nb_addr = st_addr + KT_BLK_BYTES;
+                        tc_mma_bf16(d, da_ones, umma_desc_plain(nb_addr, ones_addr + 2048u - nb_addr, 128u), KT_IDESC, 0u);
+                    }
 #pragma unroll
                     for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)   // +32 bytes per K=16 step inside the swizzle span
-                        tc_mma_bf16(d, da_hi + 2 * k16, db + 2 * k16, KT_IDESC, (kb | k16) != 0);   // hi.hi | hi.lo
-                    if (kb < SEG && !first) {                       // pass 2: a B_hi block also meets A_lo:  lo.hi
-                        const uint64_t da_lo = umma_desc_sw128(smem_u32(sA + (size_t)(SEG + ka) * KT_BLK_BYTES));
+                        tc_mma_bf16(d, da_hi + 2 * k16, db + 2 * k16, KT_IDESC, 1u);   // hi.hi | hi.lo
+                    if (kb < SEG && !first) {                   // pass 2: a B_hi block also meets A_lo:  lo.hi
 #pragma unroll
                         for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)
                             tc_mma_bf16(d, da_lo + 2 * k16, db + 2 * k16, KT_IDESC, 1u);
                     }
-                    if (pair) tc_commit_mc(empty + stage, (uint16_t)3);   // stage reusable when BOTH CTAs' MMAs retired
+                    if (CS > 1) tc_commit_mc(empty + stage, cmask);   // stage reusable when EVERY CTA's MMAs on it retired
                     else tc_commit(empty + stage);                  // smem stage reusable when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
+                    if (kb == nkb - 1) tc_commit(tm_full + buf);    // accumulator of tile g complete
                 }
-                tc_commit(tm_full + buf);                           // accumulator of tile g complete
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
             }
         }
-        __syncwarp();
     } else {
-        // ================================ epilogue: two threads per query row ===========
-        // warp w (2..9): TMEM lane quadrant q = w & 3 (hardware rule), column half h = (w - 2) >> 2.
+        // ================================ epilogue: four threads per query row =========
+        // warp w (2..17): TMEM lane quadrant q = w & 3 (hardware rule), column quarter h = (w - 2) >> 2.
         const int q = warp & 3;
         const int h = (warp - 2) >> 2;
         const int r = q * 32 + lane;             // row within the tile
         const int i = i0 + r;
-        const int et = threadIdx.x - 64;         // 0..255 among the epilogue threads
-        const float xxi = (i < N) ? P.xx[(size_t)rowbase + i] : 0.0f;
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 64;
-        float gmin[NG];
+        const int et = threadIdx.x - 64;         // 0..511 among the epilogue threads
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 32;
+        const int last_valid = N - (T - 1) * KT_COLS - h * 32;    // valid columns of this quarter in the last tile
+        const bool ragged = last_valid < 32;
+        const float shift = (P.dump && i < N) ? P.ss[(size_t)rowbase + i] : 0.0f;
+        float gmax[NGT];
 #pragma unroll
-        for (int e = 0; e < NG; ++e) gmin[e] = INFINITY;
-        Cursor cur;
-        {
-            uint2 *row_list = P.cand + ((size_t)rowbase + min(i, N - 1)) * CAP;
-            cur.step = h ? -1 : 1;
-            cur.base = h ? row_list + (CAP - 1) : row_list;
-            cur.off = 0;
-            cur.ovf = false;
-        }
-        const float *xxb = P.xx + rowbase;
-        // norms of tile 0; afterwards the norms of tile g+1 are fetched while tile g is processed.  The same threads
-        // see every norm of the cloud once during pass 1: their maximum gives the error bound of the row.
-        float nmax = 0.0f;
-        if (et < KT_COLS) {
-            const float n0 = (et < N) ? xxb[et] : INFINITY;
-            nrm_s[et] = n0;
-            if (et < N) nmax = n0;
-        }
+        for (int e = 0; e < NGT; ++e) gmax[e] = -INFINITY;
+        if (et == 0) kt_mark(P, 1);
 
-        // ---- pass 1: class minima
+        // ---- pass 1: class maxima of acc = hi.hi - t_j/2
         for (int g = 0; g < T; ++g) {
-            const int buf = g & 1;
-            float nxt = INFINITY;
-            const int jn = ((g + 1) % T) * KT_COLS + et;       // tile g+1 (pass 2 restarts at tile 0)
-            if (et < KT_COLS && jn < N) nxt = xxb[jn];           // consumed at the bottom of the iteration: the L2 latency
-                                                                // hides behind the tile (a use here would stall all 8 warps at the barrier)
-            epi_bar_sync();                                     // norms of tile g visible
-            mbar_wait(tm_full + buf, (g >> 1) & 1);
+            const int buf = g & (KT_NBUF - 1);
+            uint32_t u[32];
+            mbar_wait(tm_full + buf, (g / KT_NBUF) & 1);
             tc_fence_after();
-            if (!(P.mode & 1)) epi_tile<NG, 1>(gmin, cur, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, 0.0f, 0u);
-            if (P.dump) dump_tile(P.dump + ((size_t)rowbase + min(i, N - 1)) * N, i < N, tlane + (uint32_t)buf * KT_COLS,
-                                  nrm_s + buf * KT_COLS + h * 64, g * KT_COLS + h * 64, N);
+            if (et == 0 && g == 0) kt_mark(P, 2);
+            tc_ld32_issue(tlane + (uint32_t)buf * KT_COLS, u);
+            tc_wait32(u);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tm_empty + buf);
-            if (et < KT_COLS) {
-                nrm_s[(buf ^ 1) * KT_COLS + et] = nxt;
-                if (jn < N) nmax = fmaxf(nmax, nxt);
+            if (lane == 0) mbar_arrive(tm_empty + buf);             // the accumulator is in registers: free the buffer
+            if (ragged && g == T - 1) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (c >= last_valid) u[c] = 0xff800000u;        // columns beyond the cloud: -inf
+            }
+            if (P.dump && i < N) {
+                float *drow = P.dump + ((size_t)rowbase + i) * N + (size_t)g * KT_COLS + h * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (g * KT_COLS + h * 32 + c < N) drow[c] = __fmaf_rn(-2.0f, __uint_as_float(u[c]), -shift);
+            }
+            if (NGT == 16) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
+                    gmax[c] = fmaxf(fmaxf(gmax[c], __uint_as_float(u[c])), __uint_as_float(u[c + 16]));   // FMNMX3
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) gmax[c % NGT] = fmaxf(gmax[c % NGT], __uint_as_float(u[c]));
             }
         }
-        // ---- between the passes: the row has 2 NG class minima (NG per thread).  Each thread sorts its own;
-        // the k-th smallest of the union of two sorted lists A, B is max_{i<k} min(A[i], B[k-1-i]).
-        reg_sort<NG>(gmin);
-        if (h == 1) {
+        // ---- between the passes: the row has 4 NGT class maxima (NGT per thread); tau = their k-th largest.  Every thread
+        // sorts its own (descending, in registers); quarters 0 and 2 merge their list with their neighbour's (bitonic merge
+        // of [own | reversed neighbour]); quarter 0 then takes the k-th largest of the union of the two merged lists A, B:
+        // max over i of min(A[i-1], B[k-i-1]) (i values from A, k - i from B).
+        if (et == 0) kt_mark(P, 3);
+        reg_sort_desc<NGT>(gmax);
+        float *xchg2 = xchg + (size_t)4 * NGT * KT_ROWS;           // [2 NGT][128]: the merged list of quarters 2 | 3
 #pragma unroll
-            for (int e = 0; e < NG; ++e)
-                if (e < KX) xchg[e * KT_ROWS + r] = gmin[e];
-        }
-        if (et < KT_COLS) {                                     // warps 2..5 hold the norms
-            const uint32_t m = __reduce_max_sync(MLSP_FULL, __float_as_uint(nmax));   // non-negative floats order as uints
-            if (lane == 0) max_s[warp - 2] = m;
+        for (int e = 0; e < NGT; ++e) xchg[((size_t)h * NGT + e) * KT_ROWS + r] = gmax[e];
+        if (et == 0) kt_mark(P, 4);
+        epi_bar_sync();
+        if (et == 0) kt_mark(P, 5);
+        float mg[2 * NGT];
+        if ((h & 1) == 0) {
+#pragma unroll
+            for (int e = 0; e < NGT; ++e) {
+                mg[e] = gmax[e];
+                mg[NGT + e] = xchg[((size_t)(h + 1) * NGT + (NGT - 1 - e)) * KT_ROWS + r];
+            }
+            bitonic_merge_desc<2 * NGT>(mg);
+            if (h == 2) {
+#pragma unroll
+                for (int e = 0; e < 2 * NGT; ++e) xchg2[(size_t)e * KT_ROWS + r] = mg[e];
+            }
         }
         epi_bar_sync();
         if (h == 0) {
-            const float maxxx = __uint_as_float(max(max(max_s[0], max_s[1]), max(max_s[2], max_s[3])));
-            const float eps = pair_eps(sqrtf(xxi), xxi, maxxx);   // bound for every candidate of the cloud
-            // pass 1 saw dot~ = hi.hi only: |v1 - v| <= KT_EPS1_REL |x_i| max_j |x_j|
-            const float eps1 = three ? 0.0f : KT_EPS1_REL * sqrtf(xxi) * sqrtf(maxxx);
+            float mxx = red_s[0], myy = red_s[16];
+#pragma unroll
+            for (int w = 1; w < 16; ++w) {
+                mxx = fmaxf(mxx, red_s[w]);
+                myy = fmaxf(myy, red_s[16 + w]);
+            }
+            const float eps = pair_eps(yyi, myy, xxi, mxx, P.C);    // bound for every candidate of the cloud
+            const float eps1 = KT_EPS1_REL * sqrtf(yyi) * sqrtf(myy);   // pass 1 saw dot~ = hi.hi only
+            const int k = P.k;
             float tau = -INFINITY;
 #pragma unroll
-            for (int e = 0; e < NG; ++e)
-                if (e < P.k) tau = fmaxf(tau, fminf(gmin[e], xchg[(P.k - 1 - e) * KT_ROWS + r]));
-            thr_s[r] = tau + eps1 + 2.0f * eps;
+            for (int t = 0; t <= 2 * NGT; ++t) {                    // t values from A = mg, k - t from B = xchg2
+                const int bi = k - t - 1;
+                if (t <= k && bi < 2 * NGT) {
+                    const float av = (t == 0) ? INFINITY : mg[t == 0 ? 0 : t - 1];
+                    const float bv = (bi < 0) ? INFINITY : xchg2[(size_t)bi * KT_ROWS + r];
+                    tau = fmaxf(tau, fminf(av, bv));
+                }
+            }
+            // k columns have pass-1 values >= tau, so the k-th best exact value is >= tau - (eps1 + eps)/2 on the accumulator
+            // scale (v = -2 acc) and every member of the exact top-k has a pass-2 accumulator >= tau - (eps1 + 2 eps)/2
+            const float slack = 0.5f * 1.0009765625f * (eps1 + 2.0f * eps);
+            thr_s[r] = (i < N && tau > -INFINITY) ? tau - slack : INFINITY;   // rows beyond the cloud collect nothing
         }
-        epi_bar_sync();
-        const float thr = (i < N) ? thr_s[r] : -INFINITY;    // rows beyond the cloud collect nothing
-        // ---- pass 2: collect the candidates
+        epi_bar_sync();                                             // thr_s written, xchg (aliases the lists) no longer read
+        if (et == 0) kt_mark(P, 6);
+        const float thr = thr_s[r];
+        // ---- pass 2: collect the candidates into the row's list in shared memory.  Quarters 0/1 share the first half of
+        // the row's words (0 from the front, 1 from the back), quarters 2/3 the second half.
+        // all ones above bit 4; kept opaque to the compiler so that it stays in a register and the COLUMN is the immediate of
+        // the packing LOP3 (the other way round costs a MOV per element)
+        const uint32_t keep = 0xffffffe0u | ((uint32_t)N >> 31);
+        const uint32_t cur0 = smem_u32(lists + (size_t)r * CAPW + (h >> 1) * HC + ((h & 1) ? HC - 1 : 0));
+        const int step = (h & 1) ? -4 : 4;
+        uint32_t cur = cur0;
+        bool ovf = false;
         for (int g = T; g < 2 * T; ++g) {
-            const int buf = g & 1;
-            float nxt = INFINITY;
-            const int jn = (g + 1 - T) * KT_COLS + et;
-            if (et < KT_COLS && g + 1 < 2 * T && jn < N) nxt = xxb[jn];
-            epi_bar_sync();
-            mbar_wait(tm_full + buf, (g >> 1) & 1);
+            const int buf = g & (KT_NBUF - 1);
+            uint32_t u[32];
+            mbar_wait(tm_full + buf, (g / KT_NBUF) & 1);
             tc_fence_after();
-            if (!(P.mode & 2)) epi_tile<NG, 2>(gmin, cur, tlane + (uint32_t)buf * KT_COLS, nrm_s + buf * KT_COLS + h * 64, thr,
-                            (uint32_t)((g - T) * KT_COLS + h * 64));
-            if (P.dump) dump_tile(P.dump + ((size_t)gridDim.y * N + rowbase + min(i, N - 1)) * N, i < N, tlane + (uint32_t)buf * KT_COLS,
-                                  nrm_s + buf * KT_COLS + h * 64, (g - T) * KT_COLS + h * 64, N);
+            tc_ld32_issue(tlane + (uint32_t)buf * KT_COLS, u);
+            tc_wait32(u);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tm_empty + buf);
-            if (et < KT_COLS) nrm_s[(buf ^ 1) * KT_COLS + et] = nxt;
+            if (ragged && g == 2 * T - 1) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if (c >= last_valid) u[c] = 0xff800000u;
+            }
+            if (P.dump && i < N) {
+                float *drow = P.dump + ((size_t)gridDim.y * N + rowbase + i) * N + (size_t)(g - T) * KT_COLS + h * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c)
+                    if ((g - T) * KT_COLS + h * 32 + c < N) drow[c] = __fmaf_rn(-2.0f, __uint_as_float(u[c]), -shift);
+            }
+            // a tile can add 32 entries: without room for them nothing is stored any more and the row is flagged
+            const int cnt = abs((int)(cur - cur0)) >> 2;
+            const bool room = cnt <= HC - 32;
+            ovf |= !room;
+            const float t = room ? thr : INFINITY;
+            collect_tile<0>(cur, u, t, step, keep);
+            snap_s[(size_t)(g - T) * KT_EPI_THREADS + et] = (uint8_t)(abs((int)(cur - cur0)) >> 2);
         }
+        const int cnt_end = abs((int)(cur - cur0)) >> 2;
+        if (et == 0) kt_mark(P, 7);
         if (i < N) {
-            P.cand_cnt[2 * ((size_t)rowbase + i) + h] = cur.ovf ? CAP + 1 : abs(cur.off);
+            P.cand_cnt[4 * ((size_t)rowbase + i) + h] = (uint8_t)(ovf ? 255 : cnt_end);
+            // snapshots of this quarter: TP bytes, padding 255 (never <= an entry position)
+            uint8_t *sg = P.snap + (4 * ((size_t)rowbase + i) + h) * P.TP;
+            for (int t0 = 0; t0 < P.TP; t0 += 8) {
+                uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const uint32_t a = (t0 + t < T) ? snap_s[(size_t)(t0 + t) * KT_EPI_THREADS + et] : 255u;
+                    const uint32_t c = (t0 + 4 + t < T) ? snap_s[(size_t)(t0 + 4 + t) * KT_EPI_THREADS + et] : 255u;
+                    w0 |= a << (8 * t);
+                    w1 |= c << (8 * t);
+                }
+                *reinterpret_cast<uint2 *>(sg + t0) = make_uint2(w0, w1);
+            }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's list words, for the TMA engine
+        epi_bar_sync();                                             // every list of the CTA is complete
+        if (et == 0) {
+            kt_mark(P, 8);
+            // one bulk copy of the CTA's lists (contiguous in global memory: rows i0 .. of the cloud) by the TMA engine
+            const int rows_valid = min(KT_ROWS, N - i0);
+            bulk_store(P.cand + ((size_t)rowbase + i0) * CAPW, lists, (uint32_t)rows_valid * CAPW * 4u);
+            bulk_store_wait();                                      // shared memory is released when the CTA exits
+        }
+        if (et == 0) kt_mark(P, 9);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (pair) cluster_sync_all();            // no CTA leaves while its peer can still signal its barriers / write its smem
+    if (CS > 1) cluster_sync_all();          // no CTA leaves while a peer can still signal its barriers / write its smem
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -676,34 +809,23 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
 // sort on (cluster start, exact value desc, index asc) then gives the specification's order.
 constexpr int RF_WARPS = 8;
 
-// Keys arrive as (orderable v~ << 32 | j << 16 | list slot): the slot names where the candidate's norm |x_j|^2 --
-// fetched before the sort, so that its L2 latency hides behind the sorting network -- waits in shared memory.
+// Keys arrive as (orderable v~ << 32 | j); xxj / yyj: the candidates' norms in LIST order, fetched before the sort so
+// that their L2 latency hides behind the sorting network (only their list-wide maximum bound is needed).
 template <int S, int C, int KS>
 __device__ __forceinline__ void refine_sorted(const KtParams &P, uint32_t row, uint32_t base, unsigned long long (&key)[S],
-                                              const float (&xpre)[S], uint16_t *sj, float *se, uint32_t (&nbr)[KS])
+                                              const float (&xxj)[S], const float (&yyj)[S], uint16_t *sj, float *se,
+                                              uint32_t (&nbr)[KS])
 {
     constexpr int M = C / 16;                             // float4 pieces per lane: 4 (C = 64) or 8 (C = 128)
     const int lane = threadIdx.x & 31;
     const int g = lane >> 2, u = lane & 3;
     const int k = P.k;
-    const float xxi = P.xx[row];
-    const float ni = sqrtf(xxi);
+    const float xxi = P.xx[row], yyi = P.yy[row];
     warp_sort_u64<S>(key);
-#pragma unroll
-    for (int s = 0; s < S; ++s) se[s * 32 + lane] = xpre[s];             // norms by list slot
-    __syncwarp();
-    float xs[S];                                                         // |x_j|^2 of the candidate now at (s, lane)
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const uint32_t low = (uint32_t)key[s];
-        const bool live = key[s] != ~0ull;
-        xs[s] = live ? se[low & 0xffffu] : 0.0f;
-        if (live) key[s] = (key[s] & 0xffffffff00000000ull) | (low >> 16);   // -> (orderable v~ << 32 | j)
-    }
     // ---- links, clusters
     // A position e that starts a new cluster must certify EVERY later position m >= e against EVERY earlier one
     // t < e: exact_m - exact_t >= (v_e - v_{e-1}) - eps_m - eps_t.  The per-pair bounds differ with the norms, so the
-    // test uses the largest bound of the whole list (one redux per slot): gap > 2 max eps.
+    // test uses the largest bound of the whole list (one redux): gap > 2 max eps.
     float v[S];
     bool link[S];
     int cs[S];
@@ -714,8 +836,9 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, uint32_t row, u
         const bool live = key[s] != ~0ull;
         const uint32_t ob = (uint32_t)(key[s] >> 32);                    // f32_orderable(v~)
         v[s] = live ? __uint_as_float((ob & 0x80000000u) ? (ob ^ 0x80000000u) : ~ob) : INFINITY;
-        emax = fmaxf(emax, warp_max_f32(live ? pair_eps(ni, xxi, xs[s]) : 0.0f));
+        emax = fmaxf(emax, pair_eps(yyi, yyj[s], xxi, xxj[s], C));       // list order: only the maximum matters
     }
+    emax = warp_max_f32(emax);
     const float gap_max = 1.0009765625f * (emax + emax);
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -813,7 +936,6 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, uint32_t row, u
         if (s < KS) nbr[s] = (uint32_t)key[s] & 0xffffu;                  // rank e = s*32 + lane, for the fused gather
     }
 }
-
 // a2 fused into the refine kernel (get_graph_feature with idx=None): the warp that ranked row i writes the row's
 // k x 2C edge features [x_j - x_i | x_i] straight away -- the latency-bound ranking of some warps overlaps the
 // write stream of others, and idx is not read back.  Same lane layout as edge_fwd_vec_kernel (edge.cu): lanes span
@@ -895,35 +1017,47 @@ __device__ __noinline__ void knn_row_exact(const float *__restrict__ xt, const f
     }
 }
 
-template <int NG, int C>
+// list capacity per row (words) -> sorting slots: 128 words (k <= 32): up to 64 candidates; 192 words: up to 128
+template <int CAPW, int C>
 __global__ void __launch_bounds__(32 * RF_WARPS, 4)   // <= 64 registers: four CTAs per SM
 knn_refine_kernel(KtParams P, long long total_rows)
 {
-    constexpr int CAP = 2 * NG;
-    constexpr int SLOTS = CAP / 32;
+    constexpr int HC = CAPW / 2;
+    constexpr int SLOTS = (CAPW == 128) ? 2 : 4;
+    constexpr int KS = SLOTS / 2;                          // slots holding the k ranked neighbours (k <= 32 / 64)
+    constexpr int SW = 4 * KT_MAX_TILES / 4;               // snapshot words per row, at most
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long row64 = (long long)blockIdx.x * RF_WARPS + warp;   // b*N + i
     if (row64 >= total_rows) return;
     const uint32_t row = (uint32_t)row64;                              // B*N < 2^31 (knn_tensor_supported)
     const uint32_t base = row / (uint32_t)P.N * (uint32_t)P.N;         // first row of the cloud
-    // The two ends of the row's list are fetched SPECULATIVELY together with the two counters (one L2 round trip
-    // instead of two dependent ones): slot (h, lane) of the front end is valid iff h*32+lane < c0, of the back end iff
-    // h*32+lane < c1.  Counts above CAP/2 at one end (rare) re-read that end below.
-    constexpr int HS = CAP / 64;
-    const uint2 *list = P.cand + (size_t)row * CAP;
-    const int2 cc = *reinterpret_cast<const int2 *>(P.cand_cnt + 2 * (size_t)row);
-    uint2 fa[HS], fb[HS];
-#pragma unroll
-    for (int h = 0; h < HS; ++h) {
-        fa[h] = list[h * 32 + lane];
-        fb[h] = list[CAP - 1 - (h * 32 + lane)];
-    }
-    const int c0 = cc.x, c1 = cc.y;
-    const int cnt = c0 + c1;
-    constexpr int KS = NG / 32;                            // slots holding the k <= NG ranked neighbours
+    __shared__ __align__(16) uint32_t sl_all[RF_WARPS][CAPW];
+    __shared__ uint32_t sn_all[RF_WARPS][SW];
+    __shared__ uint16_t sj_all[RF_WARPS][32 * SLOTS];
+    __shared__ float se_all[RF_WARPS][32 * SLOTS];
+    uint32_t *sl = sl_all[warp], *sn = sn_all[warp];
+    uint16_t *sj = sj_all[warp];
+    float *se = se_all[warp];
+    // the row's list words, its four counters and its snapshots in ONE L2 round trip
+    const uint4 *l4 = reinterpret_cast<const uint4 *>(P.cand + (size_t)row * CAPW);
+    const uint32_t *g_sn = reinterpret_cast<const uint32_t *>(P.snap + (size_t)row * 4 * P.TP);
+    const uint4 w0 = l4[lane];
+    uint4 w1 = make_uint4(0u, 0u, 0u, 0u);
+    if (CAPW > 128 && lane < CAPW / 4 - 32) w1 = l4[32 + lane];
+    const uint32_t cc = *reinterpret_cast<const uint32_t *>(P.cand_cnt + 4 * (size_t)row);
+    const int TPW = P.TP;                                  // 4 quarters x TP bytes = TP words
+    const uint32_t s0 = (lane < TPW) ? g_sn[lane] : 0u;
+    const uint32_t s1 = (32 + lane < TPW) ? g_sn[32 + lane] : 0u;
+    reinterpret_cast<uint4 *>(sl)[lane] = w0;
+    if (CAPW > 128 && lane < CAPW / 4 - 32) reinterpret_cast<uint4 *>(sl)[32 + lane] = w1;
+    if (lane < TPW) sn[lane] = s0;
+    if (32 + lane < TPW) sn[32 + lane] = s1;
+    __syncwarp();
+    const int c0 = cc & 255, c1 = (cc >> 8) & 255, c2 = (cc >> 16) & 255, c3 = cc >> 24;
+    const int cnt = c0 + c1 + c2 + c3;
     uint32_t nbr[KS];
-    if (c0 > CAP || c1 > CAP || cnt > CAP || cnt < P.k) {
-        knn_row_exact<NG / 32>(P.xt, P.xx, row64, P.N, C, P.k, P.idx);   // warp-uniform
+    if (c0 == 255 || c1 == 255 || c2 == 255 || c3 == 255 || c0 + c1 > HC || c2 + c3 > HC || cnt > 32 * SLOTS || cnt < P.k) {
+        knn_row_exact<KS>(P.xt, P.xx, row64, P.N, C, P.k, P.idx);        // warp-uniform
         if (lane == 0) atomicAdd(P.fb_count, 1);
         if (P.edge_out) {
             __syncwarp();                                  // the row's idx, written by this warp, is visible to it
@@ -933,48 +1067,48 @@ knn_refine_kernel(KtParams P, long long total_rows)
         }
         return;
     }
-    __shared__ uint16_t sj_all[RF_WARPS][CAP];
-    __shared__ float se_all[RF_WARPS][CAP];
-    uint16_t *sj = sj_all[warp];
-    float *se = se_all[warp];
-    __shared__ uint2 sc_all[RF_WARPS][CAP];
-    uint2 *sc = sc_all[warp];
-    if (c0 <= 32 * HS && c1 <= 32 * HS) {                  // warp-uniform: compact the two ends into list order
-#pragma unroll
-        for (int h = 0; h < HS; ++h) {
-            const int e = h * 32 + lane;
-            if (e < c0) sc[e] = fa[h];
-            if (e < c1) sc[c0 + e] = fb[h];
-        }
-    } else {
-        for (int e = lane; e < cnt; e += 32) sc[e] = list[e < c0 ? e : CAP - 1 - (e - c0)];
-    }
-    __syncwarp();
+    // decode: entry e of the concatenated quarters -> (filter value, candidate index)
     unsigned long long key[SLOTS];
-    float xpre[SLOTS];
+    float xxj[SLOTS], yyj[SLOTS];
+    const int TQ = P.TP / 4;                               // snapshot words per quarter
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
         const int e = s * 32 + lane;
         key[s] = ~0ull;
-        xpre[s] = 0.0f;
+        xxj[s] = 0.0f;
+        yyj[s] = 0.0f;
         if (e < cnt) {
-            const uint2 ent = sc[e];
-            key[s] = ((unsigned long long)f32_orderable(__fadd_rn(__uint_as_float(ent.x), 0.0f)) << 32) | (ent.y << 16) | (uint32_t)e;
-            xpre[s] = P.xx[base + ent.y];                  // consumed after the sort
+            int seg = 0, p = e;
+            if (p >= c0) { p -= c0; seg = 1;
+                if (p >= c1) { p -= c1; seg = 2;
+                    if (p >= c2) { p -= c2; seg = 3; } } }
+            const uint32_t w = sl[(seg >> 1) * HC + ((seg & 1) ? HC - 1 - p : p)];
+            // the tile the entry was written in = number of tiles whose closing cursor is <= its position
+            const uint32_t pp = (uint32_t)p * 0x01010101u;
+            int tile = 0;
+            for (int t = 0; t < TQ; ++t) tile += __popc(__vcmpleu4(sn[seg * TQ + t], pp)) >> 3;
+            const uint32_t j = (uint32_t)tile * KT_COLS + (uint32_t)seg * 32u + (w & 31u);
+            const float vf = __fmul_rn(-2.0f, __uint_as_float(w & 0xffffffe0u));   // v~ = -2 acc (row constant dropped)
+            key[s] = ((unsigned long long)f32_orderable(__fadd_rn(vf, 0.0f)) << 32) | j;
+            xxj[s] = P.xx[base + j];                       // consumed after the sort
+            yyj[s] = P.yy[base + j];
         }
     }
     if (cnt <= 32) {                                       // warp-uniform, the usual case for k <= 20
         unsigned long long k1[1] = {key[0]};
-        const float x1[1] = {xpre[0]};
-        refine_sorted<1, C, KS>(P, row, base, k1, x1, sj, se, nbr);
+        const float x1[1] = {xxj[0]}, y1[1] = {yyj[0]};
+        refine_sorted<1, C, KS>(P, row, base, k1, x1, y1, sj, se, nbr);
     } else if (SLOTS > 2 && cnt <= 64) {
         unsigned long long k2[2] = {key[0], key[1]};
-        const float x2[2] = {xpre[0], xpre[1]};
-        refine_sorted<2, C, KS>(P, row, base, k2, x2, sj, se, nbr);
+        const float x2[2] = {xxj[0], xxj[1]}, y2[2] = {yyj[0], yyj[1]};
+        refine_sorted<2, C, KS>(P, row, base, k2, x2, y2, sj, se, nbr);
     } else {
-        refine_sorted<SLOTS, C, KS>(P, row, base, key, xpre, sj, se, nbr);
+        refine_sorted<SLOTS, C, KS>(P, row, base, key, xxj, yyj, sj, se, nbr);
     }
-    if (lane == 0) atomicAdd(P.stats, 1);
+    if (lane == 0) {
+        atomicAdd(P.stats, 1);
+        atomicAdd(P.stats + 1, cnt);                       // diagnostics: total length of the certified rows' lists
+    }
     if (P.edge_out) gather_row<C, KS>(P, row, base, nbr);
 }
 
@@ -996,45 +1130,71 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_rows)
+// bf16 matrix (rows, cols) row-major, boxes of (128 rows, box_cols): the operand blocks (64 columns, 128-byte swizzle)
+// and the norm operand (8 columns = one 16-byte K group per row, no swizzle: rows land 16 bytes apart)
+static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows,
+                    bool swizzle)
 {
     EncodeTiledFn fn = encode_fn();
     MLSP_REQUIRE(fn, MLSP_ECUDA, "knn: cuTensorMapEncodeTiled not available");
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KT_KBLK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MLSP_REQUIRE(r == CUDA_SUCCESS, MLSP_ECUDA, "knn: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return MLSP_OK;
 }
 
 struct KtLayout {
-    size_t off_counters, off_mode, off_xx, off_hi, off_lo, off_xt, off_cand, off_cnt, total;
+    size_t off_counters, off_cen, off_xx, off_yy, off_ss, off_hi, off_lo, off_nb, off_xt, off_cand, off_cnt, off_snap, total;
+    int capw, TP;
 };
 
 static KtLayout kt_layout(int B, int C, int N, int k)
 {
-    const int CAP = (k <= 32) ? 64 : 128;
     KtLayout L;
+    L.capw = (k <= 32) ? 128 : 192;
+    const int T = (N + KT_COLS - 1) / KT_COLS;
+    L.TP = (T + 7) / 8 * 8;
+    const size_t rows = (size_t)B * N;
     size_t o = 0;
     L.off_counters = o; o += 256;                                            // [0] fb_count, [1] certified rows
-    L.off_mode = o;     o += align_up(sizeof(int) * (size_t)B, 256);         // per-cloud pass-1 choice
-    L.off_xx = o;       o += align_up(sizeof(float) * (size_t)B * N, 256);
-    L.off_hi = o;       o += align_up(2 * (size_t)B * N * C, 1024);
-    L.off_lo = o;       o += align_up(2 * (size_t)B * N * C, 1024);
-    L.off_xt = o;       o += align_up(sizeof(float) * (size_t)B * N * C, 256);
-    L.off_cand = o;     o += align_up(sizeof(uint2) * (size_t)B * N * CAP, 256);
-    L.off_cnt = o;      o += align_up(2 * sizeof(int) * (size_t)B * N, 256);
+    L.off_cen = o;      o += align_up(sizeof(float) * (size_t)B * C, 256);
+    L.off_xx = o;       o += align_up(sizeof(float) * rows, 256);
+    L.off_yy = o;       o += align_up(sizeof(float) * rows, 256);
+    L.off_ss = o;       o += align_up(sizeof(float) * rows, 256);
+    L.off_hi = o;       o += align_up(2 * rows * C, 1024);
+    L.off_lo = o;       o += align_up(2 * rows * C, 1024);
+    L.off_nb = o;       o += align_up(16 * rows, 1024);
+    L.off_xt = o;       o += align_up(sizeof(float) * rows * C, 256);
+    L.off_cand = o;     o += align_up(sizeof(uint32_t) * rows * L.capw, 256);
+    L.off_cnt = o;      o += align_up(4 * rows, 256);
+    L.off_snap = o;     o += align_up(4 * (size_t)L.TP * rows, 256);
     L.total = o;
     return L;
 }
 
+// ring depth: as deep as the 227 KiB of one SM allow (one CTA per SM)
+static int kt_stages(int C, int k, int N)
+{
+    const int T = (N + KT_COLS - 1) / KT_COLS;
+    const size_t per_sm = 227 * 1024;
+    int stages = 0;
+    for (int s_ = 2; s_ <= KT_MAX_STAGES; ++s_)
+        if (kt_smem_bytes(C, k, T, s_) <= per_sm) stages = s_;
+    return stages;
+}
+
+// Limits of the tensor path (anything else takes the fp32 kernels of knn3.cu / knn.cu): C = 64 or 128; 256 <= N <= 8192
+// (per-tile cursor snapshots live in shared memory); k <= 64; a shared-memory configuration with >= 2 ring stages
+// exists (it does not for C = 128, k > 32 beyond N = 6144).
 bool knn_tensor_supported(int B, int C, int N, int k)
 {
-    return (C == 64 || C == 128) && N >= 256 && N <= 65535 && k <= 64 && (long long)B * N < (1ll << 31) && B <= 65535;
+    return (C == 64 || C == 128) && N >= 256 && N <= KT_MAX_TILES * KT_COLS && k >= 1 && k <= 64 && (long long)B * N < (1ll << 31) &&
+           B <= 65535 && kt_stages(C, k, N) >= 2;
 }
 
 size_t knn_tensor_workspace_bytes(int B, int C, int N, int k) { return kt_layout(B, C, N, k).total; }
@@ -1045,66 +1205,57 @@ const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k)
     return reinterpret_cast<const float *>(static_cast<const char *>(ws) + kt_layout(B, C, N, k).off_xt);
 }
 
-// measurement hook (mlsp_graph_feature_fwd_stage): which of the three kernels a call launches; 7 = all
-thread_local int g_kt_stages = 7;
-
+// `stages_mask` (measurement hook of mlsp_graph_feature_fwd_stage): bit 0 prep, bit 1 filter, bit 2 ranking (+ gather); 7 = all
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
-                   cudaStream_t st)
+                   int stages_mask, cudaStream_t st, long long *tstamp, int cluster)
 {
     const KtLayout L = kt_layout(B, C, N, k);
     char *w = static_cast<char *>(ws);
     int *counters = reinterpret_cast<int *>(w + L.off_counters);
-    int *cloud_mode = reinterpret_cast<int *>(w + L.off_mode);
+    float *cen = reinterpret_cast<float *>(w + L.off_cen);
     float *xx = reinterpret_cast<float *>(w + L.off_xx);
+    float *yy = reinterpret_cast<float *>(w + L.off_yy);
+    float *ss = reinterpret_cast<float *>(w + L.off_ss);
     __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(w + L.off_hi);
     __nv_bfloat16 *lo = reinterpret_cast<__nv_bfloat16 *>(w + L.off_lo);
+    uint4 *nb = reinterpret_cast<uint4 *>(w + L.off_nb);
     float *xt = reinterpret_cast<float *>(w + L.off_xt);
 
-    if (g_kt_stages & 1) {
-        knn_prep_kernel<<<dim3((N + PREP_PTS - 1) / PREP_PTS, B), PREP_THREADS, sizeof(float) * C * (PREP_PTS + 1), st>>>(
-            x, C, N, xx, counters, xt, hi, lo, cloud_mode);
+    if (stages_mask & 1) {
+        knn_centre_kernel<<<B, 256, 0, st>>>(x, C, N, cen);
+        MLSP_LAUNCH_CHECK("knn_centre_kernel");
+        knn_prep_kernel<<<dim3((N + PREP_PTS - 1) / PREP_PTS, B), PREP_THREADS, sizeof(float) * (C * (PREP_PTS + 1) + C), st>>>(
+            x, cen, C, N, xx, yy, ss, counters, xt, hi, lo, nb);
         MLSP_LAUNCH_CHECK("knn_prep_kernel");
     }
 
-    CUtensorMap map_hi, map_lo, half_hi, half_lo;       // boxes of 128 rows (A tiles, unpaired B blocks) and of 64 rows (paired)
-    int rc = make_map(&map_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_COLS);
+    dim3 grid((N + KT_ROWS - 1) / KT_ROWS, B);
+    // clusters of 4 (2) adjacent row blocks of a cloud share every candidate block by TMA multicast
+    const int cs = (cluster <= 0) ? ((grid.x % 2 == 0) ? 2 : 1) : ((cluster > 1 && grid.x % cluster == 0) ? cluster : 1);
+    CUtensorMap map_hi, map_lo, part_hi, part_lo, map_nb;  // boxes of 128 rows (A tiles, unshared B blocks) and of 128 / cs rows
+    int rc = make_map(&map_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_COLS, true);
     if (rc) return rc;
-    rc = make_map(&map_lo, lo, (uint64_t)B * N, (uint64_t)C, KT_COLS);
+    rc = make_map(&map_lo, lo, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_COLS, true);
     if (rc) return rc;
-    rc = make_map(&half_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_COLS / 2);
+    rc = make_map(&part_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_COLS / cs, true);
     if (rc) return rc;
-    rc = make_map(&half_lo, lo, (uint64_t)B * N, (uint64_t)C, KT_COLS / 2);
+    rc = make_map(&part_lo, lo, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_COLS / cs, true);
+    if (rc) return rc;
+    rc = make_map(&map_nb, nb, (uint64_t)B * N, 8, 8, KT_COLS / cs, false);
     if (rc) return rc;
 
     KtParams P;
-    P.xx = xx; P.xt = xt; P.idx = idx; P.fb_count = counters; P.cloud_mode = cloud_mode;
-    P.stats = counters + 1; P.dump = dump; P.edge_out = reinterpret_cast<float4 *>(edge_out);
-    P.cand = reinterpret_cast<uint2 *>(w + L.off_cand); P.cand_cnt = reinterpret_cast<int *>(w + L.off_cnt); P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS;
-    const int NG = (k <= 32) ? 32 : 64;
-    // ring depth: as deep as two CTAs per SM allow (NG = 32), else one CTA per SM with up to 8 stages
-    const size_t per_sm = 227 * 1024, reserved = 1024;
-    const size_t budget2 = per_sm / 2 - reserved;
-    int stages = 0;
-    if (NG == 32)
-        for (int s_ = 2; s_ <= KT_MAX_STAGES; ++s_)
-            if (kt_smem_bytes(C, k, NG, s_) <= budget2) stages = s_;
-    if (stages == 0)
-        for (int s_ = 2; s_ <= KT_MAX_STAGES; ++s_)
-            if (kt_smem_bytes(C, k, NG, s_) <= per_sm - reserved) stages = s_;
-    P.stages = stages;
-    if (const char *e = getenv("MLSP_KT_STAGES")) P.stages = atoi(e);   // tuning hook
-    P.mode = 0;
-    if (const char *e = getenv("MLSP_KT_MODE")) P.mode = atoi(e);
-    MLSP_REQUIRE(P.stages >= 2 && P.stages <= KT_MAX_STAGES && kt_smem_bytes(C, k, NG, P.stages) <= per_sm - reserved,
-                 MLSP_EUNSUPPORTED, "knn: no shared-memory configuration for C=%d k=%d", C, k);
-    const size_t smem = kt_smem_bytes(C, k, NG, P.stages);
-    dim3 grid((N + KT_ROWS - 1) / KT_ROWS, B);
-    // MLSP_KT_CLUSTER=1 (tuning hook): clusters of two adjacent row blocks of a cloud share every candidate block by TMA
-    // multicast (needs an even number of row blocks per cloud).  Off by default: halving the L2 -> SM operand traffic
-    // changed nothing (profiles/kt_ablate_r1h.log), i.e. the MMA pipeline is not fed-bound.
-    P.pair = 0;
-    if (const char *e = getenv("MLSP_KT_CLUSTER")) P.pair = (atoi(e) != 0 && grid.x % 2 == 0) ? 1 : 0;
-    if (g_kt_stages & 2) {
+    P.xx = xx; P.yy = yy; P.ss = ss; P.xt = xt; P.idx = idx; P.fb_count = counters; P.stats = counters + 1;
+    P.cand = reinterpret_cast<uint32_t *>(w + L.off_cand);
+    P.cand_cnt = reinterpret_cast<uint8_t *>(w + L.off_cnt);
+    P.snap = reinterpret_cast<uint8_t *>(w + L.off_snap);
+    P.dump = dump; P.tstamp = tstamp; P.edge_out = reinterpret_cast<float4 *>(edge_out);
+    P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS; P.TP = L.TP; P.capw = L.capw;
+    P.stages = kt_stages(C, k, N);
+    MLSP_REQUIRE(P.stages >= 2, MLSP_EUNSUPPORTED, "knn: no shared-memory configuration for C=%d k=%d N=%d", C, k, N);
+    const size_t smem = kt_smem_bytes(C, k, P.T, P.stages);
+    P.cs = cs;
+    if (stages_mask & 2) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
         cfg.blockDim = dim3(KT_THREADS);
@@ -1112,31 +1263,31 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = P.pair ? 2 : 1;
+        attr[0].val.clusterDim.x = (unsigned)cs;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (NG == 32) {
-            MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<32>, map_hi, map_lo, half_hi, half_lo, P));
+        if (k <= 32) {
+            MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<16>, map_hi, map_lo, part_hi, part_lo, map_nb, P));
         } else {
-            MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<64>, map_hi, map_lo, half_hi, half_lo, P));
+            MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<32>, map_hi, map_lo, part_hi, part_lo, map_nb, P));
         }
+        MLSP_LAUNCH_CHECK("knn_tensor_kernel");
     }
-    MLSP_LAUNCH_CHECK("knn_tensor_kernel");
-    if (g_kt_stages & 4) {
+    if (stages_mask & 4) {
         const long long rows_total = (long long)B * N;
         const unsigned rblocks = (unsigned)((rows_total + RF_WARPS - 1) / RF_WARPS);
-        if (NG == 32 && C == 64)
-            knn_refine_kernel<32, 64><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
-        else if (NG == 32)
-            knn_refine_kernel<32, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+        if (k <= 32 && C == 64)
+            knn_refine_kernel<128, 64><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+        else if (k <= 32)
+            knn_refine_kernel<128, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
         else if (C == 64)
-            knn_refine_kernel<64, 64><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+            knn_refine_kernel<192, 64><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
         else
-            knn_refine_kernel<64, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+            knn_refine_kernel<192, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
         MLSP_LAUNCH_CHECK("knn_refine_kernel");
     }
     return MLSP_OK;

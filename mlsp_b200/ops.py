@@ -74,8 +74,8 @@ def knn(x: torch.Tensor, k: int, flags: int = _lib.KNN_AUTO, return_stats: bool 
         ws = _workspace(_lib.OP_KNN, B, C, N, k, x.device)
         _lib.call("mlsp_knn_f32", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(), flags, _stream(x.device))
     if return_stats:
-        c = ws[:8].view(torch.int32).cpu()
-        return idx, {"fallback_rows": int(c[0]), "certified_rows": int(c[1])}
+        c = ws[:16].view(torch.int32).cpu()
+        return idx, {"fallback_rows": int(c[0]), "certified_rows": int(c[1]), "candidates": int(c[2])}
     return idx
 
 

@@ -544,21 +544,28 @@ def test_ops_follow_current_stream(dev, orc):
 # ------------------------------------------------------------------------------------------------ a1, tcgen05 path
 @pytest.mark.parametrize("B,C,N,k", [(2, 64, 512, 20), (2, 128, 640, 20), (1, 64, 1000, 40)])
 def test_knn_tensor_filter_values(dev, B, C, N, k):
-    """The tensor-core filter values v = |x_j|^2 - 2 dot~ must sit within the certified error bound of the
-    exact values (this is what makes the candidate list a superset of the exact top-k)."""
+    """The tensor-core filter values v = |x_j|^2 - 2 dot~ (the accumulator -2x, plus the row shift the centring
+    introduces) must sit within the certified error bound of the exact values (this is what makes the candidate list a
+    superset of the exact top-k)."""
     x = synth.smooth_features(B, C, N, 55)
+    x[-1] += 0.5                                                       # one cloud away from the origin: centring at work
     idx, v, stats = M.knn_tensor_debug(x.to(dev), k)
     xd = x.double()
     xx = (xd ** 2).sum(1)                                              # (B,N)
     exact = xx[:, None, :] - 2 * torch.einsum("bci,bcj->bij", xd, xd)   # (B,N,N): |x_j|^2 - 2 x_i.x_j
     assert torch.isfinite(v).all()
-    scale = xx.sqrt()[:, :, None] * xx.sqrt().amax(dim=1)[:, None, None]
+    # the bounds scale with the norms of the re-centred points y = x - c, c = mean of 64 points taken at stride N // 64
+    # (knn_centre_kernel), plus the specification's own rounding on the uncentred norms
+    c = xd[:, :, ::N // 64][:, :, :64].mean(2)
+    yn = ((xd - c[:, :, None]) ** 2).sum(1).sqrt()                     # (B,N)
+    scale = yn[:, :, None] * yn.amax(dim=1)[:, None, None]
+    rnd = 2.0 ** -19 * (xx[:, :, None] + xx.amax(dim=1)[:, None, None])
     err = (v[1].cpu().double() - exact).abs()                          # pass 2: the listed, certified values
-    bound = 2.0 ** -11 * scale
+    bound = 2.0 ** -11 * scale + rnd
     assert (err <= bound).all(), float((err / bound).max())
     assert float((err / bound).max()) < 0.5                            # 2x safety margin actually present
     err1 = (v[0].cpu().double() - exact).abs()                         # pass 1: bf16 heads only (threshold only)
-    bound1 = 2.0 ** -7 * scale
+    bound1 = 2.0 ** -7 * scale + rnd
     assert (err1 <= bound1).all(), float((err1 / bound1).max())
     assert stats["certified_rows"] + stats["fallback_rows"] == B * N
 
@@ -576,17 +583,6 @@ def test_knn_tensor_matches_oracle(dev, orc, B, C, N, k, quant):
         assert stats["fallback_rows"] <= 0.05 * B * N, stats            # the filter certifies nearly every row
     exact = M.knn(x.to(dev), k, flags=M._lib.KNN_EXACT_ONLY)
     assert torch.equal(exact, idx)
-
-
-def test_knn_tensor_cluster_multicast_variant(dev, orc, monkeypatch):
-    """MLSP_KT_CLUSTER=1: the filter launched in clusters of two CTAs that share every candidate block by TMA
-    multicast (each CTA fetches half of it) gives the same indices."""
-    monkeypatch.setenv("MLSP_KT_CLUSTER", "1")
-    for B, C, N, k in [(3, 64, 1024, 20), (2, 128, 768, 40)]:
-        x = synth.smooth_features(B, C, N, 78)
-        idx, stats = M.knn(x.to(dev), k, flags=M._lib.KNN_TENSOR_ONLY, return_stats=True)
-        assert np.array_equal(_np(idx), orc.knn(x.numpy(), k))
-        assert stats["fallback_rows"] <= 0.05 * B * N
 
 
 def test_knn_tensor_ties_and_duplicates(dev, orc):
@@ -842,27 +838,23 @@ def test_edge_conv_dgcnn_backbone_and_errors(dev):
         edgeconv.edge_conv(x0, torch.zeros(8, 6, device=dev), k, negative_slope=-0.1)
 
 
-def test_knn_tensor_activations_far_from_the_origin(dev, orc, monkeypatch):
+def test_knn_tensor_activations_far_from_the_origin(dev, orc):
     """A tight cluster far from the origin (what BatchNorm-free layers with a bias produce, PointSegDA/Models.py:159-184:
-    E|x|^2 ~ 10-30 x the variance): the bf16-head pass 1 of the tcgen05 filter bounds the k-th distance too loosely there
-    (every candidate list would overflow and the rows would fall back to the exact streaming selection), so the prep
-    kernel flags such clouds for the three-term pass 1.  Same bits as the oracle either way; with the flag almost every
-    row stays on the tensor path."""
+    E|x|^2 ~ 10-30 x the variance): the filter's error bounds scale with |x_i||x_j|, which there exceeds the k-th distance,
+    so every candidate list would overflow and the rows would fall back to the exact streaming selection.  The prep kernel
+    therefore re-centres every cloud before the bf16 split (distances are translation invariant; the exact re-rank still
+    uses the uncentred rows and norms of the specification).  Same bits as the oracle, (almost) every row certified."""
     from mlsp_b200 import _lib
-    B, C, N, k = 3, 64, 1024, 20
-    x = synth.smooth_features(B, C, N, 77) + 0.7               # E|x|^2 / Var ~ 25; about half the rows would overflow
-    x[1] = synth.smooth_features(1, C, N, 78)[0]              # an ordinary cloud (ratio 1.5) in the same batch keeps the fast pass
+    B, C, N, k = 4, 64, 1024, 20
+    x = synth.smooth_features(B, C, N, 77) + 0.7               # E|x|^2 / Var ~ 25
+    x[1] = synth.smooth_features(1, C, N, 78)[0]              # an ordinary cloud (ratio 1.5) in the same batch
+    x[2] = synth.smooth_features(1, C, N, 79)[0] * 3.0 - 40.0  # very far: |x|^2 / Var ~ 1e3
     ref = orc.knn(x.numpy(), k)
     idx, st = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
     assert np.array_equal(_np(idx), ref)
     assert st["fallback_rows"] <= 0.02 * B * N, st
-    monkeypatch.setenv("MLSP_KT_MODE", "8")                    # bf16 heads for every cloud: still exact, via the fallback
-    idx8, st8 = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
-    assert np.array_equal(_np(idx8), ref)
-    assert st8["fallback_rows"] >= 0.1 * 2 * N, st8           # what the flag avoids
-    monkeypatch.setenv("MLSP_KT_MODE", "4")                    # three-term pass 1 for every cloud
-    idx4, st4 = M.knn(x.to(dev), k, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
-    assert np.array_equal(_np(idx4), ref) and st4["fallback_rows"] <= st["fallback_rows"]
+    feat = M.get_graph_feature(x.to(dev), None, k=k)           # the fused gather reads the UNCENTRED rows
+    assert np.array_equal(_np(feat.permute(0, 2, 3, 1)), orc.edge_gather(x.numpy(), ref))
 
 
 def test_lazy_graph_feature_fuses_reference_shaped_layers(dev):
