@@ -57,6 +57,9 @@ extern "C" {
 #define MLSP_KNN_AUTO 0        /* C=3: two-pass 3-D kernel; C in {64,128}: tcgen05 filter + exact re-rank; else streaming */
 #define MLSP_KNN_EXACT_ONLY 1  /* force the generic fp32 streaming-selection kernel (cross-check path)  */
 #define MLSP_KNN_TENSOR_ONLY 2 /* force the tcgen05 path (error if the shape does not allow it)  */
+#define MLSP_KNN_STATS 4       /* OR-ed in: the tcgen05 path maintains four int32 diagnostic counters at offset 0 of ws --
+                                  {rows re-done exactly, rows certified, total candidate-list length, exact distances recomputed};
+                                  off by default: one same-address atomic per row costs ~17 us per counter at 32 k rows */
 
 MLSP_API int mlsp_version(void);
 MLSP_API const char *mlsp_last_error(void);

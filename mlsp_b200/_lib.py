@@ -45,7 +45,7 @@ SIGNATURES = {
 }
 
 OP_KNN, OP_EDGE_FWD, OP_EDGE_BWD, OP_CHAMFER, OP_GRAPH_FEATURE, OP_EDGECONV_BWD = 1, 2, 3, 4, 5, 6
-KNN_AUTO, KNN_EXACT_ONLY, KNN_TENSOR_ONLY = 0, 1, 2
+KNN_AUTO, KNN_EXACT_ONLY, KNN_TENSOR_ONLY, KNN_STATS = 0, 1, 2, 4
 
 
 class MlspError(RuntimeError):

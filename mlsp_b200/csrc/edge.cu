@@ -27,7 +27,7 @@ bool knn3_supported(int C, int N, int k);
 int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, float *edge_out, cudaStream_t st);
 const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k);
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
-                   int stages_mask, cudaStream_t st, long long *tstamp = nullptr, int cluster = 0);
+                   int stages_mask, cudaStream_t st, long long *tstamp = nullptr, int cluster = 0, bool want_stats = false);
 
 size_t graph_feature_workspace_bytes(int B, int C, int N, int k)
 {

@@ -21,7 +21,7 @@ constexpr size_t KNN_WS_HEADER = 256;                     // stats live in the f
 bool knn_tensor_supported(int B, int C, int N, int k);
 size_t knn_tensor_workspace_bytes(int B, int C, int N, int k);
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out, int stages_mask,
-                   cudaStream_t st, long long *tstamp = nullptr, int cluster = 0);
+                   cudaStream_t st, long long *tstamp = nullptr, int cluster = 0, bool want_stats = false);
 bool knn3_supported(int C, int N, int k);
 int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, float *edge_out, cudaStream_t st);
 
@@ -193,9 +193,11 @@ extern "C" int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t 
     MLSP_REQUIRE(ws_bytes >= knn_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "knn: workspace too small");
     cudaStream_t st = as_stream(stream);
     const bool tensor_ok = knn_tensor_supported(B, C, N, k);
+    const bool want_stats = (flags & MLSP_KNN_STATS) != 0;
+    flags &= ~MLSP_KNN_STATS;
     MLSP_REQUIRE(flags != MLSP_KNN_TENSOR_ONLY || tensor_ok, MLSP_EUNSUPPORTED,
                  "knn: tensor path not available for B=%d C=%d N=%d k=%d", B, C, N, k);
-    if (tensor_ok && flags != MLSP_KNN_EXACT_ONLY) return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, nullptr, 7, st);
+    if (tensor_ok && flags != MLSP_KNN_EXACT_ONLY) return knn_tensor_run(x, B, C, N, k, idx, ws, nullptr, nullptr, 7, st, nullptr, 0, want_stats);
     if (flags != MLSP_KNN_EXACT_ONLY && knn3_supported(C, N, k)) return knn3_run(x, B, N, k, idx, static_cast<int *>(ws), nullptr, st);
     MLSP_CUDA(cudaMemsetAsync(ws, 0, KNN_WS_HEADER, st));
     float *xx = reinterpret_cast<float *>(static_cast<char *>(ws) + KNN_WS_HEADER);

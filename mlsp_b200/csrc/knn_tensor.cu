@@ -30,24 +30,30 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "topk.cuh"
 
 namespace mlsp {
 
 constexpr int KT_ROWS = 128;     // query rows per CTA   (UMMA M, TMEM lanes)
-constexpr int KT_COLS = 128;     // candidates per tile  (UMMA N, TMEM columns per accumulator buffer)
+constexpr int KT_COLS = 256;     // candidates per tile  (UMMA N, TMEM columns per accumulator buffer): at N = 128 an MMA
+                                 // retires in 64 clocks, about what its ISSUE costs the single issuing thread (measured: the
+                                 // issue section of a 5-MMA tile took 650 clocks) -- N = 256 makes the tensor pipe the bound
 constexpr int KT_KBLK = 64;      // bf16 per K block = one 128-byte swizzle span
 constexpr int KT_MAX_STAGES = 8;
 constexpr int KT_TPR = 4;        // epilogue threads per query row: each owns a 32-column quarter of every tile
 constexpr int KT_EPI_WARPS = 4 * KT_TPR;
 constexpr int KT_EPI_THREADS = 32 * KT_EPI_WARPS;
 constexpr int KT_THREADS = 64 + KT_EPI_THREADS;
-constexpr int KT_NBUF = 4;       // accumulator buffers: 4 x 128 columns = the whole TMEM of the SM
-constexpr uint32_t KT_BLK_BYTES = KT_COLS * KT_KBLK * 2;  // 16 KiB per (128 x 64) bf16 block
-constexpr uint32_t KT_NB_BYTES = KT_COLS * 16;            // 2 KiB: one K-group (8 bf16) of the norm operand per candidate
+constexpr int KT_NBUF = 2;       // accumulator buffers: 2 x 256 columns = the whole TMEM of the SM
+constexpr uint32_t KT_A_BYTES = KT_ROWS * KT_KBLK * 2;    // 16 KiB per (128 x 64) bf16 block of the resident A operand
+constexpr uint32_t KT_BLK_BYTES = KT_COLS * KT_KBLK * 2;  // 32 KiB per (256 x 64) bf16 candidate block
+constexpr uint32_t KT_NB_BYTES = KT_COLS * 16;            // 4 KiB: one K-group (8 bf16) of the norm operand per candidate
+constexpr uint32_t KT_ONES_BYTES = 2048 + KT_NB_BYTES;    // [ones: 128 rows x 16 B | zeros: the second K group of both norm operands]
 constexpr uint32_t KT_STAGE_BYTES = KT_BLK_BYTES + KT_NB_BYTES;
-constexpr int KT_MAX_TILES = 64; // snapshots in shared memory: N <= 8192
+constexpr int KT_MAX_TILES = 32; // snapshots in shared memory: N <= 8192
 // Error model of the filter value v~ = -2 acc against the specification value:
 //   |v~_ij - (row const_i) - (-spec_ij)| <= eps_ij = KT_EPS_REL |y_i||y_j| + KT_EPS_YY (|y_i|^2+|y_j|^2) + KT_RND(C) (|x_i|^2+|x_j|^2)
 // KT_EPS_REL: dropped lo.lo and split residuals 3*2^-16 on the dot product (Cauchy-Schwarz) = 9.2e-5 on v, the 5 mantissa
@@ -99,14 +105,46 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and complete_tx is signalled
-// on the mbarrier at the same offset in each of them
-__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t mask)
+// ---- CTA pair (cta_group::2): the two CTAs of a cluster run ONE MMA of M = 256 -- each holds its own 128 rows of A and
+// HALF of every B block (64 of the 128 candidates), so the operand stream every SM has to ingest halves.  Only the
+// leader (cluster rank 0) issues MMAs and owns the full / tm_empty barriers; addresses of its barriers come from mapa.
+__device__ __forceinline__ uint32_t mapa_rank0(const void *p)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+    return r;
+}
+// the box lands in THIS CTA's shared memory, complete_tx is signalled on the barrier `bar_cluster` (a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, int c0, int c1, uint32_t bar_cluster)
 {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster)
+{
+    // relaxed: the accumulator reads this orders are TMEM reads, fenced by tcgen05.fence::before_thread_sync; a release at
+    // cluster scope costs a full memory fence + L1 invalidation per arrive
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar)      // arrives on the barrier at this offset in BOTH CTAs
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
@@ -129,15 +167,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank()
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// the same arrive, delivered to the mbarrier at this offset in every CTA of `mask` (a stage shared by a cluster is free
-// only when every CTA's MMAs have read it)
-__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t mask)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"(mask)
-                 : "memory");
 }
 // One lane of a converged warp (warp-uniform predicate: code under it keeps its operands in uniform registers -- under a
 // plain `lane == 0` test the compiler wraps every tcgen05.mma / TMA instruction in an R2UR waterfall loop of ~20
@@ -205,6 +234,7 @@ __device__ __forceinline__ uint64_t umma_desc_plain(uint32_t saddr, uint32_t lbo
 }
 // kind::f16: D = f32, A = B = bf16, both K-major, N = 128, M = 128
 constexpr uint32_t KT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((KT_COLS >> 3) << 17) | ((KT_ROWS >> 4) << 24);
+constexpr uint32_t KT_IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((KT_COLS >> 3) << 17) | (((2 * KT_ROWS) >> 4) << 24);   // M = 256
 
 // ------------------------------------------------------------------------------------------- centre kernel
 // c (B,C) = mean of KT_CEN_SAMPLES points of every cloud, taken at a fixed stride over the cloud (a representative
@@ -376,9 +406,9 @@ __device__ __forceinline__ float pair_eps(float yyi, float yyj, float xxi, float
     return __fmaf_rn(KT_EPS_REL * sqrtf(yyi), sqrtf(yyj), __fmaf_rn(KT_EPS_YY, yyi + yyj, kt_rnd(C) * (xxi + xxj)));
 }
 
-// pass 2, one element: if (acc >= t) { *cur = (acc & ~31) | column; cur += step; } -- setp, lop3 (column as the immediate),
+// pass 2, one element: if (acc >= t) { *cur = (acc & ~63) | column; cur += step; } -- setp, lop3 (column as the immediate),
 // one predicated st.shared and one predicated add on a 32-bit shared-memory address; no branch, no vote, no atomics
-template <int COL>
+template <int COL, int BASE>
 __device__ __forceinline__ void collect_tile(uint32_t &cur, const uint32_t (&u)[32], float t, int step, uint32_t keep)
 {
     asm volatile(
@@ -388,9 +418,9 @@ __device__ __forceinline__ void collect_tile(uint32_t &cur, const uint32_t (&u)[
         "@p st.shared.b32 [%0], w;\n\t"
         "@p add.s32 %0, %0, %5;\n\t}"
         : "+r"(cur)
-        : "f"(__uint_as_float(u[COL])), "f"(t), "r"(u[COL]), "n"(COL), "r"(step), "r"(keep)
+        : "f"(__uint_as_float(u[COL])), "f"(t), "r"(u[COL]), "n"(BASE + COL), "r"(step), "r"(keep)
         : "memory");
-    if constexpr (COL + 1 < 32) collect_tile<COL + 1>(cur, u, t, step, keep);
+    if constexpr (COL + 1 < 32) collect_tile<COL + 1, BASE>(cur, u, t, step, keep);
 }
 
 struct KtParams {
@@ -400,7 +430,9 @@ struct KtParams {
     const float *xt;         // (B,N,C) fp32 point-major
     int64_t *idx;            // (B,N,k)
     int *fb_count;           // rows whose list overflowed (re-done with the exact streaming selection)
-    int *stats;              // rows certified by the tensor path
+    int *stats;              // [0] rows certified by the tensor path, [1] total list length, [2] exact distances recomputed
+    int want_stats;          // the four diagnostic counters are maintained only on request (MLSP_KNN_STATS): one same-address
+                             // atomic per row serialises in L2 -- 32 k rows cost ~17 us per counter
     uint32_t *cand;          // (B*N, capw) packed candidate words: filter value with the column (mod 32) in its 5 low bits
     uint8_t *cand_cnt;       // (B*N, 4) entries written by each column quarter; 255: overflowed
     uint8_t *snap;           // (B*N, 4, TP) cursor of each quarter after every candidate tile (padding 255)
@@ -411,16 +443,16 @@ struct KtParams {
     int TP;                  // T rounded up to a multiple of 8
     int stages;              // depth of the B-operand smem ring
     int capw;                // list words per row: 128 (k <= 32) or 192
-    int cs;                  // CTAs per cluster (1, 2 or 4 adjacent row blocks of a cloud) sharing every candidate block by TMA multicast
+    int cs;                  // 2: clusters of two CTAs (adjacent row blocks of a cloud) working as a tcgen05 CTA pair; 1: unpaired
 };
 
 // ------------------------------------------------------------------------------------------- filter kernel
 // shared memory: A (2*SEG blocks) | ring (STAGES x (16 KiB block + 2 KiB norm tile)) | ones (4 KiB) |
 //                lists [128][capw] (aliased: sorted class maxima [4][KX][128]) | snapshots [T][512] | thr [128] | red [32] | barriers
-__host__ __device__ inline size_t kt_smem_bytes(int C, int k, int T, int stages)
+__host__ __device__ inline size_t kt_smem_bytes(int C, int k, int T, int stages, int cs)
 {
     const int capw = k <= 32 ? 128 : 192;
-    return (size_t)(2 * C / KT_KBLK) * KT_BLK_BYTES + (size_t)stages * KT_STAGE_BYTES + 4096 + (size_t)KT_ROWS * capw * 4 +
+    return (size_t)(2 * C / KT_KBLK) * KT_A_BYTES + (size_t)stages * (KT_STAGE_BYTES / cs) + KT_ONES_BYTES + (size_t)KT_ROWS * capw * 4 +
            (size_t)T * KT_EPI_THREADS + KT_ROWS * 4 + 32 * 4 + 32 * 8 + 16 + 1024;
 }
 
@@ -433,19 +465,24 @@ __device__ __forceinline__ void kt_mark(const KtParams &P, int slot)
     }
 }
 
-template <int NGT>                                        // column classes per thread: 16 (k <= 32) or 32 (k <= 64)
+// NGT: column classes per thread: 16 (k <= 32) or 32 (k <= 64).  PAIR: launched in clusters of two CTAs working as a tcgen05
+// CTA pair (a kernel that contains cta_group::2 instructions cannot be launched without the cluster, hence two instances).
+template <int NGT, bool PAIR>
 __global__ void __launch_bounds__(KT_THREADS, 1)
 knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                   const __grid_constant__ CUtensorMap part_hi, const __grid_constant__ CUtensorMap part_lo,
                   const __grid_constant__ CUtensorMap map_nb, KtParams P)
 {
-    // P.cs > 1: the kernel was launched in clusters of P.cs CTAs = adjacent row blocks of one cloud.  They stream the same
-    // candidate blocks, so each CTA fetches 1/cs of every block (and of the norm tile) and TMA multicasts it into all of
-    // their shared memories: the per-SM TMA issue and the L2 -> SM operand traffic, which bound the MMA pipeline at these
-    // arithmetic intensities (2 x 128 MACs per operand byte), shrink by cs.
-    const int CS = P.cs;
-    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
-    const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+    // P.cs == 2: launched in clusters of two CTAs = two adjacent row blocks of one cloud, working as a CTA pair
+    // (tcgen05 cta_group::2): one MMA of M = 256 per instruction, each CTA holding its 128 rows of A and half of every
+    // candidate block.  The operand stream bounds this kernel (2 x 128 MACs per streamed byte; measured 19 B/clk/SM for
+    // the unpaired kernel whatever the ring depth, and TMA multicast did not change it): the pair halves it.
+    constexpr bool pair = PAIR;
+    const uint32_t crank = pair ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
+    const uint32_t BLK = pair ? KT_BLK_BYTES / 2 : KT_BLK_BYTES;    // this CTA's part of a candidate block
+    const uint32_t NBB = pair ? KT_NB_BYTES / 2 : KT_NB_BYTES;      // ... and of its norm tile
+    const uint32_t STG = BLK + NBB;
     extern __shared__ uint8_t smem_dyn[];
     uint8_t *smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);   // swizzle atoms need 1 KiB alignment
     const int SEG = P.C / KT_KBLK;          // K blocks per hi / lo segment (1 or 2)
@@ -454,9 +491,9 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     const int CAPW = P.capw, HC = CAPW / 2;
     const int KX = min(P.k, NGT);
     uint8_t *sA = smem_raw;                                   // [hi blocks | lo blocks], resident
-    uint8_t *sB = sA + (size_t)KB * KT_BLK_BYTES;             // ring: STAGES x (block | norm tile)
-    uint8_t *sOnes = sB + (size_t)STAGES * KT_STAGE_BYTES;    // [K group 0: rows of (1,1,1,0,...) | K group 1: zeros]
-    uint32_t *lists = reinterpret_cast<uint32_t *>(sOnes + 4096);
+    uint8_t *sB = sA + (size_t)KB * KT_A_BYTES;               // ring: STAGES x (block | norm tile)
+    uint8_t *sOnes = sB + (size_t)STAGES * (PAIR ? KT_STAGE_BYTES / 2 : KT_STAGE_BYTES);   // [K group 0: rows of (1,1,1,0,...) | K group 1: zeros]
+    uint32_t *lists = reinterpret_cast<uint32_t *>(sOnes + KT_ONES_BYTES);
     float *xchg = reinterpret_cast<float *>(lists);           // between the passes only
     uint8_t *snap_s = reinterpret_cast<uint8_t *>(lists + (size_t)KT_ROWS * CAPW);
     float *thr_s = reinterpret_cast<float *>(snap_s + (((size_t)P.T * KT_EPI_THREADS + 15) & ~(size_t)15));
@@ -482,25 +519,30 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     if (threadIdx.x == 0) {
         for (int s = 0; s < KT_MAX_STAGES; ++s) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, (uint32_t)CS);                   // one commit-arrive from every CTA of the cluster
+            mbar_init(empty + s, 1);
         }
         mbar_init(a_full, 1);
         for (int s = 0; s < KT_NBUF; ++s) {
             mbar_init(tm_full + s, 1);
-            mbar_init(tm_empty + s, KT_EPI_WARPS);
+            mbar_init(tm_empty + s, pair ? 2 * KT_EPI_WARPS : KT_EPI_WARPS);   // pair: both CTAs' epilogues release the leader's buffer
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tma_prefetch_desc(&map_hi);
         tma_prefetch_desc(&map_lo);
-        tma_prefetch_desc(CS > 1 ? &part_hi : &map_nb);
+        tma_prefetch_desc(pair ? &part_hi : &map_nb);
     }
-    if (CS > 1) cluster_sync_all();                                 // the peers' barriers exist before anything signals them
+    if (pair) cluster_sync_all();                                 // the peers' barriers exist before anything signals them
     else __syncthreads();
     // From here the TMA producer streams; the MMA warp allocates TMEM and the epilogue warps build the constant operand
     // and reduce the cloud's norms meanwhile; those 17 warps meet at setup_bar_sync.
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (pair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
         tc_fence_before();
         setup_bar_sync();
         tc_fence_after();
@@ -513,12 +555,16 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             xxi = P.xx[(size_t)rowbase + ii];
             yyi = P.yy[(size_t)rowbase + ii];
         }
-        if (et < 256) {                                       // the constant A operand of the norm MMA
+        if (et < (int)(KT_ONES_BYTES / 16)) {                 // the constant A operand of the norm MMA + the zero K group
             const uint4 one = make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u);   // bf16 (1, 1, 1, 0, 0, 0, 0, 0)
             reinterpret_cast<uint4 *>(sOnes)[et] = (et < KT_ROWS) ? one : make_uint4(0u, 0u, 0u, 0u);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // visible to the tensor core's reads
         }
-        // maxima of the cloud's norms: the row-level error bounds of the threshold
+        tc_fence_before();
+        setup_bar_sync();
+        tc_fence_after();
+        // maxima of the cloud's norms (the row-level error bounds of the threshold, read after pass 1): their loads hide
+        // behind the wait for the first accumulator
         float mx = 0.0f, my = 0.0f;
         for (int j = et; j < N; j += KT_EPI_THREADS) {
             mx = fmaxf(mx, P.xx[(size_t)rowbase + j]);
@@ -530,41 +576,43 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             red_s[warp - 2] = mx;
             red_s[16 + warp - 2] = my;
         }
-        tc_fence_before();
-        setup_bar_sync();
-        tc_fence_after();
     }
     const uint32_t tmem_base = (warp >= 1) ? *tmem_slot : 0u;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        // the whole warp runs the loop (waits included); one elected lane issues
+        // the whole warp runs the loop (waits included); one elected lane issues.  Pair: both CTAs load their own rows of
+        // A and their half of every candidate block; every complete_tx goes to the LEADER's barrier, which expects both.
+        const uint32_t a_full_c = pair ? mapa_rank0(a_full) : 0u;
         if (elect_one()) {
-            mbar_expect_tx(a_full, (uint32_t)KB * KT_BLK_BYTES);
-            for (int kb = 0; kb < KB; ++kb)          // A = [hi | lo]
-                tma_load_2d(sA + (size_t)kb * KT_BLK_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
-                            rowbase + i0, a_full);
+            if (leader) mbar_expect_tx(a_full, (uint32_t)KB * KT_A_BYTES * (pair ? 2u : 1u));
+            for (int kb = 0; kb < KB; ++kb) {        // A = [hi | lo]
+                if constexpr (pair)
+                    tma_load_2d_pair(sA + (size_t)kb * KT_A_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
+                                     rowbase + i0, a_full_c);
+                else
+                    tma_load_2d(sA + (size_t)kb * KT_A_BYTES, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK,
+                                rowbase + i0, a_full);
+            }
         }
         int stage = 0;
         uint32_t ph = 0;
         for (int g = 0; g < 2 * T; ++g) {
-            const int j0 = (g % T) * KT_COLS;
+            const int j0 = (g % T) * KT_COLS + (int)crank * (KT_COLS / 2);   // pair: my half of the tile's candidates
             const int nkb = (g < T) ? SEG : KB;                 // pass 1 multiplies hi.hi only: no lo blocks
             for (int kb = 0; kb < nkb; ++kb) {                  // B blocks: hi ..., lo ...
-                uint8_t *st = sB + (size_t)stage * KT_STAGE_BYTES;
+                uint8_t *st = sB + (size_t)stage * STG;
                 mbar_wait(empty + stage, ph ^ 1);
+                const uint32_t full_c = pair ? mapa_rank0(full + stage) : 0u;
                 if (elect_one()) {
-                    mbar_expect_tx(full + stage, KT_BLK_BYTES + (kb == 0 ? KT_NB_BYTES : 0u));
-                    if (CS > 1) {                               // my 1/cs of the block's rows, into every CTA of the cluster
-                        const int rows = KT_COLS / CS;
-                        tma_load_2d_mc(st + (size_t)crank * rows * 128, kb < SEG ? &part_hi : &part_lo, (kb % SEG) * KT_KBLK,
-                                       rowbase + j0 + (int)crank * rows, full + stage, cmask);
-                        if (kb == 0)
-                            tma_load_2d_mc(st + KT_BLK_BYTES + (size_t)crank * rows * 16, &map_nb, 0, rowbase + j0 + (int)crank * rows,
-                                           full + stage, cmask);
+                    const bool nbt = kb == 0;
+                    if (leader) mbar_expect_tx(full + stage, (BLK + (nbt ? NBB : 0u)) * (pair ? 2u : 1u));
+                    if constexpr (pair) {
+                        tma_load_2d_pair(st, kb < SEG ? &part_hi : &part_lo, (kb % SEG) * KT_KBLK, rowbase + j0, full_c);
+                        if (nbt) tma_load_2d_pair(st + BLK, &map_nb, 0, rowbase + j0, full_c);
                     } else {
-                        tma_load_2d(st, kb < SEG ? &map_hi : &map_lo, (kb % SEG) * KT_KBLK, rowbase + j0, full + stage);
-                        if (kb == 0) tma_load_2d(st + KT_BLK_BYTES, &map_nb, 0, rowbase + j0, full + stage);   // the tile's norm operand
+                        tma_load_2d(st, kb < SEG ? &part_hi : &part_lo, (kb % SEG) * KT_KBLK, rowbase + j0, full + stage);
+                        if (nbt) tma_load_2d(st + BLK, &map_nb, 0, rowbase + j0, full + stage);   // the tile's norm operand
                     }
                 }
                 __syncwarp();
@@ -573,48 +621,63 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        // the whole warp runs the loop; one elected lane issues the tcgen05 instructions
-        mbar_wait(a_full, 0);
-        const uint32_t ones_addr = smem_u32(sOnes);
-        const uint64_t da_ones = umma_desc_plain(ones_addr, 2048u, 128u);
-        int stage = 0;
-        uint32_t ph = 0;
-        for (int g = 0; g < 2 * T; ++g) {
-            const int buf = g & (KT_NBUF - 1);
-            mbar_wait(tm_empty + buf, ((g / KT_NBUF) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d = tmem_base + (uint32_t)buf * KT_COLS;
-            const bool first = g < T;                           // pass 1: dot~ = hi.hi (a looser, cheaper bound)
-            const int nkb = first ? SEG : KB;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(full + stage, ph);
+        // the whole warp runs the loop; one elected lane issues the tcgen05 instructions (pair: the leader's warp only)
+        if (leader) {
+            mbar_wait(a_full, 0);
+            const uint32_t ones_addr = smem_u32(sOnes);
+            const uint64_t da_ones = umma_desc_plain(ones_addr, 2048u, 128u);
+            const uint32_t idesc = pair ? KT_IDESC_PAIR : KT_IDESC;
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int g = 0; g < 2 * T; ++g) {
+                const int buf = g & (KT_NBUF - 1);
+                mbar_wait(tm_empty + buf, ((g / KT_NBUF) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t st_addr = smem_u32(sB + (size_t)stage * KT_STAGE_BYTES);
-                const uint64_t db = umma_desc_sw128(st_addr);
-                const int ka = kb % SEG;                        // matching K block of A
-                const uint64_t da_hi = umma_desc_sw128(smem_u32(sA + (size_t)ka * KT_BLK_BYTES));
-                const uint64_t da_lo = umma_desc_sw128(smem_u32(sA + (size_t)(SEG + ka) * KT_BLK_BYTES));
-                if (elect_one()) {
-                    if (kb == 0) {
-                        // acc = ones . norms^T = -t_j / 2 in every row: K group 0 of B is the tile the TMA just wrote,
-                        // K group 1 is the zero half of the ones block (its A counterpart is zero as well)
-                        const uint32_t nb_addr = st_addr + KT_BLK_BYTES;
-                        tc_mma_bf16(d, da_ones, umma_desc_plain(nb_addr, ones_addr + 2048u - nb_addr, 128u), KT_IDESC, 0u);
-                    }
+                const uint32_t d = tmem_base + (uint32_t)buf * KT_COLS;
+                const bool first = g < T;                           // pass 1: dot~ = hi.hi (a looser, cheaper bound)
+                const int nkb = first ? SEG : KB;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(full + stage, ph);
+                    tc_fence_after();
+                    const uint32_t st_addr = smem_u32(sB + (size_t)stage * STG);
+                    const uint64_t db = umma_desc_sw128(st_addr);
+                    const int ka = kb % SEG;                        // matching K block of A
+                    const uint64_t da_hi = umma_desc_sw128(smem_u32(sA + (size_t)ka * KT_A_BYTES));
+                    const uint64_t da_lo = umma_desc_sw128(smem_u32(sA + (size_t)(SEG + ka) * KT_A_BYTES));
+                    // acc = ones . norms^T = -t_j / 2 in every row: K group 0 of B is the tile the TMA just wrote,
+                    // K group 1 is the zero half of the ones block (its A counterpart is zero as well)
+                    const uint32_t nb_addr = st_addr + BLK;
+                    const uint64_t db_nb = umma_desc_plain(nb_addr, ones_addr + 2048u - nb_addr, 128u);
+                    if (elect_one()) {
+                        if constexpr (pair) {
+                            if (kb == 0) tc_mma_bf16_pair(d, da_ones, db_nb, idesc, 0u);
 #pragma unroll
-                    for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)   // +32 bytes per K=16 step inside the swizzle span
-                        tc_mma_bf16(d, da_hi + 2 * k16, db + 2 * k16, KT_IDESC, 1u);   // hi.hi | hi.lo
-                    if (kb < SEG && !first) {                   // pass 2: a B_hi block also meets A_lo:  lo.hi
+                            for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)
+                                tc_mma_bf16_pair(d, da_hi + 2 * k16, db + 2 * k16, idesc, 1u);
+                            if (kb < SEG && !first) {
 #pragma unroll
-                        for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)
-                            tc_mma_bf16(d, da_lo + 2 * k16, db + 2 * k16, KT_IDESC, 1u);
+                                for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)
+                                    tc_mma_bf16_pair(d, da_lo + 2 * k16, db + 2 * k16, idesc, 1u);
+                            }
+                            tc_commit_pair(empty + stage);              // both CTAs' producers may refill the stage
+                            if (kb == nkb - 1) tc_commit_pair(tm_full + buf);   // both CTAs' epilogues may read tile g
+                        } else {
+                            if (kb == 0) tc_mma_bf16(d, da_ones, db_nb, idesc, 0u);
+#pragma unroll
+                            for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)   // +32 bytes per K=16 step inside the swizzle span
+                                tc_mma_bf16(d, da_hi + 2 * k16, db + 2 * k16, idesc, 1u);   // hi.hi | hi.lo
+                            if (kb < SEG && !first) {                   // pass 2: a B_hi block also meets A_lo:  lo.hi
+#pragma unroll
+                                for (int k16 = 0; k16 < KT_KBLK / 16; ++k16)
+                                    tc_mma_bf16(d, da_lo + 2 * k16, db + 2 * k16, idesc, 1u);
+                            }
+                            tc_commit(empty + stage);                   // smem stage reusable when these MMAs retire
+                            if (kb == nkb - 1) tc_commit(tm_full + buf);    // accumulator of tile g complete
+                        }
                     }
-                    if (CS > 1) tc_commit_mc(empty + stage, cmask);   // stage reusable when EVERY CTA's MMAs on it retired
-                    else tc_commit(empty + stage);                  // smem stage reusable when these MMAs retire
-                    if (kb == nkb - 1) tc_commit(tm_full + buf);    // accumulator of tile g complete
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; ph ^= 1; }
             }
         }
     } else {
@@ -625,38 +688,53 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         const int r = q * 32 + lane;             // row within the tile
         const int i = i0 + r;
         const int et = threadIdx.x - 64;         // 0..511 among the epilogue threads
-        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 32;
-        const int last_valid = N - (T - 1) * KT_COLS - h * 32;    // valid columns of this quarter in the last tile
-        const bool ragged = last_valid < 32;
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 64;
+        const int last_valid = N - (T - 1) * KT_COLS - h * 64;    // valid columns of this quarter in the last tile
+        const bool ragged = last_valid < 64;
         const float shift = (P.dump && i < N) ? P.ss[(size_t)rowbase + i] : 0.0f;
+        const uint32_t tm_empty_c = pair ? mapa_rank0(tm_empty) : 0u;   // pair: the LEADER's buffer-free barriers
         float gmax[NGT];
 #pragma unroll
         for (int e = 0; e < NGT; ++e) gmax[e] = -INFINITY;
         if (et == 0) kt_mark(P, 1);
 
-        // ---- pass 1: class maxima of acc = hi.hi - t_j/2
-        for (int g = 0; g < T; ++g) {
+        // A thread owns 64 columns of every tile: two tcgen05.ld of 32 columns.  With 16 classes per thread (k <= 32) both
+        // are in flight before the wait (tcgen05.wait::ld waits for all of a thread's loads anyway); with 32 classes the
+        // registers only allow one at a time.
+        constexpr bool BOTH = false;
+        auto release = [&](int g) {                                  // the accumulator is in registers: free the buffer
             const int buf = g & (KT_NBUF - 1);
-            uint32_t u[32];
-            mbar_wait(tm_full + buf, (g / KT_NBUF) & 1);
-            tc_fence_after();
-            if (et == 0 && g == 0) kt_mark(P, 2);
-            tc_ld32_issue(tlane + (uint32_t)buf * KT_COLS, u);
-            tc_wait32(u);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tm_empty + buf);             // the accumulator is in registers: free the buffer
-            if (ragged && g == T - 1) {
+            if (lane == 0) {
+                if constexpr (pair) mbar_arrive_cluster(tm_empty_c + 8u * (uint32_t)buf);
+                else mbar_arrive(tm_empty + buf);
+            }
+        };
+        auto ready = [&](int g) {
+            const int buf = g & (KT_NBUF - 1);
+            mbar_wait(tm_full + buf, (g / KT_NBUF) & 1);
+            tc_fence_after();
+        };
+        auto load = [&](int g, int half, uint32_t (&u)[32]) {
+            tc_ld32_issue(tlane + (uint32_t)(g & (KT_NBUF - 1)) * KT_COLS + (uint32_t)half * 32, u);
+        };
+        auto mask_and_dump = [&](int g, int half, uint32_t (&u)[32]) {   // g: tile index over both passes
+            const int tile = g % T;
+            if (ragged && tile == T - 1) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                    if (c >= last_valid) u[c] = 0xff800000u;        // columns beyond the cloud: -inf
+                    if (half * 32 + c >= last_valid) u[c] = 0xff800000u;   // columns beyond the cloud: -inf
             }
             if (P.dump && i < N) {
-                float *drow = P.dump + ((size_t)rowbase + i) * N + (size_t)g * KT_COLS + h * 32;
+                const int j0 = tile * KT_COLS + h * 64 + half * 32;
+                float *drow = P.dump + ((size_t)(g / T) * gridDim.y * N + rowbase + i) * N + j0;
 #pragma unroll
                 for (int c = 0; c < 32; ++c)
-                    if (g * KT_COLS + h * 32 + c < N) drow[c] = __fmaf_rn(-2.0f, __uint_as_float(u[c]), -shift);
+                    if (j0 + c < N) drow[c] = __fmaf_rn(-2.0f, __uint_as_float(u[c]), -shift);
             }
+        };
+        auto classes = [&](const uint32_t (&u)[32]) {
             if (NGT == 16) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
@@ -664,6 +742,34 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
             } else {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) gmax[c % NGT] = fmaxf(gmax[c % NGT], __uint_as_float(u[c]));
+            }
+        };
+
+        // ---- pass 1: class maxima of acc = hi.hi - t_j/2
+        for (int g = 0; g < T; ++g) {
+            uint32_t ua[32];
+            ready(g);
+            if (et == 0 && g == 0) kt_mark(P, 2);
+            load(g, 0, ua);
+            if constexpr (BOTH) {
+                uint32_t ub[32];
+                load(g, 1, ub);
+                tc_wait32(ua);
+                tc_wait32(ub);
+                release(g);
+                mask_and_dump(g, 0, ua);
+                classes(ua);
+                mask_and_dump(g, 1, ub);
+                classes(ub);
+            } else {
+                tc_wait32(ua);
+                mask_and_dump(g, 0, ua);
+                classes(ua);
+                load(g, 1, ua);
+                tc_wait32(ua);
+                release(g);
+                mask_and_dump(g, 1, ua);
+                classes(ua);
             }
         }
         // ---- between the passes: the row has 4 NGT class maxima (NGT per thread); tau = their k-th largest.  Every thread
@@ -724,38 +830,43 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         // the row's words (0 from the front, 1 from the back), quarters 2/3 the second half.
         // all ones above bit 4; kept opaque to the compiler so that it stays in a register and the COLUMN is the immediate of
         // the packing LOP3 (the other way round costs a MOV per element)
-        const uint32_t keep = 0xffffffe0u | ((uint32_t)N >> 31);
+        const uint32_t keep = 0xffffffc0u | ((uint32_t)N >> 31);
         const uint32_t cur0 = smem_u32(lists + (size_t)r * CAPW + (h >> 1) * HC + ((h & 1) ? HC - 1 : 0));
         const int step = (h & 1) ? -4 : 4;
         uint32_t cur = cur0;
         bool ovf = false;
-        for (int g = T; g < 2 * T; ++g) {
-            const int buf = g & (KT_NBUF - 1);
-            uint32_t u[32];
-            mbar_wait(tm_full + buf, (g / KT_NBUF) & 1);
-            tc_fence_after();
-            tc_ld32_issue(tlane + (uint32_t)buf * KT_COLS, u);
-            tc_wait32(u);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tm_empty + buf);
-            if (ragged && g == 2 * T - 1) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if (c >= last_valid) u[c] = 0xff800000u;
-            }
-            if (P.dump && i < N) {
-                float *drow = P.dump + ((size_t)gridDim.y * N + rowbase + i) * N + (size_t)(g - T) * KT_COLS + h * 32;
-#pragma unroll
-                for (int c = 0; c < 32; ++c)
-                    if ((g - T) * KT_COLS + h * 32 + c < N) drow[c] = __fmaf_rn(-2.0f, __uint_as_float(u[c]), -shift);
-            }
-            // a tile can add 32 entries: without room for them nothing is stored any more and the row is flagged
+        auto collect = [&](auto half_tag, const uint32_t (&u)[32]) {
+            // a half tile can add 32 entries: without room for them nothing is stored any more and the row is flagged
             const int cnt = abs((int)(cur - cur0)) >> 2;
             const bool room = cnt <= HC - 32;
             ovf |= !room;
             const float t = room ? thr : INFINITY;
-            collect_tile<0>(cur, u, t, step, keep);
+            collect_tile<0, decltype(half_tag)::value * 32>(cur, u, t, step, keep);
+        };
+        for (int g = T; g < 2 * T; ++g) {
+            uint32_t ua[32];
+            ready(g);
+            load(g, 0, ua);
+            if constexpr (BOTH) {
+                uint32_t ub[32];
+                load(g, 1, ub);
+                tc_wait32(ua);
+                tc_wait32(ub);
+                release(g);
+                mask_and_dump(g, 0, ua);
+                collect(std::integral_constant<int, 0>{}, ua);
+                mask_and_dump(g, 1, ub);
+                collect(std::integral_constant<int, 1>{}, ub);
+            } else {
+                tc_wait32(ua);
+                mask_and_dump(g, 0, ua);
+                collect(std::integral_constant<int, 0>{}, ua);
+                load(g, 1, ua);
+                tc_wait32(ua);
+                release(g);
+                mask_and_dump(g, 1, ua);
+                collect(std::integral_constant<int, 1>{}, ua);
+            }
             snap_s[(size_t)(g - T) * KT_EPI_THREADS + et] = (uint8_t)(abs((int)(cur - cur0)) >> 2);
         }
         const int cnt_end = abs((int)(cur - cur0)) >> 2;
@@ -778,21 +889,26 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's list words, for the TMA engine
         epi_bar_sync();                                             // every list of the CTA is complete
+        if (et == 0) kt_mark(P, 8);
         if (et == 0) {
-            kt_mark(P, 8);
-            // one bulk copy of the CTA's lists (contiguous in global memory: rows i0 .. of the cloud) by the TMA engine
+            // one bulk copy of the CTA's lists (contiguous in global memory: rows i0 .. of the cloud) by the TMA engine.
+            // Compacting first was measured and dropped: scattered or per-row stores cost 2.3 - 3.4 us against 1.3 us for
+            // this L2 write burst of 64 KiB per CTA.
             const int rows_valid = min(KT_ROWS, N - i0);
-            bulk_store(P.cand + ((size_t)rowbase + i0) * CAPW, lists, (uint32_t)rows_valid * CAPW * 4u);
-            bulk_store_wait();                                      // shared memory is released when the CTA exits
+            if (rows_valid > 0) {
+                bulk_store(P.cand + ((size_t)rowbase + i0) * CAPW, lists, (uint32_t)rows_valid * CAPW * 4u);
+                bulk_store_wait();                                  // shared memory is released when the CTA exits
+            }
         }
         if (et == 0) kt_mark(P, 9);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (CS > 1) cluster_sync_all();          // no CTA leaves while a peer can still signal its barriers / write its smem
+    if (pair) cluster_sync_all();            // no CTA leaves while its peer can still signal its barriers / read its smem
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if constexpr (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -874,6 +990,7 @@ __device__ __forceinline__ void refine_sorted(const KtParams &P, uint32_t row, u
         need[s] = __ballot_sync(MLSP_FULL, amb[s]);
         total += __popc(need[s]);
     }
+    if (P.want_stats && total && lane == 0) atomicAdd(P.stats + 2, total);   // diagnostics: exact distances recomputed
     if (total) {                                                         // warp-uniform
         // compact the amb entries: rank -> candidate index in shared memory, eight per pass, results back by rank
         int rank[S], off = 0;
@@ -1058,7 +1175,7 @@ knn_refine_kernel(KtParams P, long long total_rows)
     uint32_t nbr[KS];
     if (c0 == 255 || c1 == 255 || c2 == 255 || c3 == 255 || c0 + c1 > HC || c2 + c3 > HC || cnt > 32 * SLOTS || cnt < P.k) {
         knn_row_exact<KS>(P.xt, P.xx, row64, P.N, C, P.k, P.idx);        // warp-uniform
-        if (lane == 0) atomicAdd(P.fb_count, 1);
+        if (P.want_stats && lane == 0) atomicAdd(P.fb_count, 1);
         if (P.edge_out) {
             __syncwarp();                                  // the row's idx, written by this warp, is visible to it
 #pragma unroll
@@ -1087,8 +1204,8 @@ knn_refine_kernel(KtParams P, long long total_rows)
             const uint32_t pp = (uint32_t)p * 0x01010101u;
             int tile = 0;
             for (int t = 0; t < TQ; ++t) tile += __popc(__vcmpleu4(sn[seg * TQ + t], pp)) >> 3;
-            const uint32_t j = (uint32_t)tile * KT_COLS + (uint32_t)seg * 32u + (w & 31u);
-            const float vf = __fmul_rn(-2.0f, __uint_as_float(w & 0xffffffe0u));   // v~ = -2 acc (row constant dropped)
+            const uint32_t j = (uint32_t)tile * KT_COLS + (uint32_t)seg * 64u + (w & 63u);
+            const float vf = __fmul_rn(-2.0f, __uint_as_float(w & 0xffffffc0u));   // v~ = -2 acc (row constant dropped)
             key[s] = ((unsigned long long)f32_orderable(__fadd_rn(vf, 0.0f)) << 32) | j;
             xxj[s] = P.xx[base + j];                       // consumed after the sort
             yyj[s] = P.yy[base + j];
@@ -1105,7 +1222,7 @@ knn_refine_kernel(KtParams P, long long total_rows)
     } else {
         refine_sorted<SLOTS, C, KS>(P, row, base, key, xxj, yyj, sj, se, nbr);
     }
-    if (lane == 0) {
+    if (P.want_stats && lane == 0) {
         atomicAdd(P.stats, 1);
         atomicAdd(P.stats + 1, cnt);                       // diagnostics: total length of the certified rows' lists
     }
@@ -1178,13 +1295,13 @@ static KtLayout kt_layout(int B, int C, int N, int k)
 }
 
 // ring depth: as deep as the 227 KiB of one SM allow (one CTA per SM)
-static int kt_stages(int C, int k, int N)
+static int kt_stages(int C, int k, int N, int cs)
 {
     const int T = (N + KT_COLS - 1) / KT_COLS;
     const size_t per_sm = 227 * 1024;
     int stages = 0;
     for (int s_ = 2; s_ <= KT_MAX_STAGES; ++s_)
-        if (kt_smem_bytes(C, k, T, s_) <= per_sm) stages = s_;
+        if (kt_smem_bytes(C, k, T, s_, cs) <= per_sm) stages = s_;
     return stages;
 }
 
@@ -1194,7 +1311,7 @@ static int kt_stages(int C, int k, int N)
 bool knn_tensor_supported(int B, int C, int N, int k)
 {
     return (C == 64 || C == 128) && N >= 256 && N <= KT_MAX_TILES * KT_COLS && k >= 1 && k <= 64 && (long long)B * N < (1ll << 31) &&
-           B <= 65535 && kt_stages(C, k, N) >= 2;
+           B <= 65535 && kt_stages(C, k, N, 2) >= 2;
 }
 
 size_t knn_tensor_workspace_bytes(int B, int C, int N, int k) { return kt_layout(B, C, N, k).total; }
@@ -1207,7 +1324,7 @@ const float *knn_tensor_xt(const void *ws, int B, int C, int N, int k)
 
 // `stages_mask` (measurement hook of mlsp_graph_feature_fwd_stage): bit 0 prep, bit 1 filter, bit 2 ranking (+ gather); 7 = all
 int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, void *ws, float *dump, float *edge_out,
-                   int stages_mask, cudaStream_t st, long long *tstamp, int cluster)
+                   int stages_mask, cudaStream_t st, long long *tstamp, int cluster, bool want_stats)
 {
     const KtLayout L = kt_layout(B, C, N, k);
     char *w = static_cast<char *>(ws);
@@ -1229,13 +1346,15 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
         MLSP_LAUNCH_CHECK("knn_prep_kernel");
     }
 
-    dim3 grid((N + KT_ROWS - 1) / KT_ROWS, B);
-    // clusters of 4 (2) adjacent row blocks of a cloud share every candidate block by TMA multicast
-    const int cs = (cluster <= 0) ? ((grid.x % 2 == 0) ? 2 : 1) : ((cluster > 1 && grid.x % cluster == 0) ? cluster : 1);
+    // CTA pairs (cta_group::2); an odd number of row blocks per cloud gets a trailing CTA without valid rows, which still
+    // fetches its half of every candidate block.  `cluster` = 1 (profiling hook) forces the unpaired kernel.
+    const int cs = (cluster == 1) ? 1 : 2;
+    const unsigned rblk = (unsigned)((N + KT_ROWS - 1) / KT_ROWS);
+    dim3 grid(cs == 2 ? (rblk + 1) / 2 * 2 : rblk, B);
     CUtensorMap map_hi, map_lo, part_hi, part_lo, map_nb;  // boxes of 128 rows (A tiles, unshared B blocks) and of 128 / cs rows
-    int rc = make_map(&map_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_COLS, true);
+    int rc = make_map(&map_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_ROWS, true);
     if (rc) return rc;
-    rc = make_map(&map_lo, lo, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_COLS, true);
+    rc = make_map(&map_lo, lo, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_ROWS, true);
     if (rc) return rc;
     rc = make_map(&part_hi, hi, (uint64_t)B * N, (uint64_t)C, KT_KBLK, KT_COLS / cs, true);
     if (rc) return rc;
@@ -1249,12 +1368,13 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     P.cand = reinterpret_cast<uint32_t *>(w + L.off_cand);
     P.cand_cnt = reinterpret_cast<uint8_t *>(w + L.off_cnt);
     P.snap = reinterpret_cast<uint8_t *>(w + L.off_snap);
+    P.want_stats = (want_stats || dump) ? 1 : 0;
     P.dump = dump; P.tstamp = tstamp; P.edge_out = reinterpret_cast<float4 *>(edge_out);
     P.N = N; P.C = C; P.k = k; P.T = (N + KT_COLS - 1) / KT_COLS; P.TP = L.TP; P.capw = L.capw;
-    P.stages = kt_stages(C, k, N);
+    P.stages = kt_stages(C, k, N, cs);
     MLSP_REQUIRE(P.stages >= 2, MLSP_EUNSUPPORTED, "knn: no shared-memory configuration for C=%d k=%d N=%d", C, k, N);
-    const size_t smem = kt_smem_bytes(C, k, P.T, P.stages);
     P.cs = cs;
+    const size_t smem = kt_smem_bytes(C, k, P.T, P.stages, cs);
     if (stages_mask & 2) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
@@ -1268,13 +1388,16 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (k <= 32) {
-            MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<16>, map_hi, map_lo, part_hi, part_lo, map_nb, P));
-        } else {
-            MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<32>, map_hi, map_lo, part_hi, part_lo, map_nb, P));
-        }
+#define MLSP_KT_LAUNCH(NGT_, PAIR_)                                                                                              \
+    do {                                                                                                                         \
+        MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<NGT_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        MLSP_CUDA(cudaLaunchKernelEx(&cfg, knn_tensor_kernel<NGT_, PAIR_>, map_hi, map_lo, part_hi, part_lo, map_nb, P));        \
+    } while (0)
+        if (k <= 32 && cs == 2) MLSP_KT_LAUNCH(16, true);
+        else if (k <= 32) MLSP_KT_LAUNCH(16, false);
+        else if (cs == 2) MLSP_KT_LAUNCH(32, true);
+        else MLSP_KT_LAUNCH(32, false);
+#undef MLSP_KT_LAUNCH
         MLSP_LAUNCH_CHECK("knn_tensor_kernel");
     }
     if (stages_mask & 4) {

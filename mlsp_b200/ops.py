@@ -72,10 +72,11 @@ def knn(x: torch.Tensor, k: int, flags: int = _lib.KNN_AUTO, return_stats: bool 
     idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
         ws = _workspace(_lib.OP_KNN, B, C, N, k, x.device)
-        _lib.call("mlsp_knn_f32", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(), flags, _stream(x.device))
+        _lib.call("mlsp_knn_f32", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(),
+                  flags | (_lib.KNN_STATS if return_stats else 0), _stream(x.device))
     if return_stats:
         c = ws[:16].view(torch.int32).cpu()
-        return idx, {"fallback_rows": int(c[0]), "certified_rows": int(c[1]), "candidates": int(c[2])}
+        return idx, {"fallback_rows": int(c[0]), "certified_rows": int(c[1]), "candidates": int(c[2]), "exact_recomputed": int(c[3])}
     return idx
 
 
