@@ -63,6 +63,7 @@ def main():
     # ---- PointDA layer: conv_2d(2C -> O, bias=False, leakyrelu) in training mode, then one more step in eval mode
     for name, C, O, N, k in (("edgeconv_da_16_32", 16, 32, 96, 8), ("edgeconv_da_3_64", 3, 64, 128, 20)):
         x = (synth.clouds(2, N, 5) if C == 3 else synth.smooth_features(2, C, N, 6)).requires_grad_(True)
+        torch.manual_seed(1000 + C * 131 + O)                                  # the Conv2d / BatchNorm2d init draws from the global RNG
         layer = da.conv_2d(2 * C, O, kernel=1, bias=False, activation="leakyrelu")
         conv, bn = layer.conv[0], layer.conv[1]
         with torch.no_grad():

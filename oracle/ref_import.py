@@ -2,7 +2,7 @@
 
 Only usable in the build container (where /root/reference is mounted); used by
 oracle/gen_golden.py to produce tests/golden/ and by the container-only cross-checks in
-tests/test_oracle_vs_reference.py (skipped when the reference is absent, e.g. on the GPU box).
+tests/test_oracle_vs_reference.py (regenerates and byte-compares every fixture; skipped when the reference is absent, e.g. on the GPU box).
 Third-party modules the reference imports but never reaches on the hot path are stubbed
 (SURVEY.md section 8c).
 """

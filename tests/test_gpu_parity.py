@@ -373,6 +373,33 @@ def test_ball_count_matches_oracle(dev, orc):
     assert np.array_equal(_np(M.ball_count(xq.to(dev))), orc.ball_count(xq.numpy()))
 
 
+# ------------------------------------------------------------------------------------------------ a6 / a7 vs independent code
+def test_cal_density_vs_ckdtree(dev):
+    """a6 on the device against scipy's cKDTree + the reference's label arithmetic (no code shared with the oracle): the rows
+    that differ sit within float32 rounding of the sphere and differ by one count (tests/test_unpinned_crosscheck.py)."""
+    from test_unpinned_crosscheck import ckdtree_density_rows
+    for B, N, radius, num_cls, pergroup, shift, K in [(8, 1024, 0.13, 16, 2, 0, 100), (4, 2048, 0.091, 16, 5, 10, 100)]:
+        pts = synth.surface_clouds(B, N, 21).permute(0, 2, 1).contiguous()
+        _, row = M.cal_density(pts.to(dev), radius, num_cls, pergroup, shift, K)
+        ref = ckdtree_density_rows(pts.numpy(), radius, num_cls, pergroup, shift, K)
+        got = _np(row)
+        assert float((got != ref).mean()) <= 2e-3 and int(np.abs(got - ref).max()) <= 1
+
+
+def test_normals_vs_pcl_style(dev):
+    """a7 on the device against pcl::NormalEstimation's documented algorithm (float32 single-pass covariance, kd-tree
+    neighbourhoods; no code shared with the oracle): same direction up to sign within what float32 covariance supports."""
+    from test_unpinned_crosscheck import pcl_style_normals
+    for B, N, near in [(8, 1024, 20), (4, 2048, 10)]:
+        pts = synth.surface_clouds(B, N, 22).permute(0, 2, 1).contiguous()
+        nrm = _np(M.estimate_normals(pts.to(dev), near)).astype(np.float64)
+        ref, gap = pcl_style_normals(pts.numpy(), near)
+        cos = np.abs((nrm * ref).sum(-1))
+        well = gap > 1e-2
+        assert float((1.0 - cos[well] <= 1e-3).mean()) >= 0.995
+        assert ((nrm * pts.numpy()).sum(-1) <= 1e-6).all()              # facing the origin, like pcl's default viewpoint
+
+
 # ------------------------------------------------------------------------------------------------ a6
 @pytest.mark.parametrize("B,N,radius,num_cls,pergroup,shift,K", [
     (32, 1024, 0.13, 16, 2, 0, 100), (16, 2048, 0.091, 16, 5, 10, 100), (2, 1500, 0.4, 16, 2, 0, 100),
