@@ -124,7 +124,7 @@ class _Span:
 
 # kernels launched per public-API call (counted from mlsp_b200/csrc: see DESIGN.md "launch inventory")
 LAUNCHES = {"fps": 1, "knn3": 1, "knn_tensor": 3, "edge_fwd_vec": 2, "edge_bwd_vec": 2, "edge_fwd3": 1,
-            "edge_bwd3": 2, "normals": 1 + 1, "density": 1, "deform": 2, "chamfer_fwd": 2, "chamfer_bwd": 1,
+            "edge_bwd3": 2, "normals": 1 + 1, "density": 1, "structure": 1, "deform": 2, "chamfer_fwd": 2, "chamfer_bwd": 1,
             # get_graph_feature(idx=None): the kernel that ranks a row writes its edge features (no gather launch)
             "ggf3": 1, "ggf_tensor": 3}
 
@@ -192,13 +192,11 @@ def gpu_step(M, dev, lookup, k, timer, streams, clouds=None):
             for n in FPS_SPLIT:
                 M.farthest_point_sample(None, clouds, n)
         pts = clouds.permute(0, 2, 1).contiguous()
-        with timer("pca_normals"):
-            M.estimate_normals(pts, NEAR)
-        with timer("cal_density"):
-            M.cal_density(pts, RADIUS, NUM_CLS, PERGROUP, SHIFT)
+        with timer("target_structure"):                  # normals + cardinality labels: one 3-D neighbourhood pass (8f rank 2)
+            M.target_structure(pts, NEAR, RADIUS, NUM_CLS, PERGROUP, SHIFT)
         built = torch.cuda.Event()
         built.record(st)
-    launches += LAUNCHES["deform"] + LAUNCHES["fps"] * len(FPS_SPLIT) + LAUNCHES["knn3"] + LAUNCHES["normals"] + LAUNCHES["density"]
+    launches += LAUNCHES["deform"] + LAUNCHES["fps"] * len(FPS_SPLIT) + LAUNCHES["structure"]
     # -- layer 1 (deformed cloud) and the position loss need the target stream's results
     sm.wait_event(deformed)
     launches += _layer(M, timer, X, dev["grads"][1], k)
@@ -252,10 +250,9 @@ class GraphedStep:
             for i, n in list(enumerate(FPS_SPLIT))[1:]:
                 M.fps_from_start(self.clouds, n, self.start_dev[i])
             pts = self.clouds.permute(0, 2, 1).contiguous()
-            M.estimate_normals(pts, NEAR)
-            M.cal_density(pts, RADIUS, NUM_CLS, PERGROUP, SHIFT)
+            M.target_structure(pts, NEAR, RADIUS, NUM_CLS, PERGROUP, SHIFT)
             cap.wait_stream(side)
-        self.launches += LAUNCHES["fps"] * len(FPS_SPLIT) + LAUNCHES["knn3"] + LAUNCHES["normals"] + LAUNCHES["density"]
+        self.launches += LAUNCHES["fps"] * len(FPS_SPLIT) + LAUNCHES["structure"]
         self.gB = torch.cuda.CUDAGraph()
         self.X.copy_(self.clouds)
         self.mask.fill_(1.0)
@@ -316,7 +313,7 @@ def op_profile(M, dev, lookup, k, reps, barrier):
         keep.append(idx)
         # calls per step: the DGCNN layers make the fused call (ggf_fwd); knn alone runs once, for the normals'
         # neighbourhoods (C = 3); the explicit-idx gather (edge_fwd) is not in the step -- both are timed for reference
-        add(f"knn_C{C}", lambda f=f: M.knn(f, k), 1 if C == 3 else 0)
+        add(f"knn_C{C}", lambda f=f: M.knn(f, k), 0)      # stand-alone kNN: not in the step (the normals' pass is target_structure)
         add(f"edge_fwd_C{C}", lambda f=f, idx=idx: M.get_graph_feature(f, None, k=k, idx=idx), 0)
         add(f"ggf_fwd_C{C}", lambda f=f: M.get_graph_feature(f, None, k=k), per_step[C])   # knn + gather in one call
         add(f"edge_bwd_C{C}", lambda idx=idx, g=grads[C], C=C: M.ops.edge_gather_backward(g, idx, C), per_step[C])  # autograd's call
@@ -331,8 +328,9 @@ def op_profile(M, dev, lookup, k, reps, barrier):
     add("fps", lambda: M.fps_from_start(clouds, FPS_SPLIT[0], start), len(FPS_SPLIT))
     pts = clouds.permute(0, 2, 1).contiguous()
     idx_n = M.knn(clouds, NEAR)
-    add("pca_normals", lambda: M.estimate_normals(pts, NEAR, idx=idx_n), 1)          # its kNN pass is counted in knn_C3
-    add("cal_density", lambda: M.cal_density(pts, RADIUS, NUM_CLS, PERGROUP, SHIFT), 1)
+    add("pca_normals", lambda: M.estimate_normals(pts, NEAR, idx=idx_n), 0)          # stand-alone ops, for comparison (not in the step)
+    add("cal_density", lambda: M.cal_density(pts, RADIUS, NUM_CLS, PERGROUP, SHIFT), 0)
+    add("target_structure", lambda: M.target_structure(pts, NEAR, RADIUS, NUM_CLS, PERGROUP, SHIFT), 1)   # knn3 + normals + cardinality, one launch
     X = clouds.clone()
     X, mask = M.deform_input(X, lookup, "volume_based_voxels", clouds.device)
     pred = dev["pred"]
@@ -376,6 +374,8 @@ def algorithmic_bytes(op, B, N, k):
     if op.startswith("knn_C"):
         C = int(op.split("_C")[1])
         return 4 * B * C * N + 8 * B * N * k
+    if op == "target_structure":                     # cloud in; normals + soft labels + counts out (a6 + a7)
+        return 12 * B * N + 12 * B * N + 4 * B * N * NUM_CLS + 8 * B * N
     return None
 
 
@@ -1130,8 +1130,7 @@ def main():
                 M.deform_input(dev["clouds"].clone(), lookup, mode, device)
                 for n_ in FPS_SPLIT:
                     M.farthest_point_sample(None, dev["clouds"], n_)
-                M.estimate_normals(pts_c, NEAR)
-                M.cal_density(pts_c, RADIUS, NUM_CLS, PERGROUP, SHIFT)
+                M.target_structure(pts_c, NEAR, RADIUS, NUM_CLS, PERGROUP, SHIFT)
             for _ in range(3):
                 tg()
             barrier()
@@ -1171,7 +1170,7 @@ def main():
         "knn_refine_kernel": ("hbm", [n for n in per_call_ms if n.startswith("k_rank_gather_C")]),
         "knn_tensor_kernel": ("tensor", [n for n in per_call_ms if n.startswith("k_filter_C")]),
         "edge_bwd_vec_kernel": ("hbm", [n for n in per_call_ms if n.startswith("edge_bwd_C") and n != "edge_bwd_C3"]),
-        "knn3_kernel": ("hbm", ["ggf_fwd_C3", "knn_C3"]),
+        "knn3_kernel": ("hbm", ["ggf_fwd_C3", "target_structure"]),
         "edge_bwd3_kernel": ("hbm", ["edge_bwd_C3"]),
     }
     fam_ms = {f: sum(per_call_ms[n] * launches_of[n] for n in ops) for f, (_, ops) in families.items() if ops}

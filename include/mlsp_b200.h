@@ -170,6 +170,17 @@ MLSP_API int mlsp_radius_search(const float *pts, int B, int N, float r2, int K,
 MLSP_API int mlsp_pca_normals(const float *pts, const int64_t *idx, int B, int N, int k, float *normals,
                               float *curvature, void *stream);
 
+/* SURVEY.md 8f rank 2 -- one 3-D neighbourhood pass for the target builder: what PointDA/trainer.py:524-536 computes on the
+ *   undeformed target batch -- kSearchNormalEstimation per cloud (a7) and mlsp.cal_density (a6) -- in ONE launch: the kernel
+ *   that ranks the `near` nearest neighbours of every point (a1, 3-D) counts the ball cardinality in the same pass over the
+ *   staged cloud and solves the 3x3 PCA from the ranked neighbourhood while it is in registers.  Same arithmetic and
+ *   results as mlsp_knn_f32 + mlsp_pca_normals + mlsp_ball_count_labels.
+ *   pts (B,N,3); normals (B,N,3); curvature (B,N) or NULL; labels (B,N,num_cls) + row (B,N) or both NULL (normals only);
+ *   idx (B,N,near) int64 or NULL (the neighbourhoods, e.g. for a later mlsp_edge_gather_fwd).  N <= 8192, near <= 64. */
+MLSP_API int mlsp_target_structure(const float *pts, int B, int N, int near, float r2, int K, int shift, int pergroup,
+                                   int num_cls, float *normals, float *curvature, float *labels, int64_t *row,
+                                   int64_t *idx, void *stream);
+
 /* a9/a10 -- chamfer_distance(p1,p2,mask) MLSP/mlsp.py:115-153 and findneareat_index :196-220, one direction.
  *   D[i][j] = (|p1_i - p2_j|_2)^2 + (mask_j == 0 ? 100 : 0); rowmin/argmin over j (lowest j on ties).
  *   Points are addressed p[b*bstride + i*pstride + c*cstride] so both (B,N,3) and (B,3,N) tensors are

@@ -25,6 +25,7 @@ from .ops import (  # noqa: F401
     radius_search,
     reconstruction_loss,
     region_mean,
+    target_structure,
 )
 
 __version__ = "0.1.0"

@@ -34,6 +34,7 @@ SIGNATURES = {
     "mlsp_ball_count_labels": [_P, _I, _I, _F, _I, _I, _I, _I, _P, _P, _P],
     "mlsp_radius_search": [_P, _I, _I, _F, _I, _P, _P, _P],
     "mlsp_pca_normals": [_P, _P, _I, _I, _I, _P, _P, _P],
+    "mlsp_target_structure": [_P, _I, _I, _I, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "mlsp_chamfer_dir_fwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _Z, _P],
     "mlsp_chamfer_dir_bwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _P, _I, _I, _P, _F, _P, _P, _P],
     "mlsp_reconstruction_loss_fwd": [_P, _L, _L, _L, _P, _L, _L, _L, _P, _L, _I, _I, _P, _P, _P, _Z, _P],

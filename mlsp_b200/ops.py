@@ -520,6 +520,39 @@ def estimate_normals(xyz: torch.Tensor, near: int = 20, return_curvature: bool =
     return (normals, curv) if return_curvature else normals
 
 
+# ----------------------------------------------------------------------------------------------- 8f rank 2
+def target_structure(batch_pts: torch.Tensor, near: int, radius: float, num_cls: int, pergroup: int = 2, shift: int = 0,
+                     K: int = 100, return_idx: bool = False, return_curvature: bool = False):
+    """The local-structure targets of the undeformed target batch in ONE launch: what
+    PointDA/trainer.py:524-536 computes with a per-cloud python-pcl loop (kSearchNormalEstimation, :173-188) followed by
+    mlsp.cal_density (MLSP/mlsp.py:240-272).  batch_pts (B,N,3) ->
+        normals (B,N,3), soft labels (B,N,num_cls), clipped counts (B,N) int64 [, idx (B,N,near) int64] [, curvature (B,N)]
+    identical to estimate_normals(batch_pts, near) and cal_density(batch_pts, radius, num_cls, pergroup, shift, K)."""
+    _require_cuda_f32(batch_pts, "target_structure")
+    pts = batch_pts.detach().contiguous()
+    B, N, three = pts.shape
+    if three != 3:
+        raise MlspError("target_structure: expected (B,N,3)")
+    if not (1 <= near <= N):
+        raise RuntimeError(f"selected index k out of range (k={near}, N={N})")
+    r2 = float(np.float32(float(radius) * float(radius)))
+    dev = pts.device
+    normals = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    labels = torch.empty((B, N, num_cls), dtype=torch.float32, device=dev)
+    row = torch.empty((B, N), dtype=torch.int64, device=dev)
+    idx = torch.empty((B, N, near), dtype=torch.int64, device=dev) if return_idx else None
+    curv = torch.empty((B, N), dtype=torch.float32, device=dev) if return_curvature else None
+    with torch.cuda.device(dev):
+        _lib.call("mlsp_target_structure", _ptr(pts), B, N, int(near), ctypes.c_float(r2), int(K), int(shift), int(pergroup),
+                  int(num_cls), _ptr(normals), _ptr(curv), _ptr(labels), _ptr(row), _ptr(idx), _stream(dev))
+    out = (normals, labels, row)
+    if return_idx:
+        out += (idx,)
+    if return_curvature:
+        out += (curv,)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- a9 / a10
 def _point_strides(p: torch.Tensor):
     if p.dim() != 3 or p.size(2) != 3:

@@ -373,6 +373,31 @@ def test_ball_count_matches_oracle(dev, orc):
     assert np.array_equal(_np(M.ball_count(xq.to(dev))), orc.ball_count(xq.numpy()))
 
 
+# ------------------------------------------------------------------------------------------------ 8f rank 2: one 3-D pass
+@pytest.mark.parametrize("B,N,near,radius,num_cls,pergroup,shift,K", [
+    (32, 1024, 20, 0.13, 16, 2, 0, 100), (16, 2048, 10, 0.091, 16, 5, 10, 100), (3, 700, 40, 0.4, 16, 2, 0, 100),
+    (2, 333, 7, 0.12, 8, 3, 1, 10)])
+def test_target_structure_is_the_three_separate_ops(dev, orc, npo, B, N, near, radius, num_cls, pergroup, shift, K):
+    """target_structure = the kNN of the normals' neighbourhoods + the PCA normals + cal_density in ONE launch: bit-identical
+    with the three stand-alone calls (same arithmetic) and with the oracles each of them is checked against."""
+    x = synth.surface_clouds(B, N, 23)
+    pts = x.permute(0, 2, 1).contiguous()
+    nrm, lab, row, idx, curv = M.target_structure(pts.to(dev), near, radius, num_cls, pergroup, shift, K, return_idx=True,
+                                                  return_curvature=True)
+    assert np.array_equal(_np(idx), orc.knn(x.numpy(), near))                        # a1, lowest-index ties
+    ol, orow = npo.cal_density(pts.numpy(), radius, num_cls, pergroup, shift, K)
+    assert np.array_equal(_np(row), orow) and np.array_equal(_np(lab), ol.astype(np.float32))   # a6
+    n2, c2 = M.estimate_normals(pts.to(dev), near, return_curvature=True)
+    l2, r2 = M.cal_density(pts.to(dev), radius, num_cls, pergroup, shift, K)
+    assert torch.equal(r2, row) and torch.equal(l2, lab)
+    on, gap = npo.pca_normals(pts.numpy(), near, return_gap=True)                      # a7, up to sign, eigengap-gated
+    ok = gap > 1e-2
+    assert np.abs(np.abs((_np(nrm).astype(np.float64) * on).sum(-1)) - 1.0)[ok].max() < 1e-5
+    assert float((nrm - n2).abs().max()) < 1e-6 and float((curv - c2).abs().max()) < 1e-6   # fp64 sums in another order
+    nrm_only = M.target_structure(pts.to(dev), near, radius, num_cls, pergroup, shift, K)[0]
+    assert torch.equal(nrm_only, nrm)
+
+
 # ------------------------------------------------------------------------------------------------ a6 / a7 vs independent code
 def test_cal_density_vs_ckdtree(dev):
     """a6 on the device against scipy's cKDTree + the reference's label arithmetic (no code shared with the oracle): the rows
