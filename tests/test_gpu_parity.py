@@ -954,3 +954,82 @@ def test_lazy_graph_feature_fuses_reference_shaped_layers(dev):
         assert float((a - b).norm()) <= 1e-2 * max(float(b.norm()), 1e-12)
     for (n1, b1), (_, b2) in zip(mods.named_buffers(), twin.named_buffers()):
         assert torch.allclose(b1.float(), b2.float(), rtol=1e-3, atol=1e-5), n1
+
+
+# ------------------------------------------------------------------------------------------------ the DGCNN caller (8f ranks 1, 4)
+def test_dgcnn_matches_the_reference_model(golden, dev):
+    """mlsp_b200.dgcnn.DGCNN (fused EdgeConv layers, merged first layer of the three heads) against the reference's own DGCNN
+    class run on the CPU by oracle/gen_golden_dgcnn.py: same seed -> same weights; training-mode forward with
+    activate_density_normal_ondef=True.  A DGCNN is discontinuous in its inputs (a 1e-6 perturbation can swap the 20th and 21st
+    neighbour of a point, which moves a few max-pooled features by O(1)), so every STAGE is compared on the reference's own
+    input for it -- 1e-5 of the tensor's scale -- and end to end the loss and the direction of the gradients."""
+    from mlsp_b200 import dgcnn
+    torch.backends.cudnn.allow_tf32 = False                            # the reference trains with cuDNN off: fp32 convolutions
+    g = golden("dgcnn_ondef")
+    torch.manual_seed(int(g["seed"]))
+    model = dgcnn.DGCNN(num_class=10, density_num_class=16, pergroup=2, dropout=0.0).to(dev).train()
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+
+    def err(a, ref):
+        a, ref = _np(a).astype(np.float64), np.asarray(ref).astype(np.float64)
+        return float(np.abs(a - ref).max()) / max(float(np.abs(ref).max()), 1e-30)
+
+    # -- stage by stage, teacher-forced with the reference's activations (no statistics update: momentum 0 copies below)
+    import copy
+    probe = copy.deepcopy(model)
+    with torch.no_grad():
+        T = probe.input_transform_net(M.get_graph_feature(x.detach(), None, k=20))
+        assert err(torch.matmul(T, x.detach()), g["xt"]) <= 1e-4          # the learned 3x3 alignment of the cloud
+        stage_in = [g["xt"], g["x1"], g["x2"], g["x3"]]
+        for layer, xin, name in zip(probe._edge, stage_in, ("x1", "x2", "x3", "x4")):
+            out = layer(torch.from_numpy(xin).to(dev))
+            assert err(out, g[name]) <= 1e-5, name                       # graph feature -> conv_2d -> max over k, exact graph
+        x_cat = torch.from_numpy(np.concatenate([g["x1"], g["x2"], g["x3"], g["x4"]], axis=1)).to(dev)
+        x5 = torch.nn.functional.adaptive_max_pool1d(torch.nn.functional.leaky_relu(probe.bn5(probe.conv5(x_cat)), 0.2), 1).view(4, -1)
+        assert err(probe.C(x5), g["cls"]) <= 1e-4
+        firsts = probe.heads_first_layer(x_cat, x5, [probe.DefRec, probe.Norm_pred, probe.Density_cls])   # 8f rank 4
+        assert err(probe.DefRec.tail(firsts[0]), g["DefRec"]) <= 1e-4
+        assert err(probe.Norm_pred.tail(firsts[1]), g["Normal"]) <= 1e-4
+        p_vec, p_val = probe.Density_cls.tail(firsts[2])
+        assert err(p_vec, g["density"]) <= 1e-4 and err(p_val, g["density_mse"]) <= 1e-4
+    # -- end to end
+    logits = model(x, activate_density_normal_ondef=True)
+    loss = (logits["DefRec"].square().mean() + logits["Normal"].square().mean() + logits["density_mse"].mean()
+            + (logits["density"] * torch.arange(16.0, device=dev)).sum(1).mean() + logits["cls"].square().mean())
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    grads = dict(model.named_parameters())
+
+    def cosine(a, ref):
+        a, ref = _np(a).astype(np.float64).ravel(), np.asarray(ref).astype(np.float64).ravel()
+        return float(a @ ref / (np.linalg.norm(a) * np.linalg.norm(ref)))
+
+    assert cosine(x.grad, g["grad_x"]) > 0.98
+    assert cosine(grads["conv1.conv.0.weight"].grad, g["grad_conv1"]) > 0.98
+    assert cosine(grads["conv4.conv.0.weight"].grad, g["grad_conv4"]) > 0.98
+    assert cosine(grads["DefRec.conv1.weight"].grad[:, ::16, 0], g["grad_defrec_conv1"]) > 0.98
+    assert cosine(grads["C.mlp3.weight"].grad, g["grad_cls_mlp3"]) > 0.98
+    assert err(model.conv2.conv[1].running_var, g["conv2_bn_running_var"]) <= 1e-4
+    assert grads["Rec_scan.conv1.weight"].grad is None                 # not on this forward, like the reference
+
+
+def test_target_branch_loss_runs_and_trains(dev):
+    """One target-branch step (PointDA/trainer.py:522-566) end to end on the device: targets, deformation, forward with the
+    heads, the three losses, backward, an SGD step that lowers the loss on the same batch."""
+    from mlsp_b200 import dgcnn
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = dgcnn.DGCNN(dropout=0.0).to(dev).train()
+    model.Rec_scan.requires_grad_(False)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5)   # PointDA/trainer.py:258-262
+    lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=dev)
+    batch = synth.surface_clouds(4, 1024, 3).permute(0, 2, 1).contiguous().to(dev)
+    losses = []
+    for _ in range(8):
+        np.random.seed(0)                                                # the same deformation every iteration
+        opt.zero_grad(set_to_none=True)
+        loss = dgcnn.target_branch_loss(model, batch.clone(), lookup)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(np.isfinite(losses)) and min(losses[-3:]) < losses[0], losses

@@ -354,3 +354,23 @@ def test_lazy_fusion_runs_the_real_reference_models(lazy_on_cpu):
             assert torch.allclose(got[name], want[name], rtol=1e-4, atol=1e-5), name
         for (n1, b1), (_, b2) in zip(model.named_buffers(), twin.named_buffers()):
             assert torch.allclose(b1.float(), b2.float(), rtol=1e-4, atol=1e-6), n1
+
+
+def test_dgcnn_mirror_has_the_reference_parameters_and_init():
+    """mlsp_b200.dgcnn.DGCNN is a structural mirror of PointDA/Models.py:DGCNN: for the same torch.manual_seed it has the same
+    state_dict keys and bit-identical initial weights as the reference's class (digest stored by oracle/gen_golden_dgcnn.py,
+    which runs the reference's own DGCNN) -- so reference checkpoints load with strict=True."""
+    import hashlib
+    import os
+    import numpy as np
+    import torch
+    from mlsp_b200 import dgcnn
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dgcnn_ondef.npz"))
+    torch.manual_seed(int(g["seed"]))
+    m = dgcnn.DGCNN(num_class=10, density_num_class=16, pergroup=2, dropout=0.0)
+    h = hashlib.sha256()
+    for name, p in sorted(m.state_dict().items()):
+        h.update(name.encode())
+        h.update(p.detach().cpu().numpy().tobytes())
+    assert h.hexdigest() == bytes(g["digest"]).decode()
+    assert sum(p.numel() for p in m.parameters()) == 4548915          # SURVEY.md section 5: the 18.2 MB all-reduce payload
