@@ -117,6 +117,14 @@ MLSP_API int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, int
 MLSP_API int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
              float *vals, void *stream);
 
+/* SURVEY.md 8f rank 3 -- PCM.mix_shapes (MLSP/PCM.py:6-38) fused with its two farthest_point_sample calls: 2B CTAs sample
+ *   npoint_a points of cloud b and N - npoint_a points of cloud index[b] side by side and write the mixed, point-permuted
+ *   cloud directly: out[b][:, inv_perm[s]] = slot s of cat(vals_a, vals_b), i.e. cat(...)[:, :, points_perm] of PCM.py:31-33.
+ *   xyz (B,3,N); index (B) int64 = torch.randperm(B); start (2B) int64 = the two torch.randint draws (a-half first);
+ *   inv_perm (N) int32 = inverse of torch.randperm(N); out (B,3,N).  N <= 8192. */
+MLSP_API int mlsp_pcm_mix(const float *xyz, int B, int N, int npoint_a, const int64_t *index, const int64_t *start,
+                          const int32_t *inv_perm, float *out, void *stream);
+
 /* a4 -- assign_region_to_point (utils/pc_utils.py:33-73) + the per-region counts and the first-fit
  *   region choice of deform_input (MLSP/mlsp.py:28-50, groups=1).
  *   X (B,C,N), C >= 3, addressed X[b*xs_b + c*xs_c + n*xs_n] (strides in floats; all three 0 = dense): the reference's

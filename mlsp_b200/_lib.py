@@ -27,6 +27,7 @@ SIGNATURES = {
     "mlsp_graph_feature_fwd_stage": [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _I, _P],
     "mlsp_edge_gather_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P],
     "mlsp_fps": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "mlsp_pcm_mix": [_P, _I, _I, _I, _P, _P, _P, _P, _P],
     "mlsp_region_assign_select": [_P, _L, _L, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P],
     "mlsp_region_mask_scatter": [_P, _L, _L, _L, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "mlsp_ball_count": [_P, _L, _L, _L, _I, _I, _I, _F, _P, _P],

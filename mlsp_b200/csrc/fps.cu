@@ -7,8 +7,6 @@
 // dependency chain of npoint rounds; the kernel is latency-bound by construction (12 KB of input).
 // Arithmetic pinned to oracle/mlsp_oracle.c:orc_fps: d = (rn(dx^2) + rn(dy^2)) + rn(dz^2), distance =
 // min(distance, d) starting from 1e10, argmax with the lowest index on ties (torch.max semantics).
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace mlsp {
@@ -20,16 +18,37 @@ namespace mlsp {
 //               publishes (value, index) for its warp
 //   in-CTA    : one __syncthreads per round; every thread reads the W slots and picks the first maximum.
 // Points beyond N carry distance -1 forever (d >= 0 never undercuts it, and it never wins a maximum).
+// PCM mix-up (MLSP/PCM.py:26-38) fused with its two FPS calls: with mix.out set the grid is 2B CTAs -- CTA b < B samples
+// npoint_a points of cloud b, CTA B + b samples N - npoint_a points of cloud index[b] -- and every sampled point goes straight
+// to its place in the mixed cloud: slot s of cat(vals_a, vals_b) lands at out[b][:, inv_perm[s]], which is
+// cat(...)[:, :, points_perm] of PCM.py:31-33 without the two value tensors, the cat and the permuting gather.
+struct FpsMix {
+    const int64_t *index;    // (B) the batch permutation of PCM.py:20
+    const int32_t *inv_perm; // (N) inverse of points_perm (PCM.py:32)
+    float *out;              // (B,3,N) mixed clouds, or NULL: plain farthest_point_sample
+    int npoint_a, B;
+};
+
 template <int P, int W>
 __global__ void __launch_bounds__(32 * W)
 fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start,
-           int64_t *__restrict__ centroids, float *__restrict__ vals)
+           int64_t *__restrict__ centroids, float *__restrict__ vals, FpsMix mix)
 {
     extern __shared__ float4 spt[];                       // [N] (x, y, z, 0), then the winners of all rounds
     int *hist = reinterpret_cast<int *>(spt + N);         // [npoint]
     __shared__ __align__(16 * W) uint2 slot[2][W];        // (value bits, index), double buffered by round parity
 
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int slot0 = 0, out_b = b;                             // mix: first slot of this CTA's samples, destination cloud
+    if (mix.out) {
+        const bool second = b >= mix.B;
+        out_b = second ? b - mix.B : b;
+        npoint = second ? N - mix.npoint_a : mix.npoint_a;
+        slot0 = second ? mix.npoint_a : 0;
+        b = second ? (int)mix.index[out_b] : b;
+        if (npoint <= 0) return;
+    }
     const float *X = xyz + (size_t)b * 3 * N;
     for (int p = tid; p < N; p += 32 * W) spt[p] = make_float4(X[p], X[N + p], X[2 * N + p], 0.0f);
     __syncthreads();
@@ -50,7 +69,7 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
     uint32_t my_slot = slot_a + warp * 8, all_slots = slot_a;
     unsigned lt_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-    int far = (int)start[b];
+    int far = (int)start[blockIdx.x];
 
     for (int s = 0; s + 1 < npoint; ++s) {
         float cx, cy, cz, cw;
@@ -109,6 +128,17 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
     }
     if (tid == 0 && npoint > 0) hist[npoint - 1] = far;
     __syncthreads();
+    if (mix.out) {                                        // straight into the mixed cloud (scattered by the point permutation)
+        float *o = mix.out + (size_t)out_b * 3 * N;
+        for (int s = tid; s < npoint; s += 32 * W) {
+            const float4 c = spt[hist[s]];
+            const int p = mix.inv_perm[slot0 + s];
+            o[p] = c.x;
+            o[N + p] = c.y;
+            o[2 * N + p] = c.z;
+        }
+        return;
+    }
     // ---- results, written once and coalesced: centroids (B,npoint) int64, centroids_vals (B,3,npoint)
     int64_t *cen = centroids + (size_t)b * npoint;
     float *vx = vals + (size_t)b * 3 * npoint;
@@ -124,12 +154,13 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
 
 template <int P, int W>
 static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
-                      float *vals, cudaStream_t st)
+                      float *vals, cudaStream_t st, FpsMix mix = FpsMix{nullptr, nullptr, nullptr, 0, 0})
 {
-    const size_t smem = sizeof(float4) * (size_t)N + sizeof(int) * (size_t)npoint;
-    MLSP_REQUIRE(smem <= 227 * 1024, MLSP_EUNSUPPORTED, "fps: N=%d, npoint=%d needs %zu bytes of shared memory", N, npoint, smem);
+    const int np_max = mix.out ? N : npoint;
+    const size_t smem = sizeof(float4) * (size_t)N + sizeof(int) * (size_t)np_max;
+    MLSP_REQUIRE(smem <= 227 * 1024, MLSP_EUNSUPPORTED, "fps: N=%d, npoint=%d needs %zu bytes of shared memory", N, np_max, smem);
     MLSP_CUDA(cudaFuncSetAttribute(fps_kernel<P, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fps_kernel<P, W><<<B, 32 * W, smem, st>>>(xyz, N, npoint, start, centroids, vals);
+    fps_kernel<P, W><<<mix.out ? 2 * B : B, 32 * W, smem, st>>>(xyz, N, npoint, start, centroids, vals, mix);
     MLSP_LAUNCH_CHECK("fps_kernel");
     return MLSP_OK;
 }
@@ -229,16 +260,6 @@ extern "C" int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_
     if (npoint == 0) return MLSP_OK;
     cudaStream_t st = as_stream(stream);
     // a valid point with the lowest index wins all-zero rounds; invalid start indices are the caller's bug
-    const char *var = getenv("MLSP_FPS_VARIANT");          // tuning hook: "P,W"
-    if (var) {
-        int P = 0, W = 0;
-        if (sscanf(var, "%d,%d", &P, &W) == 2 && N <= 32 * P * W) {
-#define MLSP_FPS_TRY(PP, WW) if (P == PP && W == WW) return launch_fps<PP, WW>(xyz, B, N, npoint, start, centroids, vals, st);
-            MLSP_FPS_TRY(4, 8) MLSP_FPS_TRY(8, 4) MLSP_FPS_TRY(16, 2) MLSP_FPS_TRY(32, 1) MLSP_FPS_TRY(2, 16)
-            MLSP_FPS_TRY(8, 8) MLSP_FPS_TRY(16, 4) MLSP_FPS_TRY(4, 16) MLSP_FPS_TRY(16, 8) MLSP_FPS_TRY(8, 16)
-#undef MLSP_FPS_TRY
-        }
-    }
     if (N <= 128) return launch_fps<4, 1>(xyz, B, N, npoint, start, centroids, vals, st);
     if (N <= 512) return launch_fps<4, 4>(xyz, B, N, npoint, start, centroids, vals, st);
     if (N <= 1024) return launch_fps<4, 8>(xyz, B, N, npoint, start, centroids, vals, st);    // measured: 103 us / 512 rounds
@@ -248,4 +269,24 @@ extern "C" int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_
     if (N <= 16384) return launch_fps_soa<16, 1024>(xyz, B, N, npoint, start, centroids, vals, st);
     set_error("fps: N=%d > 16384 not supported", N);
     return MLSP_EUNSUPPORTED;
+}
+
+// 8f rank 3 -- PCM.mix_shapes (MLSP/PCM.py:6-38) in one launch: the two farthest_point_sample calls (npoint_a points of every
+// cloud, N - npoint_a points of its partner index[b]) run side by side in 2B CTAs and write the mixed, point-permuted cloud
+// directly.  start (2B): the torch.randint draws of the two FPS calls, a-half first.
+extern "C" int mlsp_pcm_mix(const float *xyz, int B, int N, int npoint_a, const int64_t *index, const int64_t *start,
+                            const int32_t *inv_perm, float *out, void *stream)
+{
+    using namespace mlsp;
+    MLSP_REQUIRE(xyz && index && start && inv_perm && out, MLSP_EINVAL, "pcm_mix: null pointer");
+    MLSP_REQUIRE(B > 0 && N > 0 && npoint_a >= 0 && npoint_a <= N, MLSP_EINVAL, "pcm_mix: bad shape B=%d N=%d npoint_a=%d", B, N, npoint_a);
+    MLSP_REQUIRE(N <= 8192, MLSP_EUNSUPPORTED, "pcm_mix: N=%d > 8192", N);
+    cudaStream_t st = as_stream(stream);
+    FpsMix mix{index, inv_perm, out, npoint_a, B};
+    if (N <= 128) return launch_fps<4, 1>(xyz, B, N, 0, start, nullptr, nullptr, st, mix);
+    if (N <= 512) return launch_fps<4, 4>(xyz, B, N, 0, start, nullptr, nullptr, st, mix);
+    if (N <= 1024) return launch_fps<4, 8>(xyz, B, N, 0, start, nullptr, nullptr, st, mix);
+    if (N <= 2048) return launch_fps<16, 4>(xyz, B, N, 0, start, nullptr, nullptr, st, mix);
+    if (N <= 4096) return launch_fps<16, 8>(xyz, B, N, 0, start, nullptr, nullptr, st, mix);
+    return launch_fps<16, 16>(xyz, B, N, 0, start, nullptr, nullptr, st, mix);
 }

@@ -47,11 +47,25 @@ def scalar_loss(logits):
             + (logits["density"] * torch.arange(16.0)).sum(1).mean() + logits["cls"].square().mean())
 
 
+def pcm_fixture():
+    """PCM.mix_shapes (MLSP/PCM.py:6-38) by the reference's own function, seeded torch + numpy RNG."""
+    from MLSP import PCM
+    a = types.SimpleNamespace(cuda=False, gpus=[-1], mixup_params=1.0)
+    X = synth.surface_clouds(4, 512, 41)
+    Y = torch.arange(4)
+    torch.manual_seed(7)
+    np.random.seed(7)
+    mixed, (Ya, Yb, lam) = PCM.mix_shapes(a, X, Y)
+    np.savez_compressed(os.path.join(OUT, "pcm_mix.npz"), X=X.numpy(), Y=Y.numpy(), seed=7, mixed=mixed.numpy(), Ya=Ya.numpy(),
+                        Yb=Yb.numpy(), lam=float(lam))
+    print("pcm_mix.npz", os.path.getsize(os.path.join(OUT, "pcm_mix.npz")), "lam", float(lam))
+
+
 def main():
     torch.set_num_threads(1)
     load_reference()
-    sys.modules.setdefault("utils", types.ModuleType("utils"))            # `from utils import misc` at module level only
     import PointDA.Models as ref_models
+    pcm_fixture()
     torch.manual_seed(SEED)
     model = ref_models.DGCNN(ref_args())
     digest = param_digest(model)

@@ -1033,3 +1033,25 @@ def test_target_branch_loss_runs_and_trains(dev):
         opt.step()
         losses.append(float(loss.detach()))
     assert all(np.isfinite(losses)) and min(losses[-3:]) < losses[0], losses
+
+
+def test_pcm_mix_shapes_golden(golden, dev):
+    """8f rank 3: PCM.mix_shapes with its two FPS calls and the cat / permute in one launch, against the reference's own
+    PCM.mix_shapes (seeded torch + numpy streams consumed in the reference's order): the mixed clouds bit for bit."""
+    import types
+    from mlsp_b200 import pcm
+    g = golden("pcm_mix")
+    torch.manual_seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]))
+    args = types.SimpleNamespace(mixup_params=1.0, DefRec_weight=0.5)
+    mixed, (Ya, Yb, lam) = pcm.mix_shapes(args, torch.from_numpy(g["X"]).to(dev), torch.from_numpy(g["Y"]).to(dev))
+    assert abs(lam - float(g["lam"])) < 1e-15
+    assert np.array_equal(_np(Ya), g["Ya"]) and np.array_equal(_np(Yb), g["Yb"])
+    assert np.array_equal(_np(mixed), g["mixed"])
+    for lam_edge in (0.0, 1.0):                                         # one of the two halves is empty
+        torch.manual_seed(3)
+        np.random.seed(3)
+        import unittest.mock as mock
+        with mock.patch("numpy.random.beta", return_value=lam_edge):
+            mixed, _ = pcm.mix_shapes(args, torch.from_numpy(g["X"]).to(dev), torch.from_numpy(g["Y"]).to(dev))
+        assert torch.isfinite(mixed).all() and mixed.shape == (4, 3, 512)
