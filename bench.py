@@ -997,16 +997,173 @@ def run_workload_e(args):
 
 
 # --------------------------------------------------------------------------------------------------- main
+
+# --------------------------------------------------------------------------------------------------- workload T
+def run_workload_t(args):
+    """BASELINE.json configs[2]: the full PointDA training step -- DGCNN + MLSP losses (cardinality / position-Chamfer / normal)
+    forward + backward + optimiser step -- data-parallel, one process per GPU, gradients all-reduced by DistributedDataParallel
+    over NCCL (PointDA/trainer.py:374-571; the reference uses single-process nn.DataParallel :251-252).  A step =
+      source branch (:378-410): PCM mix-up of the source batch (two FPS calls, fused), forward, mixed cross-entropy, backward
+                                under no_sync() (gradients accumulate locally, like the reference's first backward);
+      target branch (:522-566): local-structure targets of the undeformed batch, deformation, forward with the three heads,
+                                position + normal + cardinality losses, backward (the ONE all-reduce of the step, bucketed and
+                                overlapped with the backward by DDP), then opt.step().
+    B source + B target clouds per GPU per step; the reported clouds/s counts the B target clouds (the MLSP metric)."""
+    from mlsp_b200 import synth
+    B, N, k = synth.CONFIGS["A"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "MLSP clouds/sec (Bx1024,k=20) full DGCNN + MLSP training step"
+    cfg = {"workload": "train-T", "clouds_per_gpu": B, "source_clouds_per_gpu": B, "points": N, "k": k, "model": "PointDA DGCNN (4,548,915 parameters) + DefRec / Normal / Density heads",
+           "optimizer": "Adam lr 1e-3 wd 5e-5 (PointDA/trainer.py:258-262 defaults)",
+           "parallelism": f"dp{world}: one process per GPU, DistributedDataParallel over NCCL, one gradient all-reduce per step (18.2 MB fp32)",
+           "precision": "fp32 (cuDNN / matmul TF32 off, like the reference's cudnn.enabled=False training)"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        print(json.dumps({"impl": "reference", "unavailable": "workload T has no CPU reference arm: the reference's training step needs python-pcl; "
+                          "hot-path workloads A/S/E/X carry the reference arm"}), flush=True)
+        return
+    import mlsp_b200 as M
+    from mlsp_b200 import dgcnn, pcm
+    import types
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    targs = types.SimpleNamespace(mixup_params=1.0, DefRec_weight=0.5)
+    torch.manual_seed(0)                                               # identical initial weights on every rank
+    model = dgcnn.DGCNN(num_class=10, density_num_class=NUM_CLS, pergroup=PERGROUP, dropout=0.5).to(device).train()
+    model.Rec_scan.requires_grad_(False)                               # Scan_on_trgt is off by default (PointDA/trainer.py:76)
+    net = model
+    if dist is not None:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True,
+                                                        broadcast_buffers=False)   # BatchNorm statistics stay per rank (SURVEY 8e)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5)
+    criterion = torch.nn.CrossEntropyLoss()
+    lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=device)
+    np.random.seed(1234 + rank)
+    torch.manual_seed(1234 + rank)
+    src_host = synth.surface_clouds(B, N, 4321 + rank).permute(0, 2, 1).contiguous().pin_memory()       # (B,N,3) like the loaders
+    trg_host = synth.surface_clouds(B, N, 1234 + rank).permute(0, 2, 1).contiguous().pin_memory()
+    lab_host = (torch.arange(B) % 10).pin_memory()
+    src_dev, trg_dev, lab_dev = src_host.to(device), trg_host.to(device), lab_host.to(device)
+    import contextlib
+
+    def step(from_host):
+        src = src_host.to(device, non_blocking=True) if from_host else src_dev
+        trg = trg_host.to(device, non_blocking=True) if from_host else trg_dev
+        lab = lab_host.to(device, non_blocking=True) if from_host else lab_dev
+        opt.zero_grad(set_to_none=True)
+        with (net.no_sync() if dist is not None else contextlib.nullcontext()):
+            mixed, vals = pcm.mix_shapes(targs, src.permute(0, 2, 1), lab)
+            logits = net(mixed)
+            loss_s = pcm.calc_loss(targs, logits, vals, criterion)
+            loss_s.backward()
+        # the target branch's loss is computed by the module's helper through the DDP wrapper's forward
+        loss_t = dgcnn.target_branch_loss(net, trg.clone(), lookup, near=NEAR, radius=RADIUS, density_num_class=NUM_CLS,
+                                          pergroup=PERGROUP, shift=SHIFT, DefRec_weight=targs.DefRec_weight)
+        loss_t.backward()
+        opt.step()
+        return loss_s.detach() + loss_t.detach()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    # the clock sampler's filler load must be LOCAL to rank 0 (a training step contains a collective: running extra steps on one
+    # rank only would deadlock the others)
+    filler = torch.randn(2048, 2048, device=device)
+    if sampler is not None:
+        sampler.wait_first_sample(lambda: torch.mm(filler, filler))
+        sampler.skip = sampler._count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(False)
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if sampler is not None else None      # the timed region (K x ~40 ms) spans several 100 ms samples
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_host = float(step(True))                                   # host batches in, the loss read back every step
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    # share of the gradient all-reduce: time the same payload's all-reduce alone on the NCCL stream
+    ar_ms = None
+    nbytes = sum(p.numel() for p in model.parameters() if p.requires_grad) * 4
+    if dist is not None:
+        flat = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        for _ in range(3):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(flat)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = a0.elapsed_time(a1) / 10
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    step_ms, e2e_ms = max_over_ranks(dev_ms), max_over_ranks(e2e_s * 1e3)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": metric, "value": B * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(src_host.numel() * 4 + trg_host.numel() * 4 + lab_host.numel() * 8), "d2h_bytes_per_step": 4,
+                "loss": loss_host},
+        "collective": {"what": "DDP gradient all-reduce inside the timed backward (NCCL over NVLink/NVSwitch)", "bytes_per_step": nbytes,
+                       "allreduce_alone_ms": ar_ms, "share_of_step_if_not_overlapped": (ar_ms / step_ms) if ar_ms else 0.0},
+        "gpu_launches": None,
+        "roofline": None,
+        "note": "torch's own layers (1x1 convolutions, BatchNorm, heads, Adam) dominate this step and are not roofline-graded (SURVEY.md 8d); "
+                "the hot-path kernels inside it are graded by the default workload A line",
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="A", choices=["A", "S", "X", "E"],
+    ap.add_argument("--workload", default="A", choices=["A", "S", "X", "E", "T"],
                     help="A: PointDA-10 hot path (default, the BASELINE metric); S: PointSegDA hot path; "
                          "X: the scaling-sweep shape 256x4096, k=40 -- feature-space kNN on 64/128-dim features (configs[4]); "
-                         "E: the DGCNN EdgeConv backbone without the edge tensor (SURVEY 8f rank 1), forward + backward")
+                         "E: the DGCNN EdgeConv backbone without the edge tensor (SURVEY 8f rank 1), forward + backward; "
+                         "T: the full PointDA training step (DGCNN + MLSP losses + optimiser) under DDP (configs[2])")
     ap.add_argument("--seg", action="store_true",
                     help="with --workload E: the PointSegDA shape (16 x 2048) and its shared layers (plain Conv2d stacks, no BatchNorm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -1025,6 +1182,8 @@ def main():
         return run_workload_x(args)
     if args.workload == "E":
         return run_workload_e(args)
+    if args.workload == "T":
+        return run_workload_t(args)
     set_workload(args.workload)
     B, N, k = synth.CONFIGS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
