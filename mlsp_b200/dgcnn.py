@@ -29,6 +29,21 @@ from . import edgeconv, ops
 K = 20  # PointDA/Models.py:13
 
 
+def conv1x1(x: torch.Tensor, conv: nn.Module) -> torch.Tensor:
+    """A 1x1 Conv1d / Conv2d as the GEMM it is (torch.matmul -> one library SGEMM; cuDNN's fp32 convolution kernels take 3-5x
+    longer on these shapes, forward and backward).  x (B,C,N) or (B,C,N,k); same result as conv(x) up to summation order."""
+    W = conv.weight.flatten(1)                                # (O, C)
+    if x.dim() == 3:
+        y = torch.matmul(W, x)                               # (B,O,N)
+        return y if conv.bias is None else y + conv.bias.view(1, -1, 1)
+    B, C, N, k = x.shape
+    xf = x.permute(0, 2, 3, 1).reshape(B * N * k, C)          # free for the channels-last edge tensor of get_graph_feature
+    y = torch.matmul(xf, W.t())
+    if conv.bias is not None:
+        y = y + conv.bias
+    return y.view(B, N, k, -1).permute(0, 3, 1, 2)           # (B,O,N,k), channels-last strides again
+
+
 class Conv2dBlock(nn.Module):
     """conv_2d of PointDA/model_utils.py:45-63 (1x1 Conv2d + BatchNorm2d + activation), same attribute names."""
 
@@ -38,7 +53,7 @@ class Conv2dBlock(nn.Module):
         self.conv = nn.Sequential(nn.Conv2d(in_ch, out_ch, kernel_size=kernel, bias=bias), nn.BatchNorm2d(out_ch), act)
 
     def forward(self, x):
-        return self.conv(x)
+        return self.conv[2](self.conv[1](conv1x1(x, self.conv[0])))
 
 
 class FcBlock(nn.Module):
@@ -114,12 +129,12 @@ class PointHead(nn.Module):
     def tail(self, h1):
         """Everything after the first convolution; h1 = conv1(input) (B,256,N)."""
         x = self.dp1(F.relu(self.bn1(h1)))
-        x = self.dp2(F.relu(self.bn2(self.conv2(x))))
-        x = F.relu(self.bn3(self.conv3(x)))
-        return self.conv4(x).permute(0, 2, 1)
+        x = self.dp2(F.relu(self.bn2(conv1x1(x, self.conv2))))
+        x = F.relu(self.bn3(conv1x1(x, self.conv3)))
+        return conv1x1(x, self.conv4).permute(0, 2, 1)
 
     def forward(self, x):
-        return self.tail(self.conv1(x))
+        return self.tail(conv1x1(x, self.conv1))
 
 
 class DensityHead(nn.Module):
@@ -152,7 +167,7 @@ class DensityHead(nn.Module):
         return p_vec, self.fc2(p_vec)[:, 0]
 
     def forward(self, x):
-        return self.tail(self.conv1(x))
+        return self.tail(conv1x1(x, self.conv1))
 
 
 class DGCNN(nn.Module):
@@ -200,7 +215,7 @@ class DGCNN(nn.Module):
             h = layer(h.contiguous())
             feats.append(h)
         x_cat = torch.cat(feats, dim=1)
-        x5 = F.leaky_relu(self.bn5(self.conv5(x_cat)), negative_slope=0.2)
+        x5 = F.leaky_relu(self.bn5(conv1x1(x_cat, self.conv5)), negative_slope=0.2)
         x5 = F.adaptive_max_pool1d(x5, 1).view(B, -1)
         return x_cat, x5
 
