@@ -1153,6 +1153,108 @@ def run_workload_t(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------- extras of the default line
+def extra_train_T(dist, device, rank, world, steps=8):
+    """configs[2] in short form, for the default line (so that the driver's 1/2/4/8-GPU runs record it): the training step of
+    run_workload_t -- PCM source branch under no_sync, MLSP target branch, DDP gradient all-reduce inside the timed backward, Adam --
+    timed with CUDA events, max over ranks.  Same code path as `--workload T`."""
+    import contextlib
+    import types
+    import mlsp_b200 as M
+    from mlsp_b200 import dgcnn, pcm, synth
+    B, N, k = synth.CONFIGS["A"]
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    targs = types.SimpleNamespace(mixup_params=1.0, DefRec_weight=0.5)
+    rng = (torch.get_rng_state(), np.random.get_state())
+    torch.manual_seed(0)
+    model = dgcnn.DGCNN(num_class=10, density_num_class=16, pergroup=2, dropout=0.5).to(device).train()
+    model.Rec_scan.requires_grad_(False)
+    net = model
+    if dist is not None:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], gradient_as_bucket_view=True, broadcast_buffers=False)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5)
+    crit = torch.nn.CrossEntropyLoss()
+    lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=device)
+    src = synth.surface_clouds(B, N, 4321 + rank).permute(0, 2, 1).contiguous().to(device)
+    trg = synth.surface_clouds(B, N, 1234 + rank).permute(0, 2, 1).contiguous().to(device)
+    lab = (torch.arange(B) % 10).to(device)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with (net.no_sync() if dist is not None else contextlib.nullcontext()):
+            mixed, vals = pcm.mix_shapes(targs, src.permute(0, 2, 1), lab)
+            pcm.calc_loss(targs, net(mixed), vals, crit).backward()
+        dgcnn.target_branch_loss(net, trg.clone(), lookup).backward()
+        opt.step()
+
+    for _ in range(3):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ar_ms = None
+    nbytes = sum(p.numel() for p in model.parameters() if p.requires_grad) * 4
+    if dist is not None:
+        flat = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        for _ in range(3):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            dist.all_reduce(flat)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = a0.elapsed_time(a1) / 10
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    torch.set_rng_state(rng[0])
+    np.random.set_state(rng[1])
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    del model, net, opt
+    return {"workload": "train-T (BASELINE configs[2]; `bench.py --workload T` is the full line)", "clouds_per_s": B * world / (ms * 1e-3),
+            "ms_per_step": ms, "n_gpus": world, "parallelism": f"dp{world} DistributedDataParallel / NCCL",
+            "collective": {"bytes_per_step": nbytes, "allreduce_alone_ms": ar_ms, "inside_timed_region": dist is not None}}
+
+
+def extra_knn_X(device, steps=4):
+    """configs[4] in short form for the default line: knn(x, 40) on 256 x 4096 clouds at C = 64 and 128 (`--workload X` is the full line)."""
+    import mlsp_b200 as M
+    from mlsp_b200 import synth
+    B, N, k = synth.CONFIGS["X"]
+    out = {}
+    pk = peaks()
+    for C in (64, 128):
+        x = synth.features(B, C, N, 1234 + C).to(device)
+        for _ in range(2):
+            M.knn(x, k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            M.knn(x, k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        tf = (2.0 * B * N * N * C + 3.0 * B * N * N) / (ms * 1e-3) / 1e12
+        out[f"knn_C{C}"] = {"ms": round(ms, 3), "TFLOPs_algorithmic": round(tf, 1), "frac_of_sustained_bf16": round(tf / pk["bf16_tflops_sustained"], 4)}
+        del x
+    torch.cuda.empty_cache()
+    return {"workload": "knn-X 256x4096 k=40 (BASELINE configs[4]; `bench.py --workload X` is the full line)", **out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -1167,6 +1269,7 @@ def main():
     ap.add_argument("--seg", action="store_true",
                     help="with --workload E: the PointSegDA shape (16 x 2048) and its shared layers (plain Conv2d stacks, no BatchNorm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="default line without the short train-T / knn-X measurements")
     ap.add_argument("--serial", action="store_true", help="headline on one stream (no target-builder overlap)")
     ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")
     ap.add_argument("--prio", action="store_true",
@@ -1310,6 +1413,18 @@ def main():
     dev_only_ms = max_over_ranks(dev_ms / args.steps)
     e2e_ms = max_over_ranks(e2e_s * 1e3 / args.steps)
     target_gen = {m_: max_over_ranks(v) for m_, v in target_gen.items()}
+    # short forms of the other BASELINE configs, inside the line the driver records at every N: the DDP training step
+    # (configs[2], the gradient all-reduce in its timed region) on every rank, the 256 x 4096 feature-space kNN (configs[4]) at N = 1
+    extras = {}
+    if not args.no_extras and args.workload == "A":
+        try:
+            extras["train_T"] = extra_train_T(dist, device, rank, world)
+            if world == 1:
+                extras["knn_X"] = extra_knn_X(device)
+        except Exception as exc:                               # never let a context measurement cost the bench line
+            if world > 1:
+                raise                                          # ... but a rank that left a collective would hang the others
+            extras["error"] = repr(exc)[:300]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -1452,6 +1567,7 @@ def main():
         "kernel_rooflines": kernel_rooflines,
         "cpu_baseline": cpu,
         "torch_gpu_reference": torch_ref,
+        "extras": extras,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
