@@ -270,6 +270,24 @@ MLSP_API int mlsp_edgeconv_bwd(const float *g, int64_t g_bstride, const float *y
                       const float *rowsum, const float *coef, int B, int N, int O, int k, float slope, int bn_train,
                       float *dyz, float *dgamma_dbeta, void *ws, size_t ws_bytes, void *stream);
 
+/* ---- the point-wise products around the neighbourhood engine (8f ranks 1, 4): every 1x1 convolution / Linear of the DGCNN ----
+ * Replaces the library GEMM behind nn.Conv2d(kernel_size=1) in conv_2d (PointDA/model_utils.py:45-63, used by the EdgeConv
+ * layers PointDA/Models.py:114-128 and by transform_net model_utils.py:92-130), nn.Conv1d(kernel_size=1) of conv5 and of the
+ * heads (PointDA/Models.py:131, 156-160, 165-285) and nn.Linear (fc_layer model_utils.py:65-89), forward and both backward
+ * products.
+ *
+ *     D[z] (M x N) = A[z] (M x K) . B[z]^T (N x K)  (+ bias[n]),     z = 0 .. batch-1,   fp32 in / fp32 out
+ *
+ * a_kmajor != 0: A[z][m*lda + k] (K contiguous), else A[z][k*lda + m] (M contiguous); b_kmajor alike with ldb over (n, k);
+ * d_rowmajor != 0: D[z][m*ldd + n], else D[z][n*ldd + m].  Batch strides in floats (0 = operand shared by all z).
+ * bias (N) or NULL.  Any M, N, K >= 1, any leading dimensions (16-byte aligned operands take the vector loads).
+ * Arithmetic: tcgen05 tensor cores on three bf16 pieces per fp32 operand, six piece products accumulated in fp32 -- an fp32
+ * GEMM up to summation order (error ~1e-7 relative to sum |a||b|; NOT a bf16/tf32 approximation).  Non-finite inputs
+ * give NaN; |values| must stay below 3.3e38 (bf16 rounding of the leading piece). */
+MLSP_API int mlsp_gemm_f32(const float *A, int a_kmajor, long long lda, long long a_batch_stride, const float *B, int b_kmajor,
+                  long long ldb, long long b_batch_stride, float *D, int d_rowmajor, long long ldd, long long d_batch_stride,
+                  const float *bias, int M, int N, int K, int batch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,126 @@
+"""mlsp_gemm_f32 (tcgen05 GEMM on three bf16 pieces per fp32 operand) against fp64 ground truth, through the C ABI.
+Reference call sites it replaces: nn.Conv2d(kernel 1) in conv_2d PointDA/model_utils.py:45-63, nn.Conv1d(kernel 1) of the heads
+PointDA/Models.py:165-285, nn.Linear of fc_layer model_utils.py:65-89 -- fp32 products, tolerance 1e-5 relative (north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+needs_gpu = pytest.mark.gpu
+
+
+def _rel_err(got, ref64, a64, b64, bias64=None):
+    """max |got - ref| relative to the magnitude sum_k |a||b| (+ |bias|) of each entry (the scale fp32 rounding acts on)."""
+    scale = (a64.abs() @ b64.abs().transpose(-1, -2)).clamp_min(1e-30)
+    if bias64 is not None:
+        scale = scale + bias64.abs()
+    return float(((got.double() - ref64).abs() / scale).max())
+
+
+def test_gemm_argument_errors_without_gpu():
+    from mlsp_b200 import build, _lib
+    build.build()
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(256)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.mlsp_gemm_f32(None, 1, 8, 0, p, 1, 8, 0, p, 1, 8, 0, None, 4, 4, 8, 1, None) == 1 and b"null" in lib.mlsp_last_error()
+    assert lib.mlsp_gemm_f32(p, 1, 8, 0, p, 1, 8, 0, p, 1, 8, 0, None, 4, 4, 0, 1, None) == 1            # K = 0
+    assert lib.mlsp_gemm_f32(p, 1, 4, 0, p, 1, 8, 0, p, 1, 8, 0, None, 4, 4, 8, 1, None) == 1            # lda < K
+    assert lib.mlsp_gemm_f32(p, 1, 8, 0, p, 1, 8, 0, p, 0, 2, 0, None, 4, 4, 8, 1, None) == 1            # ldd < M (column-major D)
+    assert lib.mlsp_gemm_f32(p, 1, 8, 0, p, 1, 8, 0, p, 1, 8, 0, None, 0, 4, 8, 1, None) == 0            # empty product: nothing to do
+
+
+def test_linear_refuses_cpu_tensors():
+    from mlsp_b200 import linear, MlspError
+    with pytest.raises(MlspError):
+        linear.gemm_nt(torch.zeros(4, 8), torch.zeros(4, 8))
+
+
+@needs_gpu
+@pytest.mark.parametrize("akm", [1, 0])
+@pytest.mark.parametrize("bkm", [1, 0])
+@pytest.mark.parametrize("drm", [1, 0])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 128, 128), (300, 200, 136), (1024, 512, 128), (77, 19, 3), (130, 64, 6),
+                                   (5000, 300, 200), (9999, 129, 70)])       # the last two run as CTA pairs (cta_group::2)
+def test_gemm_all_layouts_vs_fp64(akm, bkm, drm, shape):
+    from mlsp_b200 import linear
+    M, N, K = shape
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M * 31 + N * 7 + K + 4 * akm + 2 * bkm + drm)
+    a = (torch.randn(M, K, generator=g) * torch.exp(2 * torch.randn(M, 1, generator=g))).to(dev)
+    b = torch.randn(N, K, generator=g).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    av = a if akm else a.t().contiguous().t()
+    bv = b if bkm else b.t().contiguous().t()
+    out = torch.full((M, N), float("nan"), device=dev) if drm else torch.full((N, M), float("nan"), device=dev).t()
+    linear.gemm_nt(av, bv, bias, out=out)
+    ref = a.double() @ b.double().t() + bias.double()
+    err = _rel_err(out, ref, a.double(), b.double(), bias.double())
+    assert err < 2e-6, err
+    assert torch.isfinite(out).all()
+
+
+@needs_gpu
+def test_gemm_batched_strided_views():
+    """The layouts the model uses: x (B,C,N) feature maps as M-major operands, shared weights, column-major output; a
+    channel slice of a wider tensor as an operand (leading dimension > extent, batch stride > matrix)."""
+    from mlsp_b200 import linear
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    B, C, N, O = 5, 96, 333, 72
+    wide = torch.randn(B, C + 32, N, generator=g).to(dev)
+    x = wide[:, 16:16 + C]                                              # (B,C,N) view, batch stride (C+32)*N
+    W = torch.randn(O, C, generator=g).to(dev)
+    y = linear.gemm_nt(x.transpose(1, 2), W, out_colmajor=True).transpose(1, 2)
+    assert y.is_contiguous() and y.shape == (B, O, N)
+    ref = torch.matmul(W.double(), x.double())
+    scale = torch.matmul(W.double().abs(), x.double().abs())
+    assert float(((y.double() - ref).abs() / scale).max()) < 2e-6
+    part = linear.gemm_nt(y, x)                                         # (B,O,C): K = N points, both K-major
+    refp = torch.matmul(ref, x.double().transpose(1, 2))
+    sc = torch.matmul(ref.abs(), x.double().abs().transpose(1, 2))
+    assert float(((part.double() - refp).abs() / sc).max()) < 4e-6
+
+
+@needs_gpu
+def test_gemm_many_tiles_persistent_loop():
+    """More tiles than SMs and several K chunks: every CTA loops over tiles, both accumulator buffers and smem stages wrap."""
+    from mlsp_b200 import linear
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(32768, 320, generator=g).to(dev)
+    b = torch.randn(512, 320, generator=g).to(dev)
+    out = linear.gemm_nt(a, b)
+    ref = a.double() @ b.double().t()
+    assert _rel_err(out, ref, a.double(), b.double()) < 2e-6
+
+
+@needs_gpu
+def test_conv1x1_and_linear_autograd_match_torch_fp64():
+    from mlsp_b200 import linear
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(7)
+    B, C, N, O, k = 3, 64, 256, 128, 20
+    x = torch.randn(B, C, N, generator=g).to(dev).requires_grad_(True)
+    W = (0.2 * torch.randn(O, C, 1, generator=g)).to(dev).requires_grad_(True)
+    bias = torch.randn(O, generator=g).to(dev).requires_grad_(True)
+    gy = torch.randn(B, O, N, generator=g).to(dev)
+    y = linear.conv1x1(x, W, bias)
+    y.backward(gy)
+    xd, Wd, bd = (t.detach().double().requires_grad_(True) for t in (x, W, bias))
+    yd = torch.nn.functional.conv1d(xd, Wd, bd)
+    yd.backward(gy.double())
+    for got, ref in ((y, yd), (x.grad, xd.grad), (W.grad, Wd.grad), (bias.grad, bd.grad)):
+        assert float((got.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), (got.shape,)
+    # channels-last edge tensor (B,C,N,k) -> (B,O,N,k), the transform net's convolutions
+    e = torch.randn(B, N, k, C, generator=g).to(dev).permute(0, 3, 1, 2).requires_grad_(True)
+    W2 = (0.2 * torch.randn(O, C, 1, 1, generator=g)).to(dev).requires_grad_(True)
+    ge = torch.randn(B, N, k, O, generator=g).to(dev).permute(0, 3, 1, 2)
+    y2 = linear.conv1x1(e, W2)
+    y2.backward(ge)
+    ed, W2d = e.detach().double().requires_grad_(True), W2.detach().double().requires_grad_(True)
+    y2d = torch.nn.functional.conv2d(ed, W2d)
+    y2d.backward(ge.double())
+    for got, ref in ((y2, y2d), (e.grad, ed.grad), (W2.grad, W2d.grad)):
+        assert float((got.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), (got.shape,)
