@@ -140,29 +140,17 @@ __device__ __forceinline__ uint32_t mapa_rank0(const void *p)
     asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
     return r;
 }
-// release at cluster scope: the operand pieces this warp stored (and fenced into the async proxy) are ordered before the arrive
-__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t bar_cluster)
+// Arrive on the leader's barrier.  Default semantics (release at CTA scope): the operand pieces were already made visible to
+// the async proxy by fence.proxy.async and are shared memory, not global -- an explicit cluster-scope release compiles to
+// MEMBAR.ALL.GPU + ERRBAR per arrive (measured: 19 % of the kernel's stall samples).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 // relaxed: what this orders are TMEM reads, fenced by tcgen05.fence::before_thread_sync
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster)
 {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "GWC_LOOP:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra GWC_DONE;\n\t"
-        "bra GWC_LOOP;\n\t"
-        "GWC_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
 }
 template <bool PAIR>
 __device__ __forceinline__ void tc_commit_to(uint64_t *bar)      // pair: arrives on the barrier at this offset in BOTH CTAs
@@ -263,16 +251,19 @@ __device__ __forceinline__ void load_item(Item &it, const float *__restrict__ ba
     }
 }
 
-__device__ __forceinline__ void store_item(const Item &it, uint8_t *oper, int kmajor, int g)
+// byte offset of item g's 16-byte chunk inside one piece (128-byte swizzle: chunk index XOR row-in-atom)
+__device__ __forceinline__ uint32_t item_smem_offset(int kmajor, int g)
 {
-    uint32_t off;
     if (kmajor) {
         const int r = g >> 3, c = g & 7;
-        off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
-    } else {
-        const int kr = g >> 4, mc = g & 15;
-        off = (uint32_t)(mc >> 3) * 8192u + (uint32_t)(kr >> 3) * 1024u + (uint32_t)(kr & 7) * 128u + (uint32_t)(((mc & 7) ^ (kr & 7)) << 4);
+        return (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((c ^ (r & 7)) << 4);
     }
+    const int kr = g >> 4, mc = g & 15;
+    return (uint32_t)(mc >> 3) * 8192u + (uint32_t)(kr >> 3) * 1024u + (uint32_t)(kr & 7) * 128u + (uint32_t)(((mc & 7) ^ (kr & 7)) << 4);
+}
+
+__device__ __forceinline__ void store_item(const Item &it, uint8_t *oper, uint32_t off)
+{
     uint4 q0, q1, q2;
     split3(it.lo.x, it.lo.y, q0.x, q1.x, q2.x);
     split3(it.lo.z, it.lo.w, q0.y, q1.y, q2.y);
@@ -286,6 +277,51 @@ __device__ __forceinline__ void store_item(const Item &it, uint8_t *oper, int km
 struct StageRegs {
     Item a[2], b[2];
 };
+
+// One operand as one loader thread sees it.  Item 1 is item 0 shifted by 64 rows (K-major) or 32 k rows (MN-major): a fixed
+// element offset `d1` in global memory and a fixed byte offset in the stage.  p0 runs along K (+ `adv` elements per chunk).
+// mode bits (per item u: bits 2u, 2u+1) say how the item is fetched in a K chunk that lies wholly inside K:
+// 0 = out of range (zeros), 1 = two 16-byte loads, 2 = the guarded element-wise path.
+struct OperandLane {
+    const float *p0;
+    uint32_t soff0;
+    int modes;
+};
+
+__device__ __forceinline__ void lane_begin_tile(OperandLane &L, const float *base, long long ld, int kmajor, int vec, int lt,
+                                                int row0, int rows)
+{
+    L.modes = 0;
+    if (kmajor) {
+        const int r = lt >> 3, c = lt & 7;
+        L.p0 = base + (long long)(row0 + r) * ld + 8 * c;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) L.modes |= ((row0 + r + 64 * u >= rows) ? 0 : (vec ? 1 : 2)) << (2 * u);
+    } else {
+        const int kr = lt >> 4, mc = lt & 15;
+        const int row = row0 + 8 * mc;
+        L.p0 = base + (long long)kr * ld + row;
+        const int m = (row >= rows) ? 0 : ((vec && row + 8 <= rows) ? 1 : 2);
+        L.modes = m | (m << 2);
+    }
+}
+
+// fetch item u of the chunk p0 currently points at
+__device__ __forceinline__ void lane_load(Item &it, const OperandLane &L, int u, long long d1, bool kfull, const float *base,
+                                          long long ld, int kmajor, int vec, int lt, int row0, int rows, int k0, int K)
+{
+    const int mode = (L.modes >> (2 * u)) & 3;
+    if (kfull && mode == 1) {
+        const float4 *q = reinterpret_cast<const float4 *>(L.p0 + (u ? d1 : 0));
+        it.lo = __ldg(q);
+        it.hi = __ldg(q + 1);
+    } else if (kfull && mode == 0) {
+        it.lo = make_float4(0.f, 0.f, 0.f, 0.f);
+        it.hi = it.lo;
+    } else {
+        load_item(it, base, ld, kmajor, vec, lt + u * LOAD_THREADS, row0, rows, k0, K);
+    }
+}
 
 // What one CTA does for output tile `tile`: rows [m0, m0+128) of A, rows [nb0, nb_end) of B (its share of the tile's
 // columns), and the accumulator it drains: 128 rows x ncols columns starting at (m0, n0).
@@ -309,18 +345,6 @@ __device__ __forceinline__ TileWork tile_work(const Params &P, int tile, uint32_
     w.nb0 = w.n0 + (PAIR ? (int)crank * share : 0);
     w.nb_end = min(P.N, w.nb0 + share);
     return w;
-}
-
-__device__ __forceinline__ void load_stage(StageRegs &R, const Params &P, const TileWork &w, int kc, int lt)
-{
-    const float *Ab = P.A + (long long)w.z * P.sa;
-    const float *Bb = P.B + (long long)w.z * P.sb;
-    const int k0 = kc * BK;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        load_item(R.a[u], Ab, P.lda, P.a_kmajor, P.a_vec, lt + u * LOAD_THREADS, w.m0, P.M, k0, P.K);
-        load_item(R.b[u], Bb, P.ldb, P.b_kmajor, P.b_vec, lt + u * LOAD_THREADS, w.nb0, w.nb_end, k0, P.K);
-    }
 }
 
 template <bool PAIR>
@@ -371,38 +395,74 @@ gemm3_kernel(const Params P)
 
     if (warp > EPI_WARPS) {
         // ================================ loaders ================================
+        // One register set: as soon as an item has been split and stored, the same registers receive the item's successor
+        // from the next K chunk, so every load has (almost) a whole iteration to arrive.
         const int lt = threadIdx.x - 32 * (EPI_WARPS + 1);
         const uint32_t full_c = PAIR ? mapa_rank0(full) : 0u;
-        StageRegs cur, nxt;
-        int j = 0, kc = 0;                                    // the chunk `nxt` is loaded for
+        OperandLane LA, LB;
+        LA.soff0 = item_smem_offset(P.a_kmajor, lt);
+        LB.soff0 = item_smem_offset(P.b_kmajor, lt);
+        const uint32_t sda = P.a_kmajor ? 8192u : 4096u, sdb = P.b_kmajor ? 8192u : 4096u;      // stage offset of item 1
+        const long long da1 = (P.a_kmajor ? 64 : 32) * P.lda, db1 = (P.b_kmajor ? 64 : 32) * P.ldb;
+        const long long adv_a = P.a_kmajor ? (long long)BK : (long long)BK * P.lda;
+        const long long adv_b = P.b_kmajor ? (long long)BK : (long long)BK * P.ldb;
+        const int n_it = my_tiles * P.kc;
+        Item ra[2], rb[2];
         TileWork w;
+        const float *Ab = P.A, *Bb = P.B;
+        int j = 0, kc = 0;                                    // the chunk being fetched
+        bool kfull = BK <= P.K;
         if (my_tiles > 0) {
             w = tile_work<PAIR>(P, unit, crank);
-            load_stage(cur, P, w, 0, lt);
+            Ab = P.A + (long long)w.z * P.sa;
+            Bb = P.B + (long long)w.z * P.sb;
+            lane_begin_tile(LA, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M);
+            lane_begin_tile(LB, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                lane_load(ra[u], LA, u, da1, kfull, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M, 0, P.K);
+                lane_load(rb[u], LB, u, db1, kfull, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end, 0, P.K);
+            }
         }
-        const int n_it = my_tiles * P.kc;
         for (int it = 0; it < n_it; ++it) {
+            // step the fetch state to chunk it + 1
+            bool more = true;
             if (++kc == P.kc) {
                 kc = 0;
-                ++j;
-                if (j < my_tiles) w = tile_work<PAIR>(P, unit + j * units, crank);
+                if (++j < my_tiles) {
+                    w = tile_work<PAIR>(P, unit + j * units, crank);
+                    Ab = P.A + (long long)w.z * P.sa;
+                    Bb = P.B + (long long)w.z * P.sb;
+                    lane_begin_tile(LA, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M);
+                    lane_begin_tile(LB, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end);
+                } else {
+                    more = false;
+                }
+            } else {
+                LA.p0 += adv_a;
+                LB.p0 += adv_b;
             }
-            if (j < my_tiles) load_stage(nxt, P, w, kc, lt);        // in flight while this chunk is converted
+            const int k0 = kc * BK;
+            kfull = k0 + BK <= P.K;
             const int slot = it % STAGES;
             mbar_wait(empty + slot, ((it / STAGES) & 1) ^ 1);
             uint8_t *st = stages + (size_t)slot * STAGE_BYTES;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                store_item(cur.a[u], st, P.a_kmajor, lt + u * LOAD_THREADS);
-                store_item(cur.b[u], st + OPER_BYTES, P.b_kmajor, lt + u * LOAD_THREADS);
+                store_item(ra[u], st, LA.soff0 + (u ? sda : 0u));
+                if (more) lane_load(ra[u], LA, u, da1, kfull, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M, k0, P.K);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                store_item(rb[u], st + OPER_BYTES, LB.soff0 + (u ? sdb : 0u));
+                if (more) lane_load(rb[u], LB, u, db1, kfull, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end, k0, P.K);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the tensor core's reads
             __syncwarp();
             if (lane == 0) {
-                if constexpr (PAIR) mbar_arrive_cluster_release(full_c + 8u * (uint32_t)slot);
+                if constexpr (PAIR) mbar_arrive_remote(full_c + 8u * (uint32_t)slot);
                 else mbar_arrive(full + slot);
             }
-            cur = nxt;
         }
     } else if (warp == EPI_WARPS) {
         // ================================ MMA issuer (pair: the leader's warp only) ================================
@@ -419,8 +479,7 @@ gemm3_kernel(const Params P)
                 const uint32_t d = tmem_base + (uint32_t)buf * TN;
                 for (int kc = 0; kc < P.kc; ++kc, ++it) {
                     const int slot = it % STAGES;
-                    if constexpr (PAIR) mbar_wait_cluster(full + slot, (it / STAGES) & 1);
-                    else mbar_wait(full + slot, (it / STAGES) & 1);
+                    mbar_wait(full + slot, (it / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stages + (size_t)slot * STAGE_BYTES), sb = sa + OPER_BYTES;
                     const int ksteps = (min(BK, P.K - kc * BK) + 15) >> 4;
@@ -477,8 +536,14 @@ gemm3_kernel(const Params P)
                         for (int c = 0; c < 32; ++c) stg[lane * EPI_PITCH + c] = __uint_as_float(v[c]);
                         __syncwarp();
                         const int mv = min(32, P.M - mrow);
-                        for (int r = 0; r < mv; ++r)
-                            if (lane < nv) Dz[(long long)(mrow + r) * P.ldd + nb + lane] = stg[r * EPI_PITCH + lane];
+                        float *drow = Dz + (long long)mrow * P.ldd + nb + lane;
+                        if (mv == 32 && nv == 32) {
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) drow[(long long)r * P.ldd] = stg[r * EPI_PITCH + lane];
+                        } else {
+                            for (int r = 0; r < mv; ++r)
+                                if (lane < nv) drow[(long long)r * P.ldd] = stg[r * EPI_PITCH + lane];
+                        }
                         __syncwarp();
                     } else {
                         const int m = mrow + lane;
