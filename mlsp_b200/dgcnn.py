@@ -24,24 +24,20 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import edgeconv, ops
+from . import edgeconv, linear, ops
 
 K = 20  # PointDA/Models.py:13
 
 
 def conv1x1(x: torch.Tensor, conv: nn.Module) -> torch.Tensor:
-    """A 1x1 Conv1d / Conv2d as the GEMM it is (torch.matmul -> one library SGEMM; cuDNN's fp32 convolution kernels take 3-5x
-    longer on these shapes, forward and backward).  x (B,C,N) or (B,C,N,k); same result as conv(x) up to summation order."""
-    W = conv.weight.flatten(1)                                # (O, C)
-    if x.dim() == 3:
-        y = torch.matmul(W, x)                               # (B,O,N)
-        return y if conv.bias is None else y + conv.bias.view(1, -1, 1)
-    B, C, N, k = x.shape
-    xf = x.permute(0, 2, 3, 1).reshape(B * N * k, C)          # free for the channels-last edge tensor of get_graph_feature
-    y = torch.matmul(xf, W.t())
-    if conv.bias is not None:
-        y = y + conv.bias
-    return y.view(B, N, k, -1).permute(0, 3, 1, 2)           # (B,O,N,k), channels-last strides again
+    """A 1x1 Conv1d / Conv2d as the GEMM it is, on the hand-written tcgen05 GEMM (mlsp_b200.linear -> mlsp_gemm_f32; fp32
+    result up to summation order).  x (B,C,N) or (B,C,N,k) in channels-last strides; same result as conv(x)."""
+    return linear.conv1x1(x, conv.weight, conv.bias)
+
+
+def fc(x: torch.Tensor, lin: nn.Linear) -> torch.Tensor:
+    """nn.Linear on a 2-D input through the same GEMM."""
+    return linear.linear(x, lin.weight, lin.bias)
 
 
 class Conv2dBlock(nn.Module):
@@ -68,7 +64,10 @@ class FcBlock(nn.Module):
             self.fc = nn.Sequential(nn.Linear(in_ch, out_ch), self.ac)
 
     def forward(self, x):
-        return self.fc(x)
+        x = fc(x, self.fc[0])
+        for m in list(self.fc)[1:]:
+            x = m(x)
+        return x
 
 
 class TransformNet(nn.Module):
@@ -89,7 +88,7 @@ class TransformNet(nn.Module):
         x = x.max(dim=-1, keepdim=False)[0].unsqueeze(3)
         x = self.conv2d3(x)
         x = torch.max(x, dim=2, keepdim=False)[0].view(x.size(0), -1)
-        x = self.fc3(self.fc2(self.fc1(x)))
+        x = fc(self.fc2(self.fc1(x)), self.fc3)
         x = x + torch.eye(self.K, device=x.device, dtype=x.dtype).view(1, self.K * self.K)
         return x.view(x.size(0), self.K, self.K)
 
@@ -106,7 +105,7 @@ class Classifier(nn.Module):
         self.mlp3 = nn.Linear(256, num_class)
 
     def forward(self, x):
-        return self.mlp3(self.dp2(self.mlp2(self.dp1(self.mlp1(x)))))
+        return fc(self.dp2(self.mlp2(self.dp1(self.mlp1(x)))), self.mlp3)
 
 
 class PointHead(nn.Module):
@@ -163,7 +162,7 @@ class DensityHead(nn.Module):
         x = self.dp1(F.relu(self.bn1(h1)))
         x = x.permute(0, 2, 1).reshape(-1, self.of1)
         x = self.dp1(self.mlp1(x))
-        p_vec = F.softmax(self.mlp3(self.dp2(self.mlp2(x))), dim=1)
+        p_vec = F.softmax(fc(self.dp2(self.mlp2(x)), self.mlp3), dim=1)
         return p_vec, self.fc2(p_vec)[:, 0]
 
     def forward(self, x):
@@ -200,7 +199,7 @@ class DGCNN(nn.Module):
         per-cloud bias from the 1024 global channels (constant over the points).  x_cat (B,512,N), x5 (B,1024)."""
         C = self.num_f_prev
         W = torch.cat([h.conv1.weight.squeeze(-1) for h in heads], dim=0)        # (sum O, 1536)
-        y = torch.matmul(W[:, :C], x_cat) + torch.matmul(x5, W[:, C:].t()).unsqueeze(2)
+        y = linear.conv1x1(x_cat, W[:, :C]) + linear.linear(x5, W[:, C:]).unsqueeze(2)
         return torch.split(y, [h.conv1.out_channels for h in heads], dim=1)
 
     def backbone(self, x):
@@ -208,7 +207,7 @@ class DGCNN(nn.Module):
         B = x.size(0)
         x0 = ops.get_graph_feature(x, None, k=self.k)                            # fused knn + gather, (B,6,N,k)
         T = self.input_transform_net(x0)
-        x = torch.matmul(T, x)
+        x = linear.apply_transform(T, x)
         feats = []
         h = x
         for layer in self._edge:                                                 # graph feature -> conv_2d -> max over k, x 4

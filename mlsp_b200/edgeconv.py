@@ -8,7 +8,7 @@ The reference builds every DGCNN layer as
 
 `edge_conv` computes the same (B,O,N) result and the same gradients without materialising anything of size
 B*N*k: the convolution is linear in [x_j - x_i | x_i], so  h_ij = Y[idx_ij] + Z[i]  with two point-wise products
-(one library GEMM on (B*N,C) x (C,2O)); BatchNorm in training mode needs only sum h and sum h^2 over the edges;
+(one tcgen05 GEMM on (B*N,C) x (C,2O), mlsp_gemm_f32); BatchNorm in training mode needs only sum h and sum h^2 over the edges;
 BatchNorm + LeakyReLU are monotone per channel, so the max over k commutes with them (min where gamma < 0).
 Kernels: mlsp_b200/csrc/edgeconv.cu behind mlsp_edgeconv_* (include/mlsp_b200.h).  No CPU path.
 
@@ -22,7 +22,7 @@ import ctypes
 import torch
 from torch import nn
 
-from . import _lib
+from . import _lib, linear
 from ._lib import MlspError
 from .ops import _ptr, _require_cuda_f32, _stream, knn
 
@@ -92,22 +92,24 @@ class _EdgeConvReduce(torch.autograd.Function):
 
 
 class _PointwiseYZ(torch.autograd.Function):
-    """yz (B,N,2O) = [Y | Z],  Y = s*Wa x,  Z = s*(Wb - Wa) x + s*bias  -- the layer's one library GEMM together with the
-    weight split W = [Wa | Wb] -> [Wa ; Wb - Wa] and the sign fold (s = +-1 per output channel, see edge_conv_functional).
-    One autograd node instead of a dozen: the backward keeps every operand in the layout it already has (grad_x comes out
-    as (B,C,N) directly), makes the weight gradient from B partial products summed afterwards (as a single
-    (2O x B*N) x (B*N x C) product it is a long reduction that cuBLAS runs on a handful of CTAs), and un-splits it."""
+    """yz (B,N,2O) = [Y | Z],  Y = s*Wa x,  Z = s*(Wb - Wa) x + s*bias  -- the layer's one GEMM (mlsp_gemm_f32: tcgen05, fp32
+    operands as three bf16 pieces, fp32-faithful) together with the weight split W = [Wa | Wb] -> [Wa ; Wb - Wa] and the
+    sign fold (s = +-1 per output channel, see edge_conv_functional).  One autograd node: every operand is read in the
+    layout it already has (x and grad_x are (B,C,N), yz and its gradient (B,N,2O): no transposed copies), the weight
+    gradient is made from B partial products (K = N points each) summed afterwards, and un-split."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, sgn):
         B, C, _ = x.shape
         Wcat = _split_weight(weight, C)                                        # (2O, C)
+        zb = None
         if sgn is not None:
             Wcat = Wcat * sgn.repeat(2).unsqueeze(1)
-        yz = torch.bmm(x.transpose(1, 2), Wcat.t().unsqueeze(0).expand(B, -1, -1))
         if bias is not None:
             zb = bias if sgn is None else bias * sgn
-            yz[..., Wcat.shape[0] // 2:] += zb
+            zb = torch.cat((torch.zeros_like(zb), zb))                          # the bias belongs to the Z half only
+        # x[b] (C,N) is the GEMM's M-major A operand as it lies in memory; yz comes out point-major (B,N,2O)
+        yz = linear.gemm_nt(x.transpose(1, 2), Wcat, zb)
         ctx.save_for_backward(x, Wcat, sgn)
         ctx.wshape = weight.shape
         return yz
@@ -117,10 +119,11 @@ class _PointwiseYZ(torch.autograd.Function):
         x, Wcat, sgn = ctx.saved_tensors
         O = Wcat.shape[0] // 2
         gx = gw = gb = None
+        dyz = dyz.contiguous()
         if ctx.needs_input_grad[0]:
-            gx = torch.matmul(Wcat.t(), dyz.transpose(1, 2))                      # (C,2O) x (B,2O,N) -> (B,C,N)
+            gx = linear.gemm_nt(dyz, Wcat.t(), out_colmajor=True).transpose(1, 2)   # (B,N,2O) x (2O,C) -> stored (B,C,N)
         if ctx.needs_input_grad[1]:
-            g = torch.bmm(dyz.transpose(1, 2), x.transpose(1, 2)).sum(dim=0)      # (B,2O,C) partials -> (2O,C)
+            g = linear.gemm_nt(dyz.transpose(1, 2), x).sum(dim=0)                 # (B,2O,C) partials (K = N points) -> (2O,C)
             if sgn is not None:
                 g = g * sgn.repeat(2).unsqueeze(1)
             gw = torch.cat((g[:O] - g[O:], g[O:]), dim=1).reshape(ctx.wshape)     # d/dWa = gY - gZ, d/dWb = gZ

@@ -161,6 +161,32 @@ def _reduce_rows_product(gy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return part.sum(dim=0)
 
 
+class _ApplyTransform(torch.autograd.Function):
+    """y[b] (O,N) = T[b] (O,C) x[b] (C,N) with a per-cloud matrix -- the input-transform product of PointDA/Models.py:113."""
+
+    @staticmethod
+    def forward(ctx, T, x):
+        ctx.save_for_backward(T, x)
+        return gemm_nt(x.transpose(1, 2), T, out_colmajor=True).transpose(1, 2)
+
+    @staticmethod
+    def backward(ctx, gy):
+        T, x = ctx.saved_tensors
+        gT = gx = None
+        if _mat(gy, "gy") is None:
+            gy = gy.contiguous()
+        if ctx.needs_input_grad[0]:
+            gT = gemm_nt(gy, x)                                                              # (B,O,C), K = N points
+        if ctx.needs_input_grad[1]:
+            gx = gemm_nt(gy.transpose(1, 2), T.transpose(1, 2), out_colmajor=True).transpose(1, 2)
+        return gT, gx
+
+
+def apply_transform(T: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """torch.matmul(T, x) for T (B,O,C), x (B,C,N)."""
+    return _ApplyTransform.apply(T, x if _mat(x.transpose(1, 2), "x") is not None else x.contiguous())
+
+
 def conv1x1(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
     """nn.Conv1d(kernel_size=1) / nn.Conv2d(kernel_size=1):  x (B,C,N) -> (B,O,N);  x (B,C,N,k) in channels-last strides (what
     get_graph_feature returns) -> (B,O,N,k) in channels-last strides.  weight (O,C[,1[,1]])."""

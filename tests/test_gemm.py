@@ -124,3 +124,35 @@ def test_conv1x1_and_linear_autograd_match_torch_fp64():
     y2d.backward(ge.double())
     for got, ref in ((y2, y2d), (e.grad, ed.grad), (W2.grad, W2d.grad)):
         assert float((got.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), (got.shape,)
+
+
+@needs_gpu
+def test_pointwise_yz_node_matches_autograd_of_the_same_expression():
+    """The EdgeConv layer's GEMM node (weight split + sign fold + bias + mlsp_gemm_f32) with its hand-written backward: grad_x
+    straight in (B,C,N), weight gradient from B partial products, un-split -- against fp64 autograd of the same expression."""
+    from mlsp_b200 import edgeconv
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    C, O = 5, 8
+    for use_b, use_s in ((True, True), (False, True), (True, False), (False, False)):
+        x = torch.randn(3, C, 8, device=dev, requires_grad=True)
+        Wf = torch.randn(O, 2 * C, 1, 1, device=dev, requires_grad=True)
+        bf = torch.randn(O, device=dev, requires_grad=True) if use_b else None
+        sg = torch.tensor([1.0, -1.0] * (O // 2), device=dev) if use_s else None
+        gy = torch.randn(3, 8, 2 * O, device=dev)
+        y = edgeconv._PointwiseYZ.apply(x, Wf, bf, sg)
+        y.backward(gy)
+        got = (x.grad.clone(), Wf.grad.clone(), bf.grad.clone() if use_b else None)
+        xd, Wd = x.detach().double().requires_grad_(True), Wf.detach().double().requires_grad_(True)
+        bd = bf.detach().double().requires_grad_(True) if use_b else None
+        Wc = edgeconv._split_weight(Wd, C)
+        if use_s:
+            Wc = Wc * sg.double().repeat(2).view(2 * O, 1)
+        ref = torch.matmul(xd.transpose(1, 2), Wc.t())
+        if use_b:
+            zb = bd * sg.double() if use_s else bd
+            ref = ref + torch.cat((torch.zeros_like(zb), zb)).view(1, 1, 2 * O)
+        ref.backward(gy.double())
+        assert torch.allclose(y.double(), ref, atol=1e-5) and got[0].is_contiguous()
+        assert torch.allclose(got[0].double(), xd.grad, atol=1e-5) and torch.allclose(got[1].double(), Wd.grad, atol=1e-5)
+        assert not use_b or torch.allclose(got[2].double(), bd.grad, atol=1e-5)

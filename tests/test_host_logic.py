@@ -218,31 +218,6 @@ def test_edgeconv_weight_algebra():
         edgeconv.FusedEdgeConv.from_reference([seq, torch.nn.Conv2d(8, 8, 1)])
     with pytest.raises(M.MlspError):
         edgeconv.edge_conv(torch.zeros(1, 3, 8), torch.zeros(4, 6))   # no CPU path
-    # the layer's GEMM node (weight split + sign fold + bias + GEMM) with its hand-written backward: grad_x straight in
-    # (B,C,N), weight gradient from B partial products, un-split -- against autograd of the same expression
-    for use_b, use_s in ((True, True), (False, True), (True, False), (False, False)):
-        x = torch.randn(3, C, 7, dtype=torch.float64, requires_grad=True)
-        Wf = torch.randn(O, 2 * C, 1, 1, dtype=torch.float64, requires_grad=True)
-        bf = torch.randn(O, dtype=torch.float64, requires_grad=True) if use_b else None
-        sg = torch.tensor([1.0, -1.0] * (O // 2), dtype=torch.float64) if use_s else None
-        gy = torch.randn(3, 7, 2 * O, dtype=torch.float64)
-        y = edgeconv._PointwiseYZ.apply(x, Wf, bf, sg)
-        y.backward(gy)
-        got = (x.grad.clone(), Wf.grad.clone(), bf.grad.clone() if use_b else None)
-        x.grad = Wf.grad = None
-        if use_b:
-            bf.grad = None
-        Wc = edgeconv._split_weight(Wf, C)
-        if use_s:
-            Wc = Wc * sg.repeat(2).view(2 * O, 1)
-        ref = torch.matmul(x.transpose(1, 2), Wc.t())
-        if use_b:
-            zb = bf * sg if use_s else bf
-            ref = ref + torch.cat((torch.zeros_like(zb), zb)).view(1, 1, 2 * O)
-        ref.backward(gy)
-        assert torch.allclose(y, ref, atol=1e-12) and got[0].is_contiguous()
-        assert torch.allclose(got[0], x.grad, atol=1e-12) and torch.allclose(got[1], Wf.grad, atol=1e-12)
-        assert not use_b or torch.allclose(got[2], bf.grad, atol=1e-12)
 
 
 # ---- mlsp_b200.lazy: the deferred graph feature (EdgeConv fusion behind the reference's unchanged model code)
