@@ -909,6 +909,28 @@ def test_knn_tensor_activations_far_from_the_origin(dev, orc):
     assert np.array_equal(_np(feat.permute(0, 2, 3, 1)), orc.edge_gather(x.numpy(), ref))
 
 
+@pytest.mark.parametrize("name,layers", [("activations_da", ("x1", "x2", "x3")), ("activations_seg", ("x1", "x2"))])
+def test_knn_tensor_on_real_backbone_activations(golden, dev, orc, name, layers):
+    """the feature-space kNN on the activations it meets in the model -- x1/x2/x3 of the seeded reference
+    DGCNN (B=2, N=1024; tests/golden/activations_da.npz) and the BatchNorm-free, bias-shifted layers of PointSegDA (N=2048;
+    activations_seg.npz), both made by oracle/gen_golden_activations.py with the reference's own classes.  tcgen05 path:
+    bit-identical with the oracle, identical with the reference's own knn output except at certified fp64 near-ties, and the
+    filter certifies (almost) every row -- no silent fallback to the exact streaming selection."""
+    from mlsp_b200 import _lib
+    g = golden(name)
+    for lay in layers:
+        x = g[lay]
+        B, C, N = x.shape
+        ref_idx = g["idx_" + lay].astype(np.int64)
+        idx, st = M.knn(torch.from_numpy(x).to(dev), 20, flags=_lib.KNN_TENSOR_ONLY, return_stats=True)
+        idx = _np(idx)
+        assert np.array_equal(idx, orc.knn(x, 20)), lay
+        assert st["fallback_rows"] <= 0.02 * B * N, (lay, st)
+        bad, unc = knn_rank_check(x, idx, 20)
+        bad_ref, unc_ref = knn_rank_check(x, ref_idx, 20)
+        assert unc == 0 and (idx != ref_idx).sum() <= bad + bad_ref, (lay, bad, bad_ref)
+
+
 def test_lazy_graph_feature_fuses_reference_shaped_layers(dev):
     """mlsp_b200.lazy on the GPU: `conv_2d(get_graph_feature(x)).max(dim=-1)[0]` written exactly like the reference writes
     it (PointDA/Models.py:114-116; PointSegDA/Models.py:171-174) runs as one edge_conv -- same output and gradients as the

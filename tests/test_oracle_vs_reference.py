@@ -1,5 +1,5 @@
 """Container-only cross-check: every committed fixture regenerates byte for byte from the committed recipes
-(oracle/gen_golden.py, oracle/gen_golden_edgeconv.py), which call the REFERENCE'S OWN functions.  Skipped where the
+(oracle/gen_golden.py, oracle/gen_golden_edgeconv.py, oracle/gen_golden_activations.py), which call the REFERENCE'S OWN functions.  Skipped where the
 reference checkout is absent (the GPU box); arrays are compared, not the zip containers (timestamps)."""
 import importlib
 import os
@@ -14,7 +14,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")
 
 
-@pytest.mark.parametrize("modname", ["oracle.gen_golden", "oracle.gen_golden_edgeconv"])
+@pytest.mark.parametrize("modname", ["oracle.gen_golden", "oracle.gen_golden_edgeconv", "oracle.gen_golden_activations"])
 def test_fixtures_regenerate_identically(tmp_path, modname, monkeypatch):
     mod = importlib.import_module(modname)
     monkeypatch.setattr(mod, "OUT", str(tmp_path))
