@@ -288,6 +288,16 @@ MLSP_API int mlsp_gemm_f32(const float *A, int a_kmajor, long long lda, long lon
                   long long ldb, long long b_batch_stride, float *D, int d_rowmajor, long long ldd, long long d_batch_stride,
                   const float *bias, int M, int N, int K, int batch, void *stream);
 
+/* ---- scan_input / p_scan, MLSP/mlsp.py:54-94 (the Scan_on_trgt branch, PointDA/trainer.py:492-503; 8f rank 3) ----
+ * X (B,N,3) contiguous, mutated in place; rot (B,3,3) double: the rotation matrix of every cloud (rotate_point_cloud_3d,
+ * mlsp.py:96-112 -- drawn by the caller from numpy's RNG like the reference); pixel = int(2 / pixel_size).
+ * Per cloud: p' = p . rot (fp64), bin = int((p'_z+1)/2*pixel*pixel + (p'_y+1)/2*pixel) on a (pixel+5)^2 grid (negative values
+ * wrap once, like the Python list index they are), the point with the largest p'_x of every bin (first index on ties) is
+ * kept: mask (B,N,3) = 0 there and X unchanged; every other point: mask = 1, X = 0.
+ * err_flag (device int): set to 1 if a bin index falls outside the grid (the reference raises IndexError).
+ * (pixel+5)^2 <= 3072 (the reference draws pixel_size in [0.045, 0.075]: pixel <= 44). */
+MLSP_API int mlsp_scan_zbuffer(float *X, int B, int N, const double *rot, int pixel, float *mask, int *err_flag, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ from .ops import (  # noqa: F401
     radius_search,
     reconstruction_loss,
     region_mean,
+    scan_input,
     target_structure,
 )
 

@@ -379,6 +379,47 @@ def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxel
     return X, mask
 
 
+def _rotation_matrix_3d() -> np.ndarray:
+    """rotate_point_cloud_3d's matrix, MLSP/mlsp.py:96-112: three angles from numpy's RNG, R = R1 @ R2 @ R3 (fp64)."""
+    ang = np.random.rand(3) * 2 * np.pi
+    c, s = np.cos(ang), np.sin(ang)
+    r1 = np.array([[c[0], 0, s[0]], [0, 1, 0], [-s[0], 0, c[0]]])
+    r2 = np.array([[1, 0, 0], [0, c[1], -s[1]], [0, s[1], c[1]]])
+    r3 = np.array([[c[2], -s[2], 0], [s[2], c[2], 0], [0, 0, 1]])
+    return np.matmul(np.matmul(r1, r2), r3)
+
+
+def scan_input(X: torch.Tensor, device="cuda:0", pixel_size: float = 0.07):
+    """scan_input(X, device, pixel_size): MLSP/mlsp.py:54-64 with p_scan :66-94 -- the single-view scan simulation of the
+    Scan_on_trgt branch (PointDA/trainer.py:492-503).  X (B,N,3) is mutated in place and returned with mask (B,N,3): per
+    cloud a random rotation, a z-buffer over a (pixel+5)^2 grid of the rotated cloud; the visible points keep their
+    coordinates (mask 0), all others are zeroed (mask 1).  The reference's RNG streams are consumed on the host in its
+    order -- `random.uniform` once for the pixel size (the argument is ignored, as in the reference), numpy's `rand(3)`
+    once per cloud -- so seeded runs give the reference's result; the z-buffer runs on the GPU, one launch for the batch,
+    no device->host copy of the clouds (the reference moves every cloud to the CPU and loops over its points in Python).
+    A bin index outside the grid raises IndexError like the reference's list indexing (one 4-byte device->host read)."""
+    import random
+    _require_cuda_f32(X, "scan_input")
+    if X.dim() != 3 or X.size(2) != 3:
+        raise MlspError(f"scan_input: expected (B,N,3), got {tuple(X.shape)}")
+    pixel_size = random.uniform(0.045, 0.075)                              # mlsp.py:56
+    pixel = int(2 / pixel_size)
+    B, N, _ = X.shape
+    rot = np.stack([_rotation_matrix_3d() for _ in range(B)])              # one rand(3) per cloud, in batch order
+    Xc = X if X.is_contiguous() else X.contiguous()
+    mask = torch.empty((B, N, 3), dtype=torch.float32, device=X.device)
+    stage = torch.from_numpy(rot).pin_memory()
+    rot_d = stage.to(X.device, non_blocking=True)
+    err = torch.empty(1, dtype=torch.int32, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.call("mlsp_scan_zbuffer", _ptr(Xc), B, N, _ptr(rot_d), pixel, _ptr(mask), _ptr(err), _stream(X.device))
+    if Xc is not X:
+        X.copy_(Xc)
+    if int(err.item()):
+        raise IndexError("scan_input: a point falls outside the scan grid (list index out of range in p_scan)")
+    return X, mask
+
+
 def _deform_voxel_groups(X, mask, lookup, region_ids, DefRec_dist, groups):
     """groups > 1 (MLSP/mlsp.py:37-50: the walk over region_ids continues until `groups` regions with >= 40 points
     were deformed; no shipped caller passes it).  The histogram comes back to the host (27 ints per cloud), the draws

@@ -37,6 +37,7 @@ TARGETS = {
     },
     "MLSP.mlsp": {
         "deform_input": ops.deform_input,
+        "scan_input": ops.scan_input,
         "chamfer_distance": ops.chamfer_distance,
         "reconstruction_loss": ops.reconstruction_loss,
         "findneareat_index": ops.findneareat_index,

@@ -148,3 +148,49 @@ def pca_normals(xyz_bnc, near, return_gap=False):
         gap = (w[..., 1] - w[..., 0]) / np.maximum(w[..., 2], 1e-300)
         return n, gap
     return n
+
+
+def rotation_matrix_3d():
+    """rotate_point_cloud_3d's matrix (MLSP/mlsp.py:96-112): consumes np.random.rand(3)."""
+    ang = np.random.rand(3) * 2 * np.pi
+    c, s = np.cos(ang), np.sin(ang)
+    r1 = np.array([[c[0], 0, s[0]], [0, 1, 0], [-s[0], 0, c[0]]])
+    r2 = np.array([[1, 0, 0], [0, c[1], -s[1]], [0, s[1], c[1]]])
+    r3 = np.array([[c[2], -s[2], 0], [s[2], c[2], 0], [0, 0, 1]])
+    return np.matmul(np.matmul(r1, r2), r3)
+
+
+def p_scan(pc, pixel_size, rot=None):
+    """p_scan of MLSP/mlsp.py:66-94, vectorised: (N,3) float32 -> (scan_points, mask).  Bin = int((z'+1)/2*pixel*pixel +
+    (y'+1)/2*pixel) of the rotated cloud on a (pixel+5)^2 grid (negative bins wrap like the Python list index they are);
+    per bin the point with the largest x' survives, the first one on ties (the reference replaces on strict `>` only)."""
+    pixel = int(2 / pixel_size)
+    if rot is None:
+        rot = rotation_matrix_3d()
+    r = np.dot(pc.reshape((-1, 3)), rot)                                   # float32 . float64 -> float64, like the reference
+    comp = ((r[:, 2] + 1) / 2 * pixel * pixel + (r[:, 1] + 1) / 2 * pixel).astype(np.int64)
+    cells = (pixel + 5) * (pixel + 5)
+    comp = np.where(comp < 0, comp + cells, comp)
+    if ((comp < 0) | (comp >= cells)).any():
+        raise IndexError("list index out of range")
+    # first index of the per-bin maximum: sort by (bin, -x', index) and take the head of every bin
+    order = np.lexsort((np.arange(len(comp)), -r[:, 0], comp))
+    head = np.ones(len(comp), bool)
+    head[1:] = comp[order][1:] != comp[order][:-1]
+    keep = order[head]
+    mask = np.ones_like(pc)
+    mask[keep, :3] = 0.0
+    out = np.zeros_like(pc)
+    out[keep] = pc[keep]
+    return out, mask
+
+
+def scan_input(X, pixel_size=0.07):
+    """scan_input of MLSP/mlsp.py:54-64 on a (B,N,3) float32 array: random.uniform for the pixel size, then per cloud p_scan."""
+    import random
+    pixel_size = random.uniform(0.045, 0.075)
+    X = X.copy()
+    mask = np.zeros_like(X)
+    for b in range(X.shape[0]):
+        X[b], mask[b] = p_scan(X[b], pixel_size)
+    return X, mask

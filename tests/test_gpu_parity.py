@@ -931,6 +931,51 @@ def test_knn_tensor_on_real_backbone_activations(golden, dev, orc, name, layers)
         assert unc == 0 and (idx != ref_idx).sum() <= bad + bad_ref, (lay, bad, bad_ref)
 
 
+def test_scan_input_golden(golden, dev):
+    """8f rank 3: scan_input (MLSP/mlsp.py:54-94) as one z-buffer launch, against the reference's own function (seeded
+    python + numpy RNG streams consumed in its order): clouds and masks bit for bit, in place, and the RNG streams left where
+    the reference leaves them."""
+    import random
+    g = golden("scan_input")
+    X = torch.from_numpy(g["X"]).to(dev)
+    random.seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]))
+    out, mask = M.scan_input(X, dev)
+    assert out is X
+    assert np.array_equal(_np(out), g["out"]) and np.array_equal(_np(mask), g["mask"])
+    after = (random.random(), np.random.rand())
+    random.seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]))
+    from oracle import np_ops
+    np_ops.scan_input(g["X"])
+    assert after == (random.random(), np.random.rand())
+    # a strided (B,N,3) view (the permuted trainer tensor) and a point outside the grid
+    Xs = torch.from_numpy(g["X"]).to(dev).permute(0, 2, 1).contiguous().permute(0, 2, 1)
+    random.seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]))
+    out2, mask2 = M.scan_input(Xs, dev)
+    assert np.array_equal(_np(out2), g["out"]) and np.array_equal(_np(mask2), g["mask"])
+    # a point far outside the unit ball: its bin wraps (negative list index) or leaves the grid (IndexError) -- whichever
+    # the restatement of the reference's indexing does for these seeds, the kernel does too
+    far_h = g["X"].copy()
+    far_h[0, 0] = (0.0, 9.0, 9.0)
+    for seed in (1, 2, 3, 4):
+        random.seed(seed)
+        np.random.seed(seed)
+        try:
+            want = np_ops.scan_input(far_h)
+        except IndexError:
+            want = None
+        random.seed(seed)
+        np.random.seed(seed)
+        if want is None:
+            with pytest.raises(IndexError):
+                M.scan_input(torch.from_numpy(far_h).to(dev), dev)
+        else:
+            got = M.scan_input(torch.from_numpy(far_h).to(dev), dev)
+            assert np.array_equal(_np(got[0]), want[0]) and np.array_equal(_np(got[1]), want[1])
+
+
 def test_lazy_graph_feature_fuses_reference_shaped_layers(dev):
     """mlsp_b200.lazy on the GPU: `conv_2d(get_graph_feature(x)).max(dim=-1)[0]` written exactly like the reference writes
     it (PointDA/Models.py:114-116; PointSegDA/Models.py:171-174) runs as one edge_conv -- same output and gradients as the

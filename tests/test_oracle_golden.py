@@ -56,6 +56,18 @@ def test_knn_on_real_backbone_activations(golden, name, layers):
         assert (idx != ref_idx).sum() <= bad + bad_ref, lay
 
 
+def test_scan_input(golden):
+    """oracle/np_ops.scan_input (vectorised z-buffer) against the reference's own scan_input / p_scan (MLSP/mlsp.py:54-94):
+    bit-identical clouds and masks for the same seeds, duplicates (ties inside a bin) included."""
+    import random
+    g = golden("scan_input")
+    random.seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]))
+    out, mask = np_ops.scan_input(g["X"])
+    assert np.array_equal(out, g["out"]) and np.array_equal(mask, g["mask"])
+    assert (mask[3, :512, 0] == 0).sum() > 0 and (mask[3, 512:, 0] == 0).sum() == 0       # of two equal points the first wins
+
+
 @pytest.mark.parametrize("name", ["ggf_3", "ggf_16"])
 def test_edge_gather(golden, name):
     g = golden(name)

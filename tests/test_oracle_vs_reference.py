@@ -14,7 +14,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 pytestmark = pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present")
 
 
-@pytest.mark.parametrize("modname", ["oracle.gen_golden", "oracle.gen_golden_edgeconv", "oracle.gen_golden_activations"])
+@pytest.mark.parametrize("modname", ["oracle.gen_golden", "oracle.gen_golden_edgeconv", "oracle.gen_golden_activations", "oracle.gen_golden_scan"])
 def test_fixtures_regenerate_identically(tmp_path, modname, monkeypatch):
     mod = importlib.import_module(modname)
     monkeypatch.setattr(mod, "OUT", str(tmp_path))
