@@ -270,6 +270,16 @@ MLSP_API int mlsp_edgeconv_bwd(const float *g, int64_t g_bstride, const float *y
                       const float *rowsum, const float *coef, int B, int N, int O, int k, float slope, int bn_train,
                       float *dyz, float *dgamma_dbeta, void *ws, size_t ws_bytes, void *stream);
 
+/* weight side of the layer product (one launch instead of a dozen elementwise kernels):
+ *   W (O,2C) = [Wa | Wb] over [x_j - x_i | x_i]; scale (O) or NULL (BatchNorm weight / fixed affine scale); bias (O) or NULL
+ *   -> Wcat (2O,C) = [s Wa ; s (Wb - Wa)], sgn (O) = s = -1 where scale < 0 else +1, zb (2O, may be NULL when bias is NULL) =
+ *   [0 ; s bias]: yz = x^T Wcat^T + zb is mlsp_gemm_f32's job (conv_2d's nn.Conv2d, PointDA/model_utils.py:45-63). */
+MLSP_API int mlsp_edgeconv_weight_prep(const float *W, const float *scale, const float *bias, int O, int C, float *Wcat, float *sgn,
+                              float *zb, void *stream);
+
+/* part (Z,2O,C) = partial products dyz^T x  ->  gW (O,2C) = [s (gY - gZ) | s gZ], summed over Z in a fixed order */
+MLSP_API int mlsp_edgeconv_weight_grad(const float *part, int Z, const float *sgn, int O, int C, float *gW, void *stream);
+
 /* ---- the point-wise products around the neighbourhood engine (8f ranks 1, 4): every 1x1 convolution / Linear of the DGCNN ----
  * Replaces the library GEMM behind nn.Conv2d(kernel_size=1) in conv_2d (PointDA/model_utils.py:45-63, used by the EdgeConv
  * layers PointDA/Models.py:114-128 and by transform_net model_utils.py:92-130), nn.Conv1d(kernel_size=1) of conv5 and of the

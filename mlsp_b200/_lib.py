@@ -44,6 +44,8 @@ SIGNATURES = {
     "mlsp_edgeconv_bn_coeffs": [_P, _P, _P, _I, ctypes.c_double, _F, _P, _P, _P, _P, _F, _P],
     "mlsp_edgeconv_apply_fwd": [_P, _P, _I, _I, _I, _F, _P, _P],
     "mlsp_edgeconv_bwd": [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _Z, _P],
+    "mlsp_edgeconv_weight_prep": [_P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "mlsp_edgeconv_weight_grad": [_P, _I, _P, _I, _I, _P, _P],
     "mlsp_scan_zbuffer": [_P, _I, _I, _P, _I, _P, _P, _P],
     "mlsp_gemm_f32": [_P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _I, _I, _I, _P],
 }

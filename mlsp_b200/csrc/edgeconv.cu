@@ -299,6 +299,47 @@ __global__ void edgeconv_param_grads_kernel(const double *__restrict__ dsum, int
     }
 }
 
+// ---- weight side of the layer's GEMM (one launch each instead of a dozen elementwise torch kernels per layer and step)
+// W (O,2C) = [Wa | Wb] over [x_j - x_i | x_i], scale (O) or NULL = the BatchNorm weight / fixed affine scale, bias (O) or NULL
+//   -> Wcat (2O,C) = [s Wa ; s (Wb - Wa)],  sgn (O) = s = sign(scale) (+1 where scale >= 0 or absent),  zb (2O) = [0 ; s bias]
+__global__ void edgeconv_weight_prep_kernel(const float *__restrict__ W, const float *__restrict__ scale, const float *__restrict__ bias,
+                                            int O, int C, float *__restrict__ Wcat, float *__restrict__ sgn, float *__restrict__ zb)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= O * C) return;
+    const int o = t / C, c = t - o * C;
+    const float s = (scale && scale[o] < 0.0f) ? -1.0f : 1.0f;
+    const float wa = W[(size_t)o * 2 * C + c], wb = W[(size_t)o * 2 * C + C + c];
+    Wcat[(size_t)o * C + c] = s * wa;
+    Wcat[(size_t)(O + o) * C + c] = s * (wb - wa);
+    if (c == 0) {
+        sgn[o] = s;
+        if (zb) {
+            zb[o] = 0.0f;
+            zb[O + o] = bias ? s * bias[o] : 0.0f;
+        }
+    }
+}
+
+// part (Z,2O,C): partial products dyz^T x of the batch slices -> gW (O,2C) = [s (gY - gZ) | s gZ]  (d/dWa = gY - gZ, d/dWb = gZ),
+// summed over Z in a fixed order (deterministic)
+__global__ void edgeconv_weight_grad_kernel(const float *__restrict__ part, int Z, const float *__restrict__ sgn, int O, int C,
+                                            float *__restrict__ gW)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= O * C) return;
+    const int o = t / C, c = t - o * C;
+    const size_t plane = (size_t)2 * O * C;
+    float gy = 0.0f, gz = 0.0f;
+    for (int z = 0; z < Z; ++z) {
+        gy += part[z * plane + (size_t)o * C + c];
+        gz += part[z * plane + (size_t)(O + o) * C + c];
+    }
+    const float s = sgn ? sgn[o] : 1.0f;
+    gW[(size_t)o * 2 * C + c] = s * (gy - gz);
+    gW[(size_t)o * 2 * C + C + c] = s * gz;
+}
+
 static int ec_block(int G) { return EC_THREADS / G * G; }      // largest multiple of G that fits a block
 
 size_t edgeconv_workspace_bytes(int B, int O, int N)
@@ -422,6 +463,25 @@ int mlsp_edgeconv_bwd(const float *g, int64_t g_bstride, const float *yz, const 
         edgeconv_param_grads_kernel<<<(O + 127) / 128, 128, 0, s>>>(dsum, O, dgamma_dbeta);
         MLSP_LAUNCH_CHECK("edgeconv_param_grads_kernel");
     }
+    return MLSP_OK;
+}
+int mlsp_edgeconv_weight_prep(const float *W, const float *scale, const float *bias, int O, int C, float *Wcat, float *sgn,
+                              float *zb, void *stream)
+{
+    MLSP_REQUIRE(W && Wcat && sgn, MLSP_EINVAL, "edgeconv_weight_prep: null pointer");
+    MLSP_REQUIRE(O > 0 && C > 0 && (long long)O * C < (1ll << 30), MLSP_EINVAL, "edgeconv_weight_prep: bad shape O=%d C=%d", O, C);
+    MLSP_REQUIRE(zb || !bias, MLSP_EINVAL, "edgeconv_weight_prep: bias without zb");
+    edgeconv_weight_prep_kernel<<<(O * C + 255) / 256, 256, 0, as_stream(stream)>>>(W, scale, bias, O, C, Wcat, sgn, zb);
+    MLSP_LAUNCH_CHECK("edgeconv_weight_prep_kernel");
+    return MLSP_OK;
+}
+
+int mlsp_edgeconv_weight_grad(const float *part, int Z, const float *sgn, int O, int C, float *gW, void *stream)
+{
+    MLSP_REQUIRE(part && gW, MLSP_EINVAL, "edgeconv_weight_grad: null pointer");
+    MLSP_REQUIRE(Z > 0 && O > 0 && C > 0 && (long long)O * C < (1ll << 30), MLSP_EINVAL, "edgeconv_weight_grad: bad shape");
+    edgeconv_weight_grad_kernel<<<(O * C + 255) / 256, 256, 0, as_stream(stream)>>>(part, Z, sgn, O, C, gW);
+    MLSP_LAUNCH_CHECK("edgeconv_weight_grad_kernel");
     return MLSP_OK;
 }
 }

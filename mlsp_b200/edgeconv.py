@@ -94,43 +94,48 @@ class _EdgeConvReduce(torch.autograd.Function):
 class _PointwiseYZ(torch.autograd.Function):
     """yz (B,N,2O) = [Y | Z],  Y = s*Wa x,  Z = s*(Wb - Wa) x + s*bias  -- the layer's one GEMM (mlsp_gemm_f32: tcgen05, fp32
     operands as three bf16 pieces, fp32-faithful) together with the weight split W = [Wa | Wb] -> [Wa ; Wb - Wa] and the
-    sign fold (s = +-1 per output channel, see edge_conv_functional).  One autograd node: every operand is read in the
+    sign fold (s = sign of the BatchNorm / affine scale per output channel, made by the same prep launch).  One autograd node: every operand is read in the
     layout it already has (x and grad_x are (B,C,N), yz and its gradient (B,N,2O): no transposed copies), the weight
     gradient is made from B partial products (K = N points each) summed afterwards, and un-split."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, sgn):
+    def forward(ctx, x, weight, bias, scale):
         B, C, _ = x.shape
-        Wcat = _split_weight(weight, C)                                        # (2O, C)
-        zb = None
-        if sgn is not None:
-            Wcat = Wcat * sgn.repeat(2).unsqueeze(1)
-        if bias is not None:
-            zb = bias if sgn is None else bias * sgn
-            zb = torch.cat((torch.zeros_like(zb), zb))                          # the bias belongs to the Z half only
+        W = weight.detach().reshape(weight.shape[0], -1).contiguous()
+        O = W.shape[0]
+        if W.shape[1] != 2 * C:
+            raise MlspError(f"edge_conv: weight has {W.shape[1]} input channels, expected 2*C = {2 * C}")
+        dev = x.device
+        Wcat = torch.empty((2 * O, C), dtype=torch.float32, device=dev)
+        sgn = torch.empty(O, dtype=torch.float32, device=dev)
+        zb = torch.empty(2 * O, dtype=torch.float32, device=dev) if bias is not None else None
+        with torch.cuda.device(dev):                                           # weight split, sign fold, bias: one launch
+            _lib.call("mlsp_edgeconv_weight_prep", _ptr(W), _ptr(scale.detach().float().contiguous() if scale is not None else None),
+                      _ptr(bias.detach().float().contiguous() if bias is not None else None), O, C, _ptr(Wcat), _ptr(sgn), _ptr(zb),
+                      _stream(dev))
         # x[b] (C,N) is the GEMM's M-major A operand as it lies in memory; yz comes out point-major (B,N,2O)
         yz = linear.gemm_nt(x.transpose(1, 2), Wcat, zb)
         ctx.save_for_backward(x, Wcat, sgn)
         ctx.wshape = weight.shape
-        return yz
+        ctx.mark_non_differentiable(sgn)
+        return yz, sgn
 
     @staticmethod
-    def backward(ctx, dyz):
+    def backward(ctx, dyz, _dsgn):
         x, Wcat, sgn = ctx.saved_tensors
-        O = Wcat.shape[0] // 2
+        O, C = Wcat.shape[0] // 2, Wcat.shape[1]
         gx = gw = gb = None
         dyz = dyz.contiguous()
         if ctx.needs_input_grad[0]:
             gx = linear.gemm_nt(dyz, Wcat.t(), out_colmajor=True).transpose(1, 2)   # (B,N,2O) x (2O,C) -> stored (B,C,N)
         if ctx.needs_input_grad[1]:
-            g = linear.gemm_nt(dyz.transpose(1, 2), x).sum(dim=0)                 # (B,2O,C) partials (K = N points) -> (2O,C)
-            if sgn is not None:
-                g = g * sgn.repeat(2).unsqueeze(1)
-            gw = torch.cat((g[:O] - g[O:], g[O:]), dim=1).reshape(ctx.wshape)     # d/dWa = gY - gZ, d/dWb = gZ
+            part = linear.gemm_nt(dyz.transpose(1, 2), x)                         # (B,2O,C) partial products, K = N points each
+            gw = torch.empty((O, 2 * C), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):                                     # sum over B, sign, un-split: one launch
+                _lib.call("mlsp_edgeconv_weight_grad", _ptr(part), part.shape[0], _ptr(sgn), O, C, _ptr(gw), _stream(x.device))
+            gw = gw.reshape(ctx.wshape)
         if ctx.needs_input_grad[2]:
-            gb = dyz[..., O:].sum(dim=(0, 1))
-            if sgn is not None:
-                gb = gb * sgn
+            gb = dyz[..., O:].sum(dim=(0, 1)) * sgn
         return gx, gw, gb, None
 
 
@@ -215,15 +220,13 @@ def edge_conv_functional(x, weight, k, bias, bnp: BNParams | None, negative_slop
         p1 = -bnp.running_mean * p0
         if bnp.bias is not None:
             p1 = p1 + bnp.bias
-    # a negative scale turns the max over k into a min: fold its sign into the rows of W (and the bias), so that the
-    # kernels always take a max and see a non-negative scale:  p0 * h = |p0| * (sign(p0) * h)
-    sgn = None
+    # a negative scale turns the max over k into a min: its sign is folded into the rows of W (and the bias) by the weight
+    # prep kernel, so that the kernels always take a max and see a non-negative scale:  p0 * h = |p0| * (sign(p0) * h)
+    yz, sgn = _PointwiseYZ.apply(x, weight, bias, p0)                 # (B,N,2O) = [Y | Z]: the layer's one GEMM
     if p0 is not None:
-        sgn = torch.where(p0.detach() < 0, -1.0, 1.0).to(torch.float32)
         p0 = p0 * sgn
-    if weight.reshape(O, -1).shape[1] != 2 * C:
-        raise MlspError(f"edge_conv: weight has {weight.reshape(O, -1).shape[1]} input channels, expected 2*C = {2 * C}")
-    yz = _PointwiseYZ.apply(x, weight, bias, sgn)                     # (B,N,2O) = [Y | Z]: the one library GEMM of the layer
+    else:
+        sgn = None
     if not train:
         return _EdgeConvReduce.apply(yz, idx, p0, p1, "affine", 0.0, slope)
     running = None

@@ -140,7 +140,8 @@ def test_pointwise_yz_node_matches_autograd_of_the_same_expression():
         bf = torch.randn(O, device=dev, requires_grad=True) if use_b else None
         sg = torch.tensor([1.0, -1.0] * (O // 2), device=dev) if use_s else None
         gy = torch.randn(3, 8, 2 * O, device=dev)
-        y = edgeconv._PointwiseYZ.apply(x, Wf, bf, sg)
+        y, s_out = edgeconv._PointwiseYZ.apply(x, Wf, bf, 0.7 * sg if use_s else None)    # scale: only its sign matters
+        assert torch.equal(s_out, sg if use_s else torch.ones(O, device=dev))
         y.backward(gy)
         got = (x.grad.clone(), Wf.grad.clone(), bf.grad.clone() if use_b else None)
         xd, Wd = x.detach().double().requires_grad_(True), Wf.detach().double().requires_grad_(True)

@@ -20,16 +20,18 @@ ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
 agg = collections.defaultdict(list)
 for r in rows[1:]:
     try:
-        agg[r[ki]].append(float(r[vi].replace(",", "")))
+        v = float(r[vi].replace(",", ""))
     except ValueError:
-        pass
+        continue
+    if v == v:                                   # ncu prints n/a (parsed as nan) for launches it could not time
+        agg[r[ki]].append(v)
 tot = sum(sum(v) for v in agg.values())
 with open(os.path.join(out, f"launches_{tag}.md"), "w") as fh:
     fh.write(f"# ncu launch list, {tag}: `ncu --metrics gpu__time_duration.sum --clock-control none` over "
              "`python bench.py --steps 2 --warmup 3`\n\n")
     fh.write("Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
     fh.write("| share | launches | avg us | min us | max us | kernel |\n|---:|---:|---:|---:|---:|---|\n")
-    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    for k, v in sorted(((k, v) for k, v in agg.items() if v), key=lambda kv: -sum(kv[1])):
         fh.write(f"| {sum(v)/tot*100:.1f}% | {len(v)} | {sum(v)/len(v)/1e3:.1f} | {min(v)/1e3:.1f} | {max(v)/1e3:.1f} | `{k[:110]}` |\n")
 
 # ---- ncu --set full -> key metrics per captured kernel
