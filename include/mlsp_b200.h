@@ -280,6 +280,16 @@ MLSP_API int mlsp_edgeconv_weight_prep(const float *W, const float *scale, const
 /* part (Z,2O,C) = partial products dyz^T x  ->  gW (O,2C) = [s (gY - gZ) | s gZ], summed over Z in a fixed order */
 MLSP_API int mlsp_edgeconv_weight_grad(const float *part, int Z, const float *sgn, int O, int C, float *gW, void *stream);
 
+/* ---- max pooling around the point-wise layers, with argmax (first index on ties, NaN propagates) and backward ----
+ * "mid": in (R,K,C), C contiguous and C % 4 == 0 -> val (R,C), arg (R,C) int32 = max over K.  x.max(dim=-1) over the k
+ *   neighbours of a channels-last edge tensor (R = B*N, K = k) and torch.max(x, dim=2) over the points of a channels-last map
+ *   (R = B, K = N): transform_net, PointDA/model_utils.py:116-121.  bwd: g (R,C), arg -> gin (R,K,C) (zeros off the argmax).
+ * "row": in (R,K), K contiguous -> val (R), arg (R): F.adaptive_max_pool1d(x, 1) of a (B,C,N) map, PointDA/Models.py:133. */
+MLSP_API int mlsp_max_mid_fwd(const float *in, long long R, int K, int C, float *val, int *arg, void *stream);
+MLSP_API int mlsp_max_mid_bwd(const float *g, const int *arg, long long R, int K, int C, float *gin, void *stream);
+MLSP_API int mlsp_max_row_fwd(const float *in, long long R, int K, float *val, int *arg, void *stream);
+MLSP_API int mlsp_max_row_bwd(const float *g, const int *arg, long long R, int K, float *gin, void *stream);
+
 /* ---- the point-wise products around the neighbourhood engine (8f ranks 1, 4): every 1x1 convolution / Linear of the DGCNN ----
  * Replaces the library GEMM behind nn.Conv2d(kernel_size=1) in conv_2d (PointDA/model_utils.py:45-63, used by the EdgeConv
  * layers PointDA/Models.py:114-128 and by transform_net model_utils.py:92-130), nn.Conv1d(kernel_size=1) of conv5 and of the

@@ -4,7 +4,7 @@ Public surface = the reference's own function names (see ops.py) + `patch()` to 
 inside the reference modules.  Everything runs in hand-written CUDA kernels behind the C ABI
 declared in include/mlsp_b200.h; there is no CPU fallback.
 """
-from . import _lib, edgeconv, lazy, linear, ops, patch, synth  # noqa: F401
+from . import _lib, edgeconv, lazy, linear, ops, patch, pool, synth  # noqa: F401
 from ._lib import MlspError  # noqa: F401
 from .ops import (  # noqa: F401
     assign_region_to_point,

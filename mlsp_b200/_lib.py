@@ -46,6 +46,10 @@ SIGNATURES = {
     "mlsp_edgeconv_bwd": [_P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _P, _Z, _P],
     "mlsp_edgeconv_weight_prep": [_P, _P, _P, _I, _I, _P, _P, _P, _P],
     "mlsp_edgeconv_weight_grad": [_P, _I, _P, _I, _I, _P, _P],
+    "mlsp_max_mid_fwd": [_P, _L, _I, _I, _P, _P, _P],
+    "mlsp_max_mid_bwd": [_P, _P, _L, _I, _I, _P, _P],
+    "mlsp_max_row_fwd": [_P, _L, _I, _P, _P, _P],
+    "mlsp_max_row_bwd": [_P, _P, _L, _I, _P, _P],
     "mlsp_scan_zbuffer": [_P, _I, _I, _P, _I, _P, _P, _P],
     "mlsp_gemm_f32": [_P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _I, _I, _I, _P],
 }

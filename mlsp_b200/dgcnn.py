@@ -24,7 +24,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import edgeconv, linear, ops
+from . import edgeconv, linear, ops, pool
 
 K = 20  # PointDA/Models.py:13
 
@@ -85,9 +85,9 @@ class TransformNet(nn.Module):
 
     def forward(self, x):                                   # x: the (B,6,N,k) edge tensor of the raw cloud
         x = self.conv2d2(self.conv2d1(x))
-        x = x.max(dim=-1, keepdim=False)[0].unsqueeze(3)
+        x = pool.max_over_neighbours(x).unsqueeze(3)
         x = self.conv2d3(x)
-        x = torch.max(x, dim=2, keepdim=False)[0].view(x.size(0), -1)
+        x = pool.max_over_points_cl(x).view(x.size(0), -1)
         x = fc(self.fc2(self.fc1(x)), self.fc3)
         x = x + torch.eye(self.K, device=x.device, dtype=x.dtype).view(1, self.K * self.K)
         return x.view(x.size(0), self.K, self.K)
@@ -215,7 +215,7 @@ class DGCNN(nn.Module):
             feats.append(h)
         x_cat = torch.cat(feats, dim=1)
         x5 = F.leaky_relu(self.bn5(conv1x1(x_cat, self.conv5)), negative_slope=0.2)
-        x5 = F.adaptive_max_pool1d(x5, 1).view(B, -1)
+        x5 = pool.global_max_pool(x5).view(B, -1)
         return x_cat, x5
 
     def forward(self, x, visualization=False, activate_DefRec=False, activate_normal=False, activate_scan=False,

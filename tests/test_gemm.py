@@ -157,3 +157,39 @@ def test_pointwise_yz_node_matches_autograd_of_the_same_expression():
         assert torch.allclose(y.double(), ref, atol=1e-5) and got[0].is_contiguous()
         assert torch.allclose(got[0].double(), xd.grad, atol=1e-5) and torch.allclose(got[1].double(), Wd.grad, atol=1e-5)
         assert not use_b or torch.allclose(got[2].double(), bd.grad, atol=1e-5)
+
+
+@needs_gpu
+def test_max_pooling_kernels_match_torch():
+    """pool.cu against torch.max / adaptive_max_pool1d: values, and the gradient on the first maximal element -- on the three
+    layouts the model uses, with ties (quantised values), a NaN, K smaller than the 8 cooperating warps, ragged channel blocks."""
+    from mlsp_b200 import pool
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    for B, C, N, k in ((3, 128, 50, 20), (2, 64, 33, 5), (2, 132, 17, 40)):
+        e = torch.randint(-3, 4, (B, N, k, C), generator=g).float().to(dev).permute(0, 3, 1, 2).requires_grad_(True)
+        out = pool.max_over_neighbours(e)
+        ref, ridx = e.detach().max(dim=-1)
+        assert torch.equal(out, ref) and out.shape == (B, C, N)
+        go = torch.randn(B, C, N, generator=g).to(dev)
+        out.backward(go)
+        # every gradient value lands on ONE maximal element of its (b,c,n) row: the first
+        first = (e.detach() == ref.unsqueeze(-1)).float().argmax(dim=-1)
+        want = torch.zeros_like(e.detach()).scatter_(3, first.unsqueeze(-1), go.unsqueeze(-1))
+        assert torch.equal(e.grad, want)
+    x = torch.randn(4, 256, 300, 1, generator=g).to(dev).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
+    out = pool.max_over_points_cl(x)
+    assert torch.equal(out, torch.max(x.detach(), dim=2)[0])
+    out.sum().backward()
+    assert float(x.grad.sum()) == 4 * 256 and torch.equal((x.grad != 0), x.detach() == out.detach().unsqueeze(2))
+    y = torch.randn(3, 40, 1000, generator=g).to(dev).requires_grad_(True)
+    out = pool.global_max_pool(y)
+    assert torch.equal(out, torch.nn.functional.adaptive_max_pool1d(y.detach(), 1))
+    out.backward(torch.ones_like(out))
+    assert torch.equal(y.grad != 0, y.detach() == out.detach())
+    yn = y.detach().clone()
+    yn[1, 2, 77] = float("nan")
+    assert torch.isnan(pool.global_max_pool(yn)[1, 2, 0]) and torch.isfinite(pool.global_max_pool(yn)[0]).all()
+    for K in (1, 3, 7, 37):                                              # unaligned rows take the scalar path
+        z = torch.randn(5, 7, K, generator=g).to(dev)
+        assert torch.equal(pool.global_max_pool(z), z.max(dim=2, keepdim=True)[0])
