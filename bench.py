@@ -59,6 +59,9 @@ def set_workload(name):
     PERGROUP, SHIFT, FPS_SPLIT = w["pergroup"], w["shift"], w["fps_split"]
 
 
+
+from mlsp_b200 import dist as mlsp_dist  # noqa: E402  (rank helpers shared with the tests)
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -639,12 +642,8 @@ def run_workload_x(args):
     barrier()
     e2e_s = (time.perf_counter() - t0) / steps
 
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def max_over_ranks(v):                   # the time every multi-GPU number is reported with (mlsp_b200/dist.py)
+        return mlsp_dist.max_over_ranks(v, device=device)
 
     step_ms, e2e_ms = max_over_ranks(dev_ms), max_over_ranks(e2e_s * 1e3)
     call_ms = [max_over_ranks(v) for v in call_ms]
@@ -923,12 +922,8 @@ def run_workload_e(args):
             per[f"knn_C{C}"] = (span(lambda: M.knn(h, k)), None, None)
             h = f(h)
 
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def max_over_ranks(v):                   # the time every multi-GPU number is reported with (mlsp_b200/dist.py)
+        return mlsp_dist.max_over_ranks(v, device=device)
 
     step_ms, e2e_ms = max_over_ranks(dev_ms), max_over_ranks(e2e_ms)
     if rank != 0:
@@ -1121,12 +1116,8 @@ def run_workload_t(args):
         torch.cuda.synchronize()
         ar_ms = a0.elapsed_time(a1) / 10
 
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def max_over_ranks(v):                   # the time every multi-GPU number is reported with (mlsp_b200/dist.py)
+        return mlsp_dist.max_over_ranks(v, device=device)
 
     step_ms, e2e_ms = max_over_ranks(dev_ms), max_over_ranks(e2e_s * 1e3)
     if rank != 0:
@@ -1227,6 +1218,47 @@ def extra_train_T(dist, device, rank, world, steps=8):
     return {"workload": "train-T (BASELINE configs[2]; `bench.py --workload T` is the full line)", "clouds_per_s": B * world / (ms * 1e-3),
             "ms_per_step": ms, "n_gpus": world, "parallelism": f"dp{world} DistributedDataParallel / NCCL",
             "collective": {"bytes_per_step": nbytes, "allreduce_alone_ms": ar_ms, "inside_timed_region": dist is not None}}
+
+
+def extra_hotpath_S(device, rank, steps=10):
+    """configs[3] in short form for the default line: the same hot-path step at the PointSegDA shape (16 x 2048 points, layers
+    (3,3,64,64), near 10; `--workload S` is the full line).  Same GraphedStep code path, device-resident inputs, CUDA events."""
+    import mlsp_b200 as M
+    from mlsp_b200 import synth
+    prev = (LAYER_CHANNELS, RADIUS, NUM_CLS, NEAR, PERGROUP, SHIFT, FPS_SPLIT)
+    rng = (torch.get_rng_state(), np.random.get_state())
+    set_workload("S")
+    try:
+        B, N, k = synth.CONFIGS["S"]
+        _, dev = make_inputs(B, N, k, 4321 + rank, device, pin=False)
+        lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=device)
+        streams = Streams(device)
+        off = OpTimer(False)
+        with torch.cuda.stream(streams.model):
+            for _ in range(2):
+                gpu_step(M, dev, lookup, k, off, streams)
+            g = GraphedStep(M, dev, lookup, k, streams)
+            for _ in range(3):
+                g(off)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(steps):
+                g(off)
+            e1.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), wall * 1e3) / steps
+        del g, dev
+    finally:
+        globals().update(LAYER_CHANNELS=prev[0], RADIUS=prev[1], NUM_CLS=prev[2], NEAR=prev[3], PERGROUP=prev[4], SHIFT=prev[5],
+                         FPS_SPLIT=prev[6])
+        torch.set_rng_state(rng[0])
+        np.random.set_state(rng[1])
+    torch.cuda.empty_cache()
+    return {"workload": "hotpath-S 16x2048 k=20 (BASELINE configs[3]; `bench.py --workload S` is the full line)",
+            "clouds_per_s": B / (ms * 1e-3), "ms_per_step": ms}
 
 
 def extra_knn_X(device, steps=4):
@@ -1402,12 +1434,8 @@ def main():
             barrier()
             target_gen[mode] = (time.perf_counter() - t0) / args.steps * 1e3
 
-    def max_over_ranks(v):
-        if dist is None:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def max_over_ranks(v):                   # the time every multi-GPU number is reported with (mlsp_b200/dist.py)
+        return mlsp_dist.max_over_ranks(v, device=device)
 
     step_ms = max_over_ranks(max(dev_ms, wall * 1e3) / args.steps)   # device time == wall here (host-sync'd step)
     dev_only_ms = max_over_ranks(dev_ms / args.steps)
@@ -1420,6 +1448,7 @@ def main():
         try:
             extras["train_T"] = extra_train_T(dist, device, rank, world)
             if world == 1:
+                extras["hotpath_S"] = extra_hotpath_S(device, rank)
                 extras["knn_X"] = extra_knn_X(device)
         except Exception as exc:                               # never let a context measurement cost the bench line
             if world > 1:
