@@ -281,7 +281,8 @@ struct StageRegs {
 // One operand as one loader thread sees it.  Item 1 is item 0 shifted by 64 rows (K-major) or 32 k rows (MN-major): a fixed
 // element offset `d1` in global memory and a fixed byte offset in the stage.  p0 runs along K (+ `adv` elements per chunk).
 // mode bits (per item u: bits 2u, 2u+1) say how the item is fetched in a K chunk that lies wholly inside K:
-// 0 = out of range (zeros), 1 = two 16-byte loads, 2 = the guarded element-wise path.
+// 0 = out of range (zeros), 1 = two 16-byte loads, 2 = the guarded element-wise path, 3 = a row of the stage that no MMA
+// reads (beyond this CTA's share of the tile's B rows): neither fetched nor stored.
 struct OperandLane {
     const float *p0;
     uint32_t soff0;
@@ -289,19 +290,20 @@ struct OperandLane {
 };
 
 __device__ __forceinline__ void lane_begin_tile(OperandLane &L, const float *base, long long ld, int kmajor, int vec, int lt,
-                                                int row0, int rows)
+                                                int row0, int rows, int read_rows)
 {
     L.modes = 0;
     if (kmajor) {
         const int r = lt >> 3, c = lt & 7;
         L.p0 = base + (long long)(row0 + r) * ld + 8 * c;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) L.modes |= ((row0 + r + 64 * u >= rows) ? 0 : (vec ? 1 : 2)) << (2 * u);
+        for (int u = 0; u < 2; ++u)
+            L.modes |= ((r + 64 * u >= read_rows) ? 3 : (row0 + r + 64 * u >= rows) ? 0 : (vec ? 1 : 2)) << (2 * u);
     } else {
         const int kr = lt >> 4, mc = lt & 15;
         const int row = row0 + 8 * mc;
         L.p0 = base + (long long)kr * ld + row;
-        const int m = (row >= rows) ? 0 : ((vec && row + 8 <= rows) ? 1 : 2);
+        const int m = (8 * mc >= read_rows) ? 3 : (row >= rows) ? 0 : ((vec && row + 8 <= rows) ? 1 : 2);
         L.modes = m | (m << 2);
     }
 }
@@ -311,6 +313,7 @@ __device__ __forceinline__ void lane_load(Item &it, const OperandLane &L, int u,
                                           long long ld, int kmajor, int vec, int lt, int row0, int rows, int k0, int K)
 {
     const int mode = (L.modes >> (2 * u)) & 3;
+    if (mode == 3) return;
     if (kfull && mode == 1) {
         const float4 *q = reinterpret_cast<const float4 *>(L.p0 + (u ? d1 : 0));
         it.lo = __ldg(q);
@@ -416,8 +419,8 @@ gemm3_kernel(const Params P)
             w = tile_work<PAIR>(P, unit, crank);
             Ab = P.A + (long long)w.z * P.sa;
             Bb = P.B + (long long)w.z * P.sb;
-            lane_begin_tile(LA, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M);
-            lane_begin_tile(LB, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end);
+            lane_begin_tile(LA, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M, BM);
+            lane_begin_tile(LB, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end, PAIR ? w.ncols / 2 : w.ncols);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 lane_load(ra[u], LA, u, da1, kfull, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M, 0, P.K);
@@ -425,6 +428,7 @@ gemm3_kernel(const Params P)
             }
         }
         for (int it = 0; it < n_it; ++it) {
+            const int store_b = LB.modes;                     // of the chunk in the registers (the state below moves on)
             // step the fetch state to chunk it + 1
             bool more = true;
             if (++kc == P.kc) {
@@ -433,8 +437,8 @@ gemm3_kernel(const Params P)
                     w = tile_work<PAIR>(P, unit + j * units, crank);
                     Ab = P.A + (long long)w.z * P.sa;
                     Bb = P.B + (long long)w.z * P.sb;
-                    lane_begin_tile(LA, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M);
-                    lane_begin_tile(LB, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end);
+                    lane_begin_tile(LA, Ab, P.lda, P.a_kmajor, P.a_vec, lt, w.m0, P.M, BM);
+                    lane_begin_tile(LB, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end, PAIR ? w.ncols / 2 : w.ncols);
                 } else {
                     more = false;
                 }
@@ -454,7 +458,7 @@ gemm3_kernel(const Params P)
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                store_item(rb[u], st + OPER_BYTES, LB.soff0 + (u ? sdb : 0u));
+                if (((store_b >> (2 * u)) & 3) != 3) store_item(rb[u], st + OPER_BYTES, LB.soff0 + (u ? sdb : 0u));
                 if (more) lane_load(rb[u], LB, u, db1, kfull, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end, k0, P.K);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the tensor core's reads
