@@ -29,8 +29,10 @@ def one_pass():
         x = f.detach().requires_grad_(True)
         M.get_graph_feature(x, None, k=k).backward(grads[C])
     M.fps_from_start(clouds, 512, start)
-    M.estimate_normals(pts, 20)                                  # knn3 + pca_normals
+    M.target_structure(pts, 20, 0.13, 16, 2, 0)                  # 8f rank 2: kNN(near) + normals + cardinality in one launch
+    M.estimate_normals(pts, 20)                                  # the stand-alone ops, for reference: knn3 + pca_normals
     M.cal_density(pts, 0.13, 16, 2, 0)
+    M.scan_input(pts.clone(), dev)                               # 8f rank 3: z-buffer scan
     X, mask = M.deform_input(clouds.clone(), lookup, "volume_based_voxels", dev)
     p = pred.detach().requires_grad_(True)
     M.reconstruction_loss(p, clouds, mask).backward()

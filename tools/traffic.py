@@ -15,7 +15,8 @@ scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 B, N, k = 32, 1024, 20
 rows = []                                               # (kernel name, dram bytes, microseconds)
 for rep in reps:
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the `ncu -i ... --page raw --csv` export of one (reports over 64 MiB do not travel back from the GPU box)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
     h = rr[0]
     kn, rd, wr, tm = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum"), h.index("gpu__time_duration.sum")
@@ -40,8 +41,8 @@ for name, tot, us in rows:
         if us > (80 if C == 128 else 50):               # with the fused edge gather (ggf*); the ranking alone is 30-40 us
             groups[f"A:k_rank_gather_C{C}"].append(tot)
     elif "knn_tensor_kernel" in name:
-        groups[f"A:knn_C{64 if us < 43 else 128}"].append(tot)
-        groups[f"A:k_filter_C{64 if us < 43 else 128}"].append(tot)
+        groups[f"A:knn_C{64 if us < 40 else 128}"].append(tot)
+        groups[f"A:k_filter_C{64 if us < 40 else 128}"].append(tot)
     elif "knn3_kernel" in name:
         groups["A:knn_C3"].append(tot)
     elif "edge_fwd3" in name:
@@ -51,7 +52,7 @@ for name, tot, us in rows:
 out = {}
 for key, v in sorted(groups.items()):
     out[key] = {"dram_bytes": sum(v) / len(v), "launches": len(v),
-                "source": f"profiles/ncu_{tag}.md (ncu --set full --clock-control none over tools/opbench.py; main kernel of the op, "
+                "source": f"profiles/ncu_{tag}.md (ncu --set full --clock-control none over tools/prof_ops.py; main kernel of the op, "
                           "dram__bytes_read.sum + dram__bytes_write.sum per launch)"}
     if (key.startswith("A:edge_") or key.startswith("A:k_rank_gather_")) and not key.endswith("C3"):
         out[key]["algorithmic_bytes"] = alg(int(key.split("_C")[1]))
