@@ -33,6 +33,12 @@ with open(os.path.join(out, f"launches_{tag}.md"), "w") as fh:
     fh.write("| share | launches | avg us | min us | max us | kernel |\n|---:|---:|---:|---:|---:|---|\n")
     for k, v in sorted(((k, v) for k, v in agg.items() if v), key=lambda kv: -sum(kv[1])):
         fh.write(f"| {sum(v)/tot*100:.1f}% | {len(v)} | {sum(v)/len(v)/1e3:.1f} | {min(v)/1e3:.1f} | {max(v)/1e3:.1f} | `{k[:110]}` |\n")
+    own = {k: v for k, v in agg.items() if v and ("mlsp::" in k or "gemm3" in k)}
+    tot_own = sum(sum(v) for v in own.values())
+    fh.write(f"\nThis library's kernels only ({tot_own / tot * 100:.1f}% of all kernel time in the command; the rest is torch: input "
+             "generation with randn, fills, copies):\n\n| share | launches | avg us | kernel |\n|---:|---:|---:|---|\n")
+    for k, v in sorted(own.items(), key=lambda kv: -sum(kv[1])):
+        fh.write(f"| {sum(v)/tot_own*100:.1f}% | {len(v)} | {sum(v)/len(v)/1e3:.1f} | `{k[:110]}` |\n")
 
 # ---- ncu --set full -> key metrics per captured kernel
 if os.path.exists(rep):
