@@ -1087,10 +1087,12 @@ def run_workload_t(args):
         sampler.skip = sampler._count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    calls0 = M._lib.calls
     e0.record()
     for _ in range(args.steps):
         loss = step(False)
     e1.record()
+    abi_calls = M._lib.calls - calls0                              # C-ABI calls of this library in the timed region (>= 1 kernel each)
     barrier()
     dev_ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if sampler is not None else None      # the timed region (K x ~40 ms) spans several 100 ms samples
@@ -1124,6 +1126,29 @@ def run_workload_t(args):
         if dist is not None:
             dist.destroy_process_group()
         return
+    # roofline of the step's dominant kernel family, measured live: mlsp_gemm_f32 (a third of the step's GPU time) on its largest
+    # product, the heads' shared first layer / conv5 (B x (N x 1024 x 512)), CUDA events around 10 launches on this stream
+    from mlsp_b200 import linear
+    xg, wg = torch.randn(B, 512, N, device=device), torch.randn(1024, 512, device=device)
+    for _ in range(3):
+        linear.gemm_nt(xg.transpose(1, 2), wg, out_colmajor=True)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(10):
+        linear.gemm_nt(xg.transpose(1, 2), wg, out_colmajor=True)
+    g1.record()
+    torch.cuda.synchronize()
+    gemm_ms = g0.elapsed_time(g1) / 10
+    gflop = 2.0 * B * N * 1024 * 512
+    pk = peaks()
+    roofline = {"kernel": "gemm3_kernel<pair> (mlsp_gemm_f32: conv5 / the heads' first layer, 512 -> 1024 channels on B x N points)",
+                "bound": "tensor", "achieved": gflop / (gemm_ms * 1e-3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": gflop / (gemm_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+                "algorithmic_flops_per_launch": gflop, "ms_per_launch": gemm_ms,
+                "note": "algorithmic fp32 flops 2MNK against the bf16 peak; the fp32-faithful product executes six bf16 MMAs per "
+                        "fp32 product (three pieces per operand), so 1/6 = 0.167 is this kernel's ceiling: it runs at "
+                        f"{gflop / (gemm_ms * 1e-3) / 1e12 / (pk['bf16_tflops'] / 6):.2f} of that; ncu: tensor pipe 69% active "
+                        "(profiles/ncu_r2 gemm capture, DESIGN.md section 10)"}
     line = {
         "metric": metric, "value": B * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -1133,10 +1158,11 @@ def run_workload_t(args):
                 "loss": loss_host},
         "collective": {"what": "DDP gradient all-reduce inside the timed backward (NCCL over NVLink/NVSwitch)", "bytes_per_step": nbytes,
                        "allreduce_alone_ms": ar_ms, "share_of_step_if_not_overlapped": (ar_ms / step_ms) if ar_ms else 0.0},
-        "gpu_launches": None,
-        "roofline": None,
-        "note": "torch's own layers (1x1 convolutions, BatchNorm, heads, Adam) dominate this step and are not roofline-graded (SURVEY.md 8d); "
-                "the hot-path kernels inside it are graded by the default workload A line",
+        "gpu_launches": abi_calls,
+        "roofline": roofline,
+        "note": "gpu_launches = C-ABI calls of this library inside the timed region (each launches one to three kernels); BatchNorm, "
+                "activations, Dropout, the small losses and Adam are torch's kernels; the hot-path kernels inside the step are "
+                "graded one by one by the default workload A line",
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

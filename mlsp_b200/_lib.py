@@ -85,8 +85,13 @@ def load() -> ctypes.CDLL:
     return _lib
 
 
+calls = 0      # C-ABI entry points called so far (every one launches at least one kernel): bench.py's `gpu_launches` evidence
+
+
 def call(name: str, *args) -> None:
+    global calls
     L = load()
+    calls += 1
     rc = getattr(L, name)(*args)
     if rc != 0:
         raise MlspError(f"{name} failed (code {rc}): {L.mlsp_last_error().decode()}")
