@@ -1063,14 +1063,18 @@ def run_workload_t(args):
         trg = trg_host.to(device, non_blocking=True) if from_host else trg_dev
         lab = lab_host.to(device, non_blocking=True) if from_host else lab_dev
         opt.zero_grad(set_to_none=True)
+        # the target batch is known now (the loader yields both batches together, PointDA/trainer.py:374): start its region
+        # histogram and the read-back to pinned memory, so that deform_input needs no stream synchronisation mid-step
+        tb = trg.clone()
+        pending = M.deform_input_begin(tb.permute(0, 2, 1))
         with (net.no_sync() if dist is not None else contextlib.nullcontext()):
             mixed, vals = pcm.mix_shapes(targs, src.permute(0, 2, 1), lab)
             logits = net(mixed)
             loss_s = pcm.calc_loss(targs, logits, vals, criterion)
             loss_s.backward()
         # the target branch's loss is computed by the module's helper through the DDP wrapper's forward
-        loss_t = dgcnn.target_branch_loss(net, trg.clone(), lookup, near=NEAR, radius=RADIUS, density_num_class=NUM_CLS,
-                                          pergroup=PERGROUP, shift=SHIFT, DefRec_weight=targs.DefRec_weight)
+        loss_t = dgcnn.target_branch_loss(net, tb, lookup, near=NEAR, radius=RADIUS, density_num_class=NUM_CLS,
+                                          pergroup=PERGROUP, shift=SHIFT, DefRec_weight=targs.DefRec_weight, pending=pending)
         loss_t.backward()
         opt.step()
         return loss_s.detach() + loss_t.detach()
@@ -1200,10 +1204,12 @@ def extra_train_T(dist, device, rank, world, steps=8):
 
     def step():
         opt.zero_grad(set_to_none=True)
+        tb = trg.clone()
+        pending = M.deform_input_begin(tb.permute(0, 2, 1))       # histogram read-back under the source branch
         with (net.no_sync() if dist is not None else contextlib.nullcontext()):
             mixed, vals = pcm.mix_shapes(targs, src.permute(0, 2, 1), lab)
             pcm.calc_loss(targs, net(mixed), vals, crit).backward()
-        dgcnn.target_branch_loss(net, trg.clone(), lookup).backward()
+        dgcnn.target_branch_loss(net, tb, lookup, pending=pending).backward()
         opt.step()
 
     for _ in range(3):

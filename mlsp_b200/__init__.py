@@ -14,6 +14,8 @@ from .ops import (  # noqa: F401
     chamfer_distance,
     collapse_to_point,
     deform_input,
+    deform_input_begin,
+    deform_input_finish,
     estimate_normals,
     farthest_point_sample,
     findindexs,

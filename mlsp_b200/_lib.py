@@ -88,13 +88,18 @@ def load() -> ctypes.CDLL:
 calls = 0      # C-ABI entry points called so far (every one launches at least one kernel): bench.py's `gpu_launches` evidence
 
 
+_fn: dict = {}
+
+
 def call(name: str, *args) -> None:
     global calls
-    L = load()
+    fn = _fn.get(name)
+    if fn is None:
+        fn = _fn[name] = getattr(load(), name)
     calls += 1
-    rc = getattr(L, name)(*args)
+    rc = fn(*args)
     if rc != 0:
-        raise MlspError(f"{name} failed (code {rc}): {L.mlsp_last_error().decode()}")
+        raise MlspError(f"{name} failed (code {rc}): {load().mlsp_last_error().decode()}")
 
 
 def workspace_bytes(op: int, B: int, C: int, N: int, k: int) -> int:

@@ -265,16 +265,23 @@ def density_loss(logits, target, target_vec, mask=None, weight=1.0, lambda_1=0.0
 
 def target_branch_loss(model, trgt_batch, lookup, *, near=20, radius=0.13, density_num_class=16, pergroup=2, shift=0,
                        DefRec_weight=0.5, normal_pred_weight=1.0, Density_weight=1.0, DefRec_dist="volume_based_voxels",
-                       defpart=False):
+                       defpart=False, pending=None):
     """The target-branch loss of one training step, PointDA/trainer.py:522-566 (Density_normal_viainput, Normal_ondef,
     Density_ondef): local-structure targets of the undeformed batch (one 3-D neighbourhood pass), deformation, forward with the
-    three heads, position (Chamfer) + normal + cardinality losses.  trgt_batch (B,N,3) as the loader yields it."""
+    three heads, position (Chamfer) + normal + cardinality losses.  trgt_batch (B,N,3) as the loader yields it.
+    pending: the handle of `ops.deform_input_begin(trgt_batch.permute(0, 2, 1))` issued earlier in the step (before the source
+    branch): the deformation then needs no stream synchronisation here (same results, same RNG stream positions)."""
     normal_gt, density_label, density_mse_label = ops.target_structure(trgt_batch, near, radius, density_num_class, pergroup, shift)
     density_label = density_label.reshape(-1, density_num_class)
     density_mse_label = density_mse_label.to(torch.float32).reshape(-1)
     trgt = trgt_batch.permute(0, 2, 1)
     trgt_orig = trgt.clone()
-    trgt, mask = ops.deform_input(trgt, lookup, DefRec_dist, trgt.device)
+    if pending is not None:
+        if pending.X.data_ptr() != trgt.data_ptr() or pending.X.shape != trgt.shape:
+            raise ops.MlspError("target_branch_loss: `pending` was begun on a different batch")
+        trgt, mask = ops.deform_input_finish(pending, lookup, DefRec_dist)
+    else:
+        trgt, mask = ops.deform_input(trgt, lookup, DefRec_dist, trgt.device)
     logits = model(trgt.contiguous(), activate_density_normal_ondef=True)
     loss = DefRec_weight * ops.reconstruction_loss(logits["DefRec"], trgt_orig, mask) * ops.DefRec_SCALER
     mask_cord = mask.permute(0, 2, 1)[:, :, 0]

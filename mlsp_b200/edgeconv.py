@@ -24,7 +24,7 @@ from torch import nn
 
 from . import _lib, linear
 from ._lib import MlspError
-from .ops import _ptr, _require_cuda_f32, _stream, knn
+from .ops import _DeviceGuard, _ptr, _require_cuda_f32, _stream, knn
 
 
 class _EdgeConvReduce(torch.autograd.Function):
@@ -49,7 +49,7 @@ class _EdgeConvReduce(torch.autograd.Function):
         rowsum = None
         p0c = p0.detach().float().contiguous() if p0 is not None else None
         p1c = p1.detach().float().contiguous() if p1 is not None else None
-        with torch.cuda.device(dev):
+        with _DeviceGuard(dev):
             s = _stream(dev)
             if train:
                 rowsum = torch.empty((B, N, O), dtype=torch.float32, device=dev)
@@ -82,7 +82,7 @@ class _EdgeConvReduce(torch.autograd.Function):
         dyz = torch.empty((B, N, 2 * O), dtype=torch.float32, device=dev)
         need_p = train or has0 or has1
         dp = torch.empty((2, O), dtype=torch.float32, device=dev) if need_p else None
-        with torch.cuda.device(dev):
+        with _DeviceGuard(dev):
             nbytes = max(_lib.workspace_bytes(_lib.OP_EDGECONV_BWD, B, O, N, k), 16)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             _lib.call("mlsp_edgeconv_bwd", _ptr(g), int(g.stride(0)), _ptr(yz), _ptr(idx), _ptr(hsel), _ptr(slot),
@@ -109,7 +109,7 @@ class _PointwiseYZ(torch.autograd.Function):
         Wcat = torch.empty((2 * O, C), dtype=torch.float32, device=dev)
         sgn = torch.empty(O, dtype=torch.float32, device=dev)
         zb = torch.empty(2 * O, dtype=torch.float32, device=dev) if bias is not None else None
-        with torch.cuda.device(dev):                                           # weight split, sign fold, bias: one launch
+        with _DeviceGuard(dev):                                           # weight split, sign fold, bias: one launch
             _lib.call("mlsp_edgeconv_weight_prep", _ptr(W), _ptr(scale.detach().float().contiguous() if scale is not None else None),
                       _ptr(bias.detach().float().contiguous() if bias is not None else None), O, C, _ptr(Wcat), _ptr(sgn), _ptr(zb),
                       _stream(dev))
@@ -131,7 +131,7 @@ class _PointwiseYZ(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             part = linear.gemm_nt(dyz.transpose(1, 2), x)                         # (B,2O,C) partial products, K = N points each
             gw = torch.empty((O, 2 * C), dtype=torch.float32, device=x.device)
-            with torch.cuda.device(x.device):                                     # sum over B, sign, un-split: one launch
+            with _DeviceGuard(x.device):                                     # sum over B, sign, un-split: one launch
                 _lib.call("mlsp_edgeconv_weight_grad", _ptr(part), part.shape[0], _ptr(sgn), O, C, _ptr(gw), _stream(x.device))
             gw = gw.reshape(ctx.wshape)
         if ctx.needs_input_grad[2]:

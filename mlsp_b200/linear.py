@@ -17,21 +17,24 @@ import torch
 
 from . import _lib
 from ._lib import MlspError
-from .ops import _ptr, _stream
+from .ops import _DeviceGuard, _ptr, _stream
 
 
-def _mat(t: torch.Tensor, name: str):
+def _mat(t: torch.Tensor, name: str = ""):
     """(rows, K) view [optionally batched (Z, rows, K)] -> (kmajor, ld, batch stride) or None if it needs a copy."""
-    if t.dim() == 2:
-        s_r, s_k, s_z = t.stride(0), t.stride(1), 0
-        rows, K = t.shape
+    st = t.stride()
+    sh = t.shape
+    if len(st) == 2:
+        s_r, s_k = st
+        s_z = 0
+        rows, K = sh
     else:
-        s_z, s_r, s_k = t.stride()
-        _, rows, K = t.shape
+        s_z, s_r, s_k = st
+        rows, K = sh[1], sh[2]
     if s_k == 1 and (s_r >= K or rows == 1):
-        return 1, max(s_r, K), s_z
+        return 1, (s_r if s_r > K else K), s_z
     if s_r == 1 and (s_k >= rows or K == 1):
-        return 0, max(s_k, rows), s_z
+        return 0, (s_k if s_k > rows else rows), s_z
     return None
 
 
@@ -41,51 +44,48 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None = None, 
     all Z], any strides with one unit stride per matrix (a view that has none is copied).  out: (M,N) / (Z,M,N) tensor or
     view whose last two strides are (ld,1) or (1,ld); default a new contiguous tensor, or -- out_colmajor=True -- a tensor
     stored (Z,N,M) and returned as its (Z,M,N) transpose view (how a (B,O,N) feature map wants a points x channels product).
-    float32 CUDA only."""
-    for t, nm in ((a, "a"), (b, "b")):
-        if not t.is_cuda or t.dtype != torch.float32 or t.dim() not in (2, 3):
-            raise MlspError(f"gemm_nt: {nm} must be a 2-D or 3-D float32 CUDA tensor")
-    Z = a.shape[0] if a.dim() == 3 else (b.shape[0] if b.dim() == 3 else (out.shape[0] if out is not None and out.dim() == 3 else 0))
-    batched = a.dim() == 3 or b.dim() == 3
-    M, K = a.shape[-2:]
-    N, Kb = b.shape[-2:]
-    if K != Kb or (a.dim() == 3 and b.dim() == 3 and a.shape[0] != b.shape[0]):
+    float32 CUDA only.  (Kept lean: the training step calls it ~120 times and is host-bound.)"""
+    da, db = a.dim(), b.dim()
+    if not (a.is_cuda and b.is_cuda) or a.dtype != torch.float32 or b.dtype != torch.float32 or da not in (2, 3) or db not in (2, 3):
+        raise MlspError("gemm_nt: a and b must be 2-D or 3-D float32 CUDA tensors")
+    batched = da == 3 or db == 3
+    M, K = a.shape[-2], a.shape[-1]
+    N, Kb = b.shape[-2], b.shape[-1]
+    Z = a.shape[0] if da == 3 else (b.shape[0] if db == 3 else 1)
+    if K != Kb or (da == 3 and db == 3 and a.shape[0] != b.shape[0]):
         raise MlspError(f"gemm_nt: shapes {tuple(a.shape)} x {tuple(b.shape)}^T do not match")
     if K == 0:
         raise MlspError("gemm_nt: K = 0")
-    a = a.detach()
-    b = b.detach()
-    la = _mat(a, "a")
+    la = _mat(a)
     if la is None:
         a = a.contiguous()
-        la = _mat(a, "a")
-    lb = _mat(b, "b")
+        la = _mat(a)
+    lb = _mat(b)
     if lb is None:
         b = b.contiguous()
-        lb = _mat(b, "b")
+        lb = _mat(b)
     dev = a.device
     if out is None:
         if out_colmajor:
-            store = torch.empty(((Z, N, M) if batched else (N, M)), dtype=torch.float32, device=dev)
-            out = store.transpose(-1, -2)
+            out = torch.empty(((Z, N, M) if batched else (N, M)), dtype=torch.float32, device=dev).transpose(-1, -2)
         else:
             out = torch.empty(((Z, M, N) if batched else (M, N)), dtype=torch.float32, device=dev)
-    else:
-        if out.dtype != torch.float32 or out.device != dev or tuple(out.shape[-2:]) != (M, N) or (out.dim() == 3) != batched:
-            raise MlspError("gemm_nt: out has the wrong shape / dtype / device")
-    ld_ = _mat(out, "out")                      # "kmajor" here means the last dimension (n) is contiguous = row-major
+    elif out.dtype != torch.float32 or out.device != dev or tuple(out.shape[-2:]) != (M, N) or (out.dim() == 3) != batched:
+        raise MlspError("gemm_nt: out has the wrong shape / dtype / device")
+    ld_ = _mat(out)                             # "kmajor" here means the last dimension (n) is contiguous = row-major
     if ld_ is None:
         raise MlspError("gemm_nt: out needs a unit stride along m or n")
     if bias is not None:
         if bias.shape != (N,) or bias.dtype != torch.float32 or bias.device != dev:
             raise MlspError("gemm_nt: bias must be float32 (N,) on the operands' device")
-        bias = bias.detach().contiguous()
-    if M == 0 or N == 0 or (batched and Z == 0):
+        if not bias.is_contiguous():
+            bias = bias.contiguous()
+    if M == 0 or N == 0 or Z == 0:
         return out
-    with torch.cuda.device(dev):
-        _lib.call("mlsp_gemm_f32", _ptr(a), la[0], la[1], la[2] if a.dim() == 3 else 0, _ptr(b), lb[0], lb[1],
-                  lb[2] if b.dim() == 3 else 0, _ptr(out), ld_[0], ld_[1], ld_[2] if out.dim() == 3 else 0, _ptr(bias),
-                  M, N, K, Z if batched else 1, _stream(dev))
+    with _DeviceGuard(dev):
+        _lib.call("mlsp_gemm_f32", a.data_ptr(), la[0], la[1], la[2] if da == 3 else 0, b.data_ptr(), lb[0], lb[1],
+                  lb[2] if db == 3 else 0, out.data_ptr(), ld_[0], ld_[1], ld_[2] if batched else 0,
+                  bias.data_ptr() if bias is not None else None, M, N, K, Z, _stream(dev))
     return out
 
 

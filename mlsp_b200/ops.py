@@ -33,12 +33,39 @@ def _require_cuda_f32(t: torch.Tensor, name: str) -> None:
         raise MlspError(f"{name}: expected float32, got {t.dtype}")
 
 
-def _stream(device) -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
-def _ptr(t) -> ctypes.c_void_p:
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+def _stream(device):
+    """torch's CURRENT stream on `device` as the raw cudaStream_t the C ABI takes (an int; ctypes converts it).  The raw getter
+    is what torch.cuda.current_stream() wraps: it skips the Stream object (7 us per call, 180 calls per training step)."""
+    if _raw_stream is not None:
+        idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t):
+    """Device address of a tensor (None -> NULL) as a plain int: the argtypes of mlsp_b200/_lib.py convert it."""
+    return t.data_ptr() if t is not None else None
+
+
+class _DeviceGuard:
+    """`with _DeviceGuard(dev)` only when dev is not already the current device (the common case costs one C call)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+        self.ctx = None if idx is None or idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 _CHECK_IDX = os.environ.get("MLSP_B200_CHECK_IDX", "0") not in ("", "0")
@@ -70,7 +97,7 @@ def knn(x: torch.Tensor, k: int, flags: int = _lib.KNN_AUTO, return_stats: bool 
     if not (1 <= k <= N):
         raise RuntimeError(f"selected index k out of range (k={k}, N={N})")  # torch.topk's message
     idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
-    with torch.cuda.device(x.device):
+    with _DeviceGuard(x.device):
         ws = _workspace(_lib.OP_KNN, B, C, N, k, x.device)
         _lib.call("mlsp_knn_f32", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(),
                   flags | (_lib.KNN_STATS if return_stats else 0), _stream(x.device))
@@ -88,7 +115,7 @@ def knn_tensor_debug(x: torch.Tensor, k: int):
     B, C, N = x.shape
     idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
     dump = torch.full((2, B, N, N), float("nan"), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _DeviceGuard(x.device):
         ws = _workspace(_lib.OP_KNN, B, C, N, k, x.device)
         _lib.call("mlsp_knn_tensor_debug", _ptr(x), B, C, N, k, _ptr(idx), _ptr(ws), ws.numel(), _ptr(dump),
                   _stream(x.device))
@@ -103,7 +130,7 @@ class _EdgeGather(torch.autograd.Function):
         B, C, N = x.shape
         k = idx.shape[2]
         out = torch.empty((B, N, k, 2 * C), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _DeviceGuard(x.device):
             ws = _workspace(_lib.OP_EDGE_FWD, B, C, N, k, x.device)
             _lib.call("mlsp_edge_gather_fwd", _ptr(x), _ptr(idx), B, C, N, k, _ptr(out), _ptr(ws), ws.numel(),
                       _stream(x.device))
@@ -128,7 +155,7 @@ def edge_gather_backward(grad: torch.Tensor, idx: torch.Tensor, C: int) -> torch
     if g.dtype != torch.float32:
         g = g.float()
     gx = torch.empty((B, C, N), dtype=torch.float32, device=g.device)
-    with torch.cuda.device(g.device):
+    with _DeviceGuard(g.device):
         ws = _workspace(_lib.OP_EDGE_BWD, B, C, N, k, g.device)
         _lib.call("mlsp_edge_gather_bwd", _ptr(g), _ptr(idx), B, C, N, k, _ptr(gx), _ptr(ws), ws.numel(),
                   _stream(g.device))
@@ -145,7 +172,7 @@ class _GraphFeature(torch.autograd.Function):
             raise RuntimeError(f"selected index k out of range (k={k}, N={N})")  # torch.topk's message
         out = torch.empty((B, N, k, 2 * C), dtype=torch.float32, device=x.device)
         idx = torch.empty((B, N, k), dtype=torch.int64, device=x.device)
-        with torch.cuda.device(x.device):
+        with _DeviceGuard(x.device):
             ws = _workspace(_lib.OP_GRAPH_FEATURE, B, C, N, k, x.device)
             _lib.call("mlsp_graph_feature_fwd", _ptr(x), B, C, N, k, _ptr(idx), _ptr(out), _ptr(ws), ws.numel(),
                       _stream(x.device))
@@ -175,7 +202,7 @@ class GraphFeatureStages:
 
     def run(self, stages: int) -> None:
         B, C, N, k = self.dims
-        with torch.cuda.device(self.x.device):
+        with _DeviceGuard(self.x.device):
             _lib.call("mlsp_graph_feature_fwd_stage", _ptr(self.x), B, C, N, k, _ptr(self.idx), _ptr(self.out), _ptr(self.ws),
                       self.ws.numel(), int(stages), _stream(self.x.device))
 
@@ -218,7 +245,7 @@ def fps_from_start(xyz: torch.Tensor, npoint: int, start: torch.Tensor):
     start = start.to(device=xyz.device, dtype=torch.int64, non_blocking=True).contiguous()
     cen = torch.empty((B, npoint), dtype=torch.int64, device=xyz.device)
     vals = torch.empty((B, 3, npoint), dtype=torch.float32, device=xyz.device)
-    with torch.cuda.device(xyz.device):
+    with _DeviceGuard(xyz.device):
         _lib.call("mlsp_fps", _ptr(xyz), B, N, int(npoint), _ptr(start), _ptr(cen), _ptr(vals), _stream(xyz.device))
     return cen, vals
 
@@ -243,7 +270,7 @@ def _region_pass(X: torch.Tensor, order: np.ndarray, min_pts: int):
     counts = torch.empty((B, NREGIONS ** 3), dtype=torch.int32, device=X.device)
     sel = torch.empty((2, B), dtype=torch.int32, device=X.device)   # [chosen ; nsel]
     order32 = np.ascontiguousarray(order, dtype=np.int32)
-    with torch.cuda.device(X.device):
+    with _DeviceGuard(X.device):
         _lib.call("mlsp_region_assign_select", _ptr(X), *_strides(X), B, C, N, ctypes.c_void_p(order32.ctypes.data), int(min_pts),
                   _ptr(region), _ptr(counts), _ptr(sel[0]), _ptr(sel[1]), _stream(X.device))
     return region, counts, sel
@@ -373,7 +400,7 @@ def deform_input(X: torch.Tensor, lookup, DefRec_dist: str = "volume_based_voxel
         look = _lookup_host(lookup)
         counts = np.where(chosen >= 0, nsel, 0)
         noise, offsets = _upload_noise(_draw_gaussians(look[np.maximum(chosen, 0)], counts), counts, X.device)
-    with torch.cuda.device(X.device):
+    with _DeviceGuard(X.device):
         _lib.call("mlsp_region_mask_scatter", _ptr(X), *_strides(X), B, C, N, _ptr(region), _ptr(sel[0]), _ptr(noise),
                   _ptr(offsets), _ptr(mask), _stream(X.device))
     return X, mask
@@ -411,12 +438,85 @@ def scan_input(X: torch.Tensor, device="cuda:0", pixel_size: float = 0.07):
     stage = torch.from_numpy(rot).pin_memory()
     rot_d = stage.to(X.device, non_blocking=True)
     err = torch.empty(1, dtype=torch.int32, device=X.device)
-    with torch.cuda.device(X.device):
+    with _DeviceGuard(X.device):
         _lib.call("mlsp_scan_zbuffer", _ptr(Xc), B, N, _ptr(rot_d), pixel, _ptr(mask), _ptr(err), _stream(X.device))
     if Xc is not X:
         X.copy_(Xc)
     if int(err.item()):
         raise IndexError("scan_input: a point falls outside the scan grid (list index out of range in p_scan)")
+    return X, mask
+
+
+class DeformPending:
+    """What deform_input_begin leaves behind: the batch, its region ids on the device and the per-cloud 27-bin histogram
+    on its way to pinned host memory."""
+    __slots__ = ("X", "region", "counts_host", "event")
+
+
+_hist_ring = _PinnedRing()
+
+
+def deform_input_begin(X: torch.Tensor) -> DeformPending:
+    """First half of deform_input (voxel modes, groups == 1) for callers that know the batch ahead of its use -- the data
+    loader has it while the previous branch / step is still running.  Launches the region assignment + histogram of X
+    (B,C,N) and starts the copy of the (B,27) histogram to pinned host memory; consumes NO random numbers and does not
+    synchronise.  `deform_input_finish` then finds the histogram on the host without waiting for the stream, so the one
+    device->host dependency of deform_input no longer stalls the host in the middle of a step."""
+    _require_cuda_f32(X, "deform_input_begin")
+    if X.dim() != 3:
+        raise MlspError(f"deform_input_begin: expected (B,C,N), got {tuple(X.shape)}")
+    B = X.shape[0]
+    region, counts, _ = _region_pass(X, np.arange(NREGIONS ** 3), 0)       # identity order: only the histogram is used
+    nbytes = 4 * B * NREGIONS ** 3
+    buf, ev = _hist_ring.stage(nbytes, X.device)
+    host = buf[:nbytes].view(torch.int32).view(B, NREGIONS ** 3)
+    host.copy_(counts, non_blocking=True)
+    ev.record(torch.cuda.current_stream(X.device))
+    h = DeformPending()
+    h.X, h.region, h.counts_host, h.event = X, region, host, ev
+    return h
+
+
+def deform_input_finish(h: DeformPending, lookup, DefRec_dist: str = "volume_based_voxels", device=None):
+    """Second half: the reference's RNG draws (one permutation(27), then per cloud the Gaussian sample of the chosen region --
+    the same stream positions as deform_input / MLSP/mlsp.py:28-50), the first-fit choice of a region with >= 40 points on
+    the host from the prefetched histogram, one pinned upload, one scatter launch.  Returns (X, mask) like deform_input; the
+    results are identical to deform_input(X, lookup, DefRec_dist) for the same RNG state (tests)."""
+    X = h.X
+    B, C, N = X.shape
+    region_ids = np.random.permutation(NREGIONS ** 3)                      # mlsp.py:28
+    h.event.synchronize()                                                   # normally long complete: no stream wait
+    counts = h.counts_host.numpy()
+    ok = counts[:, region_ids] >= _MIN_PTS_VOXEL                            # (B,27) in the walk's order
+    first = ok.argmax(axis=1)
+    has = ok[np.arange(B), first]
+    chosen = np.where(has, region_ids[first], -1).astype(np.int32)
+    nsel = np.where(has, counts[np.arange(B), np.maximum(chosen, 0)], 0).astype(np.int64)
+    mask = torch.empty((B, C, N), dtype=torch.float32, device=X.device)
+    draws = np.zeros((0, 3))
+    voxels = DefRec_dist == "volume_based_voxels"
+    if voxels:
+        look = _lookup_host(lookup)
+        draws = _draw_gaussians(look[np.maximum(chosen, 0)], nsel)
+    # one upload: [offsets (B) | chosen (B) | noise (total,3)]
+    total = int(draws.shape[0])
+    nwords = 2 * B + 3 * total
+    buf, ev = _ring.stage(4 * nwords, X.device)
+    host = buf.numpy()[: 4 * nwords].view(np.float32)
+    off = host[:B].view(np.int32)
+    off[0] = 0
+    np.cumsum(nsel[:-1], out=off[1:])
+    host[B:2 * B].view(np.int32)[:] = chosen
+    if total:
+        host[2 * B:] = draws.reshape(-1)
+    dev = torch.empty(nwords, dtype=torch.float32, device=X.device)
+    dev.copy_(buf[: 4 * nwords].view(torch.float32), non_blocking=True)
+    ev.record(torch.cuda.current_stream(X.device))
+    off_d, chosen_d = dev[:B].view(torch.int32), dev[B:2 * B].view(torch.int32)
+    noise = dev[2 * B:] if (voxels and total) else None
+    with _DeviceGuard(X.device):
+        _lib.call("mlsp_region_mask_scatter", _ptr(X), *_strides(X), B, C, N, _ptr(h.region), _ptr(chosen_d), _ptr(noise),
+                  _ptr(off_d) if voxels else None, _ptr(mask), _stream(X.device))
     return X, mask
 
 
@@ -445,7 +545,7 @@ def _deform_voxel_groups(X, mask, lookup, region_ids, DefRec_dist, groups):
         offsets = offsets.view(B, groups).t().contiguous()                   # (groups, B)
     chosen_d = torch.from_numpy(np.ascontiguousarray(chosen.T)).to(X.device)  # (groups, B)
     part = torch.empty_like(mask)
-    with torch.cuda.device(X.device):
+    with _DeviceGuard(X.device):
         for g in range(groups):
             out = mask if g == 0 else part
             _lib.call("mlsp_region_mask_scatter", _ptr(X), *_strides(X), B, C, N, _ptr(region), _ptr(chosen_d[g]), _ptr(noise),
@@ -461,7 +561,7 @@ def ball_count(x: torch.Tensor, r2: float = RADIUS ** 2) -> torch.Tensor:
     x = x.detach()
     B, C, N = x.shape
     cnt = torch.empty((B, N), dtype=torch.int32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _DeviceGuard(x.device):
         _lib.call("mlsp_ball_count", _ptr(x), *_strides(x), B, C, N, ctypes.c_float(r2), _ptr(cnt), _stream(x.device))
     return cnt
 
@@ -483,7 +583,7 @@ def _deform_radius(X: torch.Tensor, mask: torch.Tensor):
         centres[b], counts[b] = centre, n
     noise, offsets = _upload_noise(np.concatenate(chunks, axis=0), counts, X.device)
     centres_d = torch.from_numpy(centres).to(X.device, non_blocking=True)
-    with torch.cuda.device(X.device):
+    with _DeviceGuard(X.device):
         _lib.call("mlsp_ball_mask_scatter", _ptr(X), *_strides(X), B, C, N, ctypes.c_float(RADIUS ** 2), _ptr(centres_d),
                   _ptr(noise), _ptr(offsets), _ptr(mask), _stream(X.device))
     return X, mask
@@ -512,7 +612,7 @@ def cal_density(batch_pts: torch.Tensor, radius: float, num_cls: int, pergroup: 
     r2 = float(np.float32(float(radius) * float(radius)))
     labels = torch.empty((B, N, num_cls), dtype=torch.float32, device=pts.device)
     row = torch.empty((B, N), dtype=torch.int64, device=pts.device)
-    with torch.cuda.device(pts.device):
+    with _DeviceGuard(pts.device):
         _lib.call("mlsp_ball_count_labels", _ptr(pts), B, N, ctypes.c_float(r2), int(K), int(shift), int(pergroup),
                   int(num_cls), _ptr(labels), _ptr(row), _stream(pts.device))
     return labels, row
@@ -531,7 +631,7 @@ def radius_search(batch_pts: torch.Tensor, radius: float, K: int = 100):
     r2 = float(np.float32(float(radius) * float(radius)))
     ind = torch.empty((B, N, int(K)), dtype=torch.int32, device=pts.device)
     sqd = torch.empty((B, N, int(K)), dtype=torch.float32, device=pts.device)
-    with torch.cuda.device(pts.device):
+    with _DeviceGuard(pts.device):
         _lib.call("mlsp_radius_search", _ptr(pts), B, N, ctypes.c_float(r2), int(K), _ptr(ind), _ptr(sqd),
                   _stream(pts.device))
     return ind, sqd
@@ -555,7 +655,7 @@ def estimate_normals(xyz: torch.Tensor, near: int = 20, return_curvature: bool =
         idx = idx.contiguous()
     normals = torch.empty((B, N, 3), dtype=torch.float32, device=pts.device)
     curv = torch.empty((B, N), dtype=torch.float32, device=pts.device) if return_curvature else None
-    with torch.cuda.device(pts.device):
+    with _DeviceGuard(pts.device):
         _lib.call("mlsp_pca_normals", _ptr(pts), _ptr(idx), B, N, int(near), _ptr(normals), _ptr(curv),
                   _stream(pts.device))
     return (normals, curv) if return_curvature else normals
@@ -583,7 +683,7 @@ def target_structure(batch_pts: torch.Tensor, near: int, radius: float, num_cls:
     row = torch.empty((B, N), dtype=torch.int64, device=dev)
     idx = torch.empty((B, N, near), dtype=torch.int64, device=dev) if return_idx else None
     curv = torch.empty((B, N), dtype=torch.float32, device=dev) if return_curvature else None
-    with torch.cuda.device(dev):
+    with _DeviceGuard(dev):
         _lib.call("mlsp_target_structure", _ptr(pts), B, N, int(near), ctypes.c_float(r2), int(K), int(shift), int(pergroup),
                   int(num_cls), _ptr(normals), _ptr(curv), _ptr(labels), _ptr(row), _ptr(idx), _stream(dev))
     out = (normals, labels, row)
@@ -618,7 +718,7 @@ class _ChamferDir(torch.autograd.Function):
         rowmin = torch.empty((B, N), dtype=torch.float32, device=dev)
         argmin = torch.empty((B, N), dtype=torch.int64, device=dev)
         partial = torch.empty((B,), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _DeviceGuard(dev):
             ws = _workspace(_lib.OP_CHAMFER, B, 3, N, 0, dev)
             _lib.call("mlsp_chamfer_dir_fwd", _ptr(p1), *_point_strides(p1), _ptr(p2), *_point_strides(p2), _ptr(m), mbs,
                       B, N, 0, _ptr(rowmin), _ptr(argmin), _ptr(partial), _ptr(ws), ws.numel(), _stream(dev))
@@ -633,7 +733,7 @@ class _ChamferDir(torch.autograd.Function):
         g1 = torch.zeros((B, N, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
         g2 = torch.zeros((B, N, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
         grad = grad.to(torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with _DeviceGuard(dev):
             _lib.call("mlsp_chamfer_dir_bwd", _ptr(p1), *_point_strides(p1), _ptr(p2), *_point_strides(p2), _ptr(m),
                       m.stride(0), _ptr(argmin), B, N, _ptr(grad), ctypes.c_float(1.0), _ptr(g1), _ptr(g2), _stream(dev))
         return g1, g2, None
@@ -658,7 +758,7 @@ def reconstruction_loss_forward(pred, gold, mask):
     m, mbs = _mask_rows(mask)
     argmin = torch.empty((2, B, N), dtype=torch.int64, device=dev)
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _DeviceGuard(dev):
         ws = _workspace(_lib.OP_CHAMFER, B, 3, N, 0, dev)
         _lib.call("mlsp_reconstruction_loss_fwd", _ptr(pred), *_point_strides(pred), _ptr(gold), *_point_strides(gold),
                   _ptr(m), mbs, B, N, _ptr(argmin), _ptr(loss), _ptr(ws), ws.numel(), _stream(dev))
@@ -671,7 +771,7 @@ def reconstruction_loss_backward(pred, gold, m, argmin, grad):
     dev = pred.device
     gp = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
     grad = grad.to(torch.float32).contiguous()
-    with torch.cuda.device(dev):
+    with _DeviceGuard(dev):
         _lib.call("mlsp_reconstruction_loss_bwd", _ptr(pred), *_point_strides(pred), _ptr(gold), *_point_strides(gold),
                   _ptr(m), m.stride(0), _ptr(argmin), B, N, _ptr(grad), _ptr(gp), _stream(dev))
     return gp
@@ -722,7 +822,7 @@ def findneareat_index(p1: torch.Tensor, p2: torch.Tensor, mask: torch.Tensor) ->
     rowmin = torch.empty((B, N), dtype=torch.float32, device=dev)
     argmin = torch.empty((B, N), dtype=torch.int64, device=dev)
     partial = torch.empty((B,), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _DeviceGuard(dev):
         ws = _workspace(_lib.OP_CHAMFER, B, 3, N, 0, dev)
         _lib.call("mlsp_chamfer_dir_fwd", _ptr(p1), *_point_strides(p1), _ptr(p2), *_point_strides(p2), _ptr(m), mbs,
                   B, N, 1, _ptr(rowmin), _ptr(argmin), _ptr(partial), _ptr(ws), ws.numel(), _stream(dev))

@@ -13,7 +13,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from .ops import _ptr, _require_cuda_f32, _stream
+from .ops import _DeviceGuard, _ptr, _require_cuda_f32, _stream
 
 
 def mix_shapes(args, X: torch.Tensor, Y: torch.Tensor):
@@ -37,7 +37,7 @@ def mix_shapes(args, X: torch.Tensor, Y: torch.Tensor):
     meta = host.to(dev, non_blocking=True)
     inv_d = inv.pin_memory().to(dev, non_blocking=True)
     out = torch.empty_like(X)
-    with torch.cuda.device(dev):
+    with _DeviceGuard(dev):
         _lib.call("mlsp_pcm_mix", _ptr(X), B, N, int(num_pts_a), _ptr(meta[:B]), _ptr(meta[B:]), _ptr(inv_d), _ptr(out), _stream(dev))
     index_d = meta[:B]
     return out, (Y.clone(), Y[index_d].clone(), lam)

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import MlspError
-from .ops import _ptr, _require_cuda_f32, _stream
+from .ops import _DeviceGuard, _ptr, _require_cuda_f32, _stream
 
 
 class _MaxMid(torch.autograd.Function):
@@ -20,7 +20,7 @@ class _MaxMid(torch.autograd.Function):
         R, K, C = x.shape
         val = torch.empty((R, C), dtype=torch.float32, device=x.device)
         arg = torch.empty((R, C), dtype=torch.int32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _DeviceGuard(x.device):
             _lib.call("mlsp_max_mid_fwd", _ptr(x), R, K, C, _ptr(val), _ptr(arg), _stream(x.device))
         ctx.save_for_backward(arg)
         ctx.K = K
@@ -32,7 +32,7 @@ class _MaxMid(torch.autograd.Function):
         R, C = arg.shape
         g = g.contiguous()
         gin = torch.empty((R, ctx.K, C), dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
+        with _DeviceGuard(g.device):
             _lib.call("mlsp_max_mid_bwd", _ptr(g), _ptr(arg), R, ctx.K, C, _ptr(gin), _stream(g.device))
         return gin
 
@@ -45,7 +45,7 @@ class _MaxRow(torch.autograd.Function):
         R, K = x.shape
         val = torch.empty(R, dtype=torch.float32, device=x.device)
         arg = torch.empty(R, dtype=torch.int32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _DeviceGuard(x.device):
             _lib.call("mlsp_max_row_fwd", _ptr(x), R, K, _ptr(val), _ptr(arg), _stream(x.device))
         ctx.save_for_backward(arg)
         ctx.K = K
@@ -57,7 +57,7 @@ class _MaxRow(torch.autograd.Function):
         R = arg.shape[0]
         g = g.contiguous()
         gin = torch.empty((R, ctx.K), dtype=torch.float32, device=g.device)
-        with torch.cuda.device(g.device):
+        with _DeviceGuard(g.device):
             _lib.call("mlsp_max_row_bwd", _ptr(g), _ptr(arg), R, ctx.K, _ptr(gin), _stream(g.device))
         return gin
 

@@ -931,6 +931,31 @@ def test_knn_tensor_on_real_backbone_activations(golden, dev, orc, name, layers)
         assert unc == 0 and (idx != ref_idx).sum() <= bad + bad_ref, (lay, bad, bad_ref)
 
 
+def test_deform_input_begin_finish_is_deform_input(golden, dev):
+    """The asynchronous split of deform_input (histogram read-back started early, RNG draws + scatter later) gives the same
+    deformed clouds, masks and RNG stream positions as the one-call form -- on the reference-made golden and on the strided
+    view the trainers pass."""
+    lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=dev)
+    for name in ("deform_voxels_s1", "deform_voxels_s7", "deform_voxels_sparse"):
+        g = golden(name)
+        np.random.seed(int(g["seed"]))
+        h = M.deform_input_begin(torch.from_numpy(g["X0"]).to(dev))
+        torch.randn(1 << 20, device=dev).sum()                      # unrelated work between the halves
+        got_X, got_m = M.deform_input_finish(h, lookup, "volume_based_voxels")
+        after = np.random.rand()
+        assert np.array_equal(_np(got_X), g["X"]) and np.array_equal(_np(got_m), g["mask"])      # the reference's own output
+        np.random.seed(int(g["seed"]))
+        M.deform_input(torch.from_numpy(g["X0"]).to(dev), lookup, "volume_based_voxels", dev)
+        assert np.random.rand() == after                             # same RNG stream position as the one-call form
+    pts = synth.surface_clouds(6, 1024, 19).permute(0, 2, 1).contiguous().to(dev)      # (B,N,3) as the loader yields it
+    a, b = pts.clone(), pts.clone()
+    np.random.seed(5)
+    Xa, ma = M.deform_input(a.permute(0, 2, 1), lookup, "volume_based_voxels", dev)
+    np.random.seed(5)
+    Xb, mb = M.deform_input_finish(M.deform_input_begin(b.permute(0, 2, 1)), lookup)
+    assert torch.equal(a, b) and torch.equal(ma, mb) and Xb.data_ptr() == b.data_ptr() and float(ma.sum()) > 0
+
+
 def test_scan_input_golden(golden, dev):
     """8f rank 3: scan_input (MLSP/mlsp.py:54-94) as one z-buffer launch, against the reference's own function (seeded
     python + numpy RNG streams consumed in its order): clouds and masks bit for bit, in place, and the RNG streams left where
