@@ -89,6 +89,24 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None = None, 
     return out
 
 
+def _gemm_small_m(a: torch.Tensor, b: torch.Tensor, bias: torch.Tensor | None = None) -> torch.Tensor:
+    """gemm_nt for a product with few output tiles and a long K (the Linear layers on B rows: M = 32, K = 256..1024): as ONE
+    m-tile it would be a serial chain of K/64 chunks on a handful of CTAs (25 us for 0.03 GFLOP), so K is cut into 64-wide
+    chunks that run as one batched product (every chunk a CTA) and are summed -- 3x faster, same fp32 arithmetic."""
+    M, K = a.shape
+    N = b.shape[0]
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if a.dim() != 2 or b.dim() != 2 or tiles > 16 or K < 256 or K % 64:
+        return gemm_nt(a, b, bias)
+    Z = K // 64
+    while Z * tiles > 296 and Z % 2 == 0:
+        Z //= 2
+    kc = K // Z
+    part = gemm_nt(a.unflatten(1, (Z, kc)).permute(1, 0, 2), b.unflatten(1, (Z, kc)).permute(1, 0, 2))    # (Z,M,N)
+    out = part.sum(dim=0)
+    return out if bias is None else out.add_(bias)
+
+
 class _Conv1x1(torch.autograd.Function):
     """y (B,O,N) = W (O,C) x (B,C,N) + bias  -- nn.Conv1d(kernel_size=1) on the channel-major feature maps of the model.
     The kernel sees points as M (x[b] is its M-major A operand), channels as N/K; y comes out channel-major directly.
@@ -124,7 +142,7 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        y = gemm_nt(x, weight, bias)
+        y = _gemm_small_m(x, weight, bias) if x.shape[0] <= 128 else gemm_nt(x, weight, bias)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return y
@@ -137,7 +155,7 @@ class _Linear(torch.autograd.Function):
             gy = gy.contiguous()
         R = x.shape[0]
         if ctx.needs_input_grad[0]:
-            gx = gemm_nt(gy, weight.t())                                                     # (R,C)
+            gx = _gemm_small_m(gy, weight.t()) if R <= 128 else gemm_nt(gy, weight.t())      # (R,C)
         if ctx.needs_input_grad[1]:
             gw = _reduce_rows_product(gy, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:

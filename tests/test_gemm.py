@@ -193,3 +193,23 @@ def test_max_pooling_kernels_match_torch():
     for K in (1, 3, 7, 37):                                              # unaligned rows take the scalar path
         z = torch.randn(5, 7, K, generator=g).to(dev)
         assert torch.equal(pool.global_max_pool(z), z.max(dim=2, keepdim=True)[0])
+
+
+@needs_gpu
+def test_linear_on_few_rows_splits_k():
+    """nn.Linear on B rows (M = 32, K up to 1024): the K-split batched form agrees with fp64 like the plain form, forward and backward."""
+    from mlsp_b200 import linear
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    for R, C, O in ((32, 1024, 512), (32, 512, 256), (32, 256, 9), (4, 1024, 1024), (32, 192, 64)):
+        x = torch.randn(R, C, generator=g).to(dev).requires_grad_(True)
+        W = (0.1 * torch.randn(O, C, generator=g)).to(dev).requires_grad_(True)
+        b = torch.randn(O, generator=g).to(dev).requires_grad_(True)
+        gy = torch.randn(R, O, generator=g).to(dev)
+        y = linear.linear(x, W, b)
+        y.backward(gy)
+        xd, Wd, bd = (t.detach().double().requires_grad_(True) for t in (x, W, b))
+        yd = torch.nn.functional.linear(xd, Wd, bd)
+        yd.backward(gy.double())
+        for got, ref in ((y, yd), (x.grad, xd.grad), (W.grad, Wd.grad), (b.grad, bd.grad)):
+            assert float((got.detach().double() - ref.detach()).abs().max()) <= 1e-5 * float(ref.detach().abs().max()), (R, C, O, got.shape)
