@@ -318,6 +318,12 @@ MLSP_API int mlsp_gemm_f32(const float *A, int a_kmajor, long long lda, long lon
  * (pixel+5)^2 <= 3072 (the reference draws pixel_size in [0.045, 0.075]: pixel <= 44). */
 MLSP_API int mlsp_scan_zbuffer(float *X, int B, int N, const double *rot, int pixel, float *mask, int *err_flag, void *stream);
 
+/* measurement hook: mlsp_gemm_f32 with CTA 0 recording SM-clock stamps of its first 64 K-chunk iterations into tstamp (64 x 8 int64,
+ * device memory): [0] loaders see the stage free, [1] pieces stored, [2] arrived, [3] MMA warp sees the stage full, [4] MMAs issued */
+MLSP_API int mlsp_gemm_f32_timeline(const float *A, int a_kmajor, long long lda, long long a_batch_stride, const float *B, int b_kmajor,
+                           long long ldb, long long b_batch_stride, float *D, int d_rowmajor, long long ldd, long long d_batch_stride,
+                           const float *bias, int M, int N, int K, int batch, long long *tstamp, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

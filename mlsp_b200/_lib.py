@@ -52,6 +52,7 @@ SIGNATURES = {
     "mlsp_max_row_bwd": [_P, _P, _L, _I, _P, _P],
     "mlsp_scan_zbuffer": [_P, _I, _I, _P, _I, _P, _P, _P],
     "mlsp_gemm_f32": [_P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _I, _I, _I, _P],
+    "mlsp_gemm_f32_timeline": [_P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _I, _I, _I, _P, _P],
 }
 
 OP_KNN, OP_EDGE_FWD, OP_EDGE_BWD, OP_CHAMFER, OP_GRAPH_FEATURE, OP_EDGECONV_BWD = 1, 2, 3, 4, 5, 6

@@ -55,7 +55,14 @@ struct Params {
     int a_vec, b_vec;                 // 16-byte loads allowed (pointer, leading dimension and batch stride aligned)
     int mt, nt, kc;                   // tiles along M, N; K chunks
     int tiles;
+    long long *tstamp;                // measurement hook (mlsp_gemm_f32_timeline): SM-clock stamps of CTA 0's first 64 iterations
 };
+
+// stamps per iteration: [0] loader: stage free, [1] loader: pieces stored, [2] loader: arrived, [3] MMA: stage full, [4] MMA: issued + committed
+__device__ __forceinline__ void stamp(const Params &P, int it, int what)
+{
+    if (P.tstamp && blockIdx.x == 0 && it < 64) P.tstamp[it * 8 + what] = clock64();
+}
 
 // ---------------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -450,6 +457,7 @@ gemm3_kernel(const Params P)
             kfull = k0 + BK <= P.K;
             const int slot = it % STAGES;
             mbar_wait(empty + slot, ((it / STAGES) & 1) ^ 1);
+            if (lt == 0) stamp(P, it, 0);
             uint8_t *st = stages + (size_t)slot * STAGE_BYTES;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -461,12 +469,14 @@ gemm3_kernel(const Params P)
                 if (((store_b >> (2 * u)) & 3) != 3) store_item(rb[u], st + OPER_BYTES, LB.soff0 + (u ? sdb : 0u));
                 if (more) lane_load(rb[u], LB, u, db1, kfull, Bb, P.ldb, P.b_kmajor, P.b_vec, lt, w.nb0, w.nb_end, k0, P.K);
             }
+            if (lt == 0) stamp(P, it, 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> the tensor core's reads
             __syncwarp();
             if (lane == 0) {
                 if constexpr (PAIR) mbar_arrive_remote(full_c + 8u * (uint32_t)slot);
                 else mbar_arrive(full + slot);
             }
+            if (lt == 0) stamp(P, it, 2);
         }
     } else if (warp == EPI_WARPS) {
         // ================================ MMA issuer (pair: the leader's warp only) ================================
@@ -484,6 +494,7 @@ gemm3_kernel(const Params P)
                 for (int kc = 0; kc < P.kc; ++kc, ++it) {
                     const int slot = it % STAGES;
                     mbar_wait(full + slot, (it / STAGES) & 1);
+                    if (lane == 0) stamp(P, it, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(stages + (size_t)slot * STAGE_BYTES), sb = sa + OPER_BYTES;
                     const int ksteps = (min(BK, P.K - kc * BK) + 15) >> 4;
@@ -508,6 +519,7 @@ gemm3_kernel(const Params P)
                         if (kc == P.kc - 1) tc_commit_to<PAIR>(tm_full + buf);  // ... and both epilogues may drain the tile
                     }
                     __syncwarp();
+                    if (lane == 0) stamp(P, it, 4);
                 }
             }
         }
@@ -580,9 +592,9 @@ gemm3_kernel(const Params P)
 }  // namespace gemm
 }  // namespace mlsp
 
-extern "C" int mlsp_gemm_f32(const float *A, int a_kmajor, long long lda, long long a_batch_stride, const float *B, int b_kmajor,
-                             long long ldb, long long b_batch_stride, float *D, int d_rowmajor, long long ldd,
-                             long long d_batch_stride, const float *bias, int M, int N, int K, int batch, void *stream)
+static int gemm_impl(const float *A, int a_kmajor, long long lda, long long a_batch_stride, const float *B, int b_kmajor,
+                     long long ldb, long long b_batch_stride, float *D, int d_rowmajor, long long ldd,
+                     long long d_batch_stride, const float *bias, int M, int N, int K, int batch, long long *tstamp, void *stream)
 {
     using namespace mlsp;
     using namespace mlsp::gemm;
@@ -596,6 +608,7 @@ extern "C" int mlsp_gemm_f32(const float *A, int a_kmajor, long long lda, long l
     P.lda = lda; P.ldb = ldb; P.ldd = ldd;
     P.sa = a_batch_stride; P.sb = b_batch_stride; P.sd = d_batch_stride;
     P.M = M; P.N = N; P.K = K; P.batch = batch;
+    P.tstamp = tstamp;
     P.a_kmajor = a_kmajor ? 1 : 0; P.b_kmajor = b_kmajor ? 1 : 0; P.d_rowmajor = d_rowmajor ? 1 : 0;
     P.a_vec = ((reinterpret_cast<uintptr_t>(A) & 15) == 0 && lda % 4 == 0 && a_batch_stride % 4 == 0) ? 1 : 0;
     P.b_vec = ((reinterpret_cast<uintptr_t>(B) & 15) == 0 && ldb % 4 == 0 && b_batch_stride % 4 == 0) ? 1 : 0;
@@ -638,4 +651,25 @@ extern "C" int mlsp_gemm_f32(const float *A, int a_kmajor, long long lda, long l
     }
     MLSP_LAUNCH_CHECK("gemm3_kernel");
     return MLSP_OK;
+}
+
+extern "C" int mlsp_gemm_f32(const float *A, int a_kmajor, long long lda, long long a_batch_stride, const float *B, int b_kmajor,
+                             long long ldb, long long b_batch_stride, float *D, int d_rowmajor, long long ldd,
+                             long long d_batch_stride, const float *bias, int M, int N, int K, int batch, void *stream)
+{
+    return gemm_impl(A, a_kmajor, lda, a_batch_stride, B, b_kmajor, ldb, b_batch_stride, D, d_rowmajor, ldd, d_batch_stride, bias, M, N,
+                     K, batch, nullptr, stream);
+}
+
+// Measurement hook: the same call, with CTA 0 writing SM-clock stamps of its first 64 K-chunk iterations to tstamp (64 x 8
+// int64, device): [0] loaders see the stage free, [1] pieces stored, [2] arrived on `full`, [3] MMA warp sees the stage full,
+// [4] MMAs issued and committed.  tools/gemm_timeline.py turns them into the per-iteration phase table of DESIGN.md section 10.
+extern "C" int mlsp_gemm_f32_timeline(const float *A, int a_kmajor, long long lda, long long a_batch_stride, const float *B,
+                                      int b_kmajor, long long ldb, long long b_batch_stride, float *D, int d_rowmajor, long long ldd,
+                                      long long d_batch_stride, const float *bias, int M, int N, int K, int batch, long long *tstamp,
+                                      void *stream)
+{
+    MLSP_REQUIRE(tstamp, MLSP_EINVAL, "mlsp_gemm_f32_timeline: null tstamp");
+    return gemm_impl(A, a_kmajor, lda, a_batch_stride, B, b_kmajor, ldb, b_batch_stride, D, d_rowmajor, ldd, d_batch_stride, bias, M, N,
+                     K, batch, tstamp, stream);
 }
