@@ -230,6 +230,7 @@ class GraphedStep:
         self.N = N
         self.X = torch.empty_like(self.clouds)
         self.mask = torch.empty_like(self.clouds)
+        self.pending = None                                           # deform_input_begin handle of the next step's batch
         self.start_host = torch.zeros((len(FPS_SPLIT), B), dtype=torch.int64).pin_memory()
         self.start_dev = torch.zeros((len(FPS_SPLIT), B), dtype=torch.int64, device=self.clouds.device)
         off = OpTimer(False)
@@ -277,8 +278,14 @@ class GraphedStep:
         self.gA.replay()
         with torch.cuda.stream(st):
             st.wait_event(ready)
-            X = self.clouds.clone()
-            X, mask = M.deform_input(X, self.lookup, "volume_based_voxels", X.device)   # syncs st: gT of the last step is done
+            if clouds_host is None and self.pending is not None:
+                # device-resident batch: its region histogram was read back at the end of the previous step
+                # (deform_input_begin), so the host goes straight to the RNG draws -- no stream synchronisation in the step
+                X, mask = M.deform_input_finish(self.pending, self.lookup, "volume_based_voxels")
+            else:
+                X = self.clouds.clone()
+                X, mask = M.deform_input(X, self.lookup, "volume_based_voxels", X.device)   # syncs st: gT of the last step is done
+            self.pending = None
             deformed = torch.cuda.Event()
             deformed.record(st)
             for i in range(len(FPS_SPLIT)):                           # utils/pc_utils.py:150, one draw per FPS call
@@ -286,6 +293,8 @@ class GraphedStep:
             self.gT.replay()
             built = torch.cuda.Event()
             built.record(st)
+            if clouds_host is None:                                   # the next step's batch is already resident: start its read-back
+                self.pending = M.deform_input_begin(self.clouds.clone())
         sm.wait_event(deformed)
         self.X.copy_(X)
         self.mask.copy_(mask)
@@ -1620,7 +1629,9 @@ def main():
                               "two: DGCNN layers + loss on one, target builder (deform_input/FPS/normals/cardinality) on the other",
                    "graphs": "eager" if args.no_graphs else "replayed from three CUDA graphs captured through the same public API "
                              "calls (two on the model stream, one for FPS/normals/cardinality on the target stream); "
-                             "deform_input eager",
+                             "deform_input eager: with the batch resident its region histogram is read back at the end of the "
+                             "previous step (deform_input_begin / _finish: no stream sync in the step), in the e2e region "
+                             "(a new host batch every step) the one-call form with its 2B-int read-back",
                    "l2": "per-step working set ~2.9 GB (edge tensors + their gradients) >> 126 MB L2; no explicit flush",
                    "timing": "K steps between barrier+synchronize; max(CUDA-event, wall) because deform_input syncs; "
                              "op_ms_per_step / rooflines: every op captured alone in a CUDA graph and replayed K times "
