@@ -1056,7 +1056,7 @@ def run_workload_t(args):
     if dist is not None:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True,
                                                         broadcast_buffers=False)   # BatchNorm statistics stay per rank
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5, fused=True)
     criterion = torch.nn.CrossEntropyLoss()
     lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=device)
     np.random.seed(1234 + rank)
@@ -1204,7 +1204,7 @@ def extra_train_T(dist, device, rank, world, steps=8):
     net = model
     if dist is not None:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], gradient_as_bucket_view=True, broadcast_buffers=False)
-    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5)
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5, fused=True)
     crit = torch.nn.CrossEntropyLoss()
     lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=device)
     src = synth.surface_clouds(B, N, 4321 + rank).permute(0, 2, 1).contiguous().to(device)

@@ -12,7 +12,7 @@ targs = types.SimpleNamespace(mixup_params=1.0, DefRec_weight=0.5)
 torch.manual_seed(0)
 model = dgcnn.DGCNN(dropout=0.5).to(dev).train()
 model.Rec_scan.requires_grad_(False)
-opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5)
+opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5, fused=True)
 crit = torch.nn.CrossEntropyLoss()
 lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=dev)
 src = synth.surface_clouds(B, N, 1).permute(0, 2, 1).contiguous().to(dev)
