@@ -50,6 +50,7 @@ WORKLOADS = {
 LAYER_CHANNELS = WORKLOADS["A"]["layers"]
 RADIUS, NUM_CLS, NEAR, PERGROUP, SHIFT = 0.13, 16, 20, 2, 0
 FPS_SPLIT = (512, 512)                        # PCM mix-up: num_pts_a + num_pts_b = N (MLSP/PCM.py:26-30)
+PREFETCH_DEFORM = False                       # --prefetch-deform (experiment): deform_input_begin for the next step at the end of this one
 
 
 def set_workload(name):
@@ -293,7 +294,7 @@ class GraphedStep:
             self.gT.replay()
             built = torch.cuda.Event()
             built.record(st)
-            if clouds_host is None:                                   # the next step's batch is already resident: start its read-back
+            if clouds_host is None and PREFETCH_DEFORM:               # the next step's batch is already resident: start its read-back
                 self.pending = M.deform_input_begin(self.clouds.clone())
         sm.wait_event(deformed)
         self.X.copy_(X)
@@ -1342,6 +1343,9 @@ def main():
     ap.add_argument("--seg", action="store_true",
                     help="with --workload E: the PointSegDA shape (16 x 2048) and its shared layers (plain Conv2d stacks, no BatchNorm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prefetch-deform", action="store_true",
+                    help="experiment: the resident batch's deform_input histogram is read back one step ahead (deform_input_begin / "
+                         "_finish). Measured: neutral at config A (0.985 vs 0.988 ms), slower at S (1.07-1.18 vs 0.87-0.93 ms), so off")
     ap.add_argument("--no-extras", action="store_true", help="default line without the short train-T / knn-X measurements")
     ap.add_argument("--serial", action="store_true", help="headline on one stream (no target-builder overlap)")
     ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")
@@ -1351,6 +1355,8 @@ def main():
     ap.add_argument("--step-only", action="store_true",
                     help="run only the warm-up and the K timed steps (for `ncu` launch lists: kernel shares of the step itself)")
     args = ap.parse_args()
+    global PREFETCH_DEFORM
+    PREFETCH_DEFORM = args.prefetch_deform
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     from mlsp_b200 import synth
@@ -1629,9 +1635,8 @@ def main():
                               "two: DGCNN layers + loss on one, target builder (deform_input/FPS/normals/cardinality) on the other",
                    "graphs": "eager" if args.no_graphs else "replayed from three CUDA graphs captured through the same public API "
                              "calls (two on the model stream, one for FPS/normals/cardinality on the target stream); "
-                             "deform_input eager: with the batch resident its region histogram is read back at the end of the "
-                             "previous step (deform_input_begin / _finish: no stream sync in the step), in the e2e region "
-                             "(a new host batch every step) the one-call form with its 2B-int read-back",
+                             "deform_input eager (one call, 2B-int read-back; --prefetch-deform is the measured-neutral "
+                             "begin/finish variant)",
                    "l2": "per-step working set ~2.9 GB (edge tensors + their gradients) >> 126 MB L2; no explicit flush",
                    "timing": "K steps between barrier+synchronize; max(CUDA-event, wall) because deform_input syncs; "
                              "op_ms_per_step / rooflines: every op captured alone in a CUDA graph and replayed K times "
