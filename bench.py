@@ -751,6 +751,7 @@ def run_workload_e(args):
     from mlsp_b200 import synth
     seg = bool(getattr(args, "seg", False))
     B, N, k = synth.CONFIGS["S" if seg else "A"]
+    set_workload("S" if seg else "A")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -1015,14 +1016,19 @@ def run_workload_t(args):
                                 overlapped with the backward by DDP), then opt.step().
     B source + B target clouds per GPU per step; the reported clouds/s counts the B target clouds (the MLSP metric)."""
     from mlsp_b200 import synth
-    B, N, k = synth.CONFIGS["A"]
+    seg = bool(args.seg)     # --seg: BASELINE.json configs[3], the PointSegDA self-supervised step (16 x 2048, PointSegDA/trainer.py:292-431)
+    B, N, k = synth.CONFIGS["S" if seg else "A"]
+    set_workload("S" if seg else "A")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    metric = "MLSP clouds/sec (Bx1024,k=20) full DGCNN + MLSP training step"
-    cfg = {"workload": "train-T", "clouds_per_gpu": B, "source_clouds_per_gpu": B, "points": N, "k": k, "model": "PointDA DGCNN (4,548,915 parameters) + DefRec / Normal / Density heads",
+    metric = f"MLSP clouds/sec (Bx{N},k=20) full DGCNN + MLSP training step"
+    cfg = {"workload": "train-T-seg" if seg else "train-T", "clouds_per_gpu": B, "source_clouds_per_gpu": B, "points": N, "k": k,
+           "model": ("PointSegDA DGCNN_DefRec (3,082,612 parameters): segmentation + DefRec / Normal / Density heads" if seg else
+                     "PointDA DGCNN (4,548,915 parameters) + DefRec / Normal / Density heads"),
            "optimizer": "Adam lr 1e-3 wd 5e-5 (PointDA/trainer.py:258-262 defaults)",
-           "parallelism": f"dp{world}: one process per GPU, DistributedDataParallel over NCCL, one gradient all-reduce per step (18.2 MB fp32)",
+           "parallelism": f"dp{world}: one process per GPU, DistributedDataParallel over NCCL, one gradient all-reduce per step "
+                          f"({'12.3' if seg else '18.2'} MB fp32)",
            "precision": "fp32 (cuDNN / matmul TF32 off, like the reference's cudnn.enabled=False training)"}
     if args.impl == "reference":
         if rank != 0:
@@ -1031,7 +1037,7 @@ def run_workload_t(args):
                           "hot-path workloads A/S/E/X carry the reference arm"}), flush=True)
         return
     import mlsp_b200 as M
-    from mlsp_b200 import dgcnn, pcm
+    from mlsp_b200 import dgcnn, dgcnn_seg, pcm
     import types
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -1049,10 +1055,13 @@ def run_workload_t(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    targs = types.SimpleNamespace(mixup_params=1.0, DefRec_weight=0.5)
+    targs = types.SimpleNamespace(mixup_params=1.0, DefRec_weight=0.02 if seg else 0.5)   # PointSegDA/trainer.py:116 / PointDA/trainer.py
     torch.manual_seed(0)                                               # identical initial weights on every rank
-    model = dgcnn.DGCNN(num_class=10, density_num_class=NUM_CLS, pergroup=PERGROUP, dropout=0.5).to(device).train()
-    model.Rec_scan.requires_grad_(False)                               # Scan_on_trgt is off by default (PointDA/trainer.py:76)
+    if seg:
+        model = dgcnn_seg.DGCNN_DefRec(in_size=3, num_classes=8, density_num_class=NUM_CLS, pergroup=PERGROUP, dropout=0.5).to(device).train()
+    else:
+        model = dgcnn.DGCNN(num_class=10, density_num_class=NUM_CLS, pergroup=PERGROUP, dropout=0.5).to(device).train()
+        model.Rec_scan.requires_grad_(False)                           # Scan_on_trgt is off by default (PointDA/trainer.py:76)
     net = model
     if dist is not None:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True,
@@ -1064,7 +1073,7 @@ def run_workload_t(args):
     torch.manual_seed(1234 + rank)
     src_host = synth.surface_clouds(B, N, 4321 + rank).permute(0, 2, 1).contiguous().pin_memory()       # (B,N,3) like the loaders
     trg_host = synth.surface_clouds(B, N, 1234 + rank).permute(0, 2, 1).contiguous().pin_memory()
-    lab_host = (torch.arange(B) % 10).pin_memory()
+    lab_host = (torch.randint(0, 8, (B, N)) if seg else torch.arange(B) % 10).pin_memory()   # per-point part labels / class labels
     src_dev, trg_dev, lab_dev = src_host.to(device), trg_host.to(device), lab_host.to(device)
     import contextlib
 
@@ -1078,13 +1087,17 @@ def run_workload_t(args):
         tb = trg.clone()
         pending = M.deform_input_begin(tb.permute(0, 2, 1))
         with (net.no_sync() if dist is not None else contextlib.nullcontext()):
-            mixed, vals = pcm.mix_shapes(targs, src.permute(0, 2, 1), lab)
-            logits = net(mixed)
-            loss_s = pcm.calc_loss(targs, logits, vals, criterion)
+            if seg:                                                    # PointSegDA/trainer.py:298-310 (apply_PCM is off by default)
+                loss_s = dgcnn_seg.source_branch_loss(net, src, lab, DefRec_weight=targs.DefRec_weight)
+            else:
+                mixed, vals = pcm.mix_shapes(targs, src.permute(0, 2, 1), lab)
+                logits = net(mixed)
+                loss_s = pcm.calc_loss(targs, logits, vals, criterion)
             loss_s.backward()
         # the target branch's loss is computed by the module's helper through the DDP wrapper's forward
-        loss_t = dgcnn.target_branch_loss(net, tb, lookup, near=NEAR, radius=RADIUS, density_num_class=NUM_CLS,
-                                          pergroup=PERGROUP, shift=SHIFT, DefRec_weight=targs.DefRec_weight, pending=pending)
+        loss_t = (dgcnn_seg if seg else dgcnn).target_branch_loss(
+            net, tb, lookup, near=NEAR, radius=RADIUS, density_num_class=NUM_CLS, pergroup=PERGROUP, shift=SHIFT,
+            DefRec_weight=targs.DefRec_weight, pending=pending)
         loss_t.backward()
         opt.step()
         return loss_s.detach() + loss_t.detach()
@@ -1341,7 +1354,8 @@ def main():
                          "E: the DGCNN EdgeConv backbone without the edge tensor (SURVEY 8f rank 1), forward + backward; "
                          "T: the full PointDA training step (DGCNN + MLSP losses + optimiser) under DDP (configs[2])")
     ap.add_argument("--seg", action="store_true",
-                    help="with --workload E: the PointSegDA shape (16 x 2048) and its shared layers (plain Conv2d stacks, no BatchNorm)")
+                    help="with --workload E: the PointSegDA shape (16 x 2048) and its shared layers (plain Conv2d stacks, no BatchNorm); "
+                         "with --workload T: the PointSegDA training step (configs[3]: DGCNN_DefRec, 16 x 2048 per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prefetch-deform", action="store_true",
                     help="experiment: the resident batch's deform_input histogram is read back one step ahead (deform_input_begin / "

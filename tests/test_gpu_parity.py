@@ -1147,3 +1147,90 @@ def test_pcm_mix_shapes_golden(golden, dev):
         with mock.patch("numpy.random.beta", return_value=lam_edge):
             mixed, _ = pcm.mix_shapes(args, torch.from_numpy(g["X"]).to(dev), torch.from_numpy(g["Y"]).to(dev))
         assert torch.isfinite(mixed).all() and mixed.shape == (4, 3, 512)
+
+
+def test_dgcnn_seg_matches_the_reference_model(golden, dev):
+    """mlsp_b200.dgcnn_seg.DGCNN_DefRec (PointSegDA's segmentation DGCNN: fused EdgeConv layers over stacks of plain biased
+    convolutions, the four heads' first layers as one 192-channel product + per-cloud bias) against the reference's own class
+    run on the CPU by oracle/gen_golden_dgcnn_seg.py.  Stage by stage on the reference's own inputs (the kNN graph is
+    discontinuous), then the loss and the direction of the gradients end to end."""
+    from mlsp_b200 import dgcnn_seg
+    torch.backends.cudnn.allow_tf32 = False
+    g = golden("dgcnn_seg")
+    torch.manual_seed(int(g["seed"]))
+    model = dgcnn_seg.DGCNN_DefRec(in_size=3, num_classes=8, density_num_class=16, pergroup=5, dropout=0.0).to(dev).train()
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+
+    def err(a, ref):
+        a, ref = _np(a).astype(np.float64), np.asarray(ref).astype(np.float64)
+        return float(np.abs(a - ref).max()) / max(float(np.abs(ref).max()), 1e-30)
+
+    import copy
+    probe = copy.deepcopy(model)
+    with torch.no_grad():
+        T = probe.input_transform_net(M.get_graph_feature(x.detach(), None, k=20))
+        assert err(torch.matmul(T, x.detach()), g["xt"]) <= 1e-4
+        C = 64
+        stage_in = [g["xt"], g["x1"], g["x2"]]
+        stage_out = [g["x123"][:, 0:C], g["x123"][:, C:2 * C], g["x123"][:, 2 * C:]]
+        assert np.array_equal(stage_out[0], g["x1"]) and np.array_equal(stage_out[1], g["x2"])
+        for i, (layer, xin, ref) in enumerate(zip(probe.shared_layers._edge, stage_in, stage_out)):
+            out = layer(torch.from_numpy(np.ascontiguousarray(xin)).to(dev))
+            assert err(out, ref) <= 1e-5, i
+        x123 = torch.from_numpy(g["x123"]).to(dev)
+        from mlsp_b200 import pool
+        x5 = pool.global_max_pool(dgcnn_seg.conv1x1(x123, probe.shared_layers.conv6))
+        assert err(x5, g["x5"]) <= 1e-5
+        heads = [probe.seg, probe.DefRec, probe.Norm_pred, probe.Density_cls]
+        firsts = probe.heads_first_layer(x123, x5.squeeze(2), heads)
+        assert err(probe.seg.tail(firsts[0]), g["seg"]) <= 1e-4
+        assert err(probe.DefRec.tail(firsts[1]), g["DefRec"]) <= 1e-4
+        assert err(probe.Norm_pred.tail(firsts[2]), g["Normal"]) <= 1e-4
+        p_vec, p_val = probe.Density_cls.tail(firsts[3])
+        assert err(p_vec, g["density"]) <= 1e-4 and err(p_val, g["density_mse"]) <= 1e-4
+    logits = model(x, make_seg=True, activate_DefRec=False, activate_density_normal_ondef=True)
+    assert set(logits) == {"seg", "DefRec", "Normal", "density", "density_mse"}
+    loss = (logits["DefRec"].square().mean() + logits["Normal"].square().mean() + logits["density_mse"].mean()
+            + (logits["density"] * torch.arange(16.0, device=dev)).sum(1).mean() + logits["seg"].square().mean())
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    grads = dict(model.named_parameters())
+
+    def cosine(a, ref):
+        a, ref = _np(a).astype(np.float64).ravel(), np.asarray(ref).astype(np.float64).ravel()
+        return float(a @ ref / (np.linalg.norm(a) * np.linalg.norm(ref)))
+
+    assert cosine(x.grad, g["grad_x"]) > 0.98
+    assert cosine(grads["shared_layers.conv1.weight"].grad, g["grad_conv1"]) > 0.98
+    assert cosine(grads["shared_layers.conv5.weight"].grad, g["grad_conv5"]) > 0.98
+    assert cosine(grads["shared_layers.conv5.bias"].grad, g["grad_conv5_bias"]) > 0.98
+    assert cosine(grads["input_transform_net.fc3.weight"].grad, g["grad_fc3"]) > 0.98
+    assert cosine(grads["seg.conv1.weight"].grad[:, ::16, 0], g["grad_seg_conv1"]) > 0.98
+    assert cosine(grads["seg.conv1.bias"].grad, g["grad_seg_conv1_bias"]) > 0.98
+    assert cosine(grads["Norm_pred.conv1.weight"].grad[:, ::16, 0], g["grad_norm_conv1"]) > 0.98
+    assert err(model.seg.bn1.running_mean, g["seg_bn1_running_mean"]) <= 1e-3
+
+
+def test_seg_target_and_source_branch_losses_train(dev):
+    """One PointSegDA step (PointSegDA/trainer.py:298-310 source cross-entropy, :381-431 target branch) on the device at the
+    segmentation shape's N=2048: both losses finite, backward reaches the backbone, Adam lowers the target loss."""
+    from mlsp_b200 import dgcnn_seg
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = dgcnn_seg.DGCNN_DefRec(dropout=0.0).to(dev).train()
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=5e-5)
+    lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=dev)
+    batch = synth.surface_clouds(2, 2048, 3).permute(0, 2, 1).contiguous().to(dev)
+    labels = torch.randint(0, 8, (2, 2048), device=dev)
+    src = dgcnn_seg.source_branch_loss(model, batch, labels)
+    src.backward()
+    assert torch.isfinite(src) and model.shared_layers.conv1.weight.grad is not None
+    losses = []
+    for _ in range(8):
+        np.random.seed(0)
+        opt.zero_grad(set_to_none=True)
+        loss = dgcnn_seg.target_branch_loss(model, batch.clone(), lookup)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(np.isfinite(losses)) and min(losses[-3:]) < losses[0], losses

@@ -349,3 +349,23 @@ def test_dgcnn_mirror_has_the_reference_parameters_and_init():
         h.update(p.detach().cpu().numpy().tobytes())
     assert h.hexdigest() == bytes(g["digest"]).decode()
     assert sum(p.numel() for p in m.parameters()) == 4548915          # the 18.2 MB all-reduce payload
+
+
+def test_dgcnn_seg_mirror_has_the_reference_parameters_and_init():
+    """mlsp_b200.dgcnn_seg.DGCNN_DefRec mirrors PointSegDA/Models.py:197-242: same state_dict keys and bit-identical initial
+    weights for the same seed (digest stored by oracle/gen_golden_dgcnn_seg.py from the reference's own class)."""
+    import hashlib
+    import os
+    import numpy as np
+    import torch
+    from mlsp_b200 import dgcnn_seg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dgcnn_seg.npz"))
+    torch.manual_seed(int(g["seed"]))
+    m = dgcnn_seg.DGCNN_DefRec(in_size=3, num_classes=8, density_num_class=16, pergroup=5, dropout=0.0)
+    h = hashlib.sha256()
+    for name, p in sorted(m.state_dict().items()):
+        h.update(name.encode())
+        h.update(p.detach().cpu().numpy().tobytes())
+    assert h.hexdigest() == bytes(g["digest"]).decode()
+    assert sum(p.numel() for p in m.parameters()) == 3082612
+    assert not m.Density_cls.fc2.weight.requires_grad                 # PointSegDA/Models.py:373
