@@ -148,6 +148,9 @@ class Streams:
         else:
             self.model = torch.cuda.Stream(device=device) if side_model else torch.cuda.default_stream(device)
         self.target = self.model if serial else torch.cuda.Stream(device=device, priority=0)
+        # third stream: FPS x2 + normals / cardinality read only the UNDEFORMED batch, so they run beside deform_input (whose host
+        # phase -- histogram read-back, numpy draws, upload -- leaves its stream idle for ~0.25 ms)
+        self.aux = self.model if serial else torch.cuda.Stream(device=device, priority=0)
         self.serial = serial
 
 
@@ -183,7 +186,18 @@ def gpu_step(M, dev, lookup, k, timer, streams, clouds=None):
     feats = [clouds, None] + dev["feats"][2:]
     for li in [0] + list(range(2, len(feats))):
         launches += _layer(M, timer, feats[li], dev["grads"][li], k)
-    # -- target builder on its own stream
+    # -- target builder: FPS / normals / cardinality (undeformed batch) on the aux stream, enqueued before deform_input blocks the host
+    sa = streams.aux
+    with torch.cuda.stream(sa):
+        sa.wait_event(ready)
+        with timer("fps"):
+            for n in FPS_SPLIT:
+                M.farthest_point_sample(None, clouds, n)
+        pts = clouds.permute(0, 2, 1).contiguous()
+        with timer("target_structure"):                  # normals + cardinality labels: one 3-D neighbourhood pass (8f rank 2)
+            M.target_structure(pts, NEAR, RADIUS, NUM_CLS, PERGROUP, SHIFT)
+        built = torch.cuda.Event()
+        built.record(sa)
     with torch.cuda.stream(st):
         st.wait_event(ready)
         with timer("deform_input"):
@@ -192,14 +206,6 @@ def gpu_step(M, dev, lookup, k, timer, streams, clouds=None):
             X, mask = M.deform_input(X, lookup, "volume_based_voxels", clouds.device)
         deformed = torch.cuda.Event()
         deformed.record(st)
-        with timer("fps"):
-            for n in FPS_SPLIT:
-                M.farthest_point_sample(None, clouds, n)
-        pts = clouds.permute(0, 2, 1).contiguous()
-        with timer("target_structure"):                  # normals + cardinality labels: one 3-D neighbourhood pass (8f rank 2)
-            M.target_structure(pts, NEAR, RADIUS, NUM_CLS, PERGROUP, SHIFT)
-        built = torch.cuda.Event()
-        built.record(st)
     launches += LAUNCHES["deform"] + LAUNCHES["fps"] * len(FPS_SPLIT) + LAUNCHES["structure"]
     # -- layer 1 (deformed cloud) and the position loss need the target stream's results
     sm.wait_event(deformed)
@@ -218,8 +224,9 @@ class GraphedStep:
     """The same step replayed from three CUDA graphs (launch-bound otherwise: ~40 API calls, ~60 small launches),
     each captured through the public API calls of gpu_step:
       gA (model stream)  = layers 0,2,3,4 forward+backward
-      gT (target stream) = FPS x2 (start indices copied in from a pinned buffer the host fills with the same
-                           torch.randint draws farthest_point_sample makes), PCA normals, cardinality
+      gT (aux stream)    = FPS x2 (start indices uploaded just before the replay: the same torch.randint draws
+                           farthest_point_sample makes), PCA normals, cardinality -- all on the UNDEFORMED batch, so the
+                           graph is replayed BEFORE deform_input and runs beside its host phase
       gB (model stream)  = layer 1 (deformed cloud) forward+backward + reconstruction_loss forward+backward
     deform_input stays eager on the target stream (it reads two ints per cloud back to draw from numpy's RNG like
     the reference) and hands X / mask to gB through static buffers."""
@@ -232,7 +239,7 @@ class GraphedStep:
         self.X = torch.empty_like(self.clouds)
         self.mask = torch.empty_like(self.clouds)
         self.pending = None                                           # deform_input_begin handle of the next step's batch
-        self.start_host = torch.zeros((len(FPS_SPLIT), B), dtype=torch.int64).pin_memory()
+        self.built = None
         self.start_dev = torch.zeros((len(FPS_SPLIT), B), dtype=torch.int64, device=self.clouds.device)
         off = OpTimer(False)
         feats = [self.clouds, None] + dev["feats"][2:]
@@ -248,7 +255,6 @@ class GraphedStep:
             # the FPS calls are independent of each other and of the normals / cardinality (PCM samples two point sets,
             # MLSP/PCM.py:29-30): each is one CTA per cloud for ~100-250 us, so the graph forks them onto a second branch
             cap = torch.cuda.current_stream()
-            self.start_dev.copy_(self.start_host, non_blocking=True)
             side.wait_stream(cap)
             with torch.cuda.stream(side):
                 M.fps_from_start(self.clouds, FPS_SPLIT[0], self.start_dev[0])
@@ -277,6 +283,19 @@ class GraphedStep:
         ready = torch.cuda.Event()
         ready.record(sm)
         self.gA.replay()
+        sa = self.streams.aux
+        with torch.cuda.stream(sa):                                   # before deform_input: the host is about to block in it
+            sa.wait_event(ready)
+            if self.built is not None:
+                sa.wait_event(self.built)                             # (no-op in practice) the previous replay of gT is done
+            # utils/pc_utils.py:150: one CPU draw per FPS call; a fresh pinned block per step (torch's caching host allocator
+            # recycles it only after the copy has run), so the host never rewrites a buffer a pending copy still reads
+            start = torch.stack([torch.randint(0, self.N, (self.start_dev.shape[1],), dtype=torch.long) for _ in FPS_SPLIT])
+            self.start_dev.copy_(start.pin_memory(), non_blocking=True)
+            self.gT.replay()
+            built = torch.cuda.Event()
+            built.record(sa)
+            self.built = built
         with torch.cuda.stream(st):
             st.wait_event(ready)
             if clouds_host is None and self.pending is not None:
@@ -289,11 +308,6 @@ class GraphedStep:
             self.pending = None
             deformed = torch.cuda.Event()
             deformed.record(st)
-            for i in range(len(FPS_SPLIT)):                           # utils/pc_utils.py:150, one draw per FPS call
-                self.start_host[i] = torch.randint(0, self.N, (self.start_host.shape[1],), dtype=torch.long)
-            self.gT.replay()
-            built = torch.cuda.Event()
-            built.record(st)
             if clouds_host is None and PREFETCH_DEFORM:               # the next step's batch is already resident: start its read-back
                 self.pending = M.deform_input_begin(self.clouds.clone())
         sm.wait_event(deformed)

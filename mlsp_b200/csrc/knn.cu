@@ -27,7 +27,9 @@ int knn3_run(const float *x, int B, int N, int k, int64_t *idx, int *stats, floa
 
 size_t knn_workspace_bytes(int B, int C, int N, int k)
 {
-    const size_t exact = KNN_WS_HEADER + align_up(sizeof(float) * (size_t)B * N, 256);
+    // k > 64: the exact kernel runs in rounds of 64 ranks; a (pd, index) bound per row carries over between rounds
+    const size_t bounds = k > 64 ? align_up(sizeof(float2) * (size_t)B * N, 256) : 0;
+    const size_t exact = KNN_WS_HEADER + align_up(sizeof(float) * (size_t)B * N, 256) + bounds;
     if (knn_tensor_supported(B, C, N, k)) return exact > knn_tensor_workspace_bytes(B, C, N, k) ? exact : knn_tensor_workspace_bytes(B, C, N, k);
     return exact;
 }
@@ -49,10 +51,15 @@ __global__ void sq_norms_kernel(const float *__restrict__ x, int C, int N, float
 
 // NPART = number of interleaved partial chains of the pinned dot product (oracle dot_tree):
 //   C <= 4 : one chain (NPART = 1, 8 rows per warp);  otherwise 8 chains + butterfly (NPART = 8, 2 rows per warp).
+//
+// Any k <= N (the reference's args.k is a free flag): the kernel selects `k` ranks starting at rank `rank0` of a ranking whose
+// rows are `kout` long.  Round 0 is the plain top-k; a later round reads the row's bound (pd, j) = the last entry of the
+// previous round and only considers candidates that rank strictly after it -- (pd < bound) or (pd == bound and j > bound.j)
+// -- so ceil(kout / 64) launches produce the exact ranking of any length with the same arithmetic and tie rule.
 template <int KSLOTS, int NPART, int R>
 __global__ void __launch_bounds__(KNN_THREADS, 2)
 knn_exact_kernel(const float *__restrict__ x, const float *__restrict__ xx, int C, int N, int k,
-                 int64_t *__restrict__ idx)
+                 int64_t *__restrict__ idx, int rank0, int kout, float2 *__restrict__ bound)
 {
     constexpr int ROWS = (KNN_THREADS / 32) * R;
     constexpr int CK = (NPART == 1) ? 4 : 32;          // channels per shared-memory chunk (32 = one round of the 8 chains)
@@ -79,8 +86,20 @@ knn_exact_kernel(const float *__restrict__ x, const float *__restrict__ xx, int 
         xxi[rr] = (i < N) ? xxb[i] : 0.0f;
     }
     TopK<KSLOTS> top[R];
+    float bpd[R];
+    int bj[R];
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) top[rr].init(k);
+    for (int rr = 0; rr < R; ++rr) {
+        top[rr].init(k);
+        const int i = i0 + warp * R + rr;
+        bpd[rr] = INFINITY;
+        bj[rr] = -1;
+        if (rank0 > 0 && i < N) {
+            const float2 bd = bound[(size_t)b * N + i];
+            bpd[rr] = bd.x;
+            bj[rr] = __float_as_int(bd.y);
+        }
+    }
 
     for (int j0 = 0; j0 < N; j0 += KNN_TJ) {
         float acc[R][4][NPART];
@@ -140,26 +159,30 @@ knn_exact_kernel(const float *__restrict__ x, const float *__restrict__ xx, int 
                 }
                 const float t = __fmaf_rn(2.0f, dot, -cn[s]);
                 const float pd = __fsub_rn(t, xxi[rr]);
-                top[rr].offer(pd, j, j < N);
+                const bool after = pd < bpd[rr] || (pd == bpd[rr] && j > bj[rr]);     // always true in round 0
+                top[rr].offer(pd, j, j < N && after);
             }
         }
     }
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
         const int i = i0 + warp * R + rr;
+        // the worst kept entry (lowest value, largest index among equals) is the last of this round's ranking
+        if (bound != nullptr && i < N && lane == 0) bound[(size_t)b * N + i] = make_float2(top[rr].wmin, __int_as_float(top[rr].wj));
         top[rr].finish(k);
         if (i < N) {
 #pragma unroll
             for (int s = 0; s < KSLOTS; ++s) {
                 const int e = s * 32 + lane;
-                if (e < k) idx[((size_t)b * N + i) * k + e] = (int64_t)top[rr].j[s];
+                if (e < k) idx[((size_t)b * N + i) * kout + rank0 + e] = (int64_t)top[rr].j[s];
             }
         }
     }
 }
 
 template <int KSLOTS, int NPART, int R>
-static int launch_exact_t(const float *x, const float *xx, int B, int C, int N, int k, int64_t *idx, cudaStream_t st)
+static int launch_exact_t(const float *x, const float *xx, int B, int C, int N, int k, int64_t *idx, cudaStream_t st,
+                          int rank0 = 0, int kout = 0, float2 *bound = nullptr)
 {
     constexpr int ROWS = (KNN_THREADS / 32) * R;
     constexpr int CK = (NPART == 1) ? 4 : 32;
@@ -167,14 +190,23 @@ static int launch_exact_t(const float *x, const float *xx, int B, int C, int N, 
     MLSP_REQUIRE(smem <= 200 * 1024, MLSP_EUNSUPPORTED, "knn: C=%d too large for the exact kernel", C);
     dim3 grid((N + ROWS - 1) / ROWS, B);
     MLSP_CUDA(cudaFuncSetAttribute(knn_exact_kernel<KSLOTS, NPART, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_exact_kernel<KSLOTS, NPART, R><<<grid, KNN_THREADS, smem, st>>>(x, xx, C, N, k, idx);
+    knn_exact_kernel<KSLOTS, NPART, R><<<grid, KNN_THREADS, smem, st>>>(x, xx, C, N, k, idx, rank0, kout ? kout : k, bound);
     MLSP_LAUNCH_CHECK("knn_exact_kernel");
     return MLSP_OK;
 }
 
 static int launch_exact(const float *x, const float *xx, int B, int C, int N, int k, int64_t *idx,
-                        cudaStream_t st)
+                        cudaStream_t st, float2 *bound = nullptr)
 {
+    if (k > 64) {                                       // rounds of 64 ranks (see knn_exact_kernel)
+        for (int rank0 = 0; rank0 < k; rank0 += 64) {
+            const int kr = k - rank0 < 64 ? k - rank0 : 64;
+            const int rc = (C <= 4) ? launch_exact_t<2, 1, 8>(x, xx, B, C, N, kr, idx, st, rank0, k, bound)
+                                    : launch_exact_t<2, 8, 2>(x, xx, B, C, N, kr, idx, st, rank0, k, bound);
+            if (rc) return rc;
+        }
+        return MLSP_OK;
+    }
     if (C <= 4) return k <= 32 ? launch_exact_t<1, 1, 8>(x, xx, B, C, N, k, idx, st) : launch_exact_t<2, 1, 8>(x, xx, B, C, N, k, idx, st);
     return k <= 32 ? launch_exact_t<1, 8, 2>(x, xx, B, C, N, k, idx, st) : launch_exact_t<2, 8, 2>(x, xx, B, C, N, k, idx, st);
 }
@@ -188,7 +220,6 @@ extern "C" int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t 
     MLSP_REQUIRE(x && idx && ws, MLSP_EINVAL, "knn: null pointer");
     MLSP_REQUIRE(B > 0 && C > 0 && N > 0, MLSP_EINVAL, "knn: bad shape B=%d C=%d N=%d", B, C, N);
     MLSP_REQUIRE(k >= 1 && k <= N, MLSP_EINVAL, "knn: k=%d out of range for N=%d", k, N);
-    MLSP_REQUIRE(k <= 64, MLSP_EUNSUPPORTED, "knn: k=%d > 64 not supported", k);
     MLSP_REQUIRE(B <= 65535, MLSP_EUNSUPPORTED, "knn: B=%d > 65535", B);
     MLSP_REQUIRE(ws_bytes >= knn_workspace_bytes(B, C, N, k), MLSP_EWORKSPACE, "knn: workspace too small");
     cudaStream_t st = as_stream(stream);
@@ -203,7 +234,8 @@ extern "C" int mlsp_knn_f32(const float *x, int B, int C, int N, int k, int64_t 
     float *xx = reinterpret_cast<float *>(static_cast<char *>(ws) + KNN_WS_HEADER);
     sq_norms_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, C, N, xx);
     MLSP_LAUNCH_CHECK("sq_norms_kernel");
-    return launch_exact(x, xx, B, C, N, k, idx, st);
+    float2 *bound = reinterpret_cast<float2 *>(static_cast<char *>(ws) + KNN_WS_HEADER + align_up(sizeof(float) * (size_t)B * N, 256));
+    return launch_exact(x, xx, B, C, N, k, idx, st, k > 64 ? bound : nullptr);
 }
 
 // Test hook: the tensor path with a dump of the approximate filter values v = |x_j|^2 - 2 dot~ (B,N,N).

@@ -251,8 +251,16 @@ knn_centre_kernel(const float *__restrict__ x, int C, int N, float *__restrict__
     const int c = t % C, pr = t / C;
     const int stride = N / KT_CEN_SAMPLES;                 // N >= 256
     const float *row = x + ((size_t)b * C + c) * N;
+    // all of a thread's samples are loaded before the first add: one DRAM latency instead of a chain of 16-32
+    float v[KT_CEN_SAMPLES / 2];
+#pragma unroll
+    for (int u = 0; u < KT_CEN_SAMPLES / 2; ++u) {
+        const int q = pr + u * parts;
+        v[u] = (q < KT_CEN_SAMPLES) ? __ldg(row + (size_t)q * stride) : 0.0f;
+    }
     float s = 0.0f;
-    for (int q = pr; q < KT_CEN_SAMPLES; q += parts) s = __fadd_rn(s, row[(size_t)q * stride]);
+#pragma unroll
+    for (int u = 0; u < KT_CEN_SAMPLES / 2; ++u) s = __fadd_rn(s, v[u]);
     part[t] = s;
     __syncthreads();
     if (pr == 0) {

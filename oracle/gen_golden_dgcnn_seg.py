@@ -67,8 +67,8 @@ def main():
         seg=logits["seg"].detach().numpy(), DefRec=logits["DefRec"].detach().numpy(), Normal=logits["Normal"].detach().numpy(),
         density=logits["density"].detach().numpy(), density_mse=logits["density_mse"].detach().numpy(), loss=float(loss.detach()),
         grad_x=x.grad.numpy(), grad_conv1=g["shared_layers.conv1.weight"].numpy(), grad_conv5=g["shared_layers.conv5.weight"].numpy(),
-        grad_conv5_bias=g["shared_layers.conv5.bias"].numpy(), grad_fc3=g["input_transform_net.fc3.weight"].numpy(),
-        grad_seg_conv1=g["seg.conv1.weight"].numpy()[:, ::16, 0], grad_seg_conv1_bias=g["seg.conv1.bias"].numpy(),
+        grad_fc3=g["input_transform_net.fc3.weight"].numpy(),
+        grad_seg_conv1=g["seg.conv1.weight"].numpy()[:, ::16, 0], grad_seg_conv4_bias=g["seg.conv4.bias"].numpy(),
         grad_norm_conv1=g["Norm_pred.conv1.weight"].numpy()[:, ::16, 0],
         seg_bn1_running_mean=model.seg.bn1.running_mean.numpy(),
         xt=stage_in[1].numpy(), x1=stage_in[2].numpy(), x2=stage_in[3].numpy(), x123=x123.numpy(), x5=x5.numpy())
