@@ -240,6 +240,7 @@ class GraphedStep:
         self.mask = torch.empty_like(self.clouds)
         self.pending = None                                           # deform_input_begin handle of the next step's batch
         self.built = None
+        self.trace = None
         self.start_dev = torch.zeros((len(FPS_SPLIT), B), dtype=torch.int64, device=self.clouds.device)
         off = OpTimer(False)
         feats = [self.clouds, None] + dev["feats"][2:]
@@ -254,15 +255,18 @@ class GraphedStep:
         with torch.cuda.graph(self.gT):
             # the FPS calls are independent of each other and of the normals / cardinality (PCM samples two point sets,
             # MLSP/PCM.py:29-30): each is one CTA per cloud for ~100-250 us, so the graph forks them onto a second branch
+            # the structure pass does not depend on them either: every FPS call gets its own branch of the graph and the capture
+            # stream carries the normals / cardinality kernel, so the graph's critical path is one FPS call
             cap = torch.cuda.current_stream()
-            side.wait_stream(cap)
-            with torch.cuda.stream(side):
-                M.fps_from_start(self.clouds, FPS_SPLIT[0], self.start_dev[0])
-            for i, n in list(enumerate(FPS_SPLIT))[1:]:
-                M.fps_from_start(self.clouds, n, self.start_dev[i])
+            sides = [side] + [torch.cuda.Stream(device=self.clouds.device) for _ in FPS_SPLIT[1:]]
+            for i, n in enumerate(FPS_SPLIT):
+                sides[i].wait_stream(cap)
+                with torch.cuda.stream(sides[i]):
+                    M.fps_from_start(self.clouds, n, self.start_dev[i])
             pts = self.clouds.permute(0, 2, 1).contiguous()
             M.target_structure(pts, NEAR, RADIUS, NUM_CLS, PERGROUP, SHIFT)
-            cap.wait_stream(side)
+            for sd in sides:
+                cap.wait_stream(sd)
         self.launches += LAUNCHES["fps"] * len(FPS_SPLIT) + LAUNCHES["structure"]
         self.gB = torch.cuda.CUDAGraph()
         self.X.copy_(self.clouds)
@@ -280,9 +284,12 @@ class GraphedStep:
         M, sm, st = self.M, self.streams.model, self.streams.target
         if clouds_host is not None:
             self.clouds.copy_(clouds_host, non_blocking=True)        # e2e: pinned host -> the graphs' static input
-        ready = torch.cuda.Event()
+        tr = self.trace                                               # tools/step_trace.py: timing events of one step, else None
+        ready = torch.cuda.Event(enable_timing=tr is not None)
         ready.record(sm)
         self.gA.replay()
+        if tr is not None:
+            tr.append({"ready": ready, "gA": self._mark(sm)})
         sa = self.streams.aux
         with torch.cuda.stream(sa):                                   # before deform_input: the host is about to block in it
             sa.wait_event(ready)
@@ -293,9 +300,11 @@ class GraphedStep:
             start = torch.stack([torch.randint(0, self.N, (self.start_dev.shape[1],), dtype=torch.long) for _ in FPS_SPLIT])
             self.start_dev.copy_(start.pin_memory(), non_blocking=True)
             self.gT.replay()
-            built = torch.cuda.Event()
+            built = torch.cuda.Event(enable_timing=tr is not None)
             built.record(sa)
             self.built = built
+            if tr is not None:
+                tr[-1]["gT"] = built
         with torch.cuda.stream(st):
             st.wait_event(ready)
             if clouds_host is None and self.pending is not None:
@@ -306,16 +315,28 @@ class GraphedStep:
                 X = self.clouds.clone()
                 X, mask = M.deform_input(X, self.lookup, "volume_based_voxels", X.device)   # syncs st: gT of the last step is done
             self.pending = None
-            deformed = torch.cuda.Event()
+            deformed = torch.cuda.Event(enable_timing=tr is not None)
             deformed.record(st)
+            if tr is not None:
+                tr[-1]["deformed"] = deformed
+                tr[-1]["host_deform_done"] = time.perf_counter()
             if clouds_host is None and PREFETCH_DEFORM:               # the next step's batch is already resident: start its read-back
                 self.pending = M.deform_input_begin(self.clouds.clone())
         sm.wait_event(deformed)
         self.X.copy_(X)
         self.mask.copy_(mask)
         self.gB.replay()
+        if tr is not None:
+            tr[-1]["gB"] = self._mark(sm)
+            tr[-1]["host_done"] = time.perf_counter()
         sm.wait_event(built)
         return self.loss, self.launches
+
+    @staticmethod
+    def _mark(stream):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
 
 
 def op_profile(M, dev, lookup, k, reps, barrier):
@@ -1379,6 +1400,7 @@ def main():
     ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")
     ap.add_argument("--prio", action="store_true",
                     help="experiment: model stream at high stream priority, target-builder stream at low priority")
+    ap.add_argument("--fps-tune", default="", help="experiment: 'G,E' = clouds per FPS CTA (0 auto) and exclusive-SM flag (-1 auto, 0, 1) (mlsp_fps_set_*)")
     ap.add_argument("--no-graphs", action="store_true", help="eager model path (no CUDA-graph capture)")
     ap.add_argument("--step-only", action="store_true",
                     help="run only the warm-up and the K timed steps (for `ncu` launch lists: kernel shares of the step itself)")
@@ -1414,6 +1436,11 @@ def main():
         # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
+    if args.fps_tune:
+        from mlsp_b200 import _lib as _mlsp_lib
+        g_, e_ = (int(v) for v in args.fps_tune.split(","))
+        _mlsp_lib.load().mlsp_fps_set_groups(g_)
+        _mlsp_lib.load().mlsp_fps_set_exclusive(e_)
     host, dev = make_inputs(B, N, k, 1234 + rank, device, pin=True)
     lookup = torch.tensor(M.region_mean(3), dtype=torch.float32, device=device)
     np.random.seed(1234 + rank)
@@ -1427,7 +1454,8 @@ def main():
     streams = Streams(device, serial=args.serial, side_model=args.side_model_stream, prio=args.prio)
     serial = Streams(device, serial=True, side_model=args.side_model_stream)
     off = OpTimer(False)
-    sampler = ClockSampler(local_rank) if rank == 0 else None   # nvidia-smi needs ~1 s to start: begin before warm-up
+    # nvidia-smi needs ~1 s to start: begin before warm-up (MLSP_BENCH_NO_SAMPLER=1: diagnosis only -- the line then has no clocks)
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get("MLSP_BENCH_NO_SAMPLER") else None
     torch.cuda.synchronize()
     with torch.cuda.stream(streams.model):
         for _ in range(2):

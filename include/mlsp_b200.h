@@ -116,6 +116,12 @@ MLSP_API int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, int
  *   stream stays the reference's); centroids (B,npoint) int64; vals (B,3,npoint). */
 MLSP_API int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
              float *vals, void *stream);
+/* Tuning hook (process-wide, not thread-safe): clouds per CTA of the FPS kernels -- 0 = automatic (1: packing measured slower on B200,
+ * see fps.cu), 1/2/4 = forced where 1024 threads and the shared memory allow.  Results do not depend on it. */
+MLSP_API void mlsp_fps_set_groups(int groups);
+/* Tuning hook (process-wide): -1 = automatic (N > 1024), 0 = never, 1 = every FPS CTA reserves the whole shared memory of its SM so that kernels with a shared-memory
+ * footprint do not share the SM with the latency-bound sampling loop.  Results do not depend on it. */
+MLSP_API void mlsp_fps_set_exclusive(int on);
 
 /* SURVEY.md 8f rank 3 -- PCM.mix_shapes (MLSP/PCM.py:6-38) fused with its two farthest_point_sample calls: 2B CTAs sample
  *   npoint_a points of cloud b and N - npoint_a points of cloud index[b] side by side and write the mixed, point-permuted

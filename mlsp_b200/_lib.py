@@ -78,6 +78,9 @@ def load() -> ctypes.CDLL:
             fn = getattr(L, name)
             fn.argtypes = argtypes
             fn.restype = _I
+        for hook in ("mlsp_fps_set_groups", "mlsp_fps_set_exclusive"):     # void tuning hooks (include/mlsp_b200.h)
+            getattr(L, hook).argtypes = [_I]
+            getattr(L, hook).restype = None
         L.mlsp_version.restype = _I
         L.mlsp_last_error.restype = ctypes.c_char_p
         L.mlsp_workspace_bytes.argtypes = [_I, _I, _I, _I, _I]

@@ -29,17 +29,35 @@ struct FpsMix {
     int npoint_a, B;
 };
 
-template <int P, int W>
-__global__ void __launch_bounds__(32 * W)
-fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start,
-           int64_t *__restrict__ centroids, float *__restrict__ vals, FpsMix mix)
+//
+// G clouds per CTA (G groups of W warps, each with its own named barrier and its own slice of shared memory): the loop is a
+// latency chain that leaves most of an SM's issue slots idle, and a resident FPS CTA slows whatever shares its SM for the
+// whole 100-300 us it lives (measured: one 32-CTA FPS call beside the DGCNN layers' kernels costs them +0.08 ms).  Packing
+// G chains onto one SM disturbs B/G SMs instead of B -- an experiment kept behind mlsp_fps_set_groups: it did not pay (see
+// launch_fps), the default stays one cloud per CTA.
+template <int W>
+__device__ __forceinline__ void group_barrier(int group)
 {
-    extern __shared__ float4 spt[];                       // [N] (x, y, z, 0), then the winners of all rounds
-    int *hist = reinterpret_cast<int *>(spt + N);         // [npoint]
-    __shared__ __align__(16 * W) uint2 slot[2][W];        // (value bits, index), double buffered by round parity
+    if (W == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(32 * W) : "memory");
+}
 
-    int b = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+template <int P, int W, int G>
+__global__ void __launch_bounds__(32 * W * G)
+fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__restrict__ start,
+           int64_t *__restrict__ centroids, float *__restrict__ vals, FpsMix mix, int clouds, int np_max)
+{
+    extern __shared__ float4 spt_all[];                   // per group: [N] (x, y, z, 0), then the winners of all rounds [np_max]
+    __shared__ __align__(16 * W) uint2 slot_all[G][2][W]; // (value bits, index), double buffered by round parity
+
+    const int group = (G == 1) ? 0 : (int)threadIdx.x / (32 * W);
+    const int cta_cloud = blockIdx.x * G + group;         // index into `start` (and the cloud, before the mix mapping)
+    if (cta_cloud >= clouds) return;                      // whole groups leave: the named barriers are per group
+    float4 *spt = spt_all + (size_t)group * (N + (np_max + 3) / 4);
+    int *hist = reinterpret_cast<int *>(spt + N);         // [npoint]
+    uint2 (*slot)[W] = slot_all[group];
+    int b = cta_cloud;
+    const int tid = (int)threadIdx.x - group * 32 * W, lane = tid & 31, warp = tid >> 5;
     int slot0 = 0, out_b = b;                             // mix: first slot of this CTA's samples, destination cloud
     if (mix.out) {
         const bool second = b >= mix.B;
@@ -51,7 +69,7 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
     }
     const float *X = xyz + (size_t)b * 3 * N;
     for (int p = tid; p < N; p += 32 * W) spt[p] = make_float4(X[p], X[N + p], X[2 * N + p], 0.0f);
-    __syncthreads();
+    group_barrier<W>(group);
     const int p0 = tid * P;
     float px[P], py[P], pz[P], dist[P];
 #pragma unroll
@@ -69,7 +87,7 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
     uint32_t my_slot = slot_a + warp * 8, all_slots = slot_a;
     unsigned lt_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-    int far = (int)start[blockIdx.x];
+    int far = (int)start[cta_cloud];
 
     for (int s = 0; s + 1 < npoint; ++s) {
         float cx, cy, cz, cw;
@@ -103,7 +121,7 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
             "@p st.shared.v2.u32 [%1], {%2, %3};\n\t}" ::"r"((unsigned)(mine && (holders & lt_mask) == 0u)),
             "r"(my_slot), "r"(__float_as_uint(wv)), "r"((uint32_t)(p0 + br[0]))
             : "memory");
-        __syncthreads();
+        group_barrier<W>(group);
         uint32_t sv[W], si[W];
         if (W == 1) {
             asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sv[0]), "=r"(si[0]) : "r"(all_slots));
@@ -127,7 +145,7 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
         all_slots ^= W * 8;
     }
     if (tid == 0 && npoint > 0) hist[npoint - 1] = far;
-    __syncthreads();
+    group_barrier<W>(group);
     if (mix.out) {                                        // straight into the mixed cloud (scattered by the point permutation)
         float *o = mix.out + (size_t)out_b * 3 * N;
         for (int s = tid; s < npoint; s += 32 * W) {
@@ -152,17 +170,53 @@ fps_kernel(const float *__restrict__ xyz, int N, int npoint, const int64_t *__re
     }
 }
 
+// tuning hook (mlsp_fps_set_groups): 0 = automatic, else the clouds-per-CTA count to use where it fits
+static int g_fps_groups = 0;
+// tuning hook: 1 = every FPS CTA asks for the whole shared memory of its SM, so that no kernel with a shared-memory footprint
+// shares the SM with it (the chain is latency-bound: co-resident warps stretch every round)
+// -1 = automatic: on for N > 1024 (16 points per thread: a round is long and every co-resident warp stretches it -- at
+// 16 x 2048 the call takes 0.28 ms alone and 0.9 ms beside the DGCNN layers' kernels, and the step waits for it: measured
+// 0.87 -> 0.76 ms per step with the SM reserved; at 32 x 1024 the call is off the critical path and sharing is better)
+static int g_fps_exclusive = -1;
+
+template <int P, int W, int G>
+static int launch_fps_g(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
+                        float *vals, cudaStream_t st, FpsMix mix)
+{
+    const int np_max = mix.out ? N : npoint;
+    const int clouds = mix.out ? 2 * B : B;
+    const size_t smem = G * (sizeof(float4) * (size_t)N + sizeof(int) * (size_t)((np_max + 3) / 4 * 4));
+    MLSP_REQUIRE(smem <= 227 * 1024, MLSP_EUNSUPPORTED, "fps: N=%d, npoint=%d needs %zu bytes of shared memory", N, np_max, smem);
+    const bool exclusive = g_fps_exclusive < 0 ? N > 1024 : g_fps_exclusive != 0;
+    const size_t ask = exclusive ? (size_t)(227 * 1024 - 1024) : smem;
+    MLSP_CUDA(cudaFuncSetAttribute(fps_kernel<P, W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ask));
+    fps_kernel<P, W, G><<<(clouds + G - 1) / G, 32 * W * G, ask, st>>>(xyz, N, npoint, start, centroids, vals, mix, clouds, np_max);
+    MLSP_LAUNCH_CHECK("fps_kernel");
+    return MLSP_OK;
+}
+
 template <int P, int W>
 static int launch_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
                       float *vals, cudaStream_t st, FpsMix mix = FpsMix{nullptr, nullptr, nullptr, 0, 0})
 {
-    const int np_max = mix.out ? N : npoint;
-    const size_t smem = sizeof(float4) * (size_t)N + sizeof(int) * (size_t)np_max;
-    MLSP_REQUIRE(smem <= 227 * 1024, MLSP_EUNSUPPORTED, "fps: N=%d, npoint=%d needs %zu bytes of shared memory", N, np_max, smem);
-    MLSP_CUDA(cudaFuncSetAttribute(fps_kernel<P, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fps_kernel<P, W><<<mix.out ? 2 * B : B, 32 * W, smem, st>>>(xyz, N, npoint, start, centroids, vals, mix);
-    MLSP_LAUNCH_CHECK("fps_kernel");
-    return MLSP_OK;
+    // clouds per CTA: up to 1024 threads and the shared memory of one SM; small batches stay one cloud per CTA
+    const int clouds = mix.out ? 2 * B : B;
+    const size_t per = sizeof(float4) * (size_t)N + sizeof(int) * (size_t)(mix.out ? N : npoint) + 16;
+    // automatic = 1: measured on B200 (tools/fps_victims.py, tools/step_trace.py conc), packing makes the step SLOWER -- alone a
+    // call takes 0.17 (1) / 0.21 (2) / 0.31 ms (4 clouds per CTA) at 32 x 1024, and kernels that share the saturated SMs wait for
+    // their slowest CTA (kNN filter path x1.8, scatter x1.65 beside a 4-per-CTA call, x1.3 / x1.09 beside 1-per-CTA)
+    // ... except with the SM reserved (N > 1024), where two chains per SM interleave well (0.78 -> 0.76 ms per step at 16 x 2048)
+    const bool exclusive = g_fps_exclusive < 0 ? N > 1024 : g_fps_exclusive != 0;
+    int G = g_fps_groups > 0 ? g_fps_groups : (exclusive && clouds >= 16 ? 2 : 1);
+    constexpr int MAXT = (P > 4) ? 512 : 1024;          // P = 16 keeps 64 coordinates / distances in registers: <= 128 registers per thread
+    while (G > 1 && (32 * W * G > MAXT || per * G > 200 * 1024)) G >>= 1;
+    if constexpr (32 * W * 4 <= MAXT) {
+        if (G >= 4) return launch_fps_g<P, W, 4>(xyz, B, N, npoint, start, centroids, vals, st, mix);
+    }
+    if constexpr (32 * W * 2 <= MAXT) {
+        if (G >= 2) return launch_fps_g<P, W, 2>(xyz, B, N, npoint, start, centroids, vals, st, mix);
+    }
+    return launch_fps_g<P, W, 1>(xyz, B, N, npoint, start, centroids, vals, st, mix);
 }
 
 // Large clouds (8192 < N <= 16384): SoA coordinates (12 N bytes of shared memory), strided ownership, two
@@ -250,6 +304,9 @@ static int launch_fps_soa(const float *xyz, int B, int N, int npoint, const int6
 }
 
 }  // namespace mlsp
+
+extern "C" void mlsp_fps_set_groups(int groups) { mlsp::g_fps_groups = groups; }
+extern "C" void mlsp_fps_set_exclusive(int on) { mlsp::g_fps_exclusive = on; }
 
 extern "C" int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
                         float *vals, void *stream)

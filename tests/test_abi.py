@@ -37,7 +37,8 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_ctypes_signatures_cover_header(lib):
     from mlsp_b200 import _lib
-    compute = [s for s in declared_symbols() if s not in ("mlsp_version", "mlsp_last_error", "mlsp_workspace_bytes")]
+    compute = [s for s in declared_symbols() if s not in ("mlsp_version", "mlsp_last_error", "mlsp_workspace_bytes",
+                                                          "mlsp_fps_set_groups", "mlsp_fps_set_exclusive")]   # void tuning hooks
     assert sorted(compute) == sorted(_lib.SIGNATURES)
 
 
@@ -57,8 +58,10 @@ def test_argument_errors_without_gpu(lib):
     p = ctypes.cast(buf, ctypes.c_void_p)
     rc = lib.mlsp_knn_f32(p, 1, 3, 16, 40, p, p, 1 << 20, 0, None)
     assert rc == 1 and b"out of range" in lib.mlsp_last_error()
-    rc = lib.mlsp_knn_f32(p, 1, 3, 1024, 100, p, p, 1 << 20, 0, None)
+    rc = lib.mlsp_knn_f32(p, 70000, 3, 1024, 20, p, p, 1 << 20, 0, None)          # B > 65535 (grid y): MLSP_EUNSUPPORTED
     assert rc == 2
+    rc = lib.mlsp_knn_f32(p, 1, 3, 1024, 100, p, p, 16, 0, None)                  # k > 64 is accepted: the next check is the workspace
+    assert rc == 4 and b"workspace" in lib.mlsp_last_error()
 
 
 def test_edgeconv_argument_errors_without_gpu(lib):

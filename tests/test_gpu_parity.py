@@ -293,6 +293,26 @@ def test_fps_matches_oracle(dev, orc, B, N, npoint):
         assert (np.sort(_np(cen), axis=1) == np.arange(N)[None]).all()
 
 
+@pytest.mark.parametrize("B,N,npoint", [(32, 1024, 512), (16, 2048, 1024), (5, 1024, 100), (18, 300, 300), (17, 100, 37)])
+def test_fps_clouds_per_cta_do_not_change_results(dev, orc, B, N, npoint):
+    """The FPS kernel packs 1, 2 or 4 clouds into one CTA (named barriers per cloud; mlsp_fps_set_groups): same bits, ragged
+    batch sizes included (the last CTA's spare groups leave)."""
+    from mlsp_b200 import _lib
+    x = synth.clouds(B, N, 9 + N)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(N + B))
+    rc, rv = orc.fps(x.numpy(), npoint, start.numpy())
+    try:
+        for groups, exclusive in ((1, 0), (2, 0), (4, 0), (0, -1), (1, 1), (2, 1)):
+            _lib.load().mlsp_fps_set_groups(groups)
+            _lib.load().mlsp_fps_set_exclusive(exclusive)
+            cen, vals = M.fps_from_start(x.to(dev), npoint, start)
+            assert np.array_equal(_np(cen), rc), (groups, exclusive)
+            assert np.array_equal(_np(vals), rv), (groups, exclusive)
+    finally:
+        _lib.load().mlsp_fps_set_groups(0)
+        _lib.load().mlsp_fps_set_exclusive(-1)
+
+
 # ------------------------------------------------------------------------------------------------ a4 / a5 / a8
 def test_regions_golden(golden, dev):
     g = golden("regions")
