@@ -50,6 +50,7 @@ WORKLOADS = {
 LAYER_CHANNELS = WORKLOADS["A"]["layers"]
 RADIUS, NUM_CLS, NEAR, PERGROUP, SHIFT = 0.13, 16, 20, 2, 0
 FPS_SPLIT = (512, 512)                        # PCM mix-up: num_pts_a + num_pts_b = N (MLSP/PCM.py:26-30)
+PARALLEL_B = True                             # layer 1 + loss graph on the target stream, beside gA (--serial-b: behind gA, the round-1 layout)
 PREFETCH_DEFORM = False                       # --prefetch-deform (experiment): deform_input_begin for the next step at the end of this one
 
 
@@ -134,11 +135,12 @@ LAUNCHES = {"fps": 1, "knn3": 1, "knn_tensor": 3, "edge_fwd_vec": 2, "edge_bwd_v
 
 
 class Streams:
-    """Two streams per step: `model` carries the DGCNN neighbourhood layers and the loss, `target` the target
-    builder (deform_input with its host read-back, FPS, normals, cardinality).  Only layer 1 (it consumes the
-    deformed cloud) and the Chamfer loss (mask) wait for the target stream, so deform_input's device->host
-    read synchronises a nearly empty stream while the model stream keeps the GPU busy, and the latency-bound
-    FPS (one CTA per cloud) overlaps with the bandwidth-bound edge kernels."""
+    """Three streams per step: `model` carries the DGCNN neighbourhood layers of the clean batch; `target` carries deform_input
+    (with its host read-back) and then what consumes the deformed cloud -- layer 1 and the Chamfer loss; `aux` carries what only
+    reads the undeformed batch (FPS, normals, cardinality) and is enqueued BEFORE deform_input blocks the host.  deform_input's
+    device->host read synchronises a nearly empty stream while the other two keep the GPU busy.  What the overlap buys is the
+    tails of the big kernels, not free work: tools/step_trace.py shows the step is the sum of its kernels' full-GPU times (the
+    latency-bound FPS CTAs slow whatever shares their SMs, and are slowed by it: tools/fps_victims.py)."""
 
     def __init__(self, device, serial=False, side_model=False, prio=False):
         # prio: the model stream (the step's critical path) gets the high stream priority, the target builder the low
@@ -322,13 +324,26 @@ class GraphedStep:
                 tr[-1]["host_deform_done"] = time.perf_counter()
             if clouds_host is None and PREFETCH_DEFORM:               # the next step's batch is already resident: start its read-back
                 self.pending = M.deform_input_begin(self.clouds.clone())
-        sm.wait_event(deformed)
-        self.X.copy_(X)
-        self.mask.copy_(mask)
-        self.gB.replay()
-        if tr is not None:
-            tr[-1]["gB"] = self._mark(sm)
-            tr[-1]["host_done"] = time.perf_counter()
+        if PARALLEL_B and not self.streams.serial:
+            # layer 1 + the position loss only depend on the deformed cloud: replayed on the target stream they run beside the
+            # rest of gA instead of behind it (fills the tails of gA's kernels)
+            with torch.cuda.stream(st):
+                self.X.copy_(X)
+                self.mask.copy_(mask)
+                self.gB.replay()
+                done_b = self._mark(st)
+            if tr is not None:
+                tr[-1]["gB"] = done_b
+                tr[-1]["host_done"] = time.perf_counter()
+            sm.wait_event(done_b)
+        else:
+            sm.wait_event(deformed)
+            self.X.copy_(X)
+            self.mask.copy_(mask)
+            self.gB.replay()
+            if tr is not None:
+                tr[-1]["gB"] = self._mark(sm)
+                tr[-1]["host_done"] = time.perf_counter()
         sm.wait_event(built)
         return self.loss, self.launches
 
@@ -1400,13 +1415,16 @@ def main():
     ap.add_argument("--side-model-stream", action="store_true", help="experiment: model path on a non-default stream")
     ap.add_argument("--prio", action="store_true",
                     help="experiment: model stream at high stream priority, target-builder stream at low priority")
+    ap.add_argument("--serial-b", action="store_true", help="the deformed-cloud layer + loss graph behind the other layers on the model "
+                    "stream (default: beside them on the target stream; measured 0.924 -> 0.899 ms at A, 0.763 -> 0.710 at S)")
     ap.add_argument("--fps-tune", default="", help="experiment: 'G,E' = clouds per FPS CTA (0 auto) and exclusive-SM flag (-1 auto, 0, 1) (mlsp_fps_set_*)")
     ap.add_argument("--no-graphs", action="store_true", help="eager model path (no CUDA-graph capture)")
     ap.add_argument("--step-only", action="store_true",
                     help="run only the warm-up and the K timed steps (for `ncu` launch lists: kernel shares of the step itself)")
     args = ap.parse_args()
-    global PREFETCH_DEFORM
+    global PREFETCH_DEFORM, PARALLEL_B
     PREFETCH_DEFORM = args.prefetch_deform
+    PARALLEL_B = not args.serial_b
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     from mlsp_b200 import synth
@@ -1688,9 +1706,12 @@ def main():
                    "layers_C": list(LAYER_CHANNELS), "fps_split": list(FPS_SPLIT), "radius": RADIUS, "near": NEAR, "pergroup": PERGROUP, "shift": SHIFT,
                    "parallelism": f"batch-sharded x{world}, no data-path collective",
                    "streams": "one (--serial)" if args.serial else
-                              "two: DGCNN layers + loss on one, target builder (deform_input/FPS/normals/cardinality) on the other",
+                              "three: DGCNN layers of the clean batch on the model stream; deform_input, then the deformed-cloud layer + "
+                              "position loss on the target stream; FPS x2 / normals / cardinality (undeformed batch) on the aux stream, "
+                              "enqueued before deform_input's host phase",
                    "graphs": "eager" if args.no_graphs else "replayed from three CUDA graphs captured through the same public API "
-                             "calls (two on the model stream, one for FPS/normals/cardinality on the target stream); "
+                             "calls (clean-batch layers; FPS / FPS / normals+cardinality as three parallel branches; deformed-cloud "
+                             "layer + loss); "
                              "deform_input eager (one call, 2B-int read-back; --prefetch-deform is the measured-neutral "
                              "begin/finish variant)",
                    "l2": "per-step working set ~2.9 GB (edge tensors + their gradients) >> 126 MB L2; no explicit flush",
