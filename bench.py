@@ -1165,10 +1165,12 @@ def run_workload_t(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     calls0 = M._lib.calls
+    th0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         loss = step(False)
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - th0) / args.steps * 1e3   # the host's share: eager Python + launches, no sync inside
     abi_calls = M._lib.calls - calls0                              # C-ABI calls of this library in the timed region (>= 1 kernel each)
     barrier()
     dev_ms = e0.elapsed_time(e1) / args.steps
@@ -1236,6 +1238,7 @@ def run_workload_t(args):
         "collective": {"what": "DDP gradient all-reduce inside the timed backward (NCCL over NVLink/NVSwitch)", "bytes_per_step": nbytes,
                        "allreduce_alone_ms": ar_ms, "share_of_step_if_not_overlapped": (ar_ms / step_ms) if ar_ms else 0.0},
         "gpu_launches": abi_calls,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "roofline": roofline,
         "note": "gpu_launches = C-ABI calls of this library inside the timed region (each launches one to three kernels); BatchNorm, "
                 "activations, Dropout, the small losses and Adam are torch's kernels; the hot-path kernels inside the step are "

@@ -330,6 +330,25 @@ MLSP_API int mlsp_gemm_f32_timeline(const float *A, int a_kmajor, long long lda,
                            long long ldb, long long b_batch_stride, float *D, int d_rowmajor, long long ldd, long long d_batch_stride,
                            const float *bias, int M, int N, int K, int batch, long long *tstamp, void *stream);
 
+/* ---- BatchNorm (training mode) fused with the activation after it: conv_2d / fc_layer of PointDA/model_utils.py:45-89
+ * (Conv -> BatchNorm -> LeakyReLU(0.2)), the heads of PointDA/Models.py:165-285 and PointSegDA/Models.py:245-392
+ * (Conv1d -> BatchNorm1d -> ReLU) ----
+ * y = leaky_relu(batch_norm(x), slope): slope 0 = ReLU, slope 1 = no activation.  layout 0: x (R, C) row-major (channels-last
+ * 4-D maps, 2-D fc inputs; C % 4 == 0, C <= 1024, L ignored); layout 1: x (R = B, C, L) with batch stride x_batch_stride for x and
+ * y_batch_stride for y / dy / dx (floats; 0 = C * L -- a channel slice of a wider map is a valid x).  Statistics over all but
+ * the channel dimension, biased variance for the normalisation, running_var updated with the unbiased one (torch semantics);
+ * gamma / beta / running_* may be NULL.  save_mean / save_invstd (C) feed the backward; acc: 2 C doubles of scratch. */
+MLSP_API int mlsp_bn_act_fwd(const float *x, float *y, long long R, int C, int L, int layout, long long x_batch_stride,
+                    long long y_batch_stride, const float *gamma, const float *beta,
+                    float *running_mean, float *running_var, float momentum, float eps, float slope, float *save_mean,
+                    float *save_invstd, double *acc, void *stream);
+/* dx (and dgamma, dbeta (C), NULL to skip) from the layer's INPUT x, dy and the saved statistics (the activation's derivative is
+ * recomputed from x, the output is not needed). */
+MLSP_API int mlsp_bn_act_bwd(const float *x, const float *dy, float *dx, long long R, int C, int L, int layout,
+                    long long x_batch_stride, long long y_batch_stride, const float *gamma,
+                    const float *beta, const float *save_mean, const float *save_invstd, float slope, float *dgamma,
+                    float *dbeta, double *acc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,8 @@ SIGNATURES = {
     "mlsp_max_row_bwd": [_P, _P, _L, _I, _P, _P],
     "mlsp_scan_zbuffer": [_P, _I, _I, _P, _I, _P, _P, _P],
     "mlsp_gemm_f32": [_P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _I, _I, _I, _P],
+    "mlsp_bn_act_fwd": [_P, _P, _L, _I, _I, _I, _L, _L, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P],
+    "mlsp_bn_act_bwd": [_P, _P, _P, _L, _I, _I, _I, _L, _L, _P, _P, _P, _P, _F, _P, _P, _P, _P],
     "mlsp_gemm_f32_timeline": [_P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _L, _L, _P, _I, _I, _I, _I, _P, _P],
 }
 

@@ -16,7 +16,8 @@ What differs is how the forward is executed:
   channels) plus a per-cloud bias from x5 (the repeated 1024 global channels are constant over the points), i.e. the
   concatenated / repeated input is never materialised and the contraction is a third of the reference's.
 
-BatchNorm statistics, Dropout and every parameter keep torch semantics (the layers are the torch modules themselves).
+BatchNorm statistics, Dropout and every parameter keep torch semantics (the layers are the torch modules themselves; in
+training mode BatchNorm and the activation after it run as one fused pass pair, mlsp_b200.bn / csrc/bn.cu).
 """
 from __future__ import annotations
 
@@ -25,6 +26,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import edgeconv, linear, ops, pool
+from .bn import bn_act
 
 K = 20  # PointDA/Models.py:13
 
@@ -49,7 +51,8 @@ class Conv2dBlock(nn.Module):
         self.conv = nn.Sequential(nn.Conv2d(in_ch, out_ch, kernel_size=kernel, bias=bias), nn.BatchNorm2d(out_ch), act)
 
     def forward(self, x):
-        return self.conv[2](self.conv[1](conv1x1(x, self.conv[0])))
+        slope = self.conv[2].negative_slope if isinstance(self.conv[2], nn.LeakyReLU) else 0.0
+        return bn_act(conv1x1(x, self.conv[0]), self.conv[1], slope)      # BatchNorm + activation in one pass pair (bn.cu)
 
 
 class FcBlock(nn.Module):
@@ -65,9 +68,10 @@ class FcBlock(nn.Module):
 
     def forward(self, x):
         x = fc(x, self.fc[0])
-        for m in list(self.fc)[1:]:
-            x = m(x)
-        return x
+        slope = self.ac.negative_slope if isinstance(self.ac, nn.LeakyReLU) else 0.0
+        if len(self.fc) == 3:
+            return bn_act(x, self.fc[1], slope)
+        return self.ac(x)
 
 
 class TransformNet(nn.Module):
@@ -127,9 +131,9 @@ class PointHead(nn.Module):
 
     def tail(self, h1):
         """Everything after the first convolution; h1 = conv1(input) (B,256,N)."""
-        x = self.dp1(F.relu(self.bn1(h1)))
-        x = self.dp2(F.relu(self.bn2(conv1x1(x, self.conv2))))
-        x = F.relu(self.bn3(conv1x1(x, self.conv3)))
+        x = self.dp1(bn_act(h1, self.bn1, 0.0))
+        x = self.dp2(bn_act(conv1x1(x, self.conv2), self.bn2, 0.0))
+        x = bn_act(conv1x1(x, self.conv3), self.bn3, 0.0)
         return conv1x1(x, self.conv4).permute(0, 2, 1)
 
     def forward(self, x):
@@ -159,7 +163,7 @@ class DensityHead(nn.Module):
         self.fc2.weight.requires_grad = False
 
     def tail(self, h1):
-        x = self.dp1(F.relu(self.bn1(h1)))
+        x = self.dp1(bn_act(h1, self.bn1, 0.0))
         x = x.permute(0, 2, 1).reshape(-1, self.of1)
         x = self.dp1(self.mlp1(x))
         p_vec = F.softmax(fc(self.dp2(self.mlp2(x)), self.mlp3), dim=1)
@@ -214,7 +218,7 @@ class DGCNN(nn.Module):
             h = layer(h.contiguous())
             feats.append(h)
         x_cat = torch.cat(feats, dim=1)
-        x5 = F.leaky_relu(self.bn5(conv1x1(x_cat, self.conv5)), negative_slope=0.2)
+        x5 = bn_act(conv1x1(x_cat, self.conv5), self.bn5, 0.2)
         x5 = pool.global_max_pool(x5).view(B, -1)
         return x_cat, x5
 

@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import edgeconv, linear, ops, pool
+from .bn import bn_act
 from .dgcnn import DensityHead, FcBlock, conv1x1, density_loss, fc, normal_loss
 
 K = 20  # PointSegDA/Models.py:6
@@ -105,9 +106,9 @@ class PointHeadSeg(nn.Module):
         self.conv4 = nn.Conv1d(self.of3, out_size, kernel_size=1, bias=bias)
 
     def tail(self, h1):
-        x = self.dp1(F.relu(self.bn1(h1)))
-        x = self.dp2(F.relu(self.bn2(conv1x1(x, self.conv2))))
-        x = F.relu(self.bn3(conv1x1(x, self.conv3)))
+        x = self.dp1(bn_act(h1, self.bn1, 0.0))
+        x = self.dp2(bn_act(conv1x1(x, self.conv2), self.bn2, 0.0))
+        x = bn_act(conv1x1(x, self.conv3), self.bn3, 0.0)
         return conv1x1(x, self.conv4).permute(0, 2, 1)
 
     def forward(self, x):

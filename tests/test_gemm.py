@@ -213,3 +213,68 @@ def test_linear_on_few_rows_splits_k():
         yd.backward(gy.double())
         for got, ref in ((y, yd), (x.grad, xd.grad), (W.grad, Wd.grad), (b.grad, bd.grad)):
             assert float((got.detach().double() - ref.detach()).abs().max()) <= 1e-5 * float(ref.detach().abs().max()), (R, C, O, got.shape)
+
+
+@needs_gpu
+def test_bn_act_matches_torch():
+    """bn.cu against torch's BatchNorm (training mode) + LeakyReLU / ReLU in fp64: output, running statistics, num_batches_tracked,
+    and the gradients of the input, weight and bias -- on the four layouts the models use (channels-last 4-D edge features,
+    contiguous (B,C,N) maps, channels-last (B,C,N), 2-D fc inputs), ragged sizes and an odd channel count (NCL only)."""
+    import copy
+    from mlsp_b200 import bn as mbn
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+
+    def make(kind, B, C, N, k):
+        if kind == "nhwc":
+            return (torch.randn(B, N, k, C, generator=g) * 2 + 0.7).to(dev).permute(0, 3, 1, 2), torch.nn.BatchNorm2d(C)
+        if kind == "ncl":
+            return (torch.randn(B, C, N, generator=g) * 3 - 1.5).to(dev), torch.nn.BatchNorm1d(C)
+        if kind == "nlc":
+            return (torch.randn(B, N, C, generator=g) + 5.0).to(dev).permute(0, 2, 1), torch.nn.BatchNorm1d(C)
+        return (torch.randn(B, C, generator=g) * 0.5 + 100.0).to(dev), torch.nn.BatchNorm1d(C)       # large mean: cancellation case
+
+    cases = [("nhwc", 3, 64, 50, 20, 0.2), ("nhwc", 2, 128, 33, 5, 0.2), ("ncl", 4, 256, 300, 1, 0.0), ("ncl", 3, 37, 101, 1, 0.0),
+             ("nlc", 2, 1024, 77, 1, 0.2), ("fc", 32, 512, 1, 1, 0.2), ("fc", 5, 192, 1, 1, 1.0), ("ncl", 2, 16, 64, 1, 1.0)]
+    for kind, B, C, N, k, slope in cases:
+        x0, mod = make(kind, B, C, N, k)
+        mod = mod.to(dev).train()
+        with torch.no_grad():
+            mod.weight.copy_(torch.randn(C, generator=g).to(dev))         # negative scales included
+            mod.bias.copy_(torch.randn(C, generator=g).to(dev))
+            mod.running_mean.copy_(torch.randn(C, generator=g).to(dev))
+        ref = copy.deepcopy(mod).double()
+        x = x0.clone().requires_grad_(True)
+        y = mbn.bn_act(x, mod, slope)
+        xr = x0.detach().double().requires_grad_(True)
+        yr = torch.nn.functional.leaky_relu(ref(xr), slope) if slope != 1.0 else ref(xr)
+        assert y.shape == yr.shape and y.stride() == x.stride(), (kind, y.stride(), x.stride())
+        scale = float(yr.abs().max())
+        assert float((y.double() - yr).abs().max()) <= 2e-5 * scale, (kind, C, float((y.double() - yr).abs().max()), scale)
+        go = torch.randn(y.shape, generator=g).to(dev)
+        y.backward(go)
+        yr.backward(go.double())
+        for name, a, b in (("dx", x.grad, xr.grad), ("dgamma", mod.weight.grad, ref.weight.grad), ("dbeta", mod.bias.grad, ref.bias.grad)):
+            err = float((a.double() - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+            assert err <= 1e-4, (kind, C, name, err)     # act'(z) flips for |z| ~ 1e-7: a handful of elements move dgamma by < 1e-4
+        assert torch.allclose(mod.running_mean.double(), ref.running_mean, rtol=1e-5, atol=1e-6), kind
+        assert torch.allclose(mod.running_var.double(), ref.running_var, rtol=1e-5, atol=1e-6), kind
+        assert int(mod.num_batches_tracked) == int(ref.num_batches_tracked) == 1
+    # a channel slice of a wider map (torch.split of the heads' merged first layer): x keeps its batch stride, y / dx are contiguous
+    wide = torch.randn(3, 96, 50, generator=g).to(dev).requires_grad_(True)
+    parts = torch.split(wide, [32, 64], dim=1)
+    mods = [torch.nn.BatchNorm1d(32).to(dev).train(), torch.nn.BatchNorm1d(64).to(dev).train()]
+    refs = [copy.deepcopy(m).double() for m in mods]
+    out = torch.cat([mbn.bn_act(p, m, 0.0) for p, m in zip(parts, mods)], dim=1)
+    wr = wide.detach().double().requires_grad_(True)
+    outr = torch.cat([torch.relu(m(p)) for p, m in zip(torch.split(wr, [32, 64], dim=1), refs)], dim=1)
+    assert float((out.double() - outr).abs().max()) <= 2e-5 * float(outr.abs().max())
+    go = torch.randn(out.shape, generator=g).to(dev)
+    out.backward(go)
+    outr.backward(go.double())
+    assert float((wide.grad.double() - wr.grad).abs().max()) <= 1e-4 * float(wr.grad.abs().max())
+    assert torch.allclose(mods[1].running_var.double(), refs[1].running_var, rtol=1e-5, atol=1e-6)
+    # eval mode and CPU tensors run the torch modules unchanged
+    x0, mod = make("ncl", 2, 64, 40, 1)
+    mod = mod.to(dev).eval()
+    assert torch.equal(mbn.bn_act(x0, mod, 0.0), torch.relu(mod(x0)))
