@@ -337,7 +337,9 @@ MLSP_API int mlsp_gemm_f32_timeline(const float *A, int a_kmajor, long long lda,
  * 4-D maps, 2-D fc inputs; C % 4 == 0, C <= 1024, L ignored); layout 1: x (R = B, C, L) with batch stride x_batch_stride for x and
  * y_batch_stride for y / dy / dx (floats; 0 = C * L -- a channel slice of a wider map is a valid x).  Statistics over all but
  * the channel dimension, biased variance for the normalisation, running_var updated with the unbiased one (torch semantics);
- * gamma / beta / running_* may be NULL.  save_mean / save_invstd (C) feed the backward; acc: 2 C doubles of scratch. */
+ * gamma / beta / running_* may be NULL.  save_mean / save_invstd (C) feed the backward; acc: mlsp_bn_scratch_bytes(C) bytes of
+ * scratch, 8-byte aligned, contents irrelevant (per-CTA partial sums: no atomics, deterministic). */
+MLSP_API size_t mlsp_bn_scratch_bytes(int C);
 MLSP_API int mlsp_bn_act_fwd(const float *x, float *y, long long R, int C, int L, int layout, long long x_batch_stride,
                     long long y_batch_stride, const float *gamma, const float *beta,
                     float *running_mean, float *running_var, float momentum, float eps, float slope, float *save_mean,

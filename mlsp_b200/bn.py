@@ -17,6 +17,18 @@ from . import _lib
 from .ops import _DeviceGuard, _ptr, _stream
 
 
+_scratch: dict = {}
+
+
+def _scratch_doubles(C: int) -> int:
+    n = _scratch.get(C)
+    if n is None:
+        fn = _lib.load().mlsp_bn_scratch_bytes
+        fn.argtypes, fn.restype = [_lib._I], _lib._Z
+        n = _scratch[C] = (int(fn(C)) + 7) // 8
+    return n
+
+
 def _layout(x: torch.Tensor):
     """-> (layout, R, C, L) for the kernels or None.  0: (R,C) rows (channels innermost); 1: (B,C,L) contiguous."""
     if x.dim() == 2:
@@ -46,7 +58,7 @@ class _BnAct(torch.autograd.Function):
         xbs = 0 if dense else x.stride(0)
         save_mean = torch.empty(C, dtype=torch.float32, device=x.device)
         save_invstd = torch.empty(C, dtype=torch.float32, device=x.device)
-        acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        acc = torch.empty(_scratch_doubles(C), dtype=torch.float64, device=x.device)
         with _DeviceGuard(x.device):
             _lib.call("mlsp_bn_act_fwd", _ptr(x), _ptr(y), R, C, L, layout, xbs, 0, _ptr(weight) if weight is not None else None,
                       _ptr(bias) if bias is not None else None, _ptr(running_mean) if running_mean is not None else None,
@@ -71,7 +83,7 @@ class _BnAct(torch.autograd.Function):
         need_b = bias is not None and ctx.needs_input_grad[2]
         dgamma = torch.empty(C, dtype=torch.float32, device=x.device) if need_w else None
         dbeta = torch.empty(C, dtype=torch.float32, device=x.device) if need_b else None
-        acc = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+        acc = torch.empty(_scratch_doubles(C), dtype=torch.float64, device=x.device)
         with _DeviceGuard(x.device):
             _lib.call("mlsp_bn_act_bwd", _ptr(x), _ptr(dy), _ptr(dx), R, C, L, layout, ctx.xbs, 0, _ptr(weight) if weight is not None else None,
                       _ptr(bias) if bias is not None else None, _ptr(save_mean), _ptr(save_invstd), ctx.slope,

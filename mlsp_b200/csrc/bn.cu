@@ -29,9 +29,26 @@ __device__ __forceinline__ double warp_sum_d(double v)
 __device__ __forceinline__ float act_fwd(float z, float slope) { return z > 0.0f ? z : z * slope; }
 __device__ __forceinline__ float act_grad(float z, float slope) { return z > 0.0f ? 1.0f : slope; }
 
+// Statistics are accumulated about a per-channel PIVOT p (the channel's first element): d = x - p, S = sum d, T = sum d^2 in fp32
+// over chunks of BN_UNROLL elements, the chunks in fp64; mean = p + S/M, var = T/M - (S/M)^2.  With the pivot inside the data the
+// subtraction of the two moments loses nothing (a channel with mean 100 and spread 0.5 is the test case), and the fp64 work is
+// one conversion per chunk instead of per element.
+constexpr int BN_UNROLL = 4;
+
+struct BnCoef {        // per-channel coefficient block (4 C floats) in the scratch buffer, after the partial sums
+    float *a, *b, *c, *d;
+};
+__host__ __device__ __forceinline__ BnCoef bn_coef(float *f, int C) { return BnCoef{f, f + C, f + 2 * C, f + 3 * C}; }
+
+// No atomics and no zeroing: every CTA of a reduction writes its partial sums to part[cta][2 C] (fp64) and the finalize kernel
+// adds the G partials of a channel with one warp (deterministic; with atomicAdd(double) onto 2 C addresses from 1184 CTAs the
+// reduction pass ran at 44 % of the HBM peak, ncu).
+constexpr int BN_MAX_PARTS = 592;                         // 4 CTAs per SM on 148 SMs
+
 // ---------------------------------------------------------------------------------------------------------- ROWS layout
-// thread = (row residue, float4 channel group); rows_per_iter = BN_THREADS / C4 rows in flight per CTA
-// MODE 0: acc[c] += x, acc[C + c] += x^2          MODE 1: acc[c] += dz, acc[C + c] += dz * xhat
+// thread = (row residue rr, float4 channel group q); rpi = BN_THREADS / C4 consecutive rows (one contiguous 4 KB span) per CTA and
+// iteration, BN_UNROLL iterations in flight.
+// MODE 0: acc[c] += x - p, acc[C + c] += (x - p)^2          MODE 1: acc[c] += dz, acc[C + c] += dz * xhat
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_rows_reduce_kernel(const float4 *__restrict__ x, const float4 *__restrict__ dy, long long R, int C4, const float *__restrict__ mean,
@@ -43,8 +60,11 @@ bn_rows_reduce_kernel(const float4 *__restrict__ x, const float4 *__restrict__ d
     const int q = threadIdx.x % C4, rr = threadIdx.x / C4;
     double s[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
     if (rr < rpi) {
-        float m[4] = {0, 0, 0, 0}, is[4] = {1, 1, 1, 1}, g[4] = {1, 1, 1, 1}, b[4] = {0, 0, 0, 0};
-        if (MODE == 1) {
+        float m[4], is[4] = {1, 1, 1, 1}, g[4] = {1, 1, 1, 1}, b[4] = {0, 0, 0, 0};
+        if (MODE == 0) {
+            const float4 p = __ldg(x + q);                  // pivot: row 0
+            m[0] = p.x; m[1] = p.y; m[2] = p.z; m[3] = p.w;
+        } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 m[e] = mean[4 * q + e];
@@ -53,25 +73,39 @@ bn_rows_reduce_kernel(const float4 *__restrict__ x, const float4 *__restrict__ d
                 b[e] = beta ? beta[4 * q + e] : 0.0f;
             }
         }
-        for (long long r = (long long)blockIdx.x * rpi + rr; r < R; r += (long long)gridDim.x * rpi) {
-            const float4 v = __ldg(x + r * C4 + q);
-            const float xv[4] = {v.x, v.y, v.z, v.w};
-            if (MODE == 0) {
+        const long long step = (long long)gridDim.x * rpi;
+        for (long long r0 = (long long)blockIdx.x * rpi + rr; r0 < R; r0 += step * BN_UNROLL) {
+            float4 v[BN_UNROLL], d[BN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < BN_UNROLL; ++u) {
+                const long long r = r0 + u * step;
+                const bool ok = r < R;
+                v[u] = ok ? __ldg(x + r * C4 + q) : make_float4(m[0], m[1], m[2], m[3]);      // contributes 0 in both modes
+                if (MODE == 1) d[u] = ok ? __ldg(dy + r * C4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float fs[4] = {0, 0, 0, 0}, ft[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int u = 0; u < BN_UNROLL; ++u) {
+                const float xv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    s[e] += (double)xv[e];
-                    t[e] += (double)xv[e] * (double)xv[e];
+                    if (MODE == 0) {
+                        const float dd = xv[e] - m[e];
+                        fs[e] += dd;
+                        ft[e] = fmaf(dd, dd, ft[e]);
+                    } else {
+                        const float xh = (xv[e] - m[e]) * is[e];
+                        const float dz = dv[e] * act_grad(fmaf(xh, g[e], b[e]), slope);
+                        fs[e] += dz;
+                        ft[e] = fmaf(dz, xh, ft[e]);
+                    }
                 }
-            } else {
-                const float4 d = __ldg(dy + r * C4 + q);
-                const float dv[4] = {d.x, d.y, d.z, d.w};
+            }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float xh = (xv[e] - m[e]) * is[e];
-                    const float dz = dv[e] * act_grad(xh * g[e] + b[e], slope);
-                    s[e] += (double)dz;
-                    t[e] += (double)dz * (double)xh;
-                }
+            for (int e = 0; e < 4; ++e) {
+                s[e] += (double)fs[e];
+                t[e] += (double)ft[e];
             }
         }
     }
@@ -89,246 +123,290 @@ bn_rows_reduce_kernel(const float4 *__restrict__ x, const float4 *__restrict__ d
                 t[e] += red[o * C4 + q][4 + e];
             }
         const int C = 4 * C4;
+        double *part = acc + (size_t)blockIdx.x * 2 * C;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            atomicAdd(acc + 4 * q + e, s[e]);
-            atomicAdd(acc + C + 4 * q + e, t[e]);
+            part[4 * q + e] = s[e];
+            part[C + 4 * q + e] = t[e];
         }
     }
 }
 
-// per-channel coefficients from the accumulated sums; the CTA with blockIdx 0 also publishes the saved statistics and
-// updates the running ones.  sc / sh: shared arrays of C floats.
-__device__ __forceinline__ void bn_coeffs(const double *__restrict__ acc, int C, double M, const float *__restrict__ gamma,
-                                          const float *__restrict__ beta, float eps, float momentum, float *running_mean,
-                                          float *running_var, float *save_mean, float *save_invstd, bool publish, float *sc,
-                                          float *sh)
+// Between the reduction and the apply pass: one warp per channel adds the G partial sums and writes the channel's coefficients.
+//   forward : mean, invstd -> save_*, running statistics, a = scale, b = shift
+//   backward: a = mean(dz), b = mean(dz xhat), c = gamma * invstd; dgamma, dbeta
+__device__ __forceinline__ void bn_sum_parts(const double *__restrict__ part, int G, int C, int c, double &s, double &t)
 {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const double mean = acc[c] / M;
-        double var = acc[C + c] / M - mean * mean;
-        var = var > 0.0 ? var : 0.0;
-        const float is = (float)(1.0 / sqrt(var + (double)eps));
-        const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
-        sc[c] = g * is;
-        sh[c] = b - (float)mean * g * is;
-        if (publish) {
-            save_mean[c] = (float)mean;
-            save_invstd[c] = is;
-            if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
-            if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(var * (M > 1.0 ? M / (M - 1.0) : 1.0));
-        }
+    s = 0.0;
+    t = 0.0;
+    for (int g = threadIdx.x & 31; g < G; g += 32) {
+        s += part[(size_t)g * 2 * C + c];
+        t += part[(size_t)g * 2 * C + C + c];
     }
+    s = warp_sum_d(s);
+    t = warp_sum_d(t);
 }
 
 __global__ void __launch_bounds__(BN_THREADS)
-bn_rows_apply_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, long long R, int C4, const double *__restrict__ acc,
-                     const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum, float slope,
-                     float *running_mean, float *running_var, float *save_mean, float *save_invstd)
+bn_finalize_fwd_kernel(const double *__restrict__ part, int G, float *coef, int C, double M, const float *__restrict__ pivot,
+                       long long pivot_stride, const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
+                       float *running_mean, float *running_var, float *save_mean, float *save_invstd)
 {
-    extern __shared__ float coef[];                       // scale [C] | shift [C]
-    const int C = 4 * C4;
-    float *sc = coef, *sh = coef + C;
-    bn_coeffs(acc, C, (double)R, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, blockIdx.x == 0, sc, sh);
-    __syncthreads();
-    const long long total = R * C4;
-    for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * BN_THREADS) {
-        const int q = (int)(i % C4);
-        const float4 v = __ldcs(x + i);
-        const float4 a = *reinterpret_cast<const float4 *>(sc + 4 * q), b = *reinterpret_cast<const float4 *>(sh + 4 * q);
-        float4 o;
-        o.x = act_fwd(fmaf(v.x, a.x, b.x), slope);
-        o.y = act_fwd(fmaf(v.y, a.y, b.y), slope);
-        o.z = act_fwd(fmaf(v.z, a.z, b.z), slope);
-        o.w = act_fwd(fmaf(v.w, a.w, b.w), slope);
-        y[i] = o;
-    }
+    const BnCoef k = bn_coef(coef, C);
+    const int c = blockIdx.x * (BN_THREADS / 32) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double S, T;
+    bn_sum_parts(part, G, C, c, S, T);
+    if ((threadIdx.x & 31) != 0) return;
+    const double md = S / M;
+    const double mean = (double)pivot[c * pivot_stride] + md;
+    double var = T / M - md * md;
+    var = var > 0.0 ? var : 0.0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    k.a[c] = g * is;
+    k.b[c] = (float)((double)b - mean * (double)(g * is));
+    save_mean[c] = (float)mean;
+    save_invstd[c] = is;
+    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(var * (M > 1.0 ? M / (M - 1.0) : 1.0));
 }
 
-// dx = gamma * invstd * (dz - sum_dz / M - xhat * sum_dz_xhat / M); blockIdx 0 writes dgamma = sum dz xhat, dbeta = sum dz
 __global__ void __launch_bounds__(BN_THREADS)
-bn_rows_bwd_apply_kernel(const float4 *__restrict__ x, const float4 *__restrict__ dy, float4 *__restrict__ dx, long long R, int C4,
-                         const double *__restrict__ acc, const float *__restrict__ mean, const float *__restrict__ invstd,
-                         const float *__restrict__ gamma, const float *__restrict__ beta, float slope, float *dgamma, float *dbeta)
+bn_finalize_bwd_kernel(const double *__restrict__ part, int G, float *coef, int C, double M, const float *__restrict__ gamma,
+                       const float *__restrict__ invstd, float *dgamma, float *dbeta)
 {
-    extern __shared__ float coef[];                       // mean | invstd | gamma | beta | k1 = sum_dz / M | k2 = sum_dz_xhat / M
+    const BnCoef k = bn_coef(coef, C);
+    const int c = blockIdx.x * (BN_THREADS / 32) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double S, T;
+    bn_sum_parts(part, G, C, c, S, T);
+    if ((threadIdx.x & 31) != 0) return;
+    k.a[c] = (float)(S / M);                           // mean(dz)
+    k.b[c] = (float)(T / M);                           // mean(dz * xhat)
+    k.c[c] = (gamma ? gamma[c] : 1.0f) * invstd[c];    // gamma * invstd
+    if (dgamma) dgamma[c] = (float)T;
+    if (dbeta) dbeta[c] = (float)S;
+}
+
+// MODE 0: y = act(x * a + b)      MODE 1: dx = c * (dz - a - xhat * b), dz = dy * act'(xhat * gamma + beta)
+template <int MODE>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_rows_apply_kernel(const float4 *__restrict__ x, const float4 *__restrict__ dy, float4 *__restrict__ out, long long R, int C4,
+                     float *__restrict__ coef, const float *__restrict__ mean, const float *__restrict__ invstd,
+                     const float *__restrict__ gamma, const float *__restrict__ beta, float slope)
+{
     const int C = 4 * C4;
-    float *cm = coef, *ci = coef + C, *cg = coef + 2 * C, *cb = coef + 3 * C, *k1 = coef + 4 * C, *k2 = coef + 5 * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        cm[c] = mean[c];
-        ci[c] = invstd[c];
-        cg[c] = gamma ? gamma[c] : 1.0f;
-        cb[c] = beta ? beta[c] : 0.0f;
-        k1[c] = (float)(acc[c] / (double)R);
-        k2[c] = (float)(acc[C + c] / (double)R);
-        if (blockIdx.x == 0) {
-            if (dgamma) dgamma[c] = (float)acc[C + c];
-            if (dbeta) dbeta[c] = (float)acc[c];
+    const BnCoef k = bn_coef(coef, C);
+    const int rpi = BN_THREADS / C4;
+    const int q = threadIdx.x % C4, rr = threadIdx.x / C4;
+    if (rr >= rpi) return;
+    float ka[4], kb[4], kc[4], m[4], is[4], g[4], b[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        ka[e] = k.a[4 * q + e];
+        kb[e] = k.b[4 * q + e];
+        if (MODE == 1) {
+            kc[e] = k.c[4 * q + e];
+            m[e] = mean[4 * q + e];
+            is[e] = invstd[4 * q + e];
+            g[e] = gamma ? gamma[4 * q + e] : 1.0f;
+            b[e] = beta ? beta[4 * q + e] : 0.0f;
         }
     }
-    __syncthreads();
-    const long long total = R * C4;
-    for (long long i = (long long)blockIdx.x * BN_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * BN_THREADS) {
-        const int q = (int)(i % C4);
-        const float4 v = __ldcs(x + i), d = __ldcs(dy + i);
-        const float xv[4] = {v.x, v.y, v.z, v.w}, dv[4] = {d.x, d.y, d.z, d.w};
-        float o[4];
+    const long long step = (long long)gridDim.x * rpi;
+    for (long long r0 = (long long)blockIdx.x * rpi + rr; r0 < R; r0 += step * BN_UNROLL) {
+        float4 v[BN_UNROLL], d[BN_UNROLL];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = 4 * q + e;
-            const float xh = (xv[e] - cm[c]) * ci[c];
-            const float dz = dv[e] * act_grad(xh * cg[c] + cb[c], slope);
-            o[e] = cg[c] * ci[c] * (dz - k1[c] - xh * k2[c]);
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            const long long r = r0 + u * step;
+            if (r < R) {
+                v[u] = __ldcs(x + r * C4 + q);
+                if (MODE == 1) d[u] = __ldcs(dy + r * C4 + q);
+            }
         }
-        dx[i] = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int u = 0; u < BN_UNROLL; ++u) {
+            const long long r = r0 + u * step;
+            if (r >= R) break;
+            const float xv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            float o[4];
+            if (MODE == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = act_fwd(fmaf(xv[e], ka[e], kb[e]), slope);
+            } else {
+                const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float xh = (xv[e] - m[e]) * is[e];
+                    const float dz = dv[e] * act_grad(fmaf(xh, g[e], b[e]), slope);
+                    o[e] = kc[e] * (dz - ka[e] - xh * kb[e]);
+                }
+            }
+            out[r * C4 + q] = make_float4(o[0], o[1], o[2], o[3]);
+        }
     }
 }
 
 // ----------------------------------------------------------------------------------------------------------- NCL layout
-// one warp per (b, c) row of L contiguous values
+// CTA = (channel c, batch residue): the CTA walks the rows (b, c), b = blockIdx.y, blockIdx.y + gridDim.y, ..., all threads on one
+// row at a time (L = 1024: one float4 per thread), BN_UNROLL rows in flight; per-channel values are loaded once per CTA.
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_ncl_reduce_kernel(const float *__restrict__ x, const float *__restrict__ dy, int B, int C, int L, long long xbs, long long obs,
-                     const float *__restrict__ mean,
-                     const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, float slope,
-                     double *__restrict__ acc)
+                     const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
+                     const float *__restrict__ beta, float slope, double *__restrict__ acc)
 {
-    const int lane = threadIdx.x & 31;
-    const long long rows = (long long)B * C;
-    for (long long row = (long long)blockIdx.x * (BN_THREADS / 32) + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * (BN_THREADS / 32)) {
-        const int c = (int)(row % C);
-        const long long bb = row / C;
-        const float *xr = x + bb * xbs + (long long)c * L;
-        const float *dr = MODE == 1 ? dy + bb * obs + (long long)c * L : nullptr;
-        float m = 0, is = 1, g = 1, b = 0;
-        if (MODE == 1) {
-            m = mean[c];
-            is = invstd[c];
-            g = gamma ? gamma[c] : 1.0f;
-            b = beta ? beta[c] : 0.0f;
-        }
-        double s = 0, t = 0;
-        const bool vec = (L & 3) == 0 && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0) && (MODE == 0 || (reinterpret_cast<uintptr_t>(dr) & 15) == 0);
-        if (vec) {
-            for (int l = lane * 4; l < L; l += 128) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(xr + l));
-                const float xv[4] = {v.x, v.y, v.z, v.w};
-                float dv[4] = {0, 0, 0, 0};
-                if (MODE == 1) {
-                    const float4 d = __ldg(reinterpret_cast<const float4 *>(dr + l));
-                    dv[0] = d.x; dv[1] = d.y; dv[2] = d.z; dv[3] = d.w;
-                }
+    __shared__ double red[2][BN_THREADS / 32];
+    const int c = blockIdx.x;
+    float m, is = 1, g = 1, bt = 0;
+    if (MODE == 0) {
+        m = __ldg(x + (long long)c * L);                    // pivot: (b = 0, c, l = 0)
+    } else {
+        m = mean[c];
+        is = invstd[c];
+        g = gamma ? gamma[c] : 1.0f;
+        bt = beta ? beta[c] : 0.0f;
+    }
+    const bool vec = (L & 3) == 0 && (xbs & 3) == 0 && (obs & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (MODE == 0 || (reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+    double s = 0, t = 0;
+    if (vec) {
+        for (int b0 = blockIdx.y; b0 < B; b0 += gridDim.y * BN_UNROLL) {
+            for (int l = threadIdx.x * 4; l < L; l += BN_THREADS * 4) {
+                float4 v[BN_UNROLL], d[BN_UNROLL];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (MODE == 0) {
-                        s += (double)xv[e];
-                        t += (double)xv[e] * (double)xv[e];
-                    } else {
-                        const float xh = (xv[e] - m) * is;
-                        const float dz = dv[e] * act_grad(xh * g + b, slope);
-                        s += (double)dz;
-                        t += (double)dz * (double)xh;
+                for (int u = 0; u < BN_UNROLL; ++u) {
+                    const int b = b0 + u * gridDim.y;
+                    const bool ok = b < B;
+                    v[u] = ok ? __ldg(reinterpret_cast<const float4 *>(x + b * xbs + (long long)c * L + l)) : make_float4(m, m, m, m);
+                    if (MODE == 1) d[u] = ok ? __ldg(reinterpret_cast<const float4 *>(dy + b * obs + (long long)c * L + l)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float fs = 0, ft = 0;
+#pragma unroll
+                for (int u = 0; u < BN_UNROLL; ++u) {
+                    const float xv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                    const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (MODE == 0) {
+                            const float dd = xv[e] - m;
+                            fs += dd;
+                            ft = fmaf(dd, dd, ft);
+                        } else {
+                            const float xh = (xv[e] - m) * is;
+                            const float dz = dv[e] * act_grad(fmaf(xh, g, bt), slope);
+                            fs += dz;
+                            ft = fmaf(dz, xh, ft);
+                        }
                     }
                 }
+                s += (double)fs;
+                t += (double)ft;
             }
-        } else {
-            for (int l = lane; l < L; l += 32) {
-                const float xv = xr[l];
+        }
+    } else {
+        for (int b = blockIdx.y; b < B; b += gridDim.y)
+            for (int l = threadIdx.x; l < L; l += BN_THREADS) {
+                const float xv = x[b * xbs + (long long)c * L + l];
                 if (MODE == 0) {
-                    s += (double)xv;
-                    t += (double)xv * (double)xv;
+                    const float dd = xv - m;
+                    s += (double)dd;
+                    t += (double)dd * (double)dd;
                 } else {
                     const float xh = (xv - m) * is;
-                    const float dz = dr[l] * act_grad(xh * g + b, slope);
+                    const float dz = dy[b * obs + (long long)c * L + l] * act_grad(fmaf(xh, g, bt), slope);
                     s += (double)dz;
                     t += (double)dz * (double)xh;
                 }
             }
+    }
+    s = warp_sum_d(s);
+    t = warp_sum_d(t);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s;
+        red[1][threadIdx.x >> 5] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < BN_THREADS / 32; ++w) {
+            s += red[0][w];
+            t += red[1][w];
         }
-        s = warp_sum_d(s);
-        t = warp_sum_d(t);
-        if (lane == 0) {
-            atomicAdd(acc + c, s);
-            atomicAdd(acc + C + c, t);
-        }
+        double *part = acc + (size_t)blockIdx.y * 2 * C;
+        part[c] = s;
+        part[C + c] = t;
     }
 }
 
-// one CTA per (b, c) row chunk; MODE 0 = forward apply, MODE 1 = backward apply
 template <int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_ncl_apply_kernel(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ out, int B, int C, int L,
-                    long long xbs, long long obs, const double *__restrict__ acc, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
-                    float momentum, float slope, float *running_mean, float *running_var, float *save_mean, float *save_invstd,
-                    float *dgamma, float *dbeta)
+                    long long xbs, long long obs, float *__restrict__ coef, const float *__restrict__ mean,
+                    const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta, float slope)
 {
-    const long long rows = (long long)B * C;
-    const double M = (double)B * (double)L;
-    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-        const int c = (int)(row % C);
-        const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
-        float mean, is, k1 = 0, k2 = 0;
-        if (MODE == 0) {
-            const double mu = acc[c] / M;
-            double var = acc[C + c] / M - mu * mu;
-            var = var > 0.0 ? var : 0.0;
-            mean = (float)mu;
-            is = (float)(1.0 / sqrt(var + (double)eps));
-            if (row < C && threadIdx.x == 0) {               // rows 0..C-1 are cloud 0: each channel once
-                save_mean[c] = mean;
-                save_invstd[c] = is;
-                if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mean;
-                if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(var * (M > 1.0 ? M / (M - 1.0) : 1.0));
-            }
-        } else {
-            mean = save_mean[c];
-            is = save_invstd[c];
-            k1 = (float)(acc[c] / M);
-            k2 = (float)(acc[C + c] / M);
-            if (row < C && threadIdx.x == 0) {
-                if (dgamma) dgamma[c] = (float)acc[C + c];
-                if (dbeta) dbeta[c] = (float)acc[c];
-            }
-        }
-        const float sc = g * is, sh = b - mean * g * is;
-        const long long bb = row / C;
-        const float *xr = x + bb * xbs + (long long)c * L;
-        const float *dr = MODE == 1 ? dy + bb * obs + (long long)c * L : nullptr;
-        float *orow = out + bb * obs + (long long)c * L;
-        const bool vec = (L & 3) == 0 && (((reinterpret_cast<uintptr_t>(xr) | reinterpret_cast<uintptr_t>(orow)) & 15) == 0) &&
-                         (MODE == 0 || (reinterpret_cast<uintptr_t>(dr) & 15) == 0);
-        if (vec) {
+    const int c = blockIdx.x;
+    const BnCoef k = bn_coef(coef, C);
+    const float ka = k.a[c], kb = k.b[c];
+    float kc = 0, m = 0, is = 1, g = 1, bt = 0;
+    if (MODE == 1) {
+        kc = k.c[c];
+        m = mean[c];
+        is = invstd[c];
+        g = gamma ? gamma[c] : 1.0f;
+        bt = beta ? beta[c] : 0.0f;
+    }
+    const bool vec = (L & 3) == 0 && (xbs & 3) == 0 && (obs & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+                     (MODE == 0 || (reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+    if (vec) {
+        for (int b0 = blockIdx.y; b0 < B; b0 += gridDim.y * BN_UNROLL) {
             for (int l = threadIdx.x * 4; l < L; l += BN_THREADS * 4) {
-                const float4 v = __ldcs(reinterpret_cast<const float4 *>(xr + l));
-                const float xv[4] = {v.x, v.y, v.z, v.w};
-                float o[4];
-                if (MODE == 0) {
+                float4 v[BN_UNROLL], d[BN_UNROLL];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = act_fwd(fmaf(xv[e], sc, sh), slope);
-                } else {
-                    const float4 d = __ldcs(reinterpret_cast<const float4 *>(dr + l));
-                    const float dv[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float xh = (xv[e] - mean) * is;
-                        const float dz = dv[e] * act_grad(xh * g + b, slope);
-                        o[e] = sc * (dz - k1 - xh * k2);
+                for (int u = 0; u < BN_UNROLL; ++u) {
+                    const int b = b0 + u * gridDim.y;
+                    if (b < B) {
+                        v[u] = __ldcs(reinterpret_cast<const float4 *>(x + b * xbs + (long long)c * L + l));
+                        if (MODE == 1) d[u] = __ldcs(reinterpret_cast<const float4 *>(dy + b * obs + (long long)c * L + l));
                     }
                 }
-                *reinterpret_cast<float4 *>(orow + l) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-        } else {
-            for (int l = threadIdx.x; l < L; l += BN_THREADS) {
-                const float xv = xr[l];
-                if (MODE == 0) {
-                    orow[l] = act_fwd(fmaf(xv, sc, sh), slope);
-                } else {
-                    const float xh = (xv - mean) * is;
-                    const float dz = dr[l] * act_grad(xh * g + b, slope);
-                    orow[l] = sc * (dz - k1 - xh * k2);
+#pragma unroll
+                for (int u = 0; u < BN_UNROLL; ++u) {
+                    const int b = b0 + u * gridDim.y;
+                    if (b >= B) break;
+                    const float xv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                    float o[4];
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = act_fwd(fmaf(xv[e], ka, kb), slope);
+                    } else {
+                        const float dv[4] = {d[u].x, d[u].y, d[u].z, d[u].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float xh = (xv[e] - m) * is;
+                            const float dz = dv[e] * act_grad(fmaf(xh, g, bt), slope);
+                            o[e] = kc * (dz - ka - xh * kb);
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(out + b * obs + (long long)c * L + l) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }
+    } else {
+        for (int b = blockIdx.y; b < B; b += gridDim.y)
+            for (int l = threadIdx.x; l < L; l += BN_THREADS) {
+                const float xv = x[b * xbs + (long long)c * L + l];
+                float o;
+                if (MODE == 0) {
+                    o = act_fwd(fmaf(xv, ka, kb), slope);
+                } else {
+                    const float xh = (xv - m) * is;
+                    const float dz = dy[b * obs + (long long)c * L + l] * act_grad(fmaf(xh, g, bt), slope);
+                    o = kc * (dz - ka - xh * kb);
+                }
+                out[b * obs + (long long)c * L + l] = o;
+            }
     }
 }
 
@@ -351,7 +429,30 @@ static int bn_check(const void *x, const void *y, long long R, int C, int L, int
 // with batch strides x_batch_stride for x and y_batch_stride for y / dy / dx (in floats; 0 = C * L: a channel slice of a wider
 // map -- the heads' merged first layer -- is normalised in place of its view).
 // gamma / beta / running_mean / running_var may be NULL; save_mean / save_invstd (C) are written for the backward;
-// acc = 2 C doubles of scratch.
+// acc = mlsp_bn_scratch_bytes(C) bytes of scratch (per-CTA partial sums + the per-channel coefficient block; no zeroing needed).
+// grid of the ROWS kernels / batch residues of the NCL kernels = number of partial-sum rows in the scratch buffer
+static inline int bn_rows_grid(long long R, int C4)
+{
+    const int rpi = mlsp::BN_THREADS / C4;
+    const long long want = (R + (long long)rpi * mlsp::BN_UNROLL - 1) / ((long long)rpi * mlsp::BN_UNROLL);
+    const long long cap = (long long)mlsp::sm_count() * 4 < mlsp::BN_MAX_PARTS ? (long long)mlsp::sm_count() * 4 : mlsp::BN_MAX_PARTS;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+static inline int bn_ncl_gy(int B, int C)
+{
+    int gy = (mlsp::sm_count() * 8 + C - 1) / C;                                 // ~8 CTAs per SM in total
+    const int gy_max = (B + mlsp::BN_UNROLL - 1) / mlsp::BN_UNROLL;
+    gy = gy > gy_max ? gy_max : gy;
+    gy = gy > mlsp::BN_MAX_PARTS ? mlsp::BN_MAX_PARTS : gy;
+    return gy < 1 ? 1 : gy;
+}
+
+// bytes of scratch (`acc`) a call on C channels needs: BN_MAX_PARTS x 2 C doubles of partial sums + 4 C floats of coefficients
+extern "C" size_t mlsp_bn_scratch_bytes(int C)
+{
+    return C > 0 ? sizeof(double) * 2 * (size_t)C * mlsp::BN_MAX_PARTS + sizeof(float) * 4 * (size_t)C : 0;
+}
+
 extern "C" int mlsp_bn_act_fwd(const float *x, float *y, long long R, int C, int L, int layout, long long x_batch_stride,
                                long long y_batch_stride, const float *gamma, const float *beta,
                                float *running_mean, float *running_var, float momentum, float eps, float slope, float *save_mean,
@@ -362,32 +463,33 @@ extern "C" int mlsp_bn_act_fwd(const float *x, float *y, long long R, int C, int
     if (rc) return rc;
     MLSP_REQUIRE(save_mean && save_invstd, MLSP_EINVAL, "bn_act_fwd: null pointer");
     cudaStream_t st = as_stream(stream);
-    MLSP_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)C, st));
-    const int sms = sm_count();
+    const int fin_grid = (C + BN_THREADS / 32 - 1) / (BN_THREADS / 32);
     if (layout == 0) {
-        const int C4 = C / 4, rpi = BN_THREADS / C4;
-        const long long want = (R + rpi - 1) / rpi;
-        const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
-        bn_rows_reduce_kernel<0><<<grid, BN_THREADS, 0, st>>>(reinterpret_cast<const float4 *>(x), nullptr, R, C4, nullptr, nullptr, nullptr,
-                                                            nullptr, slope, acc);
+        const int C4 = C / 4;
+        const int G = bn_rows_grid(R, C4);
+        float *coef = reinterpret_cast<float *>(acc + (size_t)G * 2 * C);
+        bn_rows_reduce_kernel<0><<<G, BN_THREADS, 0, st>>>(reinterpret_cast<const float4 *>(x), nullptr, R, C4, nullptr, nullptr, nullptr,
+                                                         nullptr, slope, acc);
         MLSP_LAUNCH_CHECK("bn_rows_reduce_kernel");
-        const long long tot = R * C4, want2 = (tot + BN_THREADS - 1) / BN_THREADS;
-        const int grid2 = (int)(want2 < (long long)sms * 8 ? want2 : (long long)sms * 8);
-        bn_rows_apply_kernel<<<grid2, BN_THREADS, sizeof(float) * 2 * C, st>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), R, C4,
-                                                                             acc, gamma, beta, eps, momentum, slope, running_mean, running_var,
-                                                                             save_mean, save_invstd);
+        bn_finalize_fwd_kernel<<<fin_grid, BN_THREADS, 0, st>>>(acc, G, coef, C, (double)R, x, 1, gamma, beta, eps, momentum, running_mean,
+                                                              running_var, save_mean, save_invstd);
+        MLSP_LAUNCH_CHECK("bn_finalize_fwd_kernel");
+        bn_rows_apply_kernel<0><<<2 * G, BN_THREADS, 0, st>>>(reinterpret_cast<const float4 *>(x), nullptr, reinterpret_cast<float4 *>(y), R, C4,
+                                                            coef, nullptr, nullptr, nullptr, nullptr, slope);
         MLSP_LAUNCH_CHECK("bn_rows_apply_kernel");
     } else {
         MLSP_REQUIRE(R <= 0x7fffffff, MLSP_EUNSUPPORTED, "bn_act_fwd: B too large");
-        const long long rows = R * C, want = (rows + BN_THREADS / 32 - 1) / (BN_THREADS / 32);
-        const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
         const long long xbs = x_batch_stride ? x_batch_stride : (long long)C * L, obs = y_batch_stride ? y_batch_stride : (long long)C * L;
         MLSP_REQUIRE(xbs >= (long long)C * L && obs >= (long long)C * L, MLSP_EINVAL, "bn_act_fwd: batch stride smaller than C * L");
-        bn_ncl_reduce_kernel<0><<<grid, BN_THREADS, 0, st>>>(x, nullptr, (int)R, C, L, xbs, obs, nullptr, nullptr, nullptr, nullptr, slope, acc);
+        const int B = (int)R, gy = bn_ncl_gy(B, C);
+        float *coef = reinterpret_cast<float *>(acc + (size_t)gy * 2 * C);
+        const dim3 grid(C, gy);
+        bn_ncl_reduce_kernel<0><<<grid, BN_THREADS, 0, st>>>(x, nullptr, B, C, L, xbs, obs, nullptr, nullptr, nullptr, nullptr, slope, acc);
         MLSP_LAUNCH_CHECK("bn_ncl_reduce_kernel");
-        const int grid2 = (int)(rows < (long long)sms * 16 ? rows : (long long)sms * 16);
-        bn_ncl_apply_kernel<0><<<grid2, BN_THREADS, 0, st>>>(x, nullptr, y, (int)R, C, L, xbs, obs, acc, gamma, beta, eps, momentum, slope, running_mean,
-                                                           running_var, save_mean, save_invstd, nullptr, nullptr);
+        bn_finalize_fwd_kernel<<<fin_grid, BN_THREADS, 0, st>>>(acc, gy, coef, C, (double)B * (double)L, x, L, gamma, beta, eps, momentum,
+                                                              running_mean, running_var, save_mean, save_invstd);
+        MLSP_LAUNCH_CHECK("bn_finalize_fwd_kernel");
+        bn_ncl_apply_kernel<0><<<grid, BN_THREADS, 0, st>>>(x, nullptr, y, B, C, L, xbs, obs, coef, nullptr, nullptr, nullptr, nullptr, slope);
         MLSP_LAUNCH_CHECK("bn_ncl_apply_kernel");
     }
     return MLSP_OK;
@@ -405,32 +507,31 @@ extern "C" int mlsp_bn_act_bwd(const float *x, const float *dy, float *dx, long 
     MLSP_REQUIRE(dy && save_mean && save_invstd, MLSP_EINVAL, "bn_act_bwd: null pointer");
     MLSP_REQUIRE(layout == 1 || (reinterpret_cast<uintptr_t>(dy) & 15) == 0, MLSP_EINVAL, "bn_act_bwd: 16-byte alignment");
     cudaStream_t st = as_stream(stream);
-    MLSP_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)C, st));
-    const int sms = sm_count();
+    const int fin_grid = (C + BN_THREADS / 32 - 1) / (BN_THREADS / 32);
     if (layout == 0) {
-        const int C4 = C / 4, rpi = BN_THREADS / C4;
-        const long long want = (R + rpi - 1) / rpi;
-        const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
-        bn_rows_reduce_kernel<1><<<grid, BN_THREADS, 0, st>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(dy), R, C4,
-                                                            save_mean, save_invstd, gamma, beta, slope, acc);
+        const int C4 = C / 4;
+        const int G = bn_rows_grid(R, C4);
+        float *coef = reinterpret_cast<float *>(acc + (size_t)G * 2 * C);
+        bn_rows_reduce_kernel<1><<<G, BN_THREADS, 0, st>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(dy), R, C4,
+                                                         save_mean, save_invstd, gamma, beta, slope, acc);
         MLSP_LAUNCH_CHECK("bn_rows_reduce_kernel");
-        const long long tot = R * C4, want2 = (tot + BN_THREADS - 1) / BN_THREADS;
-        const int grid2 = (int)(want2 < (long long)sms * 8 ? want2 : (long long)sms * 8);
-        bn_rows_bwd_apply_kernel<<<grid2, BN_THREADS, sizeof(float) * 6 * C, st>>>(
-            reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(dy), reinterpret_cast<float4 *>(dx), R, C4, acc, save_mean,
-            save_invstd, gamma, beta, slope, dgamma, dbeta);
-        MLSP_LAUNCH_CHECK("bn_rows_bwd_apply_kernel");
+        bn_finalize_bwd_kernel<<<fin_grid, BN_THREADS, 0, st>>>(acc, G, coef, C, (double)R, gamma, save_invstd, dgamma, dbeta);
+        MLSP_LAUNCH_CHECK("bn_finalize_bwd_kernel");
+        bn_rows_apply_kernel<1><<<2 * G, BN_THREADS, 0, st>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(dy),
+                                                            reinterpret_cast<float4 *>(dx), R, C4, coef, save_mean, save_invstd, gamma, beta, slope);
+        MLSP_LAUNCH_CHECK("bn_rows_apply_kernel");
     } else {
         MLSP_REQUIRE(R <= 0x7fffffff, MLSP_EUNSUPPORTED, "bn_act_bwd: B too large");
-        const long long rows = R * C, want = (rows + BN_THREADS / 32 - 1) / (BN_THREADS / 32);
-        const int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
         const long long xbs = x_batch_stride ? x_batch_stride : (long long)C * L, obs = y_batch_stride ? y_batch_stride : (long long)C * L;
         MLSP_REQUIRE(xbs >= (long long)C * L && obs >= (long long)C * L, MLSP_EINVAL, "bn_act_bwd: batch stride smaller than C * L");
-        bn_ncl_reduce_kernel<1><<<grid, BN_THREADS, 0, st>>>(x, dy, (int)R, C, L, xbs, obs, save_mean, save_invstd, gamma, beta, slope, acc);
+        const int B = (int)R, gy = bn_ncl_gy(B, C);
+        float *coef = reinterpret_cast<float *>(acc + (size_t)gy * 2 * C);
+        const dim3 grid(C, gy);
+        bn_ncl_reduce_kernel<1><<<grid, BN_THREADS, 0, st>>>(x, dy, B, C, L, xbs, obs, save_mean, save_invstd, gamma, beta, slope, acc);
         MLSP_LAUNCH_CHECK("bn_ncl_reduce_kernel");
-        const int grid2 = (int)(rows < (long long)sms * 16 ? rows : (long long)sms * 16);
-        bn_ncl_apply_kernel<1><<<grid2, BN_THREADS, 0, st>>>(x, dy, dx, (int)R, C, L, xbs, obs, acc, gamma, beta, 0.0f, 0.0f, slope, nullptr, nullptr,
-                                                           const_cast<float *>(save_mean), const_cast<float *>(save_invstd), dgamma, dbeta);
+        bn_finalize_bwd_kernel<<<fin_grid, BN_THREADS, 0, st>>>(acc, gy, coef, C, (double)B * (double)L, gamma, save_invstd, dgamma, dbeta);
+        MLSP_LAUNCH_CHECK("bn_finalize_bwd_kernel");
+        bn_ncl_apply_kernel<1><<<grid, BN_THREADS, 0, st>>>(x, dy, dx, B, C, L, xbs, obs, coef, save_mean, save_invstd, gamma, beta, slope);
         MLSP_LAUNCH_CHECK("bn_ncl_apply_kernel");
     }
     return MLSP_OK;
