@@ -1420,6 +1420,8 @@ def main():
                     help="experiment: model stream at high stream priority, target-builder stream at low priority")
     ap.add_argument("--serial-b", action="store_true", help="the deformed-cloud layer + loss graph behind the other layers on the model "
                     "stream (default: beside them on the target stream; measured 0.924 -> 0.899 ms at A, 0.763 -> 0.710 at S)")
+    ap.add_argument("--pdl", type=int, default=-1, help="A/B: mlsp_knn_set_pdl mask (bit 0 centre->prep, 1 prep->filter, 2 filter->ranking; "
+                    "0 = plain stream order; default: the library's)")
     ap.add_argument("--fps-tune", default="", help="experiment: 'G,E' = clouds per FPS CTA (0 auto) and exclusive-SM flag (-1 auto, 0, 1) (mlsp_fps_set_*)")
     ap.add_argument("--no-graphs", action="store_true", help="eager model path (no CUDA-graph capture)")
     ap.add_argument("--step-only", action="store_true",
@@ -1457,6 +1459,9 @@ def main():
         # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
+    if args.pdl >= 0:
+        from mlsp_b200 import _lib as _mlsp_lib
+        _mlsp_lib.load().mlsp_knn_set_pdl(args.pdl)
     if args.fps_tune:
         from mlsp_b200 import _lib as _mlsp_lib
         g_, e_ = (int(v) for v in args.fps_tune.split(","))

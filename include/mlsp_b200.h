@@ -116,6 +116,10 @@ MLSP_API int mlsp_edge_gather_bwd(const float *grad_out, const int64_t *idx, int
  *   stream stays the reference's); centroids (B,npoint) int64; vals (B,3,npoint). */
 MLSP_API int mlsp_fps(const float *xyz, int B, int N, int npoint, const int64_t *start, int64_t *centroids,
              float *vals, void *stream);
+/* Measurement hook (process-wide): 1 (default) = the centre / prep / filter / ranking kernels of the tcgen05 kNN path are chained
+ * with programmatic dependent launch (each starts its independent prologue while the predecessor drains), 0 = plain stream order.
+ * Results do not depend on it. */
+MLSP_API void mlsp_knn_set_pdl(int on);
 /* Tuning hook (process-wide, not thread-safe): clouds per CTA of the FPS kernels -- 0 = automatic (1: packing measured slower on B200,
  * see fps.cu), 1/2/4 = forced where 1024 threads and the shared memory allow.  Results do not depend on it. */
 MLSP_API void mlsp_fps_set_groups(int groups);

@@ -80,7 +80,7 @@ def load() -> ctypes.CDLL:
             fn = getattr(L, name)
             fn.argtypes = argtypes
             fn.restype = _I
-        for hook in ("mlsp_fps_set_groups", "mlsp_fps_set_exclusive"):     # void tuning hooks (include/mlsp_b200.h)
+        for hook in ("mlsp_fps_set_groups", "mlsp_fps_set_exclusive", "mlsp_knn_set_pdl"):     # void tuning hooks (include/mlsp_b200.h)
             getattr(L, hook).argtypes = [_I]
             getattr(L, hook).restype = None
         L.mlsp_version.restype = _I

@@ -236,6 +236,17 @@ __device__ __forceinline__ uint64_t umma_desc_plain(uint32_t saddr, uint32_t lbo
 constexpr uint32_t KT_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((KT_COLS >> 3) << 17) | ((KT_ROWS >> 4) << 24);
 constexpr uint32_t KT_IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((KT_COLS >> 3) << 17) | (((2 * KT_ROWS) >> 4) << 24);   // M = 256
 
+// ------------------------------------------------------------------------------------------- programmatic dependent launch
+// The four kernels of a call (centre -> prep -> filter -> ranking) are chained with programmatic stream serialization: every
+// kernel lets its successor launch as soon as all of its own CTAs have started (pdl_launch_dependents) and the successor runs
+// whatever does not depend on the predecessor -- slab loads, barrier initialisation, tensor-map prefetch -- before pdl_wait,
+// which returns when the predecessor grid has completed and its writes are visible.  A kernel launched without the attribute
+// passes pdl_wait immediately.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// mlsp_knn_set_pdl: bit 0 centre -> prep, bit 1 prep -> filter, bit 2 filter -> ranking; 0 = plain stream order
+static int g_kt_pdl = 3;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------- centre kernel
 // c (B,C) = mean of KT_CEN_SAMPLES points of every cloud, taken at a fixed stride over the cloud (a representative
 // sample whatever the point order).  Any c works for correctness -- distances are translation invariant -- a c inside
@@ -246,6 +257,7 @@ __global__ void __launch_bounds__(256)
 knn_centre_kernel(const float *__restrict__ x, int C, int N, float *__restrict__ cen)
 {
     __shared__ float part[256];
+    pdl_launch_dependents();                               // the prep kernel may start staging its slabs
     const int b = blockIdx.x, t = threadIdx.x;
     const int parts = 256 / C;                             // 2 (C = 128) or 4 (C = 64)
     const int c = t % C, pr = t / C;
@@ -284,17 +296,19 @@ knn_prep_kernel(const float *__restrict__ x, const float *__restrict__ cen, int 
                 float *__restrict__ ss, int *__restrict__ counters, float *__restrict__ xt,
                 __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, uint4 *__restrict__ nb)
 {
+    pdl_launch_dependents();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4) counters[threadIdx.x] = 0;
     extern __shared__ float slab[];                       // [C][PREP_PTS + 1] | cvec [C]
     float *cvec = slab + C * (PREP_PTS + 1);
     const int b = blockIdx.y, n0 = blockIdx.x * PREP_PTS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float *xb = x + (size_t)b * C * N;
-    if ((int)threadIdx.x < C) cvec[threadIdx.x] = cen[(size_t)b * C + threadIdx.x];
-    for (int c = warp; c < C; c += PREP_THREADS / 32) {
+    for (int c = warp; c < C; c += PREP_THREADS / 32) {   // independent of the centre kernel: runs beside it
         const int n = n0 + lane;
         slab[c * (PREP_PTS + 1) + lane] = (n < N) ? xb[(size_t)c * N + n] : 0.0f;
     }
+    pdl_wait();                                           // the centres are complete and visible
+    if ((int)threadIdx.x < C) cvec[threadIdx.x] = cen[(size_t)b * C + threadIdx.x];
     __syncthreads();
     if (warp == 0) {                                       // one point per lane, channels in order
         float s = 0.0f, q = 0.0f;
@@ -541,6 +555,8 @@ knn_tensor_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_const
     }
     if (pair) cluster_sync_all();                                 // the peers' barriers exist before anything signals them
     else __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();                                                   // the prep kernel's operands (hi / lo / norms) are complete
     // From here the TMA producer streams; the MMA warp allocates TMEM and the epilogue warps build the constant operand
     // and reduce the cloud's norms meanwhile; those 17 warps meet at setup_bar_sync.
     if (warp == 1) {
@@ -1152,6 +1168,7 @@ knn_refine_kernel(KtParams P, long long total_rows)
     constexpr int KS = SLOTS / 2;                          // slots holding the k ranked neighbours (k <= 32 / 64)
     constexpr int SW = 4 * KT_MAX_TILES / 4;               // snapshot words per row, at most
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();                                                        // the filter's candidate lists are complete
     const long long row64 = (long long)blockIdx.x * RF_WARPS + warp;   // b*N + i
     if (row64 >= total_rows) return;
     const uint32_t row = (uint32_t)row64;                              // B*N < 2^31 (knn_tensor_supported)
@@ -1349,8 +1366,17 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     if (stages_mask & 1) {
         knn_centre_kernel<<<B, 256, 0, st>>>(x, C, N, cen);
         MLSP_LAUNCH_CHECK("knn_centre_kernel");
-        knn_prep_kernel<<<dim3((N + PREP_PTS - 1) / PREP_PTS, B), PREP_THREADS, sizeof(float) * (C * (PREP_PTS + 1) + C), st>>>(
-            x, cen, C, N, xx, yy, ss, counters, xt, hi, lo, nb);
+        cudaLaunchConfig_t pcfg = {};
+        pcfg.gridDim = dim3((N + PREP_PTS - 1) / PREP_PTS, B);
+        pcfg.blockDim = dim3(PREP_THREADS);
+        pcfg.dynamicSmemBytes = sizeof(float) * (C * (PREP_PTS + 1) + C);
+        pcfg.stream = st;
+        cudaLaunchAttribute pattr[1];
+        pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pattr[0].val.programmaticStreamSerializationAllowed = 1;
+        pcfg.attrs = pattr;
+        pcfg.numAttrs = (g_kt_pdl & 1) ? 1 : 0;
+        MLSP_CUDA(cudaLaunchKernelEx(&pcfg, knn_prep_kernel, x, (const float *)cen, C, N, xx, yy, ss, counters, xt, hi, lo, nb));
         MLSP_LAUNCH_CHECK("knn_prep_kernel");
     }
 
@@ -1389,13 +1415,15 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
         cfg.blockDim = dim3(KT_THREADS);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)cs;
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = (g_kt_pdl & 2) ? 2 : 1;
 #define MLSP_KT_LAUNCH(NGT_, PAIR_)                                                                                              \
     do {                                                                                                                         \
         MLSP_CUDA(cudaFuncSetAttribute(knn_tensor_kernel<NGT_, PAIR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -1411,17 +1439,31 @@ int knn_tensor_run(const float *x, int B, int C, int N, int k, int64_t *idx, voi
     if (stages_mask & 4) {
         const long long rows_total = (long long)B * N;
         const unsigned rblocks = (unsigned)((rows_total + RF_WARPS - 1) / RF_WARPS);
+        cudaLaunchConfig_t rcfg = {};
+        rcfg.gridDim = dim3(rblocks);
+        rcfg.blockDim = dim3(32 * RF_WARPS);
+        rcfg.stream = st;
+        cudaLaunchAttribute rattr[1];
+        rattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        rattr[0].val.programmaticStreamSerializationAllowed = 1;
+        rcfg.attrs = rattr;
+        rcfg.numAttrs = (g_kt_pdl & 4) ? 1 : 0;
         if (k <= 32 && C == 64)
-            knn_refine_kernel<128, 64><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+            MLSP_CUDA(cudaLaunchKernelEx(&rcfg, knn_refine_kernel<128, 64>, P, rows_total));
         else if (k <= 32)
-            knn_refine_kernel<128, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+            MLSP_CUDA(cudaLaunchKernelEx(&rcfg, knn_refine_kernel<128, 128>, P, rows_total));
         else if (C == 64)
-            knn_refine_kernel<192, 64><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+            MLSP_CUDA(cudaLaunchKernelEx(&rcfg, knn_refine_kernel<192, 64>, P, rows_total));
         else
-            knn_refine_kernel<192, 128><<<rblocks, 32 * RF_WARPS, 0, st>>>(P, rows_total);
+            MLSP_CUDA(cudaLaunchKernelEx(&rcfg, knn_refine_kernel<192, 128>, P, rows_total));
         MLSP_LAUNCH_CHECK("knn_refine_kernel");
     }
     return MLSP_OK;
 }
 
 }  // namespace mlsp
+
+// Measurement hook (process-wide): 1 (default) = the four kernels of the tcgen05 kNN path are chained with programmatic
+// dependent launch, 0 = plain stream order.  Results do not depend on it.
+extern "C" void mlsp_knn_set_pdl(int on) { mlsp::g_kt_pdl = on; }
+

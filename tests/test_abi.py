@@ -39,7 +39,7 @@ def test_ctypes_signatures_cover_header(lib):
     from mlsp_b200 import _lib
     compute = [s for s in declared_symbols() if s not in ("mlsp_version", "mlsp_last_error", "mlsp_workspace_bytes",
                                                           "mlsp_fps_set_groups", "mlsp_fps_set_exclusive",        # void tuning hooks
-                                                          "mlsp_bn_scratch_bytes")]
+                                                          "mlsp_bn_scratch_bytes", "mlsp_knn_set_pdl")]
     assert sorted(compute) == sorted(_lib.SIGNATURES)
 
 
