@@ -23,6 +23,13 @@ pred = (pts + 0.05 * torch.randn(B, N, 3, device=dev)).contiguous()
 start = (torch.arange(B) * 7 % N).to(dev)
 
 
+from mlsp_b200 import bn as mbn  # noqa: E402
+bn_cases = [(torch.randn(B, N, k, 128, device=dev).permute(0, 3, 1, 2), torch.nn.BatchNorm2d(128).to(dev).train()),
+            (torch.randn(B, 1024, N, device=dev), torch.nn.BatchNorm1d(1024).to(dev).train())]
+clouds_s = synth.surface_clouds(16, 2048, 77).to(dev)
+start_s = (torch.arange(16) * 7 % 2048).to(dev)
+
+
 def one_pass():
     np.random.seed(1)
     for C, f in feats.items():                                   # the DGCNN call: knn + gather fused, then its backward
@@ -38,6 +45,13 @@ def one_pass():
     M.reconstruction_loss(p, clouds, mask).backward()
     M.knn(feats[64], k)                                          # the ranking kernels without the fused gather, for reference
     M.get_graph_feature(feats[64], None, k=k, idx=M.knn(feats[64], k))   # explicit-idx gather (edge_fwd_vec_kernel)
+    # late round 2: BatchNorm + LeakyReLU pass pairs on the training step's largest maps (rows and (B,C,L) layouts), FPS at the
+    # PointSegDA shape (SM reserved, two clouds per CTA), kNN with k > 64 (two rounds of the exact kernel)
+    for xb, mod in bn_cases:
+        xin = xb.detach().requires_grad_(True)
+        mbn.bn_act(xin, mod, 0.2).backward(xb)
+    M.fps_from_start(clouds_s, 1024, start_s)
+    M.knn(feats[64][:4].contiguous(), 100)
 
 
 one_pass()
