@@ -40,7 +40,7 @@ struct BnCoef {        // per-channel coefficient block (4 C floats) in the scra
 };
 __host__ __device__ __forceinline__ BnCoef bn_coef(float *f, int C) { return BnCoef{f, f + C, f + 2 * C, f + 3 * C}; }
 
-// No atomics and no zeroing: every CTA of a reduction writes its partial sums to part[cta][2 C] (fp64) and the finalize kernel
+// No atomics and no zeroing: every CTA of a reduction writes its partial sums to part[2 C][cta] (fp64) and the finalize kernel
 // adds the G partials of a channel with one warp (deterministic; with atomicAdd(double) onto 2 C addresses from 1184 CTAs the
 // reduction pass ran at 44 % of the HBM peak, ncu).
 constexpr int BN_MAX_PARTS = 592;                         // 4 CTAs per SM on 148 SMs
@@ -122,12 +122,11 @@ bn_rows_reduce_kernel(const float4 *__restrict__ x, const float4 *__restrict__ d
                 s[e] += red[o * C4 + q][e];
                 t[e] += red[o * C4 + q][4 + e];
             }
-        const int C = 4 * C4;
-        double *part = acc + (size_t)blockIdx.x * 2 * C;
+        const int C = 4 * C4, G = gridDim.x;                 // part[stat][channel][cta]: the finalize warp reads a channel's row coalesced
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            part[4 * q + e] = s[e];
-            part[C + 4 * q + e] = t[e];
+            acc[(size_t)(4 * q + e) * G + blockIdx.x] = s[e];
+            acc[(size_t)(C + 4 * q + e) * G + blockIdx.x] = t[e];
         }
     }
 }
@@ -139,9 +138,10 @@ __device__ __forceinline__ void bn_sum_parts(const double *__restrict__ part, in
 {
     s = 0.0;
     t = 0.0;
+    const double *ps = part + (size_t)c * G, *pt = part + (size_t)(C + c) * G;
     for (int g = threadIdx.x & 31; g < G; g += 32) {
-        s += part[(size_t)g * 2 * C + c];
-        t += part[(size_t)g * 2 * C + C + c];
+        s += ps[g];
+        t += pt[g];
     }
     s = warp_sum_d(s);
     t = warp_sum_d(t);
@@ -333,9 +333,9 @@ bn_ncl_reduce_kernel(const float *__restrict__ x, const float *__restrict__ dy, 
             s += red[0][w];
             t += red[1][w];
         }
-        double *part = acc + (size_t)blockIdx.y * 2 * C;
-        part[c] = s;
-        part[C + c] = t;
+        const int G = gridDim.y;
+        acc[(size_t)c * G + blockIdx.y] = s;
+        acc[(size_t)(C + c) * G + blockIdx.y] = t;
     }
 }
 
