@@ -53,6 +53,9 @@ def main():
         "knn_q64": (synth.features(2, 64, 96, 13, quantised=True), 20),
         "knn_c64": (synth.smooth_features(2, 64, 96, 14), 20),
         "knn_c128_k40": (synth.smooth_features(1, 128, 128, 15), 40),
+        # k > 64 (the reference's args.k is a free flag): rounds of the exact kernel
+        "knn_q3_k100": (synth.clouds(1, 200, 16, quantised=True), 100),
+        "knn_c16_k130": (synth.smooth_features(1, 16, 160, 17), 130),
     }
     for name, (x, k) in cases.items():
         idx = seg.knn(x, k)

@@ -41,7 +41,7 @@ def _np(t):
 
 
 # ------------------------------------------------------------------------------------------------ a1
-@pytest.mark.parametrize("name", ["knn_q3", "knn_q64"])
+@pytest.mark.parametrize("name", ["knn_q3", "knn_q64", "knn_q3_k100"])
 def test_knn_golden_quantised(golden, dev, name):
     g = golden(name)
     k = int(g["k"])
@@ -50,7 +50,7 @@ def test_knn_golden_quantised(golden, dev, name):
     assert np.array_equal(idx, stable)
 
 
-@pytest.mark.parametrize("name", ["knn_c3", "knn_c64", "knn_c128_k40"])
+@pytest.mark.parametrize("name", ["knn_c3", "knn_c64", "knn_c128_k40", "knn_c16_k130"])
 def test_knn_golden_continuous(golden, dev, orc, name):
     g = golden(name)
     k = int(g["k"])

@@ -9,7 +9,7 @@ from oracle import np_ops
 from conftest import knn_rank_check
 
 
-@pytest.mark.parametrize("name", ["knn_q3", "knn_q64"])
+@pytest.mark.parametrize("name", ["knn_q3", "knn_q64", "knn_q3_k100"])
 def test_knn_quantised_exact(golden, name):
     """Grid-quantised inputs: every fp32 evaluation order agrees, ties are real -> strict equality with
     the stable (lowest-index) ranking of the reference's pd matrix, and value-wise equality with topk."""
@@ -25,7 +25,7 @@ def test_knn_quantised_exact(golden, name):
     assert (np.take_along_axis(pd, idx[:, :, :1], 2)[..., 0] == pd.max(axis=2)).all()
 
 
-@pytest.mark.parametrize("name", ["knn_c3", "knn_c64", "knn_c128_k40"])
+@pytest.mark.parametrize("name", ["knn_c3", "knn_c64", "knn_c128_k40", "knn_c16_k130"])
 def test_knn_continuous_certified(golden, name):
     g = golden(name)
     x, k = g["x"], int(g["k"])
