@@ -1404,7 +1404,19 @@ def extra_knn_X(device, steps=4):
     return {"workload": "knn-X 256x4096 k=40 (BASELINE configs[4]; `bench.py --workload X` is the full line)", **out}
 
 
+def protect_stdout():
+    """stdout carries exactly ONE JSON line (the driver parses it).  Libraries print there too -- NCCL's `NCCL version ...` banner
+    goes to the C-level stdout whatever NCCL_DEBUG_FILE says -- so file descriptor 1 is pointed at stderr for everything written
+    below Python, and Python's own sys.stdout (what print() uses) keeps the original stream."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w")
+
+
 def main():
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

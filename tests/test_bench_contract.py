@@ -91,3 +91,17 @@ def test_workload_e_reference_arm_line(bench):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "E", "--impl", "reference", "--gpus", "2",
                         "--steps", "1", "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_stdout_is_protected_from_library_prints():
+    """bench.protect_stdout(): bytes written to file descriptor 1 below Python (NCCL's version banner) land on stderr, print()
+    still reaches the real stdout -- a multi-GPU run prints exactly one JSON line there."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.protect_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('{\\\"metric\\\": 1}', flush=True)") % root
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() == '{"metric": 1}', r.stdout
+    assert "NCCL version" in r.stderr
